@@ -1,0 +1,87 @@
+"""Parity case table shared by the golden generator, the oracle pin tests and the GPU parity tests.
+
+Each case names a seeded synthetic fixture, the reference command line that produced the committed golden text
+(tests/golden/<name>.txt, made by tests/golden/make_goldens.py with the UNMODIFIED reference binary), and the
+equivalent analysis / parameter / printer settings of the C ABI (include/popbam_b200.h).
+"""
+from pbtest import AN, FLAG
+
+# fixtures (pbsynth parameters); kept small so that the reference needs ~1-2 s per command
+FIXTURES = {
+    # SURVEY §8(d) C1-shaped, cut down: 10 ingroup + outgroup, 20x, 3 windows of 10 kb
+    "c1": dict(contig_len=30500, n_ingroup=10, has_outgroup=1, depth=20.0, snp_density=0.01, seed=11),
+    # edge cases: flagged reads, N bases, =/X/H/P/N cigar ops, lower-case / N reference, low-coverage hole
+    "edge": dict(contig_len=20500, n_ingroup=6, has_outgroup=1, depth=14.0, snp_density=0.02, het_frac=0.3,
+                 edge_mode=1, seed=12),
+    # two read groups per sample, no outgroup, odd read length (seq4 padding)
+    "rg2": dict(contig_len=20500, n_ingroup=5, has_outgroup=0, rg_per_sample=2, depth=9.0, read_len=75,
+                snp_density=0.015, seed=13),
+    # dense SNPs, more samples: LD stress (C3-shaped, cut down)
+    "ld": dict(contig_len=20500, n_ingroup=23, has_outgroup=1, depth=12.0, snp_density=0.04, seed=14),
+}
+
+
+def _b(v):
+    """-a/-b are parsed into unsigned char: pass the byte whose value is the threshold."""
+    return chr(v)
+
+
+# name, fixture, reference argv (before "-f ref.fa ... bam region"), analysis, params kw, print kw
+CASES = [
+    ("nucdiv_c1", "c1", ["nucdiv", "-w", "10"], "NUCDIV", {}, {}),
+    ("sfs_c1_og", "c1", ["sfs", "-w", "10", "-p", "og"], "SFS", dict(flags=FLAG["OUTGROUP"], outidx=10), {}),
+    ("sfs_c1", "c1", ["sfs", "-w", "10"], "SFS", {}, {}),
+    ("ld0_c1", "c1", ["ld", "-w", "10", "-o", "0"], "LD_ZNS", {}, {}),
+    ("ld1_c1", "c1", ["ld", "-w", "10", "-o", "1"], "LD_OMEGA", {}, {}),
+    ("ld2_c1", "c1", ["ld", "-w", "10", "-o", "2"], "LD_WALL", {}, {}),
+    ("ld0e_c1", "c1", ["ld", "-w", "10", "-o", "0", "-e"], "LD_ZNS", dict(min_freq=2), {}),
+    ("div0_c1", "c1", ["diverge", "-w", "10", "-o", "0"], "DIVERGE_IND", {}, {}),
+    ("div0jc_c1", "c1", ["diverge", "-w", "10", "-o", "0", "-d", "jc"], "DIVERGE_IND", {}, dict(jc=1)),
+    ("div1_c1_og", "c1", ["diverge", "-w", "10", "-o", "1", "-p", "og"], "DIVERGE_POP",
+     dict(flags=FLAG["OUTGROUP"], outidx=10), {}),
+    ("div1t_c1", "c1", ["diverge", "-w", "10", "-o", "1", "-t"], "DIVERGE_POP", dict(flags=FLAG["SUBSTITUTE"]), {}),
+    ("hap0_c1", "c1", ["haplo", "-w", "10", "-o", "0"], "HAPLO_K", {}, {}),
+    ("hap1_c1", "c1", ["haplo", "-w", "10", "-o", "1"], "HAPLO_EHHS", {}, {}),
+    ("hap2_c1", "c1", ["haplo", "-w", "10", "-o", "2"], "HAPLO_DXY", {}, {}),
+    ("snp0_c1", "c1", ["snp", "-o", "0"], "SNP", {}, dict(snp_output=0)),
+    ("snp1_c1_og", "c1", ["snp", "-o", "1", "-p", "og"], "SNP", dict(flags=FLAG["OUTGROUP"], outidx=10),
+     dict(snp_output=1)),
+    ("snp2_c1", "c1", ["snp", "-o", "2", "-w", "10"], "SNP", {}, dict(snp_output=2)),
+    # thresholds / option semantics (SURVEY Appendix D "option semantics")
+    ("snp0_c1_x12", "c1", ["snp", "-o", "0", "-x", "12"], "SNP", dict(max_depth=12), dict(snp_output=0)),
+    ("snp0_c1_ab", "c1", ["snp", "-o", "0", "-a", _b(30), "-b", _b(21)], "SNP", dict(min_mapQ=30, min_baseQ=21),
+     dict(snp_output=0)),
+    ("snp0_c1_qs", "c1", ["snp", "-o", "0", "-q", "40", "-s", "15", "-m", "5"], "SNP",
+     dict(min_rmsQ=40, min_snpQ=15, min_depth=5), dict(snp_output=0)),
+    ("snp0_c1_z", "c1", ["snp", "-o", "0", "-z"], "SNP", dict(flags=FLAG["HETEROZYGOTE"]), dict(snp_output=0)),
+    ("snp0_c1_i", "c1", ["snp", "-o", "0", "-i", "-b", _b(4)], "SNP", dict(flags=FLAG["ILLUMINA"], min_baseQ=4),
+     dict(snp_output=0)),
+    ("nucdiv_c1_k", "c1", ["nucdiv", "-w", "10", "-k", "9900"], "NUCDIV", {}, dict(min_sites=9900)),
+    ("nucdiv_c1_now", "c1", ["nucdiv"], "NUCDIV", {}, {}),
+    # edge fixture
+    ("snp0_edge", "edge", ["snp", "-o", "0"], "SNP", {}, dict(snp_output=0)),
+    ("nucdiv_edge", "edge", ["nucdiv", "-w", "10"], "NUCDIV", {}, {}),
+    ("sfs_edge_og", "edge", ["sfs", "-w", "10", "-p", "og"], "SFS", dict(flags=FLAG["OUTGROUP"], outidx=6), {}),
+    ("hap0_edge", "edge", ["haplo", "-w", "10", "-o", "0"], "HAPLO_K", {}, {}),
+    ("hap1_edge", "edge", ["haplo", "-w", "10", "-o", "1"], "HAPLO_EHHS", {}, {}),
+    ("snp0_edge_x9", "edge", ["snp", "-o", "0", "-x", "9"], "SNP", dict(max_depth=9), dict(snp_output=0)),
+    # two read groups per sample
+    ("snp0_rg2", "rg2", ["snp", "-o", "0"], "SNP", {}, dict(snp_output=0)),
+    ("nucdiv_rg2", "rg2", ["nucdiv", "-w", "10"], "NUCDIV", {}, {}),
+    ("ld2_rg2", "rg2", ["ld", "-w", "10", "-o", "2"], "LD_WALL", {}, {}),
+    # LD fixture
+    ("ld0_ld", "ld", ["ld", "-w", "10", "-o", "0"], "LD_ZNS", {}, {}),
+    ("ld1_ld", "ld", ["ld", "-w", "10", "-o", "1"], "LD_OMEGA", {}, {}),
+    ("ld2_ld", "ld", ["ld", "-w", "10", "-o", "2"], "LD_WALL", {}, {}),
+    ("hap1_ld", "ld", ["haplo", "-w", "10", "-o", "1"], "HAPLO_EHHS", {}, {}),
+    ("sfs_ld_og", "ld", ["sfs", "-w", "10", "-p", "og"], "SFS", dict(flags=FLAG["OUTGROUP"], outidx=23), {}),
+]
+
+
+def win_kb(argv):
+    """Window size in bp from a reference argv (-w is in kb, pop_nucdiv.cpp:321); 0 when absent."""
+    return int(argv[argv.index("-w") + 1]) * 1000 if "-w" in argv else 0
+
+
+def analysis_bit(name):
+    return AN[name]

@@ -335,3 +335,61 @@ def run_ref(args, cwd=None):
     if r.returncode != 0:
         raise RuntimeError("reference popbam failed (%d): %s" % (r.returncode, r.stderr.decode()[-2000:]))
     return r.stdout.decode()
+
+
+# ---------------------------------------------------------------------------------------------
+# parity-case helpers (tests/cases.py)
+_fixture_cache = {}
+
+
+def fixture(name):
+    from cases import FIXTURES
+    if name not in _fixture_cache:
+        _fixture_cache[name] = Fixture(**FIXTURES[name])
+    return _fixture_cache[name]
+
+
+def ms_header(fx, n_windows):
+    """print_ms_header (pop_snp.cpp:305-317)."""
+    s = "ms %d %d -t 5.0 " % (fx.n_samples, n_windows)
+    if fx.n_pops > 1:
+        cnt = [fx.sample_pop.count(p) for p in range(fx.n_pops)]
+        s += "-I %d %s " % (fx.n_pops, " ".join(str(c) for c in cnt))
+    return s + "\n1350154902\n\n"
+
+
+def case_setup(case):
+    """(fixture, params, analysis bit, window arrays, print opts) of one tests/cases.py row."""
+    from cases import win_kb
+    name, fxname, argv, an, pkw, okw = case
+    fx = fixture(fxname)
+    p = fx.params(**pkw)
+    wb, we = window_grid(0, fx.contig_len, win_kb(argv))
+    o = fx.print_opts(**okw)
+    return fx, p, AN[an], wb, we, o
+
+
+def golden_text(case):
+    return (GOLDEN / (case[0] + ".txt")).read_text()
+
+
+def texts_equal(got, want, snp0=False):
+    """Exact text comparison.  For `snp -o 0` rows the base letter of a sample whose genotype byte is out of range
+    is undefined in the reference (iupac[] read out of bounds): the restatement prints '?' there and
+    that one character is excluded; every other field must match."""
+    if not snp0:
+        return got == want, "text differs"
+    gl, wl = got.splitlines(), want.splitlines()
+    if len(gl) != len(wl):
+        return False, "row count %d != %d" % (len(gl), len(wl))
+    for i, (a, b) in enumerate(zip(gl, wl)):
+        fa, fb = a.split("\t"), b.split("\t")
+        if len(fa) != len(fb):
+            return False, "row %d: field count" % i
+        for j, (x, y) in enumerate(zip(fa, fb)):
+            if x == y:
+                continue
+            if j >= 3 and (j - 3) % 4 == 0 and x == "?":
+                continue
+            return False, "row %d field %d: %r != %r" % (i, j, x, y)
+    return True, ""
