@@ -164,7 +164,7 @@ typedef struct pb_region_result {
     int32_t  span_beg, span_end;
     const uint64_t *cb;           /* [(span_end-span_beg)*n]                               */
     const uint64_t *site_type;    /* [span_end-span_beg]                                   */
-    const uint8_t  *site_flag;    /* bit0 used (all samples covered), bit1 fq>0, bit2 live */
+    const uint8_t  *site_flag;    /* bit0 used (in a window, all samples covered), bit1 fq>0 */
     /* work counters */
     int64_t  reads_pushed;        /* records received                                      */
     int64_t  reads_used;          /* after the 0x704 / tid / empty-cigar filter            */
@@ -193,7 +193,8 @@ int pb_region_begin(pb_ctx *ctx, uint32_t analyses, int32_t n_windows,
                     const int32_t *win_beg, const int32_t *win_end);
 
 /* replaces: bam_fetch(...fetch_func) -> bam_plbuf_push(b, buf) (pop_utils.cpp:500-508).
- * May be called several times per region; batches are concatenated in call order.         */
+ * May be called several times per region; batches are concatenated in call order.  The
+ * arrays are copied to the device before the call returns (use pinned memory for speed).  */
 int pb_push_batch(pb_ctx *ctx, const pb_read_batch *batch);
 
 /* bam_fetch_f-shaped shim (bam.h:618): `b` points at a raw BAM record laid out as bam1_t's
@@ -215,6 +216,10 @@ int pb_region_wait(pb_ctx *ctx, pb_region_result *out);
 int pb_region_relaunch(pb_ctx *ctx);
 void *pb_stream(pb_ctx *ctx);                   /* cudaStream_t the kernels run on        */
 int64_t pb_kernel_launches(const pb_ctx *ctx);  /* kernels launched since pb_create       */
+/* CUDA-event durations (ms) of the last region's stages, valid after pb_region_wait:
+ * [0] per-read preparation + sample partition, [1] the pileup/call/site kernel,
+ * [2] window compaction, [3] window statistics.                                            */
+int pb_stage_times(const pb_ctx *ctx, double *ms4);
 
 /* ---- helpers that mirror small reference routines ------------------------------------- */
 /* window grid of every main_X (pop_nucdiv.cpp:48-78).  win_size==0: one window

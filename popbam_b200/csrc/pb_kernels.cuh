@@ -1,0 +1,513 @@
+// pb_kernels.cuh -- sm_100a kernels of the pileup -> consensus call -> per-site path.
+//
+//   k_rebase          batch-relative offsets -> absolute device offsets        (per read)
+//   k_read_prep       bam_plp_push filter + bam_calend                         (per read)
+//   k_qual_mask       which base qualities occur                               (per base, streaming)
+//   k_level_table     distinct error-model quality levels of the region
+//   k_part_count / k_part_scatter   stable partition of the reads by sample (file order kept)
+//   k_pileup_call     CIGAR-expanding pileup, per-(site,sample) call, per-site logic (the hot kernel)
+//   k_window_sites    order-preserving compaction into num_sites / segregating-site lists
+//   k_scan_*          exclusive scans
+//
+// Reference code these replace: bam_plbuf_push/bam_plp_push/bam_plp_next/resolve_cigar2
+// (bam_pileup.c:523,365,283,90), popbamData::call_base (popbam.cpp:186-313), errmod_cal/gl2cns
+// (pop_utils.cpp:280-365, :66-100), clean_heterozygotes/segbase/qfilter (pop_utils.cpp:170-201,
+// :122-168, :102-120), make_nucdiv and its five clones (pop_nucdiv.cpp:136-204).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pb_cell.cuh"
+#include "pb_walk.cuh"
+
+#define PB_REC_SIMPLE 0x200u      // single M/=/X op: qpos = p - pos
+#define PB_REC_CAP 512            // read records staged per chunk in the hot kernel
+#define PB_PART_CHUNK 2048        // reads per warp in the sample partition
+#define PB_KEY_DROP 0xffu
+
+struct PbCounters {               // device-side region counters (one cudaMemcpy back)
+    unsigned long long reads_used;
+    unsigned long long aligned_bases;
+    unsigned long long mapq_mask;     // bit min(mapq,63) for kept reads passing min_mapQ
+    unsigned long long qual_mask;     // bit min(baseQ',63) for base qualities passing min_baseQ
+    int max_span;                     // max reference span of a kept read
+    int unsorted;                     // pos[r] < pos[r-1] seen (bam_pileup.c:384-395)
+    int n_levels;
+    int bad_sample;
+    unsigned char qrank[64];          // quality value -> level
+    unsigned char qval[64];           // level -> quality value (ascending)
+};
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_rebase(int64_t n, int64_t r0, const uint32_t *__restrict__ cig_off, const uint32_t *__restrict__ base_off,
+                         uint64_t cig_base, uint64_t byte_base, uint32_t *__restrict__ cigstart, uint32_t *__restrict__ ncig,
+                         uint64_t *__restrict__ base) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    cigstart[r0 + i] = (uint32_t)(cig_base + cig_off[i]);
+    ncig[r0 + i] = cig_off[i + 1] - cig_off[i];
+    base[r0 + i] = byte_base + base_off[i];
+}
+
+// bam_plp_push (bam_pileup.c:371-374): drop flag & 0x704; bam_calend (bam.c:20-70): reference end.
+__global__ void k_read_prep(int64_t n, const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta,
+                            const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
+                            const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ, int32_t *__restrict__ rend,
+                            uint8_t *__restrict__ rkey, uint8_t *__restrict__ rsimple, PbCounters *__restrict__ ctr) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long used = 0, aligned = 0, mqmask = 0;
+    int span = 0, unsorted = 0;
+    if (r < n) {
+        const uint32_t m = meta[r];
+        const int p = pos[r];
+        const uint32_t c0 = cigstart[r], nc = ncig[r];
+        int x = p, al = 0;
+        for (uint32_t i = 0; i < nc; ++i) {
+            const uint32_t c = __ldg(cigar + c0 + i);
+            const int op = c & 15, len = (int)(c >> 4);
+            if (op == 0 || op == 7 || op == 8) { x += len; al += len; }
+            else if (op == 2 || op == 3) x += len;
+        }
+        const bool keep = !((m >> 16) & 0x704u) && x > p;
+        rend[r] = x;
+        const uint32_t smp = m & 0xffu;
+        rkey[r] = (keep && smp < (uint32_t)n_samples) ? (uint8_t)smp : (uint8_t)PB_KEY_DROP;
+        const uint32_t op0 = nc == 1 ? (__ldg(cigar + c0) & 15u) : 1u;
+        rsimple[r] = (nc == 1 && (op0 == 0 || op0 == 7 || op0 == 8)) ? 1 : 0;
+        if (keep) {
+            used = 1; aligned = (unsigned long long)al; span = x - p;
+            const int mq = (int)((m >> 8) & 0xff);
+            if (mq >= min_mapQ) mqmask = 1ULL << (mq > 63 ? 63 : mq);
+        }
+        if (r > 0 && p < pos[r - 1]) unsorted = 1;
+    }
+    // warp-aggregate, then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        used += __shfl_xor_sync(0xffffffffu, used, o);
+        aligned += __shfl_xor_sync(0xffffffffu, aligned, o);
+        mqmask |= __shfl_xor_sync(0xffffffffu, mqmask, o);
+        span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
+        unsorted |= __shfl_xor_sync(0xffffffffu, unsorted, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (used) atomicAdd(&ctr->reads_used, used);
+        if (aligned) atomicAdd(&ctr->aligned_bases, aligned);
+        if (mqmask) atomicOr(&ctr->mapq_mask, mqmask);
+        if (span) atomicMax(&ctr->max_span, span);
+        if (unsorted) atomicOr(&ctr->unsorted, 1);
+    }
+}
+
+// Which (adjusted) base qualities >= min_baseQ occur anywhere in the batch (superset of what the
+// pileup will use: clipped / inserted / padding bytes are included, harmlessly).
+__global__ void k_qual_mask(const uint8_t *__restrict__ qual, int64_t n_bytes, int illumina, int min_baseQ,
+                            PbCounters *__restrict__ ctr) {
+    unsigned long long mask = 0;
+    const int64_t nvec = n_bytes >> 4;
+    const uint4 *q4 = reinterpret_cast<const uint4 *>(qual);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 v = __ldg(q4 + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int q = (int)((w[j] >> (8 * b)) & 0xff);
+                if (illumina) q = q > 31 ? q - 31 : 0;
+                if (q >= min_baseQ) mask |= 1ULL << (q > 63 ? 63 : q);
+            }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int64_t i = nvec << 4; i < n_bytes; ++i) {
+            int q = qual[i];
+            if (illumina) q = q > 31 ? q - 31 : 0;
+            if (q >= min_baseQ) mask |= 1ULL << (q > 63 ? 63 : q);
+        }
+    for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+    if ((threadIdx.x & 31) == 0 && mask) atomicOr(&ctr->qual_mask, mask);
+}
+
+// Distinct values of clamp(min(baseQ, mapQ), 4, 63) (popbam.cpp:279-283) that can occur.
+__global__ void k_level_table(PbCounters *ctr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const unsigned long long A = ctr->qual_mask, B = ctr->mapq_mask;
+    unsigned long long L = 0;
+    for (int a = 0; a < 64; ++a) {
+        if (!(A >> a & 1)) continue;
+        for (int b = 0; b < 64; ++b) {
+            if (!(B >> b & 1)) continue;
+            int q = a < b ? a : b;
+            if (q < 4) q = 4;
+            L |= 1ULL << q;
+        }
+    }
+    int nl = 0;
+    for (int q = 0; q < 64; ++q) {
+        ctr->qrank[q] = (unsigned char)nl;
+        if (L >> q & 1) ctr->qval[nl++] = (unsigned char)q;
+    }
+    ctr->n_levels = nl;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stable partition of the kept reads by sample.  One warp owns PB_PART_CHUNK consecutive reads, so
+// the order inside a (chunk, sample) bucket is file order; buckets are laid out sample-major,
+// chunk-minor by an exclusive scan of the count matrix.
+__global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, int n_samples, int64_t n_chunks,
+                             uint32_t *__restrict__ counts /* [n_samples][n_chunks] */) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk >= n_chunks) return;
+    uint32_t c0 = 0, c1 = 0;   // lane owns samples lane and lane+32
+    const int64_t r0 = chunk * PB_PART_CHUNK;
+    for (int i = 0; i < PB_PART_CHUNK; i += 32) {
+        const int64_t r = r0 + i + lane;
+        const uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
+        // every lane counts the keys equal to its own two samples
+        for (int src = 0; src < 32; ++src) {
+            const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
+            c0 += kk == (uint32_t)lane;
+            c1 += kk == (uint32_t)(lane + 32);
+        }
+    }
+    if (lane < n_samples) counts[(int64_t)lane * n_chunks + chunk] = c0;
+    if (lane + 32 < n_samples) counts[(int64_t)(lane + 32) * n_chunks + chunk] = c1;
+}
+
+__global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, int n_samples, int64_t n_chunks,
+                               const uint32_t *__restrict__ offs /* scanned counts */, const int32_t *__restrict__ pos,
+                               const int32_t *__restrict__ rend, const uint32_t *__restrict__ meta,
+                               const uint64_t *__restrict__ base, const uint8_t *__restrict__ rsimple,
+                               int4 *__restrict__ srec, uint32_t *__restrict__ sorig) {
+    const int lane = threadIdx.x & 31;
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk >= n_chunks) return;
+    uint32_t cur0 = lane < n_samples ? offs[(int64_t)lane * n_chunks + chunk] : 0;
+    uint32_t cur1 = lane + 32 < n_samples ? offs[(int64_t)(lane + 32) * n_chunks + chunk] : 0;
+    const int64_t r0 = chunk * PB_PART_CHUNK;
+    for (int i = 0; i < PB_PART_CHUNK; i += 32) {
+        const int64_t r = r0 + i + lane;
+        const uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        // cursor of my key lives in lane (key & 31), register cur0 or cur1
+        const uint32_t c0 = __shfl_sync(0xffffffffu, cur0, key & 31);
+        const uint32_t c1 = __shfl_sync(0xffffffffu, cur1, key & 31);
+        if (key != PB_KEY_DROP) {
+            const uint32_t dst = (key < 32 ? c0 : c1) + rank;
+            const uint32_t m = meta[r];
+            const uint64_t b = base[r];
+            // record: pos, end, low 32 bits of the byte offset of the read's first quality,
+            //         mapq | strand<<8 | simple<<9 | (offset bits 32..39)<<24
+            int4 rec;
+            rec.x = pos[r]; rec.y = rend[r]; rec.z = (int)(uint32_t)b;
+            rec.w = (int)(((m >> 8) & 0xffu) | (((m >> 20) & 1u) << 8) | (rsimple[r] ? PB_REC_SIMPLE : 0u) |
+                          ((uint32_t)(b >> 32) << 24));
+            srec[dst] = rec;
+            sorig[dst] = (uint32_t)r;
+        }
+        // advance the cursors: lane L counts the reads of samples L and L+32 in this step
+        uint32_t a0 = 0, a1 = 0;
+        for (int src = 0; src < 32; ++src) {
+            const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
+            a0 += kk == (uint32_t)lane;
+            a1 += kk == (uint32_t)(lane + 32);
+        }
+        cur0 += a0; cur1 += a1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exclusive scan of uint32 (in place), three kernels; totals fit 32 bits (number of reads).
+#define PB_SCAN_ITEMS 8
+#define PB_SCAN_THREADS 256
+__device__ __forceinline__ uint32_t pb_block_exscan(uint32_t v, uint32_t *total) {
+    __shared__ uint32_t wsum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    __syncthreads();
+    if (lane == 31) wsum[wid] = x;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t s = lane < nw ? wsum[lane] : 0;
+        for (int o = 1; o < 32; o <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += y; }
+        wsum[lane] = s;
+    }
+    __syncthreads();
+    const uint32_t base = wid ? wsum[wid - 1] : 0;
+    *total = wsum[nw - 1];
+    return base + x - v;
+}
+__global__ void __launch_bounds__(PB_SCAN_THREADS) k_scan_blocks(uint32_t *data, int64_t n, uint32_t *block_tot) {
+    const int64_t b0 = (int64_t)blockIdx.x * PB_SCAN_THREADS * PB_SCAN_ITEMS + (int64_t)threadIdx.x * PB_SCAN_ITEMS;
+    uint32_t v[PB_SCAN_ITEMS], s = 0;
+#pragma unroll
+    for (int i = 0; i < PB_SCAN_ITEMS; ++i) { v[i] = b0 + i < n ? data[b0 + i] : 0; s += v[i]; }
+    uint32_t tot;
+    uint32_t ex = pb_block_exscan(s, &tot);
+#pragma unroll
+    for (int i = 0; i < PB_SCAN_ITEMS; ++i) { if (b0 + i < n) data[b0 + i] = ex; ex += v[i]; }
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(1024) k_scan_totals(uint32_t *block_tot, int64_t nb) {
+    __shared__ uint32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < nb; b0 += 1024) {
+        const int64_t i = b0 + threadIdx.x;
+        const uint32_t v = i < nb ? block_tot[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = pb_block_exscan(v, &tot);
+        const uint32_t carry = carry_s;
+        if (i < nb) block_tot[i] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(PB_SCAN_THREADS) k_scan_add(uint32_t *data, int64_t n, const uint32_t *__restrict__ block_tot) {
+    const int64_t b0 = (int64_t)blockIdx.x * PB_SCAN_THREADS * PB_SCAN_ITEMS + (int64_t)threadIdx.x * PB_SCAN_ITEMS;
+    const uint32_t add = block_tot[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < PB_SCAN_ITEMS; ++i) if (b0 + i < n) data[b0 + i] += add;
+}
+// sample start offsets: the count matrix has one extra trailing element, so after the exclusive scan
+// offs[s * n_chunks] is the start of sample s for s < n and the total for s == n
+__global__ void k_sample_starts(const uint32_t *__restrict__ offs, int n_samples, int64_t n_chunks, uint32_t *__restrict__ sstart) {
+    const int s = threadIdx.x;
+    if (s <= n_samples) sstart[s] = offs[(int64_t)s * n_chunks];
+}
+
+// ------------------------------------------------------------------------------------------------
+// CIGAR cursor for reads that are not a single match op (resolve_cigar2, bam_pileup.c:90-221):
+// query offset of reference position p, or -1 when p falls in a deletion / reference skip.
+__device__ __forceinline__ int pb_resolve(const uint32_t *__restrict__ cig, uint32_t nc, int pos, int p) {
+    int x = pos, y = 0;
+    for (uint32_t i = 0; i < nc; ++i) {
+        const uint32_t c = __ldg(cig + i);
+        const int op = c & 15, len = (int)(c >> 4);
+        if (op == 0 || op == 7 || op == 8) {
+            if (p < x + len) return p >= x ? y + (p - x) : -1;
+            x += len; y += len;
+        } else if (op == 2 || op == 3) {
+            if (p < x + len) return -1;
+            x += len;
+        } else if (op == 1 || op == 4) y += len;
+    }
+    return -1;
+}
+
+struct PbPileArgs {
+    // reads, partitioned by sample (file order inside a sample)
+    const int4 *srec;
+    const uint32_t *sorig;
+    const uint32_t *sstart;         // [n_samples+1]
+    const uint32_t *cigstart, *ncig, *cigar;
+    const uint8_t *seq4, *qual;
+    const char *ref;
+    int64_t ref_len;
+    int span_beg, span_end;
+    const int32_t *win_beg, *win_end;
+    int n_windows;
+    int n_samples;
+    int min_depth, max_depth, min_rmsQ, min_snpQ, min_mapQ, min_baseQ;
+    int illumina, het_mode;
+    const double *fk, *beta, *lhet;
+    const PbCounters *ctr;          // max_span, level table
+    uint64_t *site_type;            // [span]
+    uint8_t *site_flag;             // [span]  bit0 used, bit1 segregating
+    uint64_t *cb_out;               // [span * n_samples] or null
+};
+
+// Dynamic shared memory of k_pileup_call<TP> for n samples and nl quality levels.
+static inline size_t pb_pile_smem(int tp, int n, int nl) {
+    return (size_t)tp * n * 8 + (size_t)PB_REC_CAP * 16 + (size_t)PB_REC_CAP * 4 + (size_t)2 * nl * tp * 4 + 256 * 8 + 128 * 4 + 128;
+}
+
+// One CTA = TP consecutive reference positions x all samples.  For each sample the CTA stages the
+// sample's candidate read records in shared memory; each thread (one position) then walks the reads
+// covering its position in file order, expands the CIGAR to a query offset, applies the depth cap and
+// the base filters (call_base), accumulates the (quality level, strand, base) histogram of its cell in
+// its private shared-memory column, and runs the error model on it.  The n consensus words of the
+// position stay in shared memory for the per-site logic, so nothing per (site, sample) goes to HBM
+// unless the caller asked for the cb words.
+template <int TP>
+__global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = a.n_samples;
+    const int nl = a.ctr->n_levels;
+    const int n_lw = 2 * nl;
+    uint64_t *cbs = reinterpret_cast<uint64_t *>(smem_raw);                 // [TP][n]
+    int4 *recs = reinterpret_cast<int4 *>(cbs + (size_t)TP * n);            // [PB_REC_CAP]
+    uint32_t *rorig = reinterpret_cast<uint32_t *>(recs + PB_REC_CAP);      // [PB_REC_CAP]
+    uint32_t *hist = rorig + PB_REC_CAP;                                    // [n_lw][TP]
+    double *fk_s = reinterpret_cast<double *>(hist + (size_t)n_lw * TP);    // [256]
+    uint32_t *rng = reinterpret_cast<uint32_t *>(fk_s + 256);               // lo[64], hi[64]
+    uint8_t *qrank_s = reinterpret_cast<uint8_t *>(rng + 128);              // [64]
+    uint8_t *qval_s = qrank_s + 64;                                         // [64]
+
+    const int tid = threadIdx.x;
+    const int p0 = a.span_beg + (int)blockIdx.x * TP;
+    const int p = p0 + tid;
+    const int p_end = min(p0 + TP, a.span_end);
+    const bool valid = p < p_end;
+    const int max_span = a.ctr->max_span;
+
+    for (int i = tid; i < 256; i += TP) fk_s[i] = a.fk[i];
+    if (tid < 64) { qrank_s[tid] = a.ctr->qrank[tid]; qval_s[tid] = a.ctr->qval[tid]; }
+    for (int lw = 0; lw < n_lw; ++lw) hist[lw * TP + tid] = 0;
+    if (tid < n) {
+        // candidate reads of sample tid: pos in (p0 - max_span, p_end)
+        const uint32_t s0 = a.sstart[tid], s1 = a.sstart[tid + 1];
+        uint32_t lo = s0, hi = s1;
+        const int t_lo = p0 - max_span;       // first with pos > t_lo
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.srec[mid].x > t_lo) hi = mid; else lo = mid + 1; }
+        rng[tid] = lo;
+        hi = s1;
+        uint32_t l2 = lo;                     // first with pos >= p_end
+        while (l2 < hi) { const uint32_t mid = (l2 + hi) >> 1; if (a.srec[mid].x >= p_end) hi = mid; else l2 = mid + 1; }
+        rng[64 + tid] = l2;
+    }
+    __syncthreads();
+
+    const int ref_c = (valid && p >= 0 && p < a.ref_len) ? (int)(unsigned char)a.ref[p] : 'N';
+    const int r4 = pb_iupac_rev(ref_c) & 3;
+
+    for (int s = 0; s < n; ++s) {
+        const uint32_t lo = rng[s], hi = rng[64 + s];
+        int depth = 0, k = 0, rmsq = 0;
+        for (uint32_t c0 = lo; c0 < hi; c0 += PB_REC_CAP) {
+            const int cnt = (int)min((uint32_t)PB_REC_CAP, hi - c0);
+            __syncthreads();
+            for (int i = tid; i < cnt; i += TP) { recs[i] = a.srec[c0 + i]; rorig[i] = a.sorig[c0 + i]; }
+            __syncthreads();
+            if (!valid) continue;
+            int j = 0, jh = cnt;
+            const int thr = p - max_span;     // reads with pos <= thr end at or before p
+            while (j < jh) { const int mid = (j + jh) >> 1; if (recs[mid].x > thr) jh = mid; else j = mid + 1; }
+            for (; j < cnt; ++j) {
+                const int4 r = recs[j];
+                if (r.x > p) break;
+                if (r.y <= p) continue;
+                int qpos;
+                if ((uint32_t)r.w & PB_REC_SIMPLE) qpos = p - r.x;
+                else {
+                    const uint32_t o = rorig[j];
+                    qpos = pb_resolve(a.cigar + a.cigstart[o], a.ncig[o], r.x, p);
+                    if (qpos < 0) continue;                       // is_del / is_refskip (popbam.cpp:222)
+                }
+                if (depth >= a.max_depth) continue;               // cap precedes the filters (popbam.cpp:242-248)
+                ++depth;
+                const uint64_t boff = ((uint64_t)((uint32_t)r.w >> 24) << 32) | (uint32_t)r.z;
+                int bq = (int)__ldg(a.qual + boff + (uint32_t)qpos);
+                if (a.illumina) bq = bq > 31 ? bq - 31 : 0;
+                const int mapq = r.w & 0xff;
+                if (bq < a.min_baseQ || mapq < a.min_mapQ) continue;
+                const uint32_t sb = __ldg(a.seq4 + (boff >> 1) + ((uint32_t)qpos >> 1));
+                const uint32_t nib = (sb >> ((~qpos & 1) << 2)) & 0xfu;
+                const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+                if (b4 > 3) continue;
+                int qq = min(bq, mapq);
+                qq = max(4, min(63, qq));
+                const int lw = qrank_s[qq] * 2 + ((r.w >> 8) & 1);
+                hist[lw * TP + tid] += 1u << (8 * b4);
+                ++k;
+                rmsq += mapq * mapq;
+            }
+        }
+        uint64_t cb = 0;
+        if (depth > 0) {
+            double bsum[4] = {0.0, 0.0, 0.0, 0.0};
+            int c[4] = {0, 0, 0, 0};
+            if (k > 0) {
+                auto take = [&](int lw) -> uint32_t {
+                    const uint32_t w = hist[lw * TP + tid];
+                    if (w) hist[lw * TP + tid] = 0;
+                    return w;
+                };
+                pb_walk_hist(take, n_lw, qval_s, k, r4, fk_s, a.beta, bsum, c);
+            }
+            cb = pb_finish_cell(bsum, c, k, rmsq, a.lhet);
+        }
+        cbs[(size_t)tid * n + s] = cb;
+    }
+
+    // per-site logic (make_X, pop_nucdiv.cpp:148-197) on the n words of this thread's position
+    if (valid) {
+        uint64_t cov, type;
+        const int fq = pb_site_logic(cbs + (size_t)tid * n, 1, n, ref_c, a.het_mode, a.min_snpQ, a.min_rmsQ, a.min_depth,
+                                     a.max_depth, &cov, &type);
+        // window membership: windows are sorted and disjoint
+        int lo = 0, hi = a.n_windows;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(a.win_end + mid) > p) hi = mid; else lo = mid + 1; }
+        const bool in_win = lo < a.n_windows && __ldg(a.win_beg + lo) <= p;
+        const bool used = in_win && __popcll(cov) == n;
+        const int64_t o = (int64_t)p - a.span_beg;
+        a.site_type[o] = type;
+        a.site_flag[o] = (uint8_t)((used ? 1 : 0) | ((used && fq > 0) ? 2 : 0));
+    }
+    if (a.cb_out) {
+        __syncthreads();
+        const int64_t o0 = ((int64_t)p0 - a.span_beg) * n;
+        const int tot = (p_end - p0) * n;
+        for (int i = tid; i < tot; i += TP) a.cb_out[o0 + i] = cbs[i];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per window: num_sites, segsites (WRITE = false) and, after the scan of segsites, the ordered list
+// of segregating sites (WRITE = true): hap.pos / hap.idx / types / ref / per-sample cb words
+// (make_nucdiv tail, pop_nucdiv.cpp:176-199).
+template <bool WRITE>
+__global__ void __launch_bounds__(256) k_window_sites(int span_beg, const int32_t *__restrict__ win_beg,
+                                                      const int32_t *__restrict__ win_end, const uint8_t *__restrict__ site_flag,
+                                                      const uint64_t *__restrict__ site_type, const char *__restrict__ ref,
+                                                      int64_t ref_len, const uint64_t *__restrict__ cb_all, int n_samples,
+                                                      int32_t *__restrict__ num_sites, int32_t *__restrict__ segsites,
+                                                      const int64_t *__restrict__ seg_off, uint32_t *__restrict__ seg_pos,
+                                                      uint32_t *__restrict__ seg_idx, uint64_t *__restrict__ seg_type,
+                                                      uint8_t *__restrict__ seg_ref, uint64_t *__restrict__ seg_cb) {
+    const int w = blockIdx.x;
+    const int beg = win_beg[w], len = win_end[w] - beg;
+    const int64_t off = (int64_t)beg - span_beg;
+    uint32_t carry_sites = 0, carry_seg = 0;
+    const int64_t so = WRITE ? seg_off[w] : 0;
+    for (int b0 = 0; b0 < len; b0 += 256) {
+        const int i = b0 + (int)threadIdx.x;
+        const uint32_t f = i < len ? site_flag[off + i] : 0;
+        const uint32_t v = (f & 1u) | ((f >> 1 & 1u) << 16);
+        uint32_t tot;
+        const uint32_t ex = pb_block_exscan(v, &tot);
+        if (WRITE && (f & 2u)) {
+            const int64_t d = so + carry_seg + (ex >> 16);
+            seg_pos[d] = (uint32_t)(beg + i);
+            seg_idx[d] = carry_sites + (ex & 0xffffu);
+            seg_type[d] = site_type[off + i];
+            const int64_t rp = (int64_t)beg + i;
+            seg_ref[d] = (rp >= 0 && rp < ref_len) ? (uint8_t)ref[rp] : (uint8_t)'N';
+            if (seg_cb) for (int s = 0; s < n_samples; ++s) seg_cb[d * n_samples + s] = cb_all[(off + i) * n_samples + s];
+        }
+        carry_sites += tot & 0xffffu;
+        carry_seg += tot >> 16;
+    }
+    if (!WRITE && threadIdx.x == 0) { num_sites[w] = (int32_t)carry_sites; segsites[w] = (int32_t)carry_seg; }
+}
+
+// seg_off[w] = exclusive sum of segsites (int64), single block
+__global__ void __launch_bounds__(1024) k_scan_windows(const int32_t *__restrict__ segsites, int n_windows, int64_t *__restrict__ seg_off) {
+    __shared__ unsigned long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < n_windows; b0 += 1024) {
+        const int i = b0 + (int)threadIdx.x;
+        const uint32_t v = i < n_windows ? (uint32_t)segsites[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = pb_block_exscan(v, &tot);
+        const unsigned long long carry = carry_s;
+        if (i < n_windows) seg_off[i] = (int64_t)(carry + ex);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) seg_off[n_windows] = (int64_t)carry_s;
+}

@@ -1,0 +1,645 @@
+// pb_lib.cu -- the C ABI of include/popbam_b200.h: context, device buffers, the kernel pipeline of
+// one region, pinned result buffers.  There is no host compute path: every statistic is produced by
+// the kernels in pb_kernels.cuh / pb_stats.cuh, and pb_create fails without a CUDA device.
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/popbam_b200.h"
+#include "pb_kernels.cuh"
+#include "pb_stats.cuh"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+struct HostBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+std::string g_create_error;
+
+enum RegionState { ST_IDLE = 0, ST_OPEN = 1, ST_LAUNCHED = 2, ST_DONE = 3 };
+
+}  // namespace
+
+struct pb_ctx {
+    pb_params prm;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int n_sms = 148;
+    size_t smem_optin = 0;
+    // tables / contig
+    DevBuf d_fk, d_beta, d_lhet, d_ref;
+    int64_t ref_len = 0;
+    int32_t ref_tid = -1;
+    // region
+    int state = ST_IDLE;
+    uint32_t analyses = 0;
+    int nw = 0;
+    int span_beg = 0, span_end = 0;
+    std::vector<int32_t> h_wbeg, h_wend;
+    DevBuf d_wbeg, d_wend;
+    // reads on the device (concatenation of the pushed batches)
+    int64_t n_reads = 0, n_cig = 0, n_bytes = 0;
+    DevBuf d_pos, d_meta, d_cigstart, d_ncig, d_base, d_cigar, d_seq4, d_qual, d_tmp_cig, d_tmp_base;
+    // derived
+    DevBuf d_rend, d_rkey, d_rsimple, d_counts, d_blocktot, d_srec, d_sorig, d_sstart, d_ctr;
+    DevBuf d_site_type, d_site_flag, d_cb;
+    DevBuf d_num_sites, d_segsites, d_seg_off, d_seg_pos, d_seg_idx, d_seg_type, d_seg_ref, d_seg_cb;
+    DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wr, d_wall_u, d_stats;
+    // pinned results
+    HostBuf h_ctr, h_small, h_seg, h_span;
+    PbCounters ctr_host;
+    int64_t s_total = 0;
+    pb_region_result res;
+    // bam_fetch_f shim staging (pb_push_record)
+    std::vector<int32_t> r_pos;
+    std::vector<uint32_t> r_meta, r_cig_off, r_cigar, r_base_off;
+    std::vector<uint8_t> r_seq4, r_qual;
+    // timing of the last pipeline run
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float ms_prep = 0, ms_pileup = 0, ms_sites = 0, ms_stats = 0;
+};
+
+namespace {
+
+int fail(pb_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define PB_CUDA(c, call)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess) return fail((c), PB_ERR_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+// grow-only device buffer; `keep` bytes of the old contents are preserved
+int dev_reserve(pb_ctx *c, DevBuf &b, size_t bytes, size_t keep = 0) {
+    if (bytes <= b.cap) return PB_OK;
+    size_t want = std::max(bytes, b.cap + b.cap / 2);
+    want = (want + 255) & ~(size_t)255;
+    void *np = nullptr;
+    cudaError_t e = cudaMalloc(&np, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, PB_ERR_NOMEM, "cudaMalloc(%zu bytes): %s", want, cudaGetErrorString(e)); }
+    if (keep && b.p) {
+        e = cudaMemcpyAsync(np, b.p, keep, cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { cudaFree(np); return fail(c, PB_ERR_CUDA, "device buffer move: %s", cudaGetErrorString(e)); }
+    } else if (b.p) {
+        cudaStreamSynchronize(c->stream);   // nothing in flight may still use the old block
+    }
+    if (b.p) cudaFree(b.p);
+    b.p = np; b.cap = want;
+    return PB_OK;
+}
+int host_reserve(pb_ctx *c, HostBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return PB_OK;
+    if (b.p) { cudaStreamSynchronize(c->stream); cudaFreeHost(b.p); b.p = nullptr; b.cap = 0; }
+    size_t want = (bytes + 4095) & ~(size_t)4095;
+    cudaError_t e = cudaHostAlloc(&b.p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); b.p = nullptr; return fail(c, PB_ERR_NOMEM, "cudaHostAlloc(%zu bytes): %s", want, cudaGetErrorString(e)); }
+    b.cap = want;
+    return PB_OK;
+}
+#define PB_TRY(x) do { int rc_ = (x); if (rc_ != PB_OK) return rc_; } while (0)
+
+template <class T> T *dp(const DevBuf &b) { return reinterpret_cast<T *>(b.p); }
+
+inline unsigned nblk(int64_t n, int per) { return (unsigned)std::max<int64_t>(1, (n + per - 1) / per); }
+
+// carve `count` elements of T out of a pinned / device arena
+struct Carver {
+    unsigned char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base(reinterpret_cast<unsigned char *>(b)) {}
+    template <class T> T *take(size_t count) {
+        off = (off + 15) & ~(size_t)15;
+        T *r = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += sizeof(T) * (count ? count : 1);
+        return r;
+    }
+};
+
+// layout of the fixed-size (per window) result arrays, identical on device and pinned host
+struct SmallLayout {
+    int32_t *num_sites, *segsites; int64_t *seg_off;
+    double *piw, *pib; uint16_t *min_dxy;
+    int32_t *sfs_num_snps; double *td, *fwh;
+    int32_t *ld_num_snps; double *zns, *omegamax;
+    int32_t *wall_num_snps; double *wallb, *wallq;
+    uint16_t *ind_div, *pop_div; int32_t *div_num_snps;
+    int32_t *nhaps; double *hdiv, *ehhs;
+    size_t bytes;
+};
+SmallLayout small_layout(void *base, int NW, int P, int n) {
+    Carver cv(base);
+    SmallLayout L;
+    const size_t wp = (size_t)NW * P, wpp = (size_t)NW * P * P, wn = (size_t)NW * n;
+    L.num_sites = cv.take<int32_t>(NW); L.segsites = cv.take<int32_t>(NW); L.seg_off = cv.take<int64_t>(NW + 1);
+    L.piw = cv.take<double>(wp); L.pib = cv.take<double>(wpp); L.min_dxy = cv.take<uint16_t>(wpp);
+    L.sfs_num_snps = cv.take<int32_t>(wp); L.td = cv.take<double>(wp); L.fwh = cv.take<double>(wp);
+    L.ld_num_snps = cv.take<int32_t>(wp); L.zns = cv.take<double>(wp); L.omegamax = cv.take<double>(wp);
+    L.wall_num_snps = cv.take<int32_t>(wp); L.wallb = cv.take<double>(wp); L.wallq = cv.take<double>(wp);
+    L.ind_div = cv.take<uint16_t>(wn); L.pop_div = cv.take<uint16_t>(wp); L.div_num_snps = cv.take<int32_t>(wp);
+    L.nhaps = cv.take<int32_t>(wp); L.hdiv = cv.take<double>(wp); L.ehhs = cv.take<double>(wp);
+    L.bytes = (cv.off + 255) & ~(size_t)255;
+    return L;
+}
+struct SegLayout {
+    uint32_t *seg_pos, *seg_idx; uint64_t *seg_type; uint8_t *seg_ref; uint64_t *seg_cb;
+    size_t bytes;
+};
+SegLayout seg_layout(void *base, int64_t S, int n, bool with_cb) {
+    Carver cv(base);
+    SegLayout L;
+    L.seg_type = cv.take<uint64_t>(S); L.seg_cb = with_cb ? cv.take<uint64_t>((size_t)S * n) : nullptr;
+    L.seg_pos = cv.take<uint32_t>(S); L.seg_idx = cv.take<uint32_t>(S); L.seg_ref = cv.take<uint8_t>(S);
+    L.bytes = (cv.off + 255) & ~(size_t)255;
+    return L;
+}
+
+int exclusive_scan_u32(pb_ctx *c, uint32_t *data, int64_t n) {
+    const int per = PB_SCAN_THREADS * PB_SCAN_ITEMS;
+    const int64_t nb = (n + per - 1) / per;
+    PB_TRY(dev_reserve(c, c->d_blocktot, sizeof(uint32_t) * (size_t)std::max<int64_t>(nb, 1)));
+    k_scan_blocks<<<(unsigned)nb, PB_SCAN_THREADS, 0, c->stream>>>(data, n, dp<uint32_t>(c->d_blocktot));
+    k_scan_totals<<<1, 1024, 0, c->stream>>>(dp<uint32_t>(c->d_blocktot), nb);
+    k_scan_add<<<(unsigned)nb, PB_SCAN_THREADS, 0, c->stream>>>(data, n, dp<uint32_t>(c->d_blocktot));
+    c->launches += 3;
+    PB_CUDA(c, cudaGetLastError());
+    return PB_OK;
+}
+
+constexpr int kTP = 128;   // positions (threads) per CTA of the hot kernel
+
+int run_pipeline(pb_ctx *c) {
+    const pb_params &P = c->prm;
+    const int n = P.n_samples, NW = c->nw;
+    const int64_t N = c->n_reads;
+    const int64_t span = (int64_t)c->span_end - c->span_beg;
+    cudaStream_t st = c->stream;
+    const bool want_cb = (P.flags & PB_FLAG_EMIT_CB) || (c->analyses & PB_AN_SNP);
+
+    PB_CUDA(c, cudaEventRecord(c->ev[0], st));
+    // ---- per-read preparation, quality levels, partition by sample
+    PB_TRY(dev_reserve(c, c->d_ctr, sizeof(PbCounters)));
+    PB_CUDA(c, cudaMemsetAsync(c->d_ctr.p, 0, sizeof(PbCounters), st));
+    PB_TRY(dev_reserve(c, c->d_rend, sizeof(int32_t) * (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_rkey, (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_rsimple, (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_srec, sizeof(int4) * (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_sorig, sizeof(uint32_t) * (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_sstart, sizeof(uint32_t) * (PB_MAX_SAMPLES + 1)));
+    const int64_t n_chunks = std::max<int64_t>(1, (N + PB_PART_CHUNK - 1) / PB_PART_CHUNK);
+    const int64_t n_counts = (int64_t)n * n_chunks + 1;
+    PB_TRY(dev_reserve(c, c->d_counts, sizeof(uint32_t) * (size_t)n_counts));
+    PbCounters *ctr = dp<PbCounters>(c->d_ctr);
+    if (N > 0) {
+        k_read_prep<<<nblk(N, 256), 256, 0, st>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
+                                                 dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), n, P.min_mapQ,
+                                                 dp<int32_t>(c->d_rend), dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rsimple), ctr);
+        k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0,
+                                                 P.min_baseQ, ctr);
+        c->launches += 2;
+    }
+    k_level_table<<<1, 32, 0, st>>>(ctr);
+    PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
+    const unsigned part_blocks = nblk(n_chunks * 32, 128);
+    k_part_count<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), n, n_chunks, dp<uint32_t>(c->d_counts));
+    c->launches += 2;
+    PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts));
+    k_sample_starts<<<1, 128, 0, st>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart));
+    k_part_scatter<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), n, n_chunks, dp<uint32_t>(c->d_counts), dp<int32_t>(c->d_pos),
+                                               dp<int32_t>(c->d_rend), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
+                                               dp<uint8_t>(c->d_rsimple), dp<int4>(c->d_srec), dp<uint32_t>(c->d_sorig));
+    c->launches += 2;
+    PB_CUDA(c, cudaGetLastError());
+    PB_TRY(host_reserve(c, c->h_ctr, sizeof(PbCounters)));
+    PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(c, cudaEventRecord(c->ev[1], st));
+    PB_CUDA(c, cudaStreamSynchronize(st));
+    c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
+    if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
+
+    // ---- the hot kernel
+    PB_TRY(dev_reserve(c, c->d_site_type, sizeof(uint64_t) * (size_t)span));
+    PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
+    if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
+    const int nl = c->ctr_host.n_levels;
+    const size_t smem = pb_pile_smem(kTP, n, nl);
+    if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d samples x %d quality levels exceeds %zu bytes", n, nl, c->smem_optin);
+    PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PbPileArgs pa;
+    pa.srec = dp<int4>(c->d_srec); pa.sorig = dp<uint32_t>(c->d_sorig); pa.sstart = dp<uint32_t>(c->d_sstart);
+    pa.cigstart = dp<uint32_t>(c->d_cigstart); pa.ncig = dp<uint32_t>(c->d_ncig); pa.cigar = dp<uint32_t>(c->d_cigar);
+    pa.seq4 = dp<uint8_t>(c->d_seq4); pa.qual = dp<uint8_t>(c->d_qual);
+    pa.ref = dp<char>(c->d_ref); pa.ref_len = c->ref_len;
+    pa.span_beg = c->span_beg; pa.span_end = c->span_end;
+    pa.win_beg = dp<int32_t>(c->d_wbeg); pa.win_end = dp<int32_t>(c->d_wend); pa.n_windows = NW;
+    pa.n_samples = n;
+    pa.min_depth = P.min_depth; pa.max_depth = P.max_depth; pa.min_rmsQ = P.min_rmsQ; pa.min_snpQ = P.min_snpQ;
+    pa.min_mapQ = P.min_mapQ; pa.min_baseQ = P.min_baseQ;
+    pa.illumina = (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0; pa.het_mode = (P.flags & PB_FLAG_HETEROZYGOTE) ? 1 : 0;
+    pa.fk = dp<double>(c->d_fk); pa.beta = dp<double>(c->d_beta); pa.lhet = dp<double>(c->d_lhet);
+    pa.ctr = ctr;
+    pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
+    pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
+    PB_CUDA(c, cudaEventRecord(c->ev[2], st));
+    k_pileup_call<kTP><<<nblk(span, kTP), kTP, smem, st>>>(pa);
+    c->launches += 1;
+    PB_CUDA(c, cudaGetLastError());
+    PB_CUDA(c, cudaEventRecord(c->ev[3], st));
+
+    // ---- per-window site counts, offsets of the segregating-site lists
+    const SmallLayout dl0 = small_layout(nullptr, NW, P.n_pops, n);
+    PB_TRY(dev_reserve(c, c->d_stats, dl0.bytes));
+    PB_TRY(host_reserve(c, c->h_small, dl0.bytes));
+    const SmallLayout dl = small_layout(c->d_stats.p, NW, P.n_pops, n);
+    PB_CUDA(c, cudaMemsetAsync(c->d_stats.p, 0, dl.bytes, st));
+    k_window_sites<false><<<NW, 256, 0, st>>>(c->span_beg, pa.win_beg, pa.win_end, pa.site_flag, pa.site_type, pa.ref, pa.ref_len, nullptr, n,
+                                             dl.num_sites, dl.segsites, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    k_scan_windows<<<1, 1024, 0, st>>>(dl.segsites, NW, dl.seg_off);
+    c->launches += 2;
+    PB_CUDA(c, cudaGetLastError());
+    int64_t *h_total = reinterpret_cast<int64_t *>(c->h_ctr.p) + (sizeof(PbCounters) + 7) / 8;   // h_ctr has a page
+    PB_CUDA(c, cudaMemcpyAsync(h_total, dl.seg_off + NW, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(c, cudaStreamSynchronize(st));
+    const int64_t S = *h_total;
+    c->s_total = S;
+
+    // ---- segregating-site lists
+    const bool with_cb = (c->analyses & PB_AN_SNP) != 0;
+    const SegLayout sl0 = seg_layout(nullptr, S, n, with_cb);
+    PB_TRY(dev_reserve(c, c->d_seg_type, sl0.bytes));
+    PB_TRY(host_reserve(c, c->h_seg, sl0.bytes));
+    const SegLayout sl = seg_layout(c->d_seg_type.p, S, n, with_cb);
+    k_window_sites<true><<<NW, 256, 0, st>>>(c->span_beg, pa.win_beg, pa.win_end, pa.site_flag, pa.site_type, pa.ref, pa.ref_len,
+                                            with_cb ? dp<uint64_t>(c->d_cb) : nullptr, n, dl.num_sites, dl.segsites, dl.seg_off,
+                                            sl.seg_pos, sl.seg_idx, sl.seg_type, sl.seg_ref, sl.seg_cb);
+    c->launches += 1;
+    PB_CUDA(c, cudaGetLastError());
+    PB_CUDA(c, cudaEventRecord(c->ev[4], st));
+
+    // ---- window statistics
+    const uint32_t stat_bits = PB_AN_NUCDIV | PB_AN_SFS | PB_AN_LD_ZNS | PB_AN_LD_OMEGA | PB_AN_LD_WALL | PB_AN_DIVERGE_IND |
+                               PB_AN_DIVERGE_POP | PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS | PB_AN_HAPLO_DXY;
+    if (c->analyses & stat_bits) {
+        PbStatArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.n = n; sa.P = P.n_pops;
+        for (int i = 0; i < PB_MAX_SAMPLES; ++i) { sa.pop_mask[i] = P.pop_mask[i]; sa.pop_nsmpl[i] = P.pop_nsmpl[i]; }
+        sa.analyses = c->analyses; sa.flags = P.flags; sa.outidx = P.outidx; sa.min_freq = P.min_freq;
+        sa.num_sites = dl.num_sites; sa.segsites = dl.segsites; sa.seg_off = dl.seg_off; sa.seg_type = sl.seg_type;
+        sa.s_total = S;
+        if (c->analyses & (PB_AN_NUCDIV | PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS | PB_AN_HAPLO_DXY | PB_AN_DIVERGE_IND)) {
+            PB_TRY(dev_reserve(c, c->d_hap, sizeof(uint64_t) * (size_t)n * (size_t)(S / 64 + NW + 1)));
+            sa.hap = dp<uint64_t>(c->d_hap);
+        }
+        if (c->analyses & (PB_AN_LD_ZNS | PB_AN_LD_OMEGA | PB_AN_HAPLO_EHHS)) {
+            PB_TRY(dev_reserve(c, c->d_kt, sizeof(uint64_t) * (size_t)(S + NW + 1)));
+            PB_TRY(dev_reserve(c, c->d_km, (size_t)(S + NW + 1)));
+            sa.kt = dp<uint64_t>(c->d_kt); sa.km = dp<uint8_t>(c->d_km);
+        }
+        if (c->analyses & PB_AN_LD_OMEGA) {
+            const size_t cnt = (size_t)(S + 2 * (int64_t)NW + 2);
+            PB_TRY(dev_reserve(c, c->d_lsum, sizeof(double) * cnt));
+            PB_TRY(dev_reserve(c, c->d_rsum, sizeof(double) * cnt));
+            PB_TRY(dev_reserve(c, c->d_wr, sizeof(double) * cnt));
+            sa.lsum = dp<double>(c->d_lsum); sa.rsum = dp<double>(c->d_rsum); sa.wr = dp<double>(c->d_wr);
+        }
+        if (c->analyses & PB_AN_LD_WALL) {
+            PB_TRY(dev_reserve(c, c->d_wall_u, sizeof(uint64_t) * (size_t)P.n_pops * (size_t)std::max<int64_t>(S, 1)));
+            sa.wall_u = dp<uint64_t>(c->d_wall_u);
+        }
+        sa.piw = dl.piw; sa.pib = dl.pib; sa.min_dxy = dl.min_dxy;
+        sa.sfs_num_snps = dl.sfs_num_snps; sa.td = dl.td; sa.fwh = dl.fwh;
+        sa.ld_num_snps = dl.ld_num_snps; sa.zns = dl.zns; sa.omegamax = dl.omegamax;
+        sa.wall_num_snps = dl.wall_num_snps; sa.wallb = dl.wallb; sa.wallq = dl.wallq;
+        sa.ind_div = dl.ind_div; sa.pop_div = dl.pop_div; sa.div_num_snps = dl.div_num_snps;
+        sa.nhaps = dl.nhaps; sa.hdiv = dl.hdiv; sa.ehhs = dl.ehhs;
+        k_window_stats<<<NW, PB_ST_THREADS, (size_t)n * n * sizeof(uint16_t), st>>>(sa);
+        c->launches += 1;
+        PB_CUDA(c, cudaGetLastError());
+    }
+    PB_CUDA(c, cudaEventRecord(c->ev[5], st));
+
+    // ---- results to pinned host memory
+    PB_CUDA(c, cudaMemcpyAsync(c->h_small.p, c->d_stats.p, dl.bytes, cudaMemcpyDeviceToHost, st));
+    if (S > 0) PB_CUDA(c, cudaMemcpyAsync(c->h_seg.p, c->d_seg_type.p, sl.bytes, cudaMemcpyDeviceToHost, st));
+    if (P.flags & PB_FLAG_EMIT_CB) {
+        Carver cv(nullptr);
+        cv.take<uint64_t>((size_t)span * n); cv.take<uint64_t>((size_t)span); cv.take<uint8_t>((size_t)span);
+        PB_TRY(host_reserve(c, c->h_span, cv.off + 64));
+        Carver hv(c->h_span.p);
+        uint64_t *hcb = hv.take<uint64_t>((size_t)span * n);
+        uint64_t *hty = hv.take<uint64_t>((size_t)span);
+        uint8_t *hfl = hv.take<uint8_t>((size_t)span);
+        PB_CUDA(c, cudaMemcpyAsync(hcb, c->d_cb.p, sizeof(uint64_t) * (size_t)span * n, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(c, cudaMemcpyAsync(hty, c->d_site_type.p, sizeof(uint64_t) * (size_t)span, cudaMemcpyDeviceToHost, st));
+        PB_CUDA(c, cudaMemcpyAsync(hfl, c->d_site_flag.p, (size_t)span, cudaMemcpyDeviceToHost, st));
+    }
+    return PB_OK;
+}
+
+int fill_result(pb_ctx *c, pb_region_result *out) {
+    const pb_params &P = c->prm;
+    const int n = P.n_samples, NW = c->nw;
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaEventElapsedTime(&c->ms_prep, c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->ms_pileup, c->ev[2], c->ev[3]);
+    cudaEventElapsedTime(&c->ms_sites, c->ev[3], c->ev[4]);
+    cudaEventElapsedTime(&c->ms_stats, c->ev[4], c->ev[5]);
+    const SmallLayout hl = small_layout(c->h_small.p, NW, P.n_pops, n);
+    const bool with_cb = (c->analyses & PB_AN_SNP) != 0;
+    const SegLayout sl = seg_layout(c->h_seg.p, c->s_total, n, with_cb);
+    pb_region_result &r = c->res;
+    memset(&r, 0, sizeof r);
+    r.n_windows = NW; r.n_pops = P.n_pops; r.n_samples = n; r.analyses = c->analyses;
+    r.win_beg = c->h_wbeg.data(); r.win_end = c->h_wend.data();
+    r.num_sites = hl.num_sites; r.segsites = hl.segsites; r.seg_off = hl.seg_off;
+    r.seg_pos = sl.seg_pos; r.seg_idx = sl.seg_idx; r.seg_type = sl.seg_type; r.seg_ref = sl.seg_ref; r.seg_cb = sl.seg_cb;
+    const uint32_t an = c->analyses;
+    if (an & (PB_AN_NUCDIV | PB_AN_HAPLO_DXY)) { r.piw = hl.piw; r.pib = hl.pib; r.min_dxy = hl.min_dxy; }
+    if (an & PB_AN_SFS) { r.sfs_num_snps = hl.sfs_num_snps; r.td = hl.td; r.fwh = hl.fwh; }
+    if (an & (PB_AN_LD_ZNS | PB_AN_LD_OMEGA)) { r.ld_num_snps = hl.ld_num_snps; r.zns = hl.zns; r.omegamax = hl.omegamax; }
+    if (an & PB_AN_LD_WALL) { r.wall_num_snps = hl.wall_num_snps; r.wallb = hl.wallb; r.wallq = hl.wallq; }
+    if (an & PB_AN_DIVERGE_IND) r.ind_div = hl.ind_div;
+    if (an & PB_AN_DIVERGE_POP) { r.pop_div = hl.pop_div; r.div_num_snps = hl.div_num_snps; }
+    if (an & (PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS)) { r.nhaps = hl.nhaps; r.hdiv = hl.hdiv; }
+    if (an & PB_AN_HAPLO_EHHS) r.ehhs = hl.ehhs;
+    r.span_beg = c->span_beg; r.span_end = c->span_end;
+    if (P.flags & PB_FLAG_EMIT_CB) {
+        const size_t span = (size_t)(c->span_end - c->span_beg);
+        Carver hv(c->h_span.p);
+        r.cb = hv.take<uint64_t>(span * n);
+        r.site_type = hv.take<uint64_t>(span);
+        r.site_flag = hv.take<uint8_t>(span);
+    }
+    r.reads_pushed = c->n_reads;
+    r.reads_used = (int64_t)c->ctr_host.reads_used;
+    r.aligned_bases = (int64_t)c->ctr_host.aligned_bases;
+    if (out) *out = r;
+    return PB_OK;
+}
+
+int flush_records(pb_ctx *c);
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char *pb_version(void) { return "popbam_b200 0.1 (sm_100a)"; }
+
+const char *pb_last_error(const pb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *status) {
+    auto bail = [&](int code, const char *msg, pb_ctx *c) -> pb_ctx * {
+        g_create_error = msg;
+        if (c && c->err.size()) g_create_error += std::string(": ") + c->err;
+        if (status) *status = code;
+        if (c) pb_destroy(c);
+        return nullptr;
+    };
+    if (!p) return bail(PB_ERR_ARG, "null params", nullptr);
+    if (p->n_samples < 1 || p->n_samples > PB_MAX_SAMPLES || p->n_pops < 1 || p->n_pops > PB_MAX_SAMPLES)
+        return bail(PB_ERR_ARG, "n_samples / n_pops out of range (1..64)", nullptr);
+    if (p->max_depth < 1 || p->max_depth > 255)
+        return bail(PB_ERR_UNSUPPORTED, "max_depth must be in 1..255 (errmod_cal subsamples above 255, pop_utils.cpp:293)", nullptr);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return bail(PB_ERR_CUDA, "no CUDA device available (this library has no CPU path)", nullptr);
+    }
+    if (p->device < 0 || p->device >= ndev) return bail(PB_ERR_ARG, "device ordinal out of range", nullptr);
+    if (cudaSetDevice(p->device) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaSetDevice failed", nullptr);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, p->device) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaGetDeviceProperties failed", nullptr);
+    if (prop.major < 10) return bail(PB_ERR_CUDA, "device is not sm_100 class (kernels are built for sm_100a only)", nullptr);
+    pb_ctx *c = new pb_ctx();
+    c->prm = *p;
+    c->n_sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
+    for (auto &ev : c->ev)
+        if (cudaEventCreate(&ev) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
+    // error-model tables
+    const size_t nb = (size_t)64 * 256 * 256;
+    std::vector<double> fk, beta, lhet;
+    const double *pfk, *pbeta, *plhet;
+    if (tables && tables->fk && tables->beta && tables->lhet) { pfk = tables->fk; pbeta = tables->beta; plhet = tables->lhet; }
+    else {
+        fk.resize(256); beta.resize(nb); lhet.resize(65536);
+        pb_build_errmod_tables(fk.data(), beta.data(), lhet.data());
+        pfk = fk.data(); pbeta = beta.data(); plhet = lhet.data();
+    }
+    if (dev_reserve(c, c->d_fk, 256 * 8) || dev_reserve(c, c->d_beta, nb * 8) || dev_reserve(c, c->d_lhet, 65536 * 8))
+        return bail(PB_ERR_NOMEM, "table allocation failed", c);
+    if (cudaMemcpy(c->d_fk.p, pfk, 256 * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_beta.p, pbeta, nb * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c->d_lhet.p, plhet, 65536 * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+        return bail(PB_ERR_CUDA, "table upload failed", c);
+    if (status) *status = PB_OK;
+    return c;
+}
+
+void pb_destroy(pb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->prm.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
+                      &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rend,
+                      &c->d_rkey, &c->d_rsimple, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sorig, &c->d_sstart, &c->d_ctr,
+                      &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
+                      &c->d_seg_idx, &c->d_seg_type, &c->d_seg_ref, &c->d_seg_cb, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
+                      &c->d_rsum, &c->d_wr, &c->d_wall_u, &c->d_stats};
+    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    HostBuf *hb[] = {&c->h_ctr, &c->h_small, &c->h_seg, &c->h_span};
+    for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
+    for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int pb_set_contig(pb_ctx *c, int32_t tid, const char *ref_bases, int64_t len) {
+    if (!c || !ref_bases || len < 0) return fail(c, PB_ERR_ARG, "pb_set_contig: bad argument");
+    if (c->state == ST_OPEN || c->state == ST_LAUNCHED) return fail(c, PB_ERR_STATE, "pb_set_contig inside a region");
+    PB_CUDA(c, cudaSetDevice(c->prm.device));
+    PB_TRY(dev_reserve(c, c->d_ref, (size_t)std::max<int64_t>(len, 1)));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_ref.p, ref_bases, (size_t)len, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->ref_len = len; c->ref_tid = tid;
+    return PB_OK;
+}
+
+int pb_region_begin(pb_ctx *c, uint32_t analyses, int32_t n_windows, const int32_t *win_beg, const int32_t *win_end) {
+    if (!c || n_windows < 1 || !win_beg || !win_end) return fail(c, PB_ERR_ARG, "pb_region_begin: bad argument");
+    if (c->ref_tid < 0 && c->ref_len == 0) return fail(c, PB_ERR_STATE, "pb_region_begin before pb_set_contig");
+    for (int i = 0; i < n_windows; ++i) {
+        if (win_end[i] < win_beg[i]) return fail(c, PB_ERR_ARG, "window %d has end < begin", i);
+        if (i && win_beg[i] < win_end[i - 1]) return fail(c, PB_ERR_ARG, "windows must be sorted and disjoint (window %d)", i);
+    }
+    if ((int64_t)win_end[n_windows - 1] - win_beg[0] < 1) return fail(c, PB_ERR_ARG, "empty region");
+    PB_CUDA(c, cudaSetDevice(c->prm.device));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->analyses = analyses; c->nw = n_windows;
+    c->h_wbeg.assign(win_beg, win_beg + n_windows); c->h_wend.assign(win_end, win_end + n_windows);
+    c->span_beg = win_beg[0]; c->span_end = win_end[n_windows - 1];
+    PB_TRY(dev_reserve(c, c->d_wbeg, sizeof(int32_t) * (size_t)n_windows));
+    PB_TRY(dev_reserve(c, c->d_wend, sizeof(int32_t) * (size_t)n_windows));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_wbeg.p, c->h_wbeg.data(), sizeof(int32_t) * (size_t)n_windows, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_wend.p, c->h_wend.data(), sizeof(int32_t) * (size_t)n_windows, cudaMemcpyHostToDevice, c->stream));
+    c->n_reads = c->n_cig = c->n_bytes = 0;
+    c->r_pos.clear(); c->r_meta.clear(); c->r_cig_off.clear(); c->r_cigar.clear(); c->r_base_off.clear(); c->r_seq4.clear(); c->r_qual.clear();
+    c->state = ST_OPEN;
+    return PB_OK;
+}
+
+int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
+    if (!c || !b) return fail(c, PB_ERR_ARG, "pb_push_batch: null argument");
+    if (c->state != ST_OPEN) return fail(c, PB_ERR_STATE, "pb_push_batch outside pb_region_begin .. pb_region_launch");
+    if (b->n_reads < 0 || b->n_cigar < 0 || b->n_bases < 0 || (b->n_bases & 1)) return fail(c, PB_ERR_ARG, "pb_push_batch: bad counts");
+    if (b->n_reads == 0) return PB_OK;
+    if (!b->pos || !b->meta || !b->cig_off || !b->cigar || !b->base_off || !b->seq4 || !b->qual) return fail(c, PB_ERR_ARG, "pb_push_batch: null array");
+    if ((uint64_t)(c->n_cig + b->n_cigar) > 0xfffffff0ULL) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one region");
+    if ((uint64_t)(c->n_reads + b->n_reads) > 0xfffffff0ULL) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^32 reads in one region");
+    if ((uint64_t)(c->n_bytes + b->n_bases) >> 40) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^40 base bytes in one region");
+    PB_CUDA(c, cudaSetDevice(c->prm.device));
+    cudaStream_t st = c->stream;
+    const int64_t N0 = c->n_reads, N1 = N0 + b->n_reads;
+    PB_TRY(dev_reserve(c, c->d_pos, 4 * (size_t)N1, 4 * (size_t)N0));
+    PB_TRY(dev_reserve(c, c->d_meta, 4 * (size_t)N1, 4 * (size_t)N0));
+    PB_TRY(dev_reserve(c, c->d_cigstart, 4 * (size_t)N1, 4 * (size_t)N0));
+    PB_TRY(dev_reserve(c, c->d_ncig, 4 * (size_t)N1, 4 * (size_t)N0));
+    PB_TRY(dev_reserve(c, c->d_base, 8 * (size_t)N1, 8 * (size_t)N0));
+    PB_TRY(dev_reserve(c, c->d_cigar, 4 * (size_t)(c->n_cig + b->n_cigar), 4 * (size_t)c->n_cig));
+    PB_TRY(dev_reserve(c, c->d_qual, (size_t)(c->n_bytes + b->n_bases) + 16, (size_t)c->n_bytes));
+    PB_TRY(dev_reserve(c, c->d_seq4, (size_t)(c->n_bytes + b->n_bases) / 2 + 16, (size_t)c->n_bytes / 2));
+    PB_TRY(dev_reserve(c, c->d_tmp_cig, 4 * (size_t)(b->n_reads + 1)));
+    PB_TRY(dev_reserve(c, c->d_tmp_base, 4 * (size_t)(b->n_reads + 1)));
+    PB_CUDA(c, cudaMemcpyAsync(dp<int32_t>(c->d_pos) + N0, b->pos, 4 * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
+    PB_CUDA(c, cudaMemcpyAsync(dp<uint32_t>(c->d_meta) + N0, b->meta, 4 * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_tmp_cig.p, b->cig_off, 4 * (size_t)(b->n_reads + 1), cudaMemcpyHostToDevice, st));
+    PB_CUDA(c, cudaMemcpyAsync(c->d_tmp_base.p, b->base_off, 4 * (size_t)(b->n_reads + 1), cudaMemcpyHostToDevice, st));
+    if (b->n_cigar) PB_CUDA(c, cudaMemcpyAsync(dp<uint32_t>(c->d_cigar) + c->n_cig, b->cigar, 4 * (size_t)b->n_cigar, cudaMemcpyHostToDevice, st));
+    if (b->n_bases) {
+        PB_CUDA(c, cudaMemcpyAsync(dp<uint8_t>(c->d_qual) + c->n_bytes, b->qual, (size_t)b->n_bases, cudaMemcpyHostToDevice, st));
+        PB_CUDA(c, cudaMemcpyAsync(dp<uint8_t>(c->d_seq4) + c->n_bytes / 2, b->seq4, (size_t)b->n_bases / 2, cudaMemcpyHostToDevice, st));
+    }
+    k_rebase<<<nblk(b->n_reads, 256), 256, 0, st>>>(b->n_reads, N0, dp<uint32_t>(c->d_tmp_cig), dp<uint32_t>(c->d_tmp_base), (uint64_t)c->n_cig,
+                                                   (uint64_t)c->n_bytes, dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint64_t>(c->d_base));
+    c->launches += 1;
+    PB_CUDA(c, cudaGetLastError());
+    // the temporaries are reused by the next push
+    PB_CUDA(c, cudaStreamSynchronize(st));
+    c->n_reads = N1; c->n_cig += b->n_cigar; c->n_bytes += b->n_bases;
+    return PB_OK;
+}
+
+int pb_push_record(pb_ctx *c, const void *core32, const void *data, int32_t l_data, int32_t sample) {
+    if (!c || !core32 || !data) return fail(c, PB_ERR_ARG, "pb_push_record: null argument");
+    if (c->state != ST_OPEN) return fail(c, PB_ERR_STATE, "pb_push_record outside a region");
+    // bam1_core_t (bam.h:178-190): tid, pos, bin:16 qual:8 l_qname:8, flag:16 n_cigar:16, l_qseq, mtid, mpos, isize
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(core32);
+    const int32_t tid = (int32_t)w[0], pos = (int32_t)w[1];
+    const uint32_t mapq = (w[2] >> 8) & 0xff, l_qname = w[2] & 0xff, flag = w[3] >> 16, n_cigar = w[3] & 0xffff;
+    const int32_t l_qseq = (int32_t)w[4];
+    if (l_qseq < 0 || (int64_t)l_qname + 4 * (int64_t)n_cigar + (l_qseq + 1) / 2 + l_qseq > l_data)
+        return fail(c, PB_ERR_ARG, "pb_push_record: record shorter than its core says");
+    if (tid < 0) return PB_OK;                                       // bam_plp_push drops tid < 0 (bam_pileup.c:371)
+    const uint8_t *d = reinterpret_cast<const uint8_t *>(data);
+    const uint8_t *cig = d + l_qname, *seq = cig + 4 * n_cigar, *qual = seq + (l_qseq + 1) / 2;
+    if (c->r_cig_off.empty()) { c->r_cig_off.push_back(0); c->r_base_off.push_back(0); }
+    c->r_pos.push_back(pos);
+    c->r_meta.push_back(flag << 16 | mapq << 8 | (uint32_t)(sample >= 0 && sample < 255 ? sample : PB_NO_SAMPLE));
+    for (uint32_t i = 0; i < n_cigar; ++i) { uint32_t v; memcpy(&v, cig + 4 * i, 4); c->r_cigar.push_back(v); }
+    c->r_cig_off.push_back((uint32_t)c->r_cigar.size());
+    const size_t pad = (size_t)(l_qseq + 1) & ~(size_t)1;
+    c->r_qual.insert(c->r_qual.end(), qual, qual + l_qseq);
+    c->r_qual.resize(c->r_qual.size() + (pad - (size_t)l_qseq), 0);
+    c->r_seq4.insert(c->r_seq4.end(), seq, seq + (l_qseq + 1) / 2);
+    c->r_base_off.push_back((uint32_t)c->r_qual.size());
+    if (c->r_qual.size() > 0x7fffff00u) return flush_records(c);
+    return PB_OK;
+}
+
+int pb_region_launch(pb_ctx *c) {
+    if (!c) return PB_ERR_ARG;
+    if (c->state != ST_OPEN) return fail(c, PB_ERR_STATE, "pb_region_launch without an open region");
+    PB_CUDA(c, cudaSetDevice(c->prm.device));
+    PB_TRY(flush_records(c));
+    c->state = ST_IDLE;
+    PB_TRY(run_pipeline(c));
+    c->state = ST_LAUNCHED;
+    return PB_OK;
+}
+
+int pb_region_relaunch(pb_ctx *c) {
+    if (!c) return PB_ERR_ARG;
+    if (c->state != ST_LAUNCHED && c->state != ST_DONE) return fail(c, PB_ERR_STATE, "pb_region_relaunch without a launched region");
+    PB_CUDA(c, cudaSetDevice(c->prm.device));
+    const int prev = c->state;
+    c->state = ST_IDLE;
+    PB_TRY(run_pipeline(c));
+    c->state = prev == ST_DONE ? ST_LAUNCHED : prev;
+    return PB_OK;
+}
+
+int pb_region_wait(pb_ctx *c, pb_region_result *out) {
+    if (!c) return PB_ERR_ARG;
+    if (c->state != ST_LAUNCHED) return fail(c, PB_ERR_STATE, "pb_region_wait without pb_region_launch");
+    PB_CUDA(c, cudaSetDevice(c->prm.device));
+    PB_TRY(fill_result(c, out));
+    c->state = ST_DONE;
+    return PB_OK;
+}
+
+int pb_region_end(pb_ctx *c, pb_region_result *out) {
+    PB_TRY(pb_region_launch(c));
+    return pb_region_wait(c, out);
+}
+
+void *pb_stream(pb_ctx *c) { return c ? (void *)c->stream : nullptr; }
+int64_t pb_kernel_launches(const pb_ctx *c) { return c ? c->launches : 0; }
+
+int pb_stage_times(const pb_ctx *c, double *ms4) {
+    if (!c || !ms4) return PB_ERR_ARG;
+    ms4[0] = c->ms_prep; ms4[1] = c->ms_pileup; ms4[2] = c->ms_sites; ms4[3] = c->ms_stats;
+    return PB_OK;
+}
+
+const pb_params *pb_ctx_params(const pb_ctx *c) { return c ? &c->prm : nullptr; }
+
+}  // extern "C"
+
+namespace {
+int flush_records(pb_ctx *c) {
+    if (c->r_pos.empty()) return PB_OK;
+    pb_read_batch b;
+    b.n_reads = (int64_t)c->r_pos.size(); b.n_cigar = (int64_t)c->r_cigar.size(); b.n_bases = (int64_t)c->r_qual.size();
+    b.pos = c->r_pos.data(); b.meta = c->r_meta.data(); b.cig_off = c->r_cig_off.data(); b.cigar = c->r_cigar.data();
+    b.base_off = c->r_base_off.data(); b.seq4 = c->r_seq4.data(); b.qual = c->r_qual.data();
+    static const uint32_t zero = 0;
+    if (!b.cigar) b.cigar = &zero;
+    const int rc = pb_push_batch(c, &b);
+    c->r_pos.clear(); c->r_meta.clear(); c->r_cig_off.clear(); c->r_cigar.clear(); c->r_base_off.clear(); c->r_seq4.clear(); c->r_qual.clear();
+    return rc;
+}
+}  // namespace

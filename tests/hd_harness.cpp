@@ -1,0 +1,39 @@
+// hd_harness.cpp -- TEST INFRASTRUCTURE.  Compiles the product's inlinable device functions
+// (popbam_b200/csrc/pb_cell.cuh, pb_walk.cuh) for the host, so that their arithmetic can be checked
+// against the reference's known-answer vectors on a machine without a GPU.  Built by tests only
+// (g++ -ffp-contract=off); never linked into libpopbam_b200.so.
+#include <cstdint>
+#include <cstring>
+#include "../popbam_b200/csrc/pb_cell.cuh"
+#include "../popbam_b200/csrc/pb_walk.cuh"
+
+extern "C" uint64_t hd_call_cell(const double *fk, const double *beta, const double *lhet, const uint16_t *codes, int k, int rmsq,
+                                 int r4) {
+    // level table of the codes present, ascending (what k_level_table builds for a region)
+    uint8_t qrank[64], qval[64];
+    uint64_t present = 0;
+    for (int i = 0; i < k; ++i) {
+        int q = codes[i] >> 5; q = q < 4 ? 4 : q > 63 ? 63 : q;
+        present |= 1ULL << q;
+    }
+    int nl = 0;
+    for (int q = 0; q < 64; ++q) { qrank[q] = (uint8_t)nl; if (present >> q & 1) qval[nl++] = (uint8_t)q; }
+    uint32_t hist[128];
+    memset(hist, 0, sizeof hist);
+    for (int i = 0; i < k; ++i) {
+        int q = codes[i] >> 5; q = q < 4 ? 4 : q > 63 ? 63 : q;
+        hist[qrank[q] * 2 + ((codes[i] >> 4) & 1)] += 1u << (8 * (codes[i] & 3));
+    }
+    double bsum[4] = {0, 0, 0, 0};
+    int c[4] = {0, 0, 0, 0};
+    if (k > 0) {
+        auto take = [&](int lw) -> uint32_t { uint32_t w = hist[lw]; hist[lw] = 0; return w; };
+        pb_walk_hist(take, 2 * nl, qval, k, r4, fk, beta, bsum, c);
+    }
+    return pb_finish_cell(bsum, c, k, rmsq, lhet);
+}
+
+extern "C" int hd_site_logic(uint64_t *cb, int n, int ref, int het_mode, int min_snpQ, int min_rmsQ, int min_depth, int max_depth,
+                             uint64_t *cov, uint64_t *type) {
+    return pb_site_logic(cb, 1, n, ref, het_mode, min_snpQ, min_rmsQ, min_depth, max_depth, cov, type);
+}

@@ -25,51 +25,14 @@ AN = dict(NUCDIV=0x001, SFS=0x002, LD_ZNS=0x004, LD_OMEGA=0x008, LD_WALL=0x010, 
 FLAG = dict(ILLUMINA=0x02, SUBSTITUTE=0x10, HETEROZYGOTE=0x20, OUTGROUP=0x40, EMIT_CB=0x10000)
 
 
-class Params(C.Structure):
-    """pb_params == pbo_params (include/popbam_b200.h, oracle/pb_oracle.h)."""
-    _fields_ = [("n_samples", C.c_int32), ("n_pops", C.c_int32),
-                ("pop_mask", C.c_uint64 * MAXS), ("pop_nsmpl", C.c_uint8 * MAXS),
-                ("min_depth", C.c_int32), ("max_depth", C.c_int32), ("min_rmsQ", C.c_int32),
-                ("min_snpQ", C.c_int32), ("min_mapQ", C.c_int32), ("min_baseQ", C.c_int32),
-                ("flags", C.c_uint32), ("outidx", C.c_int32), ("min_freq", C.c_int32),
-                ("device", C.c_int32)]
-
-
-class Batch(C.Structure):
-    """pb_read_batch == pbo_batch == pbsynth_batch."""
-    _fields_ = [("n_reads", C.c_int64), ("n_cigar", C.c_int64), ("n_bases", C.c_int64),
-                ("pos", C.POINTER(C.c_int32)), ("meta", C.POINTER(C.c_uint32)),
-                ("cig_off", C.POINTER(C.c_uint32)), ("cigar", C.POINTER(C.c_uint32)),
-                ("base_off", C.POINTER(C.c_uint32)), ("seq4", C.POINTER(C.c_uint8)),
-                ("qual", C.POINTER(C.c_uint8))]
+# The C-ABI structures are shared with the product binding (the oracle mirrors their layout on purpose:
+# oracle/pb_oracle.h pbo_params / pbo_batch / pbo_result / pbo_print_opts).
+sys.path.insert(0, str(ROOT))
+from popbam_b200.capi import Batch, Params, PrintOpts, Result  # noqa: E402
 
 
 def _p(t):
     return C.POINTER(t)
-
-
-class Result(C.Structure):
-    """pb_region_result == pbo_result."""
-    _fields_ = [("n_windows", C.c_int32), ("n_pops", C.c_int32), ("n_samples", C.c_int32),
-                ("analyses", C.c_uint32),
-                ("win_beg", _p(C.c_int32)), ("win_end", _p(C.c_int32)), ("num_sites", _p(C.c_int32)),
-                ("segsites", _p(C.c_int32)), ("seg_off", _p(C.c_int64)), ("seg_pos", _p(C.c_uint32)),
-                ("seg_idx", _p(C.c_uint32)), ("seg_type", _p(C.c_uint64)), ("seg_ref", _p(C.c_uint8)),
-                ("seg_cb", _p(C.c_uint64)),
-                ("piw", _p(C.c_double)), ("pib", _p(C.c_double)), ("min_dxy", _p(C.c_uint16)),
-                ("sfs_num_snps", _p(C.c_int32)), ("td", _p(C.c_double)), ("fwh", _p(C.c_double)),
-                ("ld_num_snps", _p(C.c_int32)), ("zns", _p(C.c_double)), ("omegamax", _p(C.c_double)),
-                ("wall_num_snps", _p(C.c_int32)), ("wallb", _p(C.c_double)), ("wallq", _p(C.c_double)),
-                ("ind_div", _p(C.c_uint16)), ("pop_div", _p(C.c_uint16)), ("div_num_snps", _p(C.c_int32)),
-                ("nhaps", _p(C.c_int32)), ("hdiv", _p(C.c_double)), ("ehhs", _p(C.c_double)),
-                ("span_beg", C.c_int32), ("span_end", C.c_int32),
-                ("cb", _p(C.c_uint64)), ("site_type", _p(C.c_uint64)), ("site_flag", _p(C.c_uint8)),
-                ("reads_pushed", C.c_int64), ("reads_used", C.c_int64), ("aligned_bases", C.c_int64)]
-
-
-class PrintOpts(C.Structure):
-    _fields_ = [("chrom", C.c_char_p), ("pop_names", _p(C.c_char_p)), ("sample_names", _p(C.c_char_p)),
-                ("min_sites", C.c_int32), ("min_snps", C.c_int32), ("jc", C.c_int32), ("snp_output", C.c_int32)]
 
 
 class SynthParams(C.Structure):
