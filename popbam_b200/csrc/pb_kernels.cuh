@@ -19,10 +19,12 @@
 #include "pb_cell.cuh"
 #include "pb_walk.cuh"
 
-#define PB_REC_SIMPLE 0x200u      // single M/=/X op: qpos = p - pos
-#define PB_REC_CAP 512            // read records staged per chunk in the hot kernel
+#define PB_REC_DEAD 0x200u        // read fails min_mapQ: it only counts towards the raw-depth cap
+#define PB_REC_CAP 1024           // segment records staged per round in the hot kernel
 #define PB_PART_CHUNK 2048        // reads per warp in the sample partition
 #define PB_KEY_DROP 0xffu
+#define PB_CODE_NONE 0xffu        // base filtered out (quality, N)
+#define PB_MAX_SEGS 255           // aligned segments (M/=/X ops) per read
 
 struct PbCounters {               // device-side region counters (one cudaMemcpy back)
     unsigned long long reads_used;
@@ -32,7 +34,7 @@ struct PbCounters {               // device-side region counters (one cudaMemcpy
     int max_span;                     // max reference span of a kept read
     int unsorted;                     // pos[r] < pos[r-1] seen (bam_pileup.c:384-395)
     int n_levels;
-    int bad_sample;
+    int too_long;                     // a read spans >= 65536 reference bases or has > 255 aligned segments
     unsigned char qrank[64];          // quality value -> level
     unsigned char qval[64];           // level -> quality value (ascending)
 };
@@ -49,36 +51,38 @@ __global__ void k_rebase(int64_t n, int64_t r0, const uint32_t *__restrict__ cig
 }
 
 // bam_plp_push (bam_pileup.c:371-374): drop flag & 0x704; bam_calend (bam.c:20-70): reference end.
+// Also counts the read's aligned segments (M/=/X ops): each becomes one record of the hot kernel.
 __global__ void k_read_prep(int64_t n, const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta,
                             const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
-                            const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ, int32_t *__restrict__ rend,
-                            uint8_t *__restrict__ rkey, uint8_t *__restrict__ rsimple, PbCounters *__restrict__ ctr) {
+                            const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ, uint8_t *__restrict__ rkey,
+                            uint8_t *__restrict__ rnseg, PbCounters *__restrict__ ctr) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long used = 0, aligned = 0, mqmask = 0;
-    int span = 0, unsorted = 0;
+    int span = 0, flags = 0;     // flags: 1 unsorted, 2 too long
     if (r < n) {
         const uint32_t m = meta[r];
         const int p = pos[r];
         const uint32_t c0 = cigstart[r], nc = ncig[r];
-        int x = p, al = 0;
+        int x = p, al = 0, nseg = 0;
+        bool longseg = false;
         for (uint32_t i = 0; i < nc; ++i) {
             const uint32_t c = __ldg(cigar + c0 + i);
             const int op = c & 15, len = (int)(c >> 4);
-            if (op == 0 || op == 7 || op == 8) { x += len; al += len; }
+            if (op == 0 || op == 7 || op == 8) { x += len; al += len; nseg += len > 0; longseg |= len > 65535; }
             else if (op == 2 || op == 3) x += len;
         }
         const bool keep = !((m >> 16) & 0x704u) && x > p;
-        rend[r] = x;
         const uint32_t smp = m & 0xffu;
-        rkey[r] = (keep && smp < (uint32_t)n_samples) ? (uint8_t)smp : (uint8_t)PB_KEY_DROP;
-        const uint32_t op0 = nc == 1 ? (__ldg(cigar + c0) & 15u) : 1u;
-        rsimple[r] = (nc == 1 && (op0 == 0 || op0 == 7 || op0 == 8)) ? 1 : 0;
+        const bool listed = keep && smp < (uint32_t)n_samples;
+        rkey[r] = listed ? (uint8_t)smp : (uint8_t)PB_KEY_DROP;
+        if (listed && (longseg || x - p > 65535 || nseg > PB_MAX_SEGS)) flags |= 2;
+        rnseg[r] = (uint8_t)(nseg > PB_MAX_SEGS ? PB_MAX_SEGS : nseg);
         if (keep) {
             used = 1; aligned = (unsigned long long)al; span = x - p;
             const int mq = (int)((m >> 8) & 0xff);
             if (mq >= min_mapQ) mqmask = 1ULL << (mq > 63 ? 63 : mq);
         }
-        if (r > 0 && p < pos[r - 1]) unsorted = 1;
+        if (r > 0 && p < pos[r - 1]) flags |= 1;
     }
     // warp-aggregate, then one atomic per warp
     for (int o = 16; o > 0; o >>= 1) {
@@ -86,14 +90,15 @@ __global__ void k_read_prep(int64_t n, const int32_t *__restrict__ pos, const ui
         aligned += __shfl_xor_sync(0xffffffffu, aligned, o);
         mqmask |= __shfl_xor_sync(0xffffffffu, mqmask, o);
         span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
-        unsorted |= __shfl_xor_sync(0xffffffffu, unsorted, o);
+        flags |= __shfl_xor_sync(0xffffffffu, flags, o);
     }
     if ((threadIdx.x & 31) == 0) {
         if (used) atomicAdd(&ctr->reads_used, used);
         if (aligned) atomicAdd(&ctr->aligned_bases, aligned);
         if (mqmask) atomicOr(&ctr->mapq_mask, mqmask);
         if (span) atomicMax(&ctr->max_span, span);
-        if (unsorted) atomicOr(&ctr->unsorted, 1);
+        if (flags & 1) atomicOr(&ctr->unsorted, 1);
+        if (flags & 2) atomicOr(&ctr->too_long, 1);
     }
 }
 
@@ -148,12 +153,46 @@ __global__ void k_level_table(PbCounters *ctr) {
     ctr->n_levels = nl;
 }
 
+// The base filter and code of call_base (popbam.cpp:268-284), once per base instead of once per
+// (base, covering position... which is the same thing) but OUTSIDE the latency-bound pileup loop:
+//   code = level(clamp(min(baseQ', mapQ), 4, 63)) << 2 | nt4      or PB_CODE_NONE when the base is dropped
+// (baseQ' < min_baseQ, or not A/C/G/T).  One warp per read, lanes stride over the read's bases.  Reads
+// that are dropped or fail min_mapQ are skipped: the pileup never looks at their codes.
+__global__ void k_encode(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
+                         const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4, const uint8_t *__restrict__ qual,
+                         int64_t n_bytes, int illumina, int min_baseQ, int min_mapQ, const PbCounters *__restrict__ ctr,
+                         uint8_t *__restrict__ codes) {
+    __shared__ uint8_t qrank_s[64];
+    if (threadIdx.x < 64) qrank_s[threadIdx.x] = ctr->qrank[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        if (rkey[r] == PB_KEY_DROP) continue;
+        const int mapq = (int)((meta[r] >> 8) & 0xff);
+        if (mapq < min_mapQ) continue;
+        const uint64_t b0 = base[r];
+        const uint64_t b1 = r + 1 < n ? base[r + 1] : (uint64_t)n_bytes;     // reads are laid out back to back
+        const int len = (int)min((uint64_t)1 << 20, b1 - b0);
+        for (int y = lane; y < len; y += 32) {
+            int bq = (int)__ldg(qual + b0 + y);
+            if (illumina) bq = bq > 31 ? bq - 31 : 0;
+            const uint32_t sb = __ldg(seq4 + (b0 >> 1) + (y >> 1));
+            const uint32_t nib = (sb >> ((~y & 1) << 2)) & 0xfu;
+            const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+            int qq = min(bq, mapq);
+            qq = max(4, min(63, qq));
+            codes[b0 + y] = (bq < min_baseQ || b4 > 3) ? (uint8_t)PB_CODE_NONE : (uint8_t)(qrank_s[qq] << 2 | b4);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
-// Stable partition of the kept reads by sample.  One warp owns PB_PART_CHUNK consecutive reads, so
-// the order inside a (chunk, sample) bucket is file order; buckets are laid out sample-major,
-// chunk-minor by an exclusive scan of the count matrix.
-__global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, int n_samples, int64_t n_chunks,
-                             uint32_t *__restrict__ counts /* [n_samples][n_chunks] */) {
+// Stable partition of the kept reads by sample, expanding every read into its aligned segments.
+// One warp owns PB_PART_CHUNK consecutive reads, so the order inside a (chunk, sample) bucket is file
+// order; buckets are laid out sample-major, chunk-minor by an exclusive scan of the count matrix.
+__global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg, int n_samples,
+                             int64_t n_chunks, uint32_t *__restrict__ counts /* [n_samples][n_chunks] */) {
     const int lane = threadIdx.x & 31;
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk >= n_chunks) return;
@@ -162,22 +201,29 @@ __global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, int n_
     for (int i = 0; i < PB_PART_CHUNK; i += 32) {
         const int64_t r = r0 + i + lane;
         const uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
-        // every lane counts the keys equal to its own two samples
+        const uint32_t ns = r < n ? rnseg[r] : 0;
+        // every lane sums the segment counts of the reads of its own two samples
         for (int src = 0; src < 32; ++src) {
             const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
-            c0 += kk == (uint32_t)lane;
-            c1 += kk == (uint32_t)(lane + 32);
+            const uint32_t nn = __shfl_sync(0xffffffffu, ns, src);
+            c0 += kk == (uint32_t)lane ? nn : 0;
+            c1 += kk == (uint32_t)(lane + 32) ? nn : 0;
         }
     }
     if (lane < n_samples) counts[(int64_t)lane * n_chunks + chunk] = c0;
     if (lane + 32 < n_samples) counts[(int64_t)(lane + 32) * n_chunks + chunk] = c1;
 }
 
-__global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, int n_samples, int64_t n_chunks,
-                               const uint32_t *__restrict__ offs /* scanned counts */, const int32_t *__restrict__ pos,
-                               const int32_t *__restrict__ rend, const uint32_t *__restrict__ meta,
-                               const uint64_t *__restrict__ base, const uint8_t *__restrict__ rsimple,
-                               int4 *__restrict__ srec, uint32_t *__restrict__ sorig) {
+// Segment record (16 bytes):
+//   x  read start (sort key of the list; all segments of a read carry it)
+//   y  (segment start - read start) | segment length << 16         (both < 65536)
+//   z  low 32 bits of the byte offset of the segment's first base in qual[] / codes[]
+//   w  mapq | strand<<8 | dead<<9 | (offset bits 32..39)<<24
+__global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg, int n_samples,
+                               int64_t n_chunks, const uint32_t *__restrict__ offs /* scanned counts */,
+                               const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta, const uint64_t *__restrict__ base,
+                               const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
+                               const uint32_t *__restrict__ cigar, int min_mapQ, int4 *__restrict__ srec) {
     const int lane = threadIdx.x & 31;
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk >= n_chunks) return;
@@ -187,30 +233,46 @@ __global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, int 
     for (int i = 0; i < PB_PART_CHUNK; i += 32) {
         const int64_t r = r0 + i + lane;
         const uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
-        const uint32_t peers = __match_any_sync(0xffffffffu, key);
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        // cursor of my key lives in lane (key & 31), register cur0 or cur1
-        const uint32_t c0 = __shfl_sync(0xffffffffu, cur0, key & 31);
-        const uint32_t c1 = __shfl_sync(0xffffffffu, cur1, key & 31);
-        if (key != PB_KEY_DROP) {
-            const uint32_t dst = (key < 32 ? c0 : c1) + rank;
-            const uint32_t m = meta[r];
-            const uint64_t b = base[r];
-            // record: pos, end, low 32 bits of the byte offset of the read's first quality,
-            //         mapq | strand<<8 | simple<<9 | (offset bits 32..39)<<24
-            int4 rec;
-            rec.x = pos[r]; rec.y = rend[r]; rec.z = (int)(uint32_t)b;
-            rec.w = (int)(((m >> 8) & 0xffu) | (((m >> 20) & 1u) << 8) | (rsimple[r] ? PB_REC_SIMPLE : 0u) |
-                          ((uint32_t)(b >> 32) << 24));
-            srec[dst] = rec;
-            sorig[dst] = (uint32_t)r;
-        }
-        // advance the cursors: lane L counts the reads of samples L and L+32 in this step
-        uint32_t a0 = 0, a1 = 0;
+        const uint32_t ns = r < n ? rnseg[r] : 0;
+        // my rank: segments of earlier lanes with my key; cursor advance: segments per sample in this step
+        uint32_t rank = 0, a0 = 0, a1 = 0;
         for (int src = 0; src < 32; ++src) {
             const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
-            a0 += kk == (uint32_t)lane;
-            a1 += kk == (uint32_t)(lane + 32);
+            const uint32_t nn = __shfl_sync(0xffffffffu, ns, src);
+            rank += (kk == key && src < lane) ? nn : 0;
+            a0 += kk == (uint32_t)lane ? nn : 0;
+            a1 += kk == (uint32_t)(lane + 32) ? nn : 0;
+        }
+        const uint32_t c0 = __shfl_sync(0xffffffffu, cur0, key & 31);
+        const uint32_t c1 = __shfl_sync(0xffffffffu, cur1, key & 31);
+        if (key != PB_KEY_DROP && ns) {
+            uint32_t dst = (key < 32 ? c0 : c1) + rank;
+            const uint32_t m = meta[r];
+            const int p = pos[r];
+            const uint32_t mapq = (m >> 8) & 0xffu;
+            const uint32_t wlo = mapq | (((m >> 20) & 1u) << 8) | ((int)mapq < min_mapQ ? PB_REC_DEAD : 0u);
+            const uint64_t b = base[r];
+            const uint32_t cs = cigstart[r], nc = ncig[r];
+            int x = p, y = 0;
+            uint32_t emitted = 0;
+            for (uint32_t ci = 0; ci < nc && emitted < ns; ++ci) {
+                const uint32_t c = __ldg(cigar + cs + ci);
+                const int op = c & 15, len = (int)(c >> 4);
+                if (op == 0 || op == 7 || op == 8) {
+                    if (len > 0) {
+                        const uint64_t sb = b + (uint64_t)y;
+                        int4 rec;
+                        rec.x = p;
+                        rec.y = (int)(((uint32_t)(x - p) & 0xffffu) | ((uint32_t)len << 16));
+                        rec.z = (int)(uint32_t)sb;
+                        rec.w = (int)(wlo | ((uint32_t)(sb >> 32) << 24));
+                        srec[dst++] = rec;
+                        ++emitted;
+                    }
+                    x += len; y += len;
+                } else if (op == 2 || op == 3) x += len;
+                else if (op == 1 || op == 4) y += len;
+            }
         }
         cur0 += a0; cur1 += a1;
     }
@@ -279,39 +341,19 @@ __global__ void k_sample_starts(const uint32_t *__restrict__ offs, int n_samples
 }
 
 // ------------------------------------------------------------------------------------------------
-// CIGAR cursor for reads that are not a single match op (resolve_cigar2, bam_pileup.c:90-221):
-// query offset of reference position p, or -1 when p falls in a deletion / reference skip.
-__device__ __forceinline__ int pb_resolve(const uint32_t *__restrict__ cig, uint32_t nc, int pos, int p) {
-    int x = pos, y = 0;
-    for (uint32_t i = 0; i < nc; ++i) {
-        const uint32_t c = __ldg(cig + i);
-        const int op = c & 15, len = (int)(c >> 4);
-        if (op == 0 || op == 7 || op == 8) {
-            if (p < x + len) return p >= x ? y + (p - x) : -1;
-            x += len; y += len;
-        } else if (op == 2 || op == 3) {
-            if (p < x + len) return -1;
-            x += len;
-        } else if (op == 1 || op == 4) y += len;
-    }
-    return -1;
-}
-
 struct PbPileArgs {
-    // reads, partitioned by sample (file order inside a sample)
+    // aligned segments of the kept reads, partitioned by sample (file order inside a sample)
     const int4 *srec;
-    const uint32_t *sorig;
     const uint32_t *sstart;         // [n_samples+1]
-    const uint32_t *cigstart, *ncig, *cigar;
-    const uint8_t *seq4, *qual;
+    const uint8_t *codes;           // per-base code (k_encode), same offsets as qual[]
     const char *ref;
     int64_t ref_len;
     int span_beg, span_end;
     const int32_t *win_beg, *win_end;
     int n_windows;
     int n_samples;
-    int min_depth, max_depth, min_rmsQ, min_snpQ, min_mapQ, min_baseQ;
-    int illumina, het_mode;
+    int min_depth, max_depth, min_rmsQ, min_snpQ;
+    int het_mode;
     const double *fk, *beta, *lhet;
     const PbCounters *ctr;          // max_span, level table
     uint64_t *site_type;            // [span]
@@ -321,16 +363,25 @@ struct PbPileArgs {
 
 // Dynamic shared memory of k_pileup_call<TP> for n samples and nl quality levels.
 static inline size_t pb_pile_smem(int tp, int n, int nl) {
-    return (size_t)tp * n * 8 + (size_t)PB_REC_CAP * 16 + (size_t)PB_REC_CAP * 4 + (size_t)2 * nl * tp * 4 + 256 * 8 + 128 * 4 + 128;
+    return (size_t)tp * n * 8 + (size_t)PB_REC_CAP * 16 + (size_t)2 * nl * tp * 4 + 256 * 8 + 128 * 4 + 64 + 64 * 16 + 64;
 }
 
-// One CTA = TP consecutive reference positions x all samples.  For each sample the CTA stages the
-// sample's candidate read records in shared memory; each thread (one position) then walks the reads
-// covering its position in file order, expands the CIGAR to a query offset, applies the depth cap and
-// the base filters (call_base), accumulates the (quality level, strand, base) histogram of its cell in
-// its private shared-memory column, and runs the error model on it.  The n consensus words of the
-// position stay in shared memory for the per-site logic, so nothing per (site, sample) goes to HBM
-// unless the caller asked for the cb words.
+// One CTA = TP consecutive reference positions x all samples; one thread = one position.
+//
+// Rounds: the CTA stages, for as many consecutive samples as fit, the candidate segment records
+// (reads starting in (p0 - max_span, p0 + TP)) in shared memory.  For each staged sample a thread
+// binary-searches its first candidate and walks the records that can cover its position IN FILE
+// ORDER: coverage is one unsigned compare (p - seg_start < seg_len), the raw-depth cap is applied
+// before the base filter as in call_base (popbam.cpp:242-248), and the base's pre-digested code
+// (k_encode) is one byte load whose address is consecutive across the lanes of a warp.  Passing bases
+// are counted in the thread's private (level, strand) x base histogram in shared memory (plain
+// read-modify-write, no atomics).  After the last record of a sample the thread runs the error model
+// on the histogram (pb_walk_hist) and leaves the consensus word in shared memory; after the last
+// sample it runs the per-site logic on its n words and writes 9 bytes.
+//
+// Cells whose bases all agree (the overwhelming majority) take an exact shortcut: the best genotype is
+// the homozygote with likelihood 0, the runner-up is min(het term, float(bsum)), and bsum only
+// grows, so the walk stops as soon as its partial sum reaches the het term (see pb_unanimous_exit).
 template <int TP>
 __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -339,12 +390,12 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     const int n_lw = 2 * nl;
     uint64_t *cbs = reinterpret_cast<uint64_t *>(smem_raw);                 // [TP][n]
     int4 *recs = reinterpret_cast<int4 *>(cbs + (size_t)TP * n);            // [PB_REC_CAP]
-    uint32_t *rorig = reinterpret_cast<uint32_t *>(recs + PB_REC_CAP);      // [PB_REC_CAP]
-    uint32_t *hist = rorig + PB_REC_CAP;                                    // [n_lw][TP]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(recs + PB_REC_CAP);       // [n_lw][TP]
     double *fk_s = reinterpret_cast<double *>(hist + (size_t)n_lw * TP);    // [256]
     uint32_t *rng = reinterpret_cast<uint32_t *>(fk_s + 256);               // lo[64], hi[64]
-    uint8_t *qrank_s = reinterpret_cast<uint8_t *>(rng + 128);              // [64]
-    uint8_t *qval_s = qrank_s + 64;                                         // [64]
+    uint8_t *qval_s = reinterpret_cast<uint8_t *>(rng + 128);               // [64]
+    int4 *plan = reinterpret_cast<int4 *>(qval_s + 64);                     // [64] {sample, src, count | last<<31, dst}
+    uint32_t *plan_n = reinterpret_cast<uint32_t *>(plan + 64);             // [0] entries, [1] next sample, [2] next src
 
     const int tid = threadIdx.x;
     const int p0 = a.span_beg + (int)blockIdx.x * TP;
@@ -354,82 +405,97 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     const int max_span = a.ctr->max_span;
 
     for (int i = tid; i < 256; i += TP) fk_s[i] = a.fk[i];
-    if (tid < 64) { qrank_s[tid] = a.ctr->qrank[tid]; qval_s[tid] = a.ctr->qval[tid]; }
+    if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
     for (int lw = 0; lw < n_lw; ++lw) hist[lw * TP + tid] = 0;
     if (tid < n) {
-        // candidate reads of sample tid: pos in (p0 - max_span, p_end)
+        // candidate records of sample tid: read start in (p0 - max_span, p_end)
         const uint32_t s0 = a.sstart[tid], s1 = a.sstart[tid + 1];
         uint32_t lo = s0, hi = s1;
-        const int t_lo = p0 - max_span;       // first with pos > t_lo
+        const int t_lo = p0 - max_span;       // first with start > t_lo
         while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a.srec[mid].x > t_lo) hi = mid; else lo = mid + 1; }
         rng[tid] = lo;
         hi = s1;
-        uint32_t l2 = lo;                     // first with pos >= p_end
+        uint32_t l2 = lo;                     // first with start >= p_end
         while (l2 < hi) { const uint32_t mid = (l2 + hi) >> 1; if (a.srec[mid].x >= p_end) hi = mid; else l2 = mid + 1; }
         rng[64 + tid] = l2;
     }
     __syncthreads();
+    if (tid == 0) { plan_n[1] = 0; plan_n[2] = rng[0]; }
 
     const int ref_c = (valid && p >= 0 && p < a.ref_len) ? (int)(unsigned char)a.ref[p] : 'N';
     const int r4 = pb_iupac_rev(ref_c) & 3;
 
-    for (int s = 0; s < n; ++s) {
-        const uint32_t lo = rng[s], hi = rng[64 + s];
-        int depth = 0, k = 0, rmsq = 0;
-        for (uint32_t c0 = lo; c0 < hi; c0 += PB_REC_CAP) {
-            const int cnt = (int)min((uint32_t)PB_REC_CAP, hi - c0);
-            __syncthreads();
-            for (int i = tid; i < cnt; i += TP) { recs[i] = a.srec[c0 + i]; rorig[i] = a.sorig[c0 + i]; }
-            __syncthreads();
-            if (!valid) continue;
-            int j = 0, jh = cnt;
-            const int thr = p - max_span;     // reads with pos <= thr end at or before p
-            while (j < jh) { const int mid = (j + jh) >> 1; if (recs[mid].x > thr) jh = mid; else j = mid + 1; }
-            for (; j < cnt; ++j) {
-                const int4 r = recs[j];
-                if (r.x > p) break;
-                if (r.y <= p) continue;
-                int qpos;
-                if ((uint32_t)r.w & PB_REC_SIMPLE) qpos = p - r.x;
-                else {
-                    const uint32_t o = rorig[j];
-                    qpos = pb_resolve(a.cigar + a.cigstart[o], a.ncig[o], r.x, p);
-                    if (qpos < 0) continue;                       // is_del / is_refskip (popbam.cpp:222)
+    int depth = 0, k = 0, rmsq = 0;
+    uint32_t bmask = 0;          // which bases occur in the cell
+    for (;;) {
+        // ---- plan one round: consecutive samples (or a piece of one) whose records fit the staging area
+        __syncthreads();         // everybody is done with the previous round's plan and records
+        if (tid == 0) {
+            int s = (int)plan_n[1], ne = 0, fill = 0;
+            uint32_t src = plan_n[2];
+            while (s < n && ne < 64) {
+                const uint32_t hi = rng[64 + s];
+                const int want = (int)(hi - src), room = PB_REC_CAP - fill;
+                if (want > room && fill > 0) break;                 // start the big one in a fresh round
+                const int take = min(want, room);
+                const bool last = take == want;
+                plan[ne++] = make_int4(s, (int)src, take | (last ? (int)0x80000000u : 0), fill);
+                fill += take;
+                if (last) { ++s; src = s < n ? rng[s] : 0; } else { src += take; break; }
+            }
+            plan_n[0] = (uint32_t)ne; plan_n[1] = (uint32_t)s; plan_n[2] = src;
+        }
+        __syncthreads();
+        const int ne = (int)plan_n[0];
+        if (ne == 0) break;
+        for (int e = 0; e < ne; ++e) {
+            const int4 pl = plan[e];
+            const int cnt = pl.z & 0x7fffffff;
+            for (int i = tid; i < cnt; i += TP) recs[pl.w + i] = a.srec[(uint32_t)pl.y + i];
+        }
+        __syncthreads();
+        for (int e = 0; e < ne; ++e) {
+            const int4 pl = plan[e];
+            const int cnt = pl.z & 0x7fffffff;
+            const int4 *rs = recs + pl.w;
+            if (valid) {
+                int j = 0, jh = cnt;
+                const int thr = p - max_span;     // reads starting at or before thr end at or before p
+                while (j < jh) { const int mid = (j + jh) >> 1; if (rs[mid].x > thr) jh = mid; else j = mid + 1; }
+                for (; j < cnt; ++j) {
+                    const int4 r = rs[j];
+                    if (r.x > p) break;
+                    const uint32_t u = (uint32_t)(p - r.x) - ((uint32_t)r.y & 0xffffu);
+                    if (u >= ((uint32_t)r.y >> 16)) continue;          // not in this aligned segment (or is_del / ref-skip)
+                    if (depth >= a.max_depth) continue;                // cap precedes the filters (popbam.cpp:242-248)
+                    ++depth;
+                    if ((uint32_t)r.w & PB_REC_DEAD) continue;         // mapQ < min_mapQ
+                    const uint64_t boff = ((uint64_t)((uint32_t)r.w >> 24) << 32) | (uint32_t)r.z;
+                    const uint32_t code = __ldg(a.codes + boff + u);
+                    if (code == PB_CODE_NONE) continue;
+                    const int lw = (int)(code >> 2) * 2 + ((r.w >> 8) & 1);
+                    const int b4 = (int)(code & 3u);
+                    hist[lw * TP + tid] += 1u << (8 * b4);
+                    bmask |= 1u << b4;
+                    ++k;
+                    const int mapq = r.w & 0xff;
+                    rmsq += mapq * mapq;
                 }
-                if (depth >= a.max_depth) continue;               // cap precedes the filters (popbam.cpp:242-248)
-                ++depth;
-                const uint64_t boff = ((uint64_t)((uint32_t)r.w >> 24) << 32) | (uint32_t)r.z;
-                int bq = (int)__ldg(a.qual + boff + (uint32_t)qpos);
-                if (a.illumina) bq = bq > 31 ? bq - 31 : 0;
-                const int mapq = r.w & 0xff;
-                if (bq < a.min_baseQ || mapq < a.min_mapQ) continue;
-                const uint32_t sb = __ldg(a.seq4 + (boff >> 1) + ((uint32_t)qpos >> 1));
-                const uint32_t nib = (sb >> ((~qpos & 1) << 2)) & 0xfu;
-                const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
-                if (b4 > 3) continue;
-                int qq = min(bq, mapq);
-                qq = max(4, min(63, qq));
-                const int lw = qrank_s[qq] * 2 + ((r.w >> 8) & 1);
-                hist[lw * TP + tid] += 1u << (8 * b4);
-                ++k;
-                rmsq += mapq * mapq;
+            }
+            if (pl.z < 0) {      // last piece of this sample: call the cell
+                uint64_t cb = 0;
+                if (depth > 0) {
+                    auto take = [&](int lw) -> uint32_t {
+                        const uint32_t w = hist[lw * TP + tid];
+                        if (w) hist[lw * TP + tid] = 0;
+                        return w;
+                    };
+                    cb = pb_call_from_hist(take, n_lw, qval_s, k, rmsq, bmask, r4, fk_s, a.beta, a.lhet);
+                }
+                cbs[(size_t)tid * n + pl.x] = cb;
+                depth = 0; k = 0; rmsq = 0; bmask = 0;
             }
         }
-        uint64_t cb = 0;
-        if (depth > 0) {
-            double bsum[4] = {0.0, 0.0, 0.0, 0.0};
-            int c[4] = {0, 0, 0, 0};
-            if (k > 0) {
-                auto take = [&](int lw) -> uint32_t {
-                    const uint32_t w = hist[lw * TP + tid];
-                    if (w) hist[lw * TP + tid] = 0;
-                    return w;
-                };
-                pb_walk_hist(take, n_lw, qval_s, k, r4, fk_s, a.beta, bsum, c);
-            }
-            cb = pb_finish_cell(bsum, c, k, rmsq, a.lhet);
-        }
-        cbs[(size_t)tid * n + s] = cb;
     }
 
     // per-site logic (make_X, pop_nucdiv.cpp:148-197) on the n words of this thread's position

@@ -53,7 +53,7 @@ struct pb_ctx {
     int64_t n_reads = 0, n_cig = 0, n_bytes = 0;
     DevBuf d_pos, d_meta, d_cigstart, d_ncig, d_base, d_cigar, d_seq4, d_qual, d_tmp_cig, d_tmp_base;
     // derived
-    DevBuf d_rend, d_rkey, d_rsimple, d_counts, d_blocktot, d_srec, d_sorig, d_sstart, d_ctr;
+    DevBuf d_rkey, d_rnseg, d_codes, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
     DevBuf d_num_sites, d_segsites, d_seg_off, d_seg_pos, d_seg_idx, d_seg_type, d_seg_ref, d_seg_cb;
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wr, d_wall_u, d_stats;
@@ -200,34 +200,40 @@ int run_pipeline(pb_ctx *c) {
     // ---- per-read preparation, quality levels, partition by sample
     PB_TRY(dev_reserve(c, c->d_ctr, sizeof(PbCounters)));
     PB_CUDA(c, cudaMemsetAsync(c->d_ctr.p, 0, sizeof(PbCounters), st));
-    PB_TRY(dev_reserve(c, c->d_rend, sizeof(int32_t) * (size_t)std::max<int64_t>(N, 1)));
     PB_TRY(dev_reserve(c, c->d_rkey, (size_t)std::max<int64_t>(N, 1)));
-    PB_TRY(dev_reserve(c, c->d_rsimple, (size_t)std::max<int64_t>(N, 1)));
-    PB_TRY(dev_reserve(c, c->d_srec, sizeof(int4) * (size_t)std::max<int64_t>(N, 1)));
-    PB_TRY(dev_reserve(c, c->d_sorig, sizeof(uint32_t) * (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_rnseg, (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_codes, (size_t)std::max<int64_t>(c->n_bytes, 1)));
+    PB_TRY(dev_reserve(c, c->d_srec, sizeof(int4) * (size_t)std::max<int64_t>(c->n_cig, 1)));   // one record per M/=/X op at most
     PB_TRY(dev_reserve(c, c->d_sstart, sizeof(uint32_t) * (PB_MAX_SAMPLES + 1)));
     const int64_t n_chunks = std::max<int64_t>(1, (N + PB_PART_CHUNK - 1) / PB_PART_CHUNK);
     const int64_t n_counts = (int64_t)n * n_chunks + 1;
     PB_TRY(dev_reserve(c, c->d_counts, sizeof(uint32_t) * (size_t)n_counts));
     PbCounters *ctr = dp<PbCounters>(c->d_ctr);
+    const int illumina = (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0;
     if (N > 0) {
         k_read_prep<<<nblk(N, 256), 256, 0, st>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
                                                  dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), n, P.min_mapQ,
-                                                 dp<int32_t>(c->d_rend), dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rsimple), ctr);
-        k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0,
-                                                 P.min_baseQ, ctr);
+                                                 dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), ctr);
+        k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
         c->launches += 2;
     }
     k_level_table<<<1, 32, 0, st>>>(ctr);
+    if (N > 0) {
+        k_encode<<<c->n_sms * 16, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
+                                               dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ,
+                                               P.min_mapQ, ctr, dp<uint8_t>(c->d_codes));
+        c->launches += 1;
+    }
     PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
     const unsigned part_blocks = nblk(n_chunks * 32, 128);
-    k_part_count<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), n, n_chunks, dp<uint32_t>(c->d_counts));
+    k_part_count<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts));
     c->launches += 2;
     PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts));
     k_sample_starts<<<1, 128, 0, st>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart));
-    k_part_scatter<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), n, n_chunks, dp<uint32_t>(c->d_counts), dp<int32_t>(c->d_pos),
-                                               dp<int32_t>(c->d_rend), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
-                                               dp<uint8_t>(c->d_rsimple), dp<int4>(c->d_srec), dp<uint32_t>(c->d_sorig));
+    k_part_scatter<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts),
+                                               dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
+                                               dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ,
+                                               dp<int4>(c->d_srec));
     c->launches += 2;
     PB_CUDA(c, cudaGetLastError());
     PB_TRY(host_reserve(c, c->h_ctr, sizeof(PbCounters)));
@@ -236,6 +242,7 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaStreamSynchronize(st));
     c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
     if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
+    if (c->ctr_host.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
 
     // ---- the hot kernel
     PB_TRY(dev_reserve(c, c->d_site_type, sizeof(uint64_t) * (size_t)span));
@@ -246,16 +253,14 @@ int run_pipeline(pb_ctx *c) {
     if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d samples x %d quality levels exceeds %zu bytes", n, nl, c->smem_optin);
     PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PbPileArgs pa;
-    pa.srec = dp<int4>(c->d_srec); pa.sorig = dp<uint32_t>(c->d_sorig); pa.sstart = dp<uint32_t>(c->d_sstart);
-    pa.cigstart = dp<uint32_t>(c->d_cigstart); pa.ncig = dp<uint32_t>(c->d_ncig); pa.cigar = dp<uint32_t>(c->d_cigar);
-    pa.seq4 = dp<uint8_t>(c->d_seq4); pa.qual = dp<uint8_t>(c->d_qual);
+    pa.srec = dp<int4>(c->d_srec); pa.sstart = dp<uint32_t>(c->d_sstart);
+    pa.codes = dp<uint8_t>(c->d_codes);
     pa.ref = dp<char>(c->d_ref); pa.ref_len = c->ref_len;
     pa.span_beg = c->span_beg; pa.span_end = c->span_end;
     pa.win_beg = dp<int32_t>(c->d_wbeg); pa.win_end = dp<int32_t>(c->d_wend); pa.n_windows = NW;
     pa.n_samples = n;
     pa.min_depth = P.min_depth; pa.max_depth = P.max_depth; pa.min_rmsQ = P.min_rmsQ; pa.min_snpQ = P.min_snpQ;
-    pa.min_mapQ = P.min_mapQ; pa.min_baseQ = P.min_baseQ;
-    pa.illumina = (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0; pa.het_mode = (P.flags & PB_FLAG_HETEROZYGOTE) ? 1 : 0;
+    pa.het_mode = (P.flags & PB_FLAG_HETEROZYGOTE) ? 1 : 0;
     pa.fk = dp<double>(c->d_fk); pa.beta = dp<double>(c->d_beta); pa.lhet = dp<double>(c->d_lhet);
     pa.ctr = ctr;
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
@@ -465,8 +470,8 @@ void pb_destroy(pb_ctx *c) {
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
-                      &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rend,
-                      &c->d_rkey, &c->d_rsimple, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sorig, &c->d_sstart, &c->d_ctr,
+                      &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rnseg,
+                      &c->d_rkey, &c->d_codes, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
                       &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
                       &c->d_seg_idx, &c->d_seg_type, &c->d_seg_ref, &c->d_seg_cb, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
                       &c->d_rsum, &c->d_wr, &c->d_wall_u, &c->d_stats};

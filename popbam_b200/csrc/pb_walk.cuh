@@ -57,3 +57,77 @@ PB_HD void pb_walk_hist(Hist &take, int n_lw, const uint8_t *qval, int k, int r4
         c[b] = j == 0 ? cc0 : j == 1 ? cc1 : j == 2 ? cc2 : cc3;
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Cells whose bases all agree (one base b, count k).  Then errmod_cal's sums are bsum[b] = B > 0 and
+// 0 for the other bases, and its ten likelihoods (pop_utils.cpp:316-362) are
+//     (b,b)                      : 0                       (no other base present -> q stays 0)
+//     (j,b) j<b   /  (b,m) m>b   : float(-4.343*lhet[k<<8|k])  /  float(-4.343*lhet[k<<8|0])   ("het" values)
+//     every other (i,j)          : float(B)                (float accumulation of B and zeros; lhet[0] == 0)
+// so gl2cns (pop_utils.cpp:66-100) returns genotype (b,b) and snpQ = (u64)(second smallest + 0.499) with
+// second smallest = min(het values, float(B)).  B is a sum of non-negative terms accumulated in
+// descending code order, so once float(partial B) >= the smallest het value the remaining terms
+// cannot change the result and the walk stops.  pb_unanimous_het returns that smallest het value,
+// or 0 when the shortcut must not be used.
+PB_HD float pb_unanimous_het(const double *__restrict__ lhet, int k, int b) {
+    float h = 3.402823466e+38f;
+    if (b < 3) { const float h0 = PB_D2F(PB_DMUL(-4.343, PB_LDG(lhet + (k << 8)))); h = h0 < h ? h0 : h; }
+    if (b > 0) { const float h1 = PB_D2F(PB_DMUL(-4.343, PB_LDG(lhet + (k << 8 | k)))); h = h1 < h ? h1 : h; }
+    return h > 0.0f ? h : 0.0f;
+}
+
+// Walk of a unanimous cell: only byte b of every histogram word is populated.  Returns true when it
+// stopped early (result fully determined by hmin); otherwise *bsum_b is the complete sum.
+// Every visited word is cleared; on early exit the words below the stopping point are cleared too.
+template <class Hist>
+PB_HD bool pb_walk_unanimous(Hist &take, int n_lw, const uint8_t *qval, int k, int b, const double *fk,
+                             const double *__restrict__ beta, float hmin, double *bsum_b) {
+    double acc = 0.0;
+    int c = 0, wf = 0, wr = 0;
+    for (int lw = n_lw - 1; lw >= 0; --lw) {
+        const uint32_t word = take(lw);
+        if (word == 0) continue;
+        const int m = (int)((word >> (8 * b)) & 255u);
+        const int st = lw & 1;
+        const double *row = beta + ((size_t)qval[lw >> 1] << 16 | (size_t)k << 8);
+        const int w0 = st ? wr : wf;
+        for (int t = 0; t < m; ++t) {
+            acc = pb_errmod_step(acc, fk[w0 + t], PB_LDG(row + c + t));
+            if (hmin > 0.0f && PB_D2F(acc) >= hmin) {
+                for (int l = lw - 1; l >= 0; --l) (void)take(l);
+                return true;
+            }
+        }
+        c += m;
+        if (st) wr += m; else wf += m;
+    }
+    *bsum_b = acc;
+    return false;
+}
+
+// call_base for one cell from its histogram: errmod_cal + gl2cns + rms packing (popbam.cpp:288-298).
+// bmask: which bases occur (bit b).  Leaves the histogram cleared.
+template <class Hist>
+PB_HD uint64_t pb_call_from_hist(Hist &take, int n_lw, const uint8_t *qval, int k, int rmsq, uint32_t bmask, int r4,
+                                 const double *fk, const double *__restrict__ beta, const double *__restrict__ lhet) {
+    double bsum[4] = {0.0, 0.0, 0.0, 0.0};
+    int c[4] = {0, 0, 0, 0};
+    if (k > 0) {
+        if ((bmask & (bmask - 1)) == 0) {
+            const int b = (bmask >> 1 & 1) | ((bmask >> 2 & 1) << 1) | ((bmask >> 3 & 1) * 3);
+            const float hmin = pb_unanimous_het(lhet, k, b);
+            double B = 0.0;
+            if (pb_walk_unanimous(take, n_lw, qval, k, b, fk, beta, hmin, &B)) {
+                const uint64_t snpq = (uint64_t)PB_DADD((double)PB_FSUB(hmin, 0.0f), 0.499);
+                uint64_t cb = (snpq << 32) + ((uint64_t)(unsigned)k << 16) + ((uint64_t)(unsigned)(b << 2 | b) << 8);
+                const uint64_t rms = (uint64_t)PB_DADD((double)PB_FSQRT(PB_FDIV((float)rmsq, (float)k)), 0.499);
+                return cb | rms << 48;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { bsum[i] = i == b ? B : 0.0; c[i] = i == b ? k : 0; }
+        } else {
+            pb_walk_hist(take, n_lw, qval, k, r4, fk, beta, bsum, c);
+        }
+    }
+    return pb_finish_cell(bsum, c, k, rmsq, lhet);
+}

@@ -24,13 +24,12 @@ extern "C" uint64_t hd_call_cell(const double *fk, const double *beta, const dou
         int q = codes[i] >> 5; q = q < 4 ? 4 : q > 63 ? 63 : q;
         hist[qrank[q] * 2 + ((codes[i] >> 4) & 1)] += 1u << (8 * (codes[i] & 3));
     }
-    double bsum[4] = {0, 0, 0, 0};
-    int c[4] = {0, 0, 0, 0};
-    if (k > 0) {
-        auto take = [&](int lw) -> uint32_t { uint32_t w = hist[lw]; hist[lw] = 0; return w; };
-        pb_walk_hist(take, 2 * nl, qval, k, r4, fk, beta, bsum, c);
-    }
-    return pb_finish_cell(bsum, c, k, rmsq, lhet);
+    uint32_t bmask = 0;
+    for (int i = 0; i < k; ++i) bmask |= 1u << (codes[i] & 3);
+    auto take = [&](int lw) -> uint32_t { uint32_t w = hist[lw]; hist[lw] = 0; return w; };
+    const uint64_t cb = pb_call_from_hist(take, 2 * nl, qval, k, rmsq, bmask, r4, fk, beta, lhet);
+    for (int lw = 0; lw < 2 * nl; ++lw) if (hist[lw]) return ~0ULL;     // the histogram must come back cleared
+    return cb;
 }
 
 extern "C" int hd_site_logic(uint64_t *cb, int n, int ref, int het_mode, int min_snpQ, int min_rmsQ, int min_depth, int max_depth,

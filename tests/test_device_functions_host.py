@@ -47,3 +47,36 @@ def test_site_logic_equals_reference(hd):
         assert fq == int(r["fq"])
         assert cov.value == int(r["cov"])
         assert (cb[:n] == r["cb_out"][:n]).all()
+
+
+def test_unanimous_shortcut_equals_oracle(hd):
+    """Cells whose bases all agree take the early-exit walk (pb_walk_unanimous): compare with the reference-pinned
+    oracle on random cells over the whole depth range and several quality distributions."""
+    L, t = pbtest.oracle_lib(), pbtest.oracle_tables()
+    rng = np.random.default_rng(42)
+    n_unan = 0
+    for i in range(6000):
+        style = i % 4
+        k = int(rng.integers(1, 256)) if style == 0 else int(rng.integers(1, 40))
+        if style == 1:
+            q = rng.choice([20, 29, 30, 35, 40], size=k)
+        elif style == 2:
+            q = rng.integers(4, 64, size=k)
+        elif style == 3:
+            q = rng.choice([4, 5, 6], size=k)            # weak evidence: the shortcut may not trigger
+        else:
+            q = rng.choice([13, 25, 37, 41, 60, 63], size=k)
+        b = int(rng.integers(0, 4))
+        base = np.full(k, b)
+        if i % 7 == 0 and k > 1:                          # a few non-unanimous cells through the same entry point
+            base[rng.integers(0, k)] = (b + 1) & 3
+        strand = rng.integers(0, 2, size=k)
+        codes = (q << 5 | strand << 4 | base).astype(np.uint16)
+        rmsq = int((rng.integers(13, 61, size=k) ** 2).sum())
+        work = np.zeros(256, dtype=np.uint16); work[:k] = codes
+        want = L.pbo_call_cell(*t.ptrs(), work.ctypes.data_as(C.POINTER(C.c_uint16)), k, rmsq, None)
+        full = np.zeros(256, dtype=np.uint16); full[:k] = codes
+        got = hd.hd_call_cell(*t.ptrs(), full.ctypes.data_as(C.POINTER(C.c_uint16)), k, rmsq, int(rng.integers(0, 4)))
+        assert got == want, (i, k, b)
+        n_unan += len(set(base.tolist())) == 1
+    assert n_unan > 4000
