@@ -102,52 +102,66 @@ PB_HD uint64_t pb_finish_cell(const double bsum[4], const int c[4], int k, int r
     return cb;
 }
 
-// clean_heterozygotes + segbase + qfilter + cal_site_type on the n cb words of one site (in place).
-// Returns fq (segbase's return value); *cov = samples passing qfilter, *type = samples with (cb&3)==3.
-// `stride` lets the words live in a strided (shared-memory) layout.
+// clean_heterozygotes + segbase + qfilter + cal_site_type for ONE sample of a site; the three reference
+// loops are independent per sample except for segbase's derived-allele counts, which accumulate in
+// *cnt4 (one byte per base; n <= 64).  Returns the final cb word; *covered = passes qfilter,
+// *derived = (cb & 3) == 3 (cal_site_type).  r = iupac_rev[ref].
+PB_HD uint64_t pb_site_sample(uint64_t w, int ref, int r, int het_mode, int min_snpQ, int min_rmsQ, int min_depth, int max_depth,
+                              uint32_t *cnt4, bool *covered, bool *derived) {
+    if (!het_mode) {   // clean_heterozygotes (pop_utils.cpp:170-201): both tests use the original alleles
+        const int g = (int)((w >> 8) & 0xff), a1 = (g >> 2) & 3, a2 = g & 3, sq = (int)((w >> 32) & 0xffff);
+        if (a1 != a2) {
+            if (sq >= min_snpQ) {
+                if (a1 == r) w += (uint64_t)(int64_t)((a2 - a1) * 1024);
+                if (a2 == r) w -= (uint64_t)(int64_t)((a2 - a1) * 256);
+            } else {
+                if (a1 != r) w += (uint64_t)(int64_t)((a2 - a1) * 1024);
+                if (a2 != r) w -= (uint64_t)(int64_t)((a2 - a1) * 256);
+            }
+        }
+    }
+    {   // segbase (pop_utils.cpp:122-168)
+        const int g = (int)((w >> 8) & 0xff), a1 = (g >> 2) & 3, a2 = g & 3, sq = (int)((w >> 32) & 0xffff);
+        // iupac[g] for a homozygous genotype byte (a1 == a2) is "ACGT"[a1]; the byte is < 16 here because
+        // the steps before only produce two-bit alleles
+        const int letter = (g < 16) ? (int)"ACGT"[a1] : 'N';
+        if (a1 == a2 && letter != ref) {
+            if (sq >= min_snpQ) { w |= 2; *cnt4 += 1u << (8 * a1); }
+            else {
+                w -= (uint64_t)(int64_t)((g - r) * 256);
+                w -= (uint64_t)(int64_t)((g - r) * 1024);
+            }
+        }
+    }
+    {   // qfilter (pop_utils.cpp:102-120)
+        const int rms = (int)((w >> 48) & 0xffff), nr = (int)((w >> 16) & 0xffff);
+        const bool ok = rms >= min_rmsQ && nr >= min_depth && nr <= max_depth;
+        if (ok) w |= 1;
+        *covered = ok;
+    }
+    *derived = (w & 3) == 3;
+    return w;
+}
+
+// segbase's return value from the derived-allele counts: -1 if more than one derived base, else the count
+PB_HD int pb_site_fq(uint32_t cnt4) {
+    const int c0 = cnt4 & 255, c1 = (cnt4 >> 8) & 255, c2 = (cnt4 >> 16) & 255, c3 = cnt4 >> 24;
+    const int nder = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
+    return nder > 1 ? -1 : c0 + c1 + c2 + c3;
+}
+
+// All n samples of one site (in place); kept for the unit-test harness and small callers.
 PB_HD int pb_site_logic(uint64_t *cb, int stride, int n, int ref, int het_mode, int min_snpQ, int min_rmsQ, int min_depth,
                         int max_depth, uint64_t *cov_out, uint64_t *type_out) {
     const int r = pb_iupac_rev(ref);
-    int cnt0 = 0, cnt1 = 0, cnt2 = 0, cnt3 = 0;
+    uint32_t cnt4 = 0;
     uint64_t cov = 0, type = 0;
     for (int i = 0; i < n; ++i) {
-        uint64_t w = cb[i * stride];
-        if (!het_mode) {
-            int g = (int)((w >> 8) & 0xff), a1 = (g >> 2) & 3, a2 = g & 3, sq = (int)((w >> 32) & 0xffff);
-            if (a1 != a2) {
-                if (sq >= min_snpQ) {
-                    if (a1 == r) w += (uint64_t)(int64_t)((a2 - a1) * 1024);
-                    if (a2 == r) w -= (uint64_t)(int64_t)((a2 - a1) * 256);
-                } else {
-                    if (a1 != r) w += (uint64_t)(int64_t)((a2 - a1) * 1024);
-                    if (a2 != r) w -= (uint64_t)(int64_t)((a2 - a1) * 256);
-                }
-            }
-        }
-        {   // segbase
-            int g = (int)((w >> 8) & 0xff), a1 = (g >> 2) & 3, a2 = g & 3, sq = (int)((w >> 32) & 0xffff);
-            // iupac[g] for a homozygous genotype byte (a1 == a2): "ACGT"[a1] when g < 16; a garbage byte
-            // (g >= 16) never reaches here on a fresh call because step one only yields 5*a
-            const int letter = (g < 16) ? (int)"ACGT"[a1] : 'N';
-            if (a1 == a2 && letter != ref) {
-                if (sq >= min_snpQ) {
-                    w |= 2;
-                    cnt0 += a1 == 0; cnt1 += a1 == 1; cnt2 += a1 == 2; cnt3 += a1 == 3;
-                } else {
-                    w -= (uint64_t)(int64_t)((g - r) * 256);
-                    w -= (uint64_t)(int64_t)((g - r) * 1024);
-                }
-            }
-        }
-        {   // qfilter
-            int rms = (int)((w >> 48) & 0xffff), nr = (int)((w >> 16) & 0xffff);
-            if (rms >= min_rmsQ && nr >= min_depth && nr <= max_depth) { w |= 1; cov |= 1ULL << i; }
-        }
-        if ((w & 3) == 3) type |= 1ULL << i;
-        cb[i * stride] = w;
+        bool c, d;
+        cb[i * stride] = pb_site_sample(cb[i * stride], ref, r, het_mode, min_snpQ, min_rmsQ, min_depth, max_depth, &cnt4, &c, &d);
+        if (c) cov |= 1ULL << i;
+        if (d) type |= 1ULL << i;
     }
-    const int nder = (cnt0 > 0) + (cnt1 > 0) + (cnt2 > 0) + (cnt3 > 0);
     *cov_out = cov; *type_out = type;
-    if (nder > 1) return -1;
-    return cnt0 + cnt1 + cnt2 + cnt3;
+    return pb_site_fq(cnt4);
 }

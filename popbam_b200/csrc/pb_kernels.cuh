@@ -19,8 +19,9 @@
 #include "pb_cell.cuh"
 #include "pb_walk.cuh"
 
-#define PB_REC_DEAD 0x200u        // read fails min_mapQ: it only counts towards the raw-depth cap
-#define PB_REC_CAP 1024           // segment records staged per round in the hot kernel
+#define PB_REC_DEAD (1u << 25)    // read fails min_mapQ: it only counts towards the raw-depth cap
+#define PB_REC_CAP 640            // segment records staged per round in the hot kernel
+#define PB_QCAP 128               // deferred (non-unanimous) cells per round
 #define PB_PART_CHUNK 2048        // reads per warp in the sample partition
 #define PB_KEY_DROP 0xffu
 #define PB_CODE_NONE 0xffu        // base filtered out (quality, N)
@@ -52,14 +53,14 @@ __global__ void k_rebase(int64_t n, int64_t r0, const uint32_t *__restrict__ cig
 
 // bam_plp_push (bam_pileup.c:371-374): drop flag & 0x704; bam_calend (bam.c:20-70): reference end.
 // Also counts the read's aligned segments (M/=/X ops): each becomes one record of the hot kernel.
-__global__ void k_read_prep(int64_t n, const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta,
-                            const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
-                            const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ, uint8_t *__restrict__ rkey,
-                            uint8_t *__restrict__ rnseg, PbCounters *__restrict__ ctr) {
-    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta,
+                                                   const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
+                                                   const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ,
+                                                   uint8_t *__restrict__ rkey, uint8_t *__restrict__ rnseg,
+                                                   PbCounters *__restrict__ ctr) {
     unsigned long long used = 0, aligned = 0, mqmask = 0;
     int span = 0, flags = 0;     // flags: 1 unsorted, 2 too long
-    if (r < n) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t m = meta[r];
         const int p = pos[r];
         const uint32_t c0 = cigstart[r], nc = ncig[r];
@@ -78,13 +79,13 @@ __global__ void k_read_prep(int64_t n, const int32_t *__restrict__ pos, const ui
         if (listed && (longseg || x - p > 65535 || nseg > PB_MAX_SEGS)) flags |= 2;
         rnseg[r] = (uint8_t)(nseg > PB_MAX_SEGS ? PB_MAX_SEGS : nseg);
         if (keep) {
-            used = 1; aligned = (unsigned long long)al; span = x - p;
+            used += 1; aligned += (unsigned long long)al; span = max(span, x - p);
             const int mq = (int)((m >> 8) & 0xff);
-            if (mq >= min_mapQ) mqmask = 1ULL << (mq > 63 ? 63 : mq);
+            if (mq >= min_mapQ) mqmask |= 1ULL << (mq > 63 ? 63 : mq);
         }
         if (r > 0 && p < pos[r - 1]) flags |= 1;
     }
-    // warp-aggregate, then one atomic per warp
+    // warp-aggregate, block-aggregate, then one atomic per counter per block
     for (int o = 16; o > 0; o >>= 1) {
         used += __shfl_xor_sync(0xffffffffu, used, o);
         aligned += __shfl_xor_sync(0xffffffffu, aligned, o);
@@ -92,7 +93,13 @@ __global__ void k_read_prep(int64_t n, const int32_t *__restrict__ pos, const ui
         span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
         flags |= __shfl_xor_sync(0xffffffffu, flags, o);
     }
-    if ((threadIdx.x & 31) == 0) {
+    __shared__ unsigned long long s_used[8], s_al[8], s_mq[8];
+    __shared__ int s_span[8], s_flags[8];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s_used[wid] = used; s_al[wid] = aligned; s_mq[wid] = mqmask; s_span[wid] = span; s_flags[wid] = flags; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { used += s_used[i]; aligned += s_al[i]; mqmask |= s_mq[i]; span = max(span, s_span[i]); flags |= s_flags[i]; }
         if (used) atomicAdd(&ctr->reads_used, used);
         if (aligned) atomicAdd(&ctr->aligned_bases, aligned);
         if (mqmask) atomicOr(&ctr->mapq_mask, mqmask);
@@ -109,17 +116,23 @@ __global__ void k_qual_mask(const uint8_t *__restrict__ qual, int64_t n_bytes, i
     unsigned long long mask = 0;
     const int64_t nvec = n_bytes >> 4;
     const uint4 *q4 = reinterpret_cast<const uint4 *>(qual);
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
-        const uint4 v = __ldg(q4 + i);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += 4 * stride) {
+        uint4 v[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int t = 0; t < 4; ++t) v[t] = i + t * stride < nvec ? __ldg(q4 + i + t * stride) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int q = (int)((w[j] >> (8 * b)) & 0xff);
-                if (illumina) q = q > 31 ? q - 31 : 0;
-                if (q >= min_baseQ) mask |= 1ULL << (q > 63 ? 63 : q);
-            }
+        for (int t = 0; t < 4; ++t) {
+            const uint32_t w[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    int q = (int)((w[j] >> (8 * b)) & 0xff);
+                    if (illumina) q = q > 31 ? q - 31 : 0;
+                    if (q >= min_baseQ) mask |= 1ULL << (q > 63 ? 63 : q);
+                }
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int64_t i = nvec << 4; i < n_bytes; ++i) {
@@ -174,6 +187,41 @@ __global__ void k_encode(int64_t n, const uint32_t *__restrict__ meta, const uin
         const uint64_t b0 = base[r];
         const uint64_t b1 = r + 1 < n ? base[r + 1] : (uint64_t)n_bytes;     // reads are laid out back to back
         const int len = (int)min((uint64_t)1 << 20, b1 - b0);
+        if ((b0 & 3) == 0) {
+            // four bases per lane: one 32-bit quality load, one 16-bit sequence load, one 32-bit store
+            const uint32_t *q32 = reinterpret_cast<const uint32_t *>(qual + b0);
+            const uint16_t *s16 = reinterpret_cast<const uint16_t *>(seq4 + (b0 >> 1));
+            uint32_t *c32 = reinterpret_cast<uint32_t *>(codes + b0);
+            const int nq = len >> 2;
+            for (int t = lane; t < nq; t += 32) {
+                const uint32_t qw = __ldg(q32 + t);
+                const uint32_t sw = __ldg(s16 + t);       // bytes: [b0 b1][b2 b3], high nibble first
+                uint32_t out = 0;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    int bq = (int)((qw >> (8 * i)) & 0xff);
+                    if (illumina) bq = bq > 31 ? bq - 31 : 0;
+                    const uint32_t nib = (sw >> (8 * (i >> 1) + ((~i & 1) << 2))) & 0xfu;
+                    const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+                    int qq = min(bq, mapq);
+                    qq = max(4, min(63, qq));
+                    const uint32_t cd = (bq < min_baseQ || b4 > 3) ? PB_CODE_NONE : (uint32_t)(qrank_s[qq] << 2 | b4);
+                    out |= cd << (8 * i);
+                }
+                c32[t] = out;
+            }
+            for (int y = (nq << 2) + lane; y < len; y += 32) {
+                int bq = (int)__ldg(qual + b0 + y);
+                if (illumina) bq = bq > 31 ? bq - 31 : 0;
+                const uint32_t sb = __ldg(seq4 + (b0 >> 1) + (y >> 1));
+                const uint32_t nib = (sb >> ((~y & 1) << 2)) & 0xfu;
+                const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+                int qq = min(bq, mapq);
+                qq = max(4, min(63, qq));
+                codes[b0 + y] = (bq < min_baseQ || b4 > 3) ? (uint8_t)PB_CODE_NONE : (uint8_t)(qrank_s[qq] << 2 | b4);
+            }
+            continue;
+        }
         for (int y = lane; y < len; y += 32) {
             int bq = (int)__ldg(qual + b0 + y);
             if (illumina) bq = bq > 31 ? bq - 31 : 0;
@@ -216,9 +264,9 @@ __global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, const 
 
 // Segment record (16 bytes):
 //   x  read start (sort key of the list; all segments of a read carry it)
-//   y  (segment start - read start) | segment length << 16         (both < 65536)
-//   z  low 32 bits of the byte offset of the segment's first base in qual[] / codes[]
-//   w  mapq | strand<<8 | dead<<9 | (offset bits 32..39)<<24
+//   y  segment start (reference coordinate)
+//   z  segment length (16 bits) | mapq<<16 | strand<<24 | dead<<25 | (offset bits 32..37)<<26
+//   w  low 32 bits of the byte offset of the segment's first base in qual[] / codes[]
 __global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg, int n_samples,
                                int64_t n_chunks, const uint32_t *__restrict__ offs /* scanned counts */,
                                const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta, const uint64_t *__restrict__ base,
@@ -250,7 +298,7 @@ __global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, cons
             const uint32_t m = meta[r];
             const int p = pos[r];
             const uint32_t mapq = (m >> 8) & 0xffu;
-            const uint32_t wlo = mapq | (((m >> 20) & 1u) << 8) | ((int)mapq < min_mapQ ? PB_REC_DEAD : 0u);
+            const uint32_t zhi = (mapq << 16) | (((m >> 20) & 1u) << 24) | ((int)mapq < min_mapQ ? PB_REC_DEAD : 0u);
             const uint64_t b = base[r];
             const uint32_t cs = cigstart[r], nc = ncig[r];
             int x = p, y = 0;
@@ -263,9 +311,9 @@ __global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, cons
                         const uint64_t sb = b + (uint64_t)y;
                         int4 rec;
                         rec.x = p;
-                        rec.y = (int)(((uint32_t)(x - p) & 0xffffu) | ((uint32_t)len << 16));
-                        rec.z = (int)(uint32_t)sb;
-                        rec.w = (int)(wlo | ((uint32_t)(sb >> 32) << 24));
+                        rec.y = x;
+                        rec.z = (int)((uint32_t)len | zhi | ((uint32_t)(sb >> 32) << 26));
+                        rec.w = (int)(uint32_t)sb;
                         srec[dst++] = rec;
                         ++emitted;
                     }
@@ -361,41 +409,51 @@ struct PbPileArgs {
     uint64_t *cb_out;               // [span * n_samples] or null
 };
 
-// Dynamic shared memory of k_pileup_call<TP> for n samples and nl quality levels.
-static inline size_t pb_pile_smem(int tp, int n, int nl) {
-    return (size_t)tp * n * 8 + (size_t)PB_REC_CAP * 16 + (size_t)2 * nl * tp * 4 + 256 * 8 + 128 * 4 + 64 + 64 * 16 + 64;
+// Dynamic shared memory of k_pileup_call<TP> for nl quality levels (independent of the sample count).
+static inline size_t pb_pile_smem(int tp, int nl) {
+    return (size_t)PB_REC_CAP * 16 + (size_t)2 * nl * tp * 4 + (size_t)PB_QCAP * (3 + 2 * nl) * 4 + (size_t)tp * 20 + 256 * 8 +
+           128 * 4 + 64 + 64 * 16 + 64;
 }
 
 // One CTA = TP consecutive reference positions x all samples; one thread = one position.
 //
-// Rounds: the CTA stages, for as many consecutive samples as fit, the candidate segment records
-// (reads starting in (p0 - max_span, p0 + TP)) in shared memory.  For each staged sample a thread
-// binary-searches its first candidate and walks the records that can cover its position IN FILE
-// ORDER: coverage is one unsigned compare (p - seg_start < seg_len), the raw-depth cap is applied
-// before the base filter as in call_base (popbam.cpp:242-248), and the base's pre-digested code
-// (k_encode) is one byte load whose address is consecutive across the lanes of a warp.  Passing bases
-// are counted in the thread's private (level, strand) x base histogram in shared memory (plain
-// read-modify-write, no atomics).  After the last record of a sample the thread runs the error model
-// on the histogram (pb_walk_hist) and leaves the consensus word in shared memory; after the last
-// sample it runs the per-site logic on its n words and writes 9 bytes.
+// Rounds.  The CTA stages, for as many consecutive samples as fit, the candidate segment records
+// (reads starting in (p0 - max_span, p0 + TP)) in shared memory.  For each staged sample a WARP walks
+// the records that can cover any of its 32 positions, all lanes in lock step over the same record
+// (file order): coverage of a lane's position is one unsigned compare (p - seg_start < seg_len), the
+// raw-depth cap is applied before the base filter as in call_base (popbam.cpp:242-248), and the base's
+// pre-digested code (k_encode) is one byte load whose address is consecutive across the lanes.  The
+// body is branch-free (predicated), so the warp never splits.  Passing bases are counted in the
+// thread's private (level, strand) x base histogram in shared memory (plain read-modify-write, no
+// atomics) and in a packed per-base total.
 //
-// Cells whose bases all agree (the overwhelming majority) take an exact shortcut: the best genotype is
-// the homozygote with likelihood 0, the runner-up is min(het term, float(bsum)), and bsum only
-// grows, so the walk stops as soon as its partial sum reaches the het term (see pb_unanimous_exit).
+// Calls.  After the last record of a sample, cells whose bases all agree (the overwhelming majority)
+// are called on the spot with the exact early-exit walk (pb_call_unanimous).  The others are deferred:
+// the thread moves its histogram into a shared-memory queue, and at the end of the round the queue is
+// drained with one cell per thread, so the long general walk (pb_call_general) runs on full warps
+// instead of on the one or two lanes of a warp that need it.
+//
+// Per-site logic (make_X, pop_nucdiv.cpp:148-197) is folded in sample by sample (pb_site_sample): a
+// position only keeps its coverage mask, derived-allele mask and derived-base counts (20 bytes of
+// shared memory), so nothing per (site, sample) is stored unless the caller asked for the cb words.
 template <int TP>
 __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n_samples;
     const int nl = a.ctr->n_levels;
     const int n_lw = 2 * nl;
-    uint64_t *cbs = reinterpret_cast<uint64_t *>(smem_raw);                 // [TP][n]
-    int4 *recs = reinterpret_cast<int4 *>(cbs + (size_t)TP * n);            // [PB_REC_CAP]
+    const int qstride = 3 + n_lw;
+    int4 *recs = reinterpret_cast<int4 *>(smem_raw);                        // [PB_REC_CAP]
     uint32_t *hist = reinterpret_cast<uint32_t *>(recs + PB_REC_CAP);       // [n_lw][TP]
-    double *fk_s = reinterpret_cast<double *>(hist + (size_t)n_lw * TP);    // [256]
+    uint32_t *queue = hist + (size_t)n_lw * TP;                             // [PB_QCAP][3 + n_lw]
+    uint64_t *s_cov = reinterpret_cast<uint64_t *>(queue + (size_t)PB_QCAP * qstride + ((PB_QCAP * qstride) & 1));   // [TP]
+    uint64_t *s_type = s_cov + TP;                                          // [TP]
+    uint32_t *s_cnt4 = reinterpret_cast<uint32_t *>(s_type + TP);           // [TP]
+    double *fk_s = reinterpret_cast<double *>(s_cnt4 + TP + (TP & 1));      // [256]
     uint32_t *rng = reinterpret_cast<uint32_t *>(fk_s + 256);               // lo[64], hi[64]
     uint8_t *qval_s = reinterpret_cast<uint8_t *>(rng + 128);               // [64]
     int4 *plan = reinterpret_cast<int4 *>(qval_s + 64);                     // [64] {sample, src, count | last<<31, dst}
-    uint32_t *plan_n = reinterpret_cast<uint32_t *>(plan + 64);             // [0] entries, [1] next sample, [2] next src
+    uint32_t *plan_n = reinterpret_cast<uint32_t *>(plan + 64);             // [0] entries, [1] next sample, [2] next src, [3] queue fill
 
     const int tid = threadIdx.x;
     const int p0 = a.span_beg + (int)blockIdx.x * TP;
@@ -403,10 +461,14 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     const int p_end = min(p0 + TP, a.span_end);
     const bool valid = p < p_end;
     const int max_span = a.ctr->max_span;
+    // the warp's position range
+    const int pw0 = p0 + (tid & ~31);
+    const int pw1 = min(pw0 + 31, p_end - 1);
 
     for (int i = tid; i < 256; i += TP) fk_s[i] = a.fk[i];
     if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
     for (int lw = 0; lw < n_lw; ++lw) hist[lw * TP + tid] = 0;
+    s_cov[tid] = 0; s_type[tid] = 0; s_cnt4[tid] = 0;
     if (tid < n) {
         // candidate records of sample tid: read start in (p0 - max_span, p_end)
         const uint32_t s0 = a.sstart[tid], s1 = a.sstart[tid + 1];
@@ -420,16 +482,35 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
         rng[64 + tid] = l2;
     }
     __syncthreads();
-    if (tid == 0) { plan_n[1] = 0; plan_n[2] = rng[0]; }
+    if (tid == 0) { plan_n[1] = 0; plan_n[2] = rng[0]; plan_n[3] = 0; }
 
     const int ref_c = (valid && p >= 0 && p < a.ref_len) ? (int)(unsigned char)a.ref[p] : 'N';
-    const int r4 = pb_iupac_rev(ref_c) & 3;
+    const int ref_r = pb_iupac_rev(ref_c);
 
-    int depth = 0, k = 0, rmsq = 0;
-    uint32_t bmask = 0;          // which bases occur in the cell
+    // fold one called cell into its position's site state.  During a round only the owner thread touches a
+    // slot; in the drain several threads may hold cells of the same position (different samples), hence
+    // the atomic variant.
+    auto fold = [&](int slot, int pos, int refc, int refr, int smp, uint64_t cb, bool atomic) {
+        uint32_t d4 = 0;
+        bool cov, der;
+        cb = pb_site_sample(cb, refc, refr, a.het_mode, a.min_snpQ, a.min_rmsQ, a.min_depth, a.max_depth, &d4, &cov, &der);
+        if (atomic) {
+            if (d4) atomicAdd(&s_cnt4[slot], d4);
+            if (cov) atomicOr(reinterpret_cast<unsigned long long *>(&s_cov[slot]), 1ULL << smp);
+            if (der) atomicOr(reinterpret_cast<unsigned long long *>(&s_type[slot]), 1ULL << smp);
+        } else {
+            s_cnt4[slot] += d4;
+            if (cov) s_cov[slot] |= 1ULL << smp;
+            if (der) s_type[slot] |= 1ULL << smp;
+        }
+        if (a.cb_out) a.cb_out[((int64_t)pos - a.span_beg) * n + smp] = cb;
+    };
+
+    int depth = 0, rmsq = 0;
+    uint32_t tot4 = 0;           // per-base counts of the cell, one byte each
     for (;;) {
+        __syncthreads();         // everybody is done with the previous round's plan, records and queue
         // ---- plan one round: consecutive samples (or a piece of one) whose records fit the staging area
-        __syncthreads();         // everybody is done with the previous round's plan and records
         if (tid == 0) {
             int s = (int)plan_n[1], ne = 0, fill = 0;
             uint32_t src = plan_n[2];
@@ -443,7 +524,7 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
                 fill += take;
                 if (last) { ++s; src = s < n ? rng[s] : 0; } else { src += take; break; }
             }
-            plan_n[0] = (uint32_t)ne; plan_n[1] = (uint32_t)s; plan_n[2] = src;
+            plan_n[0] = (uint32_t)ne; plan_n[1] = (uint32_t)s; plan_n[2] = src; plan_n[3] = 0;
         }
         __syncthreads();
         const int ne = (int)plan_n[0];
@@ -458,65 +539,86 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
             const int4 pl = plan[e];
             const int cnt = pl.z & 0x7fffffff;
             const int4 *rs = recs + pl.w;
-            if (valid) {
+            if (pw0 < p_end) {                                         // warp-uniform
                 int j = 0, jh = cnt;
-                const int thr = p - max_span;     // reads starting at or before thr end at or before p
+                const int thr = pw0 - max_span;   // reads starting at or before thr end before the warp's first position
                 while (j < jh) { const int mid = (j + jh) >> 1; if (rs[mid].x > thr) jh = mid; else j = mid + 1; }
                 for (; j < cnt; ++j) {
-                    const int4 r = rs[j];
-                    if (r.x > p) break;
-                    const uint32_t u = (uint32_t)(p - r.x) - ((uint32_t)r.y & 0xffffu);
-                    if (u >= ((uint32_t)r.y >> 16)) continue;          // not in this aligned segment (or is_del / ref-skip)
-                    if (depth >= a.max_depth) continue;                // cap precedes the filters (popbam.cpp:242-248)
-                    ++depth;
-                    if ((uint32_t)r.w & PB_REC_DEAD) continue;         // mapQ < min_mapQ
-                    const uint64_t boff = ((uint64_t)((uint32_t)r.w >> 24) << 32) | (uint32_t)r.z;
-                    const uint32_t code = __ldg(a.codes + boff + u);
-                    if (code == PB_CODE_NONE) continue;
-                    const int lw = (int)(code >> 2) * 2 + ((r.w >> 8) & 1);
-                    const int b4 = (int)(code & 3u);
-                    hist[lw * TP + tid] += 1u << (8 * b4);
-                    bmask |= 1u << b4;
-                    ++k;
-                    const int mapq = r.w & 0xff;
-                    rmsq += mapq * mapq;
+                    const int4 r = rs[j];                              // same record for every lane: broadcast
+                    if (r.x > pw1) break;                              // uniform
+                    const uint32_t u = (uint32_t)(p - r.y);
+                    const bool take = valid && u < ((uint32_t)r.z & 0xffffu) && depth < a.max_depth;   // cap precedes the filters
+                    depth += take;
+                    const bool live = take && !((uint32_t)r.z & PB_REC_DEAD);
+                    const uint64_t boff = ((uint64_t)((uint32_t)r.z >> 26) << 32) | (uint32_t)r.w;
+                    uint32_t code = PB_CODE_NONE;
+                    if (live) code = __ldg(a.codes + boff + u);
+                    if (code != PB_CODE_NONE) {
+                        const uint32_t inc = 1u << ((code & 3u) << 3);
+                        const int lw = (int)(code >> 2) * 2 + (int)(((uint32_t)r.z >> 24) & 1u);
+                        hist[lw * TP + tid] += inc;
+                        tot4 += inc;
+                        const int mapq = (int)(((uint32_t)r.z >> 16) & 0xffu);
+                        rmsq += mapq * mapq;
+                    }
                 }
             }
             if (pl.z < 0) {      // last piece of this sample: call the cell
-                uint64_t cb = 0;
-                if (depth > 0) {
-                    auto take = [&](int lw) -> uint32_t {
-                        const uint32_t w = hist[lw * TP + tid];
-                        if (w) hist[lw * TP + tid] = 0;
-                        return w;
-                    };
-                    cb = pb_call_from_hist(take, n_lw, qval_s, k, rmsq, bmask, r4, fk_s, a.beta, a.lhet);
+                if (valid) {
+                    if (depth == 0) fold(tid, p, ref_c, ref_r, pl.x, 0, false);
+                    else if (tot4 == 0) {
+                        const double z4[4] = {0.0, 0.0, 0.0, 0.0};
+                        const int c4[4] = {0, 0, 0, 0};
+                        fold(tid, p, ref_c, ref_r, pl.x, pb_finish_cell(z4, c4, 0, rmsq, a.lhet), false);
+                    } else if (pb_tot4_unanimous(tot4)) {
+                        auto take = [&](int lw) -> uint32_t {
+                            const uint32_t w = hist[lw * TP + tid];
+                            if (w) hist[lw * TP + tid] = 0;
+                            return w;
+                        };
+                        auto clear = [&](int lw) { hist[lw * TP + tid] = 0; };
+                        fold(tid, p, ref_c, ref_r, pl.x, pb_call_unanimous(take, clear, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet), false);
+                    } else {
+                        const uint32_t slot = atomicAdd(&plan_n[3], 1u);
+                        if (slot < PB_QCAP) {          // defer: move the histogram into the queue
+                            uint32_t *q = queue + (size_t)slot * qstride;
+                            q[0] = (uint32_t)tid | ((uint32_t)pl.x << 16); q[1] = (uint32_t)rmsq; q[2] = tot4;
+                            for (int lw = 0; lw < n_lw; ++lw) { q[3 + lw] = hist[lw * TP + tid]; hist[lw * TP + tid] = 0; }
+                        } else {                       // queue full: call it here
+                            auto take = [&](int lw) -> uint32_t {
+                                const uint32_t w = hist[lw * TP + tid];
+                                if (w) hist[lw * TP + tid] = 0;
+                                return w;
+                            };
+                            fold(tid, p, ref_c, ref_r, pl.x, pb_call_general(take, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet), false);
+                        }
+                    }
                 }
-                cbs[(size_t)tid * n + pl.x] = cb;
-                depth = 0; k = 0; rmsq = 0; bmask = 0;
+                depth = 0; rmsq = 0; tot4 = 0;
             }
+        }
+        __syncthreads();         // the queue is complete
+        const int qn = (int)min(plan_n[3], (uint32_t)PB_QCAP);
+        for (int e = tid; e < qn; e += TP) {
+            const uint32_t *q = queue + (size_t)e * qstride;
+            const int slot = (int)(q[0] & 0xffffu), smp = (int)(q[0] >> 16);
+            const int pos = p0 + slot;
+            const int rc = (pos >= 0 && pos < a.ref_len) ? (int)(unsigned char)a.ref[pos] : 'N';
+            auto take = [&](int lw) -> uint32_t { return q[3 + lw]; };
+            fold(slot, pos, rc, pb_iupac_rev(rc), smp, pb_call_general(take, n_lw, qval_s, q[2], (int)q[1], fk_s, a.beta, a.lhet), true);
         }
     }
 
-    // per-site logic (make_X, pop_nucdiv.cpp:148-197) on the n words of this thread's position
+    // the site: segbase's return value, coverage test, window membership (windows are sorted and disjoint)
     if (valid) {
-        uint64_t cov, type;
-        const int fq = pb_site_logic(cbs + (size_t)tid * n, 1, n, ref_c, a.het_mode, a.min_snpQ, a.min_rmsQ, a.min_depth,
-                                     a.max_depth, &cov, &type);
-        // window membership: windows are sorted and disjoint
+        const int fq = pb_site_fq(s_cnt4[tid]);
         int lo = 0, hi = a.n_windows;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(a.win_end + mid) > p) hi = mid; else lo = mid + 1; }
         const bool in_win = lo < a.n_windows && __ldg(a.win_beg + lo) <= p;
-        const bool used = in_win && __popcll(cov) == n;
+        const bool used = in_win && __popcll(s_cov[tid]) == n;
         const int64_t o = (int64_t)p - a.span_beg;
-        a.site_type[o] = type;
+        a.site_type[o] = s_type[tid];
         a.site_flag[o] = (uint8_t)((used ? 1 : 0) | ((used && fq > 0) ? 2 : 0));
-    }
-    if (a.cb_out) {
-        __syncthreads();
-        const int64_t o0 = ((int64_t)p0 - a.span_beg) * n;
-        const int tot = (p_end - p0) * n;
-        for (int i = tid; i < tot; i += TP) a.cb_out[o0 + i] = cbs[i];
     }
 }
 

@@ -211,7 +211,7 @@ int run_pipeline(pb_ctx *c) {
     PbCounters *ctr = dp<PbCounters>(c->d_ctr);
     const int illumina = (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0;
     if (N > 0) {
-        k_read_prep<<<nblk(N, 256), 256, 0, st>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
+        k_read_prep<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->n_sms * 8), 256, 0, st>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
                                                  dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), n, P.min_mapQ,
                                                  dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), ctr);
         k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
@@ -249,7 +249,7 @@ int run_pipeline(pb_ctx *c) {
     PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
     if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
     const int nl = c->ctr_host.n_levels;
-    const size_t smem = pb_pile_smem(kTP, n, nl);
+    const size_t smem = pb_pile_smem(kTP, nl);
     if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d samples x %d quality levels exceeds %zu bytes", n, nl, c->smem_optin);
     PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PbPileArgs pa;

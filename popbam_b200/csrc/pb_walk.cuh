@@ -78,9 +78,9 @@ PB_HD float pb_unanimous_het(const double *__restrict__ lhet, int k, int b) {
 
 // Walk of a unanimous cell: only byte b of every histogram word is populated.  Returns true when it
 // stopped early (result fully determined by hmin); otherwise *bsum_b is the complete sum.
-// Every visited word is cleared; on early exit the words below the stopping point are cleared too.
-template <class Hist>
-PB_HD bool pb_walk_unanimous(Hist &take, int n_lw, const uint8_t *qval, int k, int b, const double *fk,
+// `take(lw)` returns a word and clears it; `clear(lw)` only clears (used below the stopping point).
+template <class Hist, class Clear>
+PB_HD bool pb_walk_unanimous(Hist &take, Clear &clear, int n_lw, const uint8_t *qval, int k, int b, const double *fk,
                              const double *__restrict__ beta, float hmin, double *bsum_b) {
     double acc = 0.0;
     int c = 0, wf = 0, wr = 0;
@@ -94,7 +94,7 @@ PB_HD bool pb_walk_unanimous(Hist &take, int n_lw, const uint8_t *qval, int k, i
         for (int t = 0; t < m; ++t) {
             acc = pb_errmod_step(acc, fk[w0 + t], PB_LDG(row + c + t));
             if (hmin > 0.0f && PB_D2F(acc) >= hmin) {
-                for (int l = lw - 1; l >= 0; --l) (void)take(l);
+                for (int l = lw - 1; l >= 0; --l) clear(l);
                 return true;
             }
         }
@@ -105,29 +105,45 @@ PB_HD bool pb_walk_unanimous(Hist &take, int n_lw, const uint8_t *qval, int k, i
     return false;
 }
 
-// call_base for one cell from its histogram: errmod_cal + gl2cns + rms packing (popbam.cpp:288-298).
-// bmask: which bases occur (bit b).  Leaves the histogram cleared.
-template <class Hist>
-PB_HD uint64_t pb_call_from_hist(Hist &take, int n_lw, const uint8_t *qval, int k, int rmsq, uint32_t bmask, int r4,
-                                 const double *fk, const double *__restrict__ beta, const double *__restrict__ lhet) {
-    double bsum[4] = {0.0, 0.0, 0.0, 0.0};
-    int c[4] = {0, 0, 0, 0};
-    if (k > 0) {
-        if ((bmask & (bmask - 1)) == 0) {
-            const int b = (bmask >> 1 & 1) | ((bmask >> 2 & 1) << 1) | ((bmask >> 3 & 1) * 3);
-            const float hmin = pb_unanimous_het(lhet, k, b);
-            double B = 0.0;
-            if (pb_walk_unanimous(take, n_lw, qval, k, b, fk, beta, hmin, &B)) {
-                const uint64_t snpq = (uint64_t)PB_DADD((double)PB_FSUB(hmin, 0.0f), 0.499);
-                uint64_t cb = (snpq << 32) + ((uint64_t)(unsigned)k << 16) + ((uint64_t)(unsigned)(b << 2 | b) << 8);
-                const uint64_t rms = (uint64_t)PB_DADD((double)PB_FSQRT(PB_FDIV((float)rmsq, (float)k)), 0.499);
-                return cb | rms << 48;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { bsum[i] = i == b ? B : 0.0; c[i] = i == b ? k : 0; }
-        } else {
-            pb_walk_hist(take, n_lw, qval, k, r4, fk, beta, bsum, c);
-        }
+// tot4: the cell's per-base counts, one byte per base (== c[] of errmod_cal).
+PB_HD int pb_tot4_k(uint32_t tot4) { return (int)((tot4 & 255u) + ((tot4 >> 8) & 255u) + ((tot4 >> 16) & 255u) + (tot4 >> 24)); }
+PB_HD bool pb_tot4_unanimous(uint32_t tot4) {
+    return ((tot4 & 255u) != 0) + ((tot4 >> 8 & 255u) != 0) + ((tot4 >> 16 & 255u) != 0) + ((tot4 >> 24) != 0) == 1;
+}
+
+// call_base for a cell whose bases all agree (tot4 has one populated byte): errmod_cal + gl2cns + rms
+// packing (popbam.cpp:288-298) with the early exit described above.  Leaves the histogram cleared.
+template <class Hist, class Clear>
+PB_HD uint64_t pb_call_unanimous(Hist &take, Clear &clear, int n_lw, const uint8_t *qval, uint32_t tot4, int rmsq, const double *fk,
+                                 const double *__restrict__ beta, const double *__restrict__ lhet) {
+    const int b = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
+    const int k = pb_tot4_k(tot4);
+    const float hmin = pb_unanimous_het(lhet, k, b);
+    double B = 0.0;
+    if (pb_walk_unanimous(take, clear, n_lw, qval, k, b, fk, beta, hmin, &B)) {
+        const uint64_t snpq = (uint64_t)PB_DADD((double)PB_FSUB(hmin, 0.0f), 0.499);
+        const uint64_t cb = (snpq << 32) + ((uint64_t)(unsigned)k << 16) + ((uint64_t)(unsigned)(b << 2 | b) << 8);
+        const uint64_t rms = (uint64_t)PB_DADD((double)PB_FSQRT(PB_FDIV((float)rmsq, (float)k)), 0.499);
+        return cb | rms << 48;
     }
+    double bsum[4];
+    int c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { bsum[i] = i == b ? B : 0.0; c[i] = i == b ? k : 0; }
+    return pb_finish_cell(bsum, c, k, rmsq, lhet);
+}
+
+// call_base for any cell with k > 0 bases (the general path).  Leaves the histogram cleared.
+template <class Hist>
+PB_HD uint64_t pb_call_general(Hist &take, int n_lw, const uint8_t *qval, uint32_t tot4, int rmsq, const double *fk,
+                               const double *__restrict__ beta, const double *__restrict__ lhet) {
+    double bsum[4];
+    int c[4];
+    const int k = pb_tot4_k(tot4);
+    // rotate by the most frequent base so the lanes of a warp run their long loop in the same slot
+    const uint32_t c0 = tot4 & 255u, c1 = tot4 >> 8 & 255u, c2 = tot4 >> 16 & 255u, c3 = tot4 >> 24;
+    const uint32_t m01 = c0 >= c1 ? c0 : c1, m23 = c2 >= c3 ? c2 : c3;
+    const int r4 = m01 >= m23 ? (c0 >= c1 ? 0 : 1) : (c2 >= c3 ? 2 : 3);
+    pb_walk_hist(take, n_lw, qval, k, r4, fk, beta, bsum, c);
     return pb_finish_cell(bsum, c, k, rmsq, lhet);
 }

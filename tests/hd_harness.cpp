@@ -24,10 +24,15 @@ extern "C" uint64_t hd_call_cell(const double *fk, const double *beta, const dou
         int q = codes[i] >> 5; q = q < 4 ? 4 : q > 63 ? 63 : q;
         hist[qrank[q] * 2 + ((codes[i] >> 4) & 1)] += 1u << (8 * (codes[i] & 3));
     }
-    uint32_t bmask = 0;
-    for (int i = 0; i < k; ++i) bmask |= 1u << (codes[i] & 3);
+    uint32_t tot4 = 0;
+    for (int i = 0; i < k; ++i) tot4 += 1u << (8 * (codes[i] & 3));
+    (void)r4;
     auto take = [&](int lw) -> uint32_t { uint32_t w = hist[lw]; hist[lw] = 0; return w; };
-    const uint64_t cb = pb_call_from_hist(take, 2 * nl, qval, k, rmsq, bmask, r4, fk, beta, lhet);
+    auto clear = [&](int lw) { hist[lw] = 0; };
+    uint64_t cb;
+    if (k == 0) { double bs[4] = {0, 0, 0, 0}; int c[4] = {0, 0, 0, 0}; cb = pb_finish_cell(bs, c, 0, rmsq, lhet); }
+    else if (pb_tot4_unanimous(tot4)) cb = pb_call_unanimous(take, clear, 2 * nl, qval, tot4, rmsq, fk, beta, lhet);
+    else cb = pb_call_general(take, 2 * nl, qval, tot4, rmsq, fk, beta, lhet);
     for (int lw = 0; lw < 2 * nl; ++lw) if (hist[lw]) return ~0ULL;     // the histogram must come back cleared
     return cb;
 }
