@@ -20,8 +20,9 @@
 #include "pb_walk.cuh"
 
 #define PB_REC_DEAD (1u << 25)    // read fails min_mapQ: it only counts towards the raw-depth cap
-#define PB_REC_CAP 640            // segment records staged per round in the hot kernel
-#define PB_QCAP 128               // deferred (non-unanimous) cells per round
+#define PB_REC_CAP 384            // segment records staged per round in the hot kernel
+#define PB_BIN_SHIFT 7            // read-start bins of the depth bound (128 bp)
+#define PB_QCAP 96                // deferred (non-unanimous) cells per round
 #define PB_PART_CHUNK 2048        // reads per warp in the sample partition
 #define PB_KEY_DROP 0xffu
 #define PB_CODE_NONE 0xffu        // base filtered out (quality, N)
@@ -36,6 +37,8 @@ struct PbCounters {               // device-side region counters (one cudaMemcpy
     int unsorted;                     // pos[r] < pos[r-1] seen (bam_pileup.c:384-395)
     int n_levels;
     int too_long;                     // a read spans >= 65536 reference bases or has > 255 aligned segments
+    int depth_bound;                  // upper bound of the raw per-sample depth at any position
+    int nocap;                        // depth_bound <= max_depth: the raw-depth cap can never bind
     unsigned char qrank[64];          // quality value -> level
     unsigned char qval[64];           // level -> quality value (ascending)
 };
@@ -57,6 +60,7 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
                                                    const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
                                                    const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ,
                                                    uint8_t *__restrict__ rkey, uint8_t *__restrict__ rnseg,
+                                                   int bin_origin, int n_bins, uint32_t *__restrict__ bins,
                                                    PbCounters *__restrict__ ctr) {
     unsigned long long used = 0, aligned = 0, mqmask = 0;
     int span = 0, flags = 0;     // flags: 1 unsorted, 2 too long
@@ -78,6 +82,10 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
         rkey[r] = listed ? (uint8_t)smp : (uint8_t)PB_KEY_DROP;
         if (listed && (longseg || x - p > 65535 || nseg > PB_MAX_SEGS)) flags |= 2;
         rnseg[r] = (uint8_t)(nseg > PB_MAX_SEGS ? PB_MAX_SEGS : nseg);
+        if (listed) {   // read starts per (sample, 128 bp bin) for the depth bound (out-of-range starts clamp: still an upper bound)
+            const int b = min(n_bins - 1, max(0, (p - bin_origin) >> PB_BIN_SHIFT));
+            atomicAdd(&bins[(size_t)smp * n_bins + b], (uint32_t)(nseg > 0 ? nseg : 1));
+        }
         if (keep) {
             used += 1; aligned += (unsigned long long)al; span = max(span, x - p);
             const int mq = (int)((m >> 8) & 0xff);
@@ -108,6 +116,26 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
         if (flags & 2) atomicOr(&ctr->too_long, 1);
     }
 }
+
+// Upper bound of the raw depth of any (position, sample): the reads covering p start in (p - max_span, p],
+// i.e. inside m+1 consecutive 128 bp bins with m = ceil(max_span / 128).  When the bound does not exceed
+// max_depth the cap of call_base (popbam.cpp:242-248) can never bind, reads below min_mapQ contribute
+// nothing at all, and the hot kernel runs without depth bookkeeping.
+__global__ void __launch_bounds__(256) k_depth_bound(const uint32_t *__restrict__ bins, int n_samples, int n_bins, int max_depth,
+                                                     PbCounters *__restrict__ ctr) {
+    const int m = (ctr->max_span + (1 << PB_BIN_SHIFT) - 1) >> PB_BIN_SHIFT;
+    const int64_t total = (int64_t)n_samples * n_bins;
+    uint32_t best = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i % n_bins);
+        uint32_t sum = 0;
+        for (int d = 0; d <= m && d <= b; ++d) sum += bins[i - d];
+        best = max(best, sum);
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(&ctr->depth_bound, (int)min(best, 0x7fffffffu));
+}
+__global__ void k_depth_decide(int max_depth, PbCounters *ctr) { ctr->nocap = ctr->depth_bound <= max_depth ? 1 : 0; }
 
 // Which (adjusted) base qualities >= min_baseQ occur anywhere in the batch (superset of what the
 // pileup will use: clipped / inserted / padding bytes are included, harmlessly).
@@ -239,17 +267,20 @@ __global__ void k_encode(int64_t n, const uint32_t *__restrict__ meta, const uin
 // Stable partition of the kept reads by sample, expanding every read into its aligned segments.
 // One warp owns PB_PART_CHUNK consecutive reads, so the order inside a (chunk, sample) bucket is file
 // order; buckets are laid out sample-major, chunk-minor by an exclusive scan of the count matrix.
-__global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg, int n_samples,
+__global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg,
+                             const uint32_t *__restrict__ meta, int min_mapQ, const PbCounters *__restrict__ ctr, int n_samples,
                              int64_t n_chunks, uint32_t *__restrict__ counts /* [n_samples][n_chunks] */) {
     const int lane = threadIdx.x & 31;
+    const bool drop_dead = ctr->nocap != 0;
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk >= n_chunks) return;
     uint32_t c0 = 0, c1 = 0;   // lane owns samples lane and lane+32
     const int64_t r0 = chunk * PB_PART_CHUNK;
     for (int i = 0; i < PB_PART_CHUNK; i += 32) {
         const int64_t r = r0 + i + lane;
-        const uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
+        uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
         const uint32_t ns = r < n ? rnseg[r] : 0;
+        if (drop_dead && key != PB_KEY_DROP && (int)((meta[r] >> 8) & 0xffu) < min_mapQ) key = PB_KEY_DROP;
         // every lane sums the segment counts of the reads of its own two samples
         for (int src = 0; src < 32; ++src) {
             const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
@@ -271,8 +302,10 @@ __global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, cons
                                int64_t n_chunks, const uint32_t *__restrict__ offs /* scanned counts */,
                                const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta, const uint64_t *__restrict__ base,
                                const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
-                               const uint32_t *__restrict__ cigar, int min_mapQ, int4 *__restrict__ srec) {
+                               const uint32_t *__restrict__ cigar, int min_mapQ, const PbCounters *__restrict__ ctr,
+                               int4 *__restrict__ srec) {
     const int lane = threadIdx.x & 31;
+    const bool drop_dead = ctr->nocap != 0;
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk >= n_chunks) return;
     uint32_t cur0 = lane < n_samples ? offs[(int64_t)lane * n_chunks + chunk] : 0;
@@ -280,8 +313,9 @@ __global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, cons
     const int64_t r0 = chunk * PB_PART_CHUNK;
     for (int i = 0; i < PB_PART_CHUNK; i += 32) {
         const int64_t r = r0 + i + lane;
-        const uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
+        uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
         const uint32_t ns = r < n ? rnseg[r] : 0;
+        if (drop_dead && key != PB_KEY_DROP && (int)((meta[r] >> 8) & 0xffu) < min_mapQ) key = PB_KEY_DROP;
         // my rank: segments of earlier lanes with my key; cursor advance: segments per sample in this step
         uint32_t rank = 0, a0 = 0, a1 = 0;
         for (int src = 0; src < 32; ++src) {
@@ -411,21 +445,26 @@ struct PbPileArgs {
 
 // Dynamic shared memory of k_pileup_call<TP> for nl quality levels (independent of the sample count).
 static inline size_t pb_pile_smem(int tp, int nl) {
-    return (size_t)PB_REC_CAP * 16 + (size_t)2 * nl * tp * 4 + (size_t)PB_QCAP * (3 + 2 * nl) * 4 + (size_t)tp * 20 + 256 * 8 +
+    return (size_t)PB_REC_CAP * 32 + (size_t)2 * nl * tp * 4 + (size_t)PB_QCAP * (3 + 2 * nl) * 4 + (size_t)tp * 20 + 256 * 8 +
            128 * 4 + 64 + 64 * 16 + 64;
 }
 
 // One CTA = TP consecutive reference positions x all samples; one thread = one position.
 //
 // Rounds.  The CTA stages, for as many consecutive samples as fit, the candidate segment records
-// (reads starting in (p0 - max_span, p0 + TP)) in shared memory.  For each staged sample a WARP walks
-// the records that can cover any of its 32 positions, all lanes in lock step over the same record
-// (file order): coverage of a lane's position is one unsigned compare (p - seg_start < seg_len), the
-// raw-depth cap is applied before the base filter as in call_base (popbam.cpp:242-248), and the base's
-// pre-digested code (k_encode) is one byte load whose address is consecutive across the lanes.  The
-// body is branch-free (predicated), so the warp never splits.  Passing bases are counted in the
-// thread's private (level, strand) x base histogram in shared memory (plain read-modify-write, no
-// atomics) and in a packed per-base total.
+// (reads starting in (p0 - max_span, p0 + TP)) in shared memory, unpacked into two 16-byte halves so
+// the inner loop needs no field extraction.  For each staged sample a WARP walks the records that can
+// cover any of its 32 positions, all lanes in lock step over the same record (file order), two records
+// per iteration so two code loads are in flight: coverage of a lane's position is one unsigned compare
+// (p - seg_start < seg_len), and the base's pre-digested code (k_encode) is one byte load whose address
+// is consecutive across the lanes.  The body is predicated, so the warp never splits.  Passing bases
+// are counted in the thread's private (level, strand) x base histogram in shared memory (plain
+// read-modify-write, no atomics) and in a packed per-base total.
+//
+// CAP = true keeps call_base's raw-depth cap ("the first max_depth non-deleted reads in file order,
+// before the base filters", popbam.cpp:242-248).  When k_depth_bound proves that no cell can reach
+// max_depth the host launches CAP = false: the lists then hold only reads passing min_mapQ and there is
+// no depth bookkeeping.
 //
 // Calls.  After the last record of a sample, cells whose bases all agree (the overwhelming majority)
 // are called on the spot with the exact early-exit walk (pb_call_unanimous).  The others are deferred:
@@ -436,20 +475,21 @@ static inline size_t pb_pile_smem(int tp, int nl) {
 // Per-site logic (make_X, pop_nucdiv.cpp:148-197) is folded in sample by sample (pb_site_sample): a
 // position only keeps its coverage mask, derived-allele mask and derived-base counts (20 bytes of
 // shared memory), so nothing per (site, sample) is stored unless the caller asked for the cb words.
-template <int TP>
+template <int TP, bool CAP>
 __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n_samples;
     const int nl = a.ctr->n_levels;
     const int n_lw = 2 * nl;
     const int qstride = 3 + n_lw;
-    int4 *recs = reinterpret_cast<int4 *>(smem_raw);                        // [PB_REC_CAP]
-    uint32_t *hist = reinterpret_cast<uint32_t *>(recs + PB_REC_CAP);       // [n_lw][TP]
+    int4 *recA = reinterpret_cast<int4 *>(smem_raw);                        // [PB_REC_CAP] {read start, seg start, seg len, offset lo}
+    int4 *recB = recA + PB_REC_CAP;                                         // [PB_REC_CAP] {offset hi, strand*TP*4, mapq^2, dead}
+    uint32_t *hist = reinterpret_cast<uint32_t *>(recB + PB_REC_CAP);       // [n_lw][TP]
     uint32_t *queue = hist + (size_t)n_lw * TP;                             // [PB_QCAP][3 + n_lw]
-    uint64_t *s_cov = reinterpret_cast<uint64_t *>(queue + (size_t)PB_QCAP * qstride + ((PB_QCAP * qstride) & 1));   // [TP]
+    uint64_t *s_cov = reinterpret_cast<uint64_t *>(queue + (size_t)PB_QCAP * qstride);   // [TP]
     uint64_t *s_type = s_cov + TP;                                          // [TP]
     uint32_t *s_cnt4 = reinterpret_cast<uint32_t *>(s_type + TP);           // [TP]
-    double *fk_s = reinterpret_cast<double *>(s_cnt4 + TP + (TP & 1));      // [256]
+    double *fk_s = reinterpret_cast<double *>(s_cnt4 + TP);                 // [256]
     uint32_t *rng = reinterpret_cast<uint32_t *>(fk_s + 256);               // lo[64], hi[64]
     uint8_t *qval_s = reinterpret_cast<uint8_t *>(rng + 128);               // [64]
     int4 *plan = reinterpret_cast<int4 *>(qval_s + 64);                     // [64] {sample, src, count | last<<31, dst}
@@ -464,6 +504,8 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     // the warp's position range
     const int pw0 = p0 + (tid & ~31);
     const int pw1 = min(pw0 + 31, p_end - 1);
+    // lanes past the end of the span use a position no segment can cover
+    const int pq = valid ? p : 0x7fffffff;
 
     for (int i = tid; i < 256; i += TP) fk_s[i] = a.fk[i];
     if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
@@ -506,8 +548,20 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
         if (a.cb_out) a.cb_out[((int64_t)pos - a.span_beg) * n + smp] = cb;
     };
 
+    uint32_t *const my_hist = hist + tid;
     int depth = 0, rmsq = 0;
     uint32_t tot4 = 0;           // per-base counts of the cell, one byte each
+    // one record against this lane's position; `code` was loaded by the caller (PB_CODE_NONE when not taken)
+    auto count_base = [&](uint32_t code, const int4 &rb) {
+        if (code != PB_CODE_NONE) {
+            const uint32_t inc = 1u << ((code & 3u) << 3);
+            // word index (level*2 + strand) * TP  ==  byte offset (code & 0xfc) * (TP*2) + strand*TP*4
+            uint32_t *h = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(my_hist) + (code & 0xfcu) * (TP * 2) + rb.y);
+            *h += inc;
+            tot4 += inc;
+            rmsq += rb.z;
+        }
+    };
     for (;;) {
         __syncthreads();         // everybody is done with the previous round's plan, records and queue
         // ---- plan one round: consecutive samples (or a piece of one) whose records fit the staging area
@@ -532,64 +586,66 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
         for (int e = 0; e < ne; ++e) {
             const int4 pl = plan[e];
             const int cnt = pl.z & 0x7fffffff;
-            for (int i = tid; i < cnt; i += TP) recs[pl.w + i] = a.srec[(uint32_t)pl.y + i];
+            for (int i = tid; i < cnt; i += TP) {
+                const int4 r = a.srec[(uint32_t)pl.y + i];
+                const uint32_t z = (uint32_t)r.z, mq = (z >> 16) & 0xffu;
+                recA[pl.w + i] = make_int4(r.x, r.y, (int)(z & 0xffffu), r.w);
+                recB[pl.w + i] = make_int4((int)(z >> 26), (int)(((z >> 24) & 1u) * (TP * 4)), (int)(mq * mq), (int)((z >> 25) & 1u));
+            }
         }
         __syncthreads();
         for (int e = 0; e < ne; ++e) {
             const int4 pl = plan[e];
             const int cnt = pl.z & 0x7fffffff;
-            const int4 *rs = recs + pl.w;
+            const int4 *ra = recA + pl.w, *rb = recB + pl.w;
             if (pw0 < p_end) {                                         // warp-uniform
+                // records whose read starts in (pw0 - max_span, pw1]: [j, jend)
                 int j = 0, jh = cnt;
-                const int thr = pw0 - max_span;   // reads starting at or before thr end before the warp's first position
-                while (j < jh) { const int mid = (j + jh) >> 1; if (rs[mid].x > thr) jh = mid; else j = mid + 1; }
-                for (; j < cnt; ++j) {
-                    const int4 r = rs[j];                              // same record for every lane: broadcast
-                    if (r.x > pw1) break;                              // uniform
-                    const uint32_t u = (uint32_t)(p - r.y);
-                    const bool take = valid && u < ((uint32_t)r.z & 0xffffu) && depth < a.max_depth;   // cap precedes the filters
-                    depth += take;
-                    const bool live = take && !((uint32_t)r.z & PB_REC_DEAD);
-                    const uint64_t boff = ((uint64_t)((uint32_t)r.z >> 26) << 32) | (uint32_t)r.w;
-                    uint32_t code = PB_CODE_NONE;
-                    if (live) code = __ldg(a.codes + boff + u);
-                    if (code != PB_CODE_NONE) {
-                        const uint32_t inc = 1u << ((code & 3u) << 3);
-                        const int lw = (int)(code >> 2) * 2 + (int)(((uint32_t)r.z >> 24) & 1u);
-                        hist[lw * TP + tid] += inc;
-                        tot4 += inc;
-                        const int mapq = (int)(((uint32_t)r.z >> 16) & 0xffu);
-                        rmsq += mapq * mapq;
+                const int thr = pw0 - max_span;
+                while (j < jh) { const int mid = (j + jh) >> 1; if (ra[mid].x > thr) jh = mid; else j = mid + 1; }
+                int jend = j; jh = cnt;
+                while (jend < jh) { const int mid = (jend + jh) >> 1; if (ra[mid].x > pw1) jh = mid; else jend = mid + 1; }
+                for (; j + 1 < jend; j += 2) {
+                    const int4 a0 = ra[j], b0 = rb[j], a1 = ra[j + 1], b1 = rb[j + 1];   // same records for every lane: broadcast
+                    const uint32_t u0 = (uint32_t)(pq - a0.y), u1 = (uint32_t)(pq - a1.y);
+                    bool t0 = u0 < (uint32_t)a0.z, t1 = u1 < (uint32_t)a1.z;
+                    if (CAP) {                                         // the cap precedes the filters; dead reads count
+                        t0 = t0 && depth < a.max_depth; depth += t0;
+                        t1 = t1 && depth < a.max_depth; depth += t1;
+                        t0 = t0 && !b0.w; t1 = t1 && !b1.w;
                     }
+                    uint32_t c0 = PB_CODE_NONE, c1 = PB_CODE_NONE;
+                    if (t0) c0 = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
+                    if (t1) c1 = __ldg(a.codes + (((uint64_t)(uint32_t)b1.x << 32) | (uint32_t)a1.w) + u1);
+                    count_base(c0, b0);
+                    count_base(c1, b1);
+                }
+                if (j < jend) {
+                    const int4 a0 = ra[j], b0 = rb[j];
+                    const uint32_t u0 = (uint32_t)(pq - a0.y);
+                    bool t0 = u0 < (uint32_t)a0.z;
+                    if (CAP) { t0 = t0 && depth < a.max_depth; depth += t0; t0 = t0 && !b0.w; }
+                    uint32_t c0 = PB_CODE_NONE;
+                    if (t0) c0 = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
+                    count_base(c0, b0);
                 }
             }
             if (pl.z < 0) {      // last piece of this sample: call the cell
                 if (valid) {
-                    if (depth == 0) fold(tid, p, ref_c, ref_r, pl.x, 0, false);
-                    else if (tot4 == 0) {
-                        const double z4[4] = {0.0, 0.0, 0.0, 0.0};
-                        const int c4[4] = {0, 0, 0, 0};
-                        fold(tid, p, ref_c, ref_r, pl.x, pb_finish_cell(z4, c4, 0, rmsq, a.lhet), false);
-                    } else if (pb_tot4_unanimous(tot4)) {
-                        auto take = [&](int lw) -> uint32_t {
-                            const uint32_t w = hist[lw * TP + tid];
-                            if (w) hist[lw * TP + tid] = 0;
-                            return w;
-                        };
-                        auto clear = [&](int lw) { hist[lw * TP + tid] = 0; };
-                        fold(tid, p, ref_c, ref_r, pl.x, pb_call_unanimous(take, clear, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet), false);
+                    // raw depth 0, or depth > 0 with every base filtered: errmod_cal(n = 0) + gl2cns give cb = 0 either way
+                    if (tot4 == 0) fold(tid, p, ref_c, ref_r, pl.x, 0, false);
+                    else if (pb_tot4_unanimous(tot4)) {
+                        auto peek = [&](int lw) -> uint32_t { return my_hist[lw * TP]; };
+                        fold(tid, p, ref_c, ref_r, pl.x, pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet), false);
+                        for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * TP] = 0;
                     } else {
                         const uint32_t slot = atomicAdd(&plan_n[3], 1u);
                         if (slot < PB_QCAP) {          // defer: move the histogram into the queue
                             uint32_t *q = queue + (size_t)slot * qstride;
                             q[0] = (uint32_t)tid | ((uint32_t)pl.x << 16); q[1] = (uint32_t)rmsq; q[2] = tot4;
-                            for (int lw = 0; lw < n_lw; ++lw) { q[3 + lw] = hist[lw * TP + tid]; hist[lw * TP + tid] = 0; }
+                            for (int lw = 0; lw < n_lw; ++lw) { q[3 + lw] = my_hist[lw * TP]; my_hist[lw * TP] = 0; }
                         } else {                       // queue full: call it here
-                            auto take = [&](int lw) -> uint32_t {
-                                const uint32_t w = hist[lw * TP + tid];
-                                if (w) hist[lw * TP + tid] = 0;
-                                return w;
-                            };
+                            auto take = [&](int lw) -> uint32_t { const uint32_t w = my_hist[lw * TP]; my_hist[lw * TP] = 0; return w; };
                             fold(tid, p, ref_c, ref_r, pl.x, pb_call_general(take, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet), false);
                         }
                     }

@@ -53,7 +53,7 @@ struct pb_ctx {
     int64_t n_reads = 0, n_cig = 0, n_bytes = 0;
     DevBuf d_pos, d_meta, d_cigstart, d_ncig, d_base, d_cigar, d_seq4, d_qual, d_tmp_cig, d_tmp_base;
     // derived
-    DevBuf d_rkey, d_rnseg, d_codes, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
+    DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
     DevBuf d_num_sites, d_segsites, d_seg_off, d_seg_pos, d_seg_idx, d_seg_type, d_seg_ref, d_seg_cb;
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wr, d_wall_u, d_stats;
@@ -210,14 +210,24 @@ int run_pipeline(pb_ctx *c) {
     PB_TRY(dev_reserve(c, c->d_counts, sizeof(uint32_t) * (size_t)n_counts));
     PbCounters *ctr = dp<PbCounters>(c->d_ctr);
     const int illumina = (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0;
+    // read-start bins for the depth bound: 128 bp bins from 65536 bp before the span to its end
+    const int bin_origin = c->span_beg - 65536;
+    const int n_bins = (int)((span + 65536) >> PB_BIN_SHIFT) + 2;
+    PB_TRY(dev_reserve(c, c->d_bins, sizeof(uint32_t) * (size_t)n * n_bins));
+    PB_CUDA(c, cudaMemsetAsync(c->d_bins.p, 0, sizeof(uint32_t) * (size_t)n * n_bins, st));
     if (N > 0) {
         k_read_prep<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->n_sms * 8), 256, 0, st>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
                                                  dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), n, P.min_mapQ,
-                                                 dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), ctr);
+                                                 dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), bin_origin, n_bins,
+                                                 dp<uint32_t>(c->d_bins), ctr);
+        k_depth_bound<<<c->n_sms * 4, 256, 0, st>>>(dp<uint32_t>(c->d_bins), n, n_bins, P.max_depth, ctr);
+        c->launches += 1;
         k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
         c->launches += 2;
     }
     k_level_table<<<1, 32, 0, st>>>(ctr);
+    k_depth_decide<<<1, 1, 0, st>>>(P.max_depth, ctr);
+    c->launches += 1;
     if (N > 0) {
         k_encode<<<c->n_sms * 16, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
                                                dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ,
@@ -226,13 +236,14 @@ int run_pipeline(pb_ctx *c) {
     }
     PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
     const unsigned part_blocks = nblk(n_chunks * 32, 128);
-    k_part_count<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts));
+    k_part_count<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), dp<uint32_t>(c->d_meta), P.min_mapQ, ctr, n, n_chunks,
+                                             dp<uint32_t>(c->d_counts));
     c->launches += 2;
     PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts));
     k_sample_starts<<<1, 128, 0, st>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart));
     k_part_scatter<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts),
                                                dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
-                                               dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ,
+                                               dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
                                                dp<int4>(c->d_srec));
     c->launches += 2;
     PB_CUDA(c, cudaGetLastError());
@@ -251,7 +262,9 @@ int run_pipeline(pb_ctx *c) {
     const int nl = c->ctr_host.n_levels;
     const size_t smem = pb_pile_smem(kTP, nl);
     if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d samples x %d quality levels exceeds %zu bytes", n, nl, c->smem_optin);
-    PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool cap = c->ctr_host.nocap == 0;
+    if (cap) PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PbPileArgs pa;
     pa.srec = dp<int4>(c->d_srec); pa.sstart = dp<uint32_t>(c->d_sstart);
     pa.codes = dp<uint8_t>(c->d_codes);
@@ -266,7 +279,8 @@ int run_pipeline(pb_ctx *c) {
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
     PB_CUDA(c, cudaEventRecord(c->ev[2], st));
-    k_pileup_call<kTP><<<nblk(span, kTP), kTP, smem, st>>>(pa);
+    if (cap) k_pileup_call<kTP, true><<<nblk(span, kTP), kTP, smem, st>>>(pa);
+    else k_pileup_call<kTP, false><<<nblk(span, kTP), kTP, smem, st>>>(pa);
     c->launches += 1;
     PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaEventRecord(c->ev[3], st));
@@ -471,7 +485,7 @@ void pb_destroy(pb_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
                       &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rnseg,
-                      &c->d_rkey, &c->d_codes, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
+                      &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
                       &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
                       &c->d_seg_idx, &c->d_seg_type, &c->d_seg_ref, &c->d_seg_cb, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
                       &c->d_rsum, &c->d_wr, &c->d_wall_u, &c->d_stats};

@@ -78,14 +78,14 @@ PB_HD float pb_unanimous_het(const double *__restrict__ lhet, int k, int b) {
 
 // Walk of a unanimous cell: only byte b of every histogram word is populated.  Returns true when it
 // stopped early (result fully determined by hmin); otherwise *bsum_b is the complete sum.
-// `take(lw)` returns a word and clears it; `clear(lw)` only clears (used below the stopping point).
-template <class Hist, class Clear>
-PB_HD bool pb_walk_unanimous(Hist &take, Clear &clear, int n_lw, const uint8_t *qval, int k, int b, const double *fk,
+// `peek(lw)` returns a word; the caller clears the histogram afterwards.
+template <class Hist>
+PB_HD bool pb_walk_unanimous(Hist &peek, int n_lw, const uint8_t *qval, int k, int b, const double *fk,
                              const double *__restrict__ beta, float hmin, double *bsum_b) {
     double acc = 0.0;
     int c = 0, wf = 0, wr = 0;
     for (int lw = n_lw - 1; lw >= 0; --lw) {
-        const uint32_t word = take(lw);
+        const uint32_t word = peek(lw);
         if (word == 0) continue;
         const int m = (int)((word >> (8 * b)) & 255u);
         const int st = lw & 1;
@@ -93,10 +93,7 @@ PB_HD bool pb_walk_unanimous(Hist &take, Clear &clear, int n_lw, const uint8_t *
         const int w0 = st ? wr : wf;
         for (int t = 0; t < m; ++t) {
             acc = pb_errmod_step(acc, fk[w0 + t], PB_LDG(row + c + t));
-            if (hmin > 0.0f && PB_D2F(acc) >= hmin) {
-                for (int l = lw - 1; l >= 0; --l) clear(l);
-                return true;
-            }
+            if (hmin > 0.0f && PB_D2F(acc) >= hmin) return true;
         }
         c += m;
         if (st) wr += m; else wf += m;
@@ -112,15 +109,15 @@ PB_HD bool pb_tot4_unanimous(uint32_t tot4) {
 }
 
 // call_base for a cell whose bases all agree (tot4 has one populated byte): errmod_cal + gl2cns + rms
-// packing (popbam.cpp:288-298) with the early exit described above.  Leaves the histogram cleared.
-template <class Hist, class Clear>
-PB_HD uint64_t pb_call_unanimous(Hist &take, Clear &clear, int n_lw, const uint8_t *qval, uint32_t tot4, int rmsq, const double *fk,
+// packing (popbam.cpp:288-298) with the early exit described above.  The histogram is only read.
+template <class Hist>
+PB_HD uint64_t pb_call_unanimous(Hist &peek, int n_lw, const uint8_t *qval, uint32_t tot4, int rmsq, const double *fk,
                                  const double *__restrict__ beta, const double *__restrict__ lhet) {
     const int b = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
     const int k = pb_tot4_k(tot4);
     const float hmin = pb_unanimous_het(lhet, k, b);
     double B = 0.0;
-    if (pb_walk_unanimous(take, clear, n_lw, qval, k, b, fk, beta, hmin, &B)) {
+    if (pb_walk_unanimous(peek, n_lw, qval, k, b, fk, beta, hmin, &B)) {
         const uint64_t snpq = (uint64_t)PB_DADD((double)PB_FSUB(hmin, 0.0f), 0.499);
         const uint64_t cb = (snpq << 32) + ((uint64_t)(unsigned)k << 16) + ((uint64_t)(unsigned)(b << 2 | b) << 8);
         const uint64_t rms = (uint64_t)PB_DADD((double)PB_FSQRT(PB_FDIV((float)rmsq, (float)k)), 0.499);

@@ -28,10 +28,10 @@ extern "C" uint64_t hd_call_cell(const double *fk, const double *beta, const dou
     for (int i = 0; i < k; ++i) tot4 += 1u << (8 * (codes[i] & 3));
     (void)r4;
     auto take = [&](int lw) -> uint32_t { uint32_t w = hist[lw]; hist[lw] = 0; return w; };
-    auto clear = [&](int lw) { hist[lw] = 0; };
+    auto peek = [&](int lw) -> uint32_t { return hist[lw]; };
     uint64_t cb;
     if (k == 0) { double bs[4] = {0, 0, 0, 0}; int c[4] = {0, 0, 0, 0}; cb = pb_finish_cell(bs, c, 0, rmsq, lhet); }
-    else if (pb_tot4_unanimous(tot4)) cb = pb_call_unanimous(take, clear, 2 * nl, qval, tot4, rmsq, fk, beta, lhet);
+    else if (pb_tot4_unanimous(tot4)) { cb = pb_call_unanimous(peek, 2 * nl, qval, tot4, rmsq, fk, beta, lhet); memset(hist, 0, sizeof hist); }
     else cb = pb_call_general(take, 2 * nl, qval, tot4, rmsq, fk, beta, lhet);
     for (int lw = 0; lw < 2 * nl; ++lw) if (hist[lw]) return ~0ULL;     // the histogram must come back cleared
     return cb;
