@@ -138,10 +138,14 @@ __global__ void __launch_bounds__(256) k_depth_bound(const uint32_t *__restrict_
 __global__ void k_depth_decide(int max_depth, PbCounters *ctr) { ctr->nocap = ctr->depth_bound <= max_depth ? 1 : 0; }
 
 // Which (adjusted) base qualities >= min_baseQ occur anywhere in the batch (superset of what the
-// pileup will use: clipped / inserted / padding bytes are included, harmlessly).
-__global__ void k_qual_mask(const uint8_t *__restrict__ qual, int64_t n_bytes, int illumina, int min_baseQ,
-                            PbCounters *__restrict__ ctr) {
-    unsigned long long mask = 0;
+// pileup will use: clipped / inserted / padding bytes are included, harmlessly).  Streaming pass over
+// qual[]: every byte sets a presence flag in a 256-byte shared-memory table (two instructions per
+// byte; equal values hit the same address, so the stores do not conflict), one reduction per block.
+__global__ void __launch_bounds__(256) k_qual_mask(const uint8_t *__restrict__ qual, int64_t n_bytes, int illumina, int min_baseQ,
+                                                   PbCounters *__restrict__ ctr) {
+    __shared__ uint8_t seen[256];
+    seen[threadIdx.x] = 0;
+    __syncthreads();
     const int64_t nvec = n_bytes >> 4;
     const uint4 *q4 = reinterpret_cast<const uint4 *>(qual);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -155,19 +159,19 @@ __global__ void k_qual_mask(const uint8_t *__restrict__ qual, int64_t n_bytes, i
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    int q = (int)((w[j] >> (8 * b)) & 0xff);
-                    if (illumina) q = q > 31 ? q - 31 : 0;
-                    if (q >= min_baseQ) mask |= 1ULL << (q > 63 ? 63 : q);
-                }
+                for (int b = 0; b < 4; ++b) seen[(w[j] >> (8 * b)) & 0xffu] = 1;
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0)
-        for (int64_t i = nvec << 4; i < n_bytes; ++i) {
-            int q = qual[i];
-            if (illumina) q = q > 31 ? q - 31 : 0;
-            if (q >= min_baseQ) mask |= 1ULL << (q > 63 ? 63 : q);
-        }
+        for (int64_t i = nvec << 4; i < n_bytes; ++i) seen[qual[i]] = 1;
+    __syncthreads();
+    // one thread per raw quality value: transform, filter, clamp
+    unsigned long long mask = 0;
+    if (seen[threadIdx.x]) {
+        int q = (int)threadIdx.x;
+        if (illumina) q = q > 31 ? q - 31 : 0;
+        if (q >= min_baseQ) mask = 1ULL << (q > 63 ? 63 : q);
+    }
     for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
     if ((threadIdx.x & 31) == 0 && mask) atomicOr(&ctr->qual_mask, mask);
 }
@@ -194,73 +198,68 @@ __global__ void k_level_table(PbCounters *ctr) {
     ctr->n_levels = nl;
 }
 
-// The base filter and code of call_base (popbam.cpp:268-284), once per base instead of once per
-// (base, covering position... which is the same thing) but OUTSIDE the latency-bound pileup loop:
+// The base filter and code of call_base (popbam.cpp:268-284), once per base and OUTSIDE the
+// latency-bound pileup loop:
 //   code = level(clamp(min(baseQ', mapQ), 4, 63)) << 2 | nt4      or PB_CODE_NONE when the base is dropped
-// (baseQ' < min_baseQ, or not A/C/G/T).  One warp per read, lanes stride over the read's bases.  Reads
-// that are dropped or fail min_mapQ are skipped: the pileup never looks at their codes.
-__global__ void k_encode(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
-                         const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4, const uint8_t *__restrict__ qual,
-                         int64_t n_bytes, int illumina, int min_baseQ, int min_mapQ, const PbCounters *__restrict__ ctr,
-                         uint8_t *__restrict__ codes) {
+// (baseQ' < min_baseQ, not A/C/G/T, or the read is dropped / below min_mapQ).  A flat streaming pass:
+// each thread owns 16 consecutive bytes of qual[] (one 16-byte load, one 8-byte load of seq4[], one
+// 16-byte store).  The read owning a byte is found from base[] (reads are laid out back to back in file
+// order) starting from a proportional guess, which is exact for equal-length reads.
+__global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
+                                                const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4,
+                                                const uint8_t *__restrict__ qual, int64_t n_bytes, int illumina, int min_baseQ,
+                                                int min_mapQ, const PbCounters *__restrict__ ctr, uint8_t *__restrict__ codes) {
     __shared__ uint8_t qrank_s[64];
     if (threadIdx.x < 64) qrank_s[threadIdx.x] = ctr->qrank[threadIdx.x];
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
-        if (rkey[r] == PB_KEY_DROP) continue;
-        const int mapq = (int)((meta[r] >> 8) & 0xff);
-        if (mapq < min_mapQ) continue;
-        const uint64_t b0 = base[r];
-        const uint64_t b1 = r + 1 < n ? base[r + 1] : (uint64_t)n_bytes;     // reads are laid out back to back
-        const int len = (int)min((uint64_t)1 << 20, b1 - b0);
-        if ((b0 & 3) == 0) {
-            // four bases per lane: one 32-bit quality load, one 16-bit sequence load, one 32-bit store
-            const uint32_t *q32 = reinterpret_cast<const uint32_t *>(qual + b0);
-            const uint16_t *s16 = reinterpret_cast<const uint16_t *>(seq4 + (b0 >> 1));
-            uint32_t *c32 = reinterpret_cast<uint32_t *>(codes + b0);
-            const int nq = len >> 2;
-            for (int t = lane; t < nq; t += 32) {
-                const uint32_t qw = __ldg(q32 + t);
-                const uint32_t sw = __ldg(s16 + t);       // bytes: [b0 b1][b2 b3], high nibble first
-                uint32_t out = 0;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    int bq = (int)((qw >> (8 * i)) & 0xff);
-                    if (illumina) bq = bq > 31 ? bq - 31 : 0;
-                    const uint32_t nib = (sw >> (8 * (i >> 1) + ((~i & 1) << 2))) & 0xfu;
-                    const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
-                    int qq = min(bq, mapq);
-                    qq = max(4, min(63, qq));
-                    const uint32_t cd = (bq < min_baseQ || b4 > 3) ? PB_CODE_NONE : (uint32_t)(qrank_s[qq] << 2 | b4);
-                    out |= cd << (8 * i);
-                }
-                c32[t] = out;
-            }
-            for (int y = (nq << 2) + lane; y < len; y += 32) {
-                int bq = (int)__ldg(qual + b0 + y);
-                if (illumina) bq = bq > 31 ? bq - 31 : 0;
-                const uint32_t sb = __ldg(seq4 + (b0 >> 1) + (y >> 1));
-                const uint32_t nib = (sb >> ((~y & 1) << 2)) & 0xfu;
-                const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
-                int qq = min(bq, mapq);
-                qq = max(4, min(63, qq));
-                codes[b0 + y] = (bq < min_baseQ || b4 > 3) ? (uint8_t)PB_CODE_NONE : (uint8_t)(qrank_s[qq] << 2 | b4);
-            }
-            continue;
-        }
-        for (int y = lane; y < len; y += 32) {
-            int bq = (int)__ldg(qual + b0 + y);
-            if (illumina) bq = bq > 31 ? bq - 31 : 0;
-            const uint32_t sb = __ldg(seq4 + (b0 >> 1) + (y >> 1));
-            const uint32_t nib = (sb >> ((~y & 1) << 2)) & 0xfu;
-            const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
-            int qq = min(bq, mapq);
-            qq = max(4, min(63, qq));
-            codes[b0 + y] = (bq < min_baseQ || b4 > 3) ? (uint8_t)PB_CODE_NONE : (uint8_t)(qrank_s[qq] << 2 | b4);
-        }
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t o = (uint64_t)t << 4;
+    if ((int64_t)o >= n_bytes) return;
+    const int nb = (int)min((uint64_t)16, (uint64_t)n_bytes - o);
+    // owner of byte o: last r with base[r] <= o
+    int64_t lo = (int64_t)(((unsigned __int128)o * (unsigned __int128)n) / (unsigned __int128)n_bytes);
+    if (lo >= n) lo = n - 1;
+    int64_t hi = lo + 1, step = 1;
+    while (lo > 0 && __ldg(base + lo) > o) { hi = lo; lo = max((int64_t)0, lo - step); step <<= 1; }
+    step = 1;
+    while (hi < n && __ldg(base + hi) <= o) { lo = hi; hi = min(n, hi + step); step <<= 1; }
+    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (__ldg(base + mid) <= o) lo = mid; else hi = mid; }
+    int64_t r = lo;
+    uint64_t next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
+    auto read_mapq = [&](int64_t rr) -> int {       // -1: the pileup never looks at this read's codes
+        if (rkey[rr] == PB_KEY_DROP) return -1;
+        const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
+        return mq < min_mapQ ? -1 : mq;
+    };
+    int mapq = read_mapq(r);
+    uint32_t qw[4] = {0, 0, 0, 0}, sw[2] = {0, 0};
+    if (nb == 16) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(qual + o));
+        const uint2 s2 = __ldg(reinterpret_cast<const uint2 *>(seq4 + (o >> 1)));
+        qw[0] = v.x; qw[1] = v.y; qw[2] = v.z; qw[3] = v.w; sw[0] = s2.x; sw[1] = s2.y;
+    } else {
+        for (int i = 0; i < nb; ++i) qw[i >> 2] |= (uint32_t)qual[o + i] << (8 * (i & 3));
+        for (int i = 0; i < (nb + 1) / 2; ++i) sw[i >> 2] |= (uint32_t)seq4[(o >> 1) + i] << (8 * (i & 3));
     }
+    uint32_t out[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        while (o + i >= next) {                      // byte i starts the next read
+            ++r;
+            next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
+            mapq = read_mapq(r);
+        }
+        int bq = (int)((qw[i >> 2] >> (8 * (i & 3))) & 0xffu);
+        if (illumina) bq = bq > 31 ? bq - 31 : 0;
+        const uint32_t nib = (sw[i >> 3] >> (8 * ((i >> 1) & 3) + ((~i & 1) << 2))) & 0xfu;
+        const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+        int qq = min(bq, mapq);
+        qq = max(4, min(63, qq));
+        const uint32_t cd = (mapq < 0 || bq < min_baseQ || b4 > 3) ? PB_CODE_NONE : (uint32_t)(qrank_s[qq] << 2 | b4);
+        out[i >> 2] |= cd << (8 * (i & 3));
+    }
+    if (nb == 16) *reinterpret_cast<uint4 *>(codes + o) = make_uint4(out[0], out[1], out[2], out[3]);
+    else for (int i = 0; i < nb; ++i) codes[o + i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
 }
 
 // ------------------------------------------------------------------------------------------------

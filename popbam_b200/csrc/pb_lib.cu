@@ -229,7 +229,7 @@ int run_pipeline(pb_ctx *c) {
     k_depth_decide<<<1, 1, 0, st>>>(P.max_depth, ctr);
     c->launches += 1;
     if (N > 0) {
-        k_encode<<<c->n_sms * 16, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
+        k_encode<<<nblk((c->n_bytes + 15) / 16, 256), 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
                                                dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ,
                                                P.min_mapQ, ctr, dp<uint8_t>(c->d_codes));
         c->launches += 1;

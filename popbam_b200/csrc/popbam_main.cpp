@@ -1,0 +1,369 @@
+// popbam_main.cpp -- the `popbam` command line on the B200 path.
+//
+// Same command surface and output text as the reference's nucdiv / sfs / ld / diverge / haplo / snp
+// subcommands (popbam.cpp:53-77; option tables pop_nucdiv.cpp:297-414, pop_sfs.cpp:319-434,
+// pop_ld.cpp:460-584, pop_diverge.cpp:259-396, pop_haplo.cpp:460-580, pop_snp.cpp:319-446), but the
+// window loop of every main_X (e.g. pop_nucdiv.cpp:57-124) is replaced by:
+//   host threads:  BAI slicing + BGZF inflate + record decode of one region SHARD (a run of whole
+//                  windows) into a pb_read_batch                                     (pb_bamio.cpp)
+//   GPU threads:   pb_region_begin / pb_push_batch / pb_region_end on their own device, one pb_ctx each
+//   main thread:   prints the shards' rows in window order (pb_format_window)
+// Shards are independent (every window starts from an empty pileup), so the GPUs of
+// a box each take every G-th shard and no data crosses between them.
+//
+// Extra options (not in the reference): --gpus N, --shard-mb X, --threads T.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/popbam_b200.h"
+#include "pb_bamio.h"
+
+namespace {
+
+[[noreturn]] void fatal(const std::string &msg) {
+    // fatal_error (pop_utils.cpp:510-519) without the source position of the reference's call site
+    fprintf(stderr, "popbam runtime error:\n%s\nExiting program\n", msg.c_str());
+    exit(EXIT_FAILURE);
+}
+
+struct Options {
+    std::string cmd, reffile, headfile, outgroup, dist = "pdist";
+    int min_depth = 3, max_depth = 255, min_rmsQ = 25, min_snpQ = 25, min_mapQ = 13, min_baseQ = 13;
+    int min_sites = 10, min_snps = 10, win_size = 0, output = 0;
+    bool window = false, illumina = false, het = false, min_freq2 = false, substitute = false, has_p = false, has_h = false;
+    std::vector<std::string> positional;
+    int gpus = 1, threads = 0;
+    double shard_mb = 2.0;
+};
+
+// Option letters that take a value / that are flags, per subcommand (the reference's getopt_pp tables).
+struct CmdSpec { const char *name; const char *valued; const char *flags; };
+const CmdSpec kCmds[] = {
+    {"nucdiv", "fhmxqsabkw", "pin"},   // -p and -n are presence flags here (pop_nucdiv.cpp:326-331)
+    {"sfs", "fhmxqpsabkw", "i"},
+    {"ld", "fhmxqsaboznwk", "ie"},
+    {"diverge", "fhmxqsabkpwod", "nti"},
+    {"haplo", "fhomxqsabkw", "i"},
+    {"snp", "fhmxqsabozpw", "vi"},
+};
+
+void usage(const char *cmd) {
+    fprintf(stderr,
+            "Usage:   popbam %s [options] <in.bam> [region]\n"
+            "Options: -f FILE reference fastA   -w INT window (kb)   -m/-x INT min/max depth   -q INT min rms mapQ\n"
+            "         -s INT min snpQ   -a/-b INT min mapQ / baseQ   -k INT min sites   -o INT output mode   -p STR outgroup\n"
+            "         -i Illumina 1.3+ qualities   --gpus N   --shard-mb X   --threads T\n", cmd);
+}
+
+Options parse(int argc, char **argv) {
+    Options o;
+    o.cmd = argv[1];
+    const CmdSpec *spec = nullptr;
+    for (const CmdSpec &c : kCmds) if (o.cmd == c.name) spec = &c;
+    if (!spec) { fprintf(stderr, "Error: unrecognized command: %s\n", argv[1]); exit(1); }
+    for (int i = 2; i < argc; ++i) {
+        const std::string a = argv[i];
+        if (a.rfind("--", 0) == 0) {
+            auto val = [&]() -> const char * { if (i + 1 >= argc) fatal("missing value for " + a); return argv[++i]; };
+            if (a == "--gpus") o.gpus = atoi(val());
+            else if (a == "--shard-mb") o.shard_mb = atof(val());
+            else if (a == "--threads") o.threads = atoi(val());
+            else fatal("unknown option " + a);
+            continue;
+        }
+        if (a.size() >= 2 && a[0] == '-' && !isdigit((unsigned char)a[1])) {
+            // getopt_pp: every character of "-xyz" is an option; a value is the NEXT token, and only if that
+            // token is not itself an option (getopt_pp.cpp:81-143, getopt_pp.h:76-84)
+            for (size_t ci = 1; ci < a.size(); ++ci) {
+                const char c = a[ci];
+                const bool last = ci + 1 == a.size();
+                if (strchr(spec->valued, c)) {
+                    std::string v;
+                    bool have = false;
+                    if (last && i + 1 < argc) {
+                        const char *nx = argv[i + 1];
+                        const bool is_opt = nx[0] == '-' && nx[1] != '\0' && !isdigit((unsigned char)nx[1]);
+                        if (!is_opt) { v = argv[++i]; have = true; }
+                    }
+                    if (c == 'z' && o.cmd == "snp") o.het = true;          // OptionPresent('z') (pop_snp.cpp:353)
+                    if (c == 'h') o.has_h = true;
+                    if (c == 'w') o.window = true;
+                    if (c == 'p') o.has_p = true;
+                    if (!have) { if (c == 'w') o.win_size *= 1000; continue; }
+                    switch (c) {
+                    case 'f': o.reffile = v; break;
+                    case 'h': o.headfile = v; break;
+                    case 'm': o.min_depth = atoi(v.c_str()); break;
+                    case 'x': o.max_depth = atoi(v.c_str()); break;
+                    case 'q': o.min_rmsQ = atoi(v.c_str()); break;
+                    case 's': o.min_snpQ = atoi(v.c_str()); break;
+                    // -a / -b are stored in unsigned chars and read with operator>>, i.e. as ONE CHARACTER
+                    // (popbam.h:260-261): "-a 20" yields '2' == 50.  Reproduced for drop-in parity.
+                    case 'a': if (!v.empty()) o.min_mapQ = (unsigned char)v[0]; break;
+                    case 'b': if (!v.empty()) o.min_baseQ = (unsigned char)v[0]; break;
+                    case 'k': o.min_sites = atoi(v.c_str()); break;
+                    case 'n': o.min_snps = atoi(v.c_str()); break;
+                    case 'w': o.win_size = atoi(v.c_str()) * 1000; break;
+                    case 'o': o.output = atoi(v.c_str()); break;
+                    case 'p': o.outgroup = v; break;
+                    case 'd': o.dist = v; break;
+                    default: break;      // -z: value parsed and ignored
+                    }
+                } else if (strchr(spec->flags, c)) {
+                    switch (c) {
+                    case 'i': o.illumina = true; break;
+                    case 'e': o.min_freq2 = true; break;
+                    case 't': o.substitute = true; break;
+                    default: break;      // nucdiv -p, -n, -v: dead options
+                    }
+                } else fatal(std::string("unknown option -") + c);
+            }
+            continue;
+        }
+        o.positional.push_back(a);
+    }
+    return o;
+}
+
+struct Shard {
+    int w0, w1;                 // windows [w0, w1)
+    pbio::Batch batch;
+    std::string text;
+    std::string error;
+    int state = 0;              // 0 pending, 1 decoded, 2 done
+};
+
+struct Run {
+    Options opt;
+    pbio::BgzfFile bam;
+    pbio::BamHeader hdr;
+    pbio::SampleTable st;
+    pbio::BamIndex idx;
+    std::string ref;
+    int tid = -1, beg = 0, end = 0;
+    std::vector<int32_t> wb, we;
+    std::vector<Shard> shards;
+    pb_params prm;
+    uint32_t analysis = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::atomic<int> next_decode{0};
+    int max_ahead = 4;
+    int printed = 0;
+};
+
+void decode_worker(Run *R) {
+    for (;;) {
+        const int s = R->next_decode.fetch_add(1);
+        if (s >= (int)R->shards.size()) return;
+        {   // do not run too far ahead of the printer (bounds host memory)
+            std::unique_lock<std::mutex> lk(R->mu);
+            R->cv.wait(lk, [&] { return s < R->printed + R->max_ahead; });
+        }
+        Shard &sh = R->shards[s];
+        try {
+            pbio::fetch_region(R->bam, R->idx, R->st, R->tid, R->wb[sh.w0], R->we[sh.w1 - 1], sh.batch);
+        } catch (const pbio::Error &e) { sh.error = e.msg; }
+        std::lock_guard<std::mutex> lk(R->mu);
+        sh.state = 1;
+        R->cv.notify_all();
+    }
+}
+
+void gpu_worker(Run *R, int g, int G) {
+    pb_params prm = R->prm;
+    prm.device = g;
+    int st = 0;
+    pb_ctx *ctx = pb_create(&prm, nullptr, &st);
+    std::string err;
+    if (!ctx) err = std::string("cannot initialise GPU ") + std::to_string(g) + ": " + pb_last_error(nullptr);
+    else if (pb_set_contig(ctx, R->tid, R->ref.data(), (int64_t)R->ref.size()) != PB_OK) err = pb_last_error(ctx);
+    std::vector<const char *> pops, smps;
+    for (auto &s : R->st.pops) pops.push_back(s.c_str());
+    for (auto &s : R->st.samples) smps.push_back(s.c_str());
+    pb_print_opts po;
+    po.chrom = R->hdr.names[R->tid].c_str();
+    po.pop_names = pops.data(); po.sample_names = smps.data();
+    po.min_sites = R->opt.min_sites; po.min_snps = R->opt.min_snps;
+    po.jc = R->opt.dist == "jc"; po.snp_output = R->opt.output;
+    std::vector<char> line(1 << 16);
+    for (int s = g; s < (int)R->shards.size(); s += G) {
+        Shard &sh = R->shards[s];
+        {
+            std::unique_lock<std::mutex> lk(R->mu);
+            R->cv.wait(lk, [&] { return sh.state >= 1; });
+        }
+        if (err.empty() && sh.error.empty()) {
+            pbio::Batch &b = sh.batch;
+            pb_read_batch rb;
+            rb.n_reads = b.n_reads(); rb.n_cigar = (int64_t)b.cigar.size(); rb.n_bases = (int64_t)b.qual.size();
+            static const uint32_t zero = 0;
+            rb.pos = b.pos.data(); rb.meta = b.meta.data(); rb.cig_off = b.cig_off.data();
+            rb.cigar = b.cigar.empty() ? &zero : b.cigar.data();
+            rb.base_off = b.base_off.data(); rb.seq4 = b.seq4.data(); rb.qual = b.qual.data();
+            pb_region_result res;
+            int rc = pb_region_begin(ctx, R->analysis, sh.w1 - sh.w0, &R->wb[sh.w0], &R->we[sh.w0]);
+            if (rc == PB_OK && rb.n_reads > 0) rc = pb_push_batch(ctx, &rb);
+            if (rc == PB_OK) rc = pb_region_end(ctx, &res);
+            if (rc != PB_OK) sh.error = pb_last_error(ctx);
+            else
+                for (int w = 0; w < res.n_windows; ++w) {
+                    int64_t k = pb_format_window(ctx, &res, w, R->analysis, &po, line.data(), (int64_t)line.size());
+                    if (k >= (int64_t)line.size()) { line.resize((size_t)k + 16); k = pb_format_window(ctx, &res, w, R->analysis, &po, line.data(), (int64_t)line.size()); }
+                    if (k < 0) { sh.error = "formatting failed"; break; }
+                    sh.text.append(line.data(), (size_t)k);
+                }
+        } else if (sh.error.empty()) sh.error = err;
+        sh.batch = pbio::Batch();       // release the host memory
+        std::lock_guard<std::mutex> lk(R->mu);
+        sh.state = 2;
+        R->cv.notify_all();
+    }
+    if (ctx) pb_destroy(ctx);
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    if (argc < 2) {
+        fprintf(stderr, "Program: popbam (B200 path; %s)\nUsage:   popbam <command> [options] <in.bam> [region]\n"
+                        "Commands: snp haplo diverge nucdiv ld sfs\n", pb_version());
+        return 1;
+    }
+    if (!strcmp(argv[1], "_fetch")) {
+        // test hook (no GPU needed): popbam _fetch <in.bam> <region> <out.bin> dumps the host feeder's batch for the region
+        if (argc < 5) return 2;
+        try {
+            pbio::BgzfFile bam; bam.open(argv[2]);
+            pbio::BamHeader hdr = pbio::read_header(bam);
+            pbio::SampleTable st = pbio::build_samples(hdr.text, argv[2]);
+            pbio::BamIndex idx; idx.load(std::string(argv[2]) + ".bai", hdr.names.size());
+            int tid, beg, end;
+            if (!pbio::parse_region(hdr, argv[3], &tid, &beg, &end)) fatal(std::string("Bad genome coordinates: ") + argv[3]);
+            pbio::Batch b;
+            pbio::fetch_region(bam, idx, st, tid, beg, end, b);
+            FILE *f = fopen(argv[4], "wb");
+            if (!f) return 2;
+            const int64_t hdrv[6] = {b.n_reads(), (int64_t)b.cigar.size(), (int64_t)b.qual.size(), tid, beg, end};
+            fwrite(hdrv, 8, 6, f);
+            fwrite(b.pos.data(), 4, b.pos.size(), f); fwrite(b.meta.data(), 4, b.meta.size(), f);
+            fwrite(b.cig_off.data(), 4, b.cig_off.size(), f); fwrite(b.cigar.data(), 4, b.cigar.size(), f);
+            fwrite(b.base_off.data(), 4, b.base_off.size(), f); fwrite(b.seq4.data(), 1, b.seq4.size(), f);
+            fwrite(b.qual.data(), 1, b.qual.size(), f);
+            fclose(f);
+            printf("samples:"); for (auto &x : st.samples) printf(" %s", x.c_str());
+            printf("\npops:"); for (size_t i = 0; i < st.pops.size(); ++i) printf(" %s=%llx", st.pops[i].c_str(), (unsigned long long)st.pop_mask[i]);
+            printf("\n");
+        } catch (const pbio::Error &e) { fatal(e.msg); }
+        return 0;
+    }
+    Run R;
+    R.opt = parse(argc, argv);
+    Options &o = R.opt;
+    if (o.positional.size() < 2) { usage(o.cmd.c_str()); fatal("Need to specify BAM file name"); }
+    const std::string bamfile = o.positional[0], region = o.positional[1];
+    if (o.reffile.empty()) fatal("Need to specify fastA reference file");
+    if (o.cmd == "diverge" && o.dist != "pdist" && o.dist != "jc") fatal(o.dist + " is not a valid distance option");
+    try {
+        { std::ifstream t(bamfile); if (!t) fatal("Specified input file: " + bamfile + " does not exist"); }
+        { std::ifstream t(o.reffile); if (!t) fatal("Specified reference file: " + o.reffile + " does not exist"); }
+        R.bam.open(bamfile);
+        R.hdr = pbio::read_header(R.bam);
+        std::string text = R.hdr.text;
+        if (o.has_h) {      // -h: take the header text (sample / population definitions) from a file (popbam.cpp:119-127)
+            std::ifstream hin(o.headfile);
+            if (!hin) fatal("Cannot read header file " + o.headfile);
+            std::stringstream ss; ss << hin.rdbuf(); text = ss.str();
+        }
+        R.st = pbio::build_samples(text, bamfile);
+        R.idx.load(bamfile + ".bai", R.hdr.names.size());
+        if (!pbio::parse_region(R.hdr, region, &R.tid, &R.beg, &R.end)) fatal("Bad genome coordinates: " + region);
+        R.ref = pbio::fetch_contig(o.reffile, R.hdr.names[R.tid]);
+    } catch (const pbio::Error &e) { fatal(e.msg); }
+
+    // parameters == the popbamData fields the path reads
+    pb_params &p = R.prm;
+    memset(&p, 0, sizeof p);
+    p.n_samples = (int)R.st.samples.size(); p.n_pops = (int)R.st.pops.size();
+    for (int i = 0; i < 64; ++i) { p.pop_mask[i] = R.st.pop_mask[i]; p.pop_nsmpl[i] = R.st.pop_nsmpl[i]; }
+    p.min_depth = o.min_depth; p.max_depth = o.max_depth; p.min_rmsQ = o.min_rmsQ; p.min_snpQ = o.min_snpQ;
+    p.min_mapQ = o.min_mapQ; p.min_baseQ = o.min_baseQ;
+    p.min_freq = o.min_freq2 ? 2 : 1;
+    if (o.illumina) p.flags |= PB_FLAG_ILLUMINA;
+    if (o.het) p.flags |= PB_FLAG_HETEROZYGOTE;
+    if (o.substitute) p.flags |= PB_FLAG_SUBSTITUTE;
+    const bool uses_outgroup = o.has_p && (o.cmd == "sfs" || o.cmd == "diverge" || o.cmd == "snp");
+    if (uses_outgroup) {
+        int found = -1;
+        for (int i = 0; i < p.n_samples; ++i) if (R.st.samples[i] == o.outgroup) found = i;   // last match wins, as in the reference
+        if (found < 0) fatal("Specified outgroup " + o.outgroup + " not found");
+        p.outidx = found; p.flags |= PB_FLAG_OUTGROUP;
+    }
+    if (o.cmd == "nucdiv") R.analysis = PB_AN_NUCDIV;
+    else if (o.cmd == "sfs") R.analysis = PB_AN_SFS;
+    else if (o.cmd == "ld") R.analysis = o.output == 1 ? PB_AN_LD_OMEGA : o.output == 2 ? PB_AN_LD_WALL : PB_AN_LD_ZNS;
+    else if (o.cmd == "diverge") R.analysis = o.output == 1 ? PB_AN_DIVERGE_POP : PB_AN_DIVERGE_IND;
+    else if (o.cmd == "haplo") R.analysis = o.output == 1 ? PB_AN_HAPLO_EHHS : o.output == 2 ? PB_AN_HAPLO_DXY : PB_AN_HAPLO_K;
+    else R.analysis = PB_AN_SNP;
+    if (o.output < 0 || o.output > 2) fatal("invalid output option");
+
+    // window grid of the region, then shards = runs of whole windows
+    const int64_t nw = pb_window_grid(R.beg, R.end, o.window ? o.win_size : 0, 0, nullptr, nullptr);
+    if (nw < 1) return 0;       // region shorter than one window: the reference's loop does not execute
+    R.wb.resize((size_t)nw); R.we.resize((size_t)nw);
+    pb_window_grid(R.beg, R.end, o.window ? o.win_size : 0, nw, R.wb.data(), R.we.data());
+    const int64_t shard_bp = std::max<int64_t>(1, (int64_t)(o.shard_mb * 1e6));
+    for (int w = 0; w < (int)nw;) {
+        int e = w + 1;
+        while (e < (int)nw && (int64_t)R.we[e] - R.wb[w] <= shard_bp) ++e;
+        Shard sh; sh.w0 = w; sh.w1 = e;
+        R.shards.push_back(std::move(sh));
+        w = e;
+    }
+    const int G = std::max(1, o.gpus);
+    const int D = o.threads > 0 ? o.threads : std::max(2u, std::min(16u, std::thread::hardware_concurrency()));
+    R.max_ahead = std::max(2 * G + 2, std::min(D, 8));
+
+    if (o.cmd == "snp" && o.output == 2) {      // print_ms_header (pop_snp.cpp:305-317)
+        printf("ms %d %lld -t 5.0 ", p.n_samples, (long long)nw);
+        if (p.n_pops > 1) {
+            printf("-I %d ", p.n_pops);
+            for (int i = 0; i < p.n_pops; ++i) printf("%d ", (int)p.pop_nsmpl[i]);
+        }
+        printf("\n1350154902\n\n");
+    }
+
+    std::vector<std::thread> th;
+    for (int i = 0; i < D; ++i) th.emplace_back(decode_worker, &R);
+    for (int g = 0; g < G; ++g) th.emplace_back(gpu_worker, &R, g, G);
+    int rc = 0;
+    for (size_t s = 0; s < R.shards.size(); ++s) {
+        Shard &sh = R.shards[s];
+        {
+            std::unique_lock<std::mutex> lk(R.mu);
+            R.cv.wait(lk, [&] { return sh.state == 2; });
+        }
+        if (!sh.error.empty()) { fflush(stdout); fprintf(stderr, "popbam runtime error:\n%s\nExiting program\n", sh.error.c_str()); rc = 1; }
+        else fwrite(sh.text.data(), 1, sh.text.size(), stdout);
+        sh.text.clear(); sh.text.shrink_to_fit();
+        {
+            std::lock_guard<std::mutex> lk(R.mu);
+            R.printed = (int)s + 1;
+            R.cv.notify_all();
+        }
+        if (rc) { fflush(stdout); _Exit(EXIT_FAILURE); }
+    }
+    for (auto &t : th) t.join();
+    fflush(stdout);
+    return rc;
+}
