@@ -20,9 +20,9 @@
 #include "pb_walk.cuh"
 
 #define PB_REC_DEAD (1u << 25)    // read fails min_mapQ: it only counts towards the raw-depth cap
-#define PB_REC_CAP 384            // segment records staged per round in the hot kernel
+#define PB_REC_CAP 320            // segment records staged per round in the hot kernel
 #define PB_BIN_SHIFT 7            // read-start bins of the depth bound (128 bp)
-#define PB_QCAP 96                // deferred (non-unanimous) cells per round
+#define PB_QCAP 64                // deferred (non-unanimous) cells per round
 #define PB_PART_CHUNK 2048        // reads per warp in the sample partition
 #define PB_KEY_DROP 0xffu
 #define PB_CODE_NONE 0xffu        // base filtered out (quality, N)
@@ -198,26 +198,42 @@ __global__ void k_level_table(PbCounters *ctr) {
     ctr->n_levels = nl;
 }
 
+// need[L][k] of pb_need_entry for every level of the region and every depth: one thread per entry.
+__global__ void __launch_bounds__(256) k_need_table(const PbCounters *__restrict__ ctr, const double *__restrict__ fk,
+                                                    const double *__restrict__ beta, const double *__restrict__ lhet,
+                                                    uint8_t *__restrict__ need /* [64][256] */) {
+    const int L = blockIdx.x, k = threadIdx.x, nl = ctr->n_levels;
+    need[L * 256 + k] = L < nl ? pb_need_entry(L, nl, ctr->qval, k, fk, beta, lhet) : 0;
+}
+
 // The base filter and code of call_base (popbam.cpp:268-284), once per base and OUTSIDE the
 // latency-bound pileup loop:
 //   code = level(clamp(min(baseQ', mapQ), 4, 63)) << 2 | nt4      or PB_CODE_NONE when the base is dropped
 // (baseQ' < min_baseQ, not A/C/G/T, or the read is dropped / below min_mapQ).  A flat streaming pass:
 // each thread owns 16 consecutive bytes of qual[] (one 16-byte load, one 8-byte load of seq4[], one
-// 16-byte store).  The read owning a byte is found from base[] (reads are laid out back to back in file
-// order) starting from a proportional guess, which is exact for equal-length reads.
+// 16-byte store) and works on four bases at a time with byte-SIMD min / compare; the level and the
+// 2-base sequence byte go through small shared-memory tables.  The read owning a byte is found from
+// base[] (reads are laid out back to back in file order) starting from a proportional guess, which is
+// exact for equal-length reads.
 __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
                                                 const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4,
                                                 const uint8_t *__restrict__ qual, int64_t n_bytes, int illumina, int min_baseQ,
                                                 int min_mapQ, const PbCounters *__restrict__ ctr, uint8_t *__restrict__ codes) {
-    __shared__ uint8_t qrank_s[64];
-    if (threadIdx.x < 64) qrank_s[threadIdx.x] = ctr->qrank[threadIdx.x];
+    __shared__ uint8_t lvl4_s[64];        // quality 0..63 -> level << 2
+    __shared__ uint16_t seq_s[256];       // packed sequence byte -> nt4 of its two bases (0xff: not A/C/G/T), first base low
+    if (threadIdx.x < 64) lvl4_s[threadIdx.x] = (uint8_t)(ctr->qrank[max(4, (int)threadIdx.x)] << 2);
+    {
+        const uint32_t hi = threadIdx.x >> 4, lo = threadIdx.x & 15;
+        const uint32_t bh = (uint32_t)((PB_NT16_NT4_LUT >> (hi * 4)) & 0xf), bl = (uint32_t)((PB_NT16_NT4_LUT >> (lo * 4)) & 0xf);
+        seq_s[threadIdx.x] = (uint16_t)((bh > 3 ? 0xffu : bh) | (bl > 3 ? 0xffu : bl) << 8);
+    }
     __syncthreads();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t o = (uint64_t)t << 4;
     if ((int64_t)o >= n_bytes) return;
     const int nb = (int)min((uint64_t)16, (uint64_t)n_bytes - o);
     // owner of byte o: last r with base[r] <= o
-    int64_t lo = (int64_t)(((unsigned __int128)o * (unsigned __int128)n) / (unsigned __int128)n_bytes);
+    int64_t lo = (int64_t)((double)o * ((double)n / (double)n_bytes));
     if (lo >= n) lo = n - 1;
     int64_t hi = lo + 1, step = 1;
     while (lo > 0 && __ldg(base + lo) > o) { hi = lo; lo = max((int64_t)0, lo - step); step <<= 1; }
@@ -241,22 +257,43 @@ __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__res
         for (int i = 0; i < nb; ++i) qw[i >> 2] |= (uint32_t)qual[o + i] << (8 * (i & 3));
         for (int i = 0; i < (nb + 1) / 2; ++i) sw[i >> 2] |= (uint32_t)seq4[(o >> 1) + i] << (8 * (i & 3));
     }
-    uint32_t out[4] = {0, 0, 0, 0};
+    const uint32_t minq4 = (uint32_t)min(min_baseQ, 255) * 0x01010101u;
+    uint32_t out[4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        while (o + i >= next) {                      // byte i starts the next read
-            ++r;
-            next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
-            mapq = read_mapq(r);
+    for (int g = 0; g < 4; ++g) {
+        uint32_t q4 = qw[g];
+        if (illumina) q4 = __vsubus4(q4, 0x1f1f1f1fu);                    // baseQ' = baseQ > 31 ? baseQ - 31 : 0
+        const uint32_t pass4 = min_baseQ > 255 ? 0u : __vcmpgeu4(q4, minq4);
+        // nt4 of the group's four bases: two sequence bytes through the table
+        const uint32_t sb = sw[g >> 1] >> (16 * (g & 1));
+        const uint32_t b44 = (uint32_t)seq_s[sb & 0xffu] | (uint32_t)seq_s[(sb >> 8) & 0xffu] << 16;
+        const uint64_t gbeg = o + 4 * g;
+        uint32_t code4;
+        if (gbeg + 4 <= next) {                                           // the whole group belongs to read r
+            if (mapq < 0) code4 = 0xffffffffu;
+            else {
+                const uint32_t m4 = __vminu4(__vminu4(q4, (uint32_t)min(mapq, 63) * 0x01010101u), 0x3f3f3f3fu);
+                const uint32_t l4 = (uint32_t)lvl4_s[m4 & 0xffu] | (uint32_t)lvl4_s[(m4 >> 8) & 0xffu] << 8 |
+                                    (uint32_t)lvl4_s[(m4 >> 16) & 0xffu] << 16 | (uint32_t)lvl4_s[m4 >> 24] << 24;
+                // invalid bases are 0xff in b44; failed qualities have pass4 == 0: both become PB_CODE_NONE (0xff)
+                code4 = (l4 | b44) | ~pass4 | __vcmpeq4(b44, 0xffffffffu);
+            }
+        } else {                                                          // a read boundary inside the group: byte by byte
+            code4 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                while (gbeg + i >= next) {
+                    ++r;
+                    next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
+                    mapq = read_mapq(r);
+                }
+                const uint32_t bq = (q4 >> (8 * i)) & 0xffu, b4 = (b44 >> (8 * i)) & 0xffu;
+                const uint32_t qq = min(min(bq, (uint32_t)max(mapq, 0)), 63u);
+                const bool ok = mapq >= 0 && ((pass4 >> (8 * i)) & 1u) && b4 != 0xffu;
+                code4 |= (ok ? ((uint32_t)lvl4_s[qq] | b4) : (uint32_t)PB_CODE_NONE) << (8 * i);
+            }
         }
-        int bq = (int)((qw[i >> 2] >> (8 * (i & 3))) & 0xffu);
-        if (illumina) bq = bq > 31 ? bq - 31 : 0;
-        const uint32_t nib = (sw[i >> 3] >> (8 * ((i >> 1) & 3) + ((~i & 1) << 2))) & 0xfu;
-        const int b4 = (int)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
-        int qq = min(bq, mapq);
-        qq = max(4, min(63, qq));
-        const uint32_t cd = (mapq < 0 || bq < min_baseQ || b4 > 3) ? PB_CODE_NONE : (uint32_t)(qrank_s[qq] << 2 | b4);
-        out[i >> 2] |= cd << (8 * (i & 3));
+        out[g] = code4;
     }
     if (nb == 16) *reinterpret_cast<uint4 *>(codes + o) = make_uint4(out[0], out[1], out[2], out[3]);
     else for (int i = 0; i < nb; ++i) codes[o + i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
@@ -437,6 +474,7 @@ struct PbPileArgs {
     int het_mode;
     const double *fk, *beta, *lhet;
     const PbCounters *ctr;          // max_span, level table
+    const uint8_t *need;            // [64][256] walk-free shortcut table (k_need_table)
     uint64_t *site_type;            // [span]
     uint8_t *site_flag;             // [span]  bit0 used, bit1 segregating
     uint64_t *cb_out;               // [span * n_samples] or null
@@ -445,7 +483,7 @@ struct PbPileArgs {
 // Dynamic shared memory of k_pileup_call<TP> for nl quality levels (independent of the sample count).
 static inline size_t pb_pile_smem(int tp, int nl) {
     return (size_t)PB_REC_CAP * 32 + (size_t)2 * nl * tp * 4 + (size_t)PB_QCAP * (3 + 2 * nl) * 4 + (size_t)tp * 20 + 256 * 8 +
-           128 * 4 + 64 + 64 * 16 + 64;
+           128 * 4 + 64 + 64 * 16 + 64 + (size_t)nl * 256;
 }
 
 // One CTA = TP consecutive reference positions x all samples; one thread = one position.
@@ -475,7 +513,7 @@ static inline size_t pb_pile_smem(int tp, int nl) {
 // position only keeps its coverage mask, derived-allele mask and derived-base counts (20 bytes of
 // shared memory), so nothing per (site, sample) is stored unless the caller asked for the cb words.
 template <int TP, bool CAP>
-__global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
+__global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n_samples;
     const int nl = a.ctr->n_levels;
@@ -493,6 +531,7 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     uint8_t *qval_s = reinterpret_cast<uint8_t *>(rng + 128);               // [64]
     int4 *plan = reinterpret_cast<int4 *>(qval_s + 64);                     // [64] {sample, src, count | last<<31, dst}
     uint32_t *plan_n = reinterpret_cast<uint32_t *>(plan + 64);             // [0] entries, [1] next sample, [2] next src, [3] queue fill
+    uint8_t *need_s = reinterpret_cast<uint8_t *>(plan_n + 16);             // [nl][256]
 
     const int tid = threadIdx.x;
     const int p0 = a.span_beg + (int)blockIdx.x * TP;
@@ -500,6 +539,7 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
     const int p_end = min(p0 + TP, a.span_end);
     const bool valid = p < p_end;
     const int max_span = a.ctr->max_span;
+    for (int i = tid; i < nl * 64; i += TP) reinterpret_cast<uint32_t *>(need_s)[i] = reinterpret_cast<const uint32_t *>(a.need)[i];
     // the warp's position range
     const int pw0 = p0 + (tid & ~31);
     const int pw1 = min(pw0 + 31, p_end - 1);
@@ -635,7 +675,13 @@ __global__ void __launch_bounds__(TP) k_pileup_call(const PbPileArgs a) {
                     if (tot4 == 0) fold(tid, p, ref_c, ref_r, pl.x, 0, false);
                     else if (pb_tot4_unanimous(tot4)) {
                         auto peek = [&](int lw) -> uint32_t { return my_hist[lw * TP]; };
-                        fold(tid, p, ref_c, ref_r, pl.x, pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet), false);
+                        const int kk = pb_tot4_k(tot4);
+                        const int bb = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
+                        // count test against the need table (no error-model arithmetic); exact early-exit walk otherwise
+                        const uint64_t cbw = pb_unanimous_by_count(peek, nl, need_s, kk, bb)
+                                                 ? pb_unanimous_result(a.lhet, kk, bb, rmsq)
+                                                 : pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet);
+                        fold(tid, p, ref_c, ref_r, pl.x, cbw, false);
                         for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * TP] = 0;
                     } else {
                         const uint32_t slot = atomicAdd(&plan_n[3], 1u);

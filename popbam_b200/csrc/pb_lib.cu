@@ -53,7 +53,7 @@ struct pb_ctx {
     int64_t n_reads = 0, n_cig = 0, n_bytes = 0;
     DevBuf d_pos, d_meta, d_cigstart, d_ncig, d_base, d_cigar, d_seq4, d_qual, d_tmp_cig, d_tmp_base;
     // derived
-    DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
+    DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
     DevBuf d_num_sites, d_segsites, d_seg_off, d_seg_pos, d_seg_idx, d_seg_type, d_seg_ref, d_seg_cb;
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wr, d_wall_u, d_stats;
@@ -227,7 +227,9 @@ int run_pipeline(pb_ctx *c) {
     }
     k_level_table<<<1, 32, 0, st>>>(ctr);
     k_depth_decide<<<1, 1, 0, st>>>(P.max_depth, ctr);
-    c->launches += 1;
+    PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
+    k_need_table<<<64, 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
+    c->launches += 2;
     if (N > 0) {
         k_encode<<<nblk((c->n_bytes + 15) / 16, 256), 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
                                                dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ,
@@ -276,6 +278,7 @@ int run_pipeline(pb_ctx *c) {
     pa.het_mode = (P.flags & PB_FLAG_HETEROZYGOTE) ? 1 : 0;
     pa.fk = dp<double>(c->d_fk); pa.beta = dp<double>(c->d_beta); pa.lhet = dp<double>(c->d_lhet);
     pa.ctr = ctr;
+    pa.need = dp<uint8_t>(c->d_need);
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
     PB_CUDA(c, cudaEventRecord(c->ev[2], st));
@@ -485,7 +488,7 @@ void pb_destroy(pb_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
                       &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rnseg,
-                      &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
+                      &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_need, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
                       &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
                       &c->d_seg_idx, &c->d_seg_type, &c->d_seg_ref, &c->d_seg_cb, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
                       &c->d_rsum, &c->d_wr, &c->d_wall_u, &c->d_stats};

@@ -144,3 +144,55 @@ PB_HD uint64_t pb_call_general(Hist &take, int n_lw, const uint8_t *qval, uint32
     pb_walk_hist(take, n_lw, qval, k, r4, fk, beta, bsum, c);
     return pb_finish_cell(bsum, c, k, rmsq, lhet);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Walk-free test for unanimous cells.  Let the cell hold `cum` bases of quality >= q_L (level L).  In
+// errmod_cal's descending walk these are terms c = 0 .. cum-1, each fk[w]*beta[q',k,c] with w <= c and
+// q' >= q_L, hence each term (and, rounding being monotone, every partial sum) is at least the
+// corresponding one of
+//     LB(L,k,m) = sum_{c<m} min_{w<=c} fk[w] * min_{L'>=L} beta[q_L',k,c]      (same order, same rounding)
+// need[L][k] is the smallest m with float(LB(L,k,m)) >= max(het values of k); a cell with cum >= need
+// therefore has float(bsum) >= its het value and takes the shortcut result without touching beta.
+// 0 means "never".  One table per region (the levels are per region), built by k_need_table.
+PB_HD uint8_t pb_need_entry(int L, int nl, const uint8_t *qval, int k, const double *fk, const double *__restrict__ beta,
+                            const double *__restrict__ lhet) {
+    if (k < 1 || k > 255) return 0;
+    const float h0 = pb_unanimous_het(lhet, k, 0), h3 = pb_unanimous_het(lhet, k, 3);    // the two het values
+    if (!(h0 > 0.0f) || !(h3 > 0.0f)) return 0;
+    const float hcap = h0 > h3 ? h0 : h3;
+    double acc = 0.0, fkmin = fk[0];
+    for (int c = 0; c < k; ++c) {
+        if (fk[c] < fkmin) fkmin = fk[c];
+        double bmin = PB_LDG(beta + ((size_t)qval[L] << 16 | (size_t)k << 8 | (size_t)c));
+        for (int l2 = L + 1; l2 < nl; ++l2) {
+            const double v = PB_LDG(beta + ((size_t)qval[l2] << 16 | (size_t)k << 8 | (size_t)c));
+            if (v < bmin) bmin = v;
+        }
+        if (!(bmin >= 0.0)) return 0;
+        acc = pb_errmod_step(acc, fkmin, bmin);
+        if (PB_D2F(acc) >= hcap) return (uint8_t)(c + 1);
+    }
+    return 0;
+}
+
+// The shortcut result of a unanimous cell (see pb_unanimous_het): genotype (b,b), snpQ from the het value.
+PB_HD uint64_t pb_unanimous_result(const double *__restrict__ lhet, int k, int b, int rmsq) {
+    const float hmin = pb_unanimous_het(lhet, k, b);
+    const uint64_t snpq = (uint64_t)PB_DADD((double)PB_FSUB(hmin, 0.0f), 0.499);
+    const uint64_t cb = (snpq << 32) + ((uint64_t)(unsigned)k << 16) + ((uint64_t)(unsigned)(b << 2 | b) << 8);
+    const uint64_t rms = (uint64_t)PB_DADD((double)PB_FSQRT(PB_FDIV((float)rmsq, (float)k)), 0.499);
+    return cb | rms << 48;
+}
+
+// need: [nl][256].  Returns true when the cell provably takes the shortcut.
+template <class Hist>
+PB_HD bool pb_unanimous_by_count(Hist &peek, int nl, const uint8_t *need, int k, int b) {
+    int cum = 0;
+    for (int L = nl - 1; L >= 0; --L) {
+        cum += (int)((peek(2 * L) >> (8 * b)) & 255u) + (int)((peek(2 * L + 1) >> (8 * b)) & 255u);
+        const int nd = need[L * 256 + k];
+        if (nd && cum >= nd) return true;
+        if (cum == k) break;
+    }
+    return false;
+}

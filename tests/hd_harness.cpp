@@ -7,6 +7,9 @@
 #include "../popbam_b200/csrc/pb_cell.cuh"
 #include "../popbam_b200/csrc/pb_walk.cuh"
 
+static long g_by_count = 0;
+extern "C" long hd_by_count() { return g_by_count; }
+
 extern "C" uint64_t hd_call_cell(const double *fk, const double *beta, const double *lhet, const uint16_t *codes, int k, int rmsq,
                                  int r4) {
     // level table of the codes present, ascending (what k_level_table builds for a region)
@@ -31,7 +34,15 @@ extern "C" uint64_t hd_call_cell(const double *fk, const double *beta, const dou
     auto peek = [&](int lw) -> uint32_t { return hist[lw]; };
     uint64_t cb;
     if (k == 0) { double bs[4] = {0, 0, 0, 0}; int c[4] = {0, 0, 0, 0}; cb = pb_finish_cell(bs, c, 0, rmsq, lhet); }
-    else if (pb_tot4_unanimous(tot4)) { cb = pb_call_unanimous(peek, 2 * nl, qval, tot4, rmsq, fk, beta, lhet); memset(hist, 0, sizeof hist); }
+    else if (pb_tot4_unanimous(tot4)) {
+        // the kernel's order: count test against the need table first, exact early-exit walk otherwise
+        static thread_local uint8_t need[64 * 256];
+        for (int L = 0; L < nl; ++L) need[L * 256 + k] = pb_need_entry(L, nl, qval, k, fk, beta, lhet);
+        const int b = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
+        if (pb_unanimous_by_count(peek, nl, need, k, b)) { cb = pb_unanimous_result(lhet, k, b, rmsq); ++g_by_count; }
+        else cb = pb_call_unanimous(peek, 2 * nl, qval, tot4, rmsq, fk, beta, lhet);
+        memset(hist, 0, sizeof hist);
+    }
     else cb = pb_call_general(take, 2 * nl, qval, tot4, rmsq, fk, beta, lhet);
     for (int lw = 0; lw < 2 * nl; ++lw) if (hist[lw]) return ~0ULL;     // the histogram must come back cleared
     return cb;

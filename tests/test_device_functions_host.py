@@ -20,6 +20,7 @@ def hd():
     L = C.CDLL(str(so))
     L.hd_call_cell.restype = C.c_uint64
     L.hd_call_cell.argtypes = [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_uint16), C.c_int, C.c_int, C.c_int]
+    L.hd_by_count.restype = C.c_long
     L.hd_site_logic.argtypes = [C.POINTER(C.c_uint64)] + [C.c_int] * 7 + [C.POINTER(C.c_uint64)] * 2
     return L
 
@@ -80,3 +81,4 @@ def test_unanimous_shortcut_equals_oracle(hd):
         assert got == want, (i, k, b)
         n_unan += len(set(base.tolist())) == 1
     assert n_unan > 4000
+    assert hd.hd_by_count() > 2000          # the walk-free count test decided most of them
