@@ -206,97 +206,121 @@ __global__ void __launch_bounds__(256) k_need_table(const PbCounters *__restrict
     need[L * 256 + k] = L < nl ? pb_need_entry(L, nl, ctr->qval, k, fk, beta, lhet) : 0;
 }
 
+// Quality table of the encode pass: qtab[min(mapQ,63)][raw quality byte] = level(clamp(min(baseQ', mapQ),4,63)) << 2,
+// or PB_CODE_NONE when baseQ' < min_baseQ (baseQ' = Illumina-adjusted quality, popbam.cpp:268-283).
+__global__ void __launch_bounds__(256) k_qual_table(const PbCounters *__restrict__ ctr, int illumina, int min_baseQ,
+                                                    uint8_t *__restrict__ qtab /* [64][256] */) {
+    const int m = blockIdx.x, raw = threadIdx.x;
+    int bq = raw;
+    if (illumina) bq = bq > 31 ? bq - 31 : 0;
+    const int qq = max(4, min(63, min(bq, m)));
+    qtab[m * 256 + raw] = bq < min_baseQ ? (uint8_t)PB_CODE_NONE : (uint8_t)(ctr->qrank[qq] << 2);
+}
+
 // The base filter and code of call_base (popbam.cpp:268-284), once per base and OUTSIDE the
 // latency-bound pileup loop:
 //   code = level(clamp(min(baseQ', mapQ), 4, 63)) << 2 | nt4      or PB_CODE_NONE when the base is dropped
-// (baseQ' < min_baseQ, not A/C/G/T, or the read is dropped / below min_mapQ).  A flat streaming pass:
-// each thread owns 16 consecutive bytes of qual[] (one 16-byte load, one 8-byte load of seq4[], one
-// 16-byte store) and works on four bases at a time with byte-SIMD min / compare; the level and the
-// 2-base sequence byte go through small shared-memory tables.  The read owning a byte is found from
-// base[] (reads are laid out back to back in file order) starting from a proportional guess, which is
-// exact for equal-length reads.
+// (baseQ' < min_baseQ, not A/C/G/T, or the read is dropped / below min_mapQ).  A flat streaming pass
+// with persistent CTAs: the 16 KB quality table and a 256-entry sequence-byte table sit in shared
+// memory, each thread takes 64 consecutive bytes of qual[] per step (four 16-byte loads, 32 bytes of
+// seq4[], four 16-byte stores), i.e. two table lookups and an OR per base.  The read owning a byte is
+// found from base[] (reads are laid out back to back in file order) starting from a proportional
+// guess, which is exact for equal-length reads.
+#define PB_ENC_CHUNK 64
 __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
                                                 const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4,
-                                                const uint8_t *__restrict__ qual, int64_t n_bytes, int illumina, int min_baseQ,
-                                                int min_mapQ, const PbCounters *__restrict__ ctr, uint8_t *__restrict__ codes) {
-    __shared__ uint8_t lvl4_s[64];        // quality 0..63 -> level << 2
+                                                const uint8_t *__restrict__ qual, int64_t n_bytes, double reads_per_byte,
+                                                int min_mapQ, const uint8_t *__restrict__ qtab, uint8_t *__restrict__ codes) {
+    __shared__ __align__(16) uint8_t qtab_s[64 * 256];
     __shared__ uint16_t seq_s[256];       // packed sequence byte -> nt4 of its two bases (0xff: not A/C/G/T), first base low
-    if (threadIdx.x < 64) lvl4_s[threadIdx.x] = (uint8_t)(ctr->qrank[max(4, (int)threadIdx.x)] << 2);
+    for (int i = threadIdx.x; i < 64 * 256 / 16; i += 256)
+        reinterpret_cast<uint4 *>(qtab_s)[i] = __ldg(reinterpret_cast<const uint4 *>(qtab) + i);
     {
         const uint32_t hi = threadIdx.x >> 4, lo = threadIdx.x & 15;
         const uint32_t bh = (uint32_t)((PB_NT16_NT4_LUT >> (hi * 4)) & 0xf), bl = (uint32_t)((PB_NT16_NT4_LUT >> (lo * 4)) & 0xf);
         seq_s[threadIdx.x] = (uint16_t)((bh > 3 ? 0xffu : bh) | (bl > 3 ? 0xffu : bl) << 8);
     }
     __syncthreads();
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t o = (uint64_t)t << 4;
-    if ((int64_t)o >= n_bytes) return;
-    const int nb = (int)min((uint64_t)16, (uint64_t)n_bytes - o);
-    // owner of byte o: last r with base[r] <= o
-    int64_t lo = (int64_t)((double)o * ((double)n / (double)n_bytes));
-    if (lo >= n) lo = n - 1;
-    int64_t hi = lo + 1, step = 1;
-    while (lo > 0 && __ldg(base + lo) > o) { hi = lo; lo = max((int64_t)0, lo - step); step <<= 1; }
-    step = 1;
-    while (hi < n && __ldg(base + hi) <= o) { lo = hi; hi = min(n, hi + step); step <<= 1; }
-    while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (__ldg(base + mid) <= o) lo = mid; else hi = mid; }
-    int64_t r = lo;
-    uint64_t next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
-    auto read_mapq = [&](int64_t rr) -> int {       // -1: the pileup never looks at this read's codes
-        if (rkey[rr] == PB_KEY_DROP) return -1;
-        const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
-        return mq < min_mapQ ? -1 : mq;
-    };
-    int mapq = read_mapq(r);
-    uint32_t qw[4] = {0, 0, 0, 0}, sw[2] = {0, 0};
-    if (nb == 16) {
-        const uint4 v = __ldg(reinterpret_cast<const uint4 *>(qual + o));
-        const uint2 s2 = __ldg(reinterpret_cast<const uint2 *>(seq4 + (o >> 1)));
-        qw[0] = v.x; qw[1] = v.y; qw[2] = v.z; qw[3] = v.w; sw[0] = s2.x; sw[1] = s2.y;
-    } else {
-        for (int i = 0; i < nb; ++i) qw[i >> 2] |= (uint32_t)qual[o + i] << (8 * (i & 3));
-        for (int i = 0; i < (nb + 1) / 2; ++i) sw[i >> 2] |= (uint32_t)seq4[(o >> 1) + i] << (8 * (i & 3));
-    }
-    const uint32_t minq4 = (uint32_t)min(min_baseQ, 255) * 0x01010101u;
-    uint32_t out[4];
+    const int64_t n_chunks = (n_bytes + PB_ENC_CHUNK - 1) / PB_ENC_CHUNK;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_chunks; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = (uint64_t)t * PB_ENC_CHUNK;
+        const int nb = (int)min((uint64_t)PB_ENC_CHUNK, (uint64_t)n_bytes - o);
+        // owner of byte o: last r with base[r] <= o
+        int64_t lo = (int64_t)((double)o * reads_per_byte);
+        if (lo >= n) lo = n - 1;
+        int64_t hi = lo + 1, step = 1;
+        while (lo > 0 && __ldg(base + lo) > o) { hi = lo; lo = max((int64_t)0, lo - step); step <<= 1; }
+        step = 1;
+        while (hi < n && __ldg(base + hi) <= o) { lo = hi; hi = min(n, hi + step); step <<= 1; }
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (__ldg(base + mid) <= o) lo = mid; else hi = mid; }
+        int64_t r = lo;
+        uint64_t next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
+        const uint8_t *row = nullptr;                   // quality-table row of the current read; null: read not used
+        auto set_read = [&](int64_t rr) {
+            row = nullptr;
+            if (rkey[rr] == PB_KEY_DROP) return;
+            const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
+            if (mq >= min_mapQ) row = qtab_s + min(mq, 63) * 256;
+        };
+        set_read(r);
+        if (nb == PB_ENC_CHUNK) {
+            uint4 qv[4];
+            uint4 sv[2];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
-        uint32_t q4 = qw[g];
-        if (illumina) q4 = __vsubus4(q4, 0x1f1f1f1fu);                    // baseQ' = baseQ > 31 ? baseQ - 31 : 0
-        const uint32_t pass4 = min_baseQ > 255 ? 0u : __vcmpgeu4(q4, minq4);
-        // nt4 of the group's four bases: two sequence bytes through the table
-        const uint32_t sb = sw[g >> 1] >> (16 * (g & 1));
-        const uint32_t b44 = (uint32_t)seq_s[sb & 0xffu] | (uint32_t)seq_s[(sb >> 8) & 0xffu] << 16;
-        const uint64_t gbeg = o + 4 * g;
-        uint32_t code4;
-        if (gbeg + 4 <= next) {                                           // the whole group belongs to read r
-            if (mapq < 0) code4 = 0xffffffffu;
-            else {
-                const uint32_t m4 = __vminu4(__vminu4(q4, (uint32_t)min(mapq, 63) * 0x01010101u), 0x3f3f3f3fu);
-                const uint32_t l4 = (uint32_t)lvl4_s[m4 & 0xffu] | (uint32_t)lvl4_s[(m4 >> 8) & 0xffu] << 8 |
-                                    (uint32_t)lvl4_s[(m4 >> 16) & 0xffu] << 16 | (uint32_t)lvl4_s[m4 >> 24] << 24;
-                // invalid bases are 0xff in b44; failed qualities have pass4 == 0: both become PB_CODE_NONE (0xff)
-                code4 = (l4 | b44) | ~pass4 | __vcmpeq4(b44, 0xffffffffu);
+            for (int v = 0; v < 4; ++v) qv[v] = __ldg(reinterpret_cast<const uint4 *>(qual + o) + v);
+#pragma unroll
+            for (int v = 0; v < 2; ++v) sv[v] = __ldg(reinterpret_cast<const uint4 *>(seq4 + (o >> 1)) + v);
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                const uint32_t qw[4] = {qv[v].x, qv[v].y, qv[v].z, qv[v].w};
+                const uint32_t sw[2] = {v & 1 ? sv[v >> 1].z : sv[v >> 1].x, v & 1 ? sv[v >> 1].w : sv[v >> 1].y};
+                uint32_t out[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t q4 = qw[g];
+                    const uint32_t sb = sw[g >> 1] >> (16 * (g & 1));
+                    const uint32_t b44 = (uint32_t)seq_s[sb & 0xffu] | (uint32_t)seq_s[(sb >> 8) & 0xffu] << 16;
+                    const uint64_t gbeg = o + 16 * v + 4 * g;
+                    uint32_t code4;
+                    if (gbeg + 4 <= next) {                               // the whole group belongs to read r
+                        if (!row) code4 = 0xffffffffu;
+                        else {
+                            const uint32_t l4 = (uint32_t)row[q4 & 0xffu] | (uint32_t)row[(q4 >> 8) & 0xffu] << 8 |
+                                                (uint32_t)row[(q4 >> 16) & 0xffu] << 16 | (uint32_t)row[q4 >> 24] << 24;
+                            code4 = l4 | b44;                             // 0xff in either half stays 0xff: PB_CODE_NONE
+                            // a filtered quality (0xff) OR a valid base is still 0xff; an invalid base (0xff) likewise
+                        }
+                    } else {                                              // a read boundary inside the group: byte by byte
+                        code4 = 0;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            while (gbeg + i >= next) {
+                                ++r;
+                                next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
+                                set_read(r);
+                            }
+                            const uint32_t cq = row ? (uint32_t)row[(q4 >> (8 * i)) & 0xffu] : 0xffu;
+                            code4 |= (cq | ((b44 >> (8 * i)) & 0xffu)) << (8 * i);
+                        }
+                    }
+                    out[g] = code4;
+                }
+                reinterpret_cast<uint4 *>(codes + o)[v] = make_uint4(out[0], out[1], out[2], out[3]);
             }
-        } else {                                                          // a read boundary inside the group: byte by byte
-            code4 = 0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                while (gbeg + i >= next) {
+        } else {
+            for (int i = 0; i < nb; ++i) {                                // tail of the array
+                while (o + i >= next) {
                     ++r;
                     next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
-                    mapq = read_mapq(r);
+                    set_read(r);
                 }
-                const uint32_t bq = (q4 >> (8 * i)) & 0xffu, b4 = (b44 >> (8 * i)) & 0xffu;
-                const uint32_t qq = min(min(bq, (uint32_t)max(mapq, 0)), 63u);
-                const bool ok = mapq >= 0 && ((pass4 >> (8 * i)) & 1u) && b4 != 0xffu;
-                code4 |= (ok ? ((uint32_t)lvl4_s[qq] | b4) : (uint32_t)PB_CODE_NONE) << (8 * i);
+                const uint32_t sbyte = seq4[(o + i) >> 1];
+                const uint32_t b4 = (seq_s[sbyte] >> (8 * (int)((o + i) & 1))) & 0xffu;
+                const uint32_t cq = row ? (uint32_t)row[qual[o + i]] : 0xffu;
+                codes[o + i] = (uint8_t)(cq | b4);
             }
         }
-        out[g] = code4;
     }
-    if (nb == 16) *reinterpret_cast<uint4 *>(codes + o) = make_uint4(out[0], out[1], out[2], out[3]);
-    else for (int i = 0; i < nb; ++i) codes[o + i] = (uint8_t)(out[i >> 2] >> (8 * (i & 3)));
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -53,13 +53,16 @@ struct pb_ctx {
     int64_t n_reads = 0, n_cig = 0, n_bytes = 0;
     DevBuf d_pos, d_meta, d_cigstart, d_ncig, d_base, d_cigar, d_seq4, d_qual, d_tmp_cig, d_tmp_base;
     // derived
-    DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
+    DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
     DevBuf d_num_sites, d_segsites, d_seg_off, d_seg_pos, d_seg_idx, d_seg_type, d_seg_ref, d_seg_cb;
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wr, d_wall_u, d_stats;
     // pinned results
     HostBuf h_ctr, h_small, h_seg, h_span;
     PbCounters ctr_host;
+    bool need_valid = false;
+    int need_nl = 0;
+    unsigned char need_qval[64] = {0};
     int64_t s_total = 0;
     pb_region_result res;
     // bam_fetch_f shim staging (pb_push_record)
@@ -227,14 +230,15 @@ int run_pipeline(pb_ctx *c) {
     }
     k_level_table<<<1, 32, 0, st>>>(ctr);
     k_depth_decide<<<1, 1, 0, st>>>(P.max_depth, ctr);
-    PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
-    k_need_table<<<64, 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
-    c->launches += 2;
+    c->launches += 1;
     if (N > 0) {
-        k_encode<<<nblk((c->n_bytes + 15) / 16, 256), 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
-                                               dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ,
-                                               P.min_mapQ, ctr, dp<uint8_t>(c->d_codes));
-        c->launches += 1;
+        PB_TRY(dev_reserve(c, c->d_qtab, 64 * 256));
+        k_qual_table<<<64, 256, 0, st>>>(ctr, illumina, P.min_baseQ, dp<uint8_t>(c->d_qtab));
+        k_encode<<<c->n_sms * 8, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
+                                              dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes,
+                                              (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ, dp<uint8_t>(c->d_qtab),
+                                              dp<uint8_t>(c->d_codes));
+        c->launches += 2;
     }
     PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
     const unsigned part_blocks = nblk(n_chunks * 32, 128);
@@ -262,6 +266,14 @@ int run_pipeline(pb_ctx *c) {
     PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
     if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
     const int nl = c->ctr_host.n_levels;
+    // the walk-free shortcut table only depends on the level set: rebuild it when that changes
+    if (!c->need_valid || c->need_nl != nl || memcmp(c->need_qval, c->ctr_host.qval, 64) != 0) {
+        PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
+        k_need_table<<<std::max(nl, 1), 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
+        c->launches += 1;
+        PB_CUDA(c, cudaGetLastError());
+        c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, c->ctr_host.qval, 64);
+    }
     const size_t smem = pb_pile_smem(kTP, nl);
     if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d samples x %d quality levels exceeds %zu bytes", n, nl, c->smem_optin);
     const bool cap = c->ctr_host.nocap == 0;
@@ -488,7 +500,7 @@ void pb_destroy(pb_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
                       &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rnseg,
-                      &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_need, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
+                      &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_need, &c->d_qtab, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
                       &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
                       &c->d_seg_idx, &c->d_seg_type, &c->d_seg_ref, &c->d_seg_cb, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
                       &c->d_rsum, &c->d_wr, &c->d_wall_u, &c->d_stats};
