@@ -231,16 +231,23 @@ __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__res
                                                 const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4,
                                                 const uint8_t *__restrict__ qual, int64_t n_bytes, double reads_per_byte,
                                                 int min_mapQ, const uint8_t *__restrict__ qtab, uint8_t *__restrict__ codes) {
-    __shared__ __align__(16) uint8_t qtab_s[64 * 256];
+    __shared__ __align__(16) uint8_t qtab_s[65 * 256];   // row 64: all PB_CODE_NONE (reads the pileup never looks at)
     __shared__ uint16_t seq_s[256];       // packed sequence byte -> nt4 of its two bases (0xff: not A/C/G/T), first base low
     for (int i = threadIdx.x; i < 64 * 256 / 16; i += 256)
         reinterpret_cast<uint4 *>(qtab_s)[i] = __ldg(reinterpret_cast<const uint4 *>(qtab) + i);
+    qtab_s[64 * 256 + threadIdx.x] = (uint8_t)PB_CODE_NONE;
     {
         const uint32_t hi = threadIdx.x >> 4, lo = threadIdx.x & 15;
         const uint32_t bh = (uint32_t)((PB_NT16_NT4_LUT >> (hi * 4)) & 0xf), bl = (uint32_t)((PB_NT16_NT4_LUT >> (lo * 4)) & 0xf);
         seq_s[threadIdx.x] = (uint16_t)((bh > 3 ? 0xffu : bh) | (bl > 3 ? 0xffu : bl) << 8);
     }
     __syncthreads();
+    // quality-table row of a read: its mapQ row, or the all-NONE row when the read is dropped / below min_mapQ
+    auto row_of = [&](int64_t rr) -> uint32_t {
+        if (rr >= n || rkey[rr] == PB_KEY_DROP) return 64u * 256u;
+        const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
+        return mq >= min_mapQ ? (uint32_t)min(mq, 63) * 256u : 64u * 256u;
+    };
     const int64_t n_chunks = (n_bytes + PB_ENC_CHUNK - 1) / PB_ENC_CHUNK;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_chunks; t += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t o = (uint64_t)t * PB_ENC_CHUNK;
@@ -253,17 +260,14 @@ __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__res
         step = 1;
         while (hi < n && __ldg(base + hi) <= o) { lo = hi; hi = min(n, hi + step); step <<= 1; }
         while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if (__ldg(base + mid) <= o) lo = mid; else hi = mid; }
-        int64_t r = lo;
-        uint64_t next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
-        const uint8_t *row = nullptr;                   // quality-table row of the current read; null: read not used
-        auto set_read = [&](int64_t rr) {
-            row = nullptr;
-            if (rkey[rr] == PB_KEY_DROP) return;
-            const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
-            if (mq >= min_mapQ) row = qtab_s + min(mq, 63) * 256;
-        };
-        set_read(r);
-        if (nb == PB_ENC_CHUNK) {
+        const int64_t r = lo;
+        // at most one read boundary inside the chunk is handled without branches: bytes < cut use rowA, the rest rowB
+        const uint64_t next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
+        const uint64_t next2 = r + 2 < n ? __ldg(base + r + 2) : ~0ULL;
+        const uint32_t rowA = row_of(r);
+        const uint32_t cut = next - o < (uint64_t)PB_ENC_CHUNK ? (uint32_t)(next - o) : (uint32_t)PB_ENC_CHUNK;
+        const uint32_t rowB = cut < PB_ENC_CHUNK ? row_of(r + 1) : rowA;
+        if (nb == PB_ENC_CHUNK && next2 - o >= (uint64_t)PB_ENC_CHUNK) {
             uint4 qv[4];
             uint4 sv[2];
 #pragma unroll
@@ -280,44 +284,30 @@ __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__res
                     const uint32_t q4 = qw[g];
                     const uint32_t sb = sw[g >> 1] >> (16 * (g & 1));
                     const uint32_t b44 = (uint32_t)seq_s[sb & 0xffu] | (uint32_t)seq_s[(sb >> 8) & 0xffu] << 16;
-                    const uint64_t gbeg = o + 16 * v + 4 * g;
-                    uint32_t code4;
-                    if (gbeg + 4 <= next) {                               // the whole group belongs to read r
-                        if (!row) code4 = 0xffffffffu;
-                        else {
-                            const uint32_t l4 = (uint32_t)row[q4 & 0xffu] | (uint32_t)row[(q4 >> 8) & 0xffu] << 8 |
-                                                (uint32_t)row[(q4 >> 16) & 0xffu] << 16 | (uint32_t)row[q4 >> 24] << 24;
-                            code4 = l4 | b44;                             // 0xff in either half stays 0xff: PB_CODE_NONE
-                            // a filtered quality (0xff) OR a valid base is still 0xff; an invalid base (0xff) likewise
-                        }
-                    } else {                                              // a read boundary inside the group: byte by byte
-                        code4 = 0;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            while (gbeg + i >= next) {
-                                ++r;
-                                next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
-                                set_read(r);
-                            }
-                            const uint32_t cq = row ? (uint32_t)row[(q4 >> (8 * i)) & 0xffu] : 0xffu;
-                            code4 |= (cq | ((b44 >> (8 * i)) & 0xffu)) << (8 * i);
-                        }
-                    }
-                    out[g] = code4;
+                    const uint32_t i0 = 16 * v + 4 * g;
+                    // 0xff in either half stays 0xff after the OR: PB_CODE_NONE
+                    const uint32_t l4 = (uint32_t)qtab_s[(i0 + 0 < cut ? rowA : rowB) + (q4 & 0xffu)] |
+                                        (uint32_t)qtab_s[(i0 + 1 < cut ? rowA : rowB) + ((q4 >> 8) & 0xffu)] << 8 |
+                                        (uint32_t)qtab_s[(i0 + 2 < cut ? rowA : rowB) + ((q4 >> 16) & 0xffu)] << 16 |
+                                        (uint32_t)qtab_s[(i0 + 3 < cut ? rowA : rowB) + (q4 >> 24)] << 24;
+                    out[g] = l4 | b44;
                 }
                 reinterpret_cast<uint4 *>(codes + o)[v] = make_uint4(out[0], out[1], out[2], out[3]);
             }
         } else {
-            for (int i = 0; i < nb; ++i) {                                // tail of the array
-                while (o + i >= next) {
-                    ++r;
-                    next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
-                    set_read(r);
+            // tail of the array, or reads shorter than the chunk (several boundaries): byte by byte
+            int64_t rr = r;
+            uint64_t nx = next;
+            uint32_t row = rowA;
+            for (int i = 0; i < nb; ++i) {
+                while (o + i >= nx) {
+                    ++rr;
+                    nx = rr + 1 < n ? __ldg(base + rr + 1) : ~0ULL;
+                    row = row_of(rr);
                 }
                 const uint32_t sbyte = seq4[(o + i) >> 1];
                 const uint32_t b4 = (seq_s[sbyte] >> (8 * (int)((o + i) & 1))) & 0xffu;
-                const uint32_t cq = row ? (uint32_t)row[qual[o + i]] : 0xffu;
-                codes[o + i] = (uint8_t)(cq | b4);
+                codes[o + i] = (uint8_t)((uint32_t)qtab_s[row + qual[o + i]] | b4);
             }
         }
     }
