@@ -13,6 +13,7 @@
 #include "../../include/popbam_b200.h"
 #include "pb_kernels.cuh"
 #include "pb_stats.cuh"
+#include "pb_ld.cuh"
 
 namespace {
 
@@ -56,7 +57,7 @@ struct pb_ctx {
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
     DevBuf d_num_sites, d_segsites, d_seg_off, d_seg_pos, d_seg_idx, d_seg_type, d_seg_ref, d_seg_cb;
-    DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wr, d_wall_u, d_stats;
+    DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wall_u, d_stats, d_ld_kt, d_ld_km, d_ld_inv, d_ld_cnt;
     // pinned results
     HostBuf h_ctr, h_small, h_seg, h_span;
     PbCounters ctr_host;
@@ -313,9 +314,13 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaGetLastError());
     int64_t *h_total = reinterpret_cast<int64_t *>(c->h_ctr.p) + (sizeof(PbCounters) + 7) / 8;   // h_ctr has a page
     PB_CUDA(c, cudaMemcpyAsync(h_total, dl.seg_off + NW, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    const SmallLayout hl0 = small_layout(c->h_small.p, NW, P.n_pops, n);
+    PB_CUDA(c, cudaMemcpyAsync(hl0.segsites, dl.segsites, sizeof(int32_t) * (size_t)NW, cudaMemcpyDeviceToHost, st));
     PB_CUDA(c, cudaStreamSynchronize(st));
     const int64_t S = *h_total;
     c->s_total = S;
+    int s_max = 0;
+    for (int w = 0; w < NW; ++w) s_max = std::max(s_max, hl0.segsites[w]);
 
     // ---- segregating-site lists
     const bool with_cb = (c->analyses & PB_AN_SNP) != 0;
@@ -331,7 +336,7 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaEventRecord(c->ev[4], st));
 
     // ---- window statistics
-    const uint32_t stat_bits = PB_AN_NUCDIV | PB_AN_SFS | PB_AN_LD_ZNS | PB_AN_LD_OMEGA | PB_AN_LD_WALL | PB_AN_DIVERGE_IND |
+    const uint32_t stat_bits = PB_AN_NUCDIV | PB_AN_SFS | PB_AN_LD_WALL | PB_AN_DIVERGE_IND |
                                PB_AN_DIVERGE_POP | PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS | PB_AN_HAPLO_DXY;
     if (c->analyses & stat_bits) {
         PbStatArgs sa;
@@ -345,17 +350,10 @@ int run_pipeline(pb_ctx *c) {
             PB_TRY(dev_reserve(c, c->d_hap, sizeof(uint64_t) * (size_t)n * (size_t)(S / 64 + NW + 1)));
             sa.hap = dp<uint64_t>(c->d_hap);
         }
-        if (c->analyses & (PB_AN_LD_ZNS | PB_AN_LD_OMEGA | PB_AN_HAPLO_EHHS)) {
+        if (c->analyses & PB_AN_HAPLO_EHHS) {
             PB_TRY(dev_reserve(c, c->d_kt, sizeof(uint64_t) * (size_t)(S + NW + 1)));
             PB_TRY(dev_reserve(c, c->d_km, (size_t)(S + NW + 1)));
             sa.kt = dp<uint64_t>(c->d_kt); sa.km = dp<uint8_t>(c->d_km);
-        }
-        if (c->analyses & PB_AN_LD_OMEGA) {
-            const size_t cnt = (size_t)(S + 2 * (int64_t)NW + 2);
-            PB_TRY(dev_reserve(c, c->d_lsum, sizeof(double) * cnt));
-            PB_TRY(dev_reserve(c, c->d_rsum, sizeof(double) * cnt));
-            PB_TRY(dev_reserve(c, c->d_wr, sizeof(double) * cnt));
-            sa.lsum = dp<double>(c->d_lsum); sa.rsum = dp<double>(c->d_rsum); sa.wr = dp<double>(c->d_wr);
         }
         if (c->analyses & PB_AN_LD_WALL) {
             PB_TRY(dev_reserve(c, c->d_wall_u, sizeof(uint64_t) * (size_t)P.n_pops * (size_t)std::max<int64_t>(S, 1)));
@@ -363,12 +361,39 @@ int run_pipeline(pb_ctx *c) {
         }
         sa.piw = dl.piw; sa.pib = dl.pib; sa.min_dxy = dl.min_dxy;
         sa.sfs_num_snps = dl.sfs_num_snps; sa.td = dl.td; sa.fwh = dl.fwh;
-        sa.ld_num_snps = dl.ld_num_snps; sa.zns = dl.zns; sa.omegamax = dl.omegamax;
         sa.wall_num_snps = dl.wall_num_snps; sa.wallb = dl.wallb; sa.wallq = dl.wallq;
         sa.ind_div = dl.ind_div; sa.pop_div = dl.pop_div; sa.div_num_snps = dl.div_num_snps;
         sa.nhaps = dl.nhaps; sa.hdiv = dl.hdiv; sa.ehhs = dl.ehhs;
         k_window_stats<<<NW, PB_ST_THREADS, (size_t)n * n * sizeof(uint16_t), st>>>(sa);
         c->launches += 1;
+        PB_CUDA(c, cudaGetLastError());
+    }
+    // ---- pairwise LD (ld -o 0 / -o 1): keep list, tiled pair kernel, finish
+    if (c->analyses & (PB_AN_LD_ZNS | PB_AN_LD_OMEGA)) {
+        PbLdArgs la;
+        memset(&la, 0, sizeof la);
+        la.P = P.n_pops;
+        for (int i = 0; i < PB_MAX_SAMPLES; ++i) { la.pop_mask[i] = P.pop_mask[i]; la.pop_nsmpl[i] = P.pop_nsmpl[i]; }
+        la.min_freq = P.min_freq; la.analyses = c->analyses;
+        la.segsites = dl.segsites; la.seg_off = dl.seg_off; la.seg_type = sl.seg_type;
+        la.stride = S + 2 * (int64_t)NW + 2;
+        const size_t cnt = (size_t)P.n_pops * (size_t)la.stride;
+        PB_TRY(dev_reserve(c, c->d_ld_kt, sizeof(uint64_t) * cnt));
+        PB_TRY(dev_reserve(c, c->d_ld_km, sizeof(int32_t) * cnt));
+        PB_TRY(dev_reserve(c, c->d_ld_inv, sizeof(double) * cnt));
+        PB_TRY(dev_reserve(c, c->d_lsum, sizeof(double) * cnt));
+        PB_TRY(dev_reserve(c, c->d_rsum, sizeof(double) * cnt));
+        PB_TRY(dev_reserve(c, c->d_ld_cnt, sizeof(int32_t) * 2 * (size_t)NW * P.n_pops));
+        la.kt = dp<uint64_t>(c->d_ld_kt); la.km = dp<int32_t>(c->d_ld_km); la.kinv = dp<double>(c->d_ld_inv);
+        la.lsum = dp<double>(c->d_lsum); la.rsum = dp<double>(c->d_rsum);
+        la.kcount = dp<int32_t>(c->d_ld_cnt); la.nsnps = la.kcount + (size_t)NW * P.n_pops;
+        la.ld_num_snps = dl.ld_num_snps; la.zns = dl.zns; la.omegamax = dl.omegamax;
+        const unsigned pw = (unsigned)NW * (unsigned)P.n_pops;
+        const int nrb = std::max(1, (s_max + PB_LD_THREADS - 1) / PB_LD_THREADS);
+        k_ld_keep<<<pw, PB_LD_THREADS, 0, st>>>(la);
+        k_ld_rows<<<pw * (unsigned)nrb, PB_LD_THREADS, 0, st>>>(la, (c->analyses & PB_AN_LD_OMEGA) ? 1 : 0, nrb);
+        k_ld_finish<<<pw, PB_LD_THREADS, 0, st>>>(la);
+        c->launches += 3;
         PB_CUDA(c, cudaGetLastError());
     }
     PB_CUDA(c, cudaEventRecord(c->ev[5], st));
@@ -503,7 +528,7 @@ void pb_destroy(pb_ctx *c) {
                       &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_need, &c->d_qtab, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
                       &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
                       &c->d_seg_idx, &c->d_seg_type, &c->d_seg_ref, &c->d_seg_cb, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
-                      &c->d_rsum, &c->d_wr, &c->d_wall_u, &c->d_stats};
+                      &c->d_rsum, &c->d_wall_u, &c->d_stats, &c->d_ld_kt, &c->d_ld_km, &c->d_ld_inv, &c->d_ld_cnt};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     HostBuf *hb[] = {&c->h_ctr, &c->h_small, &c->h_seg, &c->h_span};
     for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);

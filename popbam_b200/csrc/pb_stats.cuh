@@ -4,7 +4,7 @@
 //   calc_diff_matrix               pop_nucdiv.cpp:242-256, hamming_distance pop_utils.cpp:51-64
 //   calc_nucdiv / calc_minDxy      pop_nucdiv.cpp:206-239, pop_haplo.cpp:325-363
 //   calc_sfs                       pop_sfs.cpp:227-291 (+ calc_a1/a2/e1/e2, :511-571)
-//   calc_zns / calc_omegamax       pop_ld.cpp:201-252, :254-373
+//   (calc_zns / calc_omegamax: pb_ld.cuh)
 //   calc_wall                      pop_ld.cpp:375-458
 //   calc_diverge                   pop_diverge.cpp:220-257
 //   calc_nhaps / calc_ehhs         pop_haplo.cpp:208-254, :256-323
@@ -33,13 +33,11 @@ struct PbStatArgs {
     uint64_t *hap;        // n * (S_total/64 + NW + 1) words
     uint64_t *kt;         // [S_total + NW] kept / list entries of the current population
     uint8_t *km;          // [S_total + NW] marginal counts
-    double *lsum, *rsum, *wr;   // [S_total + 2*NW]
     uint64_t *wall_u;     // [P * S_total] unique partitions (ld -o 2) or null
     int64_t s_total;
     // outputs (see pb_region_result)
     double *piw, *pib; uint16_t *min_dxy;
     int32_t *sfs_num_snps; double *td, *fwh;
-    int32_t *ld_num_snps; double *zns, *omegamax;
     int32_t *wall_num_snps; double *wallb, *wallq;
     uint16_t *ind_div, *pop_div; int32_t *div_num_snps;
     int32_t *nhaps; double *hdiv, *ehhs;
@@ -270,61 +268,6 @@ __global__ void __launch_bounds__(PB_ST_THREADS) k_window_stats(const PbStatArgs
                                      (9.0 * m * ((m - 1) * (m - 1)))));
                     } else { td = nan(""); fwh = nan(""); }
                     a.td[oi] = td; a.fwh[oi] = fwh;
-                }
-            }
-        }
-
-        if (an & (PBA_LD_ZNS | PBA_LD_OMEGA)) {
-            uint64_t *kt = a.kt + so + w;
-            uint8_t *km = a.km + so + w;
-            const int mf = a.min_freq;
-            int before = 0;
-            __syncthreads();
-            const int K = pb_compact_sites(T, S, mask, [=](uint64_t, int m) { return m >= mf && m <= np - mf; }, kt, km, S - 1,
-                                           &before, shu);
-            const int ns = S < 1 ? 0 : before + 1;
-            for (int i = tid; i < 65; i += PB_ST_THREADS) xtab[i] = (double)i / np;
-            __syncthreads();
-            const bool need_left = (an & PBA_LD_OMEGA) != 0;
-            double *lsum = a.lsum + so + 2 * (size_t)w, *rsum = a.rsum + so + 2 * (size_t)w, *wr = a.wr + so + 2 * (size_t)w;
-            double part = 0.0;
-            for (int i = tid; i < K; i += PB_ST_THREADS) {
-                const uint64_t ti = kt[i];
-                const double xi = xtab[km[i]];
-                double l = 0.0, r = 0.0;
-                if (need_left) for (int k = 0; k < i; ++k) l += pb_r2(kt[k], ti, xtab[km[k]], xi, xtab);
-                for (int k = i + 1; k < K; ++k) r += pb_r2(ti, kt[k], xi, xtab[km[k]], xtab);
-                if (need_left) { lsum[i] = l; rsum[i] = r; }
-                part += r;
-            }
-            const double total = pb_block_sum(part, shd);
-            if (tid == 0) {
-                a.ld_num_snps[oi] = ns;
-                if (an & PBA_LD_ZNS) a.zns[oi] = S < 1 ? 0.0 : total * (2.0 / (double)(ns * (ns - 1)));
-            }
-            if (need_left) {
-                __syncthreads();
-                if (tid == 0) {
-                    double om = 0.0;
-                    if (S >= 1) {
-                        // phantom index (last site not kept): empty row
-                        for (int i = K; i < ns; ++i) { lsum[i] = 0.0; rsum[i] = 0.0; }
-                        // wr[i] = sum of r2 over pairs inside the right block [i+1, ns)
-                        double acc = 0.0;
-                        for (int i = ns - 1; i >= 0; --i) { wr[i] = acc; acc += rsum[i]; }
-                        double sl = 0.0, sb = 0.0, sr = 0.0, wl = 0.0, x = 0.0;
-                        for (int i = 0; i < ns - 1; ++i) {
-                            wl += lsum[i];                 // pairs inside [0, i]
-                            x += rsum[i] - lsum[i];        // pairs across the split after i
-                            if (i == 0) continue;
-                            sl += wl; sb += x; sr += wr[i];   // never reset across split points
-                            const int left = i + 1, right = ns - left;
-                            double omega = (sl + sr) / (((left * (left - 1)) / 2.0) + ((right * (right - 1)) / 2.0));
-                            omega *= left * right / sb;
-                            om = omega > om ? omega : om;
-                        }
-                    }
-                    a.omegamax[oi] = om;
                 }
             }
         }
