@@ -20,9 +20,7 @@
 #include "pb_walk.cuh"
 
 #define PB_REC_DEAD (1u << 25)    // read fails min_mapQ: it only counts towards the raw-depth cap
-#define PB_REC_CAP 320            // segment records staged per round in the hot kernel
 #define PB_BIN_SHIFT 7            // read-start bins of the depth bound (128 bp)
-#define PB_QCAP 64                // deferred (non-unanimous) cells per round
 #define PB_PART_CHUNK 2048        // reads per warp in the sample partition
 #define PB_KEY_DROP 0xffu
 #define PB_CODE_NONE 0xffu        // base filtered out (quality, N)
@@ -494,23 +492,28 @@ struct PbPileArgs {
     uint64_t *cb_out;               // [span * n_samples] or null
 };
 
+#define PB_WCAP 64                // segment records staged per warp and chunk
+#define PB_WQ 32                  // deferred (non-unanimous) cells per warp
+
 // Dynamic shared memory of k_pileup_call<TP> for nl quality levels (independent of the sample count).
 static inline size_t pb_pile_smem(int tp, int nl) {
-    return (size_t)PB_REC_CAP * 32 + (size_t)2 * nl * tp * 4 + (size_t)PB_QCAP * (3 + 2 * nl) * 4 + (size_t)tp * 20 + 256 * 8 +
-           128 * 4 + 64 + 64 * 16 + 64 + (size_t)nl * 256;
+    const size_t per_warp = (size_t)PB_WCAP * 32 + (size_t)2 * nl * 32 * 4 + (size_t)PB_WQ * (3 + 2 * nl) * 4 + 32 * 20;
+    return (size_t)(tp / 32) * ((per_warp + 15) & ~(size_t)15) + 256 * 8 + 128 * 4 + 64 + (size_t)nl * 256 + 64;
 }
 
-// One CTA = TP consecutive reference positions x all samples; one thread = one position.
+// One CTA = TP consecutive reference positions x all samples; one WARP = 32 positions, one thread = one
+// position.  After a common prologue (tables, the CTA's candidate range per sample) the warps never
+// synchronise with each other: every warp owns a slice of shared memory (staged records, one
+// histogram column per lane, a queue of deferred cells, the site state of its 32 positions).
 //
-// Rounds.  The CTA stages, for as many consecutive samples as fit, the candidate segment records
-// (reads starting in (p0 - max_span, p0 + TP)) in shared memory, unpacked into two 16-byte halves so
-// the inner loop needs no field extraction.  For each staged sample a WARP walks the records that can
-// cover any of its 32 positions, all lanes in lock step over the same record (file order), two records
-// per iteration so two code loads are in flight: coverage of a lane's position is one unsigned compare
-// (p - seg_start < seg_len), and the base's pre-digested code (k_encode) is one byte load whose address
-// is consecutive across the lanes.  The body is predicated, so the warp never splits.  Passing bases
-// are counted in the thread's private (level, strand) x base histogram in shared memory (plain
-// read-modify-write, no atomics) and in a packed per-base total.
+// Per sample a warp finds, with two ballots over the sorted read starts, the segment records whose
+// read starts in (first position - max_span, last position], stages them unpacked into two 16-byte
+// halves, and walks them in lock step -- every lane looks at the same record (a broadcast
+// shared-memory load), two records per iteration so two code loads are in flight.  Coverage of a
+// lane's position is one unsigned compare (p - seg_start < seg_len); the base's pre-digested code
+// (k_encode) is one byte load whose address is consecutive across the lanes.  The body is predicated,
+// so the warp never splits.  Passing bases are counted in the lane's private (level, strand) x base
+// histogram in shared memory (plain read-modify-write, no atomics) and in a packed per-base total.
 //
 // CAP = true keeps call_base's raw-depth cap ("the first max_depth non-deleted reads in file order,
 // before the base filters", popbam.cpp:242-248).  When k_depth_bound proves that no cell can reach
@@ -518,10 +521,10 @@ static inline size_t pb_pile_smem(int tp, int nl) {
 // no depth bookkeeping.
 //
 // Calls.  After the last record of a sample, cells whose bases all agree (the overwhelming majority)
-// are called on the spot with the exact early-exit walk (pb_call_unanimous).  The others are deferred:
-// the thread moves its histogram into a shared-memory queue, and at the end of the round the queue is
-// drained with one cell per thread, so the long general walk (pb_call_general) runs on full warps
-// instead of on the one or two lanes of a warp that need it.
+// are called on the spot: a count test against the need table, else the exact early-exit walk.  The
+// others are deferred: the lane moves its histogram into the warp's queue, and the queue is drained
+// with one cell per lane when it fills up and after the last sample, so the long general walk
+// (pb_call_general) runs on many lanes instead of on the one or two that need it.
 //
 // Per-site logic (make_X, pop_nucdiv.cpp:148-197) is folded in sample by sample (pb_site_sample): a
 // position only keeps its coverage mask, derived-allele mask and derived-base counts (20 bytes of
@@ -533,21 +536,22 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
     const int nl = a.ctr->n_levels;
     const int n_lw = 2 * nl;
     const int qstride = 3 + n_lw;
-    int4 *recA = reinterpret_cast<int4 *>(smem_raw);                        // [PB_REC_CAP] {read start, seg start, seg len, offset lo}
-    int4 *recB = recA + PB_REC_CAP;                                         // [PB_REC_CAP] {offset hi, strand*TP*4, mapq^2, dead}
-    uint32_t *hist = reinterpret_cast<uint32_t *>(recB + PB_REC_CAP);       // [n_lw][TP]
-    uint32_t *queue = hist + (size_t)n_lw * TP;                             // [PB_QCAP][3 + n_lw]
-    uint64_t *s_cov = reinterpret_cast<uint64_t *>(queue + (size_t)PB_QCAP * qstride);   // [TP]
-    uint64_t *s_type = s_cov + TP;                                          // [TP]
-    uint32_t *s_cnt4 = reinterpret_cast<uint32_t *>(s_type + TP);           // [TP]
-    double *fk_s = reinterpret_cast<double *>(s_cnt4 + TP);                 // [256]
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const size_t per_warp = (((size_t)PB_WCAP * 32 + (size_t)n_lw * 32 * 4 + (size_t)PB_WQ * qstride * 4 + 32 * 20) + 15) & ~(size_t)15;
+    unsigned char *wbase = smem_raw + (size_t)wid * per_warp;
+    int4 *recA = reinterpret_cast<int4 *>(wbase);                           // [PB_WCAP] {read start, seg start, seg len, offset lo}
+    int4 *recB = recA + PB_WCAP;                                            // [PB_WCAP] {offset hi, strand*32*4, mapq^2, dead}
+    uint64_t *s_cov = reinterpret_cast<uint64_t *>(recB + PB_WCAP);         // [32]
+    uint64_t *s_type = s_cov + 32;                                          // [32]
+    uint32_t *s_cnt4 = reinterpret_cast<uint32_t *>(s_type + 32);           // [32]
+    uint32_t *hist = s_cnt4 + 32;                                           // [n_lw][32]
+    uint32_t *queue = hist + (size_t)n_lw * 32;                             // [PB_WQ][3 + n_lw]
+    unsigned char *cbase = smem_raw + (size_t)(TP / 32) * per_warp;         // CTA-wide tables
+    double *fk_s = reinterpret_cast<double *>(cbase);                       // [256]
     uint32_t *rng = reinterpret_cast<uint32_t *>(fk_s + 256);               // lo[64], hi[64]
     uint8_t *qval_s = reinterpret_cast<uint8_t *>(rng + 128);               // [64]
-    int4 *plan = reinterpret_cast<int4 *>(qval_s + 64);                     // [64] {sample, src, count | last<<31, dst}
-    uint32_t *plan_n = reinterpret_cast<uint32_t *>(plan + 64);             // [0] entries, [1] next sample, [2] next src, [3] queue fill
-    uint8_t *need_s = reinterpret_cast<uint8_t *>(plan_n + 16);             // [nl][256]
+    uint8_t *need_s = qval_s + 64;                                          // [nl][256]
 
-    const int tid = threadIdx.x;
     const int p0 = a.span_beg + (int)blockIdx.x * TP;
     const int p = p0 + tid;
     const int p_end = min(p0 + TP, a.span_end);
@@ -562,10 +566,10 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
 
     for (int i = tid; i < 256; i += TP) fk_s[i] = a.fk[i];
     if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
-    for (int lw = 0; lw < n_lw; ++lw) hist[lw * TP + tid] = 0;
-    s_cov[tid] = 0; s_type[tid] = 0; s_cnt4[tid] = 0;
+    for (int lw = 0; lw < n_lw; ++lw) hist[lw * 32 + lane] = 0;
+    s_cov[lane] = 0; s_type[lane] = 0; s_cnt4[lane] = 0;
     if (tid < n) {
-        // candidate records of sample tid: read start in (p0 - max_span, p_end)
+        // candidate records of sample tid for the whole CTA: read start in (p0 - max_span, p_end)
         const uint32_t s0 = a.sstart[tid], s1 = a.sstart[tid + 1];
         uint32_t lo = s0, hi = s1;
         const int t_lo = p0 - max_span;       // first with start > t_lo
@@ -576,15 +580,15 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
         while (l2 < hi) { const uint32_t mid = (l2 + hi) >> 1; if (a.srec[mid].x >= p_end) hi = mid; else l2 = mid + 1; }
         rng[64 + tid] = l2;
     }
-    __syncthreads();
-    if (tid == 0) { plan_n[1] = 0; plan_n[2] = rng[0]; plan_n[3] = 0; }
+    __syncthreads();                          // the only CTA-wide barrier
+    if (pw0 >= p_end) return;                 // warp entirely past the end of the span
 
     const int ref_c = (valid && p >= 0 && p < a.ref_len) ? (int)(unsigned char)a.ref[p] : 'N';
     const int ref_r = pb_iupac_rev(ref_c);
 
-    // fold one called cell into its position's site state.  During a round only the owner thread touches a
-    // slot; in the drain several threads may hold cells of the same position (different samples), hence
-    // the atomic variant.
+    // fold one called cell into its position's site state.  During the record walk only the owner lane
+    // touches a slot; in a drain several lanes may hold cells of the same position (different samples),
+    // hence the atomic variant.
     auto fold = [&](int slot, int pos, int refc, int refr, int smp, uint64_t cb, bool atomic) {
         uint32_t d4 = 0;
         bool cov, der;
@@ -600,139 +604,124 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
         }
         if (a.cb_out) a.cb_out[((int64_t)pos - a.span_beg) * n + smp] = cb;
     };
+    int qn = 0;                  // cells in the warp's queue (warp-uniform)
+    auto drain = [&]() {
+        __syncwarp();
+        if (lane < qn) {
+            const uint32_t *q = queue + (size_t)lane * qstride;
+            const int slot = (int)(q[0] & 0xffffu), smp = (int)(q[0] >> 16);
+            const int pos = pw0 + slot;
+            const int rc = (pos >= 0 && pos < a.ref_len) ? (int)(unsigned char)a.ref[pos] : 'N';
+            auto take = [&](int lw) -> uint32_t { return q[3 + lw]; };
+            fold(slot, pos, rc, pb_iupac_rev(rc), smp, pb_call_general(take, n_lw, qval_s, q[2], (int)q[1], fk_s, a.beta, a.lhet), true);
+        }
+        __syncwarp();
+        qn = 0;
+    };
 
-    uint32_t *const my_hist = hist + tid;
+    uint32_t *const my_hist = hist + lane;
+    // one base of this lane's position; `code` was loaded by the caller (PB_CODE_NONE when not taken)
     int depth = 0, rmsq = 0;
     uint32_t tot4 = 0;           // per-base counts of the cell, one byte each
-    // one record against this lane's position; `code` was loaded by the caller (PB_CODE_NONE when not taken)
     auto count_base = [&](uint32_t code, const int4 &rb) {
         if (code != PB_CODE_NONE) {
             const uint32_t inc = 1u << ((code & 3u) << 3);
-            // word index (level*2 + strand) * TP  ==  byte offset (code & 0xfc) * (TP*2) + strand*TP*4
-            uint32_t *h = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(my_hist) + (code & 0xfcu) * (TP * 2) + rb.y);
+            // word index (level*2 + strand) * 32  ==  byte offset (code & 0xfc) * 64 + strand*128
+            uint32_t *h = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(my_hist) + (code & 0xfcu) * 64 + rb.y);
             *h += inc;
             tot4 += inc;
             rmsq += rb.z;
         }
     };
-    for (;;) {
-        __syncthreads();         // everybody is done with the previous round's plan, records and queue
-        // ---- plan one round: consecutive samples (or a piece of one) whose records fit the staging area
-        if (tid == 0) {
-            int s = (int)plan_n[1], ne = 0, fill = 0;
-            uint32_t src = plan_n[2];
-            while (s < n && ne < 64) {
-                const uint32_t hi = rng[64 + s];
-                const int want = (int)(hi - src), room = PB_REC_CAP - fill;
-                if (want > room && fill > 0) break;                 // start the big one in a fresh round
-                const int take = min(want, room);
-                const bool last = take == want;
-                plan[ne++] = make_int4(s, (int)src, take | (last ? (int)0x80000000u : 0), fill);
-                fill += take;
-                if (last) { ++s; src = s < n ? rng[s] : 0; } else { src += take; break; }
-            }
-            plan_n[0] = (uint32_t)ne; plan_n[1] = (uint32_t)s; plan_n[2] = src; plan_n[3] = 0;
+
+    for (int s = 0; s < n; ++s) {
+        // ---- the warp's records of this sample: read start in (pw0 - max_span, pw1], found by ballots over the sorted starts
+        const uint32_t lo = rng[s], hi = rng[64 + s];
+        uint32_t wlo = lo, whi = lo;
+        const int thr = pw0 - max_span;
+        for (uint32_t c0 = lo; c0 < hi; c0 += 32) {
+            const uint32_t idx = c0 + lane;
+            const int x = idx < hi ? a.srec[idx].x : 0x7fffffff;
+            wlo += __popc(__ballot_sync(0xffffffffu, x <= thr));
+            const uint32_t in = __popc(__ballot_sync(0xffffffffu, x <= pw1));
+            whi += in;
+            if (in < 32) break;              // sorted: nothing further can start at or before pw1
         }
-        __syncthreads();
-        const int ne = (int)plan_n[0];
-        if (ne == 0) break;
-        for (int e = 0; e < ne; ++e) {
-            const int4 pl = plan[e];
-            const int cnt = pl.z & 0x7fffffff;
-            for (int i = tid; i < cnt; i += TP) {
-                const int4 r = a.srec[(uint32_t)pl.y + i];
+        for (uint32_t c0 = wlo; c0 < whi; c0 += PB_WCAP) {
+            const int cnt = (int)min((uint32_t)PB_WCAP, whi - c0);
+            __syncwarp();
+            for (int i = lane; i < cnt; i += 32) {
+                const int4 r = a.srec[c0 + i];
                 const uint32_t z = (uint32_t)r.z, mq = (z >> 16) & 0xffu;
-                recA[pl.w + i] = make_int4(r.x, r.y, (int)(z & 0xffffu), r.w);
-                recB[pl.w + i] = make_int4((int)(z >> 26), (int)(((z >> 24) & 1u) * (TP * 4)), (int)(mq * mq), (int)((z >> 25) & 1u));
+                recA[i] = make_int4(r.x, r.y, (int)(z & 0xffffu), r.w);
+                recB[i] = make_int4((int)(z >> 26), (int)(((z >> 24) & 1u) * 128u), (int)(mq * mq), (int)((z >> 25) & 1u));
+            }
+            __syncwarp();
+            int j = 0;
+            for (; j + 1 < cnt; j += 2) {
+                const int4 a0 = recA[j], b0 = recB[j], a1 = recA[j + 1], b1 = recB[j + 1];   // same records for every lane: broadcast
+                const uint32_t u0 = (uint32_t)(pq - a0.y), u1 = (uint32_t)(pq - a1.y);
+                bool t0 = u0 < (uint32_t)a0.z, t1 = u1 < (uint32_t)a1.z;
+                if (CAP) {                                         // the cap precedes the filters; dead reads count
+                    t0 = t0 && depth < a.max_depth; depth += t0;
+                    t1 = t1 && depth < a.max_depth; depth += t1;
+                    t0 = t0 && !b0.w; t1 = t1 && !b1.w;
+                }
+                uint32_t c0v = PB_CODE_NONE, c1v = PB_CODE_NONE;
+                if (t0) c0v = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
+                if (t1) c1v = __ldg(a.codes + (((uint64_t)(uint32_t)b1.x << 32) | (uint32_t)a1.w) + u1);
+                count_base(c0v, b0);
+                count_base(c1v, b1);
+            }
+            if (j < cnt) {
+                const int4 a0 = recA[j], b0 = recB[j];
+                const uint32_t u0 = (uint32_t)(pq - a0.y);
+                bool t0 = u0 < (uint32_t)a0.z;
+                if (CAP) { t0 = t0 && depth < a.max_depth; depth += t0; t0 = t0 && !b0.w; }
+                uint32_t c0v = PB_CODE_NONE;
+                if (t0) c0v = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
+                count_base(c0v, b0);
             }
         }
-        __syncthreads();
-        for (int e = 0; e < ne; ++e) {
-            const int4 pl = plan[e];
-            const int cnt = pl.z & 0x7fffffff;
-            const int4 *ra = recA + pl.w, *rb = recB + pl.w;
-            if (pw0 < p_end) {                                         // warp-uniform
-                // records whose read starts in (pw0 - max_span, pw1]: [j, jend)
-                int j = 0, jh = cnt;
-                const int thr = pw0 - max_span;
-                while (j < jh) { const int mid = (j + jh) >> 1; if (ra[mid].x > thr) jh = mid; else j = mid + 1; }
-                int jend = j; jh = cnt;
-                while (jend < jh) { const int mid = (jend + jh) >> 1; if (ra[mid].x > pw1) jh = mid; else jend = mid + 1; }
-                for (; j + 1 < jend; j += 2) {
-                    const int4 a0 = ra[j], b0 = rb[j], a1 = ra[j + 1], b1 = rb[j + 1];   // same records for every lane: broadcast
-                    const uint32_t u0 = (uint32_t)(pq - a0.y), u1 = (uint32_t)(pq - a1.y);
-                    bool t0 = u0 < (uint32_t)a0.z, t1 = u1 < (uint32_t)a1.z;
-                    if (CAP) {                                         // the cap precedes the filters; dead reads count
-                        t0 = t0 && depth < a.max_depth; depth += t0;
-                        t1 = t1 && depth < a.max_depth; depth += t1;
-                        t0 = t0 && !b0.w; t1 = t1 && !b1.w;
-                    }
-                    uint32_t c0 = PB_CODE_NONE, c1 = PB_CODE_NONE;
-                    if (t0) c0 = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
-                    if (t1) c1 = __ldg(a.codes + (((uint64_t)(uint32_t)b1.x << 32) | (uint32_t)a1.w) + u1);
-                    count_base(c0, b0);
-                    count_base(c1, b1);
-                }
-                if (j < jend) {
-                    const int4 a0 = ra[j], b0 = rb[j];
-                    const uint32_t u0 = (uint32_t)(pq - a0.y);
-                    bool t0 = u0 < (uint32_t)a0.z;
-                    if (CAP) { t0 = t0 && depth < a.max_depth; depth += t0; t0 = t0 && !b0.w; }
-                    uint32_t c0 = PB_CODE_NONE;
-                    if (t0) c0 = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
-                    count_base(c0, b0);
-                }
-            }
-            if (pl.z < 0) {      // last piece of this sample: call the cell
-                if (valid) {
-                    // raw depth 0, or depth > 0 with every base filtered: errmod_cal(n = 0) + gl2cns give cb = 0 either way
-                    if (tot4 == 0) fold(tid, p, ref_c, ref_r, pl.x, 0, false);
-                    else if (pb_tot4_unanimous(tot4)) {
-                        auto peek = [&](int lw) -> uint32_t { return my_hist[lw * TP]; };
-                        const int kk = pb_tot4_k(tot4);
-                        const int bb = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
-                        // count test against the need table (no error-model arithmetic); exact early-exit walk otherwise
-                        const uint64_t cbw = pb_unanimous_by_count(peek, nl, need_s, kk, bb)
-                                                 ? pb_unanimous_result(a.lhet, kk, bb, rmsq)
-                                                 : pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet);
-                        fold(tid, p, ref_c, ref_r, pl.x, cbw, false);
-                        for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * TP] = 0;
-                    } else {
-                        const uint32_t slot = atomicAdd(&plan_n[3], 1u);
-                        if (slot < PB_QCAP) {          // defer: move the histogram into the queue
-                            uint32_t *q = queue + (size_t)slot * qstride;
-                            q[0] = (uint32_t)tid | ((uint32_t)pl.x << 16); q[1] = (uint32_t)rmsq; q[2] = tot4;
-                            for (int lw = 0; lw < n_lw; ++lw) { q[3 + lw] = my_hist[lw * TP]; my_hist[lw * TP] = 0; }
-                        } else {                       // queue full: call it here
-                            auto take = [&](int lw) -> uint32_t { const uint32_t w = my_hist[lw * TP]; my_hist[lw * TP] = 0; return w; };
-                            fold(tid, p, ref_c, ref_r, pl.x, pb_call_general(take, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet), false);
-                        }
-                    }
-                }
-                depth = 0; rmsq = 0; tot4 = 0;
+        // ---- call the cell.  Raw depth 0, or depth > 0 with every base filtered: errmod_cal(n = 0) + gl2cns give cb = 0
+        const bool unan = tot4 != 0 && pb_tot4_unanimous(tot4);
+        const bool hard = valid && tot4 != 0 && !unan;
+        const uint32_t hard_mask = __ballot_sync(0xffffffffu, hard);
+        if (hard_mask && qn + __popc(hard_mask) > PB_WQ) drain();      // warp-uniform
+        if (valid) {
+            if (tot4 == 0) fold(lane, p, ref_c, ref_r, s, 0, false);
+            else if (unan) {
+                auto peek = [&](int lw) -> uint32_t { return my_hist[lw * 32]; };
+                const int kk = pb_tot4_k(tot4);
+                const int bb = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
+                // count test against the need table (no error-model arithmetic); exact early-exit walk otherwise
+                const uint64_t cbw = pb_unanimous_by_count(peek, nl, need_s, kk, bb)
+                                         ? pb_unanimous_result(a.lhet, kk, bb, rmsq)
+                                         : pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet);
+                fold(lane, p, ref_c, ref_r, s, cbw, false);
+                for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * 32] = 0;
+            } else {                           // defer: move the histogram into the warp's queue
+                const int slot = qn + __popc(hard_mask & ((1u << lane) - 1u));
+                uint32_t *q = queue + (size_t)slot * qstride;
+                q[0] = (uint32_t)lane | ((uint32_t)s << 16); q[1] = (uint32_t)rmsq; q[2] = tot4;
+                for (int lw = 0; lw < n_lw; ++lw) { q[3 + lw] = my_hist[lw * 32]; my_hist[lw * 32] = 0; }
             }
         }
-        __syncthreads();         // the queue is complete
-        const int qn = (int)min(plan_n[3], (uint32_t)PB_QCAP);
-        for (int e = tid; e < qn; e += TP) {
-            const uint32_t *q = queue + (size_t)e * qstride;
-            const int slot = (int)(q[0] & 0xffffu), smp = (int)(q[0] >> 16);
-            const int pos = p0 + slot;
-            const int rc = (pos >= 0 && pos < a.ref_len) ? (int)(unsigned char)a.ref[pos] : 'N';
-            auto take = [&](int lw) -> uint32_t { return q[3 + lw]; };
-            fold(slot, pos, rc, pb_iupac_rev(rc), smp, pb_call_general(take, n_lw, qval_s, q[2], (int)q[1], fk_s, a.beta, a.lhet), true);
-        }
+        qn += __popc(hard_mask);
+        depth = 0; rmsq = 0; tot4 = 0;
     }
+    if (qn) drain();
 
     // the site: segbase's return value, coverage test, window membership (windows are sorted and disjoint)
+    __syncwarp();
     if (valid) {
-        const int fq = pb_site_fq(s_cnt4[tid]);
+        const int fq = pb_site_fq(s_cnt4[lane]);
         int lo = 0, hi = a.n_windows;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(a.win_end + mid) > p) hi = mid; else lo = mid + 1; }
         const bool in_win = lo < a.n_windows && __ldg(a.win_beg + lo) <= p;
-        const bool used = in_win && __popcll(s_cov[tid]) == n;
+        const bool used = in_win && __popcll(s_cov[lane]) == n;
         const int64_t o = (int64_t)p - a.span_beg;
-        a.site_type[o] = s_type[tid];
+        a.site_type[o] = s_type[lane];
         a.site_flag[o] = (uint8_t)((used ? 1 : 0) | ((used && fq > 0) ? 2 : 0));
     }
 }
