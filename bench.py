@@ -54,6 +54,7 @@ def parse():
                     help="generate this many distinct shards and cycle them (0 = auto: all distinct when the host has >= 8 cores per rank)")
     ap.add_argument("--cpu-sample-kb", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cli-sample-kb", type=int, default=500, help="BAM sample for the command-line (from-BAM) tier; 0 = skip")
     return ap.parse_args()
 
 
@@ -270,6 +271,8 @@ def run_b200(args):
     }
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(keep_fx, args.cpu_sample_kb * 1000)
+        if args.cli_sample_kb > 0:
+            line["cli_from_bam"] = cli_from_bam(args.cli_sample_kb * 1000)
     if rank == 0:
         print(json.dumps(line))
     for c in ctxs:
@@ -309,6 +312,37 @@ def cpu_baseline(fx_unused, sample_len):
     fx.close()
     return {"value": aligned / dt / 1e9, "unit": "Gbases/s", "cores": 1, "kind": kind, "windows_per_s": nwin / dt,
             "sample": "%d kb of the same workload (%d windows, %.3f Gbases), one process, %.1f s" % (sample_len // 1000, nwin, aligned / 1e9, dt)}
+
+
+def cli_from_bam(sample_len):
+    """Third timing tier ("E"): the `popbam` command line on BAM/BAI/FASTA files -- BAI slicing, BGZF
+    inflate and record decode on host threads, then the GPU path -- wall time of the whole process (CUDA start-up and
+    table construction included), on a bounded sample of the same workload."""
+    import pbtest
+    import popbam_b200
+    exe = popbam_b200.capi.PKG / "_build" / "popbam"
+    if not exe.exists():
+        return {"unavailable": "popbam executable not built"}
+    fx = sample_fixture(sample_len, seed=78, threads=min(16, os.cpu_count() or 4))
+    aligned = fx.aligned_bases()
+    nwin = len(pbtest.window_grid(0, fx.contig_len, WIN)[0])
+    with tempfile.TemporaryDirectory() as td:
+        bam, fa = fx.write_files(Path(td) / "c")
+        fx.close()
+        best = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            r = subprocess.run([str(exe), "sfs", "-w", "10", "-p", "og", "--shard-mb", "0.1", "-f", fa, bam, "chr1"],
+                               stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+            dt = time.perf_counter() - t0
+            if r.returncode != 0:
+                return {"unavailable": "popbam failed: " + r.stderr.decode()[-200:]}
+            best = dt if best is None else min(best, dt)
+        rows = r.stdout.count(b"\n")
+    return {"value": aligned / best / 1e9, "unit": "Gbases/s", "windows_per_s": nwin / best, "wall_s": best, "rows": rows,
+            "host_threads": min(16, os.cpu_count() or 4),
+            "sample": "%d kb BAM of the same workload (%d windows, %.3f Gbases), whole process incl. CUDA start-up" % (
+                sample_len // 1000, nwin, aligned / 1e9)}
 
 
 def run_reference(args):

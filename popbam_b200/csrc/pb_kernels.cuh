@@ -658,22 +658,26 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
             }
             __syncwarp();
             int j = 0;
-            for (; j + 1 < cnt; j += 2) {
-                const int4 a0 = recA[j], b0 = recB[j], a1 = recA[j + 1], b1 = recB[j + 1];   // same records for every lane: broadcast
-                const uint32_t u0 = (uint32_t)(pq - a0.y), u1 = (uint32_t)(pq - a1.y);
-                bool t0 = u0 < (uint32_t)a0.z, t1 = u1 < (uint32_t)a1.z;
-                if (CAP) {                                         // the cap precedes the filters; dead reads count
-                    t0 = t0 && depth < a.max_depth; depth += t0;
-                    t1 = t1 && depth < a.max_depth; depth += t1;
-                    t0 = t0 && !b0.w; t1 = t1 && !b1.w;
+            // four records per iteration: the four code loads are issued before any histogram update, so a
+            // warp keeps four global loads in flight (the loop is bound by their latency, see profiles/)
+            for (; j + 3 < cnt; j += 4) {
+                uint32_t cv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int4 aq = recA[j + q];                       // same record for every lane: broadcast
+                    const uint32_t u = (uint32_t)(pq - aq.y);
+                    bool t = u < (uint32_t)aq.z;
+                    if (CAP) {                                         // the cap precedes the filters; dead reads count
+                        t = t && depth < a.max_depth; depth += t;
+                        t = t && !recB[j + q].w;
+                    }
+                    cv[q] = PB_CODE_NONE;
+                    if (t) cv[q] = __ldg(a.codes + (((uint64_t)(uint32_t)recB[j + q].x << 32) | (uint32_t)aq.w) + u);
                 }
-                uint32_t c0v = PB_CODE_NONE, c1v = PB_CODE_NONE;
-                if (t0) c0v = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
-                if (t1) c1v = __ldg(a.codes + (((uint64_t)(uint32_t)b1.x << 32) | (uint32_t)a1.w) + u1);
-                count_base(c0v, b0);
-                count_base(c1v, b1);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) count_base(cv[q], recB[j + q]);
             }
-            if (j < cnt) {
+            for (; j < cnt; ++j) {
                 const int4 a0 = recA[j], b0 = recB[j];
                 const uint32_t u0 = (uint32_t)(pq - a0.y);
                 bool t0 = u0 < (uint32_t)a0.z;
