@@ -18,6 +18,8 @@ FIXTURES = {
                 snp_density=0.015, seed=13),
     # dense SNPs, more samples: LD stress (C3-shaped, cut down)
     "ld": dict(contig_len=20500, n_ingroup=23, has_outgroup=1, depth=12.0, snp_density=0.04, seed=14),
+    # the 64-sample limit (popbam.1:508): sample masks use bit 63, the sample partition uses both register banks
+    "n64": dict(contig_len=10500, n_ingroup=63, has_outgroup=1, depth=18.0, snp_density=0.03, het_frac=0.2, seed=15),
 }
 
 
@@ -75,6 +77,14 @@ CASES = [
     ("ld2_ld", "ld", ["ld", "-w", "10", "-o", "2"], "LD_WALL", {}, {}),
     ("hap1_ld", "ld", ["haplo", "-w", "10", "-o", "1"], "HAPLO_EHHS", {}, {}),
     ("sfs_ld_og", "ld", ["sfs", "-w", "10", "-p", "og"], "SFS", dict(flags=FLAG["OUTGROUP"], outidx=23), {}),
+    # 64 samples
+    ("nucdiv_n64", "n64", ["nucdiv", "-w", "5"], "NUCDIV", {}, {}),
+    ("ld0_n64", "n64", ["ld", "-w", "5", "-o", "0"], "LD_ZNS", {}, {}),
+    ("ld1_n64", "n64", ["ld", "-w", "5", "-o", "1"], "LD_OMEGA", {}, {}),
+    ("sfs_n64_og", "n64", ["sfs", "-w", "5", "-p", "og"], "SFS", dict(flags=FLAG["OUTGROUP"], outidx=63), {}),
+    ("hap0_n64", "n64", ["haplo", "-w", "5", "-o", "0"], "HAPLO_K", {}, {}),
+    ("div1_n64_og", "n64", ["diverge", "-w", "5", "-o", "1", "-p", "og"], "DIVERGE_POP", dict(flags=FLAG["OUTGROUP"], outidx=63), {}),
+    ("snp1_n64", "n64", ["snp", "-o", "1"], "SNP", {}, dict(snp_output=1)),
 ]
 
 

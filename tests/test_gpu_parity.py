@@ -67,7 +67,7 @@ def test_case_matches_reference_golden_and_oracle(case):
 ALL_AN = 0x7ff
 
 
-@pytest.mark.parametrize("fxname", ["c1", "edge", "rg2", "ld"])
+@pytest.mark.parametrize("fxname", ["c1", "edge", "rg2", "ld", "n64"])
 def test_all_analyses_in_one_pass_with_cb_words(fxname):
     """Every analysis from one pileup pass, plus the per-(site,sample) cb words of the whole span (bit-exact)."""
     fx = pbtest.fixture(fxname)
