@@ -54,7 +54,7 @@ def parse():
                     help="generate this many distinct shards and cycle them (0 = auto: all distinct when the host has >= 8 cores per rank)")
     ap.add_argument("--cpu-sample-kb", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cli-sample-kb", type=int, default=500, help="BAM sample for the command-line (from-BAM) tier; 0 = skip")
+    ap.add_argument("--cli-sample-kb", type=int, default=1000, help="BAM sample for the command-line (from-BAM) tier; 0 = skip")
     return ap.parse_args()
 
 
@@ -332,7 +332,7 @@ def cli_from_bam(sample_len):
         best = None
         for _ in range(2):
             t0 = time.perf_counter()
-            r = subprocess.run([str(exe), "sfs", "-w", "10", "-p", "og", "--shard-mb", "0.1", "-f", fa, bam, "chr1"],
+            r = subprocess.run([str(exe), "sfs", "-w", "10", "-p", "og", "--shard-mb", "0.05", "-f", fa, bam, "chr1"],
                                stdout=subprocess.PIPE, stderr=subprocess.PIPE)
             dt = time.perf_counter() - t0
             if r.returncode != 0:

@@ -4,7 +4,7 @@
  * TEST INFRASTRUCTURE ONLY (see pb_oracle.h).  Every function cites the reference code it
  * restates (paths relative to /root/reference).  Written from SURVEY.md Appendix A/D and the
  * cited lines; pinned against the compiled reference (oracle/_ref/popbam, oracle/_ref/refdump)
- * by tests/test_oracle_vs_ref.py and the committed goldens in tests/golden/.
+ * by tests/test_oracle_pin.py and the committed goldens in tests/golden/.
  *
  * Build: gcc -O2 -std=c11 -ffp-contract=off (x86-64, no FMA contraction: the reference is
  * built -O2 for baseline x86-64, so every double multiply and add rounds separately).

@@ -8,7 +8,7 @@
  * restatement is pinned against OUTPUTS OF THE REFERENCE ITSELF: oracle/_ref/popbam (the
  * unmodified reference compiled by oracle/Makefile) is run on seeded synthetic BAMs and its
  * stdout must equal pbo_format_window()'s text byte for byte for every subcommand/option
- * set (tests/test_oracle_vs_ref.py; committed goldens under tests/golden/), and
+ * set (tests/test_oracle_pin.py; committed goldens under tests/golden/), and
  * oracle/_ref/refdump dumps errmod tables / errmod_cal / gl2cns / segbase known-answer
  * vectors from the reference's own object files (tests/golden/kat_*.bin).
  */

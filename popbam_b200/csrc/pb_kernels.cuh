@@ -196,6 +196,20 @@ __global__ void k_level_table(PbCounters *ctr) {
     ctr->n_levels = nl;
 }
 
+// rms_thr[k]: the smallest sum of squared mapping qualities for which call_base's
+//     rms = (u64)(sqrtf((float)rmsq / k) + 0.499)           (popbam.cpp:292)
+// reaches min_rmsQ with k bases -- every step of that expression is monotone in rmsq, so qfilter's
+// rms >= min_rmsQ (pop_utils.cpp:110) is one integer compare for the cells that need nothing else.
+__global__ void k_rms_table(int min_rmsQ, int32_t *__restrict__ rms_thr /* [256] */) {
+    const int k = threadIdx.x;
+    if (k == 0 || min_rmsQ <= 0) { rms_thr[k] = 0; return; }
+    auto rms_of = [&](int rmsq) -> uint64_t { return (uint64_t)PB_DADD((double)PB_FSQRT(PB_FDIV((float)rmsq, (float)k)), 0.499); };
+    int lo = 0, hi = 255 * 255 * 255 + 1;       // first rmsq with rms >= min_rmsQ (hi: unreachable -> never passes)
+    if (rms_of(hi - 1) < (uint64_t)min_rmsQ) { rms_thr[k] = 0x7fffffff; return; }
+    while (lo < hi) { const int mid = lo + ((hi - lo) >> 1); if (rms_of(mid) >= (uint64_t)min_rmsQ) hi = mid; else lo = mid + 1; }
+    rms_thr[k] = lo;
+}
+
 // need[L][k] of pb_need_entry for every level of the region and every depth: one thread per entry.
 __global__ void __launch_bounds__(256) k_need_table(const PbCounters *__restrict__ ctr, const double *__restrict__ fk,
                                                     const double *__restrict__ beta, const double *__restrict__ lhet,
@@ -487,6 +501,7 @@ struct PbPileArgs {
     const double *fk, *beta, *lhet;
     const PbCounters *ctr;          // max_span, level table
     const uint8_t *need;            // [64][256] walk-free shortcut table (k_need_table)
+    const int32_t *rms_thr;         // [256] k_rms_table
     uint64_t *site_type;            // [span]
     uint8_t *site_flag;             // [span]  bit0 used, bit1 segregating
     uint64_t *cb_out;               // [span * n_samples] or null
@@ -498,7 +513,7 @@ struct PbPileArgs {
 // Dynamic shared memory of k_pileup_call<TP> for nl quality levels (independent of the sample count).
 static inline size_t pb_pile_smem(int tp, int nl) {
     const size_t per_warp = (size_t)PB_WCAP * 32 + (size_t)2 * nl * 32 * 4 + (size_t)PB_WQ * (3 + 2 * nl) * 4 + 32 * 20;
-    return (size_t)(tp / 32) * ((per_warp + 15) & ~(size_t)15) + 256 * 8 + 128 * 4 + 64 + (size_t)nl * 256 + 64;
+    return (size_t)(tp / 32) * ((per_warp + 15) & ~(size_t)15) + 256 * 8 + 128 * 4 + 256 * 4 + 64 + (size_t)nl * 256 + 64;
 }
 
 // One CTA = TP consecutive reference positions x all samples; one WARP = 32 positions, one thread = one
@@ -549,7 +564,8 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
     unsigned char *cbase = smem_raw + (size_t)(TP / 32) * per_warp;         // CTA-wide tables
     double *fk_s = reinterpret_cast<double *>(cbase);                       // [256]
     uint32_t *rng = reinterpret_cast<uint32_t *>(fk_s + 256);               // lo[64], hi[64]
-    uint8_t *qval_s = reinterpret_cast<uint8_t *>(rng + 128);               // [64]
+    int32_t *rms_thr_s = reinterpret_cast<int32_t *>(rng + 128);            // [256]
+    uint8_t *qval_s = reinterpret_cast<uint8_t *>(rms_thr_s + 256);         // [64]
     uint8_t *need_s = qval_s + 64;                                          // [nl][256]
 
     const int p0 = a.span_beg + (int)blockIdx.x * TP;
@@ -564,7 +580,7 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
     // lanes past the end of the span use a position no segment can cover
     const int pq = valid ? p : 0x7fffffff;
 
-    for (int i = tid; i < 256; i += TP) fk_s[i] = a.fk[i];
+    for (int i = tid; i < 256; i += TP) { fk_s[i] = a.fk[i]; rms_thr_s[i] = a.rms_thr[i]; }
     if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
     for (int lw = 0; lw < n_lw; ++lw) hist[lw * 32 + lane] = 0;
     s_cov[lane] = 0; s_type[lane] = 0; s_cnt4[lane] = 0;
@@ -693,16 +709,25 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
         const uint32_t hard_mask = __ballot_sync(0xffffffffu, hard);
         if (hard_mask && qn + __popc(hard_mask) > PB_WQ) drain();      // warp-uniform
         if (valid) {
-            if (tot4 == 0) fold(lane, p, ref_c, ref_r, s, 0, false);
-            else if (unan) {
+            if (tot4 == 0) {
+                // cb = 0.  With min_depth > 0 and min_snpQ > 0 such a cell is not covered, not derived and adds no
+                // derived-allele count (segbase takes its revert branch): nothing to fold
+                if (a.cb_out || a.min_depth <= 0 || a.min_snpQ <= 0) fold(lane, p, ref_c, ref_r, s, 0, false);
+            } else if (unan) {
                 auto peek = [&](int lw) -> uint32_t { return my_hist[lw * 32]; };
                 const int kk = pb_tot4_k(tot4);
                 const int bb = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
                 // count test against the need table (no error-model arithmetic); exact early-exit walk otherwise
-                const uint64_t cbw = pb_unanimous_by_count(peek, nl, need_s, kk, bb)
-                                         ? pb_unanimous_result(a.lhet, kk, bb, rmsq)
-                                         : pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet);
-                fold(lane, p, ref_c, ref_r, s, cbw, false);
+                const bool by_count = pb_unanimous_by_count(peek, nl, need_s, kk, bb);
+                if (by_count && !a.cb_out && (int)"ACGT"[bb] == ref_c) {
+                    // homozygous reference: clean_heterozygotes and segbase leave the word alone, the site type
+                    // bit stays 0; only qfilter's coverage test remains (pop_utils.cpp:102-120)
+                    if (rmsq >= rms_thr_s[kk] && kk >= a.min_depth && kk <= a.max_depth) s_cov[lane] |= 1ULL << s;
+                } else {
+                    const uint64_t cbw = by_count ? pb_unanimous_result(a.lhet, kk, bb, rmsq)
+                                                  : pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet);
+                    fold(lane, p, ref_c, ref_r, s, cbw, false);
+                }
                 for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * 32] = 0;
             } else {                           // defer: move the histogram into the warp's queue
                 const int slot = qn + __popc(hard_mask & ((1u << lane) - 1u));

@@ -40,7 +40,7 @@ struct pb_ctx {
     int n_sms = 148;
     size_t smem_optin = 0;
     // tables / contig
-    DevBuf d_fk, d_beta, d_lhet, d_ref;
+    DevBuf d_fk, d_beta, d_lhet, d_ref, d_rms_thr;
     int64_t ref_len = 0;
     int32_t ref_tid = -1;
     // region
@@ -292,6 +292,7 @@ int run_pipeline(pb_ctx *c) {
     pa.fk = dp<double>(c->d_fk); pa.beta = dp<double>(c->d_beta); pa.lhet = dp<double>(c->d_lhet);
     pa.ctr = ctr;
     pa.need = dp<uint8_t>(c->d_need);
+    pa.rms_thr = dp<int32_t>(c->d_rms_thr);
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
     PB_CUDA(c, cudaEventRecord(c->ev[2], st));
@@ -515,6 +516,10 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
         cudaMemcpy(c->d_beta.p, pbeta, nb * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
         cudaMemcpy(c->d_lhet.p, plhet, 65536 * 8, cudaMemcpyHostToDevice) != cudaSuccess)
         return bail(PB_ERR_CUDA, "table upload failed", c);
+    if (dev_reserve(c, c->d_rms_thr, 256 * sizeof(int32_t))) return bail(PB_ERR_NOMEM, "table allocation failed", c);
+    k_rms_table<<<1, 256, 0, c->stream>>>(p->min_rmsQ, dp<int32_t>(c->d_rms_thr));
+    c->launches += 1;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(PB_ERR_CUDA, "k_rms_table failed", c);
     if (status) *status = PB_OK;
     return c;
 }
@@ -523,7 +528,7 @@ void pb_destroy(pb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
+    DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_rms_thr, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
                       &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rnseg,
                       &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_need, &c->d_qtab, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
                       &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
