@@ -21,7 +21,7 @@
 
 #define PB_REC_DEAD (1u << 25)    // read fails min_mapQ: it only counts towards the raw-depth cap
 #define PB_BIN_SHIFT 7            // read-start bins of the depth bound (128 bp)
-#define PB_PART_CHUNK 2048        // reads per warp in the sample partition
+#define PB_PART_CHUNK 512         // reads per warp in the sample partition
 #define PB_KEY_DROP 0xffu
 #define PB_CODE_NONE 0xffu        // base filtered out (quality, N)
 #define PB_MAX_SEGS 255           // aligned segments (M/=/X ops) per read
