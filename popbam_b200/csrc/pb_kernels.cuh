@@ -554,8 +554,8 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const size_t per_warp = (((size_t)PB_WCAP * 32 + (size_t)n_lw * 32 * 4 + (size_t)PB_WQ * qstride * 4 + 32 * 20) + 15) & ~(size_t)15;
     unsigned char *wbase = smem_raw + (size_t)wid * per_warp;
-    int4 *recA = reinterpret_cast<int4 *>(wbase);                           // [PB_WCAP] {read start, seg start, seg len, offset lo}
-    int4 *recB = recA + PB_WCAP;                                            // [PB_WCAP] {offset hi, strand*32*4, mapq^2, dead}
+    int4 *recA = reinterpret_cast<int4 *>(wbase);                           // [PB_WCAP] {seg start, seg len, D lo, D hi}
+    int4 *recB = recA + PB_WCAP;                                            // [PB_WCAP] {strand*32*4, mapq^2, dead, -}
     uint64_t *s_cov = reinterpret_cast<uint64_t *>(recB + PB_WCAP);         // [32]
     uint64_t *s_type = s_cov + 32;                                          // [32]
     uint32_t *s_cnt4 = reinterpret_cast<uint32_t *>(s_type + 32);           // [32]
@@ -640,15 +640,18 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
     int depth = 0, rmsq = 0;
     uint32_t tot4 = 0;           // per-base counts of the cell, one byte each
     auto count_base = [&](uint32_t code, const int4 &rb) {
-        if (code != PB_CODE_NONE) {
-            const uint32_t inc = 1u << ((code & 3u) << 3);
-            // word index (level*2 + strand) * 32  ==  byte offset (code & 0xfc) * 64 + strand*128
-            uint32_t *h = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(my_hist) + (code & 0xfcu) * 64 + rb.y);
-            *h += inc;
-            tot4 += inc;
-            rmsq += rb.z;
-        }
+        // branch-free: a filtered base adds 0 to the level-0 word of its strand
+        const uint32_t ok = code != PB_CODE_NONE ? 1u : 0u;
+        const uint32_t c2 = ok ? code : 0u;
+        const uint32_t inc = ok << ((c2 & 3u) << 3);
+        // word index (level*2 + strand) * 32  ==  byte offset (code & 0xfc) * 64 + strand*128
+        uint32_t *h = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(my_hist) + (c2 & 0xfcu) * 64 + rb.x);
+        *h += inc;
+        tot4 += inc;
+        rmsq += (int)ok * rb.y;
     };
+    // codes[D + p]: the lane's fixed part of the address
+    const uint8_t *const lane_codes = a.codes + (int64_t)pq;
 
     for (int s = 0; s < n; ++s) {
         // ---- the warp's records of this sample: read start in (pw0 - max_span, pw1], found by ballots over the sorted starts
@@ -669,8 +672,11 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
             for (int i = lane; i < cnt; i += 32) {
                 const int4 r = a.srec[c0 + i];
                 const uint32_t z = (uint32_t)r.z, mq = (z >> 16) & 0xffu;
-                recA[i] = make_int4(r.x, r.y, (int)(z & 0xffffu), r.w);
-                recB[i] = make_int4((int)(z >> 26), (int)(((z >> 24) & 1u) * 128u), (int)(mq * mq), (int)((z >> 25) & 1u));
+                // D = byte offset of the segment's first code minus the segment start: the code of position p is at
+                // codes[D + p], so a lane adds D to its own fixed pointer codes + p
+                const int64_t D = (int64_t)(((uint64_t)(z >> 26) << 32) | (uint32_t)r.w) - (int64_t)r.y;
+                recA[i] = make_int4(r.y, (int)(z & 0xffffu), (int)(uint32_t)(uint64_t)D, (int)(uint32_t)((uint64_t)D >> 32));
+                recB[i] = make_int4((int)(((z >> 24) & 1u) * 128u), (int)(mq * mq), (int)((z >> 25) & 1u), 0);
             }
             __syncwarp();
             int j = 0;
@@ -681,25 +687,23 @@ __global__ void __launch_bounds__(TP, 8) k_pileup_call(const PbPileArgs a) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int4 aq = recA[j + q];                       // same record for every lane: broadcast
-                    const uint32_t u = (uint32_t)(pq - aq.y);
-                    bool t = u < (uint32_t)aq.z;
+                    bool t = (uint32_t)(pq - aq.x) < (uint32_t)aq.y;
                     if (CAP) {                                         // the cap precedes the filters; dead reads count
                         t = t && depth < a.max_depth; depth += t;
-                        t = t && !recB[j + q].w;
+                        t = t && !recB[j + q].z;
                     }
                     cv[q] = PB_CODE_NONE;
-                    if (t) cv[q] = __ldg(a.codes + (((uint64_t)(uint32_t)recB[j + q].x << 32) | (uint32_t)aq.w) + u);
+                    if (t) cv[q] = __ldg(lane_codes + (int64_t)(((uint64_t)(uint32_t)aq.w << 32) | (uint32_t)aq.z));
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) count_base(cv[q], recB[j + q]);
             }
             for (; j < cnt; ++j) {
                 const int4 a0 = recA[j], b0 = recB[j];
-                const uint32_t u0 = (uint32_t)(pq - a0.y);
-                bool t0 = u0 < (uint32_t)a0.z;
-                if (CAP) { t0 = t0 && depth < a.max_depth; depth += t0; t0 = t0 && !b0.w; }
+                bool t0 = (uint32_t)(pq - a0.x) < (uint32_t)a0.y;
+                if (CAP) { t0 = t0 && depth < a.max_depth; depth += t0; t0 = t0 && !b0.z; }
                 uint32_t c0v = PB_CODE_NONE;
-                if (t0) c0v = __ldg(a.codes + (((uint64_t)(uint32_t)b0.x << 32) | (uint32_t)a0.w) + u0);
+                if (t0) c0v = __ldg(lane_codes + (int64_t)(((uint64_t)(uint32_t)a0.w << 32) | (uint32_t)a0.z));
                 count_base(c0v, b0);
             }
         }
