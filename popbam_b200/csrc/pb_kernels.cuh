@@ -239,15 +239,19 @@ __global__ void __launch_bounds__(256) k_qual_table(const PbCounters *__restrict
 // found from base[] (reads are laid out back to back in file order) starting from a proportional
 // guess, which is exact for equal-length reads.
 #define PB_ENC_CHUNK 64
+#define PB_QROW 260
 __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
                                                 const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4,
                                                 const uint8_t *__restrict__ qual, int64_t n_bytes, double reads_per_byte,
                                                 int min_mapQ, const uint8_t *__restrict__ qtab, uint8_t *__restrict__ codes) {
-    __shared__ __align__(16) uint8_t qtab_s[65 * 256];   // row 64: all PB_CODE_NONE (reads the pileup never looks at)
+    // row stride 260: a stride of 256 bytes would put equal qualities of different rows in the same bank
+    __shared__ __align__(16) uint8_t qtab_s[65 * PB_QROW];   // row 64: all PB_CODE_NONE (reads the pileup never looks at)
     __shared__ uint16_t seq_s[256];       // packed sequence byte -> nt4 of its two bases (0xff: not A/C/G/T), first base low
-    for (int i = threadIdx.x; i < 64 * 256 / 16; i += 256)
-        reinterpret_cast<uint4 *>(qtab_s)[i] = __ldg(reinterpret_cast<const uint4 *>(qtab) + i);
-    qtab_s[64 * 256 + threadIdx.x] = (uint8_t)PB_CODE_NONE;
+    for (int i = threadIdx.x; i < 64 * 256 / 4; i += 256) {
+        const int row = i >> 6, w = i & 63;
+        reinterpret_cast<uint32_t *>(qtab_s + row * PB_QROW)[w] = __ldg(reinterpret_cast<const uint32_t *>(qtab) + i);
+    }
+    qtab_s[64 * PB_QROW + threadIdx.x] = (uint8_t)PB_CODE_NONE;
     {
         const uint32_t hi = threadIdx.x >> 4, lo = threadIdx.x & 15;
         const uint32_t bh = (uint32_t)((PB_NT16_NT4_LUT >> (hi * 4)) & 0xf), bl = (uint32_t)((PB_NT16_NT4_LUT >> (lo * 4)) & 0xf);
@@ -256,9 +260,9 @@ __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__res
     __syncthreads();
     // quality-table row of a read: its mapQ row, or the all-NONE row when the read is dropped / below min_mapQ
     auto row_of = [&](int64_t rr) -> uint32_t {
-        if (rr >= n || rkey[rr] == PB_KEY_DROP) return 64u * 256u;
+        if (rr >= n || rkey[rr] == PB_KEY_DROP) return 64u * PB_QROW;
         const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
-        return mq >= min_mapQ ? (uint32_t)min(mq, 63) * 256u : 64u * 256u;
+        return mq >= min_mapQ ? (uint32_t)min(mq, 63) * PB_QROW : 64u * PB_QROW;
     };
     const int64_t n_chunks = (n_bytes + PB_ENC_CHUNK - 1) / PB_ENC_CHUNK;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_chunks; t += (int64_t)gridDim.x * blockDim.x) {
