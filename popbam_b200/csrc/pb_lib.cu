@@ -190,7 +190,7 @@ int exclusive_scan_u32(pb_ctx *c, uint32_t *data, int64_t n) {
     return PB_OK;
 }
 
-constexpr int kTP = 128;   // positions (threads) per CTA of the hot kernel
+constexpr int kTP = 256;   // positions (threads) per CTA of the hot kernel
 
 int run_pipeline(pb_ctx *c) {
     const pb_params &P = c->prm;
