@@ -549,7 +549,7 @@ static inline size_t pb_pile_smem(int tp, int nl) {
 // position only keeps its coverage mask, derived-allele mask and derived-base counts (20 bytes of
 // shared memory), so nothing per (site, sample) is stored unless the caller asked for the cb words.
 template <int TP, bool CAP>
-__global__ void __launch_bounds__(TP, 1280 / TP) k_pileup_call(const PbPileArgs a) {
+__global__ void __launch_bounds__(TP, TP == 256 ? 5 : 8) k_pileup_call(const PbPileArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = a.n_samples;
     const int nl = a.ctr->n_levels;

@@ -190,7 +190,6 @@ int exclusive_scan_u32(pb_ctx *c, uint32_t *data, int64_t n) {
     return PB_OK;
 }
 
-constexpr int kTP = 256;   // positions (threads) per CTA of the hot kernel
 
 int run_pipeline(pb_ctx *c) {
     const pb_params &P = c->prm;
@@ -275,11 +274,15 @@ int run_pipeline(pb_ctx *c) {
         PB_CUDA(c, cudaGetLastError());
         c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, c->ctr_host.qval, 64);
     }
-    const size_t smem = pb_pile_smem(kTP, nl);
-    if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d samples x %d quality levels exceeds %zu bytes", n, nl, c->smem_optin);
+    // 256-thread CTAs (40 resident warps per SM) when their shared memory stays small, else 128-thread CTAs
+    const bool big = pb_pile_smem(256, nl) <= 46 * 1024;
+    const int tp = big ? 256 : 128;
+    const size_t smem = pb_pile_smem(tp, nl);
+    if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d quality levels exceeds %zu bytes", nl, c->smem_optin);
     const bool cap = c->ctr_host.nocap == 0;
-    if (cap) PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else PB_CUDA(c, cudaFuncSetAttribute(k_pileup_call<kTP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    void (*kern)(const PbPileArgs) = big ? (cap ? k_pileup_call<256, true> : k_pileup_call<256, false>)
+                                         : (cap ? k_pileup_call<128, true> : k_pileup_call<128, false>);
+    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PbPileArgs pa;
     pa.srec = dp<int4>(c->d_srec); pa.sstart = dp<uint32_t>(c->d_sstart);
     pa.codes = dp<uint8_t>(c->d_codes);
@@ -296,8 +299,7 @@ int run_pipeline(pb_ctx *c) {
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
     PB_CUDA(c, cudaEventRecord(c->ev[2], st));
-    if (cap) k_pileup_call<kTP, true><<<nblk(span, kTP), kTP, smem, st>>>(pa);
-    else k_pileup_call<kTP, false><<<nblk(span, kTP), kTP, smem, st>>>(pa);
+    kern<<<nblk(span, tp), tp, smem, st>>>(pa);
     c->launches += 1;
     PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaEventRecord(c->ev[3], st));
