@@ -35,6 +35,8 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 import numpy as np  # noqa: E402
 
+# DRAM bytes of one k_pileup_call launch on a 2.3 Mb shard of this workload, from the committed ncu capture
+TRAFFIC_BYTES_PER_LAUNCH = 866.4e6 + 22.5e6
 WIN = 10000
 READ_LEN = 100
 DEPTH = 30.0
@@ -44,7 +46,7 @@ N_INGROUP = 10
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--contig-mb", type=float, default=23.0)
@@ -288,7 +290,8 @@ def run_b200(args):
                 "windows_per_s": world * n_windows / (e2e_s / args.steps)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_pileup_call", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None,
+                     "frac": achieved / peak_gbs, "traffic": TRAFFIC_BYTES_PER_LAUNCH if abs(shard_len - 2300000) < 1 else None,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this kernel on a 2.3 Mb shard (profiles/r1_final_pileup_raw.txt)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": alg_bytes / len(shards), "launch_ms": pile_s * 1e3 / len(shards),
                      "kernel_share_of_step": pile_s / (seq_ms / 1e3),
