@@ -683,34 +683,32 @@ __global__ void __launch_bounds__(TP, TP == 256 ? 5 : 8) k_pileup_call(const PbP
                 recB[i] = make_int4((int)(((z >> 24) & 1u) * 128u), (int)(mq * mq), (int)((z >> 25) & 1u), 0);
             }
             __syncwarp();
-            // software pipeline, four records per stage: the code loads of stage i+1 are issued before the
-            // histogram updates of stage i, so a warp keeps up to eight global loads in flight (the loop is bound
-            // by their latency, see profiles/)
-            auto issue = [&](int jj) -> uint32_t {
-                uint32_t code = PB_CODE_NONE;
-                if (jj < cnt) {                                        // warp-uniform
-                    const int4 aq = recA[jj];                          // same record for every lane: broadcast
+            int j = 0;
+            // four records per iteration: the four code loads are issued before any histogram update, so a
+            // warp keeps four global loads in flight (the loop is bound by their latency, see profiles/)
+            for (; j + 3 < cnt; j += 4) {
+                uint32_t cv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int4 aq = recA[j + q];                       // same record for every lane: broadcast
                     bool t = (uint32_t)(pq - aq.x) < (uint32_t)aq.y;
                     if (CAP) {                                         // the cap precedes the filters; dead reads count
                         t = t && depth < a.max_depth; depth += t;
-                        t = t && !recB[jj].z;
+                        t = t && !recB[j + q].z;
                     }
-                    if (t) code = __ldg(lane_codes + (int64_t)(((uint64_t)(uint32_t)aq.w << 32) | (uint32_t)aq.z));
+                    cv[q] = PB_CODE_NONE;
+                    if (t) cv[q] = __ldg(lane_codes + (int64_t)(((uint64_t)(uint32_t)aq.w << 32) | (uint32_t)aq.z));
                 }
-                return code;
-            };
-            uint32_t cv[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) cv[q] = issue(q);
-            for (int j = 0; j < cnt; j += 4) {
-                uint32_t nv[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) nv[q] = issue(j + 4 + q);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (j + q < cnt) count_base(cv[q], recB[j + q]);   // warp-uniform
-                    cv[q] = nv[q];
-                }
+                for (int q = 0; q < 4; ++q) count_base(cv[q], recB[j + q]);
+            }
+            for (; j < cnt; ++j) {
+                const int4 a0 = recA[j], b0 = recB[j];
+                bool t0 = (uint32_t)(pq - a0.x) < (uint32_t)a0.y;
+                if (CAP) { t0 = t0 && depth < a.max_depth; depth += t0; t0 = t0 && !b0.z; }
+                uint32_t c0v = PB_CODE_NONE;
+                if (t0) c0v = __ldg(lane_codes + (int64_t)(((uint64_t)(uint32_t)a0.w << 32) | (uint32_t)a0.z));
+                count_base(c0v, b0);
             }
         }
         // ---- call the cell.  Raw depth 0, or depth > 0 with every base filtered: errmod_cal(n = 0) + gl2cns give cb = 0
