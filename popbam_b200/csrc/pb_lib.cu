@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <string>
 #include <vector>
 
@@ -484,6 +485,16 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
         return bail(PB_ERR_ARG, "n_samples / n_pops out of range (1..64)", nullptr);
     if (p->max_depth < 1 || p->max_depth > 255)
         return bail(PB_ERR_UNSUPPORTED, "max_depth must be in 1..255 (errmod_cal subsamples above 255, pop_utils.cpp:293)", nullptr);
+    // the error-model tables take ~0.25 s of host arithmetic: build them while the CUDA context comes up
+    const size_t nb = (size_t)64 * 256 * 256;
+    std::vector<double> fk, beta, lhet;
+    const bool own_tables = !(tables && tables->fk && tables->beta && tables->lhet);
+    std::future<void> table_job;
+    if (own_tables) {
+        fk.resize(256); beta.resize(nb); lhet.resize(65536);
+        table_job = std::async(std::launch::async, [&]() { pb_build_errmod_tables(fk.data(), beta.data(), lhet.data()); });
+    }
+    struct Joiner { std::future<void> &f; ~Joiner() { if (f.valid()) f.wait(); } } joiner{table_job};
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev < 1) {
@@ -503,13 +514,10 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     for (auto &ev : c->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
     // error-model tables
-    const size_t nb = (size_t)64 * 256 * 256;
-    std::vector<double> fk, beta, lhet;
     const double *pfk, *pbeta, *plhet;
-    if (tables && tables->fk && tables->beta && tables->lhet) { pfk = tables->fk; pbeta = tables->beta; plhet = tables->lhet; }
+    if (!own_tables) { pfk = tables->fk; pbeta = tables->beta; plhet = tables->lhet; }
     else {
-        fk.resize(256); beta.resize(nb); lhet.resize(65536);
-        pb_build_errmod_tables(fk.data(), beta.data(), lhet.data());
+        table_job.wait();
         pfk = fk.data(); pbeta = beta.data(); plhet = lhet.data();
     }
     if (dev_reserve(c, c->d_fk, 256 * 8) || dev_reserve(c, c->d_beta, nb * 8) || dev_reserve(c, c->d_lhet, 65536 * 8))

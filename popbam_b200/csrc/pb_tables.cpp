@@ -6,6 +6,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <thread>
 #include <vector>
 #include "../../include/popbam_b200.h"
 
@@ -49,17 +51,27 @@ extern "C" int pb_build_errmod_tables(double *fk, double *beta, double *lhet) {
         const double lgn = lgamma_int(n + 1);
         for (int k = 1; k <= n; ++k) lC[n << 8 | k] = lgn - lgamma_int(k + 1) - lgamma_int(n - k + 1);
     }
-    for (int q = 1; q != 64; ++q) {
-        const double e = std::pow(10.0, -q / 10.0);
-        const double le = std::log(e), le1 = std::log(1.0 - e);
-        for (int n = 1; n <= 255; ++n) {
-            double *row = beta + (q << 16 | n << 8);
-            long double sum = 0.0, sum1 = 0.0;
-            for (int k = n; k >= 0; --k, sum1 = sum) {
-                sum = sum1 + expl(lC[n << 8 | k] + k * le + (n - k) * le1);
-                row[k] = -10.0 / kLn10 * logl(sum1 / sum);
+    // the 63 quality rows are independent: a few host threads (same arithmetic per entry, so the table is identical)
+    std::atomic<int> next_q{63};
+    auto rows = [&]() {
+        for (int q = next_q.fetch_sub(1); q >= 1; q = next_q.fetch_sub(1)) {   // rows differ a lot in cost: hand them out one by one
+            const double e = std::pow(10.0, -q / 10.0);
+            const double le = std::log(e), le1 = std::log(1.0 - e);
+            for (int n = 1; n <= 255; ++n) {
+                double *row = beta + (q << 16 | n << 8);
+                long double sum = 0.0, sum1 = 0.0;
+                for (int k = n; k >= 0; --k, sum1 = sum) {
+                    sum = sum1 + expl(lC[n << 8 | k] + k * le + (n - k) * le1);
+                    row[k] = -10.0 / kLn10 * logl(sum1 / sum);
+                }
             }
         }
+    };
+    {
+        const int nt = 8;
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(rows);
+        for (auto &x : th) x.join();
     }
     for (int n = 0; n < 256; ++n)
         for (int k = 0; k < 256; ++k) lhet[n << 8 | k] = lC[n << 8 | k] - kLn2 * n;
