@@ -1,11 +1,13 @@
 // pb_kernels.cuh -- sm_100a kernels of the pileup -> consensus call -> per-site path.
 //
-//   k_rebase          batch-relative offsets -> absolute device offsets        (per read)
-//   k_read_prep       bam_plp_push filter + bam_calend                         (per read)
-//   k_qual_mask       which base qualities occur                               (per base, streaming)
-//   k_level_table     distinct error-model quality levels of the region
-//   k_part_count / k_part_scatter   stable partition of the reads by sample (file order kept)
-//   k_pileup_call     CIGAR-expanding pileup, per-(site,sample) call, per-site logic (the hot kernel)
+//   k_rebase          batch-relative offsets -> absolute device offsets                      (per read)
+//   k_read_prep       bam_plp_push filter + bam_calend, read-start bins                       (per read)
+//   k_depth_bound / k_depth_decide    can the raw-depth cap of call_base ever bind?
+//   k_qual_mask       which base qualities occur                                              (per base, streaming)
+//   k_level_table / k_qual_table / k_need_table / k_rms_table    per-region / per-context lookup tables
+//   k_encode          the per-base filter + code of call_base, once per base                  (per base, streaming)
+//   k_part_count / k_part_scatter     stable partition of the reads by sample (file order kept), CIGAR -> segments
+//   k_pileup_call     pileup, per-(site,sample) call, per-site logic                          (the hot kernel)
 //   k_window_sites    order-preserving compaction into num_sites / segregating-site lists
 //   k_scan_*          exclusive scans
 //

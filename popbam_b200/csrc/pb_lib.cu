@@ -57,7 +57,7 @@ struct pb_ctx {
     // derived
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
-    DevBuf d_num_sites, d_segsites, d_seg_off, d_seg_pos, d_seg_idx, d_seg_type, d_seg_ref, d_seg_cb;
+    DevBuf d_seg_type;     // arena of the segregating-site arrays (seg_layout)
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wall_u, d_stats, d_ld_kt, d_ld_km, d_ld_inv, d_ld_cnt;
     // pinned results
     HostBuf h_ctr, h_small, h_seg, h_span;
@@ -541,8 +541,7 @@ void pb_destroy(pb_ctx *c) {
     DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_rms_thr, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
                       &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rnseg,
                       &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_need, &c->d_qtab, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
-                      &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_num_sites, &c->d_segsites, &c->d_seg_off, &c->d_seg_pos,
-                      &c->d_seg_idx, &c->d_seg_type, &c->d_seg_ref, &c->d_seg_cb, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
+                      &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_seg_type, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
                       &c->d_rsum, &c->d_wall_u, &c->d_stats, &c->d_ld_kt, &c->d_ld_km, &c->d_ld_inv, &c->d_ld_cnt};
     for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
     HostBuf *hb[] = {&c->h_ctr, &c->h_small, &c->h_seg, &c->h_span};

@@ -56,15 +56,6 @@ struct PbStatArgs {
 #define PBA_HAPLO_DXY 0x200u
 #define PBA_FLAG_OUTGROUP 0x40u
 
-__device__ __forceinline__ double pb_block_sum(double v, double *sh /* [32] */) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
-    return t;
-}
 __device__ __forceinline__ int pb_block_sum_int(int v, int *sh /* [32] */) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     __syncthreads();
@@ -73,13 +64,6 @@ __device__ __forceinline__ int pb_block_sum_int(int v, int *sh /* [32] */) {
     int t = 0;
     for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
     return t;
-}
-
-// pop_ld.cpp:238-242
-__device__ __forceinline__ double pb_r2(uint64_t t1, uint64_t t2, double x0, double x1, const double *xtab) {
-    const double x11 = xtab[__popcll(t1 & t2)];
-    const double d = x11 - x0 * x1;
-    return (d * d) / (x0 * (1. - x0) * x1 * (1. - x1));
 }
 
 // ordered compaction of the sites of one population that satisfy `pred`; returns the count (all threads)
@@ -124,12 +108,9 @@ __device__ int pb_compact_sites(const uint64_t *__restrict__ T, int S, uint64_t 
 __global__ void __launch_bounds__(PB_ST_THREADS) k_window_stats(const PbStatArgs a) {
     extern __shared__ __align__(16) unsigned char st_smem[];
     uint16_t *diff = reinterpret_cast<uint16_t *>(st_smem);                   // [n*n]
-    __shared__ double shd[32];
     __shared__ int shi[32];
     __shared__ uint32_t shu[33];
     __shared__ int sfs_s[66];
-    __shared__ double xtab[65];
-    __shared__ unsigned long long best_key[2];
 
     const int w = blockIdx.x, tid = threadIdx.x;
     const int n = a.n, P = a.P;
@@ -280,7 +261,6 @@ __global__ void __launch_bounds__(PB_ST_THREADS) k_window_stats(const PbStatArgs
                 int dummy;
                 __syncthreads();
                 const int L = pb_compact_sites(T, S, mask, [=](uint64_t, int m) { return m > 1 && m < np - 1; }, lt, lm, 0, &dummy, shu);
-                if (tid == 0) { best_key[0] = 0; best_key[1] = 0; }
                 __syncthreads();
                 // most frequent partition; ties -> smallest value (first in ascending order)
                 unsigned long long bm = 0, bt = 0;
