@@ -79,6 +79,10 @@ __global__ void __launch_bounds__(PB_LD_THREADS) k_ld_keep(const PbLdArgs a) {
     }
 }
 
+// exact int -> double for 0 <= n < 2^32 on the FP64 pipe (exponent-bias trick) instead of a conversion on the
+// XU pipe, which the two POPCs of every pair already keep busy (profiles/r1_ld_rows_raw.txt)
+__device__ __forceinline__ double pb_u2d(unsigned n) { return __hiloint2double(0x43300000, (int)n) - 4503599627370496.0; }
+
 __global__ void __launch_bounds__(PB_LD_THREADS) k_ld_rows(const PbLdArgs a, int need_left, int n_row_blocks) {
     __shared__ uint64_t st[PB_LD_THREADS];
     __shared__ double sinv[PB_LD_THREADS];
@@ -105,18 +109,18 @@ __global__ void __launch_bounds__(PB_LD_THREADS) k_ld_rows(const PbLdArgs a, int
 #pragma unroll 4
             for (int k = 0; k < kn; ++k) {
                 const int num = np * __popcll(ti & st[k]) - mi * sm[k];
-                l = fma((double)(num * num), sinv[k], l);
+                l = fma(pb_u2d((unsigned)(num * num)), sinv[k], l);
             }
         } else if (k0 >= i0 + PB_LD_THREADS) {     // entirely right
 #pragma unroll 4
             for (int k = 0; k < kn; ++k) {
                 const int num = np * __popcll(ti & st[k]) - mi * sm[k];
-                r = fma((double)(num * num), sinv[k], r);
+                r = fma(pb_u2d((unsigned)(num * num)), sinv[k], r);
             }
         } else {                                   // the diagonal tile
             for (int k = 0; k < kn; ++k) {
                 const int num = np * __popcll(ti & st[k]) - mi * sm[k];
-                const double v = (double)(num * num) * sinv[k];
+                const double v = pb_u2d((unsigned)(num * num)) * sinv[k];
                 if (k0 + k < i) l += v; else if (k0 + k > i) r += v;
             }
         }
