@@ -1,11 +1,11 @@
 // pb_bamio.cpp -- see pb_bamio.h.  Host feeder of the popbam command line.
 #include "pb_bamio.h"
+#include "pb_inflate.h"
 
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
-#include <zlib.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -58,18 +58,7 @@ uint32_t BgzfFile::inflate_block(uint64_t coff, std::vector<uint8_t> &out) const
     const uint32_t hdr = 12 + xlen;
     const uint32_t isize = le32(h + bsize - 4);
     out.resize(isize);
-    if (isize) {
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, -15) != Z_OK) fail("zlib inflateInit2 failed");
-        zs.next_in = const_cast<uint8_t *>(h + hdr);
-        zs.avail_in = bsize - hdr - 8;
-        zs.next_out = out.data();
-        zs.avail_out = isize;
-        const int rc = inflate(&zs, Z_FINISH);
-        inflateEnd(&zs);
-        if (rc != Z_STREAM_END || zs.total_out != isize) fail("BGZF inflate failed");
-    }
+    if (isize && !inflate_raw(h + hdr, bsize - hdr - 8, out.data(), isize)) fail("BGZF inflate failed");
     return bsize;
 }
 

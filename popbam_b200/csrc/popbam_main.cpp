@@ -267,6 +267,20 @@ int main(int argc, char **argv) {
         } catch (const pbio::Error &e) { fatal(e.msg); }
         return 0;
     }
+    if (!strcmp(argv[1], "_inflate")) {
+        // test hook: popbam _inflate <in.bam> <out.bin> writes the concatenated uncompressed BGZF stream
+        if (argc < 4) return 2;
+        try {
+            pbio::BgzfFile bam; bam.open(argv[2]);
+            FILE *f = fopen(argv[3], "wb");
+            if (!f) return 2;
+            std::vector<uint8_t> out;
+            uint64_t off = 0;
+            for (;;) { const uint32_t c = bam.inflate_block(off, out); if (!c) break; off += c; fwrite(out.data(), 1, out.size(), f); }
+            fclose(f);
+        } catch (const pbio::Error &e) { fatal(e.msg); }
+        return 0;
+    }
     Run R;
     R.opt = parse(argc, argv);
     Options &o = R.opt;

@@ -77,3 +77,66 @@ def test_cli_errors_without_gpu(tmp_path):
     assert r.returncode == 1 and "does not exist" in r.stderr
     r = subprocess.run([str(EXE), "frobnicate"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "unrecognized command" in r.stderr
+
+
+def _bgzf_block(payload, level, strategy):
+    import struct
+    import zlib
+    co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+    raw = co.compress(payload) + co.flush()
+    bsize = len(raw) + 18 + 8
+    assert bsize <= 65536
+    hdr = b"\x1f\x8b\x08\x04" + b"\0" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+    return hdr + raw + struct.pack("<II", zlib.crc32(payload) & 0xffffffff, len(payload))
+
+
+def test_own_inflate_equals_zlib(tmp_path):
+    """The feeder's DEFLATE decoder (pb_inflate.cpp) against zlib: BGZF files built from many kinds of payload at every
+    compression level and strategy (stored, fixed and dynamic Huffman blocks, long matches, overlapping copies), and the
+    generator's own BAM files."""
+    import gzip
+    import zlib
+    popbam_b200.build()
+    rng = np.random.default_rng(7)
+    payloads = []
+    for n in (0, 1, 2, 7, 100, 4095, 20000, 60000):
+        payloads.append(rng.integers(0, 256, n, dtype=np.uint8).tobytes())                  # incompressible
+        payloads.append(rng.integers(0, 4, n, dtype=np.uint8).tobytes())                    # low entropy
+        payloads.append((b"ACGTTGCA" * (n // 8 + 1))[:n])                                   # periodic: overlapping copies
+        payloads.append(bytes(n))                                                           # one long run
+        payloads.append(rng.choice(np.frombuffer(b"!5?DI", dtype=np.uint8), n).tobytes())   # quality-like
+    words = [bytes(rng.integers(97, 123, int(rng.integers(2, 12)), dtype=np.uint8)) for _ in range(300)]
+    payloads.append(b" ".join(words[int(i)] for i in rng.integers(0, 300, 9000))[:60000])  # text-like, long codes
+    # skewed symbol frequencies force maximal code lengths (sub-tables)
+    freq = np.array([2.0 ** -(i % 24) for i in range(256)]); freq /= freq.sum()
+    payloads.append(rng.choice(256, 60000, p=freq).astype(np.uint8).tobytes())
+    blob, want = b"", b""
+    for i, pl in enumerate(payloads):
+        for level in (0, 1, 6, 9):
+            for strat in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+                if (i + level + strat) % 3 and len(pl) > 4095:
+                    continue                                   # thin the big ones out
+                if len(pl) > 60000 and level == 0:
+                    continue
+                blob += _bgzf_block(pl, level, strat)
+                want += pl
+    blob += _bgzf_block(b"", 6, zlib.Z_DEFAULT_STRATEGY)        # EOF marker
+    src = tmp_path / "mix.bgzf"
+    src.write_bytes(blob)
+    out = tmp_path / "mix.raw"
+    r = subprocess.run([str(EXE), "_inflate", str(src), str(out)], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out.read_bytes() == want
+    # corrupt streams are rejected, not mis-decoded silently
+    bad = bytearray(_bgzf_block(payloads[3 * 5 + 1] + payloads[5 * 5], 6, zlib.Z_DEFAULT_STRATEGY))
+    bad[40] ^= 0x55
+    (tmp_path / "bad.bgzf").write_bytes(bytes(bad))
+    r = subprocess.run([str(EXE), "_inflate", str(tmp_path / "bad.bgzf"), str(out)], stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0 or out.read_bytes() != payloads[3 * 5 + 1] + payloads[5 * 5]
+    # the generator's BAM (level 1) and a level-6 rewrite
+    fx = pbtest.fixture("edge")
+    for level in (1, 6):
+        bam, _ = fx.write_files(tmp_path / ("e%d" % level), level=level)
+        r = subprocess.run([str(EXE), "_inflate", bam, str(out)], stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        assert out.read_bytes() == gzip.open(bam).read()
