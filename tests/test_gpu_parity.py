@@ -258,3 +258,37 @@ def test_error_paths():
     ctx.region_end()
     assert ctx.res.num_sites[0] == 0 and ctx.res.seg_off[2] == 0
     ctx.close()
+
+
+@pytest.mark.parametrize("name,kw,pkw", [
+    # ~90 segment records per warp and sample: several staging chunks per sample (PB_WCAP), no cap
+    ("deep", dict(contig_len=6000, n_ingroup=2, has_outgroup=1, depth=70.0, snp_density=0.02, het_frac=0.3, seed=31), {}),
+    # the same pileups with the raw-depth cap binding almost everywhere (CAP kernel variant across chunks)
+    ("deep_cap", dict(contig_len=6000, n_ingroup=2, has_outgroup=1, depth=70.0, snp_density=0.02, het_frac=0.3, seed=31),
+     dict(max_depth=40)),
+    # a variant at every third position, half of them heterozygous: most cells are not unanimous, so the per-warp
+    # queues of deferred cells fill up and drain many times
+    ("dense", dict(contig_len=8000, n_ingroup=7, has_outgroup=1, depth=25.0, snp_density=0.35, het_frac=0.5, edge_mode=1, seed=32), {}),
+    # short reads (36 bp): several reads per 64-byte chunk of the encode pass, many records per position
+    ("short", dict(contig_len=8000, n_ingroup=4, has_outgroup=1, depth=30.0, read_len=36, snp_density=0.03, seed=33), {}),
+])
+def test_stress_shapes_match_oracle(name, kw, pkw):
+    fx = pbtest.Fixture(**kw)
+    p = fx.params(flags=pbtest.FLAG["EMIT_CB"], **pkw)
+    wb, we = pbtest.window_grid(0, fx.contig_len, 2000)
+    an = pbtest.AN["NUCDIV"] | pbtest.AN["SFS"] | pbtest.AN["SNP"] | pbtest.AN["LD_ZNS"]
+    ctx = run_gpu(fx, p, an, wb, we)
+    orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
+    got, want = pbtest.result_arrays(ctx.res, want_cb=True), pbtest.result_arrays(orc.res, want_cb=True)
+    span = int(we[-1] - wb[0])
+    inwin = np.zeros(span, dtype=bool)
+    for b, e in zip(wb, we):
+        inwin[b - wb[0]:e - wb[0]] = True
+    n = fx.n_samples
+    assert np.array_equal(got["cb"].reshape(span, n)[inwin], want["cb"].reshape(span, n)[inwin])
+    assert_same(got, want, ["NUCDIV", "SFS", "SNP", "LD_ZNS"])
+    # and without the cb words (the fast paths that skip folding are only taken then)
+    p2 = fx.params(**pkw)
+    ctx2 = run_gpu(fx, p2, an, wb, we)
+    assert_same(pbtest.result_arrays(ctx2.res), want, ["NUCDIV", "SFS", "SNP", "LD_ZNS"])
+    orc.close(); ctx.close(); ctx2.close(); fx.close()
