@@ -1,0 +1,477 @@
+// pb_fast.cuh -- bit-sliced fast path of the pileup for the overwhelming majority of cells, and the
+// per-cell path for the rest.  Used when the raw-depth cap cannot bind (k_depth_bound), the caller did
+// not ask for the per-(site,sample) words, and min_depth / min_snpQ are positive.
+//
+// Why.  k_pileup_call spends ~29 warp instructions per (record, 32 positions): one code load, one
+// histogram update, one total per LANE per record.  But ~92 % of the cells are "easy": every passing
+// base equals the reference base and the depth alone proves the shortcut of pb_walk.cuh
+// (pb_need_entry), so the cell is homozygous reference and all the site needs from it is qfilter's
+// coverage bit (pop_utils.cpp:102-120).  For such cells nothing per base has to be looked at one by
+// one: with the bases' properties stored as BIT-PLANES (one bit per base), a single THREAD handles
+// 32 positions of one sample with 32-bit logic ops:
+//     planes (k_bitplanes, parallel to codes[]):  P passing base, B0/B1 its two base bits, H quality level >= hi
+//     per record:  window = funnel-shift of the planes to the strip, masked to the segment
+//                  mismatch |= P & ((B0 ^ R0) | (B1 ^ R1))         (R: the reference strip's planes)
+//                  lowq     |= P when the read's mapQ < min_rmsQ   (else rms >= min_rmsQ is guaranteed)
+//                  k  += P,  khi += H    as bit-sliced counters (half-adder chains over 6 / 4 planes)
+//     per strip:   easy = no mismatch, no lowq, k in the range where need[0][k] <= k, or khi >= Hmin ...
+// i.e. ~70 thread instructions per record for 32 cells instead of ~29 warp instructions (928 thread
+// slots).  The remaining cells (a sequencing error, a variant, a low-mapQ read, an odd depth) are
+// listed in bit masks and called one cell per thread by k_hard_cells with the exact machinery of
+// pb_cell.cuh / pb_walk.cuh; k_fast_sites puts the two together into the per-site result.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pb_kernels.cuh"
+
+struct PbFastParams {        // derived from the need table (k_fast_params), cached with it
+    int k0lo, k0hi;          // for k0lo <= k <= k0hi: need[0][k] != 0 and need[0][k] <= k  (the depth alone suffices)
+    int k1lo, k1hi, hmin;    // for k1lo <= k <= k1hi: need[hi][k] != 0 and <= hmin <= 15   (khi >= hmin suffices)
+    int hi_level;            // level of the H plane (n_levels: none)
+};
+
+// ---- bit-planes of the codes, interleaved: planes[1 + w] = {P, B0, B1, H} of the 32 bases codes[32w .. 32w+31]
+// (one pad element in front, PB_PLANE_PAD behind).  Each thread turns 32 code bytes into one uint4 with packed-byte
+// arithmetic: a per-byte predicate is brought to bit 7 (or bit 0) of its byte and the four flags of a word are
+// gathered into a nibble by one multiply (0x00204081 moves byte i's flag to bit 28 + i resp. 21 + i; the sixteen
+// partial products land on distinct bits, so nothing carries).
+#define PB_PLANE_PAD 16
+__device__ __forceinline__ void pb_planes_of_word(uint32_t w, uint32_t hadd, int sh, uint32_t &P, uint32_t &B0, uint32_t &B1, uint32_t &H) {
+    const uint32_t x = ~w;                                                         // a byte of x is 0 <=> code == PB_CODE_NONE
+    const uint32_t nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+    const uint32_t p4 = (nz * 0x00204081u) >> 28;
+    const uint32_t b04 = (((w & 0x01010101u) * 0x00204081u) >> 21) & p4;
+    const uint32_t b14 = ((((w >> 1) & 0x01010101u) * 0x00204081u) >> 21) & p4;
+    const uint32_t h4 = (((((w >> 2) & 0x3f3f3f3fu) + hadd) & 0x80808080u) * 0x00204081u) >> 28;      // level >= hi_level
+    P |= p4 << sh; B0 |= b04 << sh; B1 |= b14 << sh; H |= (h4 & p4) << sh;
+}
+__global__ void __launch_bounds__(256) k_bitplanes(const uint8_t *__restrict__ codes, int64_t n_bytes, const PbFastParams *__restrict__ fp,
+                                                   uint4 *__restrict__ planes) {
+    const int hi = fp->hi_level;                                                   // <= 64
+    const uint32_t hadd = (uint32_t)(128 - hi) * 0x01010101u;
+    const int64_t n_words = (n_bytes + 31) >> 5;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
+        const int64_t o = w << 5;
+        uint32_t P = 0, B0 = 0, B1 = 0, H = 0;
+        if (o + 32 <= n_bytes) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(codes + o)), b = __ldg(reinterpret_cast<const uint4 *>(codes + o + 16));
+            pb_planes_of_word(a.x, hadd, 0, P, B0, B1, H);  pb_planes_of_word(a.y, hadd, 4, P, B0, B1, H);
+            pb_planes_of_word(a.z, hadd, 8, P, B0, B1, H);  pb_planes_of_word(a.w, hadd, 12, P, B0, B1, H);
+            pb_planes_of_word(b.x, hadd, 16, P, B0, B1, H); pb_planes_of_word(b.y, hadd, 20, P, B0, B1, H);
+            pb_planes_of_word(b.z, hadd, 24, P, B0, B1, H); pb_planes_of_word(b.w, hadd, 28, P, B0, B1, H);
+        } else {
+            for (int i = 0; o + i < n_bytes; ++i) {
+                const uint32_t c = codes[o + i];
+                if (c == PB_CODE_NONE) continue;
+                P |= 1u << i; B0 |= (c & 1u) << i; B1 |= ((c >> 1) & 1u) << i; H |= (uint32_t)((int)(c >> 2) >= hi) << i;
+            }
+        }
+        planes[w + 1] = make_uint4(P, B0, B1, H);
+    }
+    if (blockIdx.x == 0 && threadIdx.x <= PB_PLANE_PAD) {                           // pad: one in front, PB_PLANE_PAD behind
+        const int64_t i = threadIdx.x ? n_words + threadIdx.x : 0;
+        planes[i] = make_uint4(0, 0, 0, 0);
+    }
+}
+
+// ---- reference planes of a contig: R0/R1 = the two bits of A/C/G/T, RV = the byte is an upper-case A/C/G/T
+// (a reference byte that is anything else never matches a called base, pop_utils.cpp:139 / SURVEY Q7)
+__global__ void __launch_bounds__(256) k_ref_planes(const char *__restrict__ ref, int64_t ref_len, uint32_t *__restrict__ r0,
+                                                    uint32_t *__restrict__ r1, uint32_t *__restrict__ rv) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_words = (ref_len + 31) >> 5;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_words + 1; w += warps) {
+        const int64_t o = (w << 5) + lane;
+        const int c = o < ref_len ? (int)(unsigned char)ref[o] : 'N';
+        const int b = c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : -1;
+        const uint32_t v = __ballot_sync(0xffffffffu, b >= 0);
+        const uint32_t x0 = __ballot_sync(0xffffffffu, b >= 0 && (b & 1));
+        const uint32_t x1 = __ballot_sync(0xffffffffu, b >= 0 && (b & 2));
+        if (lane == 0) { rv[w] = v; r0[w] = x0; r1[w] = x1; }
+    }
+}
+
+// The count tests of k_pile_fast as depth ranges.  Level 0 holds every passing base, so need[0][k] <= k
+// means "k unanimous bases always take the shortcut"; the longest such run of depths is [k0lo, k0hi].
+// Deeper cells are proven by their count of bases at or above one chosen level (the H plane): the lowest
+// level whose entries stay <= 15 (the bit-sliced counter of H saturates at 16) for the depths right above k0hi.
+__global__ void k_fast_params(const PbCounters *__restrict__ ctr, const uint8_t *__restrict__ need, PbFastParams *__restrict__ fp) {
+    if (threadIdx.x || blockIdx.x) return;
+    const int nl = ctr->n_levels;
+    int k0lo = 1, k0hi = 0;
+    for (int k = 1, start = 1; k <= 64; ++k) {
+        const int nd = (k <= 63 && nl > 0) ? need[k] : 0;
+        if (nd && nd <= k) continue;
+        if (k - start > k0hi - k0lo + 1) { k0lo = start; k0hi = k - 1; }
+        start = k + 1;
+    }
+    int hi = nl, k1lo = 1, k1hi = 0, hmin = 0;
+    for (int L = 1; L < nl && hi == nl && k0hi < 63; ++L) {
+        // a run of usable depths that starts at or below k0hi + 1
+        int lo = k0hi + 1, mx = 0;
+        const int nd0 = need[L * 256 + lo];
+        if (!nd0 || nd0 > 15) continue;
+        int k = lo;
+        for (; k <= 63; ++k) { const int nd = need[L * 256 + k]; if (!nd || nd > 15) break; mx = max(mx, nd); }
+        if (k - 1 < min(63, k0hi + 8)) continue;
+        while (lo > 1) { const int nd = need[L * 256 + lo - 1]; if (!nd || nd > mx) break; --lo; }
+        hi = L; k1lo = lo; k1hi = k - 1; hmin = mx;
+    }
+    fp->k0lo = k0lo; fp->k0hi = k0hi; fp->k1lo = k1lo; fp->k1hi = k1hi; fp->hmin = hmin; fp->hi_level = hi;
+}
+
+// bit-sliced "value <= C" for 6-plane counters (C in 0..63)
+__device__ __forceinline__ uint32_t pb_bs_le6(const uint32_t c[6], int C) {
+    uint32_t lt = 0, eq = 0xffffffffu;
+#pragma unroll
+    for (int b = 5; b >= 0; --b) {
+        if ((C >> b) & 1) { lt |= eq & ~c[b]; eq &= c[b]; }
+        else eq &= ~c[b];
+    }
+    return lt | eq;
+}
+
+// Strip index of the sample-partitioned records: F[s][i] = index of the first record of sample s whose read
+// starts at or after  span_beg + 32 * (i - M),  i in [0, NI), M = ceil(max_span / 32).  The records that can
+// cover strip t (positions S .. S+31, S = span_beg + 32 t) are then [F[s][t], F[s][t + M + 1]) -- a superset of
+// "read start in (S - max_span, S + 31]" found without any search.  One thread per record writes the entries
+// whose boundary falls between its predecessor's start and its own.
+__global__ void __launch_bounds__(256) k_strip_index(const int4 *__restrict__ srec, const uint32_t *__restrict__ sstart, int n_samples,
+                                                     int span_beg, int M, int NI, uint32_t *__restrict__ F) {
+    __shared__ uint32_t ss[PB_MAX_SAMPLES + 1];
+    if (threadIdx.x <= n_samples) ss[threadIdx.x] = sstart[threadIdx.x];
+    __syncthreads();
+    const uint32_t total = ss[n_samples];
+    auto cell_of = [&](int x) -> int {                  // last i with span_beg + 32 (i - M) <= x
+        const int d = x - span_beg;
+        return (d >= 0 ? d >> 5 : -((-d + 31) >> 5)) + M;
+    };
+    for (uint32_t j = blockIdx.x * 256u + threadIdx.x; j < total; j += gridDim.x * 256u) {
+        int s = 0;
+        while (ss[s + 1] <= j) ++s;
+        const int x = srec[j].x;
+        int i_lo = j == ss[s] ? 0 : cell_of(srec[j - 1].x) + 1;
+        int i_hi = min(cell_of(x), NI - 1);
+        uint32_t *f = F + (size_t)s * NI;
+        for (int i = max(i_lo, 0); i <= i_hi; ++i) f[i] = j;
+        if (j + 1 == ss[s + 1]) for (int i = max(cell_of(x) + 1, 0); i < NI; ++i) f[i] = j + 1;
+    }
+    // samples without records
+    for (int s = blockIdx.x; s < n_samples; s += gridDim.x)
+        if (ss[s] == ss[s + 1]) for (int i = threadIdx.x; i < NI; i += 256) F[(size_t)s * NI + i] = ss[s];
+}
+
+struct PbFastArgs {
+    const int4 *srec;
+    const uint32_t *F;                       // strip index (k_strip_index), [n_samples][NI]
+    int M, NI, RC;                           // RC: records staged per pass
+    const uint4 *planes;                     // {P, B0, B1, H} per 32 code bytes (one pad element in front)
+    const uint32_t *r0, *r1, *rv;            // reference planes, bit = absolute position
+    int64_t ref_len;
+    int span_beg, span_end;
+    int n_samples, n_strips, n_sblocks;      // n_sblocks = strip blocks of PB_FAST_STRIPS strips
+    int min_depth, min_rmsQ;
+    int W;                                   // plane elements staged per record: covers 31 + the longest segment
+    const PbCounters *ctr;
+    const PbFastParams *fp;
+    uint32_t *cov32, *hard32;                // [n_samples][n_strips]
+};
+
+#define PB_FAST_STRIPS 64          // strips of 32 positions per CTA (one sample)
+#define PB_FAST_G 4                // threads sharing a strip (each takes every G-th record; partial counters are added)
+static inline int pb_fast_words(int max_span) { return ((31 + (max_span > 0 ? max_span - 1 : 0)) >> 5) + 1; }
+static inline int pb_fast_rc(int W) { const int rc = (48 * 1024) / (16 * (1 + W)); return rc > 512 ? 512 : rc; }   // records staged per pass
+static inline size_t pb_fast_smem(int W) { return (size_t)pb_fast_rc(W) * 16 * (1 + (size_t)W); }
+
+// One CTA = one sample x 64 strips of 32 positions; PB_FAST_G threads share a strip.
+// The CTA stages its records (read start in (first position - max_span, last position]) and the plane
+// elements their bases live in into shared memory with wide coalesced-per-record loads -- every record is
+// needed by four or five neighbouring strips, and staging makes that reuse explicit instead of leaving it
+// to L2 (the unstaged version of this kernel moved 18 GB through L2 for 0.2 GB of distinct data).
+// Then every thread walks the records that can cover its strip.
+__global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const PbFastArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int4 *recS = reinterpret_cast<int4 *>(smem_raw);                      // [RC] {seg start, z, bit offset in staged words, read start}
+    uint4 *plS = reinterpret_cast<uint4 *>(recS + a.RC);                  // [RC][W]
+    const int tid = threadIdx.x;
+    const int s = (int)(blockIdx.x / a.n_sblocks), sb = (int)(blockIdx.x % a.n_sblocks);
+    const int strip = sb * PB_FAST_STRIPS + tid / PB_FAST_G, g = tid % PB_FAST_G;
+    const int W = a.W;
+    const uint32_t *Fs = a.F + (size_t)s * a.NI;
+    const int t0 = sb * PB_FAST_STRIPS;
+    const uint32_t clo = __ldg(Fs + t0), chi = __ldg(Fs + min(t0 + PB_FAST_STRIPS, a.n_strips) + a.M);
+    const int S = a.span_beg + strip * 32;
+    const bool live = strip < a.n_strips;
+    const int strip_last = min(S + 31, a.span_end - 1);
+    const uint32_t my_lo = live ? __ldg(Fs + strip) : 0u, my_hi = live ? __ldg(Fs + strip + a.M + 1) : 0u;
+    uint32_t ck[6] = {0, 0, 0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
+    uint32_t kover = 0, hover = 0, mism = 0, lowq = 0;
+    uint32_t R0 = 0, R1 = 0, RV = 0;
+    if (live && g == 0 && S >= 0 && S < a.ref_len) {                      // reference planes of the strip (bit i = position S + i)
+        const int64_t wi = S >> 5; const int sh = S & 31;
+        R0 = __funnelshift_r(a.r0[wi], a.r0[wi + 1], sh);
+        R1 = __funnelshift_r(a.r1[wi], a.r1[wi + 1], sh);
+        RV = __funnelshift_r(a.rv[wi], a.rv[wi + 1], sh);
+    }
+    R0 = __shfl_sync(0xffffffffu, R0, (tid & 31) & ~(PB_FAST_G - 1));
+    R1 = __shfl_sync(0xffffffffu, R1, (tid & 31) & ~(PB_FAST_G - 1));
+    RV = __shfl_sync(0xffffffffu, RV, (tid & 31) & ~(PB_FAST_G - 1));
+    for (uint32_t c0 = clo; c0 < chi; c0 += (uint32_t)a.RC) {
+        const int cnt = (int)min((uint32_t)a.RC, chi - c0);
+        if (c0 != clo) __syncthreads();
+        for (int r = tid; r < cnt; r += PB_FAST_STRIPS * PB_FAST_G) {
+            const int4 rc = __ldg(&a.srec[c0 + r]);
+            const uint32_t z = (uint32_t)rc.z;
+            const int64_t gb = (int64_t)(((uint64_t)(z >> 26) << 32) | (uint32_t)rc.w) + 32;      // bit index of the segment's first base
+            const uint4 *src = a.planes + (gb >> 5);
+            recS[r] = make_int4(rc.y, rc.z, (int)(gb & 31), rc.x);
+            uint4 *dst = plS + (size_t)r * W;
+            for (int k0 = 0; k0 < W; k0 += 4) {               // four loads in flight
+                uint4 v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (k0 + q < W) v[q] = __ldg(src + k0 + q);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) if (k0 + q < W) dst[k0 + q] = v[q];
+            }
+        }
+        __syncthreads();
+        if (live) {
+            const int lo = (int)(max(my_lo, c0) - c0), j1 = (int)min((uint32_t)cnt, max(my_hi, c0) - c0);
+            for (int j = lo + g; j < j1; j += PB_FAST_G) {
+                const int4 r = recS[j];
+                const uint32_t z = (uint32_t)r.y;
+                const int len = (int)(z & 0xffffu);
+                const int u = S - r.x;                                   // segment-relative index of the strip's first position
+                const int i0 = max(0, -u), i1 = min(32, len - u);
+                if (i1 <= i0) continue;
+                const uint32_t m = (i1 == 32 ? 0xffffffffu : (1u << i1) - 1u) & ~((1u << i0) - 1u);
+                const int t = r.z + u;                                   // bit index in the staged elements (>= -31)
+                const int wi = t >> 5, sh = t & 31;
+                const uint4 *pw = plS + (size_t)j * W;
+                const uint4 zero = make_uint4(0, 0, 0, 0);
+                const uint4 lo4 = wi >= 0 ? pw[wi] : zero;
+                const uint4 hi4 = pw[min(wi + 1, W - 1)];               // past the staged elements only masked bits are read
+                const uint32_t P = __funnelshift_r(lo4.x, hi4.x, sh) & m;
+                const uint32_t B0 = __funnelshift_r(lo4.y, hi4.y, sh);
+                const uint32_t B1 = __funnelshift_r(lo4.z, hi4.z, sh);
+                const uint32_t H = __funnelshift_r(lo4.w, hi4.w, sh) & m;
+                mism |= P & (((B0 ^ R0) | (B1 ^ R1)) | ~RV);
+                if ((int)((z >> 16) & 0xffu) < a.min_rmsQ) lowq |= P;
+                uint32_t carry = P;
+#pragma unroll
+                for (int b = 0; b < 6; ++b) { const uint32_t tt = ck[b] & carry; ck[b] ^= carry; carry = tt; }
+                kover |= carry;
+                carry = H;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) { const uint32_t tt = ch[b] & carry; ch[b] ^= carry; carry = tt; }
+                hover |= carry;
+            }
+        }
+    }
+    // add the partial counters of the PB_FAST_G threads of a strip (bit-sliced ripple adders)
+#pragma unroll
+    for (int o = 1; o < PB_FAST_G; o <<= 1) {
+        uint32_t carry = 0;
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, ck[b], o), x = ck[b] ^ y;
+            const uint32_t c2 = (ck[b] & y) | (x & carry);
+            ck[b] = x ^ carry; carry = c2;
+        }
+        kover |= carry | __shfl_xor_sync(0xffffffffu, kover, o);
+        carry = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, ch[b], o), x = ch[b] ^ y;
+            const uint32_t c2 = (ch[b] & y) | (x & carry);
+            ch[b] = x ^ carry; carry = c2;
+        }
+        hover |= carry | __shfl_xor_sync(0xffffffffu, hover, o);
+        mism |= __shfl_xor_sync(0xffffffffu, mism, o);
+        lowq |= __shfl_xor_sync(0xffffffffu, lowq, o);
+    }
+    if (!live || g != 0) return;
+    const PbFastParams fp = *a.fp;
+    const uint32_t valid = (strip_last - S + 1) >= 32 ? 0xffffffffu : (1u << (strip_last - S + 1)) - 1u;
+    const uint32_t nonzero = (ck[0] | ck[1] | ck[2] | ck[3] | ck[4] | ck[5] | kover) & valid;
+    // depth alone / count of high-quality bases proves the shortcut (pb_need_entry)
+    uint32_t count_ok = fp.k0hi >= fp.k0lo ? pb_bs_le6(ck, fp.k0hi) & ~pb_bs_le6(ck, fp.k0lo - 1) : 0u;
+    if (fp.k1hi >= fp.k1lo && fp.hmin > 0) {
+        // khi >= hmin  <=>  not (khi <= hmin - 1), or the 4-plane counter overflowed (>= 16 > hmin)
+        uint32_t lt = 0, eq = 0xffffffffu;
+        const int C = fp.hmin - 1;
+#pragma unroll
+        for (int b = 3; b >= 0; --b) {
+            if ((C >> b) & 1) { lt |= eq & ~ch[b]; eq &= ch[b]; }
+            else eq &= ~ch[b];
+        }
+        const uint32_t hge = ~(lt | eq) | hover;
+        count_ok |= hge & pb_bs_le6(ck, fp.k1hi) & ~pb_bs_le6(ck, fp.k1lo - 1);
+    }
+    const uint32_t easy = nonzero & ~mism & ~lowq & ~kover & count_ok;
+    // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
+    // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is a bit-sliced compare
+    const uint32_t dge = a.min_depth <= 0 ? 0xffffffffu : a.min_depth > 63 ? 0u : ~pb_bs_le6(ck, a.min_depth - 1);
+    a.cov32[(size_t)s * a.n_strips + strip] = easy & dge;
+    a.hard32[(size_t)s * a.n_strips + strip] = nonzero & ~easy;
+}
+
+struct PbHardArgs {
+    const int4 *srec;
+    const uint32_t *F;                       // strip index (k_strip_index)
+    int M, NI;
+    const uint8_t *codes;
+    const char *ref;
+    int64_t ref_len;
+    int span_beg, span_end;
+    const int32_t *win_beg, *win_end;
+    int n_windows;
+    int n_samples, n_strips;
+    int min_depth, max_depth, min_rmsQ, min_snpQ;
+    int het_mode;
+    const double *fk, *beta, *lhet;
+    const PbCounters *ctr;
+    const uint8_t *need;
+    const uint32_t *cov32, *hard32;          // [n_samples][n_strips]
+    const uint32_t *hoff;                    // [n_samples * n_strips + 1] exclusive scan of popc(hard32); last = number of hard cells
+    uint64_t *acc_cov;                       // [span] coverage bits of the hard cells      (zeroed before k_hard_cells)
+    uint32_t *acc_cnt4;                      // [span] derived-base counts of the hard cells (zeroed)
+    uint64_t *site_type;                     // [span] derived-allele bits                   (zeroed; the hard cells are the only writers)
+    uint8_t *site_flag;
+};
+
+#define PB_HARD_THREADS 128
+#define PB_HARD_SLICE 2048         // mask-word offsets a CTA keeps in shared memory
+static inline size_t pb_hard_smem(int nl) {
+    return (size_t)2 * nl * PB_HARD_THREADS * 4 + 256 * 8 + 64 + (size_t)nl * 256 + 64 + (PB_HARD_SLICE + 1) * 4;
+}
+
+// The cells the bit-sliced pass could not settle, one per THREAD: cell g of the scanned hard masks is
+// (sample, position); the thread walks that sample's segment records covering the position in file
+// order -- exactly the bases call_base sees -- into a private shared-memory histogram and calls the
+// cell with the exact machinery of pb_cell.cuh / pb_walk.cuh.  What the site needs from the cell
+// (pb_site_sample: coverage bit, derived-allele bit, derived-base counts) goes into per-position
+// accumulators with integer atomics, so the result does not depend on the order of the cells.
+__global__ void __launch_bounds__(PB_HARD_THREADS) k_hard_cells(const PbHardArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nl = a.ctr->n_levels;
+    const int n_lw = 2 * nl;
+    const int tid = threadIdx.x;
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                             // [n_lw][PB_HARD_THREADS]
+    double *fk_s = reinterpret_cast<double *>(smem_raw + (size_t)n_lw * PB_HARD_THREADS * 4);
+    uint8_t *qval_s = reinterpret_cast<uint8_t *>(fk_s + 256);                           // [64]
+    uint8_t *need_s = qval_s + 64;                                                       // [nl][256]
+    for (int i = tid; i < 256; i += PB_HARD_THREADS) fk_s[i] = a.fk[i];
+    if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
+    for (int i = tid; i < nl * 64; i += PB_HARD_THREADS) reinterpret_cast<uint32_t *>(need_s)[i] = reinterpret_cast<const uint32_t *>(a.need)[i];
+    uint32_t *hoff_s = reinterpret_cast<uint32_t *>(need_s + (size_t)nl * 256 + 64);   // [PB_HARD_SLICE + 1]
+    __shared__ uint32_t s_w[2];
+    uint32_t *const my_hist = hist + tid;
+    for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * PB_HARD_THREADS] = 0;
+    const uint32_t n_words = (uint32_t)a.n_samples * (uint32_t)a.n_strips;
+    const uint32_t total = a.hoff[n_words];
+    // the CTA's contiguous share of the cells and the mask words they live in
+    const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+    const uint32_t g_beg = min(total, blockIdx.x * per), g_end = min(total, g_beg + per);
+    if (tid < 2 && g_beg < g_end) {
+        const uint32_t g = tid ? g_end - 1 : g_beg;
+        uint32_t lo = 0, hi = n_words;                         // last idx with hoff[idx] <= g
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.hoff + mid) > g) hi = mid; else lo = mid + 1; }
+        s_w[tid] = lo - 1;
+    }
+    __syncthreads();
+    if (g_beg >= g_end) return;
+    const uint32_t w_beg = s_w[0], w_cnt = s_w[1] - s_w[0] + 1;
+    const bool sliced = w_cnt <= PB_HARD_SLICE;
+    if (sliced) for (uint32_t i = tid; i <= w_cnt; i += PB_HARD_THREADS) hoff_s[i] = __ldg(a.hoff + w_beg + i);
+    __syncthreads();
+    for (uint32_t g = g_beg + tid; g < g_end; g += PB_HARD_THREADS) {
+        uint32_t idx;
+        if (sliced) {
+            uint32_t lo = 0, hi = w_cnt;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (hoff_s[mid] > g) hi = mid; else lo = mid + 1; }
+            idx = w_beg + lo - 1;
+        } else {
+            uint32_t lo = w_beg, hi = w_beg + w_cnt;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.hoff + mid) > g) hi = mid; else lo = mid + 1; }
+            idx = lo - 1;
+        }
+        const int bit = (int)__fns(__ldg(a.hard32 + idx), 0, (int)(g - __ldg(a.hoff + idx)) + 1);
+        const int smp = (int)(idx / (uint32_t)a.n_strips), strip = (int)(idx % (uint32_t)a.n_strips);
+        const int pos = a.span_beg + strip * 32 + bit;
+        // ---- call_base for (pos, smp): the records that can cover the strip, in file order
+        const uint32_t *Fs = a.F + (size_t)smp * a.NI + strip;
+        const uint32_t j0 = __ldg(Fs), j1 = __ldg(Fs + a.M + 1);
+        uint32_t tot4 = 0;
+        int rmsq = 0;
+        for (uint32_t j = j0; j < j1; j += 4) {               // four records per step: their code loads overlap
+            uint32_t code[4], zz[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                code[q] = PB_CODE_NONE; zz[q] = 0;
+                if (j + q < j1) {
+                    const int4 r = __ldg(&a.srec[j + q]);
+                    const uint32_t z = (uint32_t)r.z;
+                    const uint32_t u = (uint32_t)(pos - r.y);
+                    zz[q] = z;
+                    if (u < (z & 0xffffu)) code[q] = __ldg(a.codes + ((int64_t)(((uint64_t)(z >> 26) << 32) | (uint32_t)r.w) + u));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (code[q] == PB_CODE_NONE) continue;
+                const uint32_t inc = 1u << ((code[q] & 3u) << 3);
+                my_hist[((code[q] >> 2) * 2 + ((zz[q] >> 24) & 1u)) * PB_HARD_THREADS] += inc;
+                tot4 += inc;
+                const int mq = (int)((zz[q] >> 16) & 0xffu);
+                rmsq += mq * mq;
+            }
+        }
+        if (tot4 == 0) continue;                               // cannot happen for a listed cell; nothing to fold anyway
+        const int rc = (pos >= 0 && pos < a.ref_len) ? (int)(unsigned char)a.ref[pos] : 'N';
+        uint64_t cb;
+        if (pb_tot4_unanimous(tot4)) {
+            auto peek = [&](int lw) -> uint32_t { return my_hist[lw * PB_HARD_THREADS]; };
+            const int kk = pb_tot4_k(tot4);
+            const int bb = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
+            cb = pb_unanimous_by_count(peek, nl, need_s, kk, bb) ? pb_unanimous_result(a.lhet, kk, bb, rmsq)
+                                                                  : pb_call_unanimous(peek, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet);
+            for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * PB_HARD_THREADS] = 0;
+        } else {
+            auto take = [&](int lw) -> uint32_t { const uint32_t w = my_hist[lw * PB_HARD_THREADS]; my_hist[lw * PB_HARD_THREADS] = 0; return w; };
+            cb = pb_call_general(take, n_lw, qval_s, tot4, rmsq, fk_s, a.beta, a.lhet);
+        }
+        uint32_t d4 = 0;
+        bool cv, der;
+        (void)pb_site_sample(cb, rc, pb_iupac_rev(rc), a.het_mode, a.min_snpQ, a.min_rmsQ, a.min_depth, a.max_depth, &d4, &cv, &der);
+        const int64_t o = (int64_t)pos - a.span_beg;
+        if (d4) atomicAdd(a.acc_cnt4 + o, d4);
+        if (cv) atomicOr(reinterpret_cast<unsigned long long *>(a.acc_cov + o), 1ULL << smp);
+        if (der) atomicOr(reinterpret_cast<unsigned long long *>(a.site_type + o), 1ULL << smp);
+    }
+}
+
+// popc of the hard masks, to be scanned into cell offsets
+__global__ void __launch_bounds__(256) k_hard_count(const uint32_t *__restrict__ hard32, uint32_t n_words, uint32_t *__restrict__ hoff) {
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i < n_words) hoff[i] = (uint32_t)__popc(hard32[i]);
+    else if (i == n_words) hoff[i] = 0;
+}
+
+// The sites (make_X tail, pop_nucdiv.cpp:168-199): coverage by every sample, segbase's value, window membership.
+__global__ void __launch_bounds__(256) k_fast_sites(const PbHardArgs a) {
+    const int64_t o = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int p = a.span_beg + (int)o;
+    if (p >= a.span_end) return;
+    const int strip = (int)(o >> 5), bit = (int)(o & 31);
+    uint64_t cov = a.acc_cov[o];
+    for (int s = 0; s < a.n_samples; ++s) cov |= (uint64_t)((__ldg(a.cov32 + (size_t)s * a.n_strips + strip) >> bit) & 1u) << s;
+    const int fq = pb_site_fq(a.acc_cnt4[o]);
+    int lo = 0, hi = a.n_windows;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(a.win_end + mid) > p) hi = mid; else lo = mid + 1; }
+    const bool in_win = lo < a.n_windows && __ldg(a.win_beg + lo) <= p;
+    const bool used = in_win && __popcll(cov) == a.n_samples;
+    a.site_flag[o] = (uint8_t)((used ? 1 : 0) | ((used && fq > 0) ? 2 : 0));
+}

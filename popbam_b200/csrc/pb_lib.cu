@@ -13,6 +13,7 @@
 
 #include "../../include/popbam_b200.h"
 #include "pb_kernels.cuh"
+#include "pb_fast.cuh"
 #include "pb_stats.cuh"
 #include "pb_ld.cuh"
 
@@ -42,6 +43,7 @@ struct pb_ctx {
     size_t smem_optin = 0;
     // tables / contig
     DevBuf d_fk, d_beta, d_lhet, d_ref, d_rms_thr;
+    DevBuf d_refpl;        // reference bit-planes of the contig (k_ref_planes): R0 | R1 | RV
     int64_t ref_len = 0;
     int32_t ref_tid = -1;
     // region
@@ -57,6 +59,8 @@ struct pb_ctx {
     // derived
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
+    DevBuf d_planes, d_fastp, d_cov32, d_hoff, d_acc, d_sidx;     // bit-sliced path: code planes P|B0|B1|H, PbFastParams, cov32|hard32
+    bool classic = false;                  // POPBAM_B200_PILEUP=classic: always k_pileup_call (A/B measurements)
     DevBuf d_seg_type;     // arena of the segregating-site arrays (seg_layout)
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wall_u, d_stats, d_ld_kt, d_ld_km, d_ld_inv, d_ld_cnt;
     // pinned results
@@ -271,7 +275,9 @@ int run_pipeline(pb_ctx *c) {
     if (!c->need_valid || c->need_nl != nl || memcmp(c->need_qval, c->ctr_host.qval, 64) != 0) {
         PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
         k_need_table<<<std::max(nl, 1), 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
-        c->launches += 1;
+        PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastParams)));
+        k_fast_params<<<1, 32, 0, st>>>(ctr, dp<uint8_t>(c->d_need), dp<PbFastParams>(c->d_fastp));
+        c->launches += 2;
         PB_CUDA(c, cudaGetLastError());
         c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, c->ctr_host.qval, 64);
     }
@@ -300,8 +306,62 @@ int run_pipeline(pb_ctx *c) {
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
     PB_CUDA(c, cudaEventRecord(c->ev[2], st));
-    kern<<<nblk(span, tp), tp, smem, st>>>(pa);
-    c->launches += 1;
+    // Bit-sliced path (pb_fast.cuh) when the depth cap cannot bind, nobody wants the per-cell words, and an
+    // empty cell is simply "not covered" (min_depth, min_snpQ > 0); k_pileup_call otherwise.
+    const int fast_w = pb_fast_words(c->ctr_host.max_span);
+    const bool fast = !cap && !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && N > 0 &&
+                      pb_hard_smem(nl) <= c->smem_optin && span * n < (int64_t)0x7fffffff && fast_w <= PB_PLANE_PAD &&
+                      pb_fast_smem(fast_w) <= 100 * 1024;
+    if (fast) {
+        const int n_strips = (int)((span + 31) >> 5);
+        const size_t plw = (size_t)((c->n_bytes + 31) >> 5) + 1 + PB_PLANE_PAD;
+        PB_TRY(dev_reserve(c, c->d_planes, sizeof(uint4) * plw));
+        PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * 2 * (size_t)n * n_strips));
+        uint4 *pl = dp<uint4>(c->d_planes);
+        const size_t rpw = (size_t)((c->ref_len + 31) >> 5) + 2;
+        const uint32_t *rp = dp<uint32_t>(c->d_refpl);
+        k_bitplanes<<<c->n_sms * 8, 256, 0, st>>>(pa.codes, c->n_bytes, dp<PbFastParams>(c->d_fastp), pl);
+        PbFastArgs fa;
+        const int fM = (c->ctr_host.max_span + 31) >> 5, fNI = n_strips + fM + 2;
+        PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
+        k_strip_index<<<c->n_sms * 8, 256, 0, st>>>(pa.srec, pa.sstart, n, c->span_beg, fM, fNI, dp<uint32_t>(c->d_sidx));
+        fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.M = fM; fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
+        fa.planes = pl;
+        fa.r0 = rp; fa.r1 = rp + rpw; fa.rv = rp + 2 * rpw;
+        fa.ref_len = c->ref_len; fa.span_beg = c->span_beg; fa.span_end = c->span_end;
+        fa.n_samples = n; fa.n_strips = n_strips; fa.n_sblocks = (n_strips + PB_FAST_STRIPS - 1) / PB_FAST_STRIPS;
+        fa.W = fast_w;
+        fa.min_depth = P.min_depth; fa.min_rmsQ = P.min_rmsQ;
+        fa.ctr = ctr; fa.fp = dp<PbFastParams>(c->d_fastp);
+        fa.cov32 = dp<uint32_t>(c->d_cov32); fa.hard32 = fa.cov32 + (size_t)n * n_strips;
+        PB_CUDA(c, cudaFuncSetAttribute(k_pile_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_fast_smem(fast_w)));
+        k_pile_fast<<<(unsigned)n * (unsigned)fa.n_sblocks, PB_FAST_STRIPS * PB_FAST_G, pb_fast_smem(fast_w), st>>>(fa);
+        PbHardArgs ha;
+        ha.srec = pa.srec; ha.F = fa.F; ha.M = fM; ha.NI = fNI; ha.codes = pa.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
+        ha.span_beg = pa.span_beg; ha.span_end = pa.span_end; ha.win_beg = pa.win_beg; ha.win_end = pa.win_end; ha.n_windows = NW;
+        ha.n_samples = n; ha.n_strips = n_strips;
+        ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
+        ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need = pa.need;
+        ha.cov32 = fa.cov32; ha.hard32 = fa.hard32;
+        const uint32_t n_words = (uint32_t)n * (uint32_t)n_strips;
+        PB_TRY(dev_reserve(c, c->d_hoff, sizeof(uint32_t) * ((size_t)n_words + 1)));
+        PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
+        ha.hoff = dp<uint32_t>(c->d_hoff);
+        ha.acc_cov = dp<uint64_t>(c->d_acc); ha.acc_cnt4 = reinterpret_cast<uint32_t *>(ha.acc_cov + span);
+        ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
+        PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, st));
+        PB_CUDA(c, cudaMemsetAsync(pa.site_type, 0, sizeof(uint64_t) * (size_t)span, st));
+        k_hard_count<<<nblk((int64_t)n_words + 1, 256), 256, 0, st>>>(fa.hard32, n_words, dp<uint32_t>(c->d_hoff));
+        PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_hoff), (int64_t)n_words + 1));
+        const size_t hsm = pb_hard_smem(nl);
+        PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+        k_hard_cells<<<c->n_sms * 8, PB_HARD_THREADS, hsm, st>>>(ha);
+        k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
+        c->launches += 6;
+    } else {
+        kern<<<nblk(span, tp), tp, smem, st>>>(pa);
+        c->launches += 1;
+    }
     PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaEventRecord(c->ev[3], st));
 
@@ -510,6 +570,7 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     c->prm = *p;
     c->n_sms = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    { const char *e = getenv("POPBAM_B200_PILEUP"); c->classic = e && strcmp(e, "classic") == 0; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
     for (auto &ev : c->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
@@ -557,6 +618,13 @@ int pb_set_contig(pb_ctx *c, int32_t tid, const char *ref_bases, int64_t len) {
     PB_CUDA(c, cudaSetDevice(c->prm.device));
     PB_TRY(dev_reserve(c, c->d_ref, (size_t)std::max<int64_t>(len, 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_ref.p, ref_bases, (size_t)len, cudaMemcpyHostToDevice, c->stream));
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const size_t pw = (size_t)((len + 31) >> 5) + 2;
+    PB_TRY(dev_reserve(c, c->d_refpl, sizeof(uint32_t) * 3 * pw));
+    uint32_t *rp = dp<uint32_t>(c->d_refpl);
+    k_ref_planes<<<c->n_sms * 4, 256, 0, c->stream>>>(dp<char>(c->d_ref), len, rp, rp + pw, rp + 2 * pw);
+    c->launches += 1;
+    PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->ref_len = len; c->ref_tid = tid;
     return PB_OK;
