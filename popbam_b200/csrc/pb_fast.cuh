@@ -127,8 +127,9 @@ __device__ __forceinline__ uint32_t pb_bs_le6(const uint32_t c[6], int C) {
     uint32_t lt = 0, eq = 0xffffffffu;
 #pragma unroll
     for (int b = 5; b >= 0; --b) {
-        if ((C >> b) & 1) { lt |= eq & ~c[b]; eq &= c[b]; }
-        else eq &= ~c[b];
+        const uint32_t cb = 0u - (uint32_t)((C >> b) & 1);       // all ones when bit b of C is set (branch-free: C is a run-time value)
+        lt |= eq & ~c[b] & cb;
+        eq &= ~(c[b] ^ cb);
     }
     return lt | eq;
 }
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
     int4 *recS = reinterpret_cast<int4 *>(smem_raw);                      // [RC] {seg start, z, bit offset in staged words, read start}
     uint4 *plS = reinterpret_cast<uint4 *>(recS + a.RC);                  // [RC][W]
     const int tid = threadIdx.x;
-    const int s = (int)(blockIdx.x / a.n_sblocks), sb = (int)(blockIdx.x % a.n_sblocks);
+    const int sb = (int)(blockIdx.x / a.n_samples), s = (int)(blockIdx.x % a.n_samples);     // the samples of a strip block run together: one pass through L2
     const int strip = sb * PB_FAST_STRIPS + tid / PB_FAST_G, g = tid % PB_FAST_G;
     const int W = a.W;
     const uint32_t *Fs = a.F + (size_t)s * a.NI;
@@ -304,8 +305,9 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
         const int C = fp.hmin - 1;
 #pragma unroll
         for (int b = 3; b >= 0; --b) {
-            if ((C >> b) & 1) { lt |= eq & ~ch[b]; eq &= ch[b]; }
-            else eq &= ~ch[b];
+            const uint32_t cb = 0u - (uint32_t)((C >> b) & 1);
+            lt |= eq & ~ch[b] & cb;
+            eq &= ~(ch[b] ^ cb);
         }
         const uint32_t hge = ~(lt | eq) | hover;
         count_ok |= hge & pb_bs_le6(ck, fp.k1hi) & ~pb_bs_le6(ck, fp.k1lo - 1);
@@ -335,84 +337,86 @@ struct PbHardArgs {
     const PbCounters *ctr;
     const uint8_t *need;
     const uint32_t *cov32, *hard32;          // [n_samples][n_strips]
-    const uint32_t *hoff;                    // [n_samples * n_strips + 1] exclusive scan of popc(hard32); last = number of hard cells
     uint64_t *acc_cov;                       // [span] coverage bits of the hard cells      (zeroed before k_hard_cells)
     uint32_t *acc_cnt4;                      // [span] derived-base counts of the hard cells (zeroed)
     uint64_t *site_type;                     // [span] derived-allele bits                   (zeroed; the hard cells are the only writers)
     uint8_t *site_flag;
 };
 
-#define PB_HARD_THREADS 128
-#define PB_HARD_SLICE 2048         // mask-word offsets a CTA keeps in shared memory
+#define PB_HARD_STRIPS 64          // strips per CTA of k_hard_cells
+#define PB_HARD_THREADS 160        // one pass handles the ~6 % unsettled cells of 64 strips at typical error rates
+#define PB_HARD_RC 1024            // segment records a CTA stages
 static inline size_t pb_hard_smem(int nl) {
-    return (size_t)2 * nl * PB_HARD_THREADS * 4 + 256 * 8 + 64 + (size_t)nl * 256 + 64 + (PB_HARD_SLICE + 1) * 4;
+    return (size_t)PB_HARD_RC * 16 + (size_t)2 * nl * PB_HARD_THREADS * 4 + 256 * 8 + 64 + (size_t)nl * 256 + 64;
 }
 
-// The cells the bit-sliced pass could not settle, one per THREAD: cell g of the scanned hard masks is
-// (sample, position); the thread walks that sample's segment records covering the position in file
-// order -- exactly the bases call_base sees -- into a private shared-memory histogram and calls the
-// cell with the exact machinery of pb_cell.cuh / pb_walk.cuh.  What the site needs from the cell
-// (pb_site_sample: coverage bit, derived-allele bit, derived-base counts) goes into per-position
-// accumulators with integer atomics, so the result does not depend on the order of the cells.
+// The cells the bit-sliced pass could not settle, one per THREAD.  One CTA = one sample x the same 64
+// strips as a k_pile_fast CTA: it reads their hard masks, stages the sample's segment records that can
+// cover them (strip index, no search), and every thread takes one listed cell: it walks the staged
+// records of its strip in file order -- exactly the bases call_base sees -- into a private
+// shared-memory histogram and calls the cell with the exact machinery of pb_cell.cuh / pb_walk.cuh.
+// What the site needs from the cell (pb_site_sample: coverage bit, derived-allele bit, derived-base
+// counts) goes into per-position accumulators with integer atomics, so the result does not depend on
+// the order of the cells.  Consecutive CTAs are the samples of one strip block, so the code bytes of a
+// region are pulled through L2 once.
 __global__ void __launch_bounds__(PB_HARD_THREADS) k_hard_cells(const PbHardArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t hm_s[PB_HARD_STRIPS], pre_s[PB_HARD_STRIPS + 1], F_s[PB_HARD_STRIPS + 40];
     const int nl = a.ctr->n_levels;
     const int n_lw = 2 * nl;
     const int tid = threadIdx.x;
-    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                             // [n_lw][PB_HARD_THREADS]
-    double *fk_s = reinterpret_cast<double *>(smem_raw + (size_t)n_lw * PB_HARD_THREADS * 4);
+    int4 *recS = reinterpret_cast<int4 *>(smem_raw);                                     // [PB_HARD_RC]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(recS + PB_HARD_RC);                     // [n_lw][PB_HARD_THREADS]
+    double *fk_s = reinterpret_cast<double *>(hist + (size_t)n_lw * PB_HARD_THREADS);
     uint8_t *qval_s = reinterpret_cast<uint8_t *>(fk_s + 256);                           // [64]
     uint8_t *need_s = qval_s + 64;                                                       // [nl][256]
+    const int sb = (int)(blockIdx.x / a.n_samples), smp = (int)(blockIdx.x % a.n_samples);
+    const int t0 = sb * PB_HARD_STRIPS, nst = min(PB_HARD_STRIPS, a.n_strips - t0);
+    // the block's hard masks and the exclusive prefix of their sizes (PB_HARD_STRIPS == 64: two strips per lane)
+    if (tid < 32) {
+        const uint32_t m0 = 2 * tid < nst ? __ldg(a.hard32 + (size_t)smp * a.n_strips + t0 + 2 * tid) : 0u;
+        const uint32_t m1 = 2 * tid + 1 < nst ? __ldg(a.hard32 + (size_t)smp * a.n_strips + t0 + 2 * tid + 1) : 0u;
+        const uint32_t c0 = (uint32_t)__popc(m0), c1 = (uint32_t)__popc(m1);
+        uint32_t x = c0 + c1;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= o) x += y; }
+        hm_s[2 * tid] = m0; hm_s[2 * tid + 1] = m1;
+        pre_s[2 * tid] = x - c0 - c1; pre_s[2 * tid + 1] = x - c1;
+        if (tid == 31) pre_s[PB_HARD_STRIPS] = x;
+    }
+    __syncthreads();
+    const uint32_t total = pre_s[PB_HARD_STRIPS];
+    if (total == 0) return;
     for (int i = tid; i < 256; i += PB_HARD_THREADS) fk_s[i] = a.fk[i];
     if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
     for (int i = tid; i < nl * 64; i += PB_HARD_THREADS) reinterpret_cast<uint32_t *>(need_s)[i] = reinterpret_cast<const uint32_t *>(a.need)[i];
-    uint32_t *hoff_s = reinterpret_cast<uint32_t *>(need_s + (size_t)nl * 256 + 64);   // [PB_HARD_SLICE + 1]
-    __shared__ uint32_t s_w[2];
     uint32_t *const my_hist = hist + tid;
     for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * PB_HARD_THREADS] = 0;
-    const uint32_t n_words = (uint32_t)a.n_samples * (uint32_t)a.n_strips;
-    const uint32_t total = a.hoff[n_words];
-    // the CTA's contiguous share of the cells and the mask words they live in
-    const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
-    const uint32_t g_beg = min(total, blockIdx.x * per), g_end = min(total, g_beg + per);
-    if (tid < 2 && g_beg < g_end) {
-        const uint32_t g = tid ? g_end - 1 : g_beg;
-        uint32_t lo = 0, hi = n_words;                         // last idx with hoff[idx] <= g
-        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.hoff + mid) > g) hi = mid; else lo = mid + 1; }
-        s_w[tid] = lo - 1;
-    }
+    // strip index slice: records that can cover strip t0 + i are [F_s[i], F_s[i + M + 1])
+    const uint32_t *Fs = a.F + (size_t)smp * a.NI + t0;
+    const int nf = nst + a.M + 1;                                                        // <= NI - t0
+    const bool f_sliced = nf <= PB_HARD_STRIPS + 40;
+    if (f_sliced) for (int i = tid; i < nf; i += PB_HARD_THREADS) F_s[i] = __ldg(Fs + i);
+    const uint32_t clo = __ldg(Fs), chi = __ldg(Fs + nst + a.M);
+    const bool staged = chi - clo <= PB_HARD_RC;
+    if (staged) for (uint32_t r = tid; r < chi - clo; r += PB_HARD_THREADS) recS[r] = __ldg(a.srec + clo + r);
     __syncthreads();
-    if (g_beg >= g_end) return;
-    const uint32_t w_beg = s_w[0], w_cnt = s_w[1] - s_w[0] + 1;
-    const bool sliced = w_cnt <= PB_HARD_SLICE;
-    if (sliced) for (uint32_t i = tid; i <= w_cnt; i += PB_HARD_THREADS) hoff_s[i] = __ldg(a.hoff + w_beg + i);
-    __syncthreads();
-    for (uint32_t g = g_beg + tid; g < g_end; g += PB_HARD_THREADS) {
-        uint32_t idx;
-        if (sliced) {
-            uint32_t lo = 0, hi = w_cnt;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (hoff_s[mid] > g) hi = mid; else lo = mid + 1; }
-            idx = w_beg + lo - 1;
-        } else {
-            uint32_t lo = w_beg, hi = w_beg + w_cnt;
-            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.hoff + mid) > g) hi = mid; else lo = mid + 1; }
-            idx = lo - 1;
-        }
-        const int bit = (int)__fns(__ldg(a.hard32 + idx), 0, (int)(g - __ldg(a.hoff + idx)) + 1);
-        const int smp = (int)(idx / (uint32_t)a.n_strips), strip = (int)(idx % (uint32_t)a.n_strips);
-        const int pos = a.span_beg + strip * 32 + bit;
+    for (uint32_t c = tid; c < total; c += PB_HARD_THREADS) {
+        int lo = 0, hi = PB_HARD_STRIPS;                       // the strip of cell c: last i with pre_s[i] <= c
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pre_s[mid] > c) hi = mid; else lo = mid + 1; }
+        const int si = lo - 1;
+        const int bit = (int)__fns(hm_s[si], 0, (int)(c - pre_s[si]) + 1);
+        const int pos = a.span_beg + (t0 + si) * 32 + bit;
         // ---- call_base for (pos, smp): the records that can cover the strip, in file order
-        const uint32_t *Fs = a.F + (size_t)smp * a.NI + strip;
-        const uint32_t j0 = __ldg(Fs), j1 = __ldg(Fs + a.M + 1);
+        const uint32_t j0 = f_sliced ? F_s[si] : __ldg(Fs + si), j1 = f_sliced ? F_s[si + a.M + 1] : __ldg(Fs + si + a.M + 1);
         uint32_t tot4 = 0;
         int rmsq = 0;
-        for (uint32_t j = j0; j < j1; j += 4) {               // four records per step: their code loads overlap
-            uint32_t code[4], zz[4];
+        for (uint32_t j = j0; j < j1; j += 8) {               // eight records per step: their code loads (DRAM latency) overlap
+            uint32_t code[8], zz[8];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 code[q] = PB_CODE_NONE; zz[q] = 0;
                 if (j + q < j1) {
-                    const int4 r = __ldg(&a.srec[j + q]);
+                    const int4 r = staged ? recS[j + q - clo] : __ldg(&a.srec[j + q]);
                     const uint32_t z = (uint32_t)r.z;
                     const uint32_t u = (uint32_t)(pos - r.y);
                     zz[q] = z;
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(PB_HARD_THREADS) k_hard_cells(const PbHardArgs
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 if (code[q] == PB_CODE_NONE) continue;
                 const uint32_t inc = 1u << ((code[q] & 3u) << 3);
                 my_hist[((code[q] >> 2) * 2 + ((zz[q] >> 24) & 1u)) * PB_HARD_THREADS] += inc;
@@ -451,13 +455,6 @@ __global__ void __launch_bounds__(PB_HARD_THREADS) k_hard_cells(const PbHardArgs
         if (cv) atomicOr(reinterpret_cast<unsigned long long *>(a.acc_cov + o), 1ULL << smp);
         if (der) atomicOr(reinterpret_cast<unsigned long long *>(a.site_type + o), 1ULL << smp);
     }
-}
-
-// popc of the hard masks, to be scanned into cell offsets
-__global__ void __launch_bounds__(256) k_hard_count(const uint32_t *__restrict__ hard32, uint32_t n_words, uint32_t *__restrict__ hoff) {
-    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i < n_words) hoff[i] = (uint32_t)__popc(hard32[i]);
-    else if (i == n_words) hoff[i] = 0;
 }
 
 // The sites (make_X tail, pop_nucdiv.cpp:168-199): coverage by every sample, segbase's value, window membership.

@@ -335,30 +335,28 @@ __global__ void __launch_bounds__(256) k_encode(int64_t n, const uint32_t *__res
 // Stable partition of the kept reads by sample, expanding every read into its aligned segments.
 // One warp owns PB_PART_CHUNK consecutive reads, so the order inside a (chunk, sample) bucket is file
 // order; buckets are laid out sample-major, chunk-minor by an exclusive scan of the count matrix.
-__global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg,
+__global__ void __launch_bounds__(128) k_part_count(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg,
                              const uint32_t *__restrict__ meta, int min_mapQ, const PbCounters *__restrict__ ctr, int n_samples,
                              int64_t n_chunks, uint32_t *__restrict__ counts /* [n_samples][n_chunks] */) {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t cnt_s[4][PB_MAX_SAMPLES];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool drop_dead = ctr->nocap != 0;
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk >= n_chunks) return;
-    uint32_t c0 = 0, c1 = 0;   // lane owns samples lane and lane+32
+    uint32_t *cnt = cnt_s[wid];                     // segments per sample in this warp's chunk
+    cnt[lane] = 0; cnt[lane + 32] = 0;
+    __syncwarp();
     const int64_t r0 = chunk * PB_PART_CHUNK;
     for (int i = 0; i < PB_PART_CHUNK; i += 32) {
         const int64_t r = r0 + i + lane;
         uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
         const uint32_t ns = r < n ? rnseg[r] : 0;
         if (drop_dead && key != PB_KEY_DROP && (int)((meta[r] >> 8) & 0xffu) < min_mapQ) key = PB_KEY_DROP;
-        // every lane sums the segment counts of the reads of its own two samples
-        for (int src = 0; src < 32; ++src) {
-            const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
-            const uint32_t nn = __shfl_sync(0xffffffffu, ns, src);
-            c0 += kk == (uint32_t)lane ? nn : 0;
-            c1 += kk == (uint32_t)(lane + 32) ? nn : 0;
-        }
+        if (key != PB_KEY_DROP && ns) atomicAdd(&cnt[key], ns);
     }
-    if (lane < n_samples) counts[(int64_t)lane * n_chunks + chunk] = c0;
-    if (lane + 32 < n_samples) counts[(int64_t)(lane + 32) * n_chunks + chunk] = c1;
+    __syncwarp();
+    if (lane < n_samples) counts[(int64_t)lane * n_chunks + chunk] = cnt[lane];
+    if (lane + 32 < n_samples) counts[(int64_t)(lane + 32) * n_chunks + chunk] = cnt[lane + 32];
 }
 
 // Segment record (16 bytes):
@@ -366,37 +364,40 @@ __global__ void k_part_count(int64_t n, const uint8_t *__restrict__ rkey, const 
 //   y  segment start (reference coordinate)
 //   z  segment length (16 bits) | mapq<<16 | strand<<24 | dead<<25 | (offset bits 32..37)<<26
 //   w  low 32 bits of the byte offset of the segment's first base in qual[] / codes[]
-__global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg, int n_samples,
+__global__ void __launch_bounds__(128) k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, const uint8_t *__restrict__ rnseg, int n_samples,
                                int64_t n_chunks, const uint32_t *__restrict__ offs /* scanned counts */,
                                const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta, const uint64_t *__restrict__ base,
                                const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
                                const uint32_t *__restrict__ cigar, int min_mapQ, const PbCounters *__restrict__ ctr,
                                int4 *__restrict__ srec) {
-    const int lane = threadIdx.x & 31;
+    __shared__ uint32_t cur_s[4][PB_MAX_SAMPLES];   // per warp: next free record slot of every sample
+    __shared__ uint32_t ns_s[4][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const bool drop_dead = ctr->nocap != 0;
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk >= n_chunks) return;
-    uint32_t cur0 = lane < n_samples ? offs[(int64_t)lane * n_chunks + chunk] : 0;
-    uint32_t cur1 = lane + 32 < n_samples ? offs[(int64_t)(lane + 32) * n_chunks + chunk] : 0;
+    uint32_t *cur = cur_s[wid], *nsw = ns_s[wid];
+    cur[lane] = lane < n_samples ? offs[(int64_t)lane * n_chunks + chunk] : 0;
+    cur[lane + 32] = lane + 32 < n_samples ? offs[(int64_t)(lane + 32) * n_chunks + chunk] : 0;
     const int64_t r0 = chunk * PB_PART_CHUNK;
     for (int i = 0; i < PB_PART_CHUNK; i += 32) {
         const int64_t r = r0 + i + lane;
         uint32_t key = r < n ? rkey[r] : PB_KEY_DROP;
-        const uint32_t ns = r < n ? rnseg[r] : 0;
+        uint32_t ns = r < n ? rnseg[r] : 0;
         if (drop_dead && key != PB_KEY_DROP && (int)((meta[r] >> 8) & 0xffu) < min_mapQ) key = PB_KEY_DROP;
-        // my rank: segments of earlier lanes with my key; cursor advance: segments per sample in this step
-        uint32_t rank = 0, a0 = 0, a1 = 0;
-        for (int src = 0; src < 32; ++src) {
-            const uint32_t kk = __shfl_sync(0xffffffffu, key, src);
-            const uint32_t nn = __shfl_sync(0xffffffffu, ns, src);
-            rank += (kk == key && src < lane) ? nn : 0;
-            a0 += kk == (uint32_t)lane ? nn : 0;
-            a1 += kk == (uint32_t)(lane + 32) ? nn : 0;
-        }
-        const uint32_t c0 = __shfl_sync(0xffffffffu, cur0, key & 31);
-        const uint32_t c1 = __shfl_sync(0xffffffffu, cur1, key & 31);
+        if (key == PB_KEY_DROP) ns = 0;
+        // my rank: segments of the earlier lanes with my key (file order inside a sample is kept)
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        nsw[lane] = ns;
+        __syncwarp();
+        uint32_t rank = 0;
+        for (uint32_t m = peers & ((1u << lane) - 1u); m; m &= m - 1) rank += nsw[__ffs(m) - 1];
+        const uint32_t mine = key != PB_KEY_DROP ? cur[key] : 0u;
+        __syncwarp();
+        if (key != PB_KEY_DROP && (peers >> lane) == 1u) cur[key] = mine + rank + ns;     // the group's last lane advances the cursor
+        __syncwarp();
         if (key != PB_KEY_DROP && ns) {
-            uint32_t dst = (key < 32 ? c0 : c1) + rank;
+            uint32_t dst = mine + rank;
             const uint32_t m = meta[r];
             const int p = pos[r];
             const uint32_t mapq = (m >> 8) & 0xffu;
@@ -424,7 +425,6 @@ __global__ void k_part_scatter(int64_t n, const uint8_t *__restrict__ rkey, cons
                 else if (op == 1 || op == 4) y += len;
             }
         }
-        cur0 += a0; cur1 += a1;
     }
 }
 

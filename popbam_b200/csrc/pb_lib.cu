@@ -59,7 +59,7 @@ struct pb_ctx {
     // derived
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
-    DevBuf d_planes, d_fastp, d_cov32, d_hoff, d_acc, d_sidx;     // bit-sliced path: code planes P|B0|B1|H, PbFastParams, cov32|hard32
+    DevBuf d_planes, d_fastp, d_cov32, d_acc, d_sidx;     // bit-sliced path: code planes P|B0|B1|H, PbFastParams, cov32|hard32
     bool classic = false;                  // POPBAM_B200_PILEUP=classic: always k_pileup_call (A/B measurements)
     DevBuf d_seg_type;     // arena of the segregating-site arrays (seg_layout)
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wall_u, d_stats, d_ld_kt, d_ld_km, d_ld_inv, d_ld_cnt;
@@ -210,7 +210,7 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaMemsetAsync(c->d_ctr.p, 0, sizeof(PbCounters), st));
     PB_TRY(dev_reserve(c, c->d_rkey, (size_t)std::max<int64_t>(N, 1)));
     PB_TRY(dev_reserve(c, c->d_rnseg, (size_t)std::max<int64_t>(N, 1)));
-    PB_TRY(dev_reserve(c, c->d_codes, (size_t)std::max<int64_t>(c->n_bytes, 1)));
+    PB_TRY(dev_reserve(c, c->d_codes, (size_t)c->n_bytes + 32));     // k_hard_cells copies aligned 16-byte pieces
     PB_TRY(dev_reserve(c, c->d_srec, sizeof(int4) * (size_t)std::max<int64_t>(c->n_cig, 1)));   // one record per M/=/X op at most
     PB_TRY(dev_reserve(c, c->d_sstart, sizeof(uint32_t) * (PB_MAX_SAMPLES + 1)));
     const int64_t n_chunks = std::max<int64_t>(1, (N + PB_PART_CHUNK - 1) / PB_PART_CHUNK);
@@ -343,21 +343,16 @@ int run_pipeline(pb_ctx *c) {
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
         ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need = pa.need;
         ha.cov32 = fa.cov32; ha.hard32 = fa.hard32;
-        const uint32_t n_words = (uint32_t)n * (uint32_t)n_strips;
-        PB_TRY(dev_reserve(c, c->d_hoff, sizeof(uint32_t) * ((size_t)n_words + 1)));
         PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
-        ha.hoff = dp<uint32_t>(c->d_hoff);
         ha.acc_cov = dp<uint64_t>(c->d_acc); ha.acc_cnt4 = reinterpret_cast<uint32_t *>(ha.acc_cov + span);
         ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
         PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, st));
         PB_CUDA(c, cudaMemsetAsync(pa.site_type, 0, sizeof(uint64_t) * (size_t)span, st));
-        k_hard_count<<<nblk((int64_t)n_words + 1, 256), 256, 0, st>>>(fa.hard32, n_words, dp<uint32_t>(c->d_hoff));
-        PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_hoff), (int64_t)n_words + 1));
         const size_t hsm = pb_hard_smem(nl);
         PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-        k_hard_cells<<<c->n_sms * 8, PB_HARD_THREADS, hsm, st>>>(ha);
+        k_hard_cells<<<(unsigned)n * (unsigned)((n_strips + PB_HARD_STRIPS - 1) / PB_HARD_STRIPS), PB_HARD_THREADS, hsm, st>>>(ha);
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
-        c->launches += 6;
+        c->launches += 5;
     } else {
         kern<<<nblk(span, tp), tp, smem, st>>>(pa);
         c->launches += 1;

@@ -43,9 +43,11 @@ PB_HD void pb_walk_hist(Hist &take, int n_lw, const uint8_t *qval, int k, int r4
             wadd |= (uint32_t)m << (8 * J);                                          \
         }
         PB_WALK_SLOT(0, acc0, cc0)
-        PB_WALK_SLOT(1, acc1, cc1)
-        PB_WALK_SLOT(2, acc2, cc2)
-        PB_WALK_SLOT(3, acc3, cc3)
+        if (word & ~(0xffu << (8 * (r4 & 3)))) {      // most words only hold the cell's dominant base (slot 0)
+            PB_WALK_SLOT(1, acc1, cc1)
+            PB_WALK_SLOT(2, acc2, cc2)
+            PB_WALK_SLOT(3, acc3, cc3)
+        }
 #undef PB_WALK_SLOT
         // per-byte add cannot carry: each (strand, base) count is <= 255 in total
         if (st) wr += wadd; else wf += wadd;
