@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
                                                    const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
                                                    const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ,
                                                    uint8_t *__restrict__ rkey, uint8_t *__restrict__ rnseg,
-                                                   int bin_origin, int n_bins, uint32_t *__restrict__ bins,
+                                                   int bin_origin, int n_bins, int span_end, uint32_t *__restrict__ bins,
                                                    PbCounters *__restrict__ ctr) {
     unsigned long long used = 0, aligned = 0, mqmask = 0;
     int span = 0, flags = 0;     // flags: 1 unsorted, 2 too long
@@ -82,7 +82,9 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
         rkey[r] = listed ? (uint8_t)smp : (uint8_t)PB_KEY_DROP;
         if (listed && (longseg || x - p > 65535 || nseg > PB_MAX_SEGS)) flags |= 2;
         rnseg[r] = (uint8_t)(nseg > PB_MAX_SEGS ? PB_MAX_SEGS : nseg);
-        if (listed) {   // read starts per (sample, 128 bp bin) for the depth bound (out-of-range starts clamp: still an upper bound)
+        // read starts per (sample, 128 bp bin) for the depth bound; reads that end before the span or start behind it
+        // cover none of its positions (bins start 65536 bp before the span: early starts clamp, still an upper bound)
+        if (listed && p < span_end && x > bin_origin + 65536) {
             const int b = min(n_bins - 1, max(0, (p - bin_origin) >> PB_BIN_SHIFT));
             atomicAdd(&bins[(size_t)smp * n_bins + b], (uint32_t)(nseg > 0 ? nseg : 1));
         }

@@ -77,6 +77,10 @@ struct pb_ctx {
     std::vector<uint8_t> r_seq4, r_qual;
     // timing of the last pipeline run
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // second stream: the per-read chain (prep, depth bound, sample partition, strip index) runs beside the per-base
+    // chain (quality mask, encode, bit-planes); fk[] = fork / join events (no timing)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t fk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     float ms_prep = 0, ms_pileup = 0, ms_sites = 0, ms_stats = 0;
 };
 
@@ -183,13 +187,13 @@ SegLayout seg_layout(void *base, int64_t S, int n, bool with_cb) {
     return L;
 }
 
-int exclusive_scan_u32(pb_ctx *c, uint32_t *data, int64_t n) {
+int exclusive_scan_u32(pb_ctx *c, uint32_t *data, int64_t n, cudaStream_t st) {
     const int per = PB_SCAN_THREADS * PB_SCAN_ITEMS;
     const int64_t nb = (n + per - 1) / per;
     PB_TRY(dev_reserve(c, c->d_blocktot, sizeof(uint32_t) * (size_t)std::max<int64_t>(nb, 1)));
-    k_scan_blocks<<<(unsigned)nb, PB_SCAN_THREADS, 0, c->stream>>>(data, n, dp<uint32_t>(c->d_blocktot));
-    k_scan_totals<<<1, 1024, 0, c->stream>>>(dp<uint32_t>(c->d_blocktot), nb);
-    k_scan_add<<<(unsigned)nb, PB_SCAN_THREADS, 0, c->stream>>>(data, n, dp<uint32_t>(c->d_blocktot));
+    k_scan_blocks<<<(unsigned)nb, PB_SCAN_THREADS, 0, st>>>(data, n, dp<uint32_t>(c->d_blocktot));
+    k_scan_totals<<<1, 1024, 0, st>>>(dp<uint32_t>(c->d_blocktot), nb);
+    k_scan_add<<<(unsigned)nb, PB_SCAN_THREADS, 0, st>>>(data, n, dp<uint32_t>(c->d_blocktot));
     c->launches += 3;
     PB_CUDA(c, cudaGetLastError());
     return PB_OK;
@@ -223,18 +227,43 @@ int run_pipeline(pb_ctx *c) {
     const int n_bins = (int)((span + 65536) >> PB_BIN_SHIFT) + 2;
     PB_TRY(dev_reserve(c, c->d_bins, sizeof(uint32_t) * (size_t)n * n_bins));
     PB_CUDA(c, cudaMemsetAsync(c->d_bins.p, 0, sizeof(uint32_t) * (size_t)n * n_bins, st));
+    PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
+    cudaStream_t s2 = c->stream2;
+    PB_CUDA(c, cudaEventRecord(c->fk[0], st));
+    PB_CUDA(c, cudaStreamWaitEvent(s2, c->fk[0], 0));
+    // -- per-read chain on the second stream: prep, depth bound, stable partition by sample
     if (N > 0) {
-        k_read_prep<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->n_sms * 8), 256, 0, st>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
+        k_read_prep<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->n_sms * 8), 256, 0, s2>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
                                                  dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), n, P.min_mapQ,
-                                                 dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), bin_origin, n_bins,
+                                                 dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), bin_origin, n_bins, c->span_end,
                                                  dp<uint32_t>(c->d_bins), ctr);
-        k_depth_bound<<<c->n_sms * 4, 256, 0, st>>>(dp<uint32_t>(c->d_bins), n, n_bins, P.max_depth, ctr);
         c->launches += 1;
-        k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
-        c->launches += 2;
     }
+    PB_CUDA(c, cudaEventRecord(c->fk[1], s2));                      // rkey, mapq mask, max_span
+    if (N > 0) {
+        k_depth_bound<<<c->n_sms * 4, 256, 0, s2>>>(dp<uint32_t>(c->d_bins), n, n_bins, P.max_depth, ctr);
+        c->launches += 1;
+    }
+    k_depth_decide<<<1, 1, 0, s2>>>(P.max_depth, ctr);
+    const unsigned part_blocks = nblk(n_chunks * 32, 128);
+    k_part_count<<<part_blocks, 128, 0, s2>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), dp<uint32_t>(c->d_meta), P.min_mapQ, ctr, n, n_chunks,
+                                             dp<uint32_t>(c->d_counts));
+    c->launches += 2;
+    PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts, s2));
+    k_sample_starts<<<1, 128, 0, s2>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart));
+    k_part_scatter<<<part_blocks, 128, 0, s2>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts),
+                                               dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
+                                               dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
+                                               dp<int4>(c->d_srec));
+    c->launches += 2;
+    PB_CUDA(c, cudaEventRecord(c->fk[2], s2));
+    // -- per-base chain on the main stream: quality values present, level table, base codes
+    if (N > 0) {
+        k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
+        c->launches += 1;
+    }
+    PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[1], 0));
     k_level_table<<<1, 32, 0, st>>>(ctr);
-    k_depth_decide<<<1, 1, 0, st>>>(P.max_depth, ctr);
     c->launches += 1;
     if (N > 0) {
         PB_TRY(dev_reserve(c, c->d_qtab, 64 * 256));
@@ -245,18 +274,7 @@ int run_pipeline(pb_ctx *c) {
                                               dp<uint8_t>(c->d_codes));
         c->launches += 2;
     }
-    PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
-    const unsigned part_blocks = nblk(n_chunks * 32, 128);
-    k_part_count<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), dp<uint32_t>(c->d_meta), P.min_mapQ, ctr, n, n_chunks,
-                                             dp<uint32_t>(c->d_counts));
-    c->launches += 2;
-    PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts));
-    k_sample_starts<<<1, 128, 0, st>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart));
-    k_part_scatter<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts),
-                                               dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
-                                               dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
-                                               dp<int4>(c->d_srec));
-    c->launches += 2;
+    PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));                // join
     PB_CUDA(c, cudaGetLastError());
     PB_TRY(host_reserve(c, c->h_ctr, sizeof(PbCounters)));
     PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
@@ -312,19 +330,31 @@ int run_pipeline(pb_ctx *c) {
     const bool fast = !cap && !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && N > 0 &&
                       pb_hard_smem(nl) <= c->smem_optin && span * n < (int64_t)0x7fffffff && fast_w <= PB_PLANE_PAD &&
                       pb_fast_smem(fast_w) <= 100 * 1024;
+    if (getenv("POPBAM_B200_DEBUG"))
+        fprintf(stderr, "[popbam_b200] pileup path: fast=%d cap=%d want_cb=%d min_depth=%d min_snpQ=%d classic=%d N=%lld nl=%d hard_smem=%zu optin=%zu fast_w=%d fast_smem=%zu depth_bound=%d max_span=%d\n",
+                (int)fast, (int)cap, (int)want_cb, P.min_depth, P.min_snpQ, (int)c->classic, (long long)N, nl, pb_hard_smem(nl), c->smem_optin,
+                fast_w, pb_fast_smem(fast_w), c->ctr_host.depth_bound, c->ctr_host.max_span);
     if (fast) {
         const int n_strips = (int)((span + 31) >> 5);
         const size_t plw = (size_t)((c->n_bytes + 31) >> 5) + 1 + PB_PLANE_PAD;
         PB_TRY(dev_reserve(c, c->d_planes, sizeof(uint4) * plw));
         PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * 2 * (size_t)n * n_strips));
+        const int fM = (c->ctr_host.max_span + 31) >> 5, fNI = n_strips + fM + 2;
+        PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
+        PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
+        // the strip index and the zeroing of the accumulators run beside the bit-plane pass
+        PB_CUDA(c, cudaEventRecord(c->fk[3], st));
+        PB_CUDA(c, cudaStreamWaitEvent(c->stream2, c->fk[3], 0));
+        k_strip_index<<<c->n_sms * 8, 256, 0, c->stream2>>>(pa.srec, pa.sstart, n, c->span_beg, fM, fNI, dp<uint32_t>(c->d_sidx));
+        PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, c->stream2));
+        PB_CUDA(c, cudaMemsetAsync(pa.site_type, 0, sizeof(uint64_t) * (size_t)span, c->stream2));
+        PB_CUDA(c, cudaEventRecord(c->fk[4], c->stream2));
         uint4 *pl = dp<uint4>(c->d_planes);
         const size_t rpw = (size_t)((c->ref_len + 31) >> 5) + 2;
         const uint32_t *rp = dp<uint32_t>(c->d_refpl);
         k_bitplanes<<<c->n_sms * 8, 256, 0, st>>>(pa.codes, c->n_bytes, dp<PbFastParams>(c->d_fastp), pl);
+        PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[4], 0));
         PbFastArgs fa;
-        const int fM = (c->ctr_host.max_span + 31) >> 5, fNI = n_strips + fM + 2;
-        PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
-        k_strip_index<<<c->n_sms * 8, 256, 0, st>>>(pa.srec, pa.sstart, n, c->span_beg, fM, fNI, dp<uint32_t>(c->d_sidx));
         fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.M = fM; fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
         fa.planes = pl;
         fa.r0 = rp; fa.r1 = rp + rpw; fa.rv = rp + 2 * rpw;
@@ -343,11 +373,8 @@ int run_pipeline(pb_ctx *c) {
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
         ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need = pa.need;
         ha.cov32 = fa.cov32; ha.hard32 = fa.hard32;
-        PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
         ha.acc_cov = dp<uint64_t>(c->d_acc); ha.acc_cnt4 = reinterpret_cast<uint32_t *>(ha.acc_cov + span);
         ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
-        PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, st));
-        PB_CUDA(c, cudaMemsetAsync(pa.site_type, 0, sizeof(uint64_t) * (size_t)span, st));
         const size_t hsm = pb_hard_smem(nl);
         PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
         k_hard_cells<<<(unsigned)n * (unsigned)((n_strips + PB_HARD_STRIPS - 1) / PB_HARD_STRIPS), PB_HARD_THREADS, hsm, st>>>(ha);
@@ -567,8 +594,11 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     c->smem_optin = prop.sharedMemPerBlockOptin;
     { const char *e = getenv("POPBAM_B200_PILEUP"); c->classic = e && strcmp(e, "classic") == 0; }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
+    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
     for (auto &ev : c->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
+    for (auto &ev : c->fk)
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
     // error-model tables
     const double *pfk, *pbeta, *plhet;
     if (!own_tables) { pfk = tables->fk; pbeta = tables->beta; plhet = tables->lhet; }
@@ -603,6 +633,8 @@ void pb_destroy(pb_ctx *c) {
     HostBuf *hb[] = {&c->h_ctr, &c->h_small, &c->h_seg, &c->h_span};
     for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->fk) if (ev) cudaEventDestroy(ev);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
