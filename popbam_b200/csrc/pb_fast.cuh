@@ -28,6 +28,7 @@ struct PbFastParams {        // derived from the need table (k_fast_params), cac
     int k0lo, k0hi;          // for k0lo <= k <= k0hi: need[0][k] != 0 and need[0][k] <= k  (the depth alone suffices)
     int k1lo, k1hi, hmin;    // for k1lo <= k <= k1hi: need[hi][k] != 0 and <= hmin <= 15   (khi >= hmin suffices)
     int hi_level;            // level of the H plane (n_levels: none)
+    int k2lo, k2hi;          // for k2lo <= k <= k2hi: one stray base cannot change a homozygous call (pb_one_stray_entry)
 };
 
 // ---- bit-planes of the codes, interleaved: planes[1 + w] = {P, B0, B1, H} of the 32 bases codes[32w .. 32w+31]
@@ -97,9 +98,21 @@ __global__ void __launch_bounds__(256) k_ref_planes(const char *__restrict__ ref
 // means "k unanimous bases always take the shortcut"; the longest such run of depths is [k0lo, k0hi].
 // Deeper cells are proven by their count of bases at or above one chosen level (the H plane): the lowest
 // level whose entries stay <= 15 (the bit-sliced counter of H saturates at 16) for the depths right above k0hi.
-__global__ void k_fast_params(const PbCounters *__restrict__ ctr, const uint8_t *__restrict__ need, PbFastParams *__restrict__ fp) {
-    if (threadIdx.x || blockIdx.x) return;
+__global__ void __launch_bounds__(64) k_fast_params(const PbCounters *__restrict__ ctr, const uint8_t *__restrict__ need,
+                                                    const double *__restrict__ fk, const double *__restrict__ beta,
+                                                    const double *__restrict__ lhet, PbFastParams *__restrict__ fp) {
+    __shared__ uint8_t stray_ok[64];
     const int nl = ctr->n_levels;
+    stray_ok[threadIdx.x] = pb_one_stray_entry(nl, ctr->qval, (int)threadIdx.x, fk, beta, lhet);     // depth k = thread index
+    __syncthreads();
+    if (threadIdx.x) return;
+    int k2lo = 1, k2hi = 0;
+    for (int k = 1, start = 1; k <= 64; ++k) {
+        if (k <= 63 && stray_ok[k]) continue;
+        if (k - start > k2hi - k2lo + 1) { k2lo = start; k2hi = k - 1; }
+        start = k + 1;
+    }
+    fp->k2lo = k2lo; fp->k2hi = k2hi;
     int k0lo = 1, k0hi = 0;
     for (int k = 1, start = 1; k <= 64; ++k) {
         const int nd = (k <= 63 && nl > 0) ? need[k] : 0;
@@ -178,6 +191,7 @@ struct PbFastArgs {
     const PbCounters *ctr;
     const PbFastParams *fp;
     uint32_t *cov32, *hard32;                // [n_samples][n_strips]
+    uint32_t *hcount;                        // [n_samples * n_strips + 1] popc(hard32), scanned into cell offsets afterwards
 };
 
 #define PB_FAST_STRIPS 64          // strips of 32 positions per CTA (one sample)
@@ -208,7 +222,7 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
     const int strip_last = min(S + 31, a.span_end - 1);
     const uint32_t my_lo = live ? __ldg(Fs + strip) : 0u, my_hi = live ? __ldg(Fs + strip + a.M + 1) : 0u;
     uint32_t ck[6] = {0, 0, 0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
-    uint32_t kover = 0, hover = 0, mism = 0, lowq = 0;
+    uint32_t kover = 0, hover = 0, mism = 0, mism2 = 0, lowq = 0;     // mism: at least one stray base, mism2: at least two
     uint32_t R0 = 0, R1 = 0, RV = 0;
     if (live && g == 0 && S >= 0 && S < a.ref_len) {                      // reference planes of the strip (bit i = position S + i)
         const int64_t wi = S >> 5; const int sh = S & 31;
@@ -258,7 +272,8 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
                 const uint32_t B0 = __funnelshift_r(lo4.y, hi4.y, sh);
                 const uint32_t B1 = __funnelshift_r(lo4.z, hi4.z, sh);
                 const uint32_t H = __funnelshift_r(lo4.w, hi4.w, sh) & m;
-                mism |= P & (((B0 ^ R0) | (B1 ^ R1)) | ~RV);
+                const uint32_t mm = P & (((B0 ^ R0) | (B1 ^ R1)) | ~RV);
+                mism2 |= mism & mm; mism |= mm;
                 if ((int)((z >> 16) & 0xffu) < a.min_rmsQ) lowq |= P;
                 uint32_t carry = P;
 #pragma unroll
@@ -290,7 +305,11 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
             ch[b] = x ^ carry; carry = c2;
         }
         hover |= carry | __shfl_xor_sync(0xffffffffu, hover, o);
-        mism |= __shfl_xor_sync(0xffffffffu, mism, o);
+        {
+            const uint32_t y = __shfl_xor_sync(0xffffffffu, mism, o);
+            mism2 |= (mism & y) | __shfl_xor_sync(0xffffffffu, mism2, o);
+            mism |= y;
+        }
         lowq |= __shfl_xor_sync(0xffffffffu, lowq, o);
     }
     if (!live || g != 0) return;
@@ -312,12 +331,16 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
         const uint32_t hge = ~(lt | eq) | hover;
         count_ok |= hge & pb_bs_le6(ck, fp.k1hi) & ~pb_bs_le6(ck, fp.k1lo - 1);
     }
-    const uint32_t easy = nonzero & ~mism & ~lowq & ~kover & count_ok;
+    // one stray base at a depth where it provably cannot change the homozygous-reference call
+    const uint32_t stray_ok = fp.k2hi >= fp.k2lo ? mism & ~mism2 & pb_bs_le6(ck, fp.k2hi) & ~pb_bs_le6(ck, fp.k2lo - 1) : 0u;
+    const uint32_t easy = nonzero & ~lowq & ~kover & ((~mism & count_ok) | stray_ok);
     // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
     // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is a bit-sliced compare
     const uint32_t dge = a.min_depth <= 0 ? 0xffffffffu : a.min_depth > 63 ? 0u : ~pb_bs_le6(ck, a.min_depth - 1);
     a.cov32[(size_t)s * a.n_strips + strip] = easy & dge;
     a.hard32[(size_t)s * a.n_strips + strip] = nonzero & ~easy;
+    a.hcount[(size_t)s * a.n_strips + strip] = (uint32_t)__popc(nonzero & ~easy);
+    if (s == 0 && strip == 0) a.hcount[(size_t)a.n_samples * a.n_strips] = 0;
 }
 
 struct PbHardArgs {
@@ -337,77 +360,78 @@ struct PbHardArgs {
     const PbCounters *ctr;
     const uint8_t *need;
     const uint32_t *cov32, *hard32;          // [n_samples][n_strips]
+    const uint32_t *hoff;                    // [n_samples * n_strips + 1] exclusive scan of popc(hard32); last = number of hard cells
     uint64_t *acc_cov;                       // [span] coverage bits of the hard cells      (zeroed before k_hard_cells)
     uint32_t *acc_cnt4;                      // [span] derived-base counts of the hard cells (zeroed)
     uint64_t *site_type;                     // [span] derived-allele bits                   (zeroed; the hard cells are the only writers)
     uint8_t *site_flag;
 };
 
-#define PB_HARD_STRIPS 64          // strips per CTA of k_hard_cells
-#define PB_HARD_THREADS 160        // one pass handles the ~6 % unsettled cells of 64 strips at typical error rates
-#define PB_HARD_RC 1024            // segment records a CTA stages
+#define PB_HARD_THREADS 128
+#define PB_HARD_SLICE 2048         // cell offsets of mask words a CTA keeps in shared memory
 static inline size_t pb_hard_smem(int nl) {
-    return (size_t)PB_HARD_RC * 16 + (size_t)2 * nl * PB_HARD_THREADS * 4 + 256 * 8 + 64 + (size_t)nl * 256 + 64;
+    return (size_t)2 * nl * PB_HARD_THREADS * 4 + 256 * 8 + 64 + (size_t)nl * 256 + 64 + (PB_HARD_SLICE + 1) * 4;
 }
 
-// The cells the bit-sliced pass could not settle, one per THREAD.  One CTA = one sample x the same 64
-// strips as a k_pile_fast CTA: it reads their hard masks, stages the sample's segment records that can
-// cover them (strip index, no search), and every thread takes one listed cell: it walks the staged
-// records of its strip in file order -- exactly the bases call_base sees -- into a private
-// shared-memory histogram and calls the cell with the exact machinery of pb_cell.cuh / pb_walk.cuh.
-// What the site needs from the cell (pb_site_sample: coverage bit, derived-allele bit, derived-base
-// counts) goes into per-position accumulators with integer atomics, so the result does not depend on
-// the order of the cells.  Consecutive CTAs are the samples of one strip block, so the code bytes of a
-// region are pulled through L2 once.
+// The cells the bit-sliced pass could not settle, one per THREAD.  The hard masks are numbered by an exclusive
+// scan of their sizes (hoff); every CTA takes an equal, contiguous share of the cell numbers, so all warps stay
+// busy however unevenly the cells are spread, and consecutive lanes hold neighbouring positions of one sample
+// (they read the same segment records: L1 hits).  A thread finds its cell's mask word by a binary search over the
+// CTA's slice of hoff in shared memory, walks the sample's records that can cover the strip (strip index, no
+// search) in file order -- exactly the bases call_base sees -- into a private shared-memory histogram and
+// calls the cell with the exact machinery of pb_cell.cuh / pb_walk.cuh.  What the site needs from the cell
+// (pb_site_sample: coverage bit, derived-allele bit, derived-base counts) goes into per-position accumulators
+// with integer atomics, so the result does not depend on the order of the cells.
 __global__ void __launch_bounds__(PB_HARD_THREADS) k_hard_cells(const PbHardArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t hm_s[PB_HARD_STRIPS], pre_s[PB_HARD_STRIPS + 1], F_s[PB_HARD_STRIPS + 40];
+    __shared__ uint32_t s_w[2];
     const int nl = a.ctr->n_levels;
     const int n_lw = 2 * nl;
     const int tid = threadIdx.x;
-    int4 *recS = reinterpret_cast<int4 *>(smem_raw);                                     // [PB_HARD_RC]
-    uint32_t *hist = reinterpret_cast<uint32_t *>(recS + PB_HARD_RC);                     // [n_lw][PB_HARD_THREADS]
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);                             // [n_lw][PB_HARD_THREADS]
     double *fk_s = reinterpret_cast<double *>(hist + (size_t)n_lw * PB_HARD_THREADS);
     uint8_t *qval_s = reinterpret_cast<uint8_t *>(fk_s + 256);                           // [64]
     uint8_t *need_s = qval_s + 64;                                                       // [nl][256]
-    const int sb = (int)(blockIdx.x / a.n_samples), smp = (int)(blockIdx.x % a.n_samples);
-    const int t0 = sb * PB_HARD_STRIPS, nst = min(PB_HARD_STRIPS, a.n_strips - t0);
-    // the block's hard masks and the exclusive prefix of their sizes (PB_HARD_STRIPS == 64: two strips per lane)
-    if (tid < 32) {
-        const uint32_t m0 = 2 * tid < nst ? __ldg(a.hard32 + (size_t)smp * a.n_strips + t0 + 2 * tid) : 0u;
-        const uint32_t m1 = 2 * tid + 1 < nst ? __ldg(a.hard32 + (size_t)smp * a.n_strips + t0 + 2 * tid + 1) : 0u;
-        const uint32_t c0 = (uint32_t)__popc(m0), c1 = (uint32_t)__popc(m1);
-        uint32_t x = c0 + c1;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= o) x += y; }
-        hm_s[2 * tid] = m0; hm_s[2 * tid + 1] = m1;
-        pre_s[2 * tid] = x - c0 - c1; pre_s[2 * tid + 1] = x - c1;
-        if (tid == 31) pre_s[PB_HARD_STRIPS] = x;
-    }
-    __syncthreads();
-    const uint32_t total = pre_s[PB_HARD_STRIPS];
-    if (total == 0) return;
+    uint32_t *hoff_s = reinterpret_cast<uint32_t *>(need_s + (size_t)nl * 256 + 64);     // [PB_HARD_SLICE + 1]
+    const uint32_t n_words = (uint32_t)a.n_samples * (uint32_t)a.n_strips;
+    const uint32_t total = a.hoff[n_words];
+    // the CTA's contiguous share of the cells and the mask words they live in
+    const uint32_t per = (total + gridDim.x - 1) / gridDim.x;
+    const uint32_t g_beg = min(total, blockIdx.x * per), g_end = min(total, g_beg + per);
+    if (g_beg >= g_end) return;
     for (int i = tid; i < 256; i += PB_HARD_THREADS) fk_s[i] = a.fk[i];
     if (tid < 64) qval_s[tid] = a.ctr->qval[tid];
     for (int i = tid; i < nl * 64; i += PB_HARD_THREADS) reinterpret_cast<uint32_t *>(need_s)[i] = reinterpret_cast<const uint32_t *>(a.need)[i];
     uint32_t *const my_hist = hist + tid;
     for (int lw = 0; lw < n_lw; ++lw) my_hist[lw * PB_HARD_THREADS] = 0;
-    // strip index slice: records that can cover strip t0 + i are [F_s[i], F_s[i + M + 1])
-    const uint32_t *Fs = a.F + (size_t)smp * a.NI + t0;
-    const int nf = nst + a.M + 1;                                                        // <= NI - t0
-    const bool f_sliced = nf <= PB_HARD_STRIPS + 40;
-    if (f_sliced) for (int i = tid; i < nf; i += PB_HARD_THREADS) F_s[i] = __ldg(Fs + i);
-    const uint32_t clo = __ldg(Fs), chi = __ldg(Fs + nst + a.M);
-    const bool staged = chi - clo <= PB_HARD_RC;
-    if (staged) for (uint32_t r = tid; r < chi - clo; r += PB_HARD_THREADS) recS[r] = __ldg(a.srec + clo + r);
+    if (tid < 2) {
+        const uint32_t g = tid ? g_end - 1 : g_beg;
+        uint32_t lo = 0, hi = n_words;                         // last idx with hoff[idx] <= g
+        while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.hoff + mid) > g) hi = mid; else lo = mid + 1; }
+        s_w[tid] = lo - 1;
+    }
     __syncthreads();
-    for (uint32_t c = tid; c < total; c += PB_HARD_THREADS) {
-        int lo = 0, hi = PB_HARD_STRIPS;                       // the strip of cell c: last i with pre_s[i] <= c
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (pre_s[mid] > c) hi = mid; else lo = mid + 1; }
-        const int si = lo - 1;
-        const int bit = (int)__fns(hm_s[si], 0, (int)(c - pre_s[si]) + 1);
-        const int pos = a.span_beg + (t0 + si) * 32 + bit;
+    const uint32_t w_beg = s_w[0], w_cnt = s_w[1] - s_w[0] + 1;
+    const bool sliced = w_cnt <= PB_HARD_SLICE;
+    if (sliced) for (uint32_t i = tid; i <= w_cnt; i += PB_HARD_THREADS) hoff_s[i] = __ldg(a.hoff + w_beg + i);
+    __syncthreads();
+    for (uint32_t g = g_beg + tid; g < g_end; g += PB_HARD_THREADS) {
+        uint32_t idx;
+        if (sliced) {
+            uint32_t lo = 0, hi = w_cnt;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (hoff_s[mid] > g) hi = mid; else lo = mid + 1; }
+            idx = w_beg + lo - 1;
+        } else {
+            uint32_t lo = w_beg, hi = w_beg + w_cnt;
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(a.hoff + mid) > g) hi = mid; else lo = mid + 1; }
+            idx = lo - 1;
+        }
+        const int bit = (int)__fns(__ldg(a.hard32 + idx), 0, (int)(g - __ldg(a.hoff + idx)) + 1);
+        const int smp = (int)(idx / (uint32_t)a.n_strips), strip = (int)(idx % (uint32_t)a.n_strips);
+        const int pos = a.span_beg + strip * 32 + bit;
         // ---- call_base for (pos, smp): the records that can cover the strip, in file order
-        const uint32_t j0 = f_sliced ? F_s[si] : __ldg(Fs + si), j1 = f_sliced ? F_s[si + a.M + 1] : __ldg(Fs + si + a.M + 1);
+        const uint32_t *Fs = a.F + (size_t)smp * a.NI + strip;
+        const uint32_t j0 = __ldg(Fs), j1 = __ldg(Fs + a.M + 1);
         uint32_t tot4 = 0;
         int rmsq = 0;
         for (uint32_t j = j0; j < j1; j += 8) {               // eight records per step: their code loads (DRAM latency) overlap
@@ -416,7 +440,7 @@ __global__ void __launch_bounds__(PB_HARD_THREADS) k_hard_cells(const PbHardArgs
             for (int q = 0; q < 8; ++q) {
                 code[q] = PB_CODE_NONE; zz[q] = 0;
                 if (j + q < j1) {
-                    const int4 r = staged ? recS[j + q - clo] : __ldg(&a.srec[j + q]);
+                    const int4 r = __ldg(&a.srec[j + q]);
                     const uint32_t z = (uint32_t)r.z;
                     const uint32_t u = (uint32_t)(pos - r.y);
                     zz[q] = z;

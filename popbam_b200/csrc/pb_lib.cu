@@ -294,7 +294,7 @@ int run_pipeline(pb_ctx *c) {
         PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
         k_need_table<<<std::max(nl, 1), 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
         PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastParams)));
-        k_fast_params<<<1, 32, 0, st>>>(ctr, dp<uint8_t>(c->d_need), dp<PbFastParams>(c->d_fastp));
+        k_fast_params<<<1, 64, 0, st>>>(ctr, dp<uint8_t>(c->d_need), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<PbFastParams>(c->d_fastp));
         c->launches += 2;
         PB_CUDA(c, cudaGetLastError());
         c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, c->ctr_host.qval, 64);
@@ -338,7 +338,7 @@ int run_pipeline(pb_ctx *c) {
         const int n_strips = (int)((span + 31) >> 5);
         const size_t plw = (size_t)((c->n_bytes + 31) >> 5) + 1 + PB_PLANE_PAD;
         PB_TRY(dev_reserve(c, c->d_planes, sizeof(uint4) * plw));
-        PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * 2 * (size_t)n * n_strips));
+        PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * (3 * (size_t)n * n_strips + 1)));
         const int fM = (c->ctr_host.max_span + 31) >> 5, fNI = n_strips + fM + 2;
         PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
         PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
@@ -363,7 +363,7 @@ int run_pipeline(pb_ctx *c) {
         fa.W = fast_w;
         fa.min_depth = P.min_depth; fa.min_rmsQ = P.min_rmsQ;
         fa.ctr = ctr; fa.fp = dp<PbFastParams>(c->d_fastp);
-        fa.cov32 = dp<uint32_t>(c->d_cov32); fa.hard32 = fa.cov32 + (size_t)n * n_strips;
+        fa.cov32 = dp<uint32_t>(c->d_cov32); fa.hard32 = fa.cov32 + (size_t)n * n_strips; fa.hcount = fa.hard32 + (size_t)n * n_strips;
         PB_CUDA(c, cudaFuncSetAttribute(k_pile_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_fast_smem(fast_w)));
         k_pile_fast<<<(unsigned)n * (unsigned)fa.n_sblocks, PB_FAST_STRIPS * PB_FAST_G, pb_fast_smem(fast_w), st>>>(fa);
         PbHardArgs ha;
@@ -372,12 +372,13 @@ int run_pipeline(pb_ctx *c) {
         ha.n_samples = n; ha.n_strips = n_strips;
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
         ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need = pa.need;
-        ha.cov32 = fa.cov32; ha.hard32 = fa.hard32;
+        ha.cov32 = fa.cov32; ha.hard32 = fa.hard32; ha.hoff = fa.hcount;
+        PB_TRY(exclusive_scan_u32(c, fa.hcount, (int64_t)n * n_strips + 1, st));
         ha.acc_cov = dp<uint64_t>(c->d_acc); ha.acc_cnt4 = reinterpret_cast<uint32_t *>(ha.acc_cov + span);
         ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
         const size_t hsm = pb_hard_smem(nl);
         PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-        k_hard_cells<<<(unsigned)n * (unsigned)((n_strips + PB_HARD_STRIPS - 1) / PB_HARD_STRIPS), PB_HARD_THREADS, hsm, st>>>(ha);
+        k_hard_cells<<<c->n_sms * 8, PB_HARD_THREADS, hsm, st>>>(ha);
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
         c->launches += 5;
     } else {

@@ -177,6 +177,46 @@ PB_HD uint8_t pb_need_entry(int L, int nl, const uint8_t *qval, int k, const dou
     return 0;
 }
 
+// One stray base.  A cell with k-1 bases of one letter b and ONE base of another letter e (any quality level of
+// the region, any strand) is still called homozygous (b,b) once k is large enough: errmod_cal gives
+// bsum[e] = fk[0]*beta[q_e,k,0] exactly (the stray base is the first and only one of its letter), every
+// likelihood other than (b,b)'s either is a table value of the counts alone (the two (b,e) heterozygotes) or
+// contains bsum[b] or adds a non-negative term to bsum[e].  bsum[b] is bounded below as in pb_need_entry (same
+// order, same rounding, every factor at its minimum), and every step of pb_finish_cell is monotone in it, so if
+// (b,b) wins STRICTLY with that bound for all twelve (b,e) letter pairs and every level of e, it wins for the
+// real cell.  Returns 1 when that holds for depth k: the cell is then homozygous b whatever its snpQ, which is
+// all the per-site logic needs when b is the reference base (pb_site_sample leaves such a word alone).
+PB_HD uint8_t pb_one_stray_entry(int nl, const uint8_t *qval, int k, const double *fk, const double *__restrict__ beta,
+                                 const double *__restrict__ lhet) {
+    if (k < 2 || k > 255 || nl < 1) return 0;
+    double acc = 0.0, fkmin = fk[0];
+    for (int c = 0; c < k - 1; ++c) {
+        if (fk[c] < fkmin) fkmin = fk[c];
+        double bmin = PB_LDG(beta + ((size_t)qval[0] << 16 | (size_t)k << 8 | (size_t)c));
+        for (int l2 = 1; l2 < nl; ++l2) {
+            const double v = PB_LDG(beta + ((size_t)qval[l2] << 16 | (size_t)k << 8 | (size_t)c));
+            if (v < bmin) bmin = v;
+        }
+        if (!(bmin >= 0.0)) return 0;
+        acc = pb_errmod_step(acc, fkmin, bmin);
+    }
+    for (int le = 0; le < nl; ++le) {
+        const double be = pb_errmod_step(0.0, fk[0], PB_LDG(beta + ((size_t)qval[le] << 16 | (size_t)k << 8)));
+        if (!(be >= 0.0)) return 0;
+        for (int b = 0; b < 4; ++b)
+            for (int e = 0; e < 4; ++e) {
+                if (e == b) continue;
+                double bs[4] = {0.0, 0.0, 0.0, 0.0};
+                int c[4] = {0, 0, 0, 0};
+                bs[b] = acc; c[b] = k - 1; bs[e] = be; c[e] = 1;
+                const uint64_t cb = pb_finish_cell(bs, c, k, 0, lhet);
+                // genotype (b,b) with a margin of at least one unit of snpQ between the best and the second best
+                if ((int)((cb >> 8) & 0xff) != (b << 2 | b) || (int)((cb >> 32) & 0xffff) < 1) return 0;
+            }
+    }
+    return 1;
+}
+
 // The shortcut result of a unanimous cell (see pb_unanimous_het): genotype (b,b), snpQ from the het value.
 PB_HD uint64_t pb_unanimous_result(const double *__restrict__ lhet, int k, int b, int rmsq) {
     const float hmin = pb_unanimous_het(lhet, k, b);

@@ -52,3 +52,8 @@ extern "C" int hd_site_logic(uint64_t *cb, int n, int ref, int het_mode, int min
                              uint64_t *cov, uint64_t *type) {
     return pb_site_logic(cb, 1, n, ref, het_mode, min_snpQ, min_rmsQ, min_depth, max_depth, cov, type);
 }
+
+// pb_one_stray_entry for a level set given as quality values (ascending)
+extern "C" int hd_one_stray(const double *fk, const double *beta, const double *lhet, const uint8_t *qval, int nl, int k) {
+    return pb_one_stray_entry(nl, qval, k, fk, beta, lhet);
+}
