@@ -785,20 +785,32 @@ __global__ void __launch_bounds__(256) k_window_sites(int span_beg, const int32_
     const int64_t off = (int64_t)beg - span_beg;
     uint32_t carry_sites = 0, carry_seg = 0;
     const int64_t so = WRITE ? seg_off[w] : 0;
-    for (int b0 = 0; b0 < len; b0 += 256) {
-        const int i = b0 + (int)threadIdx.x;
-        const uint32_t f = i < len ? site_flag[off + i] : 0;
-        const uint32_t v = (f & 1u) | ((f >> 1 & 1u) << 16);
+    // four consecutive positions per thread and step: one block scan per 1024 positions
+    for (int b0 = 0; b0 < len; b0 += 1024) {
+        const int i0 = b0 + 4 * (int)threadIdx.x;
+        uint32_t f[4], v = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            f[q] = i0 + q < len ? site_flag[off + i0 + q] : 0;
+            v += (f[q] & 1u) | ((f[q] >> 1 & 1u) << 16);
+        }
         uint32_t tot;
-        const uint32_t ex = pb_block_exscan(v, &tot);
-        if (WRITE && (f & 2u)) {
-            const int64_t d = so + carry_seg + (ex >> 16);
-            seg_pos[d] = (uint32_t)(beg + i);
-            seg_idx[d] = carry_sites + (ex & 0xffffu);
-            seg_type[d] = site_type[off + i];
-            const int64_t rp = (int64_t)beg + i;
-            seg_ref[d] = (rp >= 0 && rp < ref_len) ? (uint8_t)ref[rp] : (uint8_t)'N';
-            if (seg_cb) for (int s = 0; s < n_samples; ++s) seg_cb[d * n_samples + s] = cb_all[(off + i) * n_samples + s];
+        uint32_t ex = pb_block_exscan(v, &tot);
+        if (WRITE) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (f[q] & 2u) {
+                    const int i = i0 + q;
+                    const int64_t d = so + carry_seg + (ex >> 16);
+                    seg_pos[d] = (uint32_t)(beg + i);
+                    seg_idx[d] = carry_sites + (ex & 0xffffu);
+                    seg_type[d] = site_type[off + i];
+                    const int64_t rp = (int64_t)beg + i;
+                    seg_ref[d] = (rp >= 0 && rp < ref_len) ? (uint8_t)ref[rp] : (uint8_t)'N';
+                    if (seg_cb) for (int s = 0; s < n_samples; ++s) seg_cb[d * n_samples + s] = cb_all[(off + i) * n_samples + s];
+                }
+                ex += (f[q] & 1u) | ((f[q] >> 1 & 1u) << 16);
+            }
         }
         carry_sites += tot & 0xffffu;
         carry_seg += tot >> 16;

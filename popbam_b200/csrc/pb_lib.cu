@@ -40,6 +40,8 @@ struct pb_ctx {
     std::string err;
     int64_t launches = 0;
     int n_sms = 148;
+    // grids of the persistent (grid-stride) kernels: SM count x resident CTAs per SM, so every launch is one full wave
+    int g_encode = 148, g_bitplanes = 148, g_qual_mask = 148, g_read_prep = 148, g_strip_index = 148;
     size_t smem_optin = 0;
     // tables / contig
     DevBuf d_fk, d_beta, d_lhet, d_ref, d_rms_thr;
@@ -233,7 +235,7 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaStreamWaitEvent(s2, c->fk[0], 0));
     // -- per-read chain on the second stream: prep, depth bound, stable partition by sample
     if (N > 0) {
-        k_read_prep<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->n_sms * 8), 256, 0, s2>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
+        k_read_prep<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->g_read_prep), 256, 0, s2>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
                                                  dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), n, P.min_mapQ,
                                                  dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), bin_origin, n_bins, c->span_end,
                                                  dp<uint32_t>(c->d_bins), ctr);
@@ -259,7 +261,7 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaEventRecord(c->fk[2], s2));
     // -- per-base chain on the main stream: quality values present, level table, base codes
     if (N > 0) {
-        k_qual_mask<<<c->n_sms * 8, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
+        k_qual_mask<<<c->g_qual_mask, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
         c->launches += 1;
     }
     PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[1], 0));
@@ -268,7 +270,7 @@ int run_pipeline(pb_ctx *c) {
     if (N > 0) {
         PB_TRY(dev_reserve(c, c->d_qtab, 64 * 256));
         k_qual_table<<<64, 256, 0, st>>>(ctr, illumina, P.min_baseQ, dp<uint8_t>(c->d_qtab));
-        k_encode<<<c->n_sms * 8, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
+        k_encode<<<c->g_encode, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
                                               dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes,
                                               (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ, dp<uint8_t>(c->d_qtab),
                                               dp<uint8_t>(c->d_codes));
@@ -345,14 +347,14 @@ int run_pipeline(pb_ctx *c) {
         // the strip index and the zeroing of the accumulators run beside the bit-plane pass
         PB_CUDA(c, cudaEventRecord(c->fk[3], st));
         PB_CUDA(c, cudaStreamWaitEvent(c->stream2, c->fk[3], 0));
-        k_strip_index<<<c->n_sms * 8, 256, 0, c->stream2>>>(pa.srec, pa.sstart, n, c->span_beg, fM, fNI, dp<uint32_t>(c->d_sidx));
+        k_strip_index<<<c->g_strip_index, 256, 0, c->stream2>>>(pa.srec, pa.sstart, n, c->span_beg, fM, fNI, dp<uint32_t>(c->d_sidx));
         PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, c->stream2));
         PB_CUDA(c, cudaMemsetAsync(pa.site_type, 0, sizeof(uint64_t) * (size_t)span, c->stream2));
         PB_CUDA(c, cudaEventRecord(c->fk[4], c->stream2));
         uint4 *pl = dp<uint4>(c->d_planes);
         const size_t rpw = (size_t)((c->ref_len + 31) >> 5) + 2;
         const uint32_t *rp = dp<uint32_t>(c->d_refpl);
-        k_bitplanes<<<c->n_sms * 8, 256, 0, st>>>(pa.codes, c->n_bytes, dp<PbFastParams>(c->d_fastp), pl);
+        k_bitplanes<<<c->g_bitplanes, 256, 0, st>>>(pa.codes, c->n_bytes, dp<PbFastParams>(c->d_fastp), pl);
         PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[4], 0));
         PbFastArgs fa;
         fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.M = fM; fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
@@ -378,7 +380,9 @@ int run_pipeline(pb_ctx *c) {
         ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
         const size_t hsm = pb_hard_smem(nl);
         PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-        k_hard_cells<<<c->n_sms * 8, PB_HARD_THREADS, hsm, st>>>(ha);
+        int hard_per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hard_per_sm, k_hard_cells, PB_HARD_THREADS, hsm) != cudaSuccess || hard_per_sm < 1) { cudaGetLastError(); hard_per_sm = 1; }
+        k_hard_cells<<<c->n_sms * hard_per_sm, PB_HARD_THREADS, hsm, st>>>(ha);
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
         c->launches += 5;
     } else {
@@ -594,6 +598,15 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     c->n_sms = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     { const char *e = getenv("POPBAM_B200_PILEUP"); c->classic = e && strcmp(e, "classic") == 0; }
+    {
+        auto wave = [&](auto kern, int threads) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+            return c->n_sms * per_sm;
+        };
+        c->g_encode = wave(k_encode, 256); c->g_bitplanes = wave(k_bitplanes, 256); c->g_qual_mask = wave(k_qual_mask, 256);
+        c->g_read_prep = wave(k_read_prep, 256); c->g_strip_index = wave(k_strip_index, 256);
+    }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
     for (auto &ev : c->ev)
