@@ -312,13 +312,15 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
         }
         lowq |= __shfl_xor_sync(0xffffffffu, lowq, o);
     }
-    if (!live || g != 0) return;
+    // After the butterfly all PB_FAST_G threads of a strip hold the totals, so the range tests are shared out: thread g
+    // evaluates "depth in [lo_g, hi_g]" for one of the four ranges (bit-sliced compares against run-time constants)
     const PbFastParams fp = *a.fp;
-    const uint32_t valid = (strip_last - S + 1) >= 32 ? 0xffffffffu : (1u << (strip_last - S + 1)) - 1u;
-    const uint32_t nonzero = (ck[0] | ck[1] | ck[2] | ck[3] | ck[4] | ck[5] | kover) & valid;
-    // depth alone / count of high-quality bases proves the shortcut (pb_need_entry)
-    uint32_t count_ok = fp.k0hi >= fp.k0lo ? pb_bs_le6(ck, fp.k0hi) & ~pb_bs_le6(ck, fp.k0lo - 1) : 0u;
-    if (fp.k1hi >= fp.k1lo && fp.hmin > 0) {
+    static_assert(PB_FAST_G == 4, "four range tests, one per thread of a strip");
+    const int lo_g = g == 0 ? fp.k0lo : g == 1 ? fp.k1lo : g == 2 ? fp.k2lo : max(a.min_depth, 0);
+    const int hi_g = g == 0 ? fp.k0hi : g == 1 ? ((fp.hmin > 0) ? fp.k1hi : 0) : g == 2 ? fp.k2hi : 63;
+    uint32_t in_range = 0;
+    if (hi_g >= lo_g && lo_g <= 63) in_range = pb_bs_le6(ck, min(hi_g, 63)) & (lo_g > 0 ? ~pb_bs_le6(ck, lo_g - 1) : 0xffffffffu);
+    if (g == 1 && in_range) {
         // khi >= hmin  <=>  not (khi <= hmin - 1), or the 4-plane counter overflowed (>= 16 > hmin)
         uint32_t lt = 0, eq = 0xffffffffu;
         const int C = fp.hmin - 1;
@@ -328,15 +330,19 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
             lt |= eq & ~ch[b] & cb;
             eq &= ~(ch[b] ^ cb);
         }
-        const uint32_t hge = ~(lt | eq) | hover;
-        count_ok |= hge & pb_bs_le6(ck, fp.k1hi) & ~pb_bs_le6(ck, fp.k1lo - 1);
+        in_range &= ~(lt | eq) | hover;
     }
-    // one stray base at a depth where it provably cannot change the homozygous-reference call
-    const uint32_t stray_ok = fp.k2hi >= fp.k2lo ? mism & ~mism2 & pb_bs_le6(ck, fp.k2hi) & ~pb_bs_le6(ck, fp.k2lo - 1) : 0u;
-    const uint32_t easy = nonzero & ~lowq & ~kover & ((~mism & count_ok) | stray_ok);
+    const int lane0 = (tid & 31) & ~(PB_FAST_G - 1);
+    const uint32_t r_k0 = __shfl_sync(0xffffffffu, in_range, lane0), r_k1 = __shfl_sync(0xffffffffu, in_range, lane0 + 1);
+    const uint32_t r_k2 = __shfl_sync(0xffffffffu, in_range, lane0 + 2), dge = __shfl_sync(0xffffffffu, in_range, lane0 + 3);
+    if (!live || g != 0) return;
+    const uint32_t valid = (strip_last - S + 1) >= 32 ? 0xffffffffu : (1u << (strip_last - S + 1)) - 1u;
+    const uint32_t nonzero = (ck[0] | ck[1] | ck[2] | ck[3] | ck[4] | ck[5] | kover) & valid;
+    // depth alone / count of high-quality bases proves the unanimous shortcut (pb_need_entry); one stray base at a
+    // depth where it provably cannot change the homozygous-reference call (pb_one_stray_entry)
+    const uint32_t easy = nonzero & ~lowq & ~kover & ((~mism & (r_k0 | r_k1)) | (mism & ~mism2 & r_k2));
     // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
-    // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is a bit-sliced compare
-    const uint32_t dge = a.min_depth <= 0 ? 0xffffffffu : a.min_depth > 63 ? 0u : ~pb_bs_le6(ck, a.min_depth - 1);
+    // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is the fourth range test
     a.cov32[(size_t)s * a.n_strips + strip] = easy & dge;
     a.hard32[(size_t)s * a.n_strips + strip] = nonzero & ~easy;
     a.hcount[(size_t)s * a.n_strips + strip] = (uint32_t)__popc(nonzero & ~easy);
