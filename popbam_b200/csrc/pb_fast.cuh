@@ -31,46 +31,122 @@ struct PbFastParams {        // derived from the need table (k_fast_params), cac
     int k2lo, k2hi;          // for k2lo <= k <= k2hi: one stray base cannot change a homozygous call (pb_one_stray_entry)
 };
 
-// ---- bit-planes of the codes, interleaved: planes[1 + w] = {P, B0, B1, H} of the 32 bases codes[32w .. 32w+31]
-// (one pad element in front, PB_PLANE_PAD behind).  Each thread turns 32 code bytes into one uint4 with packed-byte
-// arithmetic: a per-byte predicate is brought to bit 7 (or bit 0) of its byte and the four flags of a word are
-// gathered into a nibble by one multiply (0x00204081 moves byte i's flag to bit 28 + i resp. 21 + i; the sixteen
-// partial products land on distinct bits, so nothing carries).
+// ---- bit-planes of the bases, interleaved: planes[1 + w] = {P, B0, B1, H} of the 32 bases at byte offsets 32w .. 32w+31
+// of qual[] (one pad element in front, PB_PLANE_PAD behind):
+//     P   the base passes call_base's filters (popbam.cpp:268-284): read kept and mapQ >= min_mapQ, baseQ' >= min_baseQ, A/C/G/T
+//     B0, B1   its two base bits (A 0, C 1, G 2, T 3), zero where P is zero
+//     H   P and clamp(min(baseQ', mapQ), 4, 63) >= the quality value of level hi  (<=> baseQ' >= qv and mapQ >= qv)
+// straight from qual[] / seq4[] with packed arithmetic -- no per-base table lookups and no codes[] in between:
+// "byte >= T" for four quality bytes is three operations (T <= 128: add 128 - T to the low seven bits, or in bit 7),
+// the four flags of a word are gathered by one multiply (0x00204081 moves byte i's bit 7 to bit 28 + i; the sixteen
+// partial products land on distinct bits, so nothing carries), a byte of seq4 (two bases) is one shared-memory lookup
+// giving "is A/C/G/T" and the two base bits of both bases, and per-read conditions (alive, mapQ >= qv) are bit masks
+// below / above the one read boundary a 64-byte chunk can have.  Chunks with several boundaries (reads shorter than 64 bases)
+// and the tail of the array go byte by byte.
 #define PB_PLANE_PAD 16
-__device__ __forceinline__ void pb_planes_of_word(uint32_t w, uint32_t hadd, int sh, uint32_t &P, uint32_t &B0, uint32_t &B1, uint32_t &H) {
-    const uint32_t x = ~w;                                                         // a byte of x is 0 <=> code == PB_CODE_NONE
-    const uint32_t nz = (((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
-    const uint32_t p4 = (nz * 0x00204081u) >> 28;
-    const uint32_t b04 = (((w & 0x01010101u) * 0x00204081u) >> 21) & p4;
-    const uint32_t b14 = ((((w >> 1) & 0x01010101u) * 0x00204081u) >> 21) & p4;
-    const uint32_t h4 = (((((w >> 2) & 0x3f3f3f3fu) + hadd) & 0x80808080u) * 0x00204081u) >> 28;      // level >= hi_level
-    P |= p4 << sh; B0 |= b04 << sh; B1 |= b14 << sh; H |= (h4 & p4) << sh;
-}
-__global__ void __launch_bounds__(256) k_bitplanes(const uint8_t *__restrict__ codes, int64_t n_bytes, const PbFastParams *__restrict__ fp,
-                                                   uint4 *__restrict__ planes) {
-    const int hi = fp->hi_level;                                                   // <= 64
-    const uint32_t hadd = (uint32_t)(128 - hi) * 0x01010101u;
-    const int64_t n_words = (n_bytes + 31) >> 5;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += stride) {
-        const int64_t o = w << 5;
-        uint32_t P = 0, B0 = 0, B1 = 0, H = 0;
-        if (o + 32 <= n_bytes) {
-            const uint4 a = __ldg(reinterpret_cast<const uint4 *>(codes + o)), b = __ldg(reinterpret_cast<const uint4 *>(codes + o + 16));
-            pb_planes_of_word(a.x, hadd, 0, P, B0, B1, H);  pb_planes_of_word(a.y, hadd, 4, P, B0, B1, H);
-            pb_planes_of_word(a.z, hadd, 8, P, B0, B1, H);  pb_planes_of_word(a.w, hadd, 12, P, B0, B1, H);
-            pb_planes_of_word(b.x, hadd, 16, P, B0, B1, H); pb_planes_of_word(b.y, hadd, 20, P, B0, B1, H);
-            pb_planes_of_word(b.z, hadd, 24, P, B0, B1, H); pb_planes_of_word(b.w, hadd, 28, P, B0, B1, H);
+#define PB_PL_CHUNK 64
+__device__ __forceinline__ uint32_t pb_ge4(uint32_t w, uint32_t add) { return ((((w & 0x7f7f7f7fu) + add) | w) & 0x80808080u) * 0x00204081u >> 28; }
+__global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
+                                                const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4,
+                                                const uint8_t *__restrict__ qual, int64_t n_bytes, double reads_per_byte,
+                                                int min_mapQ, int min_baseQ, int illumina, const PbCounters *__restrict__ ctr,
+                                                const PbFastParams *__restrict__ fp, uint4 *__restrict__ planes) {
+    // seq4 byte -> valid bits 0-1, B0 bits 8-9, B1 bits 16-17 of its two bases (high nibble = first base = lower bit)
+    __shared__ uint32_t seq_s[256];
+    {
+        const uint32_t n0 = (uint32_t)((PB_NT16_NT4_LUT >> ((threadIdx.x >> 4) * 4)) & 0xf), n1 = (uint32_t)((PB_NT16_NT4_LUT >> ((threadIdx.x & 15) * 4)) & 0xf);
+        const uint32_t v0 = n0 < 4u, v1 = n1 < 4u;
+        seq_s[threadIdx.x] = v0 | v1 << 1 | (v0 & n0 & 1u) << 8 | (v1 & n1 & 1u) << 9 | (v0 & (n0 >> 1) & 1u) << 16 | (v1 & (n1 >> 1) & 1u) << 17;
+    }
+    __syncthreads();
+    const int hi = fp->hi_level, nl = ctr->n_levels;
+    const int qv = hi < nl ? (int)ctr->qval[hi] : 256;                                  // quality value of the H plane's level
+    const int tp = min_baseQ <= 0 ? 0 : min_baseQ + (illumina ? 31 : 0);                // raw quality byte thresholds (host: tp <= 128)
+    const int th = min(128, qv + (illumina ? 31 : 0));
+    const uint32_t addP = (uint32_t)(128 - tp) * 0x01010101u, addH = (uint32_t)(128 - th) * 0x01010101u;
+    // per-read conditions: bit 0 alive (kept, mapQ >= min_mapQ), bit 1 mapQ >= qv
+    auto flags_of = [&](int64_t rr) -> uint32_t {
+        if (rr >= n || rkey[rr] == PB_KEY_DROP) return 0u;
+        const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
+        return mq >= min_mapQ ? (1u | (min(mq, 63) >= qv ? 2u : 0u)) : 0u;
+    };
+    const int64_t n_chunks = (n_bytes + PB_PL_CHUNK - 1) / PB_PL_CHUNK;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_chunks; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t o = (uint64_t)t * PB_PL_CHUNK;
+        const int nb = (int)min((uint64_t)PB_PL_CHUNK, (uint64_t)n_bytes - o);
+        // owner of byte o: last r with base[r] <= o (reads lie back to back: start from a proportional guess)
+        int64_t lo = (int64_t)((double)o * reads_per_byte);
+        if (lo >= n) lo = n - 1;
+        int64_t hi2 = lo + 1, step = 1;
+        while (lo > 0 && __ldg(base + lo) > o) { hi2 = lo; lo = max((int64_t)0, lo - step); step <<= 1; }
+        step = 1;
+        while (hi2 < n && __ldg(base + hi2) <= o) { lo = hi2; hi2 = min(n, hi2 + step); step <<= 1; }
+        while (hi2 - lo > 1) { const int64_t mid = (lo + hi2) >> 1; if (__ldg(base + mid) <= o) lo = mid; else hi2 = mid; }
+        const int64_t r = lo;
+        const uint64_t next = r + 1 < n ? __ldg(base + r + 1) : ~0ULL;
+        const uint64_t next2 = r + 2 < n ? __ldg(base + r + 2) : ~0ULL;
+        uint32_t P[2] = {0, 0}, B0[2] = {0, 0}, B1[2] = {0, 0}, H[2] = {0, 0};
+        if (nb == PB_PL_CHUNK && next2 - o >= (uint64_t)PB_PL_CHUNK) {
+            uint4 qv4[4], sv[2];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) qv4[v] = __ldg(reinterpret_cast<const uint4 *>(qual + o) + v);
+#pragma unroll
+            for (int v = 0; v < 2; ++v) sv[v] = __ldg(reinterpret_cast<const uint4 *>(seq4 + (o >> 1)) + v);
+            const uint32_t qw[16] = {qv4[0].x, qv4[0].y, qv4[0].z, qv4[0].w, qv4[1].x, qv4[1].y, qv4[1].z, qv4[1].w,
+                                     qv4[2].x, qv4[2].y, qv4[2].z, qv4[2].w, qv4[3].x, qv4[3].y, qv4[3].z, qv4[3].w};
+            const uint32_t sw[8] = {sv[0].x, sv[0].y, sv[0].z, sv[0].w, sv[1].x, sv[1].y, sv[1].z, sv[1].w};
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                P[g >> 3] |= pb_ge4(qw[g], addP) << (4 * (g & 7));
+                H[g >> 3] |= pb_ge4(qw[g], addH) << (4 * (g & 7));
+            }
+            uint32_t V[2] = {0, 0};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                // four lookups per word: 8 bases -> V in bits 0-7, B0 in 8-15, B1 in 16-23
+                const uint32_t acc = seq_s[sw[j] & 0xffu] | seq_s[(sw[j] >> 8) & 0xffu] << 2 | seq_s[(sw[j] >> 16) & 0xffu] << 4 | seq_s[sw[j] >> 24] << 6;
+                V[j >> 2] |= (acc & 0xffu) << (8 * (j & 3)); B0[j >> 2] |= ((acc >> 8) & 0xffu) << (8 * (j & 3)); B1[j >> 2] |= ((acc >> 16) & 0xffu) << (8 * (j & 3));
+            }
+            // per-read conditions below / above the boundary
+            const uint32_t fA = flags_of(r);
+            const uint32_t cut = next - o < (uint64_t)PB_PL_CHUNK ? (uint32_t)(next - o) : (uint32_t)PB_PL_CHUNK;
+            const uint32_t fB = cut < PB_PL_CHUNK ? flags_of(r + 1) : fA;
+            const uint64_t below = cut >= 64 ? ~0ULL : (1ULL << cut) - 1ULL;
+            const uint64_t alive = ((fA & 1u) ? below : 0ULL) | ((fB & 1u) ? ~below : 0ULL);
+            const uint64_t hiok = ((fA & 2u) ? below : 0ULL) | ((fB & 2u) ? ~below : 0ULL);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                P[h] &= V[h] & (uint32_t)(alive >> (32 * h));
+                H[h] &= P[h] & (uint32_t)(hiok >> (32 * h));
+                B0[h] &= P[h]; B1[h] &= P[h];
+            }
         } else {
-            for (int i = 0; o + i < n_bytes; ++i) {
-                const uint32_t c = codes[o + i];
-                if (c == PB_CODE_NONE) continue;
-                P |= 1u << i; B0 |= (c & 1u) << i; B1 |= ((c >> 1) & 1u) << i; H |= (uint32_t)((int)(c >> 2) >= hi) << i;
+            int64_t rr = r;
+            uint64_t nx = next;
+            uint32_t f = flags_of(rr);
+            for (int i = 0; i < nb; ++i) {
+                while (o + i >= nx) {
+                    ++rr;
+                    nx = rr + 1 < n ? __ldg(base + rr + 1) : ~0ULL;
+                    f = flags_of(rr);
+                }
+                const uint32_t q = qual[o + i];
+                const uint32_t sbyte = seq4[(o + i) >> 1];
+                const uint32_t nib = ((o + i) & 1) ? (sbyte & 15u) : (sbyte >> 4);
+                const uint32_t nt = (uint32_t)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+                if (!(f & 1u) || nt > 3u || (int)q < tp) continue;
+                const uint32_t bit = 1u << (i & 31);
+                P[i >> 5] |= bit;
+                if (nt & 1u) B0[i >> 5] |= bit;
+                if (nt & 2u) B1[i >> 5] |= bit;
+                if ((f & 2u) && (int)q >= th && qv <= 63) H[i >> 5] |= bit;
             }
         }
-        planes[w + 1] = make_uint4(P, B0, B1, H);
+        planes[2 * t + 1] = make_uint4(P[0], B0[0], B1[0], H[0]);
+        if (nb > 32) planes[2 * t + 2] = make_uint4(P[1], B0[1], B1[1], H[1]);
     }
     if (blockIdx.x == 0 && threadIdx.x <= PB_PLANE_PAD) {                           // pad: one in front, PB_PLANE_PAD behind
+        const int64_t n_words = (n_bytes + 31) >> 5;
         const int64_t i = threadIdx.x ? n_words + threadIdx.x : 0;
         planes[i] = make_uint4(0, 0, 0, 0);
     }
@@ -353,7 +429,8 @@ struct PbHardArgs {
     const int4 *srec;
     const uint32_t *F;                       // strip index (k_strip_index)
     int M, NI;
-    const uint8_t *codes;
+    const uint8_t *qual, *seq4;              // the read batch's bases: a cell's codes are formed on the fly (no codes[] on this path)
+    const uint8_t *qtab;                     // [64][256] k_qual_table
     const char *ref;
     int64_t ref_len;
     int span_beg, span_end;
@@ -450,7 +527,15 @@ __global__ void __launch_bounds__(PB_HARD_THREADS) k_hard_cells(const PbHardArgs
                     const uint32_t z = (uint32_t)r.z;
                     const uint32_t u = (uint32_t)(pos - r.y);
                     zz[q] = z;
-                    if (u < (z & 0xffffu)) code[q] = __ldg(a.codes + ((int64_t)(((uint64_t)(z >> 26) << 32) | (uint32_t)r.w) + u));
+                    if (u < (z & 0xffffu)) {
+                        // call_base's filter and code for this base (popbam.cpp:268-284), as k_encode forms them
+                        const int64_t off = (int64_t)(((uint64_t)(z >> 26) << 32) | (uint32_t)r.w) + u;
+                        const uint32_t qb = __ldg(a.qual + off), sb = __ldg(a.seq4 + (off >> 1));
+                        const uint32_t nib = (off & 1) ? (sb & 15u) : (sb >> 4);
+                        const uint32_t nt = (uint32_t)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+                        const uint32_t lv = __ldg(a.qtab + (min((z >> 16) & 0xffu, 63u) << 8) + qb);
+                        code[q] = nt > 3u ? PB_CODE_NONE : (lv | nt);      // 0xff | nt stays PB_CODE_NONE
+                    }
                 }
             }
 #pragma unroll

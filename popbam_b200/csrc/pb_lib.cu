@@ -216,7 +216,6 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaMemsetAsync(c->d_ctr.p, 0, sizeof(PbCounters), st));
     PB_TRY(dev_reserve(c, c->d_rkey, (size_t)std::max<int64_t>(N, 1)));
     PB_TRY(dev_reserve(c, c->d_rnseg, (size_t)std::max<int64_t>(N, 1)));
-    PB_TRY(dev_reserve(c, c->d_codes, (size_t)c->n_bytes + 32));     // k_hard_cells copies aligned 16-byte pieces
     PB_TRY(dev_reserve(c, c->d_srec, sizeof(int4) * (size_t)std::max<int64_t>(c->n_cig, 1)));   // one record per M/=/X op at most
     PB_TRY(dev_reserve(c, c->d_sstart, sizeof(uint32_t) * (PB_MAX_SAMPLES + 1)));
     const int64_t n_chunks = std::max<int64_t>(1, (N + PB_PART_CHUNK - 1) / PB_PART_CHUNK);
@@ -270,11 +269,7 @@ int run_pipeline(pb_ctx *c) {
     if (N > 0) {
         PB_TRY(dev_reserve(c, c->d_qtab, 64 * 256));
         k_qual_table<<<64, 256, 0, st>>>(ctr, illumina, P.min_baseQ, dp<uint8_t>(c->d_qtab));
-        k_encode<<<c->g_encode, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
-                                              dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes,
-                                              (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ, dp<uint8_t>(c->d_qtab),
-                                              dp<uint8_t>(c->d_codes));
-        c->launches += 2;
+        c->launches += 1;
     }
     PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));                // join
     PB_CUDA(c, cudaGetLastError());
@@ -312,7 +307,7 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PbPileArgs pa;
     pa.srec = dp<int4>(c->d_srec); pa.sstart = dp<uint32_t>(c->d_sstart);
-    pa.codes = dp<uint8_t>(c->d_codes);
+    pa.codes = nullptr;
     pa.ref = dp<char>(c->d_ref); pa.ref_len = c->ref_len;
     pa.span_beg = c->span_beg; pa.span_end = c->span_end;
     pa.win_beg = dp<int32_t>(c->d_wbeg); pa.win_end = dp<int32_t>(c->d_wend); pa.n_windows = NW;
@@ -331,7 +326,7 @@ int run_pipeline(pb_ctx *c) {
     const int fast_w = pb_fast_words(c->ctr_host.max_span);
     const bool fast = !cap && !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && N > 0 &&
                       pb_hard_smem(nl) <= c->smem_optin && span * n < (int64_t)0x7fffffff && fast_w <= PB_PLANE_PAD &&
-                      pb_fast_smem(fast_w) <= 100 * 1024;
+                      pb_fast_smem(fast_w) <= 100 * 1024 && P.min_baseQ + (illumina ? 31 : 0) <= 128;
     if (getenv("POPBAM_B200_DEBUG"))
         fprintf(stderr, "[popbam_b200] pileup path: fast=%d cap=%d want_cb=%d min_depth=%d min_snpQ=%d classic=%d N=%lld nl=%d hard_smem=%zu optin=%zu fast_w=%d fast_smem=%zu depth_bound=%d max_span=%d\n",
                 (int)fast, (int)cap, (int)want_cb, P.min_depth, P.min_snpQ, (int)c->classic, (long long)N, nl, pb_hard_smem(nl), c->smem_optin,
@@ -354,7 +349,9 @@ int run_pipeline(pb_ctx *c) {
         uint4 *pl = dp<uint4>(c->d_planes);
         const size_t rpw = (size_t)((c->ref_len + 31) >> 5) + 2;
         const uint32_t *rp = dp<uint32_t>(c->d_refpl);
-        k_bitplanes<<<c->g_bitplanes, 256, 0, st>>>(pa.codes, c->n_bytes, dp<PbFastParams>(c->d_fastp), pl);
+        k_planes<<<c->g_bitplanes, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base), dp<uint8_t>(c->d_seq4),
+                                                 dp<uint8_t>(c->d_qual), c->n_bytes, (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ,
+                                                 P.min_baseQ, illumina, ctr, dp<PbFastParams>(c->d_fastp), pl);
         PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[4], 0));
         PbFastArgs fa;
         fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.M = fM; fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
@@ -369,7 +366,7 @@ int run_pipeline(pb_ctx *c) {
         PB_CUDA(c, cudaFuncSetAttribute(k_pile_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_fast_smem(fast_w)));
         k_pile_fast<<<(unsigned)n * (unsigned)fa.n_sblocks, PB_FAST_STRIPS * PB_FAST_G, pb_fast_smem(fast_w), st>>>(fa);
         PbHardArgs ha;
-        ha.srec = pa.srec; ha.F = fa.F; ha.M = fM; ha.NI = fNI; ha.codes = pa.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
+        ha.srec = pa.srec; ha.F = fa.F; ha.M = fM; ha.NI = fNI; ha.qual = dp<uint8_t>(c->d_qual); ha.seq4 = dp<uint8_t>(c->d_seq4); ha.qtab = dp<uint8_t>(c->d_qtab); ha.ref = pa.ref; ha.ref_len = pa.ref_len;
         ha.span_beg = pa.span_beg; ha.span_end = pa.span_end; ha.win_beg = pa.win_beg; ha.win_end = pa.win_end; ha.n_windows = NW;
         ha.n_samples = n; ha.n_strips = n_strips;
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
@@ -386,8 +383,16 @@ int run_pipeline(pb_ctx *c) {
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
         c->launches += 5;
     } else {
+        // base codes for k_pileup_call (the bit-sliced path reads qual[] / seq4[] directly)
+        PB_TRY(dev_reserve(c, c->d_codes, (size_t)std::max<int64_t>(c->n_bytes, 1)));
+        pa.codes = dp<uint8_t>(c->d_codes);
+        if (N > 0)
+            k_encode<<<c->g_encode, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base),
+                                                  dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes,
+                                                  (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ, dp<uint8_t>(c->d_qtab),
+                                                  dp<uint8_t>(c->d_codes));
         kern<<<nblk(span, tp), tp, smem, st>>>(pa);
-        c->launches += 1;
+        c->launches += 2;
     }
     PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaEventRecord(c->ev[3], st));
@@ -604,7 +609,7 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
             return c->n_sms * per_sm;
         };
-        c->g_encode = wave(k_encode, 256); c->g_bitplanes = wave(k_bitplanes, 256); c->g_qual_mask = wave(k_qual_mask, 256);
+        c->g_encode = wave(k_encode, 256); c->g_bitplanes = wave(k_planes, 256); c->g_qual_mask = wave(k_qual_mask, 256);
         c->g_read_prep = wave(k_read_prep, 256); c->g_strip_index = wave(k_strip_index, 256);
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
