@@ -11,8 +11,9 @@ production: BAM-index chunks of whole windows); ONE STEP = the whole contig = ev
              result copy) re-run on resident inputs, timed with CUDA events on the library's stream.
   e2e        same job through the public C ABI from PINNED HOST batches: pb_region_begin / pb_push_batch (host->device
              copy inside the timed region) / pb_region_end (device->host result copy inside the timed region).
-  roofline   the pileup / call / site stage (k_bitplanes, k_pile_fast, k_hard_cells, k_fast_sites, with k_strip_index
-             beside them): algorithmic bytes per region / the stage's CUDA-event duration.
+  roofline   the pileup / call / site stage (k_pile_fast, k_hard_cells, k_fast_sites): algorithmic bytes per region / the
+             stage's CUDA-event duration.  The per-base pass that feeds it (k_planes) is timed with the
+             preparation, as the base-code pass of the single-kernel formulation was.
   cpu_baseline  the unmodified reference (oracle/_ref/popbam, built from /root/reference by oracle/Makefile) timed on
              one host core on a bounded sample of the same workload; falls back to the oracle port if the binary is absent.
 
@@ -37,8 +38,8 @@ sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np  # noqa: E402
 
 # DRAM bytes (read + written) of the pileup stage's kernels on a 2.3 Mb shard of this workload, from the committed ncu
-# capture profiles/r1_bs_stage_raw.txt: k_bitplanes, k_strip_index, k_pile_fast, k_hard_cells, k_fast_sites
-TRAFFIC_BYTES_PER_LAUNCH = 100.3e6 + 1112.9e6 + 491.2e6 + 730.7e6 + 30.8e6
+# capture profiles/r1_pl_stage_raw.txt: k_pile_fast, the cell-list scan, k_hard_cells, k_fast_sites
+TRAFFIC_BYTES_PER_LAUNCH = 486.7e6 + 7.0e6 + 1370.8e6 + 30.8e6
 WIN = 10000
 READ_LEN = 100
 DEPTH = 30.0
@@ -303,10 +304,10 @@ def run_b200(args):
                 "h2d_bytes_per_step": sum(s["h2d"] for s in shards), "d2h_bytes_per_step": int(d2h),
                 "windows_per_s": world * n_windows / (e2e_s / args.steps)},
         "gpu_launches": int(launches),
-        "stage_ms_per_shard": {k: v / len(shards) for k, v in zip(["prep_encode_partition", "pileup_call_site", "window_compaction", "window_stats"], stage_ms)},
-        "roofline": {"kernel": "pileup/call/site stage: k_bitplanes + k_pile_fast + k_hard_cells + k_fast_sites (k_strip_index beside them)", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "stage_ms_per_shard": {k: v / len(shards) for k, v in zip(["prep_planes_partition", "pileup_call_site", "window_compaction", "window_stats"], stage_ms)},
+        "roofline": {"kernel": "pileup/call/site stage: k_pile_fast + k_hard_cells + k_fast_sites", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": TRAFFIC_BYTES_PER_LAUNCH if abs(shard_len - 2300000) < 1 else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels, one ncu --set full capture on a 2.3 Mb shard (profiles/r1_bs_stage_raw.txt)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels, one ncu --set full capture on a 2.3 Mb shard (profiles/r1_pl_stage_raw.txt)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": alg_bytes / len(shards), "launch_ms": pile_s * 1e3 / len(shards),
                      "kernel_share_of_step": pile_s / (seq_ms / 1e3),

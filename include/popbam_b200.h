@@ -217,8 +217,9 @@ int pb_region_relaunch(pb_ctx *ctx);
 void *pb_stream(pb_ctx *ctx);                   /* cudaStream_t the kernels run on        */
 int64_t pb_kernel_launches(const pb_ctx *ctx);  /* kernels launched since pb_create       */
 /* CUDA-event durations (ms) of the last region's stages, valid after pb_region_wait:
- * [0] per-read preparation + sample partition, [1] the pileup/call/site kernel,
- * [2] window compaction, [3] window statistics.                                            */
+ * [0] preparation: per-read pass, quality levels, sample partition, and the per-base pass
+ *     (bit-planes, or base codes for the single-kernel pileup),
+ * [1] the pileup / call / site stage, [2] window compaction, [3] window statistics.        */
 int pb_stage_times(const pb_ctx *ctx, double *ms4);
 
 /* ---- helpers that mirror small reference routines ------------------------------------- */

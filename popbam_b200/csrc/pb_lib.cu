@@ -78,7 +78,7 @@ struct pb_ctx {
     std::vector<uint32_t> r_meta, r_cig_off, r_cigar, r_base_off;
     std::vector<uint8_t> r_seq4, r_qual;
     // timing of the last pipeline run
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // second stream: the per-read chain (prep, depth bound, sample partition, strip index) runs beside the per-base
     // chain (quality mask, encode, bit-planes); fk[] = fork / join events (no timing)
     cudaStream_t stream2 = nullptr;
@@ -320,7 +320,7 @@ int run_pipeline(pb_ctx *c) {
     pa.rms_thr = dp<int32_t>(c->d_rms_thr);
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
-    PB_CUDA(c, cudaEventRecord(c->ev[2], st));
+    PB_CUDA(c, cudaEventRecord(c->ev[6], st));     // the per-base pass (planes or codes) counts as preparation: ev[6] .. ev[2]
     // Bit-sliced path (pb_fast.cuh) when the depth cap cannot bind, nobody wants the per-cell words, and an
     // empty cell is simply "not covered" (min_depth, min_snpQ > 0); k_pileup_call otherwise.
     const int fast_w = pb_fast_words(c->ctr_host.max_span);
@@ -352,6 +352,7 @@ int run_pipeline(pb_ctx *c) {
         k_planes<<<c->g_bitplanes, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base), dp<uint8_t>(c->d_seq4),
                                                  dp<uint8_t>(c->d_qual), c->n_bytes, (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ,
                                                  P.min_baseQ, illumina, ctr, dp<PbFastParams>(c->d_fastp), pl);
+        PB_CUDA(c, cudaEventRecord(c->ev[2], st));
         PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[4], 0));
         PbFastArgs fa;
         fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.M = fM; fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
@@ -391,6 +392,7 @@ int run_pipeline(pb_ctx *c) {
                                                   dp<uint8_t>(c->d_seq4), dp<uint8_t>(c->d_qual), c->n_bytes,
                                                   (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ, dp<uint8_t>(c->d_qtab),
                                                   dp<uint8_t>(c->d_codes));
+        PB_CUDA(c, cudaEventRecord(c->ev[2], st));
         kern<<<nblk(span, tp), tp, smem, st>>>(pa);
         c->launches += 2;
     }
@@ -517,6 +519,7 @@ int fill_result(pb_ctx *c, pb_region_result *out) {
     const int n = P.n_samples, NW = c->nw;
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaEventElapsedTime(&c->ms_prep, c->ev[0], c->ev[1]);
+    { float per_base = 0; cudaEventElapsedTime(&per_base, c->ev[6], c->ev[2]); c->ms_prep += per_base; }
     cudaEventElapsedTime(&c->ms_pileup, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&c->ms_sites, c->ev[3], c->ev[4]);
     cudaEventElapsedTime(&c->ms_stats, c->ev[4], c->ev[5]);
