@@ -39,7 +39,7 @@ import numpy as np  # noqa: E402
 
 # DRAM bytes (read + written) of the pileup stage's kernels on a 2.3 Mb shard of this workload, from the committed ncu
 # capture profiles/r1_pl_stage_raw.txt: k_pile_fast, the cell-list scan, k_hard_cells, k_fast_sites
-TRAFFIC_BYTES_PER_LAUNCH = 486.7e6 + 7.0e6 + 1370.8e6 + 30.8e6
+TRAFFIC_BYTES_PER_LAUNCH = 489.9e6 + 6.3e6 + 1373.4e6 + 30.8e6
 WIN = 10000
 READ_LEN = 100
 DEPTH = 30.0

@@ -1,24 +1,26 @@
-// pb_fast.cuh -- bit-sliced fast path of the pileup for the overwhelming majority of cells, and the
-// per-cell path for the rest.  Used when the raw-depth cap cannot bind (k_depth_bound), the caller did
-// not ask for the per-(site,sample) words, and min_depth / min_snpQ are positive.
+// pb_fast.cuh -- the bit-sliced pileup: the default formulation of the pileup / call / site stage.
+// Used when the raw-depth cap cannot bind (k_depth_bound), the caller did not ask for the
+// per-(site,sample) words, and min_depth / min_snpQ are positive; k_pileup_call otherwise.
 //
 // Why.  k_pileup_call spends ~29 warp instructions per (record, 32 positions): one code load, one
-// histogram update, one total per LANE per record.  But ~92 % of the cells are "easy": every passing
-// base equals the reference base and the depth alone proves the shortcut of pb_walk.cuh
-// (pb_need_entry), so the cell is homozygous reference and all the site needs from it is qfilter's
-// coverage bit (pop_utils.cpp:102-120).  For such cells nothing per base has to be looked at one by
-// one: with the bases' properties stored as BIT-PLANES (one bit per base), a single THREAD handles
-// 32 positions of one sample with 32-bit logic ops:
-//     planes (k_bitplanes, parallel to codes[]):  P passing base, B0/B1 its two base bits, H quality level >= hi
+// histogram update, one total per LANE per record.  But ~97 % of the cells are "easy": every passing
+// base equals the reference base (or all but one do) and the depth alone proves that call_base would
+// call the cell homozygous reference (pb_need_entry, pb_one_stray_entry in pb_walk.cuh), so all the
+// site needs from the cell is qfilter's coverage bit (pop_utils.cpp:102-120).  For such cells nothing
+// per base has to be looked at one by one: with the bases' properties stored as BIT-PLANES (one bit per
+// base), a single THREAD handles 32 positions of one sample with 32-bit logic operations:
+//     planes (k_planes, from qual[] / seq4[]):  P passing base, B0/B1 its two base bits, H quality level >= hi
 //     per record:  window = funnel-shift of the planes to the strip, masked to the segment
-//                  mismatch |= P & ((B0 ^ R0) | (B1 ^ R1))         (R: the reference strip's planes)
-//                  lowq     |= P when the read's mapQ < min_rmsQ   (else rms >= min_rmsQ is guaranteed)
+//                  stray    = P & ((B0 ^ R0) | (B1 ^ R1))          (R: the reference strip's planes), counted 0 / 1 / 2+
+//                  lowq    |= P when the read's mapQ < min_rmsQ    (else rms >= min_rmsQ is guaranteed)
 //                  k  += P,  khi += H    as bit-sliced counters (half-adder chains over 6 / 4 planes)
-//     per strip:   easy = no mismatch, no lowq, k in the range where need[0][k] <= k, or khi >= Hmin ...
+//     per strip:   easy = no lowq, and (no stray base, k or khi in a proven range) or (one stray base, k in a proven range)
 // i.e. ~70 thread instructions per record for 32 cells instead of ~29 warp instructions (928 thread
-// slots).  The remaining cells (a sequencing error, a variant, a low-mapQ read, an odd depth) are
-// listed in bit masks and called one cell per thread by k_hard_cells with the exact machinery of
+// slots).  The remaining cells (two stray bases, a variant, a low-mapQ read, an odd depth) are listed
+// in bit masks and called one cell per thread by k_hard_cells with the exact machinery of
 // pb_cell.cuh / pb_walk.cuh; k_fast_sites puts the two together into the per-site result.
+// Kernels: k_ref_planes (per contig), k_fast_params (per level set), k_planes, k_strip_index,
+// k_pile_fast, k_hard_cells, k_fast_sites.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -264,6 +266,7 @@ struct PbFastArgs {
     int n_samples, n_strips, n_sblocks;      // n_sblocks = strip blocks of PB_FAST_STRIPS strips
     int min_depth, min_rmsQ;
     int W;                                   // plane elements staged per record: covers 31 + the longest segment
+    int max_span;                            // longest reference span of a kept read
     const PbCounters *ctr;
     const PbFastParams *fp;
     uint32_t *cov32, *hard32;                // [n_samples][n_strips]
@@ -329,7 +332,10 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
         }
         __syncthreads();
         if (live) {
-            const int lo = (int)(max(my_lo, c0) - c0), j1 = (int)min((uint32_t)cnt, max(my_hi, c0) - c0);
+            int lo = (int)(max(my_lo, c0) - c0);
+            const int j1 = (int)min((uint32_t)cnt, max(my_hi, c0) - c0);
+            // the strip index is 32 positions coarse: step over the leading records whose read ends before the strip
+            while (lo < j1 && recS[lo].w + a.max_span <= S) ++lo;
             for (int j = lo + g; j < j1; j += PB_FAST_G) {
                 const int4 r = recS[j];
                 const uint32_t z = (uint32_t)r.y;

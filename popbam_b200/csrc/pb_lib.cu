@@ -360,7 +360,7 @@ int run_pipeline(pb_ctx *c) {
         fa.r0 = rp; fa.r1 = rp + rpw; fa.rv = rp + 2 * rpw;
         fa.ref_len = c->ref_len; fa.span_beg = c->span_beg; fa.span_end = c->span_end;
         fa.n_samples = n; fa.n_strips = n_strips; fa.n_sblocks = (n_strips + PB_FAST_STRIPS - 1) / PB_FAST_STRIPS;
-        fa.W = fast_w;
+        fa.W = fast_w; fa.max_span = c->ctr_host.max_span;
         fa.min_depth = P.min_depth; fa.min_rmsQ = P.min_rmsQ;
         fa.ctr = ctr; fa.fp = dp<PbFastParams>(c->d_fastp);
         fa.cov32 = dp<uint32_t>(c->d_cov32); fa.hard32 = fa.cov32 + (size_t)n * n_strips; fa.hcount = fa.hard32 + (size_t)n * n_strips;
