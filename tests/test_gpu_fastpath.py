@@ -44,6 +44,13 @@ def _ctx(fx, p, an, wb, we, classic):
     # 64 samples: both halves of the 64-bit site masks, sparse coverage (empty cells, strips without records)
     ("n64_sparse", dict(contig_len=6000, n_ingroup=63, has_outgroup=1, depth=14.0, snp_density=0.05, het_frac=0.2, seed=47),
      dict(min_depth=2)),
+    # Illumina-1.3 qualities (-i): the packed quality thresholds of k_planes are offset by 31
+    ("illumina", dict(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=24.0, snp_density=0.03, seed=49),
+     dict(flags=pbtest.FLAG["ILLUMINA"], min_baseQ=4)),
+    # odd read length (padding nibble / byte after every read), two read groups per sample
+    ("odd_rg2", dict(contig_len=9000, n_ingroup=4, has_outgroup=1, rg_per_sample=2, depth=12.0, read_len=75, snp_density=0.03, seed=50), {}),
+    # base-quality threshold above every quality value but the two highest
+    ("baseq", dict(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=40.0, snp_density=0.03, seed=51), dict(min_baseQ=33)),
     # heterozygote mode
     ("het", dict(contig_len=9000, n_ingroup=6, has_outgroup=1, depth=28.0, snp_density=0.05, het_frac=0.6, seed=48),
      dict(flags=pbtest.FLAG["HETEROZYGOTE"])),
