@@ -26,6 +26,8 @@
 #include <stdint.h>
 #include "pb_kernels.cuh"
 
+#define PB_H_QUALITY 30            // quality value of the H plane
+
 struct PbFastParams {        // derived from the need table (k_fast_params), cached with it
     int k0lo, k0hi;          // for k0lo <= k <= k0hi: need[0][k] != 0 and need[0][k] <= k  (the depth alone suffices)
     int k1lo, k1hi, hmin;    // for k1lo <= k <= k1hi: need[hi][k] != 0 and <= hmin <= 15   (khi >= hmin suffices)
@@ -48,11 +50,11 @@ struct PbFastParams {        // derived from the need table (k_fast_params), cac
 #define PB_PLANE_PAD 16
 #define PB_PL_CHUNK 64
 __device__ __forceinline__ uint32_t pb_ge4(uint32_t w, uint32_t add) { return ((((w & 0x7f7f7f7fu) + add) | w) & 0x80808080u) * 0x00204081u >> 28; }
-__global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__restrict__ meta, const uint8_t *__restrict__ rkey,
+__global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__restrict__ meta, int n_samples,
                                                 const uint64_t *__restrict__ base, const uint8_t *__restrict__ seq4,
                                                 const uint8_t *__restrict__ qual, int64_t n_bytes, double reads_per_byte,
-                                                int min_mapQ, int min_baseQ, int illumina, const PbCounters *__restrict__ ctr,
-                                                const PbFastParams *__restrict__ fp, uint4 *__restrict__ planes) {
+                                                int min_mapQ, int min_baseQ, int illumina, PbCounters *__restrict__ ctr,
+                                                uint4 *__restrict__ planes) {
     // seq4 byte -> valid bits 0-1, B0 bits 8-9, B1 bits 16-17 of its two bases (high nibble = first base = lower bit)
     __shared__ uint32_t seq_s[256];
     {
@@ -60,17 +62,23 @@ __global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__res
         const uint32_t v0 = n0 < 4u, v1 = n1 < 4u;
         seq_s[threadIdx.x] = v0 | v1 << 1 | (v0 & n0 & 1u) << 8 | (v1 & n1 & 1u) << 9 | (v0 & (n0 >> 1) & 1u) << 16 | (v1 & (n1 >> 1) & 1u) << 17;
     }
+    // which raw quality values occur (k_level_table builds the region's quality levels from them): one flag per value
+    __shared__ uint8_t seen[256];
+    seen[threadIdx.x] = 0;
     __syncthreads();
-    const int hi = fp->hi_level, nl = ctr->n_levels;
-    const int qv = hi < nl ? (int)ctr->qval[hi] : 256;                                  // quality value of the H plane's level
+    const int qv = PB_H_QUALITY;                                                        // quality value of the H plane
     const int tp = min_baseQ <= 0 ? 0 : min_baseQ + (illumina ? 31 : 0);                // raw quality byte thresholds (host: tp <= 128)
     const int th = min(128, qv + (illumina ? 31 : 0));
     const uint32_t addP = (uint32_t)(128 - tp) * 0x01010101u, addH = (uint32_t)(128 - th) * 0x01010101u;
-    // per-read conditions: bit 0 alive (kept, mapQ >= min_mapQ), bit 1 mapQ >= qv
+    // per-read conditions from meta alone (so this pass does not wait for k_read_prep): bit 0 alive -- not flagged
+    // 0x704 (bam_pileup.c:371-374), a listed sample, mapQ >= min_mapQ -- bit 1 mapQ >= qv.  A read without reference span
+    // is dropped by k_read_prep as well, but no segment record points at its bases, so its bits are never looked at.
     auto flags_of = [&](int64_t rr) -> uint32_t {
-        if (rr >= n || rkey[rr] == PB_KEY_DROP) return 0u;
-        const int mq = (int)((__ldg(meta + rr) >> 8) & 0xffu);
-        return mq >= min_mapQ ? (1u | (min(mq, 63) >= qv ? 2u : 0u)) : 0u;
+        if (rr >= n) return 0u;
+        const uint32_t m = __ldg(meta + rr);
+        const int mq = (int)((m >> 8) & 0xffu);
+        if (((m >> 16) & 0x704u) || (m & 0xffu) >= (uint32_t)n_samples || mq < min_mapQ) return 0u;
+        return 1u | (min(mq, 63) >= qv ? 2u : 0u);
     };
     const int64_t n_chunks = (n_bytes + PB_PL_CHUNK - 1) / PB_PL_CHUNK;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_chunks; t += (int64_t)gridDim.x * blockDim.x) {
@@ -101,6 +109,8 @@ __global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__res
             for (int g = 0; g < 16; ++g) {
                 P[g >> 3] |= pb_ge4(qw[g], addP) << (4 * (g & 7));
                 H[g >> 3] |= pb_ge4(qw[g], addH) << (4 * (g & 7));
+#pragma unroll
+                for (int b = 0; b < 4; ++b) seen[(qw[g] >> (8 * b)) & 0xffu] = 1;
             }
             uint32_t V[2] = {0, 0};
 #pragma unroll
@@ -133,6 +143,7 @@ __global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__res
                     f = flags_of(rr);
                 }
                 const uint32_t q = qual[o + i];
+                seen[q] = 1;
                 const uint32_t sbyte = seq4[(o + i) >> 1];
                 const uint32_t nib = ((o + i) & 1) ? (sbyte & 15u) : (sbyte >> 4);
                 const uint32_t nt = (uint32_t)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
@@ -141,7 +152,7 @@ __global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__res
                 P[i >> 5] |= bit;
                 if (nt & 1u) B0[i >> 5] |= bit;
                 if (nt & 2u) B1[i >> 5] |= bit;
-                if ((f & 2u) && (int)q >= th && qv <= 63) H[i >> 5] |= bit;
+                if ((f & 2u) && (int)q >= th) H[i >> 5] |= bit;
             }
         }
         planes[2 * t + 1] = make_uint4(P[0], B0[0], B1[0], H[0]);
@@ -152,6 +163,16 @@ __global__ void __launch_bounds__(256) k_planes(int64_t n, const uint32_t *__res
         const int64_t i = threadIdx.x ? n_words + threadIdx.x : 0;
         planes[i] = make_uint4(0, 0, 0, 0);
     }
+    __syncthreads();
+    // one thread per raw quality value: transform, filter, clamp (as k_qual_mask)
+    unsigned long long mask = 0;
+    if (seen[threadIdx.x]) {
+        int q = (int)threadIdx.x;
+        if (illumina) q = q > 31 ? q - 31 : 0;
+        if (q >= min_baseQ) mask = 1ULL << (q > 63 ? 63 : q);
+    }
+    for (int o = 16; o > 0; o >>= 1) mask |= __shfl_xor_sync(0xffffffffu, mask, o);
+    if ((threadIdx.x & 31) == 0 && mask) atomicOr(&ctr->qual_mask, mask);
 }
 
 // ---- reference planes of a contig: R0/R1 = the two bits of A/C/G/T, RV = the byte is an upper-case A/C/G/T
@@ -198,17 +219,17 @@ __global__ void __launch_bounds__(64) k_fast_params(const PbCounters *__restrict
         if (k - start > k0hi - k0lo + 1) { k0lo = start; k0hi = k - 1; }
         start = k + 1;
     }
-    int hi = nl, k1lo = 1, k1hi = 0, hmin = 0;
-    for (int L = 1; L < nl && hi == nl && k0hi < 63; ++L) {
-        // a run of usable depths that starts at or below k0hi + 1
-        int lo = k0hi + 1, mx = 0;
-        const int nd0 = need[L * 256 + lo];
-        if (!nd0 || nd0 > 15) continue;
-        int k = lo;
-        for (; k <= 63; ++k) { const int nd = need[L * 256 + k]; if (!nd || nd > 15) break; mx = max(mx, nd); }
-        if (k - 1 < min(63, k0hi + 8)) continue;
-        while (lo > 1) { const int nd = need[L * 256 + lo - 1]; if (!nd || nd > mx) break; --lo; }
-        hi = L; k1lo = lo; k1hi = k - 1; hmin = mx;
+    // the H plane holds "quality >= PB_H_QUALITY" (k_planes runs before the level table exists): its level is the first
+    // one at or above that value, usable for the run of depths above k0hi whose entries stay <= 15
+    int hi = 0, k1lo = 1, k1hi = 0, hmin = 0;
+    while (hi < nl && (int)ctr->qval[hi] < PB_H_QUALITY) ++hi;
+    if (hi < nl && k0hi < 63) {
+        int lo = k0hi + 1, mx = 0, k = lo;
+        for (; k <= 63; ++k) { const int nd = need[hi * 256 + k]; if (!nd || nd > 15) break; mx = max(mx, nd); }
+        if (k > lo) {
+            while (lo > 1) { const int nd = need[hi * 256 + lo - 1]; if (!nd || nd > mx) break; --lo; }
+            k1lo = lo; k1hi = k - 1; hmin = mx;
+        }
     }
     fp->k0lo = k0lo; fp->k0hi = k0hi; fp->k1lo = k1lo; fp->k1hi = k1hi; fp->hmin = hmin; fp->hi_level = hi;
 }
@@ -230,8 +251,11 @@ __device__ __forceinline__ uint32_t pb_bs_le6(const uint32_t c[6], int C) {
 // cover strip t (positions S .. S+31, S = span_beg + 32 t) are then [F[s][t], F[s][t + M + 1]) -- a superset of
 // "read start in (S - max_span, S + 31]" found without any search.  One thread per record writes the entries
 // whose boundary falls between its predecessor's start and its own.
+// Runs before the host has seen max_span: M comes from the device counters and NI is sized for the largest M.
+#define PB_SIDX_MMAX 2048          // 65536 / 32: reads span fewer than 65536 reference bases
 __global__ void __launch_bounds__(256) k_strip_index(const int4 *__restrict__ srec, const uint32_t *__restrict__ sstart, int n_samples,
-                                                     int span_beg, int M, int NI, uint32_t *__restrict__ F) {
+                                                     int span_beg, const PbCounters *__restrict__ ctr, int NI, uint32_t *__restrict__ F) {
+    const int M = (ctr->max_span + 31) >> 5;
     __shared__ uint32_t ss[PB_MAX_SAMPLES + 1];
     if (threadIdx.x <= n_samples) ss[threadIdx.x] = sstart[threadIdx.x];
     __syncthreads();

@@ -70,11 +70,13 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
         const uint32_t c0 = cigstart[r], nc = ncig[r];
         int x = p, al = 0, nseg = 0;
         bool longseg = false;
+        // branch-free per operation (most reads have one, a few have five: the warp runs the longest list):
+        // M = X consume reference and query (bits 0, 7, 8 of the class masks), D N consume reference (bits 2, 3)
         for (uint32_t i = 0; i < nc; ++i) {
             const uint32_t c = __ldg(cigar + c0 + i);
             const int op = c & 15, len = (int)(c >> 4);
-            if (op == 0 || op == 7 || op == 8) { x += len; al += len; nseg += len > 0; longseg |= len > 65535; }
-            else if (op == 2 || op == 3) x += len;
+            const int aln = (0x181 >> op) & 1, ref = (0x18d >> op) & 1;
+            x += len & -ref; al += len & -aln; nseg += aln & (len > 0); longseg |= (aln & (len > 65535)) != 0;
         }
         const bool keep = !((m >> 16) & 0x704u) && x > p;
         const uint32_t smp = m & 0xffu;
@@ -392,8 +394,14 @@ __global__ void __launch_bounds__(128) k_part_scatter(int64_t n, const uint8_t *
         const uint32_t peers = __match_any_sync(0xffffffffu, key);
         nsw[lane] = ns;
         __syncwarp();
-        uint32_t rank = 0;
-        for (uint32_t m = peers & ((1u << lane) - 1u); m; m &= m - 1) rank += nsw[__ffs(m) - 1];
+        // = number of earlier lanes with my key that emit a record, plus the extra records of the few reads with several
+        // segments (a warp-uniform loop over those lanes instead of a per-lane loop over peers)
+        const uint32_t lower = peers & ((1u << lane) - 1u);
+        uint32_t rank = (uint32_t)__popc(lower & __ballot_sync(0xffffffffu, ns > 0));
+        for (uint32_t multi = __ballot_sync(0xffffffffu, ns > 1); multi; multi &= multi - 1) {
+            const int j = __ffs(multi) - 1;
+            if ((lower >> j) & 1u) rank += nsw[j] - 1;
+        }
         const uint32_t mine = key != PB_KEY_DROP ? cur[key] : 0u;
         __syncwarp();
         if (key != PB_KEY_DROP && (peers >> lane) == 1u) cur[key] = mine + rank + ns;     // the group's last lane advances the cursor

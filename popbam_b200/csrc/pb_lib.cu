@@ -83,6 +83,7 @@ struct pb_ctx {
     // chain (quality mask, encode, bit-planes); fk[] = fork / join events (no timing)
     cudaStream_t stream2 = nullptr;
     cudaEvent_t fk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};   // POPBAM_B200_DEBUG: timeline of the two prep chains
     float ms_prep = 0, ms_pileup = 0, ms_sites = 0, ms_stats = 0;
 };
 
@@ -241,6 +242,7 @@ int run_pipeline(pb_ctx *c) {
         c->launches += 1;
     }
     PB_CUDA(c, cudaEventRecord(c->fk[1], s2));                      // rkey, mapq mask, max_span
+    if (c->dbg[0]) cudaEventRecord(c->dbg[0], s2);
     if (N > 0) {
         k_depth_bound<<<c->n_sms * 4, 256, 0, s2>>>(dp<uint32_t>(c->d_bins), n, n_bins, P.max_depth, ctr);
         c->launches += 1;
@@ -257,9 +259,35 @@ int run_pipeline(pb_ctx *c) {
                                                dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
                                                dp<int4>(c->d_srec));
     c->launches += 2;
+    // (decided below as `planes_early`) the bit-sliced path's strip index and zeroed accumulators, still on the per-read stream
+    const bool planes_early = !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && N > 0 &&
+                              P.min_baseQ + (illumina ? 31 : 0) <= 128;
+    const int n_strips = (int)((span + 31) >> 5), fNI = n_strips + PB_SIDX_MMAX + 2;
+    PB_TRY(dev_reserve(c, c->d_site_type, sizeof(uint64_t) * (size_t)span));
+    if (planes_early) {
+        PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
+        PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
+        k_strip_index<<<c->g_strip_index, 256, 0, s2>>>(dp<int4>(c->d_srec), dp<uint32_t>(c->d_sstart), n, c->span_beg, ctr, fNI, dp<uint32_t>(c->d_sidx));
+        PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, s2));
+        PB_CUDA(c, cudaMemsetAsync(c->d_site_type.p, 0, sizeof(uint64_t) * (size_t)span, s2));
+        c->launches += 1;
+    }
     PB_CUDA(c, cudaEventRecord(c->fk[2], s2));
+    if (c->dbg[1]) cudaEventRecord(c->dbg[1], s2);
+    if (c->dbg[2]) cudaEventRecord(c->dbg[2], st);
     // -- per-base chain on the main stream: quality values present, level table, base codes
-    if (N > 0) {
+    // The bit-planes of the default pileup path are built here, before the host knows whether that path will be
+    // taken (it needs the depth bound): the pass also collects the quality values present, which the single-kernel
+    // path gets from k_qual_mask.  Wasted only when the depth cap turns out to bind.
+    if (planes_early) {
+        const size_t plw = (size_t)((c->n_bytes + 31) >> 5) + 1 + PB_PLANE_PAD;
+        PB_TRY(dev_reserve(c, c->d_planes, sizeof(uint4) * plw));
+        k_planes<<<c->g_bitplanes, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), n, dp<uint64_t>(c->d_base), dp<uint8_t>(c->d_seq4),
+                                                 dp<uint8_t>(c->d_qual), c->n_bytes, (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ,
+                                                 P.min_baseQ, illumina, ctr, dp<uint4>(c->d_planes));
+        if (c->dbg[3]) cudaEventRecord(c->dbg[3], st);
+        c->launches += 1;
+    } else if (N > 0) {
         k_qual_mask<<<c->g_qual_mask, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
         c->launches += 1;
     }
@@ -278,11 +306,17 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaEventRecord(c->ev[1], st));
     PB_CUDA(c, cudaStreamSynchronize(st));
     c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
+    if (c->dbg[0] && planes_early) {
+        float t[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->ev[0], c->dbg[i]);
+        cudaEventElapsedTime(&t[4], c->ev[0], c->ev[1]);
+        fprintf(stderr, "[popbam_b200] prep timeline (ms after start): read_prep done %.3f, per-read chain done %.3f | planes start %.3f, planes done %.3f | prep done %.3f\n",
+                t[0], t[1], t[2], t[3], t[4]);
+    }
     if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
     if (c->ctr_host.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
 
     // ---- the hot kernel
-    PB_TRY(dev_reserve(c, c->d_site_type, sizeof(uint64_t) * (size_t)span));
     PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
     if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
     const int nl = c->ctr_host.n_levels;
@@ -324,36 +358,20 @@ int run_pipeline(pb_ctx *c) {
     // Bit-sliced path (pb_fast.cuh) when the depth cap cannot bind, nobody wants the per-cell words, and an
     // empty cell is simply "not covered" (min_depth, min_snpQ > 0); k_pileup_call otherwise.
     const int fast_w = pb_fast_words(c->ctr_host.max_span);
-    const bool fast = !cap && !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && N > 0 &&
+    const bool fast = !cap && planes_early &&
                       pb_hard_smem(nl) <= c->smem_optin && span * n < (int64_t)0x7fffffff && fast_w <= PB_PLANE_PAD &&
-                      pb_fast_smem(fast_w) <= 100 * 1024 && P.min_baseQ + (illumina ? 31 : 0) <= 128;
+                      pb_fast_smem(fast_w) <= 100 * 1024;
     if (getenv("POPBAM_B200_DEBUG"))
         fprintf(stderr, "[popbam_b200] pileup path: fast=%d cap=%d want_cb=%d min_depth=%d min_snpQ=%d classic=%d N=%lld nl=%d hard_smem=%zu optin=%zu fast_w=%d fast_smem=%zu depth_bound=%d max_span=%d\n",
                 (int)fast, (int)cap, (int)want_cb, P.min_depth, P.min_snpQ, (int)c->classic, (long long)N, nl, pb_hard_smem(nl), c->smem_optin,
                 fast_w, pb_fast_smem(fast_w), c->ctr_host.depth_bound, c->ctr_host.max_span);
     if (fast) {
-        const int n_strips = (int)((span + 31) >> 5);
-        const size_t plw = (size_t)((c->n_bytes + 31) >> 5) + 1 + PB_PLANE_PAD;
-        PB_TRY(dev_reserve(c, c->d_planes, sizeof(uint4) * plw));
         PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * (3 * (size_t)n * n_strips + 1)));
-        const int fM = (c->ctr_host.max_span + 31) >> 5, fNI = n_strips + fM + 2;
-        PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
-        PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
-        // the strip index and the zeroing of the accumulators run beside the bit-plane pass
-        PB_CUDA(c, cudaEventRecord(c->fk[3], st));
-        PB_CUDA(c, cudaStreamWaitEvent(c->stream2, c->fk[3], 0));
-        k_strip_index<<<c->g_strip_index, 256, 0, c->stream2>>>(pa.srec, pa.sstart, n, c->span_beg, fM, fNI, dp<uint32_t>(c->d_sidx));
-        PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, c->stream2));
-        PB_CUDA(c, cudaMemsetAsync(pa.site_type, 0, sizeof(uint64_t) * (size_t)span, c->stream2));
-        PB_CUDA(c, cudaEventRecord(c->fk[4], c->stream2));
+        const int fM = (c->ctr_host.max_span + 31) >> 5;
         uint4 *pl = dp<uint4>(c->d_planes);
         const size_t rpw = (size_t)((c->ref_len + 31) >> 5) + 2;
         const uint32_t *rp = dp<uint32_t>(c->d_refpl);
-        k_planes<<<c->g_bitplanes, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), dp<uint8_t>(c->d_rkey), dp<uint64_t>(c->d_base), dp<uint8_t>(c->d_seq4),
-                                                 dp<uint8_t>(c->d_qual), c->n_bytes, (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ,
-                                                 P.min_baseQ, illumina, ctr, dp<PbFastParams>(c->d_fastp), pl);
         PB_CUDA(c, cudaEventRecord(c->ev[2], st));
-        PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[4], 0));
         PbFastArgs fa;
         fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.M = fM; fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
         fa.planes = pl;
@@ -382,7 +400,7 @@ int run_pipeline(pb_ctx *c) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hard_per_sm, k_hard_cells, PB_HARD_THREADS, hsm) != cudaSuccess || hard_per_sm < 1) { cudaGetLastError(); hard_per_sm = 1; }
         k_hard_cells<<<c->n_sms * hard_per_sm, PB_HARD_THREADS, hsm, st>>>(ha);
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
-        c->launches += 5;
+        c->launches += 3;
     } else {
         // base codes for k_pileup_call (the bit-sliced path reads qual[] / seq4[] directly)
         PB_TRY(dev_reserve(c, c->d_codes, (size_t)std::max<int64_t>(c->n_bytes, 1)));
@@ -612,7 +630,8 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
             return c->n_sms * per_sm;
         };
-        c->g_encode = wave(k_encode, 256); c->g_bitplanes = wave(k_planes, 256); c->g_qual_mask = wave(k_qual_mask, 256);
+        c->g_encode = wave(k_encode, 256);
+        c->g_bitplanes = std::max(c->n_sms, wave(k_planes, 256) - c->n_sms);     // one CTA slot per SM left to the per-read chain on the second stream c->g_qual_mask = wave(k_qual_mask, 256);
         c->g_read_prep = wave(k_read_prep, 256); c->g_strip_index = wave(k_strip_index, 256);
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
@@ -621,6 +640,8 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
     for (auto &ev : c->fk)
         if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
+    if (getenv("POPBAM_B200_DEBUG"))
+        for (auto &ev : c->dbg) cudaEventCreate(&ev);
     // error-model tables
     const double *pfk, *pbeta, *plhet;
     if (!own_tables) { pfk = tables->fk; pbeta = tables->beta; plhet = tables->lhet; }
@@ -656,6 +677,7 @@ void pb_destroy(pb_ctx *c) {
     for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->fk) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : c->dbg) if (ev) cudaEventDestroy(ev);
     if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
