@@ -55,7 +55,7 @@ def parse():
     ap.add_argument("--contig-mb", type=float, default=23.0)
     ap.add_argument("--shard-mb", type=float, default=2.3)
     ap.add_argument("--threads", type=int, default=0, help="generator threads (0 = auto)")
-    ap.add_argument("--inflight", type=int, default=2, help="region shards processed concurrently per GPU (one host thread and one context each)")
+    ap.add_argument("--inflight", type=int, default=4, help="region shards processed concurrently per GPU (one host thread and one context each)")
     ap.add_argument("--distinct-shards", type=int, default=0,
                     help="generate this many distinct shards and cycle them (0 = auto: all distinct when the host has >= 8 cores per rank)")
     ap.add_argument("--cpu-sample-kb", type=int, default=150)
