@@ -38,8 +38,9 @@ sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np  # noqa: E402
 
 # DRAM bytes (read + written) of the pileup stage's kernels on a 2.3 Mb shard of this workload, from the committed ncu
-# capture profiles/r1_pl_stage_raw.txt: k_pile_fast, the cell-list scan, k_hard_cells, k_fast_sites
-TRAFFIC_BYTES_PER_LAUNCH = 489.9e6 + 6.3e6 + 1373.4e6 + 30.8e6
+# launch list profiles/r1_end_launches.csv (dram__bytes_read.sum + dram__bytes_write.sum per kernel): k_pile_fast, the
+# cell-list scan, k_hard_cells, k_fast_sites
+TRAFFIC_BYTES_PER_LAUNCH = 486.1e6 + 6.4e6 + 1442.3e6 + 30.8e6
 WIN = 10000
 READ_LEN = 100
 DEPTH = 30.0
@@ -307,7 +308,7 @@ def run_b200(args):
         "stage_ms_per_shard": {k: v / len(shards) for k, v in zip(["prep_planes_partition", "pileup_call_site", "window_compaction", "window_stats"], stage_ms)},
         "roofline": {"kernel": "pileup/call/site stage: k_pile_fast + k_hard_cells + k_fast_sites", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": TRAFFIC_BYTES_PER_LAUNCH if abs(shard_len - 2300000) < 1 else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels, one ncu --set full capture on a 2.3 Mb shard (profiles/r1_pl_stage_raw.txt)",
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels, one ncu capture on a 2.3 Mb shard (profiles/r1_end_launches.csv)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback (B200_PROFILING.md)",
                      "algorithmic_bytes_per_launch": alg_bytes / len(shards), "launch_ms": pile_s * 1e3 / len(shards),
                      "kernel_share_of_step": pile_s / (seq_ms / 1e3),
