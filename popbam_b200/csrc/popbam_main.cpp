@@ -19,6 +19,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <mutex>
 #include <sstream>
 #include <string>
@@ -33,7 +34,8 @@ namespace {
 [[noreturn]] void fatal(const std::string &msg) {
     // fatal_error (pop_utils.cpp:510-519) without the source position of the reference's call site
     fprintf(stderr, "popbam runtime error:\n%s\nExiting program\n", msg.c_str());
-    exit(EXIT_FAILURE);
+    fflush(stdout);
+    _Exit(EXIT_FAILURE);       // the table-building thread may still be running: no static destructors
 }
 
 struct Options {
@@ -155,6 +157,9 @@ struct Run {
     std::vector<Shard> shards;
     pb_params prm;
     uint32_t analysis = 0;
+    // error-model tables, built once on the host (while the files are opened) and shared by every context
+    std::vector<double> fk, beta, lhet;
+    std::shared_future<void> tables_ready;
     std::mutex mu;
     std::condition_variable cv;
     std::atomic<int> next_decode{0};
@@ -180,13 +185,17 @@ void decode_worker(Run *R) {
     }
 }
 
-void gpu_worker(Run *R, int g, int G) {
+// worker w of W takes shards w, w + W, ...; several workers may share a device
+void gpu_worker(Run *R, int g, int G, int device) {
     pb_params prm = R->prm;
-    prm.device = g;
+    prm.device = device;
     int st = 0;
-    pb_ctx *ctx = pb_create(&prm, nullptr, &st);
+    R->tables_ready.wait();
+    pb_errmod_tables tb;
+    tb.fk = R->fk.data(); tb.beta = R->beta.data(); tb.lhet = R->lhet.data();
+    pb_ctx *ctx = pb_create(&prm, &tb, &st);
     std::string err;
-    if (!ctx) err = std::string("cannot initialise GPU ") + std::to_string(g) + ": " + pb_last_error(nullptr);
+    if (!ctx) err = std::string("cannot initialise GPU ") + std::to_string(device) + ": " + pb_last_error(nullptr);
     else if (pb_set_contig(ctx, R->tid, R->ref.data(), (int64_t)R->ref.size()) != PB_OK) err = pb_last_error(ctx);
     std::vector<const char *> pops, smps;
     for (auto &s : R->st.pops) pops.push_back(s.c_str());
@@ -291,6 +300,9 @@ int main(int argc, char **argv) {
     try {
         { std::ifstream t(bamfile); if (!t) fatal("Specified input file: " + bamfile + " does not exist"); }
         { std::ifstream t(o.reffile); if (!t) fatal("Specified reference file: " + o.reffile + " does not exist"); }
+        // the error-model tables take ~0.25 s of host arithmetic: build them while the files are opened and CUDA comes up
+        R.fk.resize(256); R.beta.resize((size_t)64 * 256 * 256); R.lhet.resize(65536);
+        R.tables_ready = std::async(std::launch::async, [&R]() { pb_build_errmod_tables(R.fk.data(), R.beta.data(), R.lhet.data()); }).share();
         R.bam.open(bamfile);
         R.hdr = pbio::read_header(R.bam);
         std::string text = R.hdr.text;
@@ -345,8 +357,11 @@ int main(int argc, char **argv) {
         w = e;
     }
     const int G = std::max(1, o.gpus);
-    const int D = o.threads > 0 ? o.threads : std::max(2u, std::min(16u, std::thread::hardware_concurrency()));
-    R.max_ahead = std::max(2 * G + 2, std::min(D, 8));
+    const int D = o.threads > 0 ? o.threads : std::max(2u, std::min(32u, std::thread::hardware_concurrency()));
+    // two contexts (host threads) per GPU: one shard's host->device copy runs beside another shard's kernels
+    const int W = 2 * G;
+    // every decode thread can have a shard in hand and one waiting (a decoded 50 kb shard of the bench workload is 34 MB)
+    R.max_ahead = std::max(2 * W + 2, 2 * D);
 
     if (o.cmd == "snp" && o.output == 2) {      // print_ms_header (pop_snp.cpp:305-317)
         printf("ms %d %lld -t 5.0 ", p.n_samples, (long long)nw);
@@ -359,7 +374,7 @@ int main(int argc, char **argv) {
 
     std::vector<std::thread> th;
     for (int i = 0; i < D; ++i) th.emplace_back(decode_worker, &R);
-    for (int g = 0; g < G; ++g) th.emplace_back(gpu_worker, &R, g, G);
+    for (int w = 0; w < W; ++w) th.emplace_back(gpu_worker, &R, w, W, w % G);
     int rc = 0;
     for (size_t s = 0; s < R.shards.size(); ++s) {
         Shard &sh = R.shards[s];
