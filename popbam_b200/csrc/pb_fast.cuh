@@ -23,6 +23,7 @@
 // k_pile_fast, k_hard_cells, k_fast_sites.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_pipeline.h>
 #include <stdint.h>
 #include "pb_kernels.cuh"
 
@@ -345,15 +346,12 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
             const int64_t gb = (int64_t)(((uint64_t)(z >> 26) << 32) | (uint32_t)rc.w) + 32;      // bit index of the segment's first base
             const uint4 *src = a.planes + (gb >> 5);
             recS[r] = make_int4(rc.y, rc.z, (int)(gb & 31), rc.x);
+            // asynchronous 16-byte copies global -> shared (no registers, no wait until the whole pass is issued)
             uint4 *dst = plS + (size_t)r * W;
-            for (int k0 = 0; k0 < W; k0 += 4) {               // four loads in flight
-                uint4 v[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) if (k0 + q < W) v[q] = __ldg(src + k0 + q);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) if (k0 + q < W) dst[k0 + q] = v[q];
-            }
+            for (int k = 0; k < W; ++k) __pipeline_memcpy_async(dst + k, src + k, 16);
         }
+        __pipeline_commit();
+        __pipeline_wait_prior(0);
         __syncthreads();
         if (live) {
             int lo = (int)(max(my_lo, c0) - c0);
