@@ -60,6 +60,7 @@ typedef enum pb_status {
 #define PB_AN_HAPLO_EHHS    0x100u  /* pop_haplo.cpp:256   calc_ehhs      (haplo -o 1)    */
 #define PB_AN_HAPLO_DXY     0x200u  /* pop_haplo.cpp:325   calc_minDxy    (haplo -o 2)    */
 #define PB_AN_SNP           0x400u  /* pop_snp.cpp:148     per-segregating-site rows      */
+#define PB_AN_TREE          0x800u  /* pop_tree.cpp:472    difference matrix incl. the reference taxon (tree) */
 
 /* Run parameters == the fields of popbamData the hot path reads (popbam.h:218-265) plus
  * the population tables assign_pops builds (popbam.cpp:145-171).                           */
@@ -169,6 +170,8 @@ typedef struct pb_region_result {
     int64_t  reads_pushed;        /* records received                                      */
     int64_t  reads_used;          /* after the 0x704 / tid / empty-cigar filter            */
     int64_t  aligned_bases;       /* sum of M/=/X lengths of used reads                    */
+    /* tree */
+    const uint16_t *tree_diff;    /* [NW*(n+1)*(n+1)] treeData::diff_matrix (pop_tree.cpp:472-494), taxon 0 = reference */
 } pb_region_result;
 
 typedef struct pb_ctx pb_ctx;
@@ -245,6 +248,7 @@ typedef struct pb_print_opts {
     int32_t min_snps;                 /* default 10 */
     int32_t jc;
     int32_t snp_output;
+    const char *ref_name;             /* tree: treeData::refid, the AS tag of the sequence dictionary (pop_utils.cpp:463) */
 } pb_print_opts;
 int64_t pb_format_window(const pb_ctx *ctx, const pb_region_result *res, int32_t window,
                          uint32_t analysis, const pb_print_opts *opts, char *buf, int64_t cap);

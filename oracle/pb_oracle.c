@@ -285,6 +285,25 @@ static void calc_diff(const pbo_params *p, const uint64_t *T, int S, uint16_t *d
         }
 }
 
+static void calc_tree_diff(const pbo_params *p, const uint64_t *T, int S, uint16_t *d /* (n+1)*(n+1) */) {
+    /* calc_diff_matrix of the tree subcommand (pop_tree.cpp:472-494): taxon 0 is the reference sequence, whose
+     * difference to sample i is the number of segregating sites where i carries the derived allele; samples among
+     * themselves as in calc_diff.  unsigned short, wraps.                                                       */
+    int n = p->n_samples, m = n + 1;
+    memset(d, 0, sizeof(uint16_t) * (size_t)m * m);
+    for (int i = 0; i < n; ++i) {
+        unsigned c = 0;
+        for (int s = 0; s < S; ++s) c += (unsigned)((T[s] >> i) & 1);
+        d[(i + 1) * m] = d[i + 1] = (uint16_t)c;
+    }
+    for (int i = 0; i < n - 1; ++i)
+        for (int j = i + 1; j < n; ++j) {
+            unsigned c = 0;
+            for (int s = 0; s < S; ++s) c += (unsigned)(((T[s] >> i) ^ (T[s] >> j)) & 1);
+            d[(j + 1) * m + i + 1] = d[(i + 1) * m + j + 1] = (uint16_t)c;
+        }
+}
+
 static void calc_nucdiv(const pbo_params *p, const uint16_t *diff, double *piw, double *pib, uint16_t *mind) {
     /* calc_nucdiv (pop_nucdiv.cpp:206-239) and calc_minDxy (pop_haplo.cpp:325-363) */
     int P = p->n_pops, n = p->n_samples;
@@ -583,6 +602,7 @@ int pbo_run_region(const pbo_params *p, const double *fk, const double *beta, co
     ALLOC(out->sfs_num_snps, int32_t, (int64_t)NW * P); ALLOC(out->td, double, (int64_t)NW * P); ALLOC(out->fwh, double, (int64_t)NW * P);
     ALLOC(out->ld_num_snps, int32_t, (int64_t)NW * P); ALLOC(out->zns, double, (int64_t)NW * P); ALLOC(out->omegamax, double, (int64_t)NW * P);
     ALLOC(out->wall_num_snps, int32_t, (int64_t)NW * P); ALLOC(out->wallb, double, (int64_t)NW * P); ALLOC(out->wallq, double, (int64_t)NW * P);
+    ALLOC(out->tree_diff, uint16_t, (int64_t)NW * (n + 1) * (n + 1));
     ALLOC(out->ind_div, uint16_t, (int64_t)NW * n); ALLOC(out->pop_div, uint16_t, (int64_t)NW * P); ALLOC(out->div_num_snps, int32_t, (int64_t)NW * P);
     ALLOC(out->nhaps, int32_t, (int64_t)NW * P); ALLOC(out->hdiv, double, (int64_t)NW * P); ALLOC(out->ehhs, double, (int64_t)NW * P);
     ALLOC(out->site_type, uint64_t, span); ALLOC(out->site_flag, uint8_t, span);
@@ -679,6 +699,7 @@ int pbo_run_region(const pbo_params *p, const double *fk, const double *beta, co
         const uint64_t *T = seg_type + out->seg_off[w];
         if (analyses & (PBO_AN_NUCDIV | PBO_AN_HAPLO_K | PBO_AN_HAPLO_EHHS | PBO_AN_HAPLO_DXY)) calc_diff(p, T, S, diff);
         if (analyses & (PBO_AN_NUCDIV | PBO_AN_HAPLO_DXY)) calc_nucdiv(p, diff, out->piw + (int64_t)w * P, out->pib + (int64_t)w * P * P, out->min_dxy + (int64_t)w * P * P);
+        if (analyses & PBO_AN_TREE) calc_tree_diff(p, T, S, out->tree_diff + (int64_t)w * (n + 1) * (n + 1));
         if (analyses & PBO_AN_SFS) calc_sfs(p, T, S, out->sfs_num_snps + (int64_t)w * P, out->td + (int64_t)w * P, out->fwh + (int64_t)w * P);
         if (analyses & PBO_AN_LD_ZNS) calc_zns(p, T, S, out->ld_num_snps + (int64_t)w * P, out->zns + (int64_t)w * P);
         if (analyses & PBO_AN_LD_OMEGA) calc_omegamax(p, T, S, out->ld_num_snps + (int64_t)w * P, out->omegamax + (int64_t)w * P);
@@ -700,6 +721,7 @@ void pbo_free_result(pbo_result *r) {
     free(r->seg_pos); free(r->seg_idx); free(r->seg_type); free(r->seg_ref); free(r->seg_cb);
     free(r->piw); free(r->pib); free(r->min_dxy); free(r->sfs_num_snps); free(r->td); free(r->fwh);
     free(r->ld_num_snps); free(r->zns); free(r->omegamax); free(r->wall_num_snps); free(r->wallb); free(r->wallq);
+    free(r->tree_diff);
     free(r->ind_div); free(r->pop_div); free(r->div_num_snps); free(r->nhaps); free(r->hdiv); free(r->ehhs);
     free(r->cb); free(r->site_type); free(r->site_flag);
     memset(r, 0, sizeof *r);
@@ -726,6 +748,112 @@ static void sb_printf(sbuf *s, const char *fmt, ...) {
 static void sb_stat(sbuf *s, const char *name, const char *pop, int ok, double v) {
     if (ok) sb_printf(s, "\t%s[%s]:\t%.5f", name, pop, v);
     else sb_printf(s, "\t%s[%s]:\t%7s", name, pop, "NA");
+}
+
+/* ---- neighbour joining of the tree subcommand (pop_tree.cpp:208-470), kept in the reference's own terms: a tip is a
+ * single node, an interior node a ring of three; a branch is a pair of nodes pointing at each other.            */
+typedef struct njnode { struct njnode *next, *back; int tip, index; double v; } njnode;
+
+static void nj_print(sbuf *s, const njnode *q, const njnode *start, const pbo_print_opts *o) {
+    /* print_tree (pop_tree.cpp:439-470) */
+    if (q->tip) sb_printf(s, "%s", q->index == 1 ? o->ref_name : o->sample_names[q->index - 2]);
+    else {
+        sb_printf(s, "(");
+        nj_print(s, q->next->back, start, o);
+        sb_printf(s, ",");
+        nj_print(s, q->next->next->back, start, o);
+        if (q == start) { sb_printf(s, ","); nj_print(s, q->back, start, o); }
+        sb_printf(s, ")");
+    }
+    if (q == start) sb_printf(s, ";\n");
+    else if (q->v < 0) sb_printf(s, ":0.00000");
+    else sb_printf(s, ":%.5f", q->v);
+}
+
+static void nj_link(njnode *a, njnode *b) { a->back = b; b->back = a; }
+
+static void nj_tree(sbuf *s, const uint16_t *diff, int ntaxa, int num_sites, const pbo_print_opts *o) {
+    /* calc_dist_matrix (pop_tree.cpp:496-515) */
+    double *x = (double *)calloc((size_t)ntaxa * ntaxa, sizeof(double));
+    for (int i = 0; i < ntaxa - 1; ++i)
+        for (int j = i + 1; j < ntaxa; ++j) {
+            double d = (double)diff[i * ntaxa + j] / num_sites;
+            if (o->jc) d = -0.75 * log(1.0 - (4.0 * d / 3.0));
+            x[i * ntaxa + j] = x[j * ntaxa + i] = d;
+        }
+    /* tree_init + setup_tree (pop_tree.cpp:517-566): tips 1..ntaxa, rings ntaxa+1..2*ntaxa-1 */
+    int nnodes = 2 * ntaxa - 1;
+    njnode *pool = (njnode *)calloc((size_t)ntaxa + 3 * (size_t)(nnodes - ntaxa), sizeof(njnode));
+    njnode **nodep = (njnode **)calloc((size_t)nnodes, sizeof(njnode *));
+    for (int i = 0; i < ntaxa; ++i) { nodep[i] = pool + i; nodep[i]->tip = 1; nodep[i]->index = i + 1; }
+    for (int i = ntaxa; i < nnodes; ++i) {
+        njnode *a = pool + ntaxa + 3 * (i - ntaxa);
+        a[0].next = a + 1; a[1].next = a + 2; a[2].next = a;
+        a[0].index = a[1].index = a[2].index = i + 1;
+        nodep[i] = a;
+    }
+    /* join_tree (pop_tree.cpp:254-429) */
+    njnode **cluster = (njnode **)calloc((size_t)ntaxa, sizeof(njnode *));
+    double *av = (double *)calloc((size_t)ntaxa, sizeof(double)), *R = (double *)calloc((size_t)ntaxa, sizeof(double));
+    for (int i = 0; i < ntaxa; ++i) cluster[i] = nodep[i];
+#define X(a, b) x[(size_t)(a) * ntaxa + (b)]
+    for (int i = 0; i < ntaxa - 1; ++i)
+        for (int j = i + 1; j < ntaxa; ++j) { double da = (X(i, j) + X(j, i)) / 2.0; X(i, j) = da; X(j, i) = da; }
+    double fotu2 = ntaxa - 2.0, total = 0, tmin, dmin;
+    int nextnode = ntaxa + 1, mini = 0, minj = 0;
+    for (int nc = 1; nc <= ntaxa - 3; ++nc) {
+        for (int j = 2; j <= ntaxa; ++j)
+            for (int i = 0; i <= j - 2; ++i) X(j - 1, i) = X(i, j - 1);
+        tmin = DBL_MAX;
+        for (int i = 0; i < ntaxa; ++i) R[i] = 0.0;
+        /* the enter order is the identity (make_nj, pop_tree.cpp:231-232) */
+        for (int jj = 2; jj <= ntaxa; ++jj) {
+            if (!cluster[jj - 1]) continue;
+            for (int ii = 1; ii <= jj - 1; ++ii)
+                if (cluster[ii - 1]) { R[ii - 1] += X(ii - 1, jj - 1); R[jj - 1] += X(ii - 1, jj - 1); }
+        }
+        for (int jj = 2; jj <= ntaxa; ++jj) {
+            if (!cluster[jj - 1]) continue;
+            for (int ii = 1; ii <= jj - 1; ++ii) {
+                if (cluster[ii - 1]) total = fotu2 * X(ii - 1, jj - 1) - R[ii - 1] - R[jj - 1];
+                if (total < tmin) { tmin = total; mini = ii; minj = jj; }       /* a stale total is compared again (:332-340) */
+            }
+        }
+        double dio = 0.0, djo = 0.0;
+        for (int i = 0; i < ntaxa; ++i) { dio += X(i, mini - 1); djo += X(i, minj - 1); }
+        dmin = X(mini - 1, minj - 1);
+        dio = (dio - dmin) / fotu2; djo = (djo - dmin) / fotu2;
+        double bi = (dmin + dio - djo) * 0.5, bj = dmin - bi;
+        bi -= av[mini - 1]; bj -= av[minj - 1];
+        nj_link(nodep[nextnode - 1]->next, cluster[mini - 1]);
+        nj_link(nodep[nextnode - 1]->next->next, cluster[minj - 1]);
+        cluster[mini - 1]->v = bi; cluster[minj - 1]->v = bj;
+        cluster[mini - 1]->back->v = bi; cluster[minj - 1]->back->v = bj;
+        cluster[mini - 1] = nodep[nextnode - 1]; cluster[minj - 1] = 0;
+        ++nextnode;
+        av[mini - 1] = dmin * 0.5;
+        fotu2 -= 1.0;
+        for (int j = 0; j < ntaxa; ++j)
+            if (cluster[j]) {
+                double da = (X(mini - 1, j) + X(minj - 1, j)) * 0.5;
+                if (mini - j - 1 < 0) X(mini - 1, j) = da;
+                if (mini - j - 1 > 0) X(j, mini - 1) = da;
+            }
+        for (int j = 0; j < ntaxa; ++j) { X(minj - 1, j) = 0.0; X(j, minj - 1) = 0.0; }
+    }
+    int el[3], nude = 0;
+    for (int i = 1; i <= ntaxa && nude < 3; ++i) if (cluster[i - 1]) el[nude++] = i;
+    double bi = (X(el[0] - 1, el[1] - 1) + X(el[0] - 1, el[2] - 1) - X(el[1] - 1, el[2] - 1)) * 0.5;
+    double bj = X(el[0] - 1, el[1] - 1) - bi, bk = X(el[0] - 1, el[2] - 1) - bi;
+    bi -= av[el[0] - 1]; bj -= av[el[1] - 1]; bk -= av[el[2] - 1];
+    nj_link(nodep[nextnode - 1], cluster[el[0] - 1]);
+    nj_link(nodep[nextnode - 1]->next, cluster[el[1] - 1]);
+    nj_link(nodep[nextnode - 1]->next->next, cluster[el[2] - 1]);
+    cluster[el[0] - 1]->v = bi; cluster[el[1] - 1]->v = bj; cluster[el[2] - 1]->v = bk;
+    cluster[el[0] - 1]->back->v = bi; cluster[el[1] - 1]->back->v = bj; cluster[el[2] - 1]->back->v = bk;
+#undef X
+    nj_print(s, nodep[0]->back, nodep[0]->back, o);        /* make_nj: start = nodep[0]->back (pop_tree.cpp:246-248) */
+    free(x); free(pool); free(nodep); free(cluster); free(av); free(R);
 }
 
 int64_t pbo_format_window(const pbo_params *p, const pbo_result *r, int32_t w, uint32_t an,
@@ -776,6 +904,11 @@ int64_t pbo_format_window(const pbo_params *p, const pbo_result *r, int32_t w, u
         return s.len;
     }
     sb_printf(&s, "%s\t%d\t%d\t%d", o->chrom, r->win_beg[w] + 1, r->win_end[w] + 1, ns);
+    if (an == PBO_AN_TREE) {     /* make_nj (pop_tree.cpp:208-252) */
+        if (ns < o->min_sites || S < 1) sb_printf(&s, "\tNA\n");
+        else { sb_printf(&s, "\t"); nj_tree(&s, r->tree_diff + (int64_t)w * (n + 1) * (n + 1), n + 1, ns, o); }
+        return s.len;
+    }
     const int ok = ns >= o->min_sites;
     if (an == PBO_AN_NUCDIV) {
         for (int i = 0; i < P; ++i) sb_stat(&s, "pi", o->pop_names[i], ok, r->piw[(int64_t)w * P + i] / ns);

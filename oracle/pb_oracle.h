@@ -39,6 +39,7 @@ extern "C" {
 #define PBO_AN_HAPLO_EHHS    0x100u
 #define PBO_AN_HAPLO_DXY     0x200u
 #define PBO_AN_SNP           0x400u
+#define PBO_AN_TREE          0x800u  /* pop_tree.cpp: difference matrix incl. the reference taxon */
 
 typedef struct pbo_params {
     int32_t  n_samples, n_pops;
@@ -80,6 +81,7 @@ typedef struct pbo_result {
     int32_t span_beg, span_end;
     uint64_t *cb, *site_type; uint8_t *site_flag;
     int64_t reads_pushed, reads_used, aligned_bases;
+    uint16_t *tree_diff;          /* [NW][(n+1)*(n+1)] treeData::diff_matrix, taxon 0 = the reference */
 } pbo_result;
 
 typedef struct pbo_print_opts {
@@ -87,6 +89,7 @@ typedef struct pbo_print_opts {
     const char *const *pop_names;
     const char *const *sample_names;
     int32_t min_sites, min_snps, jc, snp_output;
+    const char *ref_name;         /* treeData::refid: the AS tag of the sequence dictionary */
 } pbo_print_opts;
 
 /* errmod_init(1.0-0.83) -> cal_coef (pop_utils.cpp:203-266).  Buffers: 256, 64*256*256, 256*256 */

@@ -10,7 +10,7 @@ PKG = Path(__file__).resolve().parent
 MAXS = 64
 
 AN = dict(NUCDIV=0x001, SFS=0x002, LD_ZNS=0x004, LD_OMEGA=0x008, LD_WALL=0x010, DIVERGE_IND=0x020,
-          DIVERGE_POP=0x040, HAPLO_K=0x080, HAPLO_EHHS=0x100, HAPLO_DXY=0x200, SNP=0x400)
+          DIVERGE_POP=0x040, HAPLO_K=0x080, HAPLO_EHHS=0x100, HAPLO_DXY=0x200, SNP=0x400, TREE=0x800)
 FLAG = dict(ILLUMINA=0x02, SUBSTITUTE=0x10, HETEROZYGOTE=0x20, OUTGROUP=0x40, EMIT_CB=0x10000)
 
 EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_version", "pb_set_contig", "pb_region_begin", "pb_push_batch",
@@ -58,12 +58,14 @@ class Result(C.Structure):
                 ("nhaps", _p(C.c_int32)), ("hdiv", _p(C.c_double)), ("ehhs", _p(C.c_double)),
                 ("span_beg", C.c_int32), ("span_end", C.c_int32),
                 ("cb", _p(C.c_uint64)), ("site_type", _p(C.c_uint64)), ("site_flag", _p(C.c_uint8)),
-                ("reads_pushed", C.c_int64), ("reads_used", C.c_int64), ("aligned_bases", C.c_int64)]
+                ("reads_pushed", C.c_int64), ("reads_used", C.c_int64), ("aligned_bases", C.c_int64),
+                ("tree_diff", _p(C.c_uint16))]
 
 
 class PrintOpts(C.Structure):
     _fields_ = [("chrom", C.c_char_p), ("pop_names", _p(C.c_char_p)), ("sample_names", _p(C.c_char_p)),
-                ("min_sites", C.c_int32), ("min_snps", C.c_int32), ("jc", C.c_int32), ("snp_output", C.c_int32)]
+                ("min_sites", C.c_int32), ("min_snps", C.c_int32), ("jc", C.c_int32), ("snp_output", C.c_int32),
+                ("ref_name", C.c_char_p)]
 
 
 def lib_path():

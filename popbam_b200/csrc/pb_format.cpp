@@ -2,13 +2,16 @@
 //   print_nucdiv  pop_nucdiv.cpp:258-289     print_sfs     pop_sfs.cpp:293-317
 //   print_ld      pop_ld.cpp:650-712         print_diverge pop_diverge.cpp:496-574
 //   print_haplo   pop_haplo.cpp:365-442      print_popbam_snp / print_sweep / print_ms  pop_snp.cpp:224-303
+//   make_nj / join_tree / print_tree  pop_tree.cpp:208-470  (neighbour joining on the window's difference matrix)
 // The reference streams with std::fixed << std::setprecision(5) and prints "NA" through std::setw(7);
 // "%.5f" and "%7s" produce the same bytes.  Host-only formatting of results the kernels computed.
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cfloat>
 #include <string>
+#include <vector>
 #include "../../include/popbam_b200.h"
 
 extern "C" const pb_params *pb_ctx_params(const pb_ctx *c);
@@ -60,6 +63,106 @@ char nt16_roundtrip(int c) {
 const char kIupacLetters[17] = "AMRWNCSYNNGKNNNT";   // popbam.cpp iupac[]
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
+
+// Neighbour joining as the tree subcommand does it (calc_dist_matrix, join_tree, print_tree: pop_tree.cpp:496-515,
+// 254-429, 439-470), on flat arrays: taxon t (0 = the reference sequence) is end point t; interior node k has the three
+// end points T + 3k + {0, 1, 2}, of which 1 and 2 receive the two clusters it joins and 0 is joined later.  `mate[e]` is
+// the end point at the other end of e's branch, `len[e]` the branch length (stored at both ends).  The arithmetic keeps
+// the reference's order of operations: ties in the minimisation and the printed lengths depend on it.
+struct NjTree {
+    int T;
+    std::vector<int> mate;
+    std::vector<double> len;
+    const pb_print_opts *o;
+    void link(int a, int b) { mate[a] = b; mate[b] = a; }
+    bool tip(int e) const { return e < T; }
+    int next(int e) const { const int k = (e - T) / 3; return T + 3 * k + ((e - T) % 3 + 1) % 3; }
+    void print(Out &out, int e, int start) const {
+        if (tip(e)) out.s += e == 0 ? o->ref_name : o->sample_names[e - 1];
+        else {
+            out.s += '(';
+            print(out, mate[next(e)], start);
+            out.s += ',';
+            print(out, mate[next(next(e))], start);
+            if (e == start) { out.s += ','; print(out, mate[e], start); }
+            out.s += ')';
+        }
+        if (e == start) out.s += ";\n";
+        else if (len[e] < 0) out.s += ":0.00000";
+        else out.f(":%.5f", len[e]);
+    }
+};
+
+void nj_newick(Out &out, const uint16_t *diff, int T, int num_sites, const pb_print_opts *o) {
+    std::vector<double> x((size_t)T * T, 0.0), av((size_t)T, 0.0), R((size_t)T);
+    auto X = [&](int a, int b) -> double & { return x[(size_t)a * T + b]; };
+    for (int i = 0; i < T - 1; ++i)
+        for (int j = i + 1; j < T; ++j) {
+            double d = (double)diff[i * T + j] / num_sites;                 // p-distance
+            if (o->jc) d = -0.75 * log(1.0 - (4.0 * d / 3.0));              // Jukes-Cantor
+            X(i, j) = d; X(j, i) = d;
+        }
+    NjTree t;
+    t.T = T; t.o = o;
+    t.mate.assign((size_t)T + 3 * (size_t)(T - 2), -1);
+    t.len.assign(t.mate.size(), 0.0);
+    std::vector<int> cl((size_t)T);          // live clusters: the end point that represents each, -1 when merged away
+    for (int i = 0; i < T; ++i) cl[i] = i;
+    for (int i = 0; i < T - 1; ++i)
+        for (int j = i + 1; j < T; ++j) { const double da = (X(i, j) + X(j, i)) / 2.0; X(i, j) = da; X(j, i) = da; }
+    double fotu2 = T - 2.0, total = 0.0;
+    int node = 0, mi = 0, mj = 0;
+    for (int cycle = 1; cycle <= T - 3; ++cycle, ++node) {
+        for (int j = 1; j < T; ++j)
+            for (int i = 0; i < j; ++i) X(j, i) = X(i, j);
+        double tmin = DBL_MAX;
+        for (int i = 0; i < T; ++i) R[i] = 0.0;
+        for (int j = 1; j < T; ++j) {
+            if (cl[j] < 0) continue;
+            for (int i = 0; i < j; ++i)
+                if (cl[i] >= 0) { R[i] += X(i, j); R[j] += X(i, j); }
+        }
+        for (int j = 1; j < T; ++j) {
+            if (cl[j] < 0) continue;
+            for (int i = 0; i < j; ++i) {
+                if (cl[i] >= 0) total = fotu2 * X(i, j) - R[i] - R[j];
+                if (total < tmin) { tmin = total; mi = i; mj = j; }          // the reference compares a stale total for dead i too
+            }
+        }
+        double dio = 0.0, djo = 0.0;
+        for (int i = 0; i < T; ++i) { dio += X(i, mi); djo += X(i, mj); }
+        const double dmin = X(mi, mj);
+        dio = (dio - dmin) / fotu2;
+        djo = (djo - dmin) / fotu2;
+        double bi = (dmin + dio - djo) * 0.5, bj = dmin - bi;
+        bi -= av[mi]; bj -= av[mj];
+        const int e0 = T + 3 * node;
+        t.link(e0 + 1, cl[mi]); t.link(e0 + 2, cl[mj]);
+        t.len[cl[mi]] = bi; t.len[e0 + 1] = bi;
+        t.len[cl[mj]] = bj; t.len[e0 + 2] = bj;
+        cl[mi] = e0; cl[mj] = -1;
+        av[mi] = dmin * 0.5;
+        fotu2 -= 1.0;
+        for (int j = 0; j < T; ++j)
+            if (cl[j] >= 0) {
+                const double da = (X(mi, j) + X(mj, j)) * 0.5;
+                if (mi < j) X(mi, j) = da;
+                if (mi > j) X(j, mi) = da;
+            }
+        for (int j = 0; j < T; ++j) { X(mj, j) = 0.0; X(j, mj) = 0.0; }
+    }
+    int el[3], k = 0;
+    for (int i = 0; i < T && k < 3; ++i) if (cl[i] >= 0) el[k++] = i;
+    double bi = (X(el[0], el[1]) + X(el[0], el[2]) - X(el[1], el[2])) * 0.5;
+    double bj = X(el[0], el[1]) - bi, bk = X(el[0], el[2]) - bi;
+    bi -= av[el[0]]; bj -= av[el[1]]; bk -= av[el[2]];
+    const int e0 = T + 3 * node;
+    t.link(e0, cl[el[0]]); t.link(e0 + 1, cl[el[1]]); t.link(e0 + 2, cl[el[2]]);
+    t.len[cl[el[0]]] = bi; t.len[e0] = bi;
+    t.len[cl[el[1]]] = bj; t.len[e0 + 1] = bj;
+    t.len[cl[el[2]]] = bk; t.len[e0 + 2] = bk;
+    t.print(out, t.mate[0], t.mate[0]);      // make_nj starts at the node the reference taxon hangs on
+}
 
 }  // namespace
 
@@ -122,6 +225,11 @@ extern "C" int64_t pb_format_window(const pb_ctx *ctx, const pb_region_result *r
         out.f("%s\t%d\t%d\t%d", o->chrom, r->win_beg[w] + 1, r->win_end[w] + 1, ns);
         const bool ok = ns >= o->min_sites;
         char nm[600];
+        if (an == PB_AN_TREE) {      // make_nj (pop_tree.cpp:208-252): the tree ends the row itself
+            if (!r->tree_diff || !o->ref_name || n < 2) return PB_ERR_ARG;      // three taxa at least
+            if (!ok || S < 1) out.f("\tNA\n");
+            else { out.f("\t"); nj_newick(out, r->tree_diff + (size_t)w * (n + 1) * (n + 1), n + 1, ns, o); }
+        } else {
         switch (an) {
         case PB_AN_NUCDIV:
             for (int i = 0; i < P; ++i) out.stat("pi", o->pop_names[i], ok, r->piw[wp + i] / ns);
@@ -188,6 +296,7 @@ extern "C" int64_t pb_format_window(const pb_ctx *ctx, const pb_region_result *r
         default: return PB_ERR_ARG;
         }
         out.f("\n");
+        }
     }
     const int64_t len = (int64_t)out.s.size();
     if (buf && cap > 0) {

@@ -161,9 +161,10 @@ struct SmallLayout {
     int32_t *wall_num_snps; double *wallb, *wallq;
     uint16_t *ind_div, *pop_div; int32_t *div_num_snps;
     int32_t *nhaps; double *hdiv, *ehhs;
+    uint16_t *tree_diff;
     size_t bytes;
 };
-SmallLayout small_layout(void *base, int NW, int P, int n) {
+SmallLayout small_layout(void *base, int NW, int P, int n, bool with_tree) {
     Carver cv(base);
     SmallLayout L;
     const size_t wp = (size_t)NW * P, wpp = (size_t)NW * P * P, wn = (size_t)NW * n;
@@ -174,6 +175,7 @@ SmallLayout small_layout(void *base, int NW, int P, int n) {
     L.wall_num_snps = cv.take<int32_t>(wp); L.wallb = cv.take<double>(wp); L.wallq = cv.take<double>(wp);
     L.ind_div = cv.take<uint16_t>(wn); L.pop_div = cv.take<uint16_t>(wp); L.div_num_snps = cv.take<int32_t>(wp);
     L.nhaps = cv.take<int32_t>(wp); L.hdiv = cv.take<double>(wp); L.ehhs = cv.take<double>(wp);
+    L.tree_diff = cv.take<uint16_t>(with_tree ? (size_t)NW * (n + 1) * (n + 1) : 1);
     L.bytes = (cv.off + 255) & ~(size_t)255;
     return L;
 }
@@ -418,10 +420,10 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaEventRecord(c->ev[3], st));
 
     // ---- per-window site counts, offsets of the segregating-site lists
-    const SmallLayout dl0 = small_layout(nullptr, NW, P.n_pops, n);
+    const SmallLayout dl0 = small_layout(nullptr, NW, P.n_pops, n, (c->analyses & PB_AN_TREE) != 0);
     PB_TRY(dev_reserve(c, c->d_stats, dl0.bytes));
     PB_TRY(host_reserve(c, c->h_small, dl0.bytes));
-    const SmallLayout dl = small_layout(c->d_stats.p, NW, P.n_pops, n);
+    const SmallLayout dl = small_layout(c->d_stats.p, NW, P.n_pops, n, (c->analyses & PB_AN_TREE) != 0);
     PB_CUDA(c, cudaMemsetAsync(c->d_stats.p, 0, dl.bytes, st));
     k_window_sites<false><<<NW, 256, 0, st>>>(c->span_beg, pa.win_beg, pa.win_end, pa.site_flag, pa.site_type, pa.ref, pa.ref_len, nullptr, n,
                                              dl.num_sites, dl.segsites, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
@@ -430,7 +432,7 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaGetLastError());
     int64_t *h_total = reinterpret_cast<int64_t *>(c->h_ctr.p) + (sizeof(PbCounters) + 7) / 8;   // h_ctr has a page
     PB_CUDA(c, cudaMemcpyAsync(h_total, dl.seg_off + NW, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    const SmallLayout hl0 = small_layout(c->h_small.p, NW, P.n_pops, n);
+    const SmallLayout hl0 = small_layout(c->h_small.p, NW, P.n_pops, n, (c->analyses & PB_AN_TREE) != 0);
     PB_CUDA(c, cudaMemcpyAsync(hl0.segsites, dl.segsites, sizeof(int32_t) * (size_t)NW, cudaMemcpyDeviceToHost, st));
     PB_CUDA(c, cudaStreamSynchronize(st));
     const int64_t S = *h_total;
@@ -453,7 +455,7 @@ int run_pipeline(pb_ctx *c) {
 
     // ---- window statistics
     const uint32_t stat_bits = PB_AN_NUCDIV | PB_AN_SFS | PB_AN_LD_WALL | PB_AN_DIVERGE_IND |
-                               PB_AN_DIVERGE_POP | PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS | PB_AN_HAPLO_DXY;
+                               PB_AN_DIVERGE_POP | PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS | PB_AN_HAPLO_DXY | PB_AN_TREE;
     if (c->analyses & stat_bits) {
         PbStatArgs sa;
         memset(&sa, 0, sizeof sa);
@@ -462,7 +464,7 @@ int run_pipeline(pb_ctx *c) {
         sa.analyses = c->analyses; sa.flags = P.flags; sa.outidx = P.outidx; sa.min_freq = P.min_freq;
         sa.num_sites = dl.num_sites; sa.segsites = dl.segsites; sa.seg_off = dl.seg_off; sa.seg_type = sl.seg_type;
         sa.s_total = S;
-        if (c->analyses & (PB_AN_NUCDIV | PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS | PB_AN_HAPLO_DXY | PB_AN_DIVERGE_IND)) {
+        if (c->analyses & (PB_AN_NUCDIV | PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS | PB_AN_HAPLO_DXY | PB_AN_DIVERGE_IND | PB_AN_TREE)) {
             PB_TRY(dev_reserve(c, c->d_hap, sizeof(uint64_t) * (size_t)n * (size_t)(S / 64 + NW + 1)));
             sa.hap = dp<uint64_t>(c->d_hap);
         }
@@ -478,7 +480,7 @@ int run_pipeline(pb_ctx *c) {
         sa.piw = dl.piw; sa.pib = dl.pib; sa.min_dxy = dl.min_dxy;
         sa.sfs_num_snps = dl.sfs_num_snps; sa.td = dl.td; sa.fwh = dl.fwh;
         sa.wall_num_snps = dl.wall_num_snps; sa.wallb = dl.wallb; sa.wallq = dl.wallq;
-        sa.ind_div = dl.ind_div; sa.pop_div = dl.pop_div; sa.div_num_snps = dl.div_num_snps;
+        sa.ind_div = dl.ind_div; sa.pop_div = dl.pop_div; sa.div_num_snps = dl.div_num_snps; sa.tree_diff = dl.tree_diff;
         sa.nhaps = dl.nhaps; sa.hdiv = dl.hdiv; sa.ehhs = dl.ehhs;
         k_window_stats<<<NW, PB_ST_THREADS, (size_t)n * n * sizeof(uint16_t), st>>>(sa);
         c->launches += 1;
@@ -541,7 +543,7 @@ int fill_result(pb_ctx *c, pb_region_result *out) {
     cudaEventElapsedTime(&c->ms_pileup, c->ev[2], c->ev[3]);
     cudaEventElapsedTime(&c->ms_sites, c->ev[3], c->ev[4]);
     cudaEventElapsedTime(&c->ms_stats, c->ev[4], c->ev[5]);
-    const SmallLayout hl = small_layout(c->h_small.p, NW, P.n_pops, n);
+    const SmallLayout hl = small_layout(c->h_small.p, NW, P.n_pops, n, (c->analyses & PB_AN_TREE) != 0);
     const bool with_cb = (c->analyses & PB_AN_SNP) != 0;
     const SegLayout sl = seg_layout(c->h_seg.p, c->s_total, n, with_cb);
     pb_region_result &r = c->res;
@@ -556,6 +558,7 @@ int fill_result(pb_ctx *c, pb_region_result *out) {
     if (an & (PB_AN_LD_ZNS | PB_AN_LD_OMEGA)) { r.ld_num_snps = hl.ld_num_snps; r.zns = hl.zns; r.omegamax = hl.omegamax; }
     if (an & PB_AN_LD_WALL) { r.wall_num_snps = hl.wall_num_snps; r.wallb = hl.wallb; r.wallq = hl.wallq; }
     if (an & PB_AN_DIVERGE_IND) r.ind_div = hl.ind_div;
+    if (an & PB_AN_TREE) r.tree_diff = hl.tree_diff;
     if (an & PB_AN_DIVERGE_POP) { r.pop_div = hl.pop_div; r.div_num_snps = hl.div_num_snps; }
     if (an & (PB_AN_HAPLO_K | PB_AN_HAPLO_EHHS)) { r.nhaps = hl.nhaps; r.hdiv = hl.hdiv; }
     if (an & PB_AN_HAPLO_EHHS) r.ehhs = hl.ehhs;

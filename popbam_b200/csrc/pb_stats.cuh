@@ -41,6 +41,7 @@ struct PbStatArgs {
     int32_t *wall_num_snps; double *wallb, *wallq;
     uint16_t *ind_div, *pop_div; int32_t *div_num_snps;
     int32_t *nhaps; double *hdiv, *ehhs;
+    uint16_t *tree_diff;  // [NW][(n+1)*(n+1)]
 };
 
 // analysis bits (include/popbam_b200.h)
@@ -51,6 +52,7 @@ struct PbStatArgs {
 #define PBA_LD_WALL 0x010u
 #define PBA_DIVERGE_IND 0x020u
 #define PBA_DIVERGE_POP 0x040u
+#define PBA_TREE 0x800u
 #define PBA_HAPLO_K 0x080u
 #define PBA_HAPLO_EHHS 0x100u
 #define PBA_HAPLO_DXY 0x200u
@@ -123,7 +125,7 @@ __global__ void __launch_bounds__(PB_ST_THREADS) k_window_stats(const PbStatArgs
     const bool outg = (a.flags & PBA_FLAG_OUTGROUP) != 0;
 
     // ---- haplotype words: bit s of hap[i] = sample i carries the derived allele at segsite s
-    if (an & (PBA_NUCDIV | PBA_HAPLO_K | PBA_HAPLO_EHHS | PBA_HAPLO_DXY | PBA_DIVERGE_IND)) {
+    if (an & (PBA_NUCDIV | PBA_HAPLO_K | PBA_HAPLO_EHHS | PBA_HAPLO_DXY | PBA_DIVERGE_IND | PBA_TREE)) {
         for (int idx = tid; idx < n * nwords; idx += PB_ST_THREADS) {
             const int i = idx / nwords, kw = idx - i * nwords;
             uint64_t word = 0;
@@ -138,6 +140,23 @@ __global__ void __launch_bounds__(PB_ST_THREADS) k_window_stats(const PbStatArgs
             unsigned d = 0;
             for (int k = 0; k < nwords; ++k) d += __popcll(hap[(size_t)i * nwords + k]);
             a.ind_div[(size_t)w * n + i] = (uint16_t)d;
+        }
+    }
+    // ---- tree: difference matrix with the reference as taxon 0 (pop_tree.cpp:472-494; unsigned short, wraps)
+    if (an & PBA_TREE) {
+        const int m = n + 1;
+        uint16_t *td = a.tree_diff + (size_t)w * m * m;
+        for (int pi = tid; pi < m * m; pi += PB_ST_THREADS) {
+            const int i = pi / m, j = pi - i * m;
+            unsigned d = 0;
+            if (i != j) {
+                if (i == 0 || j == 0) {
+                    const int smp = (i ? i : j) - 1;
+                    for (int k = 0; k < nwords; ++k) d += __popcll(hap[(size_t)smp * nwords + k]);
+                } else
+                    for (int k = 0; k < nwords; ++k) d += __popcll(hap[(size_t)(i - 1) * nwords + k] ^ hap[(size_t)(j - 1) * nwords + k]);
+            }
+            td[pi] = (uint16_t)d;
         }
     }
     // ---- pairwise difference matrix (unsigned short, wraps)

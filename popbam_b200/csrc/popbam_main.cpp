@@ -57,6 +57,7 @@ const CmdSpec kCmds[] = {
     {"diverge", "fhmxqsabkpwod", "nti"},
     {"haplo", "fhomxqsabkw", "i"},
     {"snp", "fhmxqsabozpw", "vi"},
+    {"tree", "fhmxqsabkwd", "i"},      // pop_tree.cpp:601-620
 };
 
 void usage(const char *cmd) {
@@ -152,6 +153,7 @@ struct Run {
     pbio::SampleTable st;
     pbio::BamIndex idx;
     std::string ref;
+    std::string ref_name;       // tree: the AS tag
     int tid = -1, beg = 0, end = 0;
     std::vector<int32_t> wb, we;
     std::vector<Shard> shards;
@@ -205,6 +207,7 @@ void gpu_worker(Run *R, int g, int G, int device) {
     po.pop_names = pops.data(); po.sample_names = smps.data();
     po.min_sites = R->opt.min_sites; po.min_snps = R->opt.min_snps;
     po.jc = R->opt.dist == "jc"; po.snp_output = R->opt.output;
+    po.ref_name = R->ref_name.c_str();
     std::vector<char> line(1 << 16);
     for (int s = g; s < (int)R->shards.size(); s += G) {
         Shard &sh = R->shards[s];
@@ -246,7 +249,7 @@ void gpu_worker(Run *R, int g, int G, int device) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr, "Program: popbam (B200 path; %s)\nUsage:   popbam <command> [options] <in.bam> [region]\n"
-                        "Commands: snp haplo diverge nucdiv ld sfs\n", pb_version());
+                        "Commands: snp haplo diverge tree nucdiv ld sfs\n", pb_version());
         return 1;
     }
     if (!strcmp(argv[1], "_fetch")) {
@@ -296,7 +299,7 @@ int main(int argc, char **argv) {
     if (o.positional.size() < 2) { usage(o.cmd.c_str()); fatal("Need to specify BAM file name"); }
     const std::string bamfile = o.positional[0], region = o.positional[1];
     if (o.reffile.empty()) fatal("Need to specify fastA reference file");
-    if (o.cmd == "diverge" && o.dist != "pdist" && o.dist != "jc") fatal(o.dist + " is not a valid distance option");
+    if ((o.cmd == "diverge" || o.cmd == "tree") && o.dist != "pdist" && o.dist != "jc") fatal(o.dist + " is not a valid distance option");
     try {
         { std::ifstream t(bamfile); if (!t) fatal("Specified input file: " + bamfile + " does not exist"); }
         { std::ifstream t(o.reffile); if (!t) fatal("Specified reference file: " + o.reffile + " does not exist"); }
@@ -312,6 +315,13 @@ int main(int argc, char **argv) {
             std::stringstream ss; ss << hin.rdbuf(); text = ss.str();
         }
         R.st = pbio::build_samples(text, bamfile);
+        if (o.cmd == "tree") {     // get_refid (pop_utils.cpp:463-500): the first AS: tag of the header names the reference taxon
+            const size_t at = R.hdr.text.find("AS:");
+            if (at == std::string::npos) fatal("Unable to parse reference sequence name\nBe sure the AS tag is defined in the sequence dictionary");
+            size_t e = at + 3;
+            while (e < R.hdr.text.size() && R.hdr.text[e] && R.hdr.text[e] != '\t' && R.hdr.text[e] != '\n') ++e;
+            R.ref_name = R.hdr.text.substr(at + 3, e - (at + 3));
+        }
         R.idx.load(bamfile + ".bai", R.hdr.names.size());
         if (!pbio::parse_region(R.hdr, region, &R.tid, &R.beg, &R.end)) fatal("Bad genome coordinates: " + region);
         R.ref = pbio::fetch_contig(o.reffile, R.hdr.names[R.tid]);
@@ -340,6 +350,7 @@ int main(int argc, char **argv) {
     else if (o.cmd == "ld") R.analysis = o.output == 1 ? PB_AN_LD_OMEGA : o.output == 2 ? PB_AN_LD_WALL : PB_AN_LD_ZNS;
     else if (o.cmd == "diverge") R.analysis = o.output == 1 ? PB_AN_DIVERGE_POP : PB_AN_DIVERGE_IND;
     else if (o.cmd == "haplo") R.analysis = o.output == 1 ? PB_AN_HAPLO_EHHS : o.output == 2 ? PB_AN_HAPLO_DXY : PB_AN_HAPLO_K;
+    else if (o.cmd == "tree") R.analysis = PB_AN_TREE;
     else R.analysis = PB_AN_SNP;
     if (o.output < 0 || o.output > 2) fatal("invalid output option");
 

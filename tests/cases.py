@@ -77,6 +77,15 @@ CASES = [
     ("ld2_ld", "ld", ["ld", "-w", "10", "-o", "2"], "LD_WALL", {}, {}),
     ("hap1_ld", "ld", ["haplo", "-w", "10", "-o", "1"], "HAPLO_EHHS", {}, {}),
     ("sfs_ld_og", "ld", ["sfs", "-w", "10", "-p", "og"], "SFS", dict(flags=FLAG["OUTGROUP"], outidx=23), {}),
+    # tree (neighbour joining on the difference matrix incl. the reference taxon)
+    ("tree_c1", "c1", ["tree", "-w", "10"], "TREE", {}, {}),
+    ("tree_c1_jc", "c1", ["tree", "-w", "10", "-d", "jc"], "TREE", {}, dict(jc=1)),
+    ("tree_c1_now", "c1", ["tree"], "TREE", {}, {}),
+    ("tree_c1_k", "c1", ["tree", "-w", "10", "-k", "9900"], "TREE", {}, dict(min_sites=9900)),
+    ("tree_edge", "edge", ["tree", "-w", "10"], "TREE", {}, {}),
+    ("tree_rg2", "rg2", ["tree", "-w", "10", "-d", "jc"], "TREE", {}, dict(jc=1)),
+    ("tree_ld", "ld", ["tree", "-w", "10"], "TREE", {}, {}),
+    ("tree_n64", "n64", ["tree", "-w", "5"], "TREE", {}, {}),
     # 64 samples
     ("nucdiv_n64", "n64", ["nucdiv", "-w", "5"], "NUCDIV", {}, {}),
     ("ld0_n64", "n64", ["ld", "-w", "5", "-o", "0"], "LD_ZNS", {}, {}),

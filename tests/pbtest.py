@@ -21,7 +21,7 @@ REFDUMP = ORACLE_DIR / "_ref" / "refdump"
 MAXS = 64
 
 AN = dict(NUCDIV=0x001, SFS=0x002, LD_ZNS=0x004, LD_OMEGA=0x008, LD_WALL=0x010, DIVERGE_IND=0x020,
-          DIVERGE_POP=0x040, HAPLO_K=0x080, HAPLO_EHHS=0x100, HAPLO_DXY=0x200, SNP=0x400)
+          DIVERGE_POP=0x040, HAPLO_K=0x080, HAPLO_EHHS=0x100, HAPLO_DXY=0x200, SNP=0x400, TREE=0x800)
 FLAG = dict(ILLUMINA=0x02, SUBSTITUTE=0x10, HETEROZYGOTE=0x20, OUTGROUP=0x40, EMIT_CB=0x10000)
 
 
@@ -211,6 +211,7 @@ class Fixture:
         o.chrom = self.contig_name(c).encode()
         o.pop_names, o.sample_names = self._keep
         o.min_sites, o.min_snps, o.jc, o.snp_output = 10, 10, 0, 0
+        o.ref_name = b"synth"          # the AS tag tools/pbsynth writes into @SQ (tree subcommand: treeData::refid)
         for k, v in kw.items():
             setattr(o, k, v)
         return o
@@ -282,7 +283,8 @@ def result_arrays(res, want_cb=False):
              wall_num_snps=arr(res.wall_num_snps, NW * P), wallb=arr(res.wallb, NW * P), wallq=arr(res.wallq, NW * P),
              ind_div=arr(res.ind_div, NW * n), pop_div=arr(res.pop_div, NW * P),
              div_num_snps=arr(res.div_num_snps, NW * P), nhaps=arr(res.nhaps, NW * P), hdiv=arr(res.hdiv, NW * P),
-             ehhs=arr(res.ehhs, NW * P), site_type=arr(res.site_type, span), site_flag=arr(res.site_flag, span))
+             ehhs=arr(res.ehhs, NW * P), site_type=arr(res.site_type, span), site_flag=arr(res.site_flag, span),
+             tree_diff=arr(res.tree_diff, NW * (n + 1) * (n + 1)))
     if want_cb:
         d["cb"] = arr(res.cb, span * n)
     return d

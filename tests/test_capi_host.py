@@ -31,8 +31,8 @@ def test_struct_layouts_match_header_sizes():
     # pb_params: 2 ints + 64 u64 + 64 u8 + 10 ints ; the oracle's mirror struct has the same layout
     assert C.sizeof(capi.Params) == 8 + 512 + 64 + 40
     assert C.sizeof(capi.Batch) == 80
-    assert C.sizeof(capi.Result) == 16 + 8 * 28 + 8 + 8 * 3 + 8 * 3
-    assert C.sizeof(capi.PrintOpts) == 24 + 16
+    assert C.sizeof(capi.Result) == 16 + 8 * 28 + 8 + 8 * 3 + 8 * 3 + 8          # + tree_diff
+    assert C.sizeof(capi.PrintOpts) == 24 + 16 + 8                               # + ref_name
 
 
 @pytest.mark.parametrize("beg,end,win", [(0, 1000000, 10000), (0, 50000, 10000), (0, 30500, 0), (12345, 99999, 5000),

@@ -24,6 +24,7 @@ BY_AN = {
     "DIVERGE_IND": (["ind_div"], []), "DIVERGE_POP": (["pop_div", "div_num_snps"], []),
     "HAPLO_K": (["nhaps"], ["hdiv"]), "HAPLO_EHHS": (["nhaps"], ["hdiv", "ehhs"]),
     "SNP": (["seg_cb"], []),
+    "TREE": (["tree_diff"], []),
 }
 
 
