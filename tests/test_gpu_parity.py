@@ -65,7 +65,7 @@ def test_case_matches_reference_golden_and_oracle(case):
     orc.close(); ctx.close()
 
 
-ALL_AN = 0x7ff
+ALL_AN = 0xfff
 
 
 @pytest.mark.parametrize("fxname", ["c1", "edge", "rg2", "ld", "n64"])
