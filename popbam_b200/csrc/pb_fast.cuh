@@ -34,6 +34,7 @@ struct PbFastParams {        // derived from the need table (k_fast_params), cac
     int k1lo, k1hi, hmin;    // for k1lo <= k <= k1hi: need[hi][k] != 0 and <= hmin <= 15   (khi >= hmin suffices)
     int hi_level;            // level of the H plane (n_levels: none)
     int k2lo, k2hi;          // for k2lo <= k <= k2hi: one stray base cannot change a homozygous call (pb_one_stray_entry)
+    int k3lo, k3hi;          // the same for a stray base below the H plane's level (a wider range of depths)
 };
 
 // ---- bit-planes of the bases, interleaved: planes[1 + w] = {P, B0, B1, H} of the 32 bases at byte offsets 32w .. 32w+31
@@ -201,9 +202,14 @@ __global__ void __launch_bounds__(256) k_ref_planes(const char *__restrict__ ref
 __global__ void __launch_bounds__(64) k_fast_params(const PbCounters *__restrict__ ctr, const uint8_t *__restrict__ need,
                                                     const double *__restrict__ fk, const double *__restrict__ beta,
                                                     const double *__restrict__ lhet, PbFastParams *__restrict__ fp) {
-    __shared__ uint8_t stray_ok[64];
+    __shared__ uint8_t stray_ok[64], stray_low_ok[64];
     const int nl = ctr->n_levels;
-    stray_ok[threadIdx.x] = pb_one_stray_entry(nl, ctr->qval, (int)threadIdx.x, fk, beta, lhet);     // depth k = thread index
+    stray_ok[threadIdx.x] = pb_one_stray_entry(nl, ctr->qval, (int)threadIdx.x, fk, beta, lhet, 0, nl);     // depth k = thread index
+    {
+        int hi0 = 0;
+        while (hi0 < nl && (int)ctr->qval[hi0] < PB_H_QUALITY) ++hi0;
+        stray_low_ok[threadIdx.x] = (hi0 > 0 && hi0 < nl) ? pb_one_stray_entry(nl, ctr->qval, (int)threadIdx.x, fk, beta, lhet, 0, hi0) : 0;
+    }
     __syncthreads();
     if (threadIdx.x) return;
     int k2lo = 1, k2hi = 0;
@@ -213,6 +219,13 @@ __global__ void __launch_bounds__(64) k_fast_params(const PbCounters *__restrict
         start = k + 1;
     }
     fp->k2lo = k2lo; fp->k2hi = k2hi;
+    int k3lo = 1, k3hi = 0;
+    for (int k = 1, start = 1; k <= 64; ++k) {
+        if (k <= 63 && stray_low_ok[k]) continue;
+        if (k - start > k3hi - k3lo + 1) { k3lo = start; k3hi = k - 1; }
+        start = k + 1;
+    }
+    fp->k3lo = k3lo; fp->k3hi = k3hi;
     int k0lo = 1, k0hi = 0;
     for (int k = 1, start = 1; k <= 64; ++k) {
         const int nd = (k <= 63 && nl > 0) ? need[k] : 0;
@@ -326,7 +339,7 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
     const int strip_last = min(S + 31, a.span_end - 1);
     const uint32_t my_lo = live ? __ldg(Fs + strip) : 0u, my_hi = live ? __ldg(Fs + strip + a.M + 1) : 0u;
     uint32_t ck[6] = {0, 0, 0, 0, 0, 0}, ch[4] = {0, 0, 0, 0};
-    uint32_t kover = 0, hover = 0, mism = 0, mism2 = 0, lowq = 0;     // mism: at least one stray base, mism2: at least two
+    uint32_t kover = 0, hover = 0, mism = 0, mism2 = 0, mismH = 0, lowq = 0;     // mism: at least one stray base, mism2: at least two, mismH: a high-quality one
     uint32_t R0 = 0, R1 = 0, RV = 0;
     if (live && g == 0 && S >= 0 && S < a.ref_len) {                      // reference planes of the strip (bit i = position S + i)
         const int64_t wi = S >> 5; const int sh = S & 31;
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
                 const uint32_t B1 = __funnelshift_r(lo4.z, hi4.z, sh);
                 const uint32_t H = __funnelshift_r(lo4.w, hi4.w, sh) & m;
                 const uint32_t mm = P & (((B0 ^ R0) | (B1 ^ R1)) | ~RV);
-                mism2 |= mism & mm; mism |= mm;
+                mism2 |= mism & mm; mism |= mm; mismH |= mm & H;
                 if ((int)((z >> 16) & 0xffu) < a.min_rmsQ) lowq |= P;
                 uint32_t carry = P;
 #pragma unroll
@@ -413,6 +426,7 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
             const uint32_t y = __shfl_xor_sync(0xffffffffu, mism, o);
             mism2 |= (mism & y) | __shfl_xor_sync(0xffffffffu, mism2, o);
             mism |= y;
+            mismH |= __shfl_xor_sync(0xffffffffu, mismH, o);
         }
         lowq |= __shfl_xor_sync(0xffffffffu, lowq, o);
     }
@@ -439,12 +453,16 @@ __global__ void __launch_bounds__(PB_FAST_STRIPS * PB_FAST_G) k_pile_fast(const 
     const int lane0 = (tid & 31) & ~(PB_FAST_G - 1);
     const uint32_t r_k0 = __shfl_sync(0xffffffffu, in_range, lane0), r_k1 = __shfl_sync(0xffffffffu, in_range, lane0 + 1);
     const uint32_t r_k2 = __shfl_sync(0xffffffffu, in_range, lane0 + 2), dge = __shfl_sync(0xffffffffu, in_range, lane0 + 3);
+    // fifth range (a low-quality stray base), evaluated by the thread that had the cheapest test
+    uint32_t r_k3 = 0;
+    if (g == 3 && fp.k3hi >= fp.k3lo) r_k3 = pb_bs_le6(ck, min(fp.k3hi, 63)) & (fp.k3lo > 0 ? ~pb_bs_le6(ck, fp.k3lo - 1) : 0xffffffffu);
+    r_k3 = __shfl_sync(0xffffffffu, r_k3, lane0 + 3);
     if (!live || g != 0) return;
     const uint32_t valid = (strip_last - S + 1) >= 32 ? 0xffffffffu : (1u << (strip_last - S + 1)) - 1u;
     const uint32_t nonzero = (ck[0] | ck[1] | ck[2] | ck[3] | ck[4] | ck[5] | kover) & valid;
     // depth alone / count of high-quality bases proves the unanimous shortcut (pb_need_entry); one stray base at a
     // depth where it provably cannot change the homozygous-reference call (pb_one_stray_entry)
-    const uint32_t easy = nonzero & ~lowq & ~kover & ((~mism & (r_k0 | r_k1)) | (mism & ~mism2 & r_k2));
+    const uint32_t easy = nonzero & ~lowq & ~kover & ((~mism & (r_k0 | r_k1)) | (mism & ~mism2 & (r_k2 | (~mismH & r_k3))));
     // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
     // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is the fourth range test
     a.cov32[(size_t)s * a.n_strips + strip] = easy & dge;

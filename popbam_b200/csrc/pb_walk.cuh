@@ -186,8 +186,10 @@ PB_HD uint8_t pb_need_entry(int L, int nl, const uint8_t *qval, int k, const dou
 // (b,b) wins STRICTLY with that bound for all twelve (b,e) letter pairs and every level of e, it wins for the
 // real cell.  Returns 1 when that holds for depth k: the cell is then homozygous b whatever its snpQ, which is
 // all the per-site logic needs when b is the reference base (pb_site_sample leaves such a word alone).
+// The stray base's level is taken from [le_lo, le_hi): all levels, or only those below the H plane's level when the
+// caller knows the stray base is not a high-quality one (a low-quality stray base is harmless at smaller depths).
 PB_HD uint8_t pb_one_stray_entry(int nl, const uint8_t *qval, int k, const double *fk, const double *__restrict__ beta,
-                                 const double *__restrict__ lhet) {
+                                 const double *__restrict__ lhet, int le_lo, int le_hi) {
     if (k < 2 || k > 255 || nl < 1) return 0;
     double acc = 0.0, fkmin = fk[0];
     for (int c = 0; c < k - 1; ++c) {
@@ -200,7 +202,8 @@ PB_HD uint8_t pb_one_stray_entry(int nl, const uint8_t *qval, int k, const doubl
         if (!(bmin >= 0.0)) return 0;
         acc = pb_errmod_step(acc, fkmin, bmin);
     }
-    for (int le = 0; le < nl; ++le) {
+    if (le_lo < 0 || le_hi > nl || le_lo >= le_hi) return 0;
+    for (int le = le_lo; le < le_hi; ++le) {
         const double be = pb_errmod_step(0.0, fk[0], PB_LDG(beta + ((size_t)qval[le] << 16 | (size_t)k << 8)));
         if (!(be >= 0.0)) return 0;
         for (int b = 0; b < 4; ++b)

@@ -54,6 +54,6 @@ extern "C" int hd_site_logic(uint64_t *cb, int n, int ref, int het_mode, int min
 }
 
 // pb_one_stray_entry for a level set given as quality values (ascending)
-extern "C" int hd_one_stray(const double *fk, const double *beta, const double *lhet, const uint8_t *qval, int nl, int k) {
-    return pb_one_stray_entry(nl, qval, k, fk, beta, lhet);
+extern "C" int hd_one_stray(const double *fk, const double *beta, const double *lhet, const uint8_t *qval, int nl, int k, int le_lo, int le_hi) {
+    return pb_one_stray_entry(nl, qval, k, fk, beta, lhet, le_lo, le_hi);
 }
