@@ -40,7 +40,7 @@ import numpy as np  # noqa: E402
 # DRAM bytes (read + written) of the pileup stage's kernels on a 2.3 Mb shard of this workload, from the committed ncu
 # launch list profiles/r1_end_launches.csv (dram__bytes_read.sum + dram__bytes_write.sum per kernel): k_pile_fast, the
 # cell-list scan, k_hard_cells, k_fast_sites
-TRAFFIC_BYTES_PER_LAUNCH = 486.1e6 + 6.4e6 + 1442.3e6 + 30.8e6
+TRAFFIC_BYTES_PER_LAUNCH = 488.6e6 + 6.4e6 + 980.9e6 + 30.8e6
 WIN = 10000
 READ_LEN = 100
 DEPTH = 30.0
