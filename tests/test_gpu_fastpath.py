@@ -3,6 +3,7 @@ the same region is run through the bit-sliced path, through k_pileup_call (POPBA
 the CPU oracle, and all three must agree bit for bit on the integer results (1e-9 on the fp64 statistics)."""
 import os
 
+import numpy as np
 import pytest
 
 import pbtest
@@ -71,6 +72,33 @@ def test_bit_sliced_path_equals_classic_kernel_and_oracle(name, kw, pkw):
     orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
     got, ref, want = pbtest.result_arrays(fast.res), pbtest.result_arrays(classic.res), pbtest.result_arrays(orc.res)
     assert int(want["segsites"].sum()) > 0
+    assert_same(got, ref, AN_NAMES)
+    assert_same(got, want, AN_NAMES)
+    orc.close(); fast.close(); classic.close(); fx.close()
+
+
+@pytest.mark.parametrize("name,pkw,windows", [
+    # no read passes min_mapQ: every list is empty, the planes hold no passing base
+    ("no_usable_reads", dict(min_mapQ=255), [(0, 3000), (3000, 6000)]),
+    # windows with gaps between them, starting at an odd offset: strips straddle window edges and gap positions
+    ("gaps_unaligned", {}, [(1237, 2001), (2500, 4999), (6001, 8000)]),
+    # a region shorter than one strip
+    ("tiny", {}, [(4111, 4130)]),
+    # one-position windows
+    ("single_positions", {}, [(100, 101), (5000, 5001), (8999, 9000)]),
+])
+def test_bit_sliced_path_region_shapes(name, pkw, windows):
+    fx = pbtest.Fixture(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=22.0, snp_density=0.05, het_frac=0.3, seed=61)
+    p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=fx.n_samples - 1, **pkw)
+    wb = np.array([w[0] for w in windows], dtype=np.int32); we = np.array([w[1] for w in windows], dtype=np.int32)
+    an = 0
+    for a in AN_NAMES:
+        an |= pbtest.AN[a]
+    fast = _ctx(fx, p, an, wb, we, classic=False)
+    classic = _ctx(fx, p, an, wb, we, classic=True)
+    assert fast.kernel_launches() > classic.kernel_launches(), "bit-sliced path was not taken"
+    orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
+    got, ref, want = pbtest.result_arrays(fast.res), pbtest.result_arrays(classic.res), pbtest.result_arrays(orc.res)
     assert_same(got, ref, AN_NAMES)
     assert_same(got, want, AN_NAMES)
     orc.close(); fast.close(); classic.close(); fx.close()
