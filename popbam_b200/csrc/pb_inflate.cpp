@@ -230,9 +230,9 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
 
         // ---- symbols
         const uint32_t *LL = T->litlen, *DD = T->dist;
-        for (;;) {
-            br.refill();                              // >= 56 bits: enough for a length (15+5) and a distance (15+13) symbol
-            uint32_t e = LL[br.peek(kLitLenBits)];
+        br.refill();                                  // >= 56 bits: enough for a length (15+5) and a distance (15+13) symbol
+        uint32_t e = LL[br.peek(kLitLenBits)];        // the entry of the next symbol is always looked up one step ahead,
+        for (;;) {                                    // so its load overlaps the copy of the match before it
             if (e & kSub) { br.drop(kLitLenBits); e = LL[(e >> 16) + br.peek((int)((e >> 8) & 31))]; }
             if (!(e & 0xff)) return false;
             br.drop((int)(e & 0xff));
@@ -247,6 +247,8 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
                     e = LL[br.peek(kLitLenBits)];
                     if ((e & (kLiteral | kEob | kSub)) == kLiteral && op < oend) { br.drop((int)(e & 0xff)); *op++ = (uint8_t)(e >> 16); }
                 }
+                br.refill();
+                e = LL[br.peek(kLitLenBits)];
                 continue;
             }
             if (e & kEob) break;
@@ -258,6 +260,8 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
             if (br.n < 13) br.refill();
             const uint32_t dist = (d >> 16) + br.take((int)((d >> 8) & 31));
             if (dist > (size_t)(op - out) || len > (size_t)(oend - op)) return false;
+            br.refill();
+            e = LL[br.peek(kLitLenBits)];
             const uint8_t *src = op - dist;
             if (dist >= 8 && (size_t)(oend - op) >= len + 8) {
                 uint8_t *dst = op;
