@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
 
 namespace pbio {
 
@@ -260,6 +261,124 @@ std::vector<Chunk> BamIndex::query(int tid, int32_t beg, int32_t end) const {
 // ------------------------------------------------------------------------------------------------ records
 void Batch::clear() {
     pos.clear(); meta.clear(); cig_off.clear(); cigar.clear(); base_off.clear(); seq4.clear(); qual.clear();
+}
+
+namespace {
+// reg2bin (bam.h:697-708): the smallest bin of the UCSC scheme containing [beg, end)
+inline uint32_t region_bin(int64_t beg, int64_t end) {
+    --end;
+    if (beg >> 14 == end >> 14) return (uint32_t)(4681 + (beg >> 14));
+    if (beg >> 17 == end >> 17) return (uint32_t)(585 + (beg >> 17));
+    if (beg >> 20 == end >> 20) return (uint32_t)(73 + (beg >> 20));
+    if (beg >> 23 == end >> 23) return (uint32_t)(9 + (beg >> 23));
+    if (beg >> 26 == end >> 26) return (uint32_t)(1 + (beg >> 26));
+    return 0;
+}
+}  // namespace
+
+int64_t build_bai(const BgzfFile &f, const std::string &bai_path) {
+    const BamHeader h = read_header(f);
+    const size_t nref = h.names.size();
+    const uint32_t kMetaBin = 37450;
+    struct RefIdx { std::map<uint32_t, std::vector<Chunk>> bins; std::vector<uint64_t> linear; };
+    std::vector<RefIdx> refs(nref);
+    BgzfReader rd(f);
+    rd.seek(h.first_record_voffset);
+    std::vector<uint8_t> rec;
+    int64_t n_rec = 0;
+    uint64_t n_no_coor = 0, n_mapped = 0, n_unmapped = 0;
+    int32_t last_tid = -1, last_pos = -1;
+    bool have_run = false;                 // a run = consecutive records of one (reference, bin)
+    int32_t run_tid = -1; uint32_t run_bin = 0; uint64_t run_beg = 0;
+    uint64_t ref_beg = rd.tell();          // first virtual offset of the current reference's records
+    uint64_t last_off = rd.tell();         // virtual offset of the record being read
+    auto close_ref = [&](int32_t tid, uint64_t off_end) {
+        if (tid < 0) return;
+        std::vector<Chunk> &m = refs[(size_t)tid].bins[kMetaBin];
+        m.push_back(Chunk{ref_beg, off_end});
+        m.push_back(Chunk{n_mapped, n_unmapped});
+        n_mapped = n_unmapped = 0;
+        ref_beg = off_end;
+    };
+    for (;;) {
+        last_off = rd.tell();
+        uint8_t b4[4];
+        if (!rd.read(b4, 4)) break;
+        const uint32_t bs = le32(b4);
+        if (bs < 32) fail("corrupted BAM record");
+        rec.resize(bs);
+        if (!rd.read(rec.data(), bs)) fail("truncated BAM record");
+        ++n_rec;
+        const int32_t tid = (int32_t)le32(&rec[0]), pos = (int32_t)le32(&rec[4]);
+        const uint32_t bmq = le32(&rec[8]), fnc = le32(&rec[12]);
+        const uint32_t l_qname = bmq & 0xff, flag = fnc >> 16, n_cig = fnc & 0xffff;
+        if (tid < 0) { ++n_no_coor; if (have_run) { refs[(size_t)run_tid].bins[run_bin].push_back(Chunk{run_beg, last_off}); close_ref(run_tid, last_off); have_run = false; } last_tid = tid; continue; }
+        if ((size_t)tid >= nref) fail("BAM record on an unknown reference");
+        if (n_no_coor) fail("the alignment is not sorted: reads without coordinates prior to reads with coordinates");
+        if (tid < last_tid || (tid == last_tid && pos < last_pos)) fail("the alignment is not sorted");
+        // reference end (bam_calend) for the bin and the linear index
+        int64_t end = pos;
+        const size_t o_cig = 32 + l_qname;
+        if (o_cig + 4 * (size_t)n_cig > bs) fail("corrupted BAM record");
+        for (uint32_t i = 0; i < n_cig; ++i) {
+            const uint32_t c = le32(&rec[o_cig + 4 * i]);
+            const uint32_t op = c & 15;
+            if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) end += c >> 4;
+        }
+        if (end <= pos) end = (int64_t)pos + 1;
+        const bool unmapped = (flag & 0x4) != 0;
+        if (!unmapped) {                   // insert_offset2 (bam_index.c:110-142): smallest offset per 16 kb tile
+            std::vector<uint64_t> &lin = refs[(size_t)tid].linear;
+            const size_t w0 = (size_t)pos >> 14, w1 = (size_t)(end - 1) >> 14;
+            if (lin.size() < w1 + 1) lin.resize(w1 + 1, 0);
+            for (size_t w = w0; w <= w1; ++w) if (lin[w] == 0) lin[w] = last_off;
+        }
+        const uint32_t bin = region_bin(pos, end);
+        if (!have_run || tid != run_tid || bin != run_bin) {
+            if (have_run) {
+                refs[(size_t)run_tid].bins[run_bin].push_back(Chunk{run_beg, last_off});
+                if (tid != run_tid) close_ref(run_tid, last_off);
+            }
+            have_run = true; run_tid = tid; run_bin = bin; run_beg = last_off;
+        }
+        if (unmapped) ++n_unmapped; else ++n_mapped;
+        last_tid = tid; last_pos = pos;
+    }
+    if (have_run) { refs[(size_t)run_tid].bins[run_bin].push_back(Chunk{run_beg, last_off}); close_ref(run_tid, last_off); }
+    // merge_chunks (bam_index.c:141-177): neighbours of one bin that meet inside a BGZF block; fill_missing (:179-191)
+    for (RefIdx &R : refs) {
+        for (auto &kv : R.bins) {
+            if (kv.first == kMetaBin) continue;
+            std::vector<Chunk> &v = kv.second;
+            size_t m = 0;
+            for (size_t l = 1; l < v.size(); ++l) {
+                if (v[m].end >> 16 == v[l].beg >> 16) v[m].end = v[l].end;
+                else v[++m] = v[l];
+            }
+            v.resize(v.empty() ? 0 : m + 1);
+        }
+        for (size_t j = 1; j < R.linear.size(); ++j) if (R.linear[j] == 0) R.linear[j] = R.linear[j - 1];
+    }
+    // bam_index_save (bam_index.c:322-373)
+    std::string out("BAI\1", 4);
+    auto put32 = [&](uint32_t v) { char b[4]; for (int i = 0; i < 4; ++i) b[i] = (char)(v >> (8 * i)); out.append(b, 4); };
+    auto put64 = [&](uint64_t v) { char b[8]; for (int i = 0; i < 8; ++i) b[i] = (char)(v >> (8 * i)); out.append(b, 8); };
+    put32((uint32_t)nref);
+    for (const RefIdx &R : refs) {
+        put32((uint32_t)R.bins.size());
+        for (const auto &kv : R.bins) {
+            put32(kv.first); put32((uint32_t)kv.second.size());
+            for (const Chunk &c : kv.second) { put64(c.beg); put64(c.end); }
+        }
+        put32((uint32_t)R.linear.size());
+        for (uint64_t v : R.linear) put64(v);
+    }
+    put64(n_no_coor);
+    std::ofstream of(bai_path, std::ios::binary);
+    if (!of) fail("cannot write " + bai_path);
+    of.write(out.data(), (std::streamsize)out.size());
+    if (!of) fail("cannot write " + bai_path);
+    return n_rec;
 }
 
 int64_t fetch_region(const BgzfFile &f, const BamIndex &idx, const SampleTable &st, int tid, int32_t beg, int32_t end, Batch &out) {

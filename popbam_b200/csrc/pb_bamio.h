@@ -95,6 +95,13 @@ private:
     std::vector<Ref> refs_;
 };
 
+// bam_index_build / bam_index_core / bam_index_save (bam_index.c:193-320, :641-700, :322-373): writes <bam>.bai for a
+// coordinate-sorted BAM -- UCSC bins with chunks of consecutive records (chunks meeting inside one BGZF block merged),
+// the 16 kb linear index with gaps filled from the left, the per-reference pseudo-bin 37450 (file range, mapped /
+// unmapped counts) and the count of records without coordinates.  Throws Error on unsorted input.  Returns the number
+// of records seen.
+int64_t build_bai(const BgzfFile &f, const std::string &bai_path);
+
 // ---- records -> batch -------------------------------------------------------------------------------
 // Growable structure-of-arrays batch in the pb_read_batch layout (offsets 4-byte aligned per read).
 struct Batch {

@@ -249,7 +249,7 @@ void gpu_worker(Run *R, int g, int G, int device) {
 int main(int argc, char **argv) {
     if (argc < 2) {
         fprintf(stderr, "Program: popbam (B200 path; %s)\nUsage:   popbam <command> [options] <in.bam> [region]\n"
-                        "Commands: snp haplo diverge tree nucdiv ld sfs\n", pb_version());
+                        "Commands: snp haplo diverge tree nucdiv ld sfs   (and: index <in.bam>)\n", pb_version());
         return 1;
     }
     if (!strcmp(argv[1], "_fetch")) {
@@ -276,6 +276,18 @@ int main(int argc, char **argv) {
             printf("samples:"); for (auto &x : st.samples) printf(" %s", x.c_str());
             printf("\npops:"); for (size_t i = 0; i < st.pops.size(); ++i) printf(" %s=%llx", st.pops[i].c_str(), (unsigned long long)st.pop_mask[i]);
             printf("\n");
+        } catch (const pbio::Error &e) { fatal(e.msg); }
+        return 0;
+    }
+    if (!strcmp(argv[1], "index")) {
+        // not a subcommand of the reference's command line (its bam_index_build, bam_index.c:641, is never exposed):
+        // popbam index <in.bam> writes <in.bam>.bai, which every analysis needs (popbam.cpp:130)
+        if (argc < 3) { fprintf(stderr, "Usage:   popbam index <in.bam>\n"); return 1; }
+        try {
+            pbio::BgzfFile bam;
+            bam.open(argv[2]);
+            const long long n = pbio::build_bai(bam, std::string(argv[2]) + ".bai");
+            fprintf(stderr, "[popbam index] %lld records\n", n);
         } catch (const pbio::Error &e) { fatal(e.msg); }
         return 0;
     }

@@ -140,3 +140,80 @@ def test_own_inflate_equals_zlib(tmp_path):
         r = subprocess.run([str(EXE), "_inflate", bam, str(out)], stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0, r.stderr
         assert out.read_bytes() == gzip.open(bam).read()
+
+
+def _parse_bai(path):
+    d = open(path, "rb").read()
+    assert d[:4] == b"BAI\x01"
+    o = 4
+    nref = int(np.frombuffer(d[o:o + 4], dtype=np.uint32)[0]); o += 4
+    refs = []
+    for _ in range(nref):
+        nbin = int(np.frombuffer(d[o:o + 4], dtype=np.uint32)[0]); o += 4
+        bins = {}
+        for _b in range(nbin):
+            b, nch = np.frombuffer(d[o:o + 8], dtype=np.uint32); o += 8
+            bins[int(b)] = np.frombuffer(d[o:o + 16 * int(nch)], dtype=np.uint64).reshape(-1, 2).copy(); o += 16 * int(nch)
+        nint = int(np.frombuffer(d[o:o + 4], dtype=np.uint32)[0]); o += 4
+        lin = np.frombuffer(d[o:o + 8 * nint], dtype=np.uint64).copy(); o += 8 * nint
+        refs.append((bins, lin))
+    tail = d[o:]
+    return refs, tail
+
+
+@pytest.mark.parametrize("fxname", ["edge", "rg2", "c1"])
+def test_index_builder_serves_the_same_records(tmp_path, fxname):
+    """`popbam index` (pbio::build_bai, the restatement of bam_index_build): the index it writes must serve every region
+    query exactly as the generator's own index does, cover the same bins with chunks that start where the runs of records
+    start, and carry the per-reference record counts in the pseudo-bin."""
+    popbam_b200.build()
+    fx = pbtest.fixture(fxname)
+    bam, fa = fx.write_files(tmp_path / fxname)
+    gen_bai = tmp_path / "gen.bai"
+    (tmp_path / (fxname + ".bam.bai")).rename(gen_bai) if (tmp_path / (fxname + ".bam.bai")).exists() else None
+    bai = str(bam) + ".bai"
+    if not gen_bai.exists():            # write_files may name the index differently
+        import shutil
+        shutil.copy(bai, gen_bai)
+    r = subprocess.run([str(EXE), "index", bam], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    n_reads = fx.batch().n_reads
+    assert "%d records" % n_reads in r.stderr
+    ours, tail = _parse_bai(bai)
+    theirs, _ = _parse_bai(gen_bai)
+    assert len(tail) == 8 and int(np.frombuffer(tail, dtype=np.uint64)[0]) == 0          # no records without coordinates
+    assert len(ours) == len(theirs)
+    for (bo, lo), (bt, lt) in zip(ours, theirs):
+        meta = bo.pop(37450)
+        bt.pop(37450, None)
+        assert set(bo) == set(bt)                                                         # the same bins are populated
+        assert int(meta[1, 0]) + int(meta[1, 1]) == n_reads                               # mapped + unmapped
+        for b in bo:
+            # the bin's first chunk starts at the same record; chunk ends may name the same stream position differently
+            # (end of one BGZF block == start of the next), so they are checked through the region queries below
+            assert bo[b][0, 0] == bt[b][0, 0]
+        n = min(len(lo), len(lt))
+        assert np.array_equal(lo[:n], lt[:n])                                             # linear index
+    # region queries through our index
+    rng = np.random.default_rng(3)
+    for _ in range(6):
+        beg = int(rng.integers(0, fx.contig_len - 200)); end = beg + int(rng.integers(1, 4000))
+        end = min(end, fx.contig_len)
+        out = tmp_path / "q.bin"
+        rr = subprocess.run([str(EXE), "_fetch", bam, "chr1:%d-%d" % (beg + 1, end), str(out)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert rr.returncode == 0, rr.stderr
+        got = _load(out)
+        pos, meta_, co, bo_, cig, qual, seq, idx = _expected(fx, beg, end)
+        assert np.array_equal(got["pos"], pos[idx])
+
+
+@pytest.mark.skipif(not pbtest.have_ref(), reason="reference binary not built (needs /root/reference)")
+def test_reference_reads_our_index(tmp_path):
+    """The unmodified reference, given the index `popbam index` wrote, prints its golden output."""
+    popbam_b200.build()
+    fx = pbtest.fixture("c1")
+    bam, fa = fx.write_files(tmp_path / "c1")
+    r = subprocess.run([str(EXE), "index", bam], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    out = pbtest.run_ref(["nucdiv", "-w", "10", "-f", fa, bam, "chr1"])
+    assert out == (pbtest.GOLDEN / "nucdiv_c1.txt").read_text()
