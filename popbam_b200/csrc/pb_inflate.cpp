@@ -264,9 +264,10 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
             e = LL[br.peek(kLitLenBits)];
             const uint8_t *src = op - dist;
             if (dist >= 8 && (size_t)(oend - op) >= len + 8) {
-                uint8_t *dst = op;
-                const uint8_t *s = src;
-                for (uint32_t k = 0; k < len; k += 8) { uint64_t w; memcpy(&w, s + k, 8); memcpy(dst + k, &w, 8); }
+                // most matches of read data are short: one unconditional 8-byte move, more only when needed
+                uint64_t w;
+                memcpy(&w, src, 8); memcpy(op, &w, 8);
+                for (uint32_t k = 8; k < len; k += 8) { memcpy(&w, src + k, 8); memcpy(op + k, &w, 8); }
                 op += len;
             } else {
                 for (uint32_t k = 0; k < len; ++k) op[k] = src[k];
