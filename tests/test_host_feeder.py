@@ -77,6 +77,18 @@ def test_cli_errors_without_gpu(tmp_path):
     assert r.returncode == 1 and "does not exist" in r.stderr
     r = subprocess.run([str(EXE), "frobnicate"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "unrecognized command" in r.stderr
+    # errors the reference raises before it touches the data (tree: pop_tree.cpp:621-625; all: popbam.cpp:157-166, :130)
+    fx = pbtest.fixture("edge")
+    bam, fa = fx.write_files(tmp_path / "edge")
+    r = subprocess.run([str(EXE), "tree", "-d", "kimura", "-f", fa, bam, "chr1"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "kimura is not a valid distance option" in r.stderr
+    r = subprocess.run([str(EXE), "nucdiv", "-f", fa, bam, "chrZ"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Bad genome coordinates: chrZ" in r.stderr
+    r = subprocess.run([str(EXE), "index"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Usage" in r.stderr
+    (tmp_path / "noidx.bam").write_bytes(open(bam, "rb").read())
+    r = subprocess.run([str(EXE), "sfs", "-f", fa, str(tmp_path / "noidx.bam"), "chr1"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Index file not available" in r.stderr
 
 
 def _bgzf_block(payload, level, strategy):
