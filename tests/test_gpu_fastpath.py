@@ -102,3 +102,20 @@ def test_bit_sliced_path_region_shapes(name, pkw, windows):
     assert_same(got, ref, AN_NAMES)
     assert_same(got, want, AN_NAMES)
     orc.close(); fast.close(); classic.close(); fx.close()
+
+
+def test_depth_cap_binds_after_the_planes_were_built():
+    """The plane pass runs before the host knows the depth bound; when the cap turns out to bind, the region falls back to
+    k_pileup_call (base codes built then, quality levels taken from the plane pass) and must still equal the oracle."""
+    fx = pbtest.Fixture(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=26.0, snp_density=0.04, het_frac=0.3, seed=71)
+    p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=fx.n_samples - 1, max_depth=14)
+    wb, we = pbtest.window_grid(0, fx.contig_len, 3000)
+    an = 0
+    for a in AN_NAMES:
+        an |= pbtest.AN[a]
+    ctx = run_gpu(fx, p, an, wb, we)
+    orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
+    got, want = pbtest.result_arrays(ctx.res), pbtest.result_arrays(orc.res)
+    assert int(want["segsites"].sum()) > 0
+    assert_same(got, want, AN_NAMES)
+    orc.close(); ctx.close(); fx.close()
