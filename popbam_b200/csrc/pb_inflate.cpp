@@ -257,7 +257,8 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
             if (d & kSub) { br.drop(kDistBits); d = DD[(d >> 16) + br.peek((int)((d >> 8) & 31))]; }
             if (!(d & 0xff) || (d & kEob)) return false;
             br.drop((int)(d & 0xff));
-            if (br.n < 13) br.refill();
+            // no refill needed here: the buffer held >= 56 bits when this symbol started (refilled before the look-ahead)
+            // and a length (15 + 5) plus a distance (15 + 13) take at most 48
             const uint32_t dist = (d >> 16) + br.take((int)((d >> 8) & 31));
             if (dist > (size_t)(op - out) || len > (size_t)(oend - op)) return false;
             br.refill();
