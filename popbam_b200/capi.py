@@ -15,7 +15,7 @@ FLAG = dict(ILLUMINA=0x02, SUBSTITUTE=0x10, HETEROZYGOTE=0x20, OUTGROUP=0x40, EM
 
 EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_version", "pb_set_contig", "pb_region_begin", "pb_push_batch",
            "pb_push_record", "pb_region_end", "pb_region_launch", "pb_region_wait", "pb_region_relaunch", "pb_stream",
-           "pb_kernel_launches", "pb_stage_times", "pb_window_grid", "pb_build_errmod_tables", "pb_format_window"]
+           "pb_kernel_launches", "pb_region_path", "pb_region_reruns", "pb_stage_times", "pb_window_grid", "pb_build_errmod_tables", "pb_format_window"]
 
 
 def _p(t):
@@ -113,6 +113,8 @@ def lib():
         L.pb_kernel_launches.restype = C.c_int64
         L.pb_kernel_launches.argtypes = [C.c_void_p]
         L.pb_stage_times.argtypes = [C.c_void_p, _p(C.c_double)]
+        L.pb_region_path.argtypes = [C.c_void_p]
+        L.pb_region_reruns.argtypes = [C.c_void_p]
         L.pb_window_grid.restype = C.c_int64
         L.pb_window_grid.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _p(C.c_int32), _p(C.c_int32)]
         L.pb_build_errmod_tables.argtypes = [_p(C.c_double)] * 3
@@ -189,6 +191,13 @@ class Context:
 
     def kernel_launches(self):
         return self.L.pb_kernel_launches(self.h)
+
+    def path(self):
+        """1: the last region took the bit-sliced pileup kernels, 0: the single-kernel pileup."""
+        return self.L.pb_region_path(self.h)
+
+    def reruns(self):
+        return self.L.pb_region_reruns(self.h)
 
     def text(self, analysis, opts, windows=None):
         out = []

@@ -41,6 +41,13 @@ struct PbCounters {               // device-side region counters (one cudaMemcpy
     int nocap;                        // depth_bound <= max_depth: the raw-depth cap can never bind
     unsigned char qrank[64];          // quality value -> level
     unsigned char qval[64];           // level -> quality value (ascending)
+    // bit-sliced path (pb_fast.cuh): the cells it hands to k_hard_cells, and the assumptions it verified
+    unsigned long long n_cells;       // directory entries written
+    unsigned long long n_codes;       // base-code slots reserved in the arena
+    int arena_overflow;               // the directory or the code arena was too small: results incomplete
+    int spec_fail;                    // launched for a smaller max_span, or the depth cap can bind after all
+    int qual_over;                    // a base quality above the assumed ceiling was seen ...
+    int qual_max_seen;                // ... and this is the largest (adjusted) one
 };
 
 // ------------------------------------------------------------------------------------------------

@@ -22,6 +22,7 @@ namespace {
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
+    bool listed = false;     // registered in pb_ctx::bufs (done by dev_reserve), so pb_destroy frees every buffer ever allocated
 };
 struct HostBuf {
     void *p = nullptr;
@@ -41,7 +42,7 @@ struct pb_ctx {
     int64_t launches = 0;
     int n_sms = 148;
     // grids of the persistent (grid-stride) kernels: SM count x resident CTAs per SM, so every launch is one full wave
-    int g_encode = 148, g_bitplanes = 148, g_qual_mask = 148, g_read_prep = 148, g_strip_index = 148;
+    int g_encode = 148, g_qual_mask = 148, g_hard_cells = 148, g_read_prep = 148, g_strip_index = 148;
     size_t smem_optin = 0;
     // tables / contig
     DevBuf d_fk, d_beta, d_lhet, d_ref, d_rms_thr;
@@ -61,8 +62,16 @@ struct pb_ctx {
     // derived
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
-    DevBuf d_planes, d_fastp, d_cov32, d_acc, d_sidx;     // bit-sliced path: code planes P|B0|B1|H, PbFastParams, cov32|hard32
+    DevBuf d_fastp, d_cov32, d_acc, d_sidx;     // bit-sliced path: PbFastParams, cov32, per-position accumulators, strip index
+    DevBuf d_cells, d_codes16, d_need_raw;      // cells left for k_hard_cells (directory + base codes), need_raw[64][256]
+    std::vector<DevBuf *> bufs;            // every device buffer of the context
     bool classic = false;                  // POPBAM_B200_PILEUP=classic: always k_pileup_call (A/B measurements)
+    int qual_ceiling = 41;                 // assumed largest base quality (pb_fast.cuh: checked on the device, raised on violation)
+    int arena_scale = 1;                   // cell arena size factor (raised on overflow)
+    bool need_raw_valid = false;
+    bool ran_fast = false;                 // the last pipeline run took the bit-sliced path
+    int force_classic = 0;                 // the bit-sliced path gave up on this region (arena overflow twice): k_pileup_call
+    int reruns = 0;                        // regions run again because an assumption of the bit-sliced path did not hold
     DevBuf d_seg_type;     // arena of the segregating-site arrays (seg_layout)
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wall_u, d_stats, d_ld_kt, d_ld_km, d_ld_inv, d_ld_cnt;
     // pinned results
@@ -122,6 +131,7 @@ int dev_reserve(pb_ctx *c, DevBuf &b, size_t bytes, size_t keep = 0) {
     }
     if (b.p) cudaFree(b.p);
     b.p = np; b.cap = want;
+    if (!b.listed) { c->bufs.push_back(&b); b.listed = true; }
     return PB_OK;
 }
 int host_reserve(pb_ctx *c, HostBuf &b, size_t bytes) {
@@ -205,7 +215,7 @@ int exclusive_scan_u32(pb_ctx *c, uint32_t *data, int64_t n, cudaStream_t st) {
 }
 
 
-int run_pipeline(pb_ctx *c) {
+int run_pipeline(pb_ctx *c, int attempt = 0) {
     const pb_params &P = c->prm;
     const int n = P.n_samples, NW = c->nw;
     const int64_t N = c->n_reads;
@@ -261,12 +271,15 @@ int run_pipeline(pb_ctx *c) {
                                                dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
                                                dp<int4>(c->d_srec));
     c->launches += 2;
-    // (decided below as `planes_early`) the bit-sliced path's strip index and zeroed accumulators, still on the per-read stream
-    const bool planes_early = !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && N > 0 &&
-                              P.min_baseQ + (illumina ? 31 : 0) <= 128;
+    // The bit-sliced path (pb_fast.cuh) is tried when nobody wants the per-cell words and an empty cell is simply "not
+    // covered" (min_depth, min_snpQ > 0); whether it can be TAKEN also needs the depth bound from the device.  Its strip
+    // index and zeroed accumulators are prepared on the per-read stream.
+    const int qoff = illumina ? 31 : 0;
+    const bool fast_try = !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && !c->force_classic && N > 0 &&
+                          P.min_baseQ + qoff <= 128 && span * n < (int64_t)0x7fffffff;
     const int n_strips = (int)((span + 31) >> 5), fNI = n_strips + PB_SIDX_MMAX + 2;
     PB_TRY(dev_reserve(c, c->d_site_type, sizeof(uint64_t) * (size_t)span));
-    if (planes_early) {
+    if (fast_try) {
         PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
         PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
         k_strip_index<<<c->g_strip_index, 256, 0, s2>>>(dp<int4>(c->d_srec), dp<uint32_t>(c->d_sstart), n, c->span_beg, ctr, fNI, dp<uint32_t>(c->d_sidx));
@@ -277,70 +290,76 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaEventRecord(c->fk[2], s2));
     if (c->dbg[1]) cudaEventRecord(c->dbg[1], s2);
     if (c->dbg[2]) cudaEventRecord(c->dbg[2], st);
-    // -- per-base chain on the main stream: quality values present, level table, base codes
-    // The bit-planes of the default pileup path are built here, before the host knows whether that path will be
-    // taken (it needs the depth bound): the pass also collects the quality values present, which the single-kernel
-    // path gets from k_qual_mask.  Wasted only when the depth cap turns out to bind.
-    if (planes_early) {
-        const size_t plw = (size_t)((c->n_bytes + 31) >> 5) + 1 + PB_PLANE_PAD;
-        PB_TRY(dev_reserve(c, c->d_planes, sizeof(uint4) * plw));
-        k_planes<<<c->g_bitplanes, 256, 0, st>>>(N, dp<uint32_t>(c->d_meta), n, dp<uint64_t>(c->d_base), dp<uint8_t>(c->d_seq4),
-                                                 dp<uint8_t>(c->d_qual), c->n_bytes, (double)N / (double)std::max<int64_t>(c->n_bytes, 1), P.min_mapQ,
-                                                 P.min_baseQ, illumina, ctr, dp<uint4>(c->d_planes));
-        if (c->dbg[3]) cudaEventRecord(c->dbg[3], st);
-        c->launches += 1;
-    } else if (N > 0) {
-        k_qual_mask<<<c->g_qual_mask, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
-        c->launches += 1;
-    }
-    PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[1], 0));
-    k_level_table<<<1, 32, 0, st>>>(ctr);
-    c->launches += 1;
-    if (N > 0) {
-        PB_TRY(dev_reserve(c, c->d_qtab, 64 * 256));
-        k_qual_table<<<64, 256, 0, st>>>(ctr, illumina, P.min_baseQ, dp<uint8_t>(c->d_qtab));
-        c->launches += 1;
-    }
-    PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));                // join
-    PB_CUDA(c, cudaGetLastError());
-    PB_TRY(host_reserve(c, c->h_ctr, sizeof(PbCounters)));
-    PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
-    PB_CUDA(c, cudaEventRecord(c->ev[1], st));
-    PB_CUDA(c, cudaStreamSynchronize(st));
-    c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
-    if (c->dbg[0] && planes_early) {
-        float t[5] = {0, 0, 0, 0, 0};
-        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], c->ev[0], c->dbg[i]);
-        cudaEventElapsedTime(&t[4], c->ev[0], c->ev[1]);
-        fprintf(stderr, "[popbam_b200] prep timeline (ms after start): read_prep done %.3f, per-read chain done %.3f | planes start %.3f, planes done %.3f | prep done %.3f\n",
-                t[0], t[1], t[2], t[3], t[4]);
-    }
-    if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
-    if (c->ctr_host.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
-
-    // ---- the hot kernel
-    PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
-    if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
-    const int nl = c->ctr_host.n_levels;
-    // the walk-free shortcut table only depends on the level set: rebuild it when that changes
-    if (!c->need_valid || c->need_nl != nl || memcmp(c->need_qval, c->ctr_host.qval, 64) != 0) {
+    // -- quality levels on the main stream.  Bit-sliced path: the RANGE of levels a passing base can have (no pass over
+    // the bases).  Single-kernel path: the values present (k_qual_mask), as its per-cell histograms are sized by them.
+    auto need_tables = [&](const unsigned char *qval, int nl) -> int {
+        // the walk-free shortcut table and the depth ranges only depend on the level set: rebuild them when that changes
+        if (c->need_valid && c->need_nl == nl && memcmp(c->need_qval, qval, 64) == 0) return PB_OK;
         PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
         k_need_table<<<std::max(nl, 1), 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
         PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastParams)));
         k_fast_params<<<1, 64, 0, st>>>(ctr, dp<uint8_t>(c->d_need), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<PbFastParams>(c->d_fastp));
         c->launches += 2;
         PB_CUDA(c, cudaGetLastError());
-        c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, c->ctr_host.qval, 64);
+        c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, qval, 64);
+        return PB_OK;
+    };
+    auto classic_levels = [&]() -> int {
+        if (N > 0) {
+            k_qual_mask<<<c->g_qual_mask, 256, 0, st>>>(dp<uint8_t>(c->d_qual), c->n_bytes, illumina, P.min_baseQ, ctr);
+            c->launches += 1;
+        }
+        PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[1], 0));
+        k_level_table<<<1, 32, 0, st>>>(ctr);
+        c->launches += 1;
+        if (N > 0) {
+            PB_TRY(dev_reserve(c, c->d_qtab, 64 * 256));
+            k_qual_table<<<64, 256, 0, st>>>(ctr, illumina, P.min_baseQ, dp<uint8_t>(c->d_qtab));
+            c->launches += 1;
+        }
+        return PB_OK;
+    };
+    if (fast_try) {
+        const int qlo = std::max(4, std::min(63, std::min(P.min_baseQ, P.min_mapQ)));
+        const int qhi = std::max(qlo, std::min(63, c->qual_ceiling));
+        unsigned char qv[64] = {0};
+        for (int q = qlo; q <= qhi; ++q) qv[q - qlo] = (unsigned char)q;
+        k_set_levels<<<1, 64, 0, st>>>(ctr, qlo, qhi);
+        c->launches += 1;
+        PB_TRY(need_tables(qv, qhi - qlo + 1));
+        if (!c->need_raw_valid) {
+            PB_TRY(dev_reserve(c, c->d_need_raw, 64 * 256));
+            k_need_raw<<<64, 256, 0, st>>>(dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need_raw));
+            c->launches += 1;
+            c->need_raw_valid = true;
+        }
+    } else {
+        PB_TRY(classic_levels());
     }
-    // 256-thread CTAs (40 resident warps per SM) when their shared memory stays small, else 128-thread CTAs
-    const bool big = pb_pile_smem(256, nl) <= 46 * 1024;
-    const int tp = big ? 256 : 128;
-    const size_t smem = pb_pile_smem(tp, nl);
-    if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d quality levels exceeds %zu bytes", nl, c->smem_optin);
+    PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));                // join
+    PB_CUDA(c, cudaGetLastError());
+    PB_TRY(host_reserve(c, c->h_ctr, 3 * sizeof(PbCounters) + 64));
+    PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
+    PB_CUDA(c, cudaEventRecord(c->ev[1], st));
+    PB_CUDA(c, cudaStreamSynchronize(st));
+    c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
+    if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
+    if (c->ctr_host.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
+
+    // ---- the hot kernel
+    PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
+    if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
     const bool cap = c->ctr_host.nocap == 0;
-    void (*kern)(const PbPileArgs) = big ? (cap ? k_pileup_call<256, true> : k_pileup_call<256, false>)
-                                         : (cap ? k_pileup_call<128, true> : k_pileup_call<128, false>);
-    PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int fast_w = pb_fast_words(c->ctr_host.max_span);
+    const bool fast = fast_try && !cap && fast_w <= PB_FAST_WMAX;
+    if (fast_try && !fast) {
+        // the depth cap can bind (or a read is too long for the staged planes): the single-kernel path needs the levels present
+        PB_TRY(classic_levels());
+        PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(c, cudaStreamSynchronize(st));
+        c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
+    }
+    const int nl = c->ctr_host.n_levels;
     PbPileArgs pa;
     pa.srec = dp<int4>(c->d_srec); pa.sstart = dp<uint32_t>(c->d_sstart);
     pa.codes = nullptr;
@@ -356,54 +375,62 @@ int run_pipeline(pb_ctx *c) {
     pa.rms_thr = dp<int32_t>(c->d_rms_thr);
     pa.site_type = dp<uint64_t>(c->d_site_type); pa.site_flag = dp<uint8_t>(c->d_site_flag);
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
-    PB_CUDA(c, cudaEventRecord(c->ev[6], st));     // the per-base pass (planes or codes) counts as preparation: ev[6] .. ev[2]
-    // Bit-sliced path (pb_fast.cuh) when the depth cap cannot bind, nobody wants the per-cell words, and an
-    // empty cell is simply "not covered" (min_depth, min_snpQ > 0); k_pileup_call otherwise.
-    const int fast_w = pb_fast_words(c->ctr_host.max_span);
-    const bool fast = !cap && planes_early &&
-                      pb_hard_smem(nl) <= c->smem_optin && span * n < (int64_t)0x7fffffff && fast_w <= PB_PLANE_PAD &&
-                      pb_fast_smem(fast_w) <= 100 * 1024;
+    PB_CUDA(c, cudaEventRecord(c->ev[6], st));     // a per-base pass of the single-kernel path (base codes) counts as preparation: ev[6] .. ev[2]
     if (getenv("POPBAM_B200_DEBUG"))
-        fprintf(stderr, "[popbam_b200] pileup path: fast=%d cap=%d want_cb=%d min_depth=%d min_snpQ=%d classic=%d N=%lld nl=%d hard_smem=%zu optin=%zu fast_w=%d fast_smem=%zu depth_bound=%d max_span=%d\n",
-                (int)fast, (int)cap, (int)want_cb, P.min_depth, P.min_snpQ, (int)c->classic, (long long)N, nl, pb_hard_smem(nl), c->smem_optin,
-                fast_w, pb_fast_smem(fast_w), c->ctr_host.depth_bound, c->ctr_host.max_span);
+        fprintf(stderr, "[popbam_b200] pileup path: fast=%d cap=%d want_cb=%d min_depth=%d min_snpQ=%d classic=%d N=%lld nl=%d fast_w=%d fast_smem=%zu depth_bound=%d max_span=%d ceiling=%d\n",
+                (int)fast, (int)cap, (int)want_cb, P.min_depth, P.min_snpQ, (int)c->classic, (long long)N, nl,
+                fast_w, pb_fast_smem(fast_w), c->ctr_host.depth_bound, c->ctr_host.max_span, c->qual_ceiling);
+    c->ran_fast = fast;
     if (fast) {
-        PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * (3 * (size_t)n * n_strips + 1)));
-        const int fM = (c->ctr_host.max_span + 31) >> 5;
-        uint4 *pl = dp<uint4>(c->d_planes);
+        PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * ((size_t)n * n_strips + 1)));
         const size_t rpw = (size_t)((c->ref_len + 31) >> 5) + 2;
         const uint32_t *rp = dp<uint32_t>(c->d_refpl);
+        // arena of the cells left for k_hard_cells: room for one cell in eight and one base in eight (times arena_scale);
+        // k_pile_fast reports an overflow, the region is then run again with a larger arena
+        const unsigned long long cell_cap = std::max<unsigned long long>(65536, (unsigned long long)span * n / 8 * c->arena_scale);
+        const unsigned long long code_cap = std::min<unsigned long long>(0xfffffff0ULL, std::max<unsigned long long>(1 << 20, (unsigned long long)c->n_bytes / 8 * c->arena_scale));
+        PB_TRY(dev_reserve(c, c->d_cells, sizeof(uint4) * cell_cap));
+        PB_TRY(dev_reserve(c, c->d_codes16, sizeof(uint16_t) * code_cap));
         PB_CUDA(c, cudaEventRecord(c->ev[2], st));
         PbFastArgs fa;
-        fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.M = fM; fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
-        fa.planes = pl;
+        fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
+        fa.qual = dp<uint8_t>(c->d_qual); fa.seq4 = dp<uint8_t>(c->d_seq4);
         fa.r0 = rp; fa.r1 = rp + rpw; fa.rv = rp + 2 * rpw;
         fa.ref_len = c->ref_len; fa.span_beg = c->span_beg; fa.span_end = c->span_end;
-        fa.n_samples = n; fa.n_strips = n_strips; fa.n_sblocks = (n_strips + PB_FAST_STRIPS - 1) / PB_FAST_STRIPS;
-        fa.W = fast_w; fa.max_span = c->ctr_host.max_span;
-        fa.min_depth = P.min_depth; fa.min_rmsQ = P.min_rmsQ;
+        fa.n_samples = n; fa.n_strips = n_strips;
+        fa.min_depth = P.min_depth; fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
+        fa.qual_ceiling = std::min(63, c->qual_ceiling);
+        fa.W = fast_w;
         fa.ctr = ctr; fa.fp = dp<PbFastParams>(c->d_fastp);
-        fa.cov32 = dp<uint32_t>(c->d_cov32); fa.hard32 = fa.cov32 + (size_t)n * n_strips; fa.hcount = fa.hard32 + (size_t)n * n_strips;
+        fa.cov32 = dp<uint32_t>(c->d_cov32);
+        fa.cells = dp<uint4>(c->d_cells); fa.codes = dp<uint16_t>(c->d_codes16); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
+        const unsigned n_sblocks = (unsigned)((n_strips + PB_FAST_STRIPS - 1) / PB_FAST_STRIPS);
         PB_CUDA(c, cudaFuncSetAttribute(k_pile_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_fast_smem(fast_w)));
-        k_pile_fast<<<(unsigned)n * (unsigned)fa.n_sblocks, PB_FAST_STRIPS * PB_FAST_G, pb_fast_smem(fast_w), st>>>(fa);
+        k_pile_fast<<<(unsigned)n * n_sblocks, PB_FAST_THREADS, pb_fast_smem(fast_w), st>>>(fa);
         PbHardArgs ha;
-        ha.srec = pa.srec; ha.F = fa.F; ha.M = fM; ha.NI = fNI; ha.qual = dp<uint8_t>(c->d_qual); ha.seq4 = dp<uint8_t>(c->d_seq4); ha.qtab = dp<uint8_t>(c->d_qtab); ha.ref = pa.ref; ha.ref_len = pa.ref_len;
+        ha.cells = fa.cells; ha.codes = fa.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
         ha.span_beg = pa.span_beg; ha.span_end = pa.span_end; ha.win_beg = pa.win_beg; ha.win_end = pa.win_end; ha.n_windows = NW;
         ha.n_samples = n; ha.n_strips = n_strips;
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
-        ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need = pa.need;
-        ha.cov32 = fa.cov32; ha.hard32 = fa.hard32; ha.hoff = fa.hcount;
-        PB_TRY(exclusive_scan_u32(c, fa.hcount, (int64_t)n * n_strips + 1, st));
+        ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need_raw = dp<uint8_t>(c->d_need_raw);
+        ha.cov32 = fa.cov32;
         ha.acc_cov = dp<uint64_t>(c->d_acc); ha.acc_cnt4 = reinterpret_cast<uint32_t *>(ha.acc_cov + span);
         ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
-        const size_t hsm = pb_hard_smem(nl);
-        PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-        int hard_per_sm = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hard_per_sm, k_hard_cells, PB_HARD_THREADS, hsm) != cudaSuccess || hard_per_sm < 1) { cudaGetLastError(); hard_per_sm = 1; }
-        k_hard_cells<<<c->n_sms * hard_per_sm, PB_HARD_THREADS, hsm, st>>>(ha);
+        PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_hard_smem()));
+        k_hard_cells<<<c->g_hard_cells, PB_HARD_THREADS, pb_hard_smem(), st>>>(ha);
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
         c->launches += 3;
     } else {
+        PB_TRY(need_tables(c->ctr_host.qval, nl));
+        pa.need = dp<uint8_t>(c->d_need);
+        // 256-thread CTAs (40 resident warps per SM) when their shared memory stays small, else 128-thread CTAs
+        const bool big = pb_pile_smem(256, nl) <= 46 * 1024;
+        const int tp = big ? 256 : 128;
+        const size_t smem = pb_pile_smem(tp, nl);
+        if (smem > c->smem_optin) return fail(c, PB_ERR_UNSUPPORTED, "shared memory for %d quality levels exceeds %zu bytes", nl, c->smem_optin);
+        void (*kern)(const PbPileArgs) = big ? (cap ? k_pileup_call<256, true> : k_pileup_call<256, false>)
+                                             : (cap ? k_pileup_call<128, true> : k_pileup_call<128, false>);
+        PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         // base codes for k_pileup_call (the bit-sliced path reads qual[] / seq4[] directly)
         PB_TRY(dev_reserve(c, c->d_codes, (size_t)std::max<int64_t>(c->n_bytes, 1)));
         pa.codes = dp<uint8_t>(c->d_codes);
@@ -434,7 +461,28 @@ int run_pipeline(pb_ctx *c) {
     PB_CUDA(c, cudaMemcpyAsync(h_total, dl.seg_off + NW, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     const SmallLayout hl0 = small_layout(c->h_small.p, NW, P.n_pops, n, (c->analyses & PB_AN_TREE) != 0);
     PB_CUDA(c, cudaMemcpyAsync(hl0.segsites, dl.segsites, sizeof(int32_t) * (size_t)NW, cudaMemcpyDeviceToHost, st));
+    PbCounters *h_final = reinterpret_cast<PbCounters *>(reinterpret_cast<unsigned char *>(c->h_ctr.p) + 2 * sizeof(PbCounters));
+    PB_CUDA(c, cudaMemcpyAsync(h_final, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
     PB_CUDA(c, cudaStreamSynchronize(st));
+    if (fast && getenv("POPBAM_B200_DEBUG"))
+        fprintf(stderr, "[popbam_b200] bit-sliced path: %llu of %lld cells left for k_hard_cells (%.2f %%), %llu code slots; overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
+                h_final->n_cells, (long long)(span * n), 100.0 * (double)h_final->n_cells / (double)(span * n), h_final->n_codes,
+                h_final->arena_overflow, h_final->qual_over, h_final->qual_max_seen, h_final->spec_fail);
+    if (fast && (h_final->arena_overflow || h_final->qual_over || h_final->spec_fail)) {
+        // an assumption of the bit-sliced path did not hold for this region: nothing of its result is used.  Raise the
+        // quality ceiling / the arena size (both stay raised for the context) and run the region again; give up on the
+        // bit-sliced path for this region after three attempts.
+        if (getenv("POPBAM_B200_DEBUG"))
+            fprintf(stderr, "[popbam_b200] bit-sliced path: run again (arena overflow %d: %llu cells, %llu codes; quality %d above ceiling %d: %d; launch assumptions %d)\n",
+                    h_final->arena_overflow, h_final->n_cells, h_final->n_codes, h_final->qual_max_seen, c->qual_ceiling, h_final->qual_over, h_final->spec_fail);
+        if (h_final->qual_over) c->qual_ceiling = std::min(63, std::max(c->qual_ceiling + 1, h_final->qual_max_seen));
+        if (h_final->arena_overflow) c->arena_scale *= 4;
+        c->reruns += 1;
+        if (attempt >= 2 || c->arena_scale > 64) c->force_classic = 1;
+        const int rc = run_pipeline(c, attempt + 1);
+        c->force_classic = 0;
+        return rc;
+    }
     const int64_t S = *h_total;
     c->s_total = S;
     int s_max = 0;
@@ -634,8 +682,14 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
             return c->n_sms * per_sm;
         };
         c->g_encode = wave(k_encode, 256);
-        c->g_bitplanes = std::max(c->n_sms, wave(k_planes, 256) - c->n_sms);     // one CTA slot per SM left to the per-read chain on the second stream c->g_qual_mask = wave(k_qual_mask, 256);
+        c->g_qual_mask = wave(k_qual_mask, 256);
         c->g_read_prep = wave(k_read_prep, 256); c->g_strip_index = wave(k_strip_index, 256);
+        {
+            int per_sm = 0;
+            cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_hard_smem());
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hard_cells, PB_HARD_THREADS, pb_hard_smem()) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+            c->g_hard_cells = c->n_sms * per_sm;
+        }
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
@@ -670,12 +724,8 @@ void pb_destroy(pb_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->d_fk, &c->d_beta, &c->d_lhet, &c->d_ref, &c->d_rms_thr, &c->d_wbeg, &c->d_wend, &c->d_pos, &c->d_meta, &c->d_cigstart,
-                      &c->d_ncig, &c->d_base, &c->d_cigar, &c->d_seq4, &c->d_qual, &c->d_tmp_cig, &c->d_tmp_base, &c->d_rnseg,
-                      &c->d_rkey, &c->d_codes, &c->d_bins, &c->d_need, &c->d_qtab, &c->d_counts, &c->d_blocktot, &c->d_srec, &c->d_sstart, &c->d_ctr,
-                      &c->d_site_type, &c->d_site_flag, &c->d_cb, &c->d_seg_type, &c->d_hap, &c->d_kt, &c->d_km, &c->d_lsum,
-                      &c->d_rsum, &c->d_wall_u, &c->d_stats, &c->d_ld_kt, &c->d_ld_km, &c->d_ld_inv, &c->d_ld_cnt};
-    for (DevBuf *b : bufs) if (b->p) cudaFree(b->p);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    for (DevBuf *b : c->bufs) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     HostBuf *hb[] = {&c->h_ctr, &c->h_small, &c->h_seg, &c->h_span};
     for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
     for (auto &ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -745,8 +795,9 @@ int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
     PB_TRY(dev_reserve(c, c->d_ncig, 4 * (size_t)N1, 4 * (size_t)N0));
     PB_TRY(dev_reserve(c, c->d_base, 8 * (size_t)N1, 8 * (size_t)N0));
     PB_TRY(dev_reserve(c, c->d_cigar, 4 * (size_t)(c->n_cig + b->n_cigar), 4 * (size_t)c->n_cig));
-    PB_TRY(dev_reserve(c, c->d_qual, (size_t)(c->n_bytes + b->n_bases) + 16, (size_t)c->n_bytes));
-    PB_TRY(dev_reserve(c, c->d_seq4, (size_t)(c->n_bytes + b->n_bases) / 2 + 16, (size_t)c->n_bytes / 2));
+    // 64 zeroed bytes behind the last base: k_pile_fast converts whole 32-byte groups of qual[] (16 of seq4[])
+    PB_TRY(dev_reserve(c, c->d_qual, (size_t)(c->n_bytes + b->n_bases) + 96, (size_t)c->n_bytes));
+    PB_TRY(dev_reserve(c, c->d_seq4, (size_t)(c->n_bytes + b->n_bases) / 2 + 96, (size_t)c->n_bytes / 2));
     PB_TRY(dev_reserve(c, c->d_tmp_cig, 4 * (size_t)(b->n_reads + 1)));
     PB_TRY(dev_reserve(c, c->d_tmp_base, 4 * (size_t)(b->n_reads + 1)));
     PB_CUDA(c, cudaMemcpyAsync(dp<int32_t>(c->d_pos) + N0, b->pos, 4 * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
@@ -758,6 +809,8 @@ int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
         PB_CUDA(c, cudaMemcpyAsync(dp<uint8_t>(c->d_qual) + c->n_bytes, b->qual, (size_t)b->n_bases, cudaMemcpyHostToDevice, st));
         PB_CUDA(c, cudaMemcpyAsync(dp<uint8_t>(c->d_seq4) + c->n_bytes / 2, b->seq4, (size_t)b->n_bases / 2, cudaMemcpyHostToDevice, st));
     }
+    PB_CUDA(c, cudaMemsetAsync(dp<uint8_t>(c->d_qual) + c->n_bytes + b->n_bases, 0, 64, st));
+    PB_CUDA(c, cudaMemsetAsync(dp<uint8_t>(c->d_seq4) + (c->n_bytes + b->n_bases) / 2, 0, 64, st));
     k_rebase<<<nblk(b->n_reads, 256), 256, 0, st>>>(b->n_reads, N0, dp<uint32_t>(c->d_tmp_cig), dp<uint32_t>(c->d_tmp_base), (uint64_t)c->n_cig,
                                                    (uint64_t)c->n_bytes, dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint64_t>(c->d_base));
     c->launches += 1;
@@ -831,6 +884,8 @@ int pb_region_end(pb_ctx *c, pb_region_result *out) {
     return pb_region_wait(c, out);
 }
 
+int pb_region_path(const pb_ctx *c) { return c ? (c->ran_fast ? 1 : 0) : PB_ERR_ARG; }
+int pb_region_reruns(const pb_ctx *c) { return c ? c->reruns : PB_ERR_ARG; }
 void *pb_stream(pb_ctx *c) { return c ? (void *)c->stream : nullptr; }
 int64_t pb_kernel_launches(const pb_ctx *c) { return c ? c->launches : 0; }
 

@@ -16,10 +16,12 @@
 #include "pb_cell.cuh"
 
 // Hist: callable `uint32_t take(int lw)` returning the word of level-word lw and clearing it.
+// QV: anything indexable by level that yields the level's quality value (a `const uint8_t *` table of the region's
+// levels, or a per-cell view for kernels that rank the levels of every cell separately).
 // r4: rotation applied to the base index so that the lanes of a warp (different positions, different
 // reference bases) run their heavy loop -- the reference base -- in the same unrolled slot.
-template <class Hist>
-PB_HD void pb_walk_hist(Hist &take, int n_lw, const uint8_t *qval, int k, int r4, const double *fk,
+template <class Hist, class QV>
+PB_HD void pb_walk_hist(Hist &take, int n_lw, QV qval, int k, int r4, const double *fk,
                         const double *__restrict__ beta, double bsum[4], int c[4]) {
     double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
     int cc0 = 0, cc1 = 0, cc2 = 0, cc3 = 0;
@@ -81,8 +83,8 @@ PB_HD float pb_unanimous_het(const double *__restrict__ lhet, int k, int b) {
 // Walk of a unanimous cell: only byte b of every histogram word is populated.  Returns true when it
 // stopped early (result fully determined by hmin); otherwise *bsum_b is the complete sum.
 // `peek(lw)` returns a word; the caller clears the histogram afterwards.
-template <class Hist>
-PB_HD bool pb_walk_unanimous(Hist &peek, int n_lw, const uint8_t *qval, int k, int b, const double *fk,
+template <class Hist, class QV>
+PB_HD bool pb_walk_unanimous(Hist &peek, int n_lw, QV qval, int k, int b, const double *fk,
                              const double *__restrict__ beta, float hmin, double *bsum_b) {
     double acc = 0.0;
     int c = 0, wf = 0, wr = 0;
@@ -112,8 +114,8 @@ PB_HD bool pb_tot4_unanimous(uint32_t tot4) {
 
 // call_base for a cell whose bases all agree (tot4 has one populated byte): errmod_cal + gl2cns + rms
 // packing (popbam.cpp:288-298) with the early exit described above.  The histogram is only read.
-template <class Hist>
-PB_HD uint64_t pb_call_unanimous(Hist &peek, int n_lw, const uint8_t *qval, uint32_t tot4, int rmsq, const double *fk,
+template <class Hist, class QV>
+PB_HD uint64_t pb_call_unanimous(Hist &peek, int n_lw, QV qval, uint32_t tot4, int rmsq, const double *fk,
                                  const double *__restrict__ beta, const double *__restrict__ lhet) {
     const int b = (tot4 >> 8 & 255u) ? 1 : (tot4 >> 16 & 255u) ? 2 : (tot4 >> 24) ? 3 : 0;
     const int k = pb_tot4_k(tot4);
@@ -133,8 +135,8 @@ PB_HD uint64_t pb_call_unanimous(Hist &peek, int n_lw, const uint8_t *qval, uint
 }
 
 // call_base for any cell with k > 0 bases (the general path).  Leaves the histogram cleared.
-template <class Hist>
-PB_HD uint64_t pb_call_general(Hist &take, int n_lw, const uint8_t *qval, uint32_t tot4, int rmsq, const double *fk,
+template <class Hist, class QV>
+PB_HD uint64_t pb_call_general(Hist &take, int n_lw, QV qval, uint32_t tot4, int rmsq, const double *fk,
                                const double *__restrict__ beta, const double *__restrict__ lhet) {
     double bsum[4];
     int c[4];
@@ -156,7 +158,8 @@ PB_HD uint64_t pb_call_general(Hist &take, int n_lw, const uint8_t *qval, uint32
 // need[L][k] is the smallest m with float(LB(L,k,m)) >= max(het values of k); a cell with cum >= need
 // therefore has float(bsum) >= its het value and takes the shortcut result without touching beta.
 // 0 means "never".  One table per region (the levels are per region), built by k_need_table.
-PB_HD uint8_t pb_need_entry(int L, int nl, const uint8_t *qval, int k, const double *fk, const double *__restrict__ beta,
+template <class QV>
+PB_HD uint8_t pb_need_entry(int L, int nl, QV qval, int k, const double *fk, const double *__restrict__ beta,
                             const double *__restrict__ lhet) {
     if (k < 1 || k > 255) return 0;
     const float h0 = pb_unanimous_het(lhet, k, 0), h3 = pb_unanimous_het(lhet, k, 3);    // the two het values
@@ -228,6 +231,22 @@ PB_HD uint64_t pb_unanimous_result(const double *__restrict__ lhet, int k, int b
     const uint64_t rms = (uint64_t)PB_DADD((double)PB_FSQRT(PB_FDIV((float)rmsq, (float)k)), 0.499);
     return cb | rms << 48;
 }
+
+// The same test for a kernel that ranks the quality levels of every cell separately (qval[L]: the cell's own
+// ascending quality values): need_raw[q][k] is pb_need_entry for the level set {q, q+1, ..., 63}, a lower bound
+// that holds whatever higher levels the cell contains.
+template <class Hist, class QV>
+PB_HD bool pb_unanimous_by_count_raw(Hist &peek, int nl, QV qval, const uint8_t *__restrict__ need_raw, int k, int b) {
+    int cum = 0;
+    for (int L = nl - 1; L >= 0; --L) {
+        cum += (int)((peek(2 * L) >> (8 * b)) & 255u) + (int)((peek(2 * L + 1) >> (8 * b)) & 255u);
+        const int nd = PB_LDG(need_raw + (int)qval[L] * 256 + k);
+        if (nd && cum >= nd) return true;
+        if (cum == k) break;
+    }
+    return false;
+}
+struct PbIota { int base; PB_HD int operator[](int i) const { return base + i; } };   // level set {base, base + 1, ...}
 
 // need: [nl][256].  Returns true when the cell provably takes the shortcut.
 template <class Hist>
