@@ -48,6 +48,8 @@ struct PbCounters {               // device-side region counters (one cudaMemcpy
     int spec_fail;                    // launched for a smaller max_span, or the depth cap can bind after all
     int qual_over;                    // a base quality above the assumed ceiling was seen ...
     int qual_max_seen;                // ... and this is the largest (adjusted) one
+    int qual_high;                    // a quality byte >= 128 was seen by the kernel variant that assumes there is none
+    unsigned int n_records;           // aligned-segment records of the region (all samples)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -502,9 +504,11 @@ __global__ void __launch_bounds__(PB_SCAN_THREADS) k_scan_add(uint32_t *data, in
 }
 // sample start offsets: the count matrix has one extra trailing element, so after the exclusive scan
 // offs[s * n_chunks] is the start of sample s for s < n and the total for s == n
-__global__ void k_sample_starts(const uint32_t *__restrict__ offs, int n_samples, int64_t n_chunks, uint32_t *__restrict__ sstart) {
+__global__ void k_sample_starts(const uint32_t *__restrict__ offs, int n_samples, int64_t n_chunks, uint32_t *__restrict__ sstart,
+                                PbCounters *__restrict__ ctr) {
     const int s = threadIdx.x;
     if (s <= n_samples) sstart[s] = offs[(int64_t)s * n_chunks];
+    if (s == n_samples) ctr->n_records = offs[(int64_t)s * n_chunks];
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -46,7 +46,6 @@ struct pb_ctx {
     size_t smem_optin = 0;
     // tables / contig
     DevBuf d_fk, d_beta, d_lhet, d_ref, d_rms_thr;
-    DevBuf d_refpl;        // reference bit-planes of the contig (k_ref_planes): R0 | R1 | RV
     int64_t ref_len = 0;
     int32_t ref_tid = -1;
     // region
@@ -67,6 +66,7 @@ struct pb_ctx {
     std::vector<DevBuf *> bufs;            // every device buffer of the context
     bool classic = false;                  // POPBAM_B200_PILEUP=classic: always k_pileup_call (A/B measurements)
     int qual_ceiling = 41;                 // assumed largest base quality (pb_fast.cuh: checked on the device, raised on violation)
+    bool qual_robust = false;              // quality bytes >= 128 occur: kernel variant whose packed compares are right for any byte
     int arena_scale = 1;                   // cell arena size factor (raised on overflow)
     bool need_raw_valid = false;
     bool ran_fast = false;                 // the last pipeline run took the bit-sliced path
@@ -265,7 +265,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
                                              dp<uint32_t>(c->d_counts));
     c->launches += 2;
     PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts, s2));
-    k_sample_starts<<<1, 128, 0, s2>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart));
+    k_sample_starts<<<1, 128, 0, s2>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart), ctr);
     k_part_scatter<<<part_blocks, 128, 0, s2>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts),
                                                dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
                                                dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
@@ -297,9 +297,12 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
         if (c->need_valid && c->need_nl == nl && memcmp(c->need_qval, qval, 64) == 0) return PB_OK;
         PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
         k_need_table<<<std::max(nl, 1), 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
-        PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastParams)));
-        k_fast_params<<<1, 64, 0, st>>>(ctr, dp<uint8_t>(c->d_need), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<PbFastParams>(c->d_fastp));
-        c->launches += 2;
+        c->launches += 1;
+        if (fast_try) {
+            PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastTables)));
+            k_fast_tables<<<1, 256, 0, st>>>(ctr, dp<uint8_t>(c->d_need), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), P.min_depth, dp<PbFastTables>(c->d_fastp));
+            c->launches += 1;
+        }
         PB_CUDA(c, cudaGetLastError());
         c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, qval, 64);
         return PB_OK;
@@ -350,8 +353,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
     PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
     if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
     const bool cap = c->ctr_host.nocap == 0;
-    const int fast_w = pb_fast_words(c->ctr_host.max_span);
-    const bool fast = fast_try && !cap && fast_w <= PB_FAST_WMAX;
+    const bool fast = fast_try && !cap && pb_cnt_smem(1, c->ctr_host.max_span) <= c->smem_optin && pb_cnt_qslot(c->ctr_host.max_span) <= 16 + 16 * 32;
     if (fast_try && !fast) {
         // the depth cap can bind (or a read is too long for the staged planes): the single-kernel path needs the levels present
         PB_TRY(classic_levels());
@@ -377,36 +379,47 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
     pa.cb_out = want_cb ? dp<uint64_t>(c->d_cb) : nullptr;
     PB_CUDA(c, cudaEventRecord(c->ev[6], st));     // a per-base pass of the single-kernel path (base codes) counts as preparation: ev[6] .. ev[2]
     if (getenv("POPBAM_B200_DEBUG"))
-        fprintf(stderr, "[popbam_b200] pileup path: fast=%d cap=%d want_cb=%d min_depth=%d min_snpQ=%d classic=%d N=%lld nl=%d fast_w=%d fast_smem=%zu depth_bound=%d max_span=%d ceiling=%d\n",
-                (int)fast, (int)cap, (int)want_cb, P.min_depth, P.min_snpQ, (int)c->classic, (long long)N, nl,
-                fast_w, pb_fast_smem(fast_w), c->ctr_host.depth_bound, c->ctr_host.max_span, c->qual_ceiling);
+        fprintf(stderr, "[popbam_b200] pileup path: fast=%d cap=%d want_cb=%d min_depth=%d min_snpQ=%d classic=%d N=%lld records=%u nl=%d depth_bound=%d max_span=%d ceiling=%d robust=%d\n",
+                (int)fast, (int)cap, (int)want_cb, P.min_depth, P.min_snpQ, (int)c->classic, (long long)N, c->ctr_host.n_records, nl,
+                c->ctr_host.depth_bound, c->ctr_host.max_span, c->qual_ceiling, (int)c->qual_robust);
     c->ran_fast = fast;
     if (fast) {
         PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * ((size_t)n * n_strips + 1)));
-        const size_t rpw = (size_t)((c->ref_len + 31) >> 5) + 2;
-        const uint32_t *rp = dp<uint32_t>(c->d_refpl);
         // arena of the cells left for k_hard_cells: room for one cell in eight and one base in eight (times arena_scale);
-        // k_pile_fast reports an overflow, the region is then run again with a larger arena
+        // k_pile_count reports an overflow, the region is then run again with a larger arena
         const unsigned long long cell_cap = std::max<unsigned long long>(65536, (unsigned long long)span * n / 8 * c->arena_scale);
         const unsigned long long code_cap = std::min<unsigned long long>(0xfffffff0ULL, std::max<unsigned long long>(1 << 20, (unsigned long long)c->n_bytes / 8 * c->arena_scale));
         PB_TRY(dev_reserve(c, c->d_cells, sizeof(uint4) * cell_cap));
         PB_TRY(dev_reserve(c, c->d_codes16, sizeof(uint16_t) * code_cap));
         PB_CUDA(c, cudaEventRecord(c->ev[2], st));
-        PbFastArgs fa;
-        fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.NI = fNI; fa.RC = pb_fast_rc(fast_w);
+        // strips per CTA: a CTA stages one record per thread and pass, so its positions should hold about that many records
+        const int ms = c->ctr_host.max_span;
+        const double density = std::max(1e-6, (double)c->ctr_host.n_records / ((double)n * (double)std::max<int64_t>(span, 1)));   // records starting per position and sample
+        int spc = (int)((0.92 * PB_CNT_THREADS / density - ms) / 32.0);
+        spc = std::max(1, std::min(PB_CNT_SPC_MAX, spc));
+        while (spc > 1 && pb_cnt_smem(spc, ms) > c->smem_optin) --spc;
+        PbCountArgs fa;
+        fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.NI = fNI;
         fa.qual = dp<uint8_t>(c->d_qual); fa.seq4 = dp<uint8_t>(c->d_seq4);
-        fa.r0 = rp; fa.r1 = rp + rpw; fa.rv = rp + 2 * rpw;
-        fa.ref_len = c->ref_len; fa.span_beg = c->span_beg; fa.span_end = c->span_end;
-        fa.n_samples = n; fa.n_strips = n_strips;
-        fa.min_depth = P.min_depth; fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
+        fa.ref = pa.ref; fa.ref_len = c->ref_len; fa.span_beg = c->span_beg; fa.span_end = c->span_end;
+        fa.n_samples = n; fa.n_strips = n_strips; fa.spc = spc;
+        fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
         fa.qual_ceiling = std::min(63, c->qual_ceiling);
-        fa.W = fast_w;
-        fa.ctr = ctr; fa.fp = dp<PbFastParams>(c->d_fastp);
+        fa.qslot = pb_cnt_qslot(ms); fa.sslot = pb_cnt_sslot(ms);
+        fa.lq = 0;
+        while ((16 << fa.lq) < std::max(fa.qslot, fa.sslot) - 16) ++fa.lq;      // lanes per record: covers the data chunks of either slot
+        fa.ctr = ctr; fa.tab = dp<PbFastTables>(c->d_fastp);
         fa.cov32 = dp<uint32_t>(c->d_cov32);
         fa.cells = dp<uint4>(c->d_cells); fa.codes = dp<uint16_t>(c->d_codes16); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
-        const unsigned n_sblocks = (unsigned)((n_strips + PB_FAST_STRIPS - 1) / PB_FAST_STRIPS);
-        PB_CUDA(c, cudaFuncSetAttribute(k_pile_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_fast_smem(fast_w)));
-        k_pile_fast<<<(unsigned)n * n_sblocks, PB_FAST_THREADS, pb_fast_smem(fast_w), st>>>(fa);
+        const unsigned n_blocks = (unsigned)((n_strips + spc - 1) / spc);
+        const size_t csm = pb_cnt_smem(spc, ms);
+        if (c->qual_robust) {
+            PB_CUDA(c, cudaFuncSetAttribute(k_pile_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            k_pile_count<true><<<(unsigned)n * n_blocks, PB_CNT_THREADS, csm, st>>>(fa);
+        } else {
+            PB_CUDA(c, cudaFuncSetAttribute(k_pile_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+            k_pile_count<false><<<(unsigned)n * n_blocks, PB_CNT_THREADS, csm, st>>>(fa);
+        }
         PbHardArgs ha;
         ha.cells = fa.cells; ha.codes = fa.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
         ha.span_beg = pa.span_beg; ha.span_end = pa.span_end; ha.win_beg = pa.win_beg; ha.win_end = pa.win_end; ha.n_windows = NW;
@@ -476,6 +489,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
             fprintf(stderr, "[popbam_b200] bit-sliced path: run again (arena overflow %d: %llu cells, %llu codes; quality %d above ceiling %d: %d; launch assumptions %d)\n",
                     h_final->arena_overflow, h_final->n_cells, h_final->n_codes, h_final->qual_max_seen, c->qual_ceiling, h_final->qual_over, h_final->spec_fail);
         if (h_final->qual_over) c->qual_ceiling = std::min(63, std::max(c->qual_ceiling + 1, h_final->qual_max_seen));
+        if (h_final->qual_high) { c->qual_robust = true; c->qual_ceiling = 63; }
         if (h_final->arena_overflow) c->arena_scale *= 4;
         c->reruns += 1;
         if (attempt >= 2 || c->arena_scale > 64) c->force_classic = 1;
@@ -742,13 +756,6 @@ int pb_set_contig(pb_ctx *c, int32_t tid, const char *ref_bases, int64_t len) {
     PB_CUDA(c, cudaSetDevice(c->prm.device));
     PB_TRY(dev_reserve(c, c->d_ref, (size_t)std::max<int64_t>(len, 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_ref.p, ref_bases, (size_t)len, cudaMemcpyHostToDevice, c->stream));
-    PB_CUDA(c, cudaStreamSynchronize(c->stream));
-    const size_t pw = (size_t)((len + 31) >> 5) + 2;
-    PB_TRY(dev_reserve(c, c->d_refpl, sizeof(uint32_t) * 3 * pw));
-    uint32_t *rp = dp<uint32_t>(c->d_refpl);
-    k_ref_planes<<<c->n_sms * 4, 256, 0, c->stream>>>(dp<char>(c->d_ref), len, rp, rp + pw, rp + 2 * pw);
-    c->launches += 1;
-    PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->ref_len = len; c->ref_tid = tid;
     return PB_OK;
