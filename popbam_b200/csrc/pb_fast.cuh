@@ -123,13 +123,23 @@ __global__ void __launch_bounds__(256) k_strip_index(const int4 *__restrict__ sr
         if (ss[s] == ss[s + 1]) for (int i = threadIdx.x; i < NI; i += 256) F[(size_t)s * NI + i] = ss[s];
 }
 
+// Reference code bytes of a contig, in the code the PRMT lookup of k_pile_count yields for a read base (bits 1-4):
+// A 0x02, C 0x04, G 0x08, T 0x1e; 0 for anything else (an upper-case A/C/G/T is the only thing a called base can equal,
+// pop_utils.cpp:139 / SURVEY Q7) and for the padding behind the contig.
+#define PB_REFCODE_PAD 4096
+__global__ void __launch_bounds__(256) k_ref_codes(const char *__restrict__ ref, int64_t ref_len, uint8_t *__restrict__ code) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ref_len + PB_REFCODE_PAD; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = i < ref_len ? (int)(unsigned char)ref[i] : 'N';
+        code[i] = (uint8_t)(c == 'A' ? 0x02 : c == 'C' ? 0x04 : c == 'G' ? 0x08 : c == 'T' ? 0x1e : 0x00);
+    }
+}
+
 struct PbCountArgs {
     const int4 *srec;
     const uint32_t *F;                       // strip index (k_strip_index), [n_samples][NI]
     int NI;
     const uint8_t *qual, *seq4;              // the read batch's bases (16-byte aligned, padded by 64 zero bytes)
-    const char *ref;
-    int64_t ref_len;
+    const uint8_t *refcode;                  // reference code bytes of the contig (k_ref_codes)
     int span_beg, span_end;
     int n_samples, n_strips;
     int spc;                                 // strips of 32 positions per CTA
@@ -143,28 +153,34 @@ struct PbCountArgs {
     uint4 *cells;                            // directory of the cells left for k_hard_cells: {pos, sample | k << 8, sum mapq^2, first code}
     uint16_t *codes;                         // their base codes  q << 5 | strand << 4 | base  (popbam.cpp:279-284)
     unsigned long long cell_cap, code_cap;
+    uint32_t *carry;                         // [blocks][n_samples][4][halo / 4] counts a CTA's reads add behind its block
+    uint32_t *carry_flag;                    // [blocks][n_samples] set once they are published (zeroed per region)
+    int halo;                                // positions of that tail: max_span rounded up to 32 (<= 32 * spc)
 };
 
-#define PB_CNT_THREADS 128         // threads per CTA = records staged per pass
+#define PB_CNT_THREADS 256         // threads per CTA = records staged per pass
 #define PB_CNT_SPC_MAX 64          // strips per CTA at most (cell ids are 16 bits, the emit scratch is sized for it)
+#define PB_CNT_STRIDE (PB_CNT_SPC_MAX * 32)      // bytes between the four counter arrays (fixed: immediate offsets in the scatter)
 // slots: 16 bytes of front padding (the first position word of a record can start up to three bytes before its first
 // base), then the 16-byte chunks that hold the segment; an odd number of chunks, so that consecutive slots start in
 // different bank groups
 __host__ __device__ static inline int pb_cnt_qslot(int max_span) { int c = 1 + (15 + max_span + 15) / 16; return 16 * (c | 1); }
 static inline int pb_cnt_sslot(int max_span) { int c = 1 + (15 + (max_span + 1) / 2 + 1 + 15) / 16; return 16 * (c | 1); }
+static inline int pb_cnt_halo(int max_span) { return (max_span + 31) & ~31; }
 static inline size_t pb_cnt_smem(int spc, int max_span) {
-    const size_t pb = (size_t)spc * 32;
+    const size_t pb = (size_t)spc * 32, halo = (size_t)pb_cnt_halo(max_span);
     const size_t slots = (size_t)PB_CNT_THREADS * (pb_cnt_qslot(max_span) + pb_cnt_sslot(max_span));
     const size_t emit = (size_t)pb * 6;                       // cell ids + code offsets, in the slots' place
-    return 4 * pb + pb + 16 + 512 + 64 * 4 + (slots > emit ? slots : emit) + 16;
+    return 4 * PB_CNT_STRIDE + pb + halo + 16 + 512 + 64 * 4 + (slots > emit ? slots : emit) + 16;
 }
 
 // ---- 16-byte asynchronous copy global -> shared (LDGSTS, L2 only).  A 1-D bulk copy per record (cp.async.bulk, UBLKCP)
 // was tried first: its operands live in uniform registers, so the compiler serialises the 32 lanes of a warp in an
 // ELECT / R2UR loop of ten instructions per copy -- as many issue slots as the scatter itself.  Eight lanes copying the
 // eight chunks of one record with one LDGSTS each cost a fifth of that and the 128 bytes of a record are one request.
-__device__ __forceinline__ void pb_cp16(void *dst, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+__device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pb_cp16(uint32_t dst_shared, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_shared), "l"(src) : "memory");
 }
 __device__ __forceinline__ void pb_cp_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
@@ -193,11 +209,11 @@ __global__ void __launch_bounds__(PB_CNT_THREADS) k_pile_count(const PbCountArgs
     }
     const int PB = a.spc * 32;
     uint32_t *cK = reinterpret_cast<uint32_t *>(smem_raw);               // [PB / 4] passing bases, one byte per position
-    uint32_t *cH = cK + PB / 4;                                           // those at or above the khi level
-    uint32_t *cM = cH + PB / 4;                                           // stray bases
-    uint32_t *cF = cM + PB / 4;                                           // bit 0: a stray base at or above the khi level, bit 1: lowq
-    uint8_t *rcode = reinterpret_cast<uint8_t *>(cF + PB / 4);            // [PB + 16] reference code bytes (0: not A/C/G/T)
-    uint8_t *tabS = rcode + PB + 16;                                      // flags[256], hneed[256]
+    uint32_t *cH = cK + PB_CNT_STRIDE / 4;                                // those at or above the khi level
+    uint32_t *cM = cH + PB_CNT_STRIDE / 4;                                // stray bases
+    uint32_t *cF = cM + PB_CNT_STRIDE / 4;                                // bit 0: a stray base at or above the khi level, bit 1: lowq
+    uint8_t *rcode = reinterpret_cast<uint8_t *>(cF + PB_CNT_STRIDE / 4); // [PB + 16] reference code bytes (0: not A/C/G/T)
+    uint8_t *tabS = rcode + PB + a.halo + 16;                                      // flags[256], hneed[256]
     uint32_t *hardS = reinterpret_cast<uint32_t *>(tabS + 512);           // [64] hard masks per strip
     unsigned char *slots = reinterpret_cast<unsigned char *>(hardS + 64); // [THREADS] quality slots, then [THREADS] sequence slots
     const int M = (max_span + 31) >> 5;
@@ -205,15 +221,15 @@ __global__ void __launch_bounds__(PB_CNT_THREADS) k_pile_count(const PbCountArgs
     const int t0 = sb * a.spc;
     const int p0 = a.span_beg + t0 * 32, p1 = min(p0 + PB, a.span_end);
     const uint32_t *Fs = a.F + (size_t)s * a.NI;
-    const uint32_t clo = __ldg(Fs + t0), chi = __ldg(Fs + min(t0 + a.spc, a.n_strips) + M);
-    for (int i = tid; i < PB; i += PB_CNT_THREADS) reinterpret_cast<uint32_t *>(smem_raw)[i] = 0;        // the four counter arrays
-    for (int i = tid; i < PB + 16; i += PB_CNT_THREADS) {
-        const int64_t p = (int64_t)p0 + i;
-        const int c = (p >= 0 && p < a.ref_len) ? (int)(unsigned char)a.ref[p] : 'N';
-        // code bytes: bit 0 "valid" is the read side's; bits 1-4: A 0x02, C 0x04, G 0x08, T 0x1e (what the PRMT lookup below yields)
-        rcode[i] = (uint8_t)(c == 'A' ? 0x02 : c == 'C' ? 0x04 : c == 'G' ? 0x08 : c == 'T' ? 0x1e : 0x00);
-    }
+    // Every record belongs to ONE CTA, the one whose block holds its read's start (the first block also takes the reads
+    // that start before the span), and is scattered in full: the counters reach `halo` positions behind the block, and
+    // what lands there is handed to the next block's CTA through global memory (below).
+    const uint32_t clo = __ldg(Fs + (sb == 0 ? 0 : t0 + M)), chi = __ldg(Fs + min(t0 + a.spc, a.n_strips) + M);
+    const int pend = p0 + PB + a.halo;                                    // end of the counters
+    for (int i = tid; i < (PB + a.halo) / 4 + 1; i += PB_CNT_THREADS) { cK[i] = 0; cH[i] = 0; cM[i] = 0; cF[i] = 0; }
+    for (int i = tid; i < PB + a.halo + 16; i += PB_CNT_THREADS) rcode[i] = __ldg(a.refcode + (int64_t)p0 + i);       // k_ref_codes; padded behind the contig
     for (int i = tid; i < 128; i += PB_CNT_THREADS) reinterpret_cast<uint32_t *>(tabS)[i] = __ldg(reinterpret_cast<const uint32_t *>(a.tab) + i);
+    *reinterpret_cast<uint4 *>(slots + (size_t)tid * a.qslot) = make_uint4(0, 0, 0, 0);        // front padding of the quality slot: read (never counted) by a segment's first word
     __syncthreads();
     // raw quality byte thresholds (host: all <= 128): passing, khi level, above the assumed ceiling
     const int qoff = a.illumina ? 31 : 0;
@@ -235,25 +251,26 @@ __global__ void __launch_bounds__(PB_CNT_THREADS) k_pile_count(const PbCountArgs
             const int4 rc = __ldg(&a.srec[c0 + tid]);
             z = (uint32_t)rc.z; x = rc.y; len = (int)(z & 0xffffu);
             o = ((uint64_t)(z >> 26) << 32) | (uint32_t)rc.w;                                // byte offset of the segment's first base
-            pa = max(x, p0); pb = min(x + len, p1);
+            pa = max(x, p0); pb = min(x + len, pend);
         }
         const bool active = pb > pa;
+        if (c0 + (uint32_t)(tid & ~31) >= chi) break;                             // none of this warp's threads has a record (later passes neither)
         {
             // 2^lq lanes stage one record: lane c of the group copies chunk c of its quality bytes and of its packed bases.
             // Every warp stages the 32 records of its own threads, so a warp-level wait is all the scatter needs.
-            const uint32_t d_lo = (uint32_t)o, d_hi = (uint32_t)(o >> 32) | (uint32_t)len << 8 | (active ? 0x80000000u : 0u);
+            const uint32_t qc = (uint32_t)(o >> 4);                                        // first 16-byte chunk of qual[] (seq4[]: qc >> 1)
+            const uint32_t nq = (uint32_t)((o + (uint64_t)len + 15) >> 4) - qc, ns = (uint32_t)((((o + (uint64_t)len + 1) >> 1) + 15) >> 4) - (qc >> 1);
+            const uint32_t d_cnt = active ? (nq | ns << 8) : 0u;
             const int per = 32 >> a.lq, cl = lane & ((1 << a.lq) - 1);
-            for (int it = 0; it < (1 << a.lq); ++it) {
-                const int rl = it * per + (lane >> a.lq);                                   // record (lane of its owner) staged by this lane now
-                const uint32_t r_lo = __shfl_sync(0xffffffffu, d_lo, rl), r_hi = __shfl_sync(0xffffffffu, d_hi, rl);
-                if (r_hi & 0x80000000u) {
-                    const uint64_t ro = ((uint64_t)(r_hi & 0xffu) << 32) | r_lo, re = ro + ((r_hi >> 8) & 0xffffu);
-                    const uint64_t q0 = (ro & ~15ULL) + 16u * (uint32_t)cl, s0 = ((ro >> 1) & ~15ULL) + 16u * (uint32_t)cl;
-                    unsigned char *qd = slots + (size_t)((tid & ~31) + rl) * a.qslot + 16 + 16 * cl;
-                    unsigned char *sd = slots + (size_t)PB_CNT_THREADS * a.qslot + (size_t)((tid & ~31) + rl) * a.sslot + 16 + 16 * cl;
-                    if (q0 < re) pb_cp16(qd, a.qual + q0);
-                    if (s0 < ((re + 1) >> 1)) pb_cp16(sd, a.seq4 + s0);
-                }
+            uint32_t qd = pb_smem_addr(slots) + (uint32_t)(((tid & ~31) + (lane >> a.lq)) * a.qslot + 16 + 16 * cl);
+            uint32_t sd = pb_smem_addr(slots) + (uint32_t)(PB_CNT_THREADS * a.qslot + ((tid & ~31) + (lane >> a.lq)) * a.sslot + 16 + 16 * cl);
+            const uint8_t *qsrc = a.qual + 16 * (size_t)cl, *ssrc = a.seq4 + 16 * (size_t)cl;
+            const uint32_t qstep = (uint32_t)(per * a.qslot), sstep = (uint32_t)(per * a.sslot);
+            for (int rl = lane >> a.lq; rl < 32; rl += per) {                               // record (lane of its owner) staged by this lane now
+                const uint32_t r_qc = __shfl_sync(0xffffffffu, qc, rl), r_cnt = __shfl_sync(0xffffffffu, d_cnt, rl);
+                if ((uint32_t)cl < (r_cnt & 0xffu)) pb_cp16(qd, qsrc + ((size_t)r_qc << 4));
+                if ((uint32_t)cl < (r_cnt >> 8)) pb_cp16(sd, ssrc + ((size_t)(r_qc >> 1) << 4));
+                qd += qstep; sd += sstep;
             }
             pb_cp_wait_all();
             __syncwarp();
@@ -272,57 +289,64 @@ __global__ void __launch_bounds__(PB_CNT_THREADS) k_pile_count(const PbCountArgs
             const int nb = 32 + (int)(o & 31u) + i0;                                         // its nibble in the sequence slot (>= 29)
             const uint32_t *sw = reinterpret_cast<const uint32_t *>(sslot) + (nb >> 3);
             const int sh = 4 * (nb & 7);
-            uint32_t wq0 = qw[0];
-            uint32_t sn0 = pb_nibble_order(sw[0]);
-            const uint32_t *rcw = reinterpret_cast<const uint32_t *>(rcode);
-            // one position word: quality bytes qv, base nibbles in the low 16 bits of sx, byte mask bm (segment ends)
-            auto word = [&](int j, uint32_t qv, uint32_t sx, uint32_t bm) {
-                // 16-entry lookup for four bases: nibble 1 (A) -> 0x03, 2 (C) -> 0x05, 4 (G) -> 0x09, 8 (T) -> 0xff
-                // (selector bit 3 replicates the sign of entry 0, 0x80), everything else -> bit 0 clear
-                const uint32_t sq = pb_prmt(0x00050380u, 0x00000009u, sx);
-                const uint32_t qm = qv & bm;                                 // bytes outside the segment (neighbours, padding) read as 0
-                uint32_t fa, fh;
-                if (ROBUST) {
-                    const uint32_t lo7 = qm & 0x7f7f7f7fu;
-                    fa = (lo7 + addP) | qm; fh = ((lo7 + addH) | qm) & hmask;
-                    if (check) over |= (lo7 + addC) | qm;
-                } else {
-                    fa = qm + addP; fh = qm + addH;
-                    over |= qm | (qm + addC);
-                }
-                const uint32_t P = (fa >> 7) & sq & bm & 0x01010101u;
-                const uint32_t H = (fh >> 7) & P;
-                const uint32_t y = (sq ^ rcw[j]) & 0x1e1e1e1eu;
-                const uint32_t mmw = ((y + 0x7f7f7f7fu) >> 7) & P;
-                if (P) atomicAdd(cK + j, P);
-                if (H) atomicAdd(cH + j, H);
-                if (mmw) {
-                    atomicAdd(cM + j, mmw);
-                    if (mmw & H) atomicOr(cF + j, mmw & H);
-                }
-                if (lowq && P) atomicOr(cF + j, P << 1);
-            };
-            auto mask_of = [&](int i) -> uint32_t {                                         // bytes of a word whose base index i + b lies in [0, len)
-                const int lo = min(4, max(0, -i)), hi = min(4, max(0, len - i));
-                const uint32_t mlo = lo >= 4 ? 0u : 0xffffffffu << (8 * lo);
-                const uint32_t mhi = hi >= 4 ? 0xffffffffu : ~(0xffffffffu << (8 * hi));
-                return mlo & mhi;
-            };
-            const int T = j1 - j0 + 1;
-            for (int t = 0; t < T; t += 2) {
-                const uint32_t wq1 = qw[t + 1], wq2 = qw[t + 2];
-                const uint32_t sn1 = pb_nibble_order(sw[(t >> 1) + 1]);
+            // Segment ends.  The first and the last position word of a segment also hold bytes of its neighbours in qual[] /
+            // seq4[] (or padding).  The slot is this thread's private copy, so those bases are simply made invalid there:
+            // a zero nibble is no base (popbam.cpp:276-278), the lookup below gives it "not valid", and it passes no test.
+            {
+                const int lim = pb - x;                                                      // end of the segment's part inside the counters
+                uint8_t *sb8 = sslot;
+                for (int i = i0; i < 0; ++i) { const int n = 32 + (int)(o & 31u) + i; sb8[n >> 1] &= (n & 1) ? 0xf0 : 0x0f; }
+                const int iend = i0 + 8 * ((j1 - j0 + 2) >> 1);                              // one past the last base the pairs below look at
+                for (int i = lim; i < iend; ++i) { const int n = 32 + (int)(o & 31u) + i; sb8[n >> 1] &= (n & 1) ? 0xf0 : 0x0f; }
+            }
+            // One position word: quality bytes qv, base nibbles in the low 16 bits of sx; cp = the word's four counters
+            // (arrays PB_CNT_STRIDE bytes apart: immediate offsets), rv = the reference's code bytes.
+#define PB_CNT_WORD(cp, rv, qv_, sx_)                                                                                      \
+            {                                                                                                              \
+                /* 16-entry lookup for four bases: nibble 1 (A) -> 0x03, 2 (C) -> 0x05, 4 (G) -> 0x09, 8 (T) -> 0xff       \
+                   (selector bit 3 replicates the sign of entry 0, 0x80), everything else -> bit 0 clear */               \
+                const uint32_t sq = pb_prmt(0x00050380u, 0x00000009u, (sx_));                                              \
+                const uint32_t qm = (qv_);                                                                                 \
+                uint32_t fa, fh;                                                                                           \
+                if (ROBUST) {                                                                                              \
+                    const uint32_t lo7 = qm & 0x7f7f7f7fu;                                                                 \
+                    fa = (lo7 + addP) | qm; fh = ((lo7 + addH) | qm) & hmask;                                              \
+                    if (check) over |= (lo7 + addC) | qm;                                                                  \
+                } else {                                                                                                   \
+                    fa = qm + addP; fh = qm + addH;                                                                        \
+                    over |= qm | (qm + addC);                                                                              \
+                }                                                                                                          \
+                const uint32_t P = (fa >> 7) & sq & 0x01010101u;                                                           \
+                const uint32_t H = (fh >> 7) & P;                                                                          \
+                const uint32_t y = (sq ^ (rv)) & 0x1e1e1e1eu;                                                              \
+                const uint32_t mmw = ((y + 0x7f7f7f7fu) >> 7) & P;                                                         \
+                atomicAdd((cp), P);                                                                                        \
+                atomicAdd((cp) + PB_CNT_STRIDE / 4, H);                                                                    \
+                if (mmw) {                                                                                                 \
+                    atomicAdd((cp) + 2 * (PB_CNT_STRIDE / 4), mmw);                                                        \
+                    if (mmw & H) atomicOr((cp) + 3 * (PB_CNT_STRIDE / 4), mmw & H);                                        \
+                }                                                                                                          \
+            }
+            // pairs of position words share one 32-bit window of the nibble stream
+            const int NP = (j1 - j0 + 2) >> 1;
+            uint32_t *cp = cK + j0;
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(rcode) + j0;
+            uint32_t wq0 = qw[0], sn0 = pb_nibble_order(sw[0]);
+            for (int p = 0; p < NP; ++p) {
+                const uint32_t wq1 = qw[1], wq2 = qw[2];
+                const uint32_t sn1 = pb_nibble_order(sw[1]);
                 const uint32_t sx = __funnelshift_r(sn0, sn1, sh);
-                sn0 = sn1;
                 const uint32_t qa = __byte_perm(wq0, wq1, selq), qb = __byte_perm(wq1, wq2, selq);
-                wq0 = wq2;
-                if (t > 0 && t + 2 < T) {                                                   // interior words: every byte belongs to the segment
-                    word(j0 + t, qa, sx, 0xffffffffu);
-                    word(j0 + t + 1, qb, sx >> 16, 0xffffffffu);
-                } else {
-                    word(j0 + t, qa, sx, mask_of(i0 + 4 * t));
-                    if (t + 1 < T) word(j0 + t + 1, qb, sx >> 16, mask_of(i0 + 4 * t + 4));
-                }
+                sn0 = sn1; wq0 = wq2;
+                PB_CNT_WORD(cp, rp[0], qa, sx)
+                PB_CNT_WORD(cp + 1, rp[1], qb, sx >> 16)
+                qw += 2; sw += 1; cp += 2; rp += 2;
+            }
+#undef PB_CNT_WORD
+            if (lowq) {
+                // a read below min_rmsQ: every cell it covers leaves the easy path (its bases may or may not pass; k_hard_cells
+                // computes the exact rms).  Rare, and outside the loop above.
+                for (int j = j0; j <= j1; ++j) atomicOr(cF + j, 0x02020202u);
             }
             if (over & 0x80808080u) {
                 // some byte this thread touched (its own or a neighbour's) is >= 128 or above the assumed ceiling: look at
@@ -338,7 +362,32 @@ __global__ void __launch_bounds__(PB_CNT_THREADS) k_pile_count(const PbCountArgs
         }
         __syncwarp();                                                         // the warp's slots are free again
     }
-    __syncthreads();                                                          // the counts are final
+    __syncthreads();                                                          // this CTA's reads are counted
+    {
+        // publish what they added behind the block, take what the previous block's reads added to the front of this one.
+        // The previous CTA of this sample has a lower block index, so it was scheduled no later than this one and does not
+        // wait for anything itself: the wait below ends (decoupled look-back, as in a single-pass scan).
+        const int hw = a.halo / 4;
+        uint32_t *mine = a.carry + ((size_t)blockIdx.x * 4) * hw;
+        for (int i = tid; i < 4 * hw; i += PB_CNT_THREADS) mine[i] = cK[(i / hw) * (PB_CNT_STRIDE / 4) + PB / 4 + (i % hw)];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            atomicExch(a.carry_flag + blockIdx.x, 1u);
+            if (sb > 0) while (atomicAdd(a.carry_flag + (blockIdx.x - a.n_samples), 0u) == 0u) __nanosleep(20);
+            __threadfence();
+        }
+        __syncthreads();
+        if (sb > 0) {
+            const uint32_t *prev = a.carry + ((size_t)(blockIdx.x - a.n_samples) * 4) * hw;
+            for (int i = tid; i < 4 * hw; i += PB_CNT_THREADS) {
+                const uint32_t v = __ldcg(prev + i);
+                uint32_t *d = cK + (i / hw) * (PB_CNT_STRIDE / 4) + (i % hw);
+                if (i / hw == 3) *d |= v; else *d += v;                       // counts add byte-wise (no cell exceeds 255); flags or
+            }
+            __syncthreads();
+        }
+    }
     // ---- classify: one thread per position, 32 consecutive positions per warp
     const uint8_t *bK = reinterpret_cast<const uint8_t *>(cK), *bH = reinterpret_cast<const uint8_t *>(cH);
     const uint8_t *bM = reinterpret_cast<const uint8_t *>(cM), *bF = reinterpret_cast<const uint8_t *>(cF);
@@ -366,9 +415,21 @@ __global__ void __launch_bounds__(PB_CNT_THREADS) k_pile_count(const PbCountArgs
         n_cand = __ldg(Fs + t0 + tid + M + 1) - __ldg(Fs + t0 + tid);                  // upper bound of a cell's depth: the strip's candidate records
     }
     const uint32_t my_cells = (uint32_t)__popc(hard);
-    uint32_t tot_cells, tot_codes;
-    uint32_t cell_at = pb_block_exscan(my_cells, &tot_cells);
-    uint32_t code_at = pb_block_exscan(my_cells * n_cand, &tot_codes);
+    // offsets of the strips' cells and code slots: at most 64 strips, so the first two warps scan and the rest wait
+    __shared__ uint32_t s_scan[4];
+    uint32_t cell_at = 0, code_at = 0;
+    if (tid < 64) {
+        uint32_t xc = my_cells, xk = my_cells * n_cand;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) {
+            const uint32_t yc = __shfl_up_sync(0xffffffffu, xc, o2), yk = __shfl_up_sync(0xffffffffu, xk, o2);
+            if (lane >= o2) { xc += yc; xk += yk; }
+        }
+        if (lane == 31) { s_scan[(tid >> 5) * 2] = xc; s_scan[(tid >> 5) * 2 + 1] = xk; }
+        cell_at = xc - my_cells; code_at = xk - my_cells * n_cand;
+    }
+    __syncthreads();
+    const uint32_t tot_cells = s_scan[0] + s_scan[2], tot_codes = s_scan[1] + s_scan[3];
+    if (tid >= 32 && tid < 64) { cell_at += s_scan[0]; code_at += s_scan[1]; }
     if (tot_cells == 0) return;
     uint16_t *cellS = reinterpret_cast<uint16_t *>(slots);                              // [<= PB] strip << 5 | bit
     uint32_t *codeS = reinterpret_cast<uint32_t *>(slots + 2 * (size_t)PB);             // first code slot, relative to the CTA's reservation

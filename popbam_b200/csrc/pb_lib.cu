@@ -63,6 +63,8 @@ struct pb_ctx {
     DevBuf d_site_type, d_site_flag, d_cb;
     DevBuf d_fastp, d_cov32, d_acc, d_sidx;     // bit-sliced path: PbFastParams, cov32, per-position accumulators, strip index
     DevBuf d_cells, d_codes16, d_need_raw;      // cells left for k_hard_cells (directory + base codes), need_raw[64][256]
+    DevBuf d_refcode;                           // reference code bytes of the contig (k_ref_codes)
+    DevBuf d_carry;                             // k_pile_count: counts handed from a block to the next one, and their flags
     std::vector<DevBuf *> bufs;            // every device buffer of the context
     bool classic = false;                  // POPBAM_B200_PILEUP=classic: always k_pileup_call (A/B measurements)
     int qual_ceiling = 41;                 // assumed largest base quality (pb_fast.cuh: checked on the device, raised on violation)
@@ -353,7 +355,8 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
     PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
     if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
     const bool cap = c->ctr_host.nocap == 0;
-    const bool fast = fast_try && !cap && pb_cnt_smem(1, c->ctr_host.max_span) <= c->smem_optin && pb_cnt_qslot(c->ctr_host.max_span) <= 16 + 16 * 32;
+    const bool fast = fast_try && !cap && 2 * pb_cnt_halo(c->ctr_host.max_span) <= 32 * PB_CNT_SPC_MAX &&
+                      pb_cnt_smem(PB_CNT_SPC_MAX - pb_cnt_halo(c->ctr_host.max_span) / 32, c->ctr_host.max_span) <= c->smem_optin && pb_cnt_qslot(c->ctr_host.max_span) <= 16 + 16 * 32;
     if (fast_try && !fast) {
         // the depth cap can bind (or a read is too long for the staged planes): the single-kernel path needs the levels present
         PB_TRY(classic_levels());
@@ -395,13 +398,13 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
         // strips per CTA: a CTA stages one record per thread and pass, so its positions should hold about that many records
         const int ms = c->ctr_host.max_span;
         const double density = std::max(1e-6, (double)c->ctr_host.n_records / ((double)n * (double)std::max<int64_t>(span, 1)));   // records starting per position and sample
-        int spc = (int)((0.92 * PB_CNT_THREADS / density - ms) / 32.0);
-        spc = std::max(1, std::min(PB_CNT_SPC_MAX, spc));
-        while (spc > 1 && pb_cnt_smem(spc, ms) > c->smem_optin) --spc;
+        const int halo = pb_cnt_halo(ms);
+        int spc = (int)(0.87 * PB_CNT_THREADS / density / 32.0);
+        spc = std::max(halo / 32, std::min(PB_CNT_SPC_MAX - halo / 32, spc));    // block >= halo (a read ends in the next block at the latest), block + halo <= the counter arrays
         PbCountArgs fa;
         fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.NI = fNI;
         fa.qual = dp<uint8_t>(c->d_qual); fa.seq4 = dp<uint8_t>(c->d_seq4);
-        fa.ref = pa.ref; fa.ref_len = c->ref_len; fa.span_beg = c->span_beg; fa.span_end = c->span_end;
+        fa.refcode = dp<uint8_t>(c->d_refcode); fa.span_beg = c->span_beg; fa.span_end = c->span_end;
         fa.n_samples = n; fa.n_strips = n_strips; fa.spc = spc;
         fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
         fa.qual_ceiling = std::min(63, c->qual_ceiling);
@@ -413,6 +416,9 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
         fa.cells = dp<uint4>(c->d_cells); fa.codes = dp<uint16_t>(c->d_codes16); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
         const unsigned n_blocks = (unsigned)((n_strips + spc - 1) / spc);
         const size_t csm = pb_cnt_smem(spc, ms);
+        PB_TRY(dev_reserve(c, c->d_carry, sizeof(uint32_t) * ((size_t)n_blocks * n * (size_t)halo + (size_t)n_blocks * n)));
+        fa.carry = dp<uint32_t>(c->d_carry); fa.carry_flag = fa.carry + (size_t)n_blocks * n * (size_t)halo; fa.halo = halo;
+        PB_CUDA(c, cudaMemsetAsync(fa.carry_flag, 0, sizeof(uint32_t) * (size_t)n_blocks * n, st));
         if (c->qual_robust) {
             PB_CUDA(c, cudaFuncSetAttribute(k_pile_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
             k_pile_count<true><<<(unsigned)n * n_blocks, PB_CNT_THREADS, csm, st>>>(fa);
@@ -757,6 +763,11 @@ int pb_set_contig(pb_ctx *c, int32_t tid, const char *ref_bases, int64_t len) {
     PB_TRY(dev_reserve(c, c->d_ref, (size_t)std::max<int64_t>(len, 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_ref.p, ref_bases, (size_t)len, cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    PB_TRY(dev_reserve(c, c->d_refcode, (size_t)len + PB_REFCODE_PAD));
+    k_ref_codes<<<c->n_sms * 4, 256, 0, c->stream>>>(dp<char>(c->d_ref), len, dp<uint8_t>(c->d_refcode));
+    c->launches += 1;
+    PB_CUDA(c, cudaGetLastError());
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));
     c->ref_len = len; c->ref_tid = tid;
     return PB_OK;
 }
@@ -792,7 +803,7 @@ int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
     if (!b->pos || !b->meta || !b->cig_off || !b->cigar || !b->base_off || !b->seq4 || !b->qual) return fail(c, PB_ERR_ARG, "pb_push_batch: null array");
     if ((uint64_t)(c->n_cig + b->n_cigar) > 0xfffffff0ULL) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one region");
     if ((uint64_t)(c->n_reads + b->n_reads) > 0xfffffff0ULL) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^32 reads in one region");
-    if ((uint64_t)(c->n_bytes + b->n_bases) >> 40) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^40 base bytes in one region");
+    if ((uint64_t)(c->n_bytes + b->n_bases) >> 36) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^36 base bytes in one region");
     PB_CUDA(c, cudaSetDevice(c->prm.device));
     cudaStream_t st = c->stream;
     const int64_t N0 = c->n_reads, N1 = N0 + b->n_reads;
