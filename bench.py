@@ -188,7 +188,7 @@ def run_b200(args):
     def one_e2e(cs):
         ctx, sh = cs
         ctx.region_begin(an, sh["wb"], sh["we"])
-        ctx.push_batch(sh["batch"])
+        ctx.push_batch_async(sh["batch"])     # pinned arrays, untouched until region_end returns
         res = ctx.region_end()
         return res.n_windows * (3 * 4 + 8 + 3 * 8 * res.n_pops) + int(res.seg_off[res.n_windows]) * 17
 

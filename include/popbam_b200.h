@@ -199,6 +199,10 @@ int pb_region_begin(pb_ctx *ctx, uint32_t analyses, int32_t n_windows,
  * May be called several times per region; batches are concatenated in call order.  The
  * arrays are copied to the device before the call returns (use pinned memory for speed).  */
 int pb_push_batch(pb_ctx *ctx, const pb_read_batch *batch);
+/* The same without waiting for the copies: the batch arrays (pinned host memory) must stay untouched until
+ * pb_region_wait / pb_region_end of this region has returned.  Several pushes and the kernels of the region then
+ * queue up behind each other on the context's stream with no host round trip in between.                          */
+int pb_push_batch_async(pb_ctx *ctx, const pb_read_batch *batch);
 
 /* bam_fetch_f-shaped shim (bam.h:618): `b` points at a raw BAM record laid out as bam1_t's
  * core (32 bytes, bam.h:178-190, little endian) followed by its variable-length data

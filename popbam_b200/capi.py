@@ -13,7 +13,7 @@ AN = dict(NUCDIV=0x001, SFS=0x002, LD_ZNS=0x004, LD_OMEGA=0x008, LD_WALL=0x010, 
           DIVERGE_POP=0x040, HAPLO_K=0x080, HAPLO_EHHS=0x100, HAPLO_DXY=0x200, SNP=0x400, TREE=0x800)
 FLAG = dict(ILLUMINA=0x02, SUBSTITUTE=0x10, HETEROZYGOTE=0x20, OUTGROUP=0x40, EMIT_CB=0x10000)
 
-EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_version", "pb_set_contig", "pb_region_begin", "pb_push_batch",
+EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_version", "pb_set_contig", "pb_region_begin", "pb_push_batch", "pb_push_batch_async",
            "pb_push_record", "pb_region_end", "pb_region_launch", "pb_region_wait", "pb_region_relaunch", "pb_stream",
            "pb_kernel_launches", "pb_region_path", "pb_region_reruns", "pb_stage_times", "pb_window_grid", "pb_build_errmod_tables", "pb_format_window"]
 
@@ -103,6 +103,7 @@ def lib():
         L.pb_set_contig.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int64]
         L.pb_region_begin.argtypes = [C.c_void_p, C.c_uint32, C.c_int32, _p(C.c_int32), _p(C.c_int32)]
         L.pb_push_batch.argtypes = [C.c_void_p, _p(Batch)]
+        L.pb_push_batch_async.argtypes = [C.c_void_p, _p(Batch)]
         L.pb_push_record.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         L.pb_region_end.argtypes = [C.c_void_p, _p(Result)]
         L.pb_region_launch.argtypes = [C.c_void_p]
@@ -169,6 +170,10 @@ class Context:
 
     def push_batch(self, batch):
         self._chk(self.L.pb_push_batch(self.h, C.byref(batch)))
+
+    def push_batch_async(self, batch):
+        """The arrays of `batch` must stay untouched until region_end / wait has returned."""
+        self._chk(self.L.pb_push_batch_async(self.h, C.byref(batch)))
 
     def region_end(self):
         self._chk(self.L.pb_region_end(self.h, C.byref(self.res)))

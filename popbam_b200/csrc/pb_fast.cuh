@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(PB_CNT_THREADS) k_pile_count(const PbCountArgs
     __shared__ unsigned long long s_base[2];
     const int tid = threadIdx.x, lane = tid & 31;
     const int max_span = a.ctr->max_span;
-    if (!a.ctr->nocap || pb_cnt_qslot(max_span) > a.qslot) {      // launched on an assumption that does not hold: say so, do nothing
+    if (!a.ctr->nocap || pb_cnt_qslot(max_span) > a.qslot || ((max_span + 31) & ~31) > a.halo) {      // launched on an assumption that does not hold: say so, do nothing
         if (tid == 0) a.ctr->spec_fail = 1;
         return;
     }

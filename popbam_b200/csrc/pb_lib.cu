@@ -56,7 +56,7 @@ struct pb_ctx {
     std::vector<int32_t> h_wbeg, h_wend;
     DevBuf d_wbeg, d_wend;
     // reads on the device (concatenation of the pushed batches)
-    int64_t n_reads = 0, n_cig = 0, n_bytes = 0;
+    int64_t n_reads = 0, n_cig = 0, n_bytes = 0, n_pushes = 0;
     DevBuf d_pos, d_meta, d_cigstart, d_ncig, d_base, d_cigar, d_seq4, d_qual, d_tmp_cig, d_tmp_base;
     // derived
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
@@ -74,6 +74,13 @@ struct pb_ctx {
     bool ran_fast = false;                 // the last pipeline run took the bit-sliced path
     int force_classic = 0;                 // the bit-sliced path gave up on this region (arena overflow twice): k_pileup_call
     int reruns = 0;                        // regions run again because an assumption of the bit-sliced path did not hold
+    // what a context has learnt from its earlier regions: with it a region is enqueued without a host round trip
+    bool spec_valid = false;
+    int spec_span = 0;                     // largest reference span of a read seen so far
+    double spec_density = 0;               // segment records per position and sample of the last region
+    bool async_run = false;                // the last run_pipeline left its checks and the segregating-site copy to fill_result
+    bool no_async = false;                 // POPBAM_B200_SYNC=1: always take the host round trips (A/B measurements)
+    int64_t seg_cap = 0;                   // device layout of the segregating-site arrays (async: sized by the span)
     DevBuf d_seg_type;     // arena of the segregating-site arrays (seg_layout)
     DevBuf d_hap, d_kt, d_km, d_lsum, d_rsum, d_wall_u, d_stats, d_ld_kt, d_ld_km, d_ld_inv, d_ld_cnt;
     // pinned results
@@ -217,7 +224,7 @@ int exclusive_scan_u32(pb_ctx *c, uint32_t *data, int64_t n, cudaStream_t st) {
 }
 
 
-int run_pipeline(pb_ctx *c, int attempt = 0) {
+int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     const pb_params &P = c->prm;
     const int n = P.n_samples, NW = c->nw;
     const int64_t N = c->n_reads;
@@ -344,12 +351,25 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
     PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));                // join
     PB_CUDA(c, cudaGetLastError());
     PB_TRY(host_reserve(c, c->h_ctr, 3 * sizeof(PbCounters) + 64));
-    PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
     PB_CUDA(c, cudaEventRecord(c->ev[1], st));
-    PB_CUDA(c, cudaStreamSynchronize(st));
-    c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
-    if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
-    if (c->ctr_host.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
+    // Asynchronous mode: the launch parameters the counting pileup needs from the device (largest read span, record
+    // density, "the depth cap cannot bind") are taken from the context's earlier regions; k_pile_count verifies them on the
+    // device, and fill_result looks at the verdict (and at the sorted / too-long flags) once the region is done.  No host
+    // round trip in the middle of the pipeline, so one context keeps a GPU busy.
+    const uint32_t sync_bits = PB_AN_SNP | PB_AN_LD_ZNS | PB_AN_LD_OMEGA;          // their buffers / grids are sized by the number of segregating sites
+    const bool async = allow_async && !c->no_async && fast_try && c->spec_valid && attempt == 0 && !(c->analyses & sync_bits) && !(P.flags & PB_FLAG_EMIT_CB);
+    c->async_run = async;
+    if (async) {
+        memset(&c->ctr_host, 0, sizeof c->ctr_host);
+        c->ctr_host.max_span = c->spec_span; c->ctr_host.nocap = 1;
+        c->ctr_host.n_records = (unsigned)std::min<double>(4.0e9, c->spec_density * (double)n * (double)span);
+    } else {
+        PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
+        PB_CUDA(c, cudaStreamSynchronize(st));
+        c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
+        if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
+        if (c->ctr_host.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
+    }
 
     // ---- the hot kernel
     PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
@@ -357,6 +377,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
     const bool cap = c->ctr_host.nocap == 0;
     const bool fast = fast_try && !cap && 2 * pb_cnt_halo(c->ctr_host.max_span) <= 32 * PB_CNT_SPC_MAX &&
                       pb_cnt_smem(PB_CNT_SPC_MAX - pb_cnt_halo(c->ctr_host.max_span) / 32, c->ctr_host.max_span) <= c->smem_optin && pb_cnt_qslot(c->ctr_host.max_span) <= 16 + 16 * 32;
+    if (async && !fast) return run_pipeline(c, attempt, false);          // (cannot happen with the context's own numbers)
     if (fast_try && !fast) {
         // the depth cap can bind (or a read is too long for the staged planes): the single-kernel path needs the levels present
         PB_TRY(classic_levels());
@@ -482,12 +503,12 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
     PB_CUDA(c, cudaMemcpyAsync(hl0.segsites, dl.segsites, sizeof(int32_t) * (size_t)NW, cudaMemcpyDeviceToHost, st));
     PbCounters *h_final = reinterpret_cast<PbCounters *>(reinterpret_cast<unsigned char *>(c->h_ctr.p) + 2 * sizeof(PbCounters));
     PB_CUDA(c, cudaMemcpyAsync(h_final, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
-    PB_CUDA(c, cudaStreamSynchronize(st));
-    if (fast && getenv("POPBAM_B200_DEBUG"))
+    if (!async) PB_CUDA(c, cudaStreamSynchronize(st));
+    if (!async && fast && getenv("POPBAM_B200_DEBUG"))
         fprintf(stderr, "[popbam_b200] bit-sliced path: %llu of %lld cells left for k_hard_cells (%.2f %%), %llu code slots; overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
                 h_final->n_cells, (long long)(span * n), 100.0 * (double)h_final->n_cells / (double)(span * n), h_final->n_codes,
                 h_final->arena_overflow, h_final->qual_over, h_final->qual_max_seen, h_final->spec_fail);
-    if (fast && (h_final->arena_overflow || h_final->qual_over || h_final->spec_fail)) {
+    if (!async && fast && (h_final->arena_overflow || h_final->qual_over || h_final->spec_fail)) {
         // an assumption of the bit-sliced path did not hold for this region: nothing of its result is used.  Raise the
         // quality ceiling / the arena size (both stay raised for the context) and run the region again; give up on the
         // bit-sliced path for this region after three attempts.
@@ -499,20 +520,28 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
         if (h_final->arena_overflow) c->arena_scale *= 4;
         c->reruns += 1;
         if (attempt >= 2 || c->arena_scale > 64) c->force_classic = 1;
-        const int rc = run_pipeline(c, attempt + 1);
+        const int rc = run_pipeline(c, attempt + 1, false);
         c->force_classic = 0;
         return rc;
     }
-    const int64_t S = *h_total;
-    c->s_total = S;
+    if (!async && fast) {           // what this region teaches the context
+        c->spec_valid = true;
+        c->spec_span = std::max(c->spec_span, c->ctr_host.max_span);
+        c->spec_density = (double)c->ctr_host.n_records / ((double)n * (double)std::max<int64_t>(span, 1));
+    }
+    // number of segregating sites: known now, or (asynchronous mode) bounded by the span -- the device arrays are laid out
+    // for the bound, the kernels read the real offsets from device memory, and fill_result copies what there is
+    const int64_t S = async ? span : *h_total;
+    c->s_total = async ? -1 : S;
+    c->seg_cap = S;
     int s_max = 0;
-    for (int w = 0; w < NW; ++w) s_max = std::max(s_max, hl0.segsites[w]);
+    if (!async) for (int w = 0; w < NW; ++w) s_max = std::max(s_max, hl0.segsites[w]);
 
     // ---- segregating-site lists
     const bool with_cb = (c->analyses & PB_AN_SNP) != 0;
     const SegLayout sl0 = seg_layout(nullptr, S, n, with_cb);
     PB_TRY(dev_reserve(c, c->d_seg_type, sl0.bytes));
-    PB_TRY(host_reserve(c, c->h_seg, sl0.bytes));
+    if (!async) PB_TRY(host_reserve(c, c->h_seg, sl0.bytes));
     const SegLayout sl = seg_layout(c->d_seg_type.p, S, n, with_cb);
     k_window_sites<true><<<NW, 256, 0, st>>>(c->span_beg, pa.win_beg, pa.win_end, pa.site_flag, pa.site_type, pa.ref, pa.ref_len,
                                             with_cb ? dp<uint64_t>(c->d_cb) : nullptr, n, dl.num_sites, dl.segsites, dl.seg_off,
@@ -586,7 +615,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0) {
 
     // ---- results to pinned host memory
     PB_CUDA(c, cudaMemcpyAsync(c->h_small.p, c->d_stats.p, dl.bytes, cudaMemcpyDeviceToHost, st));
-    if (S > 0) PB_CUDA(c, cudaMemcpyAsync(c->h_seg.p, c->d_seg_type.p, sl.bytes, cudaMemcpyDeviceToHost, st));
+    if (!async && S > 0) PB_CUDA(c, cudaMemcpyAsync(c->h_seg.p, c->d_seg_type.p, sl.bytes, cudaMemcpyDeviceToHost, st));
     if (P.flags & PB_FLAG_EMIT_CB) {
         Carver cv(nullptr);
         cv.take<uint64_t>((size_t)span * n); cv.take<uint64_t>((size_t)span); cv.take<uint8_t>((size_t)span);
@@ -606,6 +635,41 @@ int fill_result(pb_ctx *c, pb_region_result *out) {
     const pb_params &P = c->prm;
     const int n = P.n_samples, NW = c->nw;
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->async_run) {
+        // the region was enqueued on assumptions (run_pipeline): look at what the device found
+        const PbCounters fin = *reinterpret_cast<PbCounters *>(reinterpret_cast<unsigned char *>(c->h_ctr.p) + 2 * sizeof(PbCounters));
+        if (fin.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
+        if (fin.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
+        if (getenv("POPBAM_B200_DEBUG"))
+            fprintf(stderr, "[popbam_b200] asynchronous region: %llu cells left for k_hard_cells, overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
+                    fin.n_cells, fin.arena_overflow, fin.qual_over, fin.qual_max_seen, fin.spec_fail);
+        if (fin.arena_overflow || fin.qual_over || fin.spec_fail) {
+            if (fin.qual_over) c->qual_ceiling = std::min(63, std::max(c->qual_ceiling + 1, fin.qual_max_seen));
+            if (fin.qual_high) { c->qual_robust = true; c->qual_ceiling = 63; }
+            if (fin.arena_overflow) c->arena_scale *= 4;
+            c->reruns += 1;
+            PB_TRY(run_pipeline(c, 0, false));          // with the host round trips: learns the span / density / cap again
+            PB_CUDA(c, cudaStreamSynchronize(c->stream));
+        } else {
+            c->spec_span = std::max(c->spec_span, fin.max_span);
+            c->spec_density = (double)fin.n_records / ((double)n * (double)std::max<int64_t>((int64_t)c->span_end - c->span_beg, 1));
+            c->ctr_host = fin;
+            // the segregating-site arrays: device layout for seg_cap entries, host layout for the S there are
+            const int64_t S = *(reinterpret_cast<int64_t *>(c->h_ctr.p) + (sizeof(PbCounters) + 7) / 8);
+            c->s_total = S;
+            const SegLayout dl = seg_layout(c->d_seg_type.p, c->seg_cap, n, false), hl0 = seg_layout(nullptr, S, n, false);
+            PB_TRY(host_reserve(c, c->h_seg, hl0.bytes));
+            const SegLayout hl = seg_layout(c->h_seg.p, S, n, false);
+            if (S > 0) {
+                PB_CUDA(c, cudaMemcpyAsync(hl.seg_type, dl.seg_type, sizeof(uint64_t) * (size_t)S, cudaMemcpyDeviceToHost, c->stream));
+                PB_CUDA(c, cudaMemcpyAsync(hl.seg_pos, dl.seg_pos, sizeof(uint32_t) * (size_t)S, cudaMemcpyDeviceToHost, c->stream));
+                PB_CUDA(c, cudaMemcpyAsync(hl.seg_idx, dl.seg_idx, sizeof(uint32_t) * (size_t)S, cudaMemcpyDeviceToHost, c->stream));
+                PB_CUDA(c, cudaMemcpyAsync(hl.seg_ref, dl.seg_ref, (size_t)S, cudaMemcpyDeviceToHost, c->stream));
+                PB_CUDA(c, cudaStreamSynchronize(c->stream));
+            }
+        }
+        c->async_run = false;
+    }
     cudaEventElapsedTime(&c->ms_prep, c->ev[0], c->ev[1]);
     { float per_base = 0; cudaEventElapsedTime(&per_base, c->ev[6], c->ev[2]); c->ms_prep += per_base; }
     cudaEventElapsedTime(&c->ms_pileup, c->ev[2], c->ev[3]);
@@ -695,6 +759,7 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     c->n_sms = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     { const char *e = getenv("POPBAM_B200_PILEUP"); c->classic = e && strcmp(e, "classic") == 0; }
+    { const char *e = getenv("POPBAM_B200_SYNC"); c->no_async = e && *e == '1'; }
     {
         auto wave = [&](auto kern, int threads) {
             int per_sm = 0;
@@ -789,18 +854,21 @@ int pb_region_begin(pb_ctx *c, uint32_t analyses, int32_t n_windows, const int32
     PB_TRY(dev_reserve(c, c->d_wend, sizeof(int32_t) * (size_t)n_windows));
     PB_CUDA(c, cudaMemcpyAsync(c->d_wbeg.p, c->h_wbeg.data(), sizeof(int32_t) * (size_t)n_windows, cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaMemcpyAsync(c->d_wend.p, c->h_wend.data(), sizeof(int32_t) * (size_t)n_windows, cudaMemcpyHostToDevice, c->stream));
-    c->n_reads = c->n_cig = c->n_bytes = 0;
+    c->n_reads = c->n_cig = c->n_bytes = c->n_pushes = 0;
     c->r_pos.clear(); c->r_meta.clear(); c->r_cig_off.clear(); c->r_cigar.clear(); c->r_base_off.clear(); c->r_seq4.clear(); c->r_qual.clear();
     c->state = ST_OPEN;
     return PB_OK;
 }
 
-int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
+int pb_push_batch_async(pb_ctx *c, const pb_read_batch *b) {
     if (!c || !b) return fail(c, PB_ERR_ARG, "pb_push_batch: null argument");
     if (c->state != ST_OPEN) return fail(c, PB_ERR_STATE, "pb_push_batch outside pb_region_begin .. pb_region_launch");
     if (b->n_reads < 0 || b->n_cigar < 0 || b->n_bases < 0 || (b->n_bases & 1)) return fail(c, PB_ERR_ARG, "pb_push_batch: bad counts");
     if (b->n_reads == 0) return PB_OK;
     if (!b->pos || !b->meta || !b->cig_off || !b->cigar || !b->base_off || !b->seq4 || !b->qual) return fail(c, PB_ERR_ARG, "pb_push_batch: null array");
+    if ((uint64_t)b->n_bases > 0xffffffffULL || (uint64_t)b->n_cigar > 0xffffffffULL) return fail(c, PB_ERR_ARG, "pb_push_batch: a batch holds at most 2^32 - 1 base bytes / CIGAR operations (its offsets are 32-bit); split it");
+    if (b->cig_off[0] != 0 || b->base_off[0] != 0 || (int64_t)b->cig_off[b->n_reads] != b->n_cigar || (int64_t)b->base_off[b->n_reads] != b->n_bases)
+        return fail(c, PB_ERR_ARG, "pb_push_batch: cig_off / base_off do not start at 0 or do not end at n_cigar / n_bases");
     if ((uint64_t)(c->n_cig + b->n_cigar) > 0xfffffff0ULL) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^32 CIGAR operations in one region");
     if ((uint64_t)(c->n_reads + b->n_reads) > 0xfffffff0ULL) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^32 reads in one region");
     if ((uint64_t)(c->n_bytes + b->n_bases) >> 36) return fail(c, PB_ERR_UNSUPPORTED, "more than 2^36 base bytes in one region");
@@ -816,12 +884,14 @@ int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
     // 64 zeroed bytes behind the last base: k_pile_fast converts whole 32-byte groups of qual[] (16 of seq4[])
     PB_TRY(dev_reserve(c, c->d_qual, (size_t)(c->n_bytes + b->n_bases) + 96, (size_t)c->n_bytes));
     PB_TRY(dev_reserve(c, c->d_seq4, (size_t)(c->n_bytes + b->n_bases) / 2 + 96, (size_t)c->n_bytes / 2));
-    PB_TRY(dev_reserve(c, c->d_tmp_cig, 4 * (size_t)(b->n_reads + 1)));
-    PB_TRY(dev_reserve(c, c->d_tmp_base, 4 * (size_t)(b->n_reads + 1)));
+    // batch-relative offsets of every push of the region, one after the other (no push waits for the one before it)
+    const size_t t0 = (size_t)N0 + (size_t)c->n_pushes;
+    PB_TRY(dev_reserve(c, c->d_tmp_cig, 4 * (t0 + (size_t)b->n_reads + 1), 4 * t0));
+    PB_TRY(dev_reserve(c, c->d_tmp_base, 4 * (t0 + (size_t)b->n_reads + 1), 4 * t0));
     PB_CUDA(c, cudaMemcpyAsync(dp<int32_t>(c->d_pos) + N0, b->pos, 4 * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
     PB_CUDA(c, cudaMemcpyAsync(dp<uint32_t>(c->d_meta) + N0, b->meta, 4 * (size_t)b->n_reads, cudaMemcpyHostToDevice, st));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_tmp_cig.p, b->cig_off, 4 * (size_t)(b->n_reads + 1), cudaMemcpyHostToDevice, st));
-    PB_CUDA(c, cudaMemcpyAsync(c->d_tmp_base.p, b->base_off, 4 * (size_t)(b->n_reads + 1), cudaMemcpyHostToDevice, st));
+    PB_CUDA(c, cudaMemcpyAsync(dp<uint32_t>(c->d_tmp_cig) + t0, b->cig_off, 4 * (size_t)(b->n_reads + 1), cudaMemcpyHostToDevice, st));
+    PB_CUDA(c, cudaMemcpyAsync(dp<uint32_t>(c->d_tmp_base) + t0, b->base_off, 4 * (size_t)(b->n_reads + 1), cudaMemcpyHostToDevice, st));
     if (b->n_cigar) PB_CUDA(c, cudaMemcpyAsync(dp<uint32_t>(c->d_cigar) + c->n_cig, b->cigar, 4 * (size_t)b->n_cigar, cudaMemcpyHostToDevice, st));
     if (b->n_bases) {
         PB_CUDA(c, cudaMemcpyAsync(dp<uint8_t>(c->d_qual) + c->n_bytes, b->qual, (size_t)b->n_bases, cudaMemcpyHostToDevice, st));
@@ -829,13 +899,18 @@ int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
     }
     PB_CUDA(c, cudaMemsetAsync(dp<uint8_t>(c->d_qual) + c->n_bytes + b->n_bases, 0, 64, st));
     PB_CUDA(c, cudaMemsetAsync(dp<uint8_t>(c->d_seq4) + (c->n_bytes + b->n_bases) / 2, 0, 64, st));
-    k_rebase<<<nblk(b->n_reads, 256), 256, 0, st>>>(b->n_reads, N0, dp<uint32_t>(c->d_tmp_cig), dp<uint32_t>(c->d_tmp_base), (uint64_t)c->n_cig,
+    k_rebase<<<nblk(b->n_reads, 256), 256, 0, st>>>(b->n_reads, N0, dp<uint32_t>(c->d_tmp_cig) + t0, dp<uint32_t>(c->d_tmp_base) + t0, (uint64_t)c->n_cig,
                                                    (uint64_t)c->n_bytes, dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint64_t>(c->d_base));
     c->launches += 1;
     PB_CUDA(c, cudaGetLastError());
-    // the temporaries are reused by the next push
-    PB_CUDA(c, cudaStreamSynchronize(st));
-    c->n_reads = N1; c->n_cig += b->n_cigar; c->n_bytes += b->n_bases;
+    c->n_reads = N1; c->n_cig += b->n_cigar; c->n_bytes += b->n_bases; c->n_pushes += 1;
+    return PB_OK;
+}
+
+int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
+    const int rc = pb_push_batch_async(c, b);
+    if (rc != PB_OK) return rc;
+    PB_CUDA(c, cudaStreamSynchronize(c->stream));                  // the caller may reuse its arrays when this returns
     return PB_OK;
 }
 

@@ -118,3 +118,87 @@ def test_depth_cap_binds_after_the_planes_were_built():
     assert int(want["segsites"].sum()) > 0
     assert_same(got, want, AN_NAMES)
     orc.close(); ctx.close(); fx.close()
+
+
+def _an(names=AN_NAMES):
+    an = 0
+    for a in names:
+        an |= pbtest.AN[a]
+    return an
+
+
+NOSYNC = ["NUCDIV", "SFS", "HAPLO_K", "DIVERGE_POP"]     # analyses whose buffers do not depend on the number of segregating sites
+
+
+def test_asynchronous_regions_equal_the_oracle_and_the_synchronous_run():
+    """After its first region a context enqueues the next ones without a host round trip, on launch parameters learnt
+    from the earlier regions and verified on the device (pb_lib.cu run_pipeline).  Results must not depend on the mode."""
+    fxs = [pbtest.Fixture(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=d, snp_density=0.04, het_frac=0.3, seed=sd)
+           for d, sd in ((22.0, 81), (31.0, 82), (12.0, 83))]
+    p = fxs[0].params(flags=pbtest.FLAG["OUTGROUP"], outidx=fxs[0].n_samples - 1)
+    an = _an(NOSYNC)
+    wb, we = pbtest.window_grid(0, 9000, 3000)
+    for sync in (False, True):
+        if sync:
+            os.environ["POPBAM_B200_SYNC"] = "1"
+        try:
+            ctx = popbam_b200.Context(p)
+        finally:
+            os.environ.pop("POPBAM_B200_SYNC", None)
+        for fx in fxs:
+            ctx.set_contig(0, fx.ref())
+            ctx.region_begin(an, wb, we)
+            ctx.push_batch_async(fx.batch())
+            ctx.region_end()
+            assert ctx.path() == 1
+            orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
+            assert_same(pbtest.result_arrays(ctx.res), pbtest.result_arrays(orc.res), NOSYNC)
+            orc.close()
+        # the same reads again, resident on the device
+        ctx.relaunch(); ctx.wait()
+        orc = pbtest.OracleRun(p, fxs[-1].batch(), fxs[-1].ref(), an, wb, we)
+        assert_same(pbtest.result_arrays(ctx.res), pbtest.result_arrays(orc.res), NOSYNC)
+        orc.close()
+        assert ctx.reruns() == 0
+        ctx.close()
+    for fx in fxs:
+        fx.close()
+
+
+def test_asynchronous_region_whose_assumptions_fail_is_run_again():
+    """Region 2 has longer reads than the context has seen (staging slots too small) and base qualities far above the
+    assumed ceiling; region 3 is deep enough for the raw-depth cap to bind.  The device reports each, the host runs the
+    region again (with the round trips), and the results still equal the oracle."""
+    a = pbtest.Fixture(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=20.0, snp_density=0.04, seed=91)
+    b = pbtest.Fixture(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=20.0, read_len=150, snp_density=0.2, het_frac=0.4, edge_mode=1, seed=92)
+    c = pbtest.Fixture(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=90.0, snp_density=0.04, seed=93)
+    p = a.params(flags=pbtest.FLAG["OUTGROUP"], outidx=a.n_samples - 1, max_depth=110)
+    an = _an(NOSYNC)
+    wb, we = pbtest.window_grid(0, 9000, 3000)
+    ctx = popbam_b200.Context(p)
+    paths = []
+    for fx in (a, b, c, a):
+        ctx.set_contig(0, fx.ref())
+        ctx.region_begin(an, wb, we)
+        ctx.push_batch(fx.batch())
+        ctx.region_end()
+        paths.append(ctx.path())
+        orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
+        assert_same(pbtest.result_arrays(ctx.res), pbtest.result_arrays(orc.res), NOSYNC)
+        orc.close()
+    assert paths == [1, 1, 0, 1], paths          # region 3 ends up in the single-kernel pileup (cap binds)
+    assert ctx.reruns() >= 2
+    # unsorted reads in asynchronous mode are still reported (bam_pileup.c:384-395)
+    import ctypes as C
+    from test_gpu_parity import _slice_batch
+    keep = []
+    bb = a.batch()
+    hi = _slice_batch(bb, bb.n_reads // 2, bb.n_reads, keep)
+    lo = _slice_batch(bb, 0, bb.n_reads // 2, keep)
+    ctx.set_contig(0, a.ref())
+    ctx.region_begin(an, wb, we)
+    ctx.push_batch(hi); ctx.push_batch(lo)
+    assert ctx.L.pb_region_end(ctx.h, C.byref(ctx.res)) == -5
+    ctx.close()
+    for fx in (a, b, c):
+        fx.close()
