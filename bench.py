@@ -1,24 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- aligned Gbases/s of the per-window statistics path on B200 (BASELINE.json metric).
 
-Workload (config.workload): BASELINE.json configs[1] -- `popbam sfs` (Tajima's D, Fay & Wu's H; outgroup-polarised) on a
-23 Mb X-like contig, 10 samples + outgroup, 30x per sample, 100 bp reads, 10 kb windows, synthetic data from tools/pbsynth
-(SURVEY.md §8(d) data model).  The contig is fed as region shards of --shard-mb (the unit the host feeder hands over in
-production: BAM-index chunks of whole windows); ONE STEP = the whole contig = every shard once.
+Workload (config.workload): by default BASELINE.json configs[1] (--config c2) -- `popbam sfs` (Tajima's D, Fay & Wu's H;
+outgroup-polarised) on a 23 Mb X-like contig, 10 samples + outgroup, 30x per sample, 100 bp reads, 10 kb windows,
+synthetic data from tools/pbsynth (SURVEY.md §8(d) data model).  --config c1 / c3 / c4 / c5 select the other BASELINE
+configurations.  The contig is fed as region shards of --shard-mb (the unit the host feeder hands over in production:
+BAM-index chunks of whole windows); ONE STEP = the whole contig = every shard once.
 
   value      whole-job aligned Gbases/s with every shard's read batch already resident in HBM: the complete device
-             pipeline (per-read prep, sample partition, pileup/call/site kernel, window compaction, window statistics,
-             result copy) re-run on resident inputs, timed with CUDA events on the library's stream.
-  e2e        same job through the public C ABI from PINNED HOST batches: pb_region_begin / pb_push_batch (host->device
-             copy inside the timed region) / pb_region_end (device->host result copy inside the timed region).
-  roofline   the pileup / call / site stage (k_pile_fast, k_hard_cells, k_fast_sites): algorithmic bytes per region / the
-             stage's CUDA-event duration.  The per-base pass that feeds it (k_planes) is timed with the
-             preparation, as the base-code pass of the single-kernel formulation was.
+             pipeline (per-read prep, sample partition, counting pileup, hard cells, sites, window compaction, window
+             statistics, result copy) re-run on resident inputs, timed with CUDA events on the library's streams.
+  e2e        same job through the public C ABI from PINNED HOST batches: pb_region_begin / pb_push_batch_async (host->
+             device copy inside the timed region) / pb_region_end (device->host result copy inside the timed region).
+  roofline   the WHOLE device pipeline: algorithmic bytes of a step / the step's CUDA-event duration (the same region
+             `value` is timed on); `dominant_kernel` = the pileup / call / site stage alone; `traffic` = DRAM bytes of all
+             kernels of a region from the committed ncu launch list.
+  verified   before anything is timed, one window of every distinct shard is compared with the CPU oracle.
   cpu_baseline  the unmodified reference (oracle/_ref/popbam, built from /root/reference by oracle/Makefile) timed on
              one host core on a bounded sample of the same workload; falls back to the oracle port if the binary is absent.
+  cli_from_bam  the `popbam` command line of this repo on BAM/BAI/FASTA files (host feeder + GPU), start-up separately.
 
 `--impl reference` times the reference CPU implementation with one process per host core over split regions.
-Under torchrun every rank runs its own 23 Mb job on its own GPU (weak scaling; no collective on the data path).
+Under torchrun every rank runs its own contig on its own GPU (weak scaling; no collective on the data path).
 """
 import argparse
 import ctypes as C
@@ -37,14 +40,26 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 import numpy as np  # noqa: E402
 
-# DRAM bytes (read + written) of the pileup stage's kernels on a 2.3 Mb shard of this workload, from the committed ncu
-# launch list profiles/r1_end_launches.csv (dram__bytes_read.sum + dram__bytes_write.sum per kernel): k_pile_fast, the
-# cell-list scan, k_hard_cells, k_fast_sites
-TRAFFIC_BYTES_PER_LAUNCH = 488.6e6 + 6.4e6 + 980.9e6 + 30.8e6
-WIN = 10000
+# DRAM bytes (read + written) of ALL kernels of one region on a 2.3 Mb shard of configs[1], summed over the committed ncu
+# launch list profiles/r2_launches.csv (dram__bytes_read.sum + dram__bytes_write.sum per kernel, one pipeline run)
+TRAFFIC_BYTES_PER_SHARD_C2 = 1.93e9
 READ_LEN = 100
-DEPTH = 30.0
-N_INGROUP = 10
+
+# BASELINE.json configs[0..4] as c1..c5 (SURVEY.md §8(d) data model).  One STEP = the whole contig = every shard once.
+CONFIGS = {
+    "c1": dict(label="configs[0]: popbam nucdiv", an=["NUCDIV"], flags=["OUTGROUP"], contig_mb=1.0, shard_mb=1.0, n_ingroup=10, has_outgroup=1,
+               rg_per_sample=1, depth=20.0, win=10000, snp=0.01, cli=["nucdiv", "-w", "10", "-p", "og"]),
+    "c2": dict(label="configs[1]: popbam sfs -p og", an=["SFS"], flags=["OUTGROUP"], contig_mb=23.0, shard_mb=2.3, n_ingroup=10, has_outgroup=1,
+               rg_per_sample=1, depth=30.0, win=10000, snp=0.01, cli=["sfs", "-w", "10", "-p", "og"]),
+    "c3": dict(label="configs[2]: popbam ld -o 0 / -o 1 / -o 2 (ZnS, omega_max, Wall B/Q in one pass)", an=["LD_ZNS", "LD_OMEGA", "LD_WALL"], flags=[],
+               contig_mb=5.0, shard_mb=0.5, n_ingroup=64, has_outgroup=0, rg_per_sample=1, depth=20.0, win=50000, snp=0.06, cli=["ld", "-w", "50"]),
+    "c4": dict(label="configs[3]: popbam diverge -o 0 / -o 1 + haplo -o 0 / -o 1 / -o 2 in one pass, one contig per GPU",
+               an=["DIVERGE_IND", "DIVERGE_POP", "HAPLO_K", "HAPLO_EHHS", "HAPLO_DXY"], flags=["OUTGROUP"], contig_mb=24.0, shard_mb=1.0,
+               n_ingroup=31, has_outgroup=1, rg_per_sample=1, depth=20.0, win=10000, snp=0.01, cli=["diverge", "-w", "10", "-p", "og"]),
+    "c5": dict(label="configs[4]: nucdiv + sfs + ld (ZnS) in one pass, 128 read groups -> 64 samples", an=["NUCDIV", "SFS", "LD_ZNS"], flags=["OUTGROUP"],
+               contig_mb=10.0, shard_mb=0.5, n_ingroup=63, has_outgroup=1, rg_per_sample=2, depth=30.0, win=10000, snp=0.01,
+               cli=["nucdiv", "-w", "10", "-p", "og"]),
+}
 
 
 def parse():
@@ -53,16 +68,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--contig-mb", type=float, default=23.0)
-    ap.add_argument("--shard-mb", type=float, default=2.3)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="BASELINE.json configs[0..4] = c1..c5 (default: configs[1], the one the metric is quoted on)")
+    ap.add_argument("--contig-mb", type=float, default=0.0, help="0 = the configuration's own")
+    ap.add_argument("--shard-mb", type=float, default=0.0, help="0 = the configuration's own")
     ap.add_argument("--threads", type=int, default=0, help="generator threads (0 = auto)")
     ap.add_argument("--inflight", type=int, default=4, help="region shards processed concurrently per GPU (one host thread and one context each)")
     ap.add_argument("--distinct-shards", type=int, default=0,
                     help="generate this many distinct shards and cycle them (0 = auto: all distinct when the host has >= 8 cores per rank)")
     ap.add_argument("--cpu-sample-kb", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cli-sample-kb", type=int, default=1000, help="BAM sample for the command-line (from-BAM) tier; 0 = skip")
-    return ap.parse_args()
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one window per distinct shard (outside the timed region)")
+    ap.add_argument("--cli-sample-kb", type=int, default=-1, help="BAM sample for the command-line (from-BAM) tier; 0 = skip, -1 = the whole contig up to 23 Mb")
+    a = ap.parse_args()
+    a.cfg = CONFIGS[a.config]
+    a.contig_mb = a.contig_mb or a.cfg["contig_mb"]
+    a.shard_mb = a.shard_mb or a.cfg["shard_mb"]
+    return a
 
 
 def dist_env():
@@ -110,7 +131,8 @@ class ClockSampler:
 
 
 def shard_plan(args):
-    shard_len = int(round(args.shard_mb * 1e6 / WIN)) * WIN
+    win = args.cfg["win"]
+    shard_len = max(1, int(round(args.shard_mb * 1e6 / win))) * win
     n_shards = max(1, int(round(args.contig_mb * 1e6 / shard_len)))
     return shard_len, n_shards
 
@@ -121,10 +143,72 @@ def gen_threads(args, world):
     return max(2, min(32, (os.cpu_count() or 8) // max(1, world)))
 
 
+def product_window_grid(beg, end, win):
+    """The reference's window arithmetic through the PRODUCT's pb_window_grid (pop_nucdiv.cpp:48-78)."""
+    import popbam_b200
+    L = popbam_b200.lib()
+    nw = L.pb_window_grid(beg, end, win, 0, None, None)
+    wb = (C.c_int32 * max(nw, 1))(); we = (C.c_int32 * max(nw, 1))()
+    L.pb_window_grid(beg, end, win, nw, wb, we)
+    return np.array(wb[:nw], dtype=np.int32), np.array(we[:nw], dtype=np.int32)
+
+
 def algorithmic_bytes(batch, n_cells, n_sites):
     """per read pos 4 + meta 4 + offsets 8 + 4/cigar op + packed seq + qual; per (site,sample) one 8-byte
     consensus word; one reference byte per site."""
     return int(batch.n_reads) * 16 + int(batch.n_cigar) * 4 + int(batch.n_bases) // 2 + int(batch.n_bases) + 8 * n_cells + n_sites
+
+
+def config_fixture(cfg, length, seed, threads):
+    import pbtest
+    return pbtest.Fixture(contig_len=length + 1, n_ingroup=cfg["n_ingroup"], has_outgroup=cfg["has_outgroup"], rg_per_sample=cfg["rg_per_sample"],
+                          depth=cfg["depth"], read_len=READ_LEN, snp_density=cfg["snp"], seed=seed, n_threads=threads)
+
+
+def config_params(cfg, fx, device=0):
+    import pbtest
+    fl = 0
+    for f in cfg["flags"]:
+        fl |= pbtest.FLAG[f]
+    return fx.params(flags=fl, outidx=fx.n_samples - 1 if "OUTGROUP" in cfg["flags"] else 0, device=device)
+
+
+def verify_shard(sh, res_arrays, an_names, an):
+    """One window of the shard against the CPU oracle (TEST INFRASTRUCTURE, outside every timed region): site counts and
+    segregating-site types bit for bit, window statistics to 1e-9."""
+    import pbtest
+    BY_AN = pbtest.BY_AN
+    w = len(sh["wb"]) // 2
+    orc = pbtest.OracleRun(sh["params"], sh["batch"], sh["ref"], an, sh["wb"][w:w + 1], sh["we"][w:w + 1])
+    want = pbtest.result_arrays(orc.res)
+    got = res_arrays
+    assert int(want["num_sites"][0]) == int(got["num_sites"][w]), "bench self-check: num_sites of window %d" % w
+    s0, s1 = int(got["seg_off"][w]), int(got["seg_off"][w + 1])
+    assert np.array_equal(want["seg_type"], got["seg_type"][s0:s1]), "bench self-check: segregating-site types of window %d" % w
+    assert np.array_equal(want["seg_pos"], got["seg_pos"][s0:s1]), "bench self-check: segregating-site positions of window %d" % w
+    NW = len(sh["wb"])
+    dev = {}
+    for name in an_names:
+        ints, flts = BY_AN[name]
+        for k in list(ints) + list(flts):
+            per = got[k].size // NW
+            if per == 0 or k.startswith("seg_"):
+                continue
+            a, b = want[k][:per], got[k][w * per:(w + 1) * per]
+            if k in ints:
+                assert np.array_equal(a, b), "bench self-check: %s of window %d" % (k, w)
+            else:
+                assert np.array_equal(np.isnan(a), np.isnan(b)), "bench self-check: NA pattern of %s, window %d" % (k, w)
+                ok = ~np.isnan(a) & (a != 0)
+                d = float(np.max(np.abs(a[ok] - b[ok]) / np.abs(a[ok]))) if ok.any() else 0.0
+                dev[k] = max(dev.get(k, 0.0), d)
+                # omega_max of a window with thousands of kept SNPs: the reference (and the oracle, which restates its loop)
+                # adds ~K^3/3 terms one by one into three running sums, whose own rounding noise grows with K^1.5 * 2^-53;
+                # tests/test_gpu_parity.py holds omega_max to 1e-9 up to K = 1850
+                tol = 5e-8 if k == "omegamax" else 1e-9
+                assert d <= tol, "bench self-check: %s of window %d deviates by %.3g (relative)" % (k, w, d)
+    orc.close()
+    return w, dev
 
 
 def run_b200(args):
@@ -136,26 +220,31 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    cfg = args.cfg
+    WIN = cfg["win"]
     shard_len, n_shards = shard_plan(args)
-    n = N_INGROUP + 1
-    an = pbtest.AN["SFS"]
+    an = 0
+    for a in cfg["an"]:
+        an |= pbtest.AN[a]
     shards = []
     t_gen = time.time()
     distinct = args.distinct_shards or (n_shards if (os.cpu_count() or 8) // world >= 8 else min(n_shards, 3))
-    try:        # ~1.3 GB pinned + ~1.3 GB transient per distinct 2.3 Mb shard and rank: stay well inside the host's memory
+    bytes_per_pos = (cfg["n_ingroup"] + cfg["has_outgroup"]) * cfg["depth"] * 1.75          # pinned bytes per reference position
+    try:        # pinned + transient copies of every distinct shard and rank: stay well inside the host's memory
         import psutil
-        per_shard = 2.8e9 * (shard_len / 2.3e6)
+        per_shard = 2.2 * bytes_per_pos * shard_len
         fit = int(psutil.virtual_memory().available * 0.5 / max(1, world) / per_shard)
         if not args.distinct_shards:
             distinct = max(1, min(distinct, fit))
     except Exception:
         pass
+    n = None
     for s in range(n_shards):
         if s >= distinct:       # cycle the generated shards (same shape, same work; each still has its own context and copy in HBM)
             shards.append(shards[s % distinct])
             continue
-        fx = pbtest.Fixture(contig_len=shard_len + 1, n_ingroup=N_INGROUP, has_outgroup=1, depth=DEPTH, read_len=READ_LEN,
-                            snp_density=0.01, seed=1000 * (rank + 1) + s, n_threads=gen_threads(args, world))
+        fx = config_fixture(cfg, shard_len, 1000 * (rank + 1) + s, gen_threads(args, world))
+        n = fx.n_samples
         b = fx.batch()
         # pinned host copies of the batch arrays (what the host feeder fills in production)
         pins, pb = {}, pbtest.Batch()
@@ -168,8 +257,8 @@ def run_b200(args):
             C.memmove(t.data_ptr(), getattr(b, name), t.numel() * t.element_size())
             pins[name] = t
             setattr(pb, name, C.cast(t.data_ptr(), C.POINTER(ct)))
-        wb, we = pbtest.window_grid(0, shard_len + 1, WIN)
-        p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=n - 1, device=local)
+        wb, we = product_window_grid(0, shard_len + 1, WIN)
+        p = config_params(cfg, fx, local)
         shards.append(dict(batch=pb, pins=pins, ref=fx.ref(), wb=wb, we=we, params=p, aligned=fx.aligned_bases(),
                            h2d=sum(t.numel() * t.element_size() for t in pins.values())))
         fx.close()
@@ -202,8 +291,6 @@ def run_b200(args):
         return ctx.stage_times()[1]
 
     def resident_step():
-        # the library allows one context per host thread; with two shards in flight the host round trips inside a
-        # region's pipeline (two small synchronisations) are hidden behind the other shard's kernels
         return sum(pool.map(one_resident, ctxs))
 
     def barrier():
@@ -223,6 +310,18 @@ def run_b200(args):
     # ---- e2e (also leaves every shard resident for the device-only leg); clocks are sampled over both timed legs
     for _ in range(max(1, args.warmup)):
         d2h = e2e_step()
+    # ---- what is about to be timed is checked first: one window per distinct shard against the CPU oracle
+    verified = None
+    if not args.no_verify and rank == 0:
+        t_v = time.time()
+        wins = [verify_shard(shards[i], pbtest.result_arrays(ctxs[i].res), cfg["an"], an) for i in range(min(distinct, n_shards))]
+        devs = {}
+        for _w, dv in wins:
+            for k, v in dv.items():
+                devs[k] = max(devs.get(k, 0.0), v)
+        verified = {"against": "oracle/pb_oracle.c (CPU restatement), outside the timed regions", "windows": len(wins), "max_relative_deviation": devs,
+                    "what": "num_sites, segregating-site positions and types bit for bit; window statistics to 1e-9", "seconds": round(time.time() - t_v, 1)}
+    paths = [c.path() for c in ctxs]
     barrier()
     clk = ClockSampler(local)
     clk.__enter__()
@@ -234,50 +333,47 @@ def run_b200(args):
 
     # ---- device-resident leg, CUDA events around the whole step on the library's stream(s)
     total_aligned = sum(int(c.res.aligned_bases) for c in ctxs)
-    n_sites_total = sum(int(we[-1] - wb[0]) for wb, we in ((s["wb"], s["we"]) for s in shards))
     for _ in range(args.warmup):
         resident_step()
     launches0 = sum(c.kernel_launches() for c in ctxs)
     pile_ms = 0.0
     barrier()
-    if True:
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        ev1 = [torch.cuda.Event() for _ in ctxs]
-        streams = [torch.cuda.ExternalStream(c.L.pb_stream(c.h)) for c in ctxs]
-        cur = torch.cuda.current_stream()
-        step_ms = 0.0
-        for _ in range(args.steps):
-            # device-side bracket: e0 precedes every library stream's work of this step, e1 follows all of it
-            e0.record(cur)
-            for st in streams:
-                st.wait_event(e0)
-            resident_step()
-            for i, st in enumerate(streams):
-                ev1[i].record(st)
-                cur.wait_event(ev1[i])
-            e1.record(cur)
-            torch.cuda.synchronize()
-            step_ms += e0.elapsed_time(e1)
-        barrier()
-        # the hot kernel alone (roofline): one more pass with the shards strictly one after the other, so that no
-        # other kernel shares the SMs while k_pileup_call is timed by the library's events
-        seq_ms = 0.0
-        stage_ms = [0.0, 0.0, 0.0, 0.0]
-        for ctx, st in zip(ctxs, streams):
-            e0.record(st)
-            ctx.relaunch()
-            ctx.wait()
-            e1.record(st)
-            e1.synchronize()
-            seq_ms += e0.elapsed_time(e1)
-            stt = ctx.stage_times()
-            pile_ms += stt[1]
-            for i in range(4):
-                stage_ms[i] += stt[i]
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    ev1 = [torch.cuda.Event() for _ in ctxs]
+    streams = [torch.cuda.ExternalStream(c.L.pb_stream(c.h)) for c in ctxs]
+    cur = torch.cuda.current_stream()
+    step_ms = 0.0
+    for _ in range(args.steps):
+        # device-side bracket: e0 precedes every library stream's work of this step, e1 follows all of it
+        e0.record(cur)
+        for st in streams:
+            st.wait_event(e0)
+        resident_step()
+        for i, st in enumerate(streams):
+            ev1[i].record(st)
+            cur.wait_event(ev1[i])
+        e1.record(cur)
+        torch.cuda.synchronize()
+        step_ms += e0.elapsed_time(e1)
+    barrier()
+    launches = sum(c.kernel_launches() for c in ctxs) - launches0
+    # the stages alone: one more pass with the shards strictly one after the other (library events, pb_stage_times)
+    seq_ms = 0.0
+    stage_ms = [0.0, 0.0, 0.0, 0.0]
+    for ctx, st in zip(ctxs, streams):
+        e0.record(st)
+        ctx.relaunch()
+        ctx.wait()
+        e1.record(st)
+        e1.synchronize()
+        seq_ms += e0.elapsed_time(e1)
+        stt = ctx.stage_times()
+        pile_ms += stt[1]
+        for i in range(4):
+            stage_ms[i] += stt[i]
     clk.__exit__(None, None, None)
     dev_s = max_over_ranks(step_ms / 1e3)
-    launches = sum(c.kernel_launches() for c in ctxs) - launches0
 
     peaks = {}
     try:
@@ -286,39 +382,59 @@ def run_b200(args):
         pass
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = sum(algorithmic_bytes(s["batch"], int(s["we"][-1] - s["wb"][0]) * n, int(s["we"][-1] - s["wb"][0])) for s in shards)
-    pile_s = pile_ms / 1e3                        # all shards' hot-kernel launches of one (sequential) step
-    achieved = alg_bytes / pile_s / 1e9
+    step_s = dev_s / args.steps
+    achieved = alg_bytes / step_s / 1e9                      # the WHOLE device pipeline of every shard of a step
     n_windows = sum(len(s["wb"]) for s in shards)
+    is_c2_shard = args.config == "c2" and abs(shard_len - 2300000) < 1
 
     line = {
-        "metric": "aligned Gbases/s", "value": world * total_aligned / (dev_s / args.steps) / 1e9, "unit": "Gbases/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+        "metric": "aligned Gbases/s", "value": world * total_aligned / step_s / 1e9, "unit": "Gbases/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u64 + f64 (error model)",
         "data": "synthetic (tools/pbsynth, seeded)",
-        "config": {"workload": "configs[1]: popbam sfs -p og, %.1f Mb contig as %d region shards of %.2f Mb, 10 samples + outgroup, "
-                               "30x, 100 bp reads, 10 kb windows" % (n_shards * shard_len / 1e6, n_shards, shard_len / 1e6),
-                   "per_gpu": "each rank runs its own contig", "windows_per_step": n_windows * world,
-                   "windows_per_s": world * n_windows / (dev_s / args.steps),
+        "config": {"workload": "%s, %.1f Mb contig as %d region shards of %.2f Mb, %d samples%s, %gx per sample, 100 bp reads, %d kb windows" % (
+                       cfg["label"], n_shards * shard_len / 1e6, n_shards, shard_len / 1e6, n, " (%d read groups each)" % cfg["rg_per_sample"] if cfg["rg_per_sample"] > 1 else "",
+                       cfg["depth"], WIN // 1000),
+                   "config": args.config, "per_gpu": "each rank runs its own contig", "windows_per_step": n_windows * world,
+                   "windows_per_s": world * n_windows / step_s,
                    "aligned_bases_per_step": world * total_aligned, "l2": "inputs (%.1f GB per step) exceed L2" % (alg_bytes / 1e9),
-                   "distinct_shards": distinct, "shards_in_flight": max(1, args.inflight), "generator_s": round(t_gen, 1)},
+                   "distinct_shards": distinct, "shards_in_flight": max(1, args.inflight), "generator_s": round(t_gen, 1),
+                   "pileup_path": "counting kernels (k_pile_count + k_hard_cells)" if all(p == 1 for p in paths) else "single-kernel pileup on %d of %d shards" % (sum(1 for p in paths if p == 0), len(paths)),
+                   "regions_run_twice": sum(c.reruns() for c in ctxs)},
         "e2e": {"value": world * total_aligned / (e2e_s / args.steps) / 1e9, "unit": "Gbases/s",
                 "h2d_bytes_per_step": sum(s["h2d"] for s in shards), "d2h_bytes_per_step": int(d2h),
                 "windows_per_s": world * n_windows / (e2e_s / args.steps)},
         "gpu_launches": int(launches),
-        "stage_ms_per_shard": {k: v / len(shards) for k, v in zip(["prep_planes_partition", "pileup_call_site", "window_compaction", "window_stats"], stage_ms)},
-        "roofline": {"kernel": "pileup/call/site stage: k_pile_fast + k_hard_cells + k_fast_sites", "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": TRAFFIC_BYTES_PER_LAUNCH if abs(shard_len - 2300000) < 1 else None,
-                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the stage's kernels, one ncu capture on a 2.3 Mb shard (profiles/r1_end_launches.csv)",
+        "stage_ms_per_shard": {k: v / len(shards) for k, v in zip(["per_read_prep_partition", "pileup_call_site", "window_compaction", "window_stats"], stage_ms)},
+        "roofline": {"kernel": "the whole device pipeline of a region: per-read chain, k_pile_count, k_hard_cells, k_fast_sites, window compaction and statistics",
+                     "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                     "traffic": TRAFFIC_BYTES_PER_SHARD_C2 if is_c2_shard else None,
+                     "traffic_source": "sum over ALL kernels of one region of dram__bytes_read.sum + dram__bytes_write.sum, ncu launch list on a 2.3 Mb shard (profiles/r2_launches.csv)",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback (B200_PROFILING.md)",
-                     "algorithmic_bytes_per_launch": alg_bytes / len(shards), "launch_ms": pile_s * 1e3 / len(shards),
-                     "kernel_share_of_step": pile_s / (seq_ms / 1e3),
-                     "timed": "alone (shards one after the other); `value` runs %d shards in flight" % max(1, args.inflight)},
+                     "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes / len(shards),
+                     "launch_ms": step_s * 1e3 / len(shards),
+                     "timed": "CUDA events around whole steps, %d shards in flight (same region as `value`)" % max(1, args.inflight),
+                     "dominant_kernel": {"kernel": "pileup / call / site stage alone: k_pile_count + k_hard_cells + k_fast_sites (library events, shards one after the other)",
+                                         "launch_ms": pile_ms / len(shards), "achieved": alg_bytes / (pile_ms / 1e3) / 1e9,
+                                         "frac": alg_bytes / (pile_ms / 1e3) / 1e9 / peak_gbs, "share_of_step": pile_ms / max(seq_ms, 1e-9)}},
         "clocks": clk.summary(),
     }
+    if verified:
+        line["verified"] = verified
+    if pbtest.AN["LD_ZNS"] & an or pbtest.AN["LD_OMEGA"] & an:
+        # pairwise LD: kept SNP pairs per step (x2 when omega_max needs the sums on both sides) over the statistics stage's time
+        pairs = 0
+        for c in ctxs:
+            k = pbtest.arr(c.res.ld_num_snps, c.res.n_windows * c.res.n_pops).astype(np.int64)
+            pairs += int((k * (k - 1) // 2).sum())
+        line["ld"] = {"snp_pairs_per_step": pairs, "stats_stage_ms_per_step": stage_ms[3],
+                      "pairs_per_s": pairs * (2 if pbtest.AN["LD_OMEGA"] & an else 1) / max(stage_ms[3] / 1e3, 1e-12),
+                      "note": "integer popcount work (AND, POPC, IMAD, one DFMA per pair); pipe utilisation from ncu in profiles/"}
     if rank == 0 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(None, args.cpu_sample_kb * 1000)
-        if args.cli_sample_kb > 0:
-            line["cli_from_bam"] = cli_from_bam(args.cli_sample_kb * 1000)
+        line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_kb * 1000)
+        if args.cli_sample_kb != 0:
+            cli_len = int(min(args.contig_mb, 23.0) * 1e6) if args.cli_sample_kb < 0 else args.cli_sample_kb * 1000
+            line["cli_from_bam"] = cli_from_bam(args, cli_len)
     if rank == 0:
         print(json.dumps(line))
     for c in ctxs:
@@ -328,103 +444,141 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def sample_fixture(length, seed=77, threads=8):
-    import pbtest
-    return pbtest.Fixture(contig_len=length + 1, n_ingroup=N_INGROUP, has_outgroup=1, depth=DEPTH, read_len=READ_LEN,
-                          snp_density=0.01, seed=seed, n_threads=threads)
+def ref_runs(cfg):
+    """The reference has one subcommand (and one -o mode) per process: the runs that produce what the configuration's
+    single pass produces."""
+    w = str(cfg["win"] // 1000)
+    og = ["-p", "og"] if "OUTGROUP" in cfg["flags"] else []
+    runs = []
+    for a in cfg["an"]:
+        runs.append({"NUCDIV": ["nucdiv", "-w", w] + og, "SFS": ["sfs", "-w", w] + og, "LD_ZNS": ["ld", "-o", "0", "-w", w], "LD_OMEGA": ["ld", "-o", "1", "-w", w],
+                     "LD_WALL": ["ld", "-o", "2", "-w", w], "DIVERGE_IND": ["diverge", "-o", "0", "-w", w] + og, "DIVERGE_POP": ["diverge", "-o", "1", "-w", w] + og,
+                     "HAPLO_K": ["haplo", "-o", "0", "-w", w], "HAPLO_EHHS": ["haplo", "-o", "1", "-w", w], "HAPLO_DXY": ["haplo", "-o", "2", "-w", w]}[a])
+    return runs
 
 
-def cpu_baseline(fx_unused, sample_len):
+def scaled_sample(cfg, base_len):
+    """Sample length with about the work of `base_len` positions of configs[1] (11 samples x 30x), a whole number of windows."""
+    scale = (11 * 30.0) / ((cfg["n_ingroup"] + cfg["has_outgroup"]) * cfg["depth"]) / max(1, len(cfg["an"]))
+    return max(2, int(round(base_len * scale / cfg["win"]))) * cfg["win"]
+
+
+def cpu_baseline(args, sample_len):
     """One host core on a bounded sample of the same workload: the unmodified reference binary when it is there
     (kind "reference"), else the oracle port (kind "port")."""
     import pbtest
-    fx = sample_fixture(sample_len)
+    cfg = args.cfg
+    sample_len = scaled_sample(cfg, sample_len)
+    fx = config_fixture(cfg, sample_len, 77, 8)
     aligned = fx.aligned_bases()
-    nwin = len(pbtest.window_grid(0, fx.contig_len, WIN)[0])
+    wb, we = product_window_grid(0, fx.contig_len, cfg["win"])
+    nwin = len(wb)
     if pbtest.have_ref():
         with tempfile.TemporaryDirectory() as td:
             bam, fa = fx.write_files(Path(td) / "s")
             t0 = time.perf_counter()
-            pbtest.run_ref(["sfs", "-w", "10", "-p", "og", "-f", fa, bam, "chr1"])
+            for r in ref_runs(cfg):
+                pbtest.run_ref(r + ["-f", fa, bam, "chr1"])
             dt = time.perf_counter() - t0
         kind = "reference"
     else:
-        p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=N_INGROUP)
-        wb, we = pbtest.window_grid(0, fx.contig_len, WIN)
+        p = config_params(cfg, fx)
+        an = 0
+        for a in cfg["an"]:
+            an |= pbtest.AN[a]
         t0 = time.perf_counter()
-        pbtest.OracleRun(p, fx.batch(), fx.ref(), pbtest.AN["SFS"], wb, we).close()
+        pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we).close()
         dt = time.perf_counter() - t0
         kind = "port"
     fx.close()
     return {"value": aligned / dt / 1e9, "unit": "Gbases/s", "cores": 1, "kind": kind, "windows_per_s": nwin / dt,
-            "sample": "%d kb of the same workload (%d windows, %.3f Gbases), one process, %.1f s" % (sample_len // 1000, nwin, aligned / 1e9, dt)}
+            "sample": "%d kb of the same workload (%d windows, %.3f Gbases), %d reference process(es) one after the other, %.1f s" % (
+                sample_len // 1000, nwin, aligned / 1e9, len(ref_runs(cfg)), dt)}
 
 
-def cli_from_bam(sample_len):
+def cli_from_bam(args, sample_len):
     """Third timing tier ("E"): the `popbam` command line on BAM/BAI/FASTA files -- BAI slicing, BGZF
-    inflate and record decode on host threads, then the GPU path -- wall time of the whole process (CUDA start-up and
-    table construction included), on a bounded sample of the same workload."""
+    inflate and record decode on host threads into pinned batches, then the GPU path -- wall time of the whole process.
+    Start-up (CUDA context, error-model tables, index, FASTA) is measured separately on a one-window region."""
     import pbtest
     import popbam_b200
+    cfg = args.cfg
     exe = popbam_b200.capi.PKG / "_build" / "popbam"
     if not exe.exists():
         return {"unavailable": "popbam executable not built"}
-    fx = sample_fixture(sample_len, seed=78, threads=min(16, os.cpu_count() or 4))
+    sample_len = max(cfg["win"] * 2, (sample_len // cfg["win"]) * cfg["win"])
+    fx = config_fixture(cfg, sample_len, 78, min(32, os.cpu_count() or 4))
     aligned = fx.aligned_bases()
-    nwin = len(pbtest.window_grid(0, fx.contig_len, WIN)[0])
-    with tempfile.TemporaryDirectory() as td:
+    nwin = len(product_window_grid(0, fx.contig_len, cfg["win"])[0])
+    runs = ref_runs(cfg)
+    with tempfile.TemporaryDirectory(dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
         bam, fa = fx.write_files(Path(td) / "c")
+        bam_bytes = os.path.getsize(bam)
         fx.close()
-        best = None
-        for _ in range(2):
+
+        def once(region):
             t0 = time.perf_counter()
-            r = subprocess.run([str(exe), "sfs", "-w", "10", "-p", "og", "--shard-mb", "0.05", "-f", fa, bam, "chr1"],
-                               stdout=subprocess.PIPE, stderr=subprocess.PIPE)
-            dt = time.perf_counter() - t0
-            if r.returncode != 0:
-                return {"unavailable": "popbam failed: " + r.stderr.decode()[-200:]}
-            best = dt if best is None else min(best, dt)
-        rows = r.stdout.count(b"\n")
+            rows = 0
+            for r in runs:
+                q = subprocess.run([str(exe)] + r + ["-f", fa, bam, region], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                if q.returncode != 0:
+                    raise RuntimeError("popbam failed: " + q.stderr.decode()[-300:])
+                rows += q.stdout.count(b"\n")
+            return time.perf_counter() - t0, rows
+        try:
+            once("chr1")                                            # page cache, driver
+            best, rows = min(once("chr1") for _ in range(2))
+            startup = min(once("chr1:1-%d" % (cfg["win"] + 1))[0] for _ in range(2))
+        except RuntimeError as e:
+            return {"unavailable": str(e)}
     return {"value": aligned / best / 1e9, "unit": "Gbases/s", "windows_per_s": nwin / best, "wall_s": best, "rows": rows,
-            "host_threads": min(16, os.cpu_count() or 4),
-            "sample": "%d kb BAM of the same workload (%d windows, %.3f Gbases), whole process incl. CUDA start-up" % (
-                sample_len // 1000, nwin, aligned / 1e9)}
+            "startup_s": startup, "value_without_startup": aligned / max(best - startup, 1e-9) / 1e9,
+            "host_threads": os.cpu_count() or 4, "bam_bytes": bam_bytes,
+            "sample": "%.1f Mb BAM of the same workload (%d windows, %.3f Gbases, %.0f MB compressed), %d popbam process(es), whole process incl. CUDA start-up" % (
+                sample_len / 1e6, nwin, aligned / 1e9, bam_bytes / 1e6, len(runs))}
 
 
 def run_reference(args):
-    """Reference arm: the reference's CPU implementation with every host core, one `popbam sfs` process per core over
-    split regions chr1:a+1-a+mW+1 (BASELINE.md CPU-baseline plan); a step = all regions once."""
+    """Reference arm: the reference's CPU implementation with every host core, one `popbam` process per core over
+    split regions chr1:a+1-a+mW+1 (BASELINE.md CPU-baseline plan); a step = all regions once (and all the
+    configuration's subcommands, one after the other: the reference computes one per process)."""
     import pbtest
     rank, world, _ = dist_env()
     if rank != 0:
         return
+    cfg = args.cfg
+    WIN = cfg["win"]
     cores = os.cpu_count() or 1
     procs = min(cores, 64)
-    win_per_proc = 4
+    win_per_proc = max(1, scaled_sample(cfg, 4 * 10000) // WIN)
     length = procs * win_per_proc * WIN
-    fx = sample_fixture(length, threads=min(32, cores))
+    fx = config_fixture(cfg, length, 77, min(32, cores))
     aligned = fx.aligned_bases()
     use_ref = pbtest.have_ref()
+    runs = ref_runs(cfg)
     with tempfile.TemporaryDirectory() as td:
-        times = []
         if use_ref:
             bam, fa = fx.write_files(Path(td) / "r")
             regions = ["chr1:%d-%d" % (i * win_per_proc * WIN + 1, (i + 1) * win_per_proc * WIN + 1) for i in range(procs)]
 
             def step():
-                ps = [subprocess.Popen([str(pbtest.REF_BIN), "sfs", "-w", "10", "-p", "og", "-f", fa, bam, r], stdout=subprocess.DEVNULL,
-                                       stderr=subprocess.DEVNULL) for r in regions]
-                for q in ps:
-                    if q.wait() != 0:
-                        raise RuntimeError("reference popbam failed")
+                for r in runs:
+                    ps = [subprocess.Popen([str(pbtest.REF_BIN)] + r + ["-f", fa, bam, reg], stdout=subprocess.DEVNULL,
+                                           stderr=subprocess.DEVNULL) for reg in regions]
+                    for q in ps:
+                        if q.wait() != 0:
+                            raise RuntimeError("reference popbam failed")
             kind = "reference"
         else:
-            p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=N_INGROUP)
+            p = config_params(cfg, fx)
+            an = 0
+            for a in cfg["an"]:
+                an |= pbtest.AN[a]
             b, ref = fx.batch(), fx.ref()
-            grids = [pbtest.window_grid(i * win_per_proc * WIN, (i + 1) * win_per_proc * WIN + 1, WIN) for i in range(procs)]
+            grids = [product_window_grid(i * win_per_proc * WIN, (i + 1) * win_per_proc * WIN + 1, WIN) for i in range(procs)]
 
             def one(i):
-                pbtest.OracleRun(p, b, ref, pbtest.AN["SFS"], grids[i][0], grids[i][1]).close()
+                pbtest.OracleRun(p, b, ref, an, grids[i][0], grids[i][1]).close()
 
             def step():
                 th = [threading.Thread(target=one, args=(i,)) for i in range(procs)]     # ctypes releases the GIL
@@ -439,16 +593,17 @@ def run_reference(args):
         dt = (time.perf_counter() - t0) / args.steps
     value = aligned / dt / 1e9
     nwin = procs * win_per_proc
-    sample = "%d regions of %d kb (%d windows, %.3f Gbases) of the same workload per step, one process per core" % (
-        procs, win_per_proc * WIN // 1000, nwin, aligned / 1e9)
+    sample = "%d regions of %d kb (%d windows, %.3f Gbases) of the same workload per step, one process per core%s" % (
+        procs, win_per_proc * WIN // 1000, nwin, aligned / 1e9, ", %d subcommands one after the other" % len(runs) if len(runs) > 1 else "")
     print(json.dumps({
         "impl": "reference", "metric": "aligned Gbases/s", "value": value, "unit": "Gbases/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/u64 + f64 (error model)", "data": "synthetic (tools/pbsynth, seeded)",
-        "config": {"workload": "configs[1]: popbam sfs -p og, 10 samples + outgroup, 30x, 100 bp reads, 10 kb windows; bounded sample: " + sample,
-                   "windows_per_s": nwin / dt},
+        "config": {"workload": "%s, %d samples, %gx, 100 bp reads, %d kb windows; bounded sample: %s" % (cfg["label"], fx.n_samples, cfg["depth"], WIN // 1000, sample),
+                   "config": args.config, "windows_per_s": nwin / dt},
         "cpu_baseline": {"value": value, "unit": "Gbases/s", "cores": procs, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    fx.close()
 
 
 if __name__ == "__main__":

@@ -155,13 +155,15 @@ __global__ void __launch_bounds__(PB_LD_THREADS) k_ld_finish(const PbLdArgs a) {
             for (int i = K; i < ns; ++i) { lsum[i] = 0.0; rsum[i] = 0.0; }      // phantom index: last site not kept
             // sl / sb / sr are running totals over the split points (never reset):
             //   wl(i) pairs inside [0,i], x(i) pairs across the split after i, wr(i) pairs inside [i+1, ns)
-            double tot_r = 0.0;
-            for (int i = 0; i < ns; ++i) tot_r += rsum[i];
-            double sl = 0.0, sb = 0.0, sr = 0.0, wl = 0.0, x = 0.0, wr = tot_r;
+            // wr(i) as a suffix sum (kinv[] is free by now: scratch), not as "total minus prefix": the subtraction would
+            // cancel towards the right end of the window
+            double *suf = a.kinv + base;
+            { double acc = 0.0; for (int i = ns - 1; i >= 0; --i) { suf[i] = acc; acc += rsum[i]; } }      // suf[i] = sum of rsum over (i, ns)
+            double sl = 0.0, sb = 0.0, sr = 0.0, wl = 0.0, pr = 0.0, pl = 0.0;
             for (int i = 0; i < ns - 1; ++i) {
                 wl += lsum[i];
-                x += rsum[i] - lsum[i];
-                wr -= rsum[i];                      // pairs whose smaller index is > i
+                pr += rsum[i]; pl += lsum[i];
+                const double x = pr - pl, wr = suf[i];   // pairs across the split after i; pairs whose smaller index is > i
                 if (i == 0) continue;
                 sl += wl; sb += x; sr += wr;
                 const int left = i + 1, right = ns - left;

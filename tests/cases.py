@@ -20,6 +20,11 @@ FIXTURES = {
     "ld": dict(contig_len=20500, n_ingroup=23, has_outgroup=1, depth=12.0, snp_density=0.04, seed=14),
     # the 64-sample limit (popbam.1:508): sample masks use bit 63, the sample partition uses both register banks
     "n64": dict(contig_len=10500, n_ingroup=63, has_outgroup=1, depth=18.0, snp_density=0.03, het_frac=0.2, seed=15),
+    # C3-shaped at a size the reference's O(S^3) omega_max still finishes in seconds: 64 samples, 20 kb windows with ~1000
+    # segregating sites -- several 256-SNP row blocks and partner tiles per population in k_ld_rows
+    "ldbig": dict(contig_len=40500, n_ingroup=63, has_outgroup=1, depth=24.0, snp_density=0.12, seed=16),
+    # a realistic quality spectrum: base qualities 2..41 (40 values), 20 mapping qualities (0..60), some below min_rmsQ
+    "wideq": dict(contig_len=20500, n_ingroup=9, has_outgroup=1, depth=30.0, snp_density=0.02, het_frac=0.3, edge_mode=2, seed=17),
 }
 
 
@@ -94,6 +99,16 @@ CASES = [
     ("hap0_n64", "n64", ["haplo", "-w", "5", "-o", "0"], "HAPLO_K", {}, {}),
     ("div1_n64_og", "n64", ["diverge", "-w", "5", "-o", "1", "-p", "og"], "DIVERGE_POP", dict(flags=FLAG["OUTGROUP"], outidx=63), {}),
     ("snp1_n64", "n64", ["snp", "-o", "1"], "SNP", {}, dict(snp_output=1)),
+    # pairwise LD with ~1000 segregating sites per window (pop_ld.cpp:201-373)
+    ("ld0_ldbig", "ldbig", ["ld", "-w", "20", "-o", "0"], "LD_ZNS", {}, {}),
+    ("ld1_ldbig", "ldbig", ["ld", "-w", "20", "-o", "1"], "LD_OMEGA", {}, {}),
+    ("ld2_ldbig", "ldbig", ["ld", "-w", "20", "-o", "2"], "LD_WALL", {}, {}),
+    # wide quality spectrum
+    ("snp0_wideq", "wideq", ["snp", "-o", "0"], "SNP", {}, dict(snp_output=0)),
+    ("nucdiv_wideq", "wideq", ["nucdiv", "-w", "10"], "NUCDIV", {}, {}),
+    ("sfs_wideq_og", "wideq", ["sfs", "-w", "10", "-p", "og"], "SFS", dict(flags=FLAG["OUTGROUP"], outidx=9), {}),
+    ("ld0_wideq", "wideq", ["ld", "-w", "10", "-o", "0"], "LD_ZNS", {}, {}),
+    ("snp0_wideq_q", "wideq", ["snp", "-o", "0", "-q", "12", "-a", _b(5), "-b", _b(3)], "SNP", dict(min_rmsQ=12, min_mapQ=5, min_baseQ=3), dict(snp_output=0)),
 ]
 
 

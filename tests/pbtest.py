@@ -25,6 +25,18 @@ AN = dict(NUCDIV=0x001, SFS=0x002, LD_ZNS=0x004, LD_OMEGA=0x008, LD_WALL=0x010, 
 FLAG = dict(ILLUMINA=0x02, SUBSTITUTE=0x10, HETEROZYGOTE=0x20, OUTGROUP=0x40, EMIT_CB=0x10000)
 
 
+# result arrays that belong to each analysis bit: (integer arrays compared exactly, fp64 arrays compared to 1e-9)
+BY_AN = {
+    "NUCDIV": (["min_dxy"], ["piw", "pib"]), "HAPLO_DXY": (["min_dxy"], ["piw", "pib"]),
+    "SFS": (["sfs_num_snps"], ["td", "fwh"]),
+    "LD_ZNS": (["ld_num_snps"], ["zns"]), "LD_OMEGA": (["ld_num_snps"], ["omegamax"]),
+    "LD_WALL": (["wall_num_snps"], ["wallb", "wallq"]),
+    "DIVERGE_IND": (["ind_div"], []), "DIVERGE_POP": (["pop_div", "div_num_snps"], []),
+    "HAPLO_K": (["nhaps"], ["hdiv"]), "HAPLO_EHHS": (["nhaps"], ["hdiv", "ehhs"]),
+    "SNP": (["seg_cb"], []),
+    "TREE": (["tree_diff"], []),
+}
+
 # The C-ABI structures are shared with the product binding (the oracle mirrors their layout on purpose:
 # oracle/pb_oracle.h pbo_params / pbo_batch / pbo_result / pbo_print_opts).
 sys.path.insert(0, str(ROOT))

@@ -16,16 +16,7 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-9
 INT_KEYS = ["win_beg", "win_end", "num_sites", "segsites", "seg_off", "seg_pos", "seg_idx", "seg_type", "seg_ref"]
-BY_AN = {
-    "NUCDIV": (["min_dxy"], ["piw", "pib"]), "HAPLO_DXY": (["min_dxy"], ["piw", "pib"]),
-    "SFS": (["sfs_num_snps"], ["td", "fwh"]),
-    "LD_ZNS": (["ld_num_snps"], ["zns"]), "LD_OMEGA": (["ld_num_snps"], ["omegamax"]),
-    "LD_WALL": (["wall_num_snps"], ["wallb", "wallq"]),
-    "DIVERGE_IND": (["ind_div"], []), "DIVERGE_POP": (["pop_div", "div_num_snps"], []),
-    "HAPLO_K": (["nhaps"], ["hdiv"]), "HAPLO_EHHS": (["nhaps"], ["hdiv", "ehhs"]),
-    "SNP": (["seg_cb"], []),
-    "TREE": (["tree_diff"], []),
-}
+BY_AN = pbtest.BY_AN
 
 
 def run_gpu(fx, p, an, wb, we, batches=None):

@@ -40,6 +40,7 @@ typedef struct pbsynth_params {
     double  frac_del;         // fraction of reads with a deletion CIGAR
     double  frac_ins;         // fraction of reads with soft clip + insertion CIGAR
     int32_t edge_mode;        // 1: also emit flagged reads, N bases, =/X/H/P/N ops, low-depth holes
+                              // 2: realistic quality spectrum instead -- base qualities 2..41 (skewed to the top), 20 mapping qualities
     uint64_t seed;
     int32_t n_threads;
 } pbsynth_params;
@@ -108,6 +109,8 @@ static const char kBases[4] = {'A', 'C', 'G', 'T'};
 static const uint8_t kNt16[4] = {1, 2, 4, 8};
 // error probability scaled to 2^32 for the 5 quality values
 static uint32_t kErrThresh[5];
+static uint32_t kErrThreshQ[64];     // the same for every quality value (edge_mode 2)
+static const uint8_t kMapqWide[20] = {0, 3, 7, 10, 13, 16, 19, 22, 25, 27, 29, 30, 33, 37, 40, 44, 48, 52, 57, 60};
 
 // CIGAR templates.  ops: M0 I1 D2 N3 S4 H5 P6 =7 X8
 struct CigT { int n; uint32_t op[8]; };
@@ -146,7 +149,7 @@ static void build_panel(Synth &S, Contig &C, uint64_t seed) {
     int L = p.contig_len;
     C.ref.resize(L);
     for (int i = 0; i < L; ++i) C.ref[i] = kBases[r.next() >> 62];
-    if (p.edge_mode) {  // a few lower-case and N reference bytes
+    if (p.edge_mode == 1) {  // a few lower-case and N reference bytes
         for (int i = 0; i < L / 997 + 1; ++i) { int q = r.below(L); C.ref[q] = (char)(C.ref[q] | 0x20); }
         for (int i = 0; i < L / 1999 + 1; ++i) { int q = r.below(L); C.ref[q] = 'N'; }
     }
@@ -201,12 +204,12 @@ static void gen_contig(Synth &S, int ci) {
             double u = r.uni();
             int kind = 0;
             if (u < p.frac_del) kind = 1; else if (u < p.frac_del + p.frac_ins) kind = 2;
-            else if (p.edge_mode && u < p.frac_del + p.frac_ins + 0.02) kind = 3 + (int)r.below(3);
+            else if (p.edge_mode == 1 && u < p.frac_del + p.frac_ins + 0.02) kind = 3 + (int)r.below(3);
             CigT c; make_cigar(kind, R, c);
             int span = cigar_refspan(c);
             if (span >= L) { kind = 0; make_cigar(0, R, c); span = R; }
             ReadKey k; k.pos = (int32_t)r.below((uint32_t)(L - span + 1)); k.rg = (uint32_t)g; k.id = idc++; k.kind = (uint8_t)kind;
-            if (p.edge_mode) {  // carve a low-coverage hole for one read group
+            if (p.edge_mode == 1) {  // carve a low-coverage hole for one read group
                 int hb = L / 3, he = hb + L / 50;
                 if (g == 1 && k.pos + span > hb && k.pos < he) continue;
             }
@@ -244,9 +247,9 @@ static void gen_contig(Synth &S, int ci) {
                 for (int j = 0; j < c.n; ++j) C.cigar[C.cig_off[i] + j] = c.op[j];
                 uint64_t w = r.next();
                 uint32_t flag = (w & 1) ? 16u : 0u;             // reverse strand
-                uint32_t mapq = kMapqSet[(w >> 1) & 3];
+                uint32_t mapq = p.edge_mode == 2 ? kMapqWide[(w >> 1) % 20] : kMapqSet[(w >> 1) & 3];
                 uint32_t smeta = (uint32_t)smp;
-                if (p.edge_mode) {
+                if (p.edge_mode == 1) {
                     uint32_t e = (uint32_t)((w >> 8) & 0x3ff);
                     if (e < 6) flag |= 0x400;                   // duplicate
                     else if (e < 10) flag |= 0x200;             // QC fail
@@ -288,6 +291,14 @@ static void gen_contig(Synth &S, int ci) {
                     uint64_t u = r.next();
                     int qi = (int)((u >> 60) % 5);
                     uint8_t code = kNt16[bb[y2]];
+                    if (p.edge_mode == 2) {
+                        // 2..41, the larger of two draws: most bases in the thirties, a tail down to 2 (as a real run's)
+                        const int qa = (int)((u >> 52) % 40), qb2 = (int)((u >> 46) % 40), qv = 2 + (qa > qb2 ? qa : qb2);
+                        if ((uint32_t)u < kErrThreshQ[qv]) code = kNt16[(bb[y2] + 1 + ((u >> 40) % 3)) & 3];
+                        q[y2] = (uint8_t)qv;
+                        if (y2 & 1) s4[y2 >> 1] |= code; else s4[y2 >> 1] = (uint8_t)(code << 4);
+                        continue;
+                    }
                     if ((uint32_t)u < kErrThresh[qi]) code = kNt16[(bb[y2] + 1 + ((u >> 40) % 3)) & 3];
                     if (p.edge_mode) {
                         uint32_t e = (uint32_t)((u >> 44) & 0xfff);
@@ -476,6 +487,7 @@ void pbsynth_default_params(pbsynth_params *p) {
 
 void *pbsynth_create(const pbsynth_params *pp) {
     for (int i = 0; i < 5; ++i) kErrThresh[i] = (uint32_t)(std::pow(10.0, -kQualSet[i] / 10.0) * 4294967296.0);
+    for (int i = 0; i < 64; ++i) kErrThreshQ[i] = (uint32_t)(std::min(0.75, std::pow(10.0, -i / 10.0)) * 4294967296.0);
     Synth *S = new Synth();
     S->p = *pp;
     const pbsynth_params &p = S->p;
