@@ -244,6 +244,17 @@ int64_t pb_window_grid(int32_t beg, int32_t end, int32_t win_size, int64_t cap,
 /* Host-side table construction == errmod_init(1.0-0.83) (pop_utils.cpp:203-266).  Buffers
  * must hold 256, 64*256*256 and 256*256 doubles.                                          */
 int pb_build_errmod_tables(double *fk, double *beta, double *lhet);
+/* The same through a cache on disk: the tables only depend on the host's libm, so they are
+ * computed once per machine.  `cache_dir` NULL: $POPBAM_B200_CACHE_DIR, else $XDG_CACHE_HOME/popbam_b200, else
+ * $HOME/.cache/popbam_b200, else /tmp.  The file name carries a fingerprint of the libm calls cal_coef makes; its
+ * contents are checksummed; anything that does not verify is rebuilt (and rewritten atomically).  Set
+ * POPBAM_B200_NO_TABLE_CACHE=1 to always compute.  Returns PB_OK; *from_cache (may be NULL) says which way.        */
+int pb_errmod_tables_cached(double *fk, double *beta, double *lhet, const char *cache_dir);
+int pb_errmod_tables_cached_ex(double *fk, double *beta, double *lhet, const char *cache_dir, int *from_cache);
+
+/* Page-locked host memory for pb_read_batch arrays (what pb_push_batch_async wants); NULL when out of memory.     */
+void *pb_host_alloc(size_t bytes);
+void  pb_host_free(void *p);
 
 /* Text of one window exactly as print_X writes it (pop_nucdiv.cpp:258, pop_sfs.cpp:293,
  * pop_ld.cpp:650, pop_diverge.cpp:496, pop_haplo.cpp:365, pop_snp.cpp:224-303), without

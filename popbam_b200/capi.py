@@ -15,7 +15,7 @@ FLAG = dict(ILLUMINA=0x02, SUBSTITUTE=0x10, HETEROZYGOTE=0x20, OUTGROUP=0x40, EM
 
 EXPORTS = ["pb_create", "pb_destroy", "pb_last_error", "pb_version", "pb_set_contig", "pb_region_begin", "pb_push_batch", "pb_push_batch_async",
            "pb_push_record", "pb_region_end", "pb_region_launch", "pb_region_wait", "pb_region_relaunch", "pb_stream",
-           "pb_kernel_launches", "pb_region_path", "pb_region_reruns", "pb_stage_times", "pb_window_grid", "pb_build_errmod_tables", "pb_format_window"]
+           "pb_kernel_launches", "pb_region_path", "pb_region_reruns", "pb_stage_times", "pb_window_grid", "pb_build_errmod_tables", "pb_errmod_tables_cached", "pb_errmod_tables_cached_ex", "pb_host_alloc", "pb_host_free", "pb_format_window"]
 
 
 def _p(t):
@@ -119,6 +119,10 @@ def lib():
         L.pb_window_grid.restype = C.c_int64
         L.pb_window_grid.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64, _p(C.c_int32), _p(C.c_int32)]
         L.pb_build_errmod_tables.argtypes = [_p(C.c_double)] * 3
+        L.pb_errmod_tables_cached_ex.argtypes = [_p(C.c_double)] * 3 + [C.c_char_p, _p(C.c_int)]
+        L.pb_host_alloc.restype = C.c_void_p
+        L.pb_host_alloc.argtypes = [C.c_size_t]
+        L.pb_host_free.argtypes = [C.c_void_p]
         L.pb_format_window.restype = C.c_int64
         L.pb_format_window.argtypes = [C.c_void_p, _p(Result), C.c_int32, C.c_uint32, _p(PrintOpts), C.c_char_p, C.c_int64]
         _lib = L

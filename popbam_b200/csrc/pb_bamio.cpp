@@ -48,6 +48,7 @@ uint32_t BgzfFile::inflate_block(uint64_t coff, std::vector<uint8_t> &out) const
     // gzip member with a 'BC' extra subfield holding BSIZE (member size - 1)
     if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) fail("invalid BGZF block header");
     const uint32_t xlen = le16(h + 10);
+    if (coff + 12 + xlen > size_) fail("truncated BGZF block");
     uint32_t bsize = 0;
     for (uint32_t o = 0; o + 4 <= xlen;) {
         const uint8_t *x = h + 12 + o;
@@ -57,7 +58,9 @@ uint32_t BgzfFile::inflate_block(uint64_t coff, std::vector<uint8_t> &out) const
     }
     if (!bsize || coff + bsize > size_) fail("truncated BGZF block");
     const uint32_t hdr = 12 + xlen;
+    if ((uint64_t)hdr + 8 > bsize) fail("corrupted BGZF block (extra field longer than the block)");
     const uint32_t isize = le32(h + bsize - 4);
+    if (isize > 65536) fail("corrupted BGZF block (uncompressed size above 64 KiB, bgzf.c:47-61)");
     out.resize(isize);
     if (isize && !inflate_raw(h + hdr, bsize - hdr - 8, out.data(), isize)) fail("BGZF inflate failed");
     return bsize;
@@ -264,6 +267,18 @@ void Batch::clear() {
 }
 
 namespace {
+AllocFn g_alloc = nullptr;
+FreeFn g_free = nullptr;
+}  // namespace
+void set_batch_allocator(AllocFn alloc, FreeFn release) { g_alloc = alloc; g_free = release; }
+void *batch_alloc(size_t bytes) {
+    void *p = g_alloc ? g_alloc(bytes) : malloc(bytes);
+    if (!p) fail("out of host memory for read batches");
+    return p;
+}
+void batch_free(void *p) { if (g_free) g_free(p); else free(p); }
+
+namespace {
 // reg2bin (bam.h:697-708): the smallest bin of the UCSC scheme containing [beg, end)
 inline uint32_t region_bin(int64_t beg, int64_t end) {
     --end;
@@ -382,14 +397,22 @@ int64_t build_bai(const BgzfFile &f, const std::string &bai_path) {
 }
 
 int64_t fetch_region(const BgzfFile &f, const BamIndex &idx, const SampleTable &st, int tid, int32_t beg, int32_t end, Batch &out) {
-    const std::vector<Chunk> chunks = idx.query(tid, beg, end);
+    return fetch_piece(f, idx, st, tid, beg, end, beg, end, out);
+}
+
+int64_t fetch_piece(const BgzfFile &f, const BamIndex &idx, const SampleTable &st, int tid, int32_t beg, int32_t end, int32_t lo, int32_t hi,
+                    Batch &out) {
+    const bool first = lo <= beg;
+    if (hi > end) hi = end;
+    if (lo >= hi) { if (out.cig_off.empty()) { out.cig_off.push_back(0); out.base_off.push_back(0); } return 0; }
+    const std::vector<Chunk> chunks = idx.query(tid, first ? beg : lo, hi);
     if (out.cig_off.empty()) { out.cig_off.push_back(0); out.base_off.push_back(0); }
     BgzfReader rd(f);
     std::vector<uint8_t> rec;
     int64_t delivered = 0;
     std::string last_rg;
     int last_sample = -1;
-    const bool file_sample = st.rg2sample.empty();       // header without @RG: every read belongs to sample 0
+    const bool file_sample = st.rg2sample.empty();       // header without @RG: a read WITH an RG tag falls back to the file's sample (popbam.cpp:231-232)
     for (const Chunk &ch : chunks) {
         rd.seek(ch.beg);
         while (rd.tell() < ch.end) {
@@ -400,7 +423,8 @@ int64_t fetch_region(const BgzfFile &f, const BamIndex &idx, const SampleTable &
             rec.resize(bs);
             if (!rd.read(rec.data(), bs)) fail("truncated BAM record");
             const int32_t rtid = (int32_t)le32(&rec[0]), pos = (int32_t)le32(&rec[4]);
-            if (rtid != tid || pos >= end) return delivered;           // bam_iter_read: no need to proceed
+            if (rtid != tid || pos >= hi) return delivered;            // bam_iter_read: no need to proceed
+            if (!first && pos < lo) continue;                          // an earlier piece's record
             const uint32_t bmq = le32(&rec[8]), fnc = le32(&rec[12]);
             const uint32_t l_qname = bmq & 0xff, mapq = (bmq >> 8) & 0xff, flag = fnc >> 16, n_cig = fnc & 0xffff;
             const int32_t l_seq = (int32_t)le32(&rec[16]);
@@ -417,9 +441,8 @@ int64_t fetch_region(const BgzfFile &f, const BamIndex &idx, const SampleTable &
             if (n_cig == 0) rend = (int64_t)pos + 1;
             if (!(rend > beg && pos < end)) continue;
             // RG:Z tag -> sample (call_base, popbam.cpp:224-240)
-            int sample = 0xff;
-            if (file_sample) sample = 0;
-            else {
+            int sample = 0xff;                                          // no RG tag: call_base skips the read (popbam.cpp:226-228)
+            {
                 size_t a = o_aux;
                 const char *rg = nullptr;
                 while (a + 3 <= bs) {
@@ -446,24 +469,25 @@ int64_t fetch_region(const BgzfFile &f, const BamIndex &idx, const SampleTable &
                     if (last_sample >= 0 && last_rg == rg) sample = last_sample;
                     else {
                         auto it = st.rg2sample.find(rg);
-                        if (it == st.rg2sample.end())
+                        if (it == st.rg2sample.end() && !file_sample)
                             fail(std::string("Problem assigning read group ") + rg +
                                  " to a sample.\nPlease check BAM header for correct SM and PO tags");
-                        sample = it->second; last_rg = rg; last_sample = sample;
+                        sample = file_sample ? 0 : it->second; last_rg = rg; last_sample = sample;
                     }
                 }
             }
             out.pos.push_back(pos);
             out.meta.push_back(flag << 16 | mapq << 8 | (uint32_t)sample);
-            for (uint32_t i = 0; i < n_cig; ++i) out.cigar.push_back(le32(&rec[o_cig + 4 * i]));
+            { uint32_t *cg = out.cigar.grow(n_cig); for (uint32_t i = 0; i < n_cig; ++i) cg[i] = le32(&rec[o_cig + 4 * i]); }
             out.cig_off.push_back((uint32_t)out.cigar.size());
-            const size_t pad = ((size_t)l_seq + 3) & ~(size_t)3;      // 4-byte aligned reads: vector loads in k_encode
-            const size_t q0 = out.qual.size();
-            out.qual.resize(q0 + pad, 0);
-            memcpy(&out.qual[q0], &rec[o_qual], (size_t)l_seq);
-            const size_t s0 = out.seq4.size();
-            out.seq4.resize(s0 + pad / 2, 0);
-            memcpy(&out.seq4[s0], &rec[o_seq], (size_t)(l_seq + 1) / 2);
+            const size_t pad = ((size_t)l_seq + 3) & ~(size_t)3;      // reads start 4-byte aligned
+            if (out.qual.size() + pad > 0xfffffff0u) fail("a single fetch holds more than 4 GiB of bases: use smaller pieces");
+            uint8_t *qd = out.qual.grow(pad);
+            memcpy(qd, &rec[o_qual], (size_t)l_seq);
+            memset(qd + l_seq, 0, pad - (size_t)l_seq);
+            uint8_t *sd = out.seq4.grow(pad / 2);
+            memcpy(sd, &rec[o_seq], (size_t)(l_seq + 1) / 2);
+            memset(sd + (l_seq + 1) / 2, 0, pad / 2 - (size_t)(l_seq + 1) / 2);
             out.base_off.push_back((uint32_t)out.qual.size());
             ++delivered;
         }

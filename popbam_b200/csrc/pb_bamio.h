@@ -9,7 +9,9 @@
 //   @RG    pop_sample.cpp:15-107 (bam_smpl_add), :152-226, popbam.cpp:145-171 (assign_pops)
 // Everything here runs on host threads and only produces pb_read_batch arrays for the C ABI.
 #pragma once
+#include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -103,19 +105,57 @@ private:
 int64_t build_bai(const BgzfFile &f, const std::string &bai_path);
 
 // ---- records -> batch -------------------------------------------------------------------------------
-// Growable structure-of-arrays batch in the pb_read_batch layout (offsets 4-byte aligned per read).
+// Where batch arrays live.  The command line points these at pb_host_alloc / pb_host_free of the C ABI (page-locked
+// host memory: the device reads it with asynchronous copies); the default is malloc / free (tests without a GPU).
+typedef void *(*AllocFn)(size_t);
+typedef void (*FreeFn)(void *);
+void set_batch_allocator(AllocFn alloc, FreeFn release);
+
+// Minimal growable array on the batch allocator (grow-only capacity: a Batch is reused for many chunks).
+template <class T>
+class Vec {
+public:
+    Vec() = default;
+    Vec(const Vec &) = delete;
+    Vec &operator=(const Vec &) = delete;
+    Vec(Vec &&o) noexcept : p_(o.p_), n_(o.n_), cap_(o.cap_) { o.p_ = nullptr; o.n_ = o.cap_ = 0; }
+    Vec &operator=(Vec &&o) noexcept { if (this != &o) { release(); p_ = o.p_; n_ = o.n_; cap_ = o.cap_; o.p_ = nullptr; o.n_ = o.cap_ = 0; } return *this; }
+    ~Vec() { release(); }
+    size_t size() const { return n_; }
+    bool empty() const { return n_ == 0; }
+    T *data() { return p_; }
+    const T *data() const { return p_; }
+    T &operator[](size_t i) { return p_[i]; }
+    const T &operator[](size_t i) const { return p_[i]; }
+    T &back() { return p_[n_ - 1]; }
+    void clear() { n_ = 0; }
+    void reserve(size_t c);
+    void push_back(const T &v) { if (n_ == cap_) reserve(cap_ ? cap_ * 2 : 1024); p_[n_++] = v; }
+    T *grow(size_t k) { if (n_ + k > cap_) reserve(std::max(n_ + k, cap_ * 2)); T *r = p_ + n_; n_ += k; return r; }   // k uninitialised elements
+private:
+    void release();
+    T *p_ = nullptr;
+    size_t n_ = 0, cap_ = 0;
+};
+
+// Structure-of-arrays batch in the pb_read_batch layout (offsets 4-byte aligned per read).
 struct Batch {
-    std::vector<int32_t> pos;
-    std::vector<uint32_t> meta, cig_off, cigar, base_off;
-    std::vector<uint8_t> seq4, qual;
+    Vec<int32_t> pos;
+    Vec<uint32_t> meta, cig_off, cigar, base_off;
+    Vec<uint8_t> seq4, qual;
     void clear();
     int64_t n_reads() const { return (int64_t)pos.size(); }
 };
 
 // bam_fetch over [beg, end) of tid (bam_index.c:943-957): every record overlapping the interval, in file
-// order, appended to `out`.  Reads without an RG tag get sample PB_NO_SAMPLE; an RG that is not in the
-// header raises the reference's "Problem assigning read group" error.  Returns records delivered.
+// order, appended to `out`.  Reads without an RG tag get sample PB_NO_SAMPLE (call_base skips them, popbam.cpp:227);
+// an RG that is not in the header raises the reference's "Problem assigning read group" error.  Returns records delivered.
 int64_t fetch_region(const BgzfFile &f, const BamIndex &idx, const SampleTable &st, int tid, int32_t beg, int32_t end, Batch &out);
+// One PIECE of such a fetch, so that several threads can decode one region: of the records bam_fetch would deliver for
+// [beg, end) exactly those whose start lies in [lo, hi) -- and, for the first piece (lo == beg), also the ones that start
+// before beg.  The pieces of a partition of [beg, end), concatenated in order, equal fetch_region's batch.
+int64_t fetch_piece(const BgzfFile &f, const BamIndex &idx, const SampleTable &st, int tid, int32_t beg, int32_t end, int32_t lo, int32_t hi,
+                    Batch &out);
 
 // ---- FASTA ------------------------------------------------------------------------------------------
 // Whole contig, bytes verbatim (case preserved, faidx.c:433-468); builds <fa>.fai next to the FASTA if it
@@ -124,5 +164,16 @@ std::string fetch_contig(const std::string &fasta_path, const std::string &name)
 
 // "chr[:beg[-end]]" -> tid, 0-based beg, end (bam_parse_region, pop_utils.cpp:386-461)
 bool parse_region(const BamHeader &h, const std::string &region, int *tid, int32_t *beg, int32_t *end);
+
+void *batch_alloc(size_t bytes);
+void batch_free(void *p);
+template <class T> void Vec<T>::reserve(size_t c) {
+    if (c <= cap_) return;
+    T *np = static_cast<T *>(batch_alloc(c * sizeof(T)));
+    if (n_) memcpy(np, p_, n_ * sizeof(T));
+    if (p_) batch_free(p_);
+    p_ = np; cap_ = c;
+}
+template <class T> void Vec<T>::release() { if (p_) batch_free(p_); p_ = nullptr; n_ = cap_ = 0; }
 
 }  // namespace pbio

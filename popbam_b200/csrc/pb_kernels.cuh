@@ -50,6 +50,7 @@ struct PbCounters {               // device-side region counters (one cudaMemcpy
     int qual_max_seen;                // ... and this is the largest (adjusted) one
     int qual_high;                    // a quality byte >= 128 was seen by the kernel variant that assumes there is none
     unsigned int n_records;           // aligned-segment records of the region (all samples)
+    int total_bound;                  // upper bound of the reads of ALL samples live at one position (bam_pileup.c:260,375: maxcnt)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -147,6 +148,17 @@ __global__ void __launch_bounds__(256) k_depth_bound(const uint32_t *__restrict_
     }
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     if ((threadIdx.x & 31) == 0 && best) atomicMax(&ctr->depth_bound, (int)min(best, 0x7fffffffu));
+    // the same bound over all samples together: bam_plp_push stops taking reads that start at the current position once
+    // more than 8000 are live (bam_pileup.c:260,375); the host refuses a region where that could happen
+    uint32_t tbest = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += gridDim.x * blockDim.x) {
+        uint32_t sum = 0;
+        for (int s = 0; s < n_samples; ++s)
+            for (int d = 0; d <= m && d <= b; ++d) sum += bins[(int64_t)s * n_bins + b - d];
+        tbest = max(tbest, sum);
+    }
+    for (int o = 16; o > 0; o >>= 1) tbest = max(tbest, __shfl_xor_sync(0xffffffffu, tbest, o));
+    if ((threadIdx.x & 31) == 0 && tbest) atomicMax(&ctr->total_bound, (int)min(tbest, 0x7fffffffu));
 }
 __global__ void k_depth_decide(int max_depth, PbCounters *ctr) { ctr->nocap = ctr->depth_bound <= max_depth ? 1 : 0; }
 

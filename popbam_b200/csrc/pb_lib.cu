@@ -369,6 +369,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
         if (c->ctr_host.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
         if (c->ctr_host.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
+        if (c->ctr_host.total_bound > 8000) return fail(c, PB_ERR_UNSUPPORTED, "up to %d reads may be live at one position: above 8000 the reference's pileup drops reads (bam_pileup.c:260,375), which this library does not reproduce", c->ctr_host.total_bound);
     }
 
     // ---- the hot kernel
@@ -640,6 +641,7 @@ int fill_result(pb_ctx *c, pb_region_result *out) {
         const PbCounters fin = *reinterpret_cast<PbCounters *>(reinterpret_cast<unsigned char *>(c->h_ctr.p) + 2 * sizeof(PbCounters));
         if (fin.unsorted) return fail(c, PB_ERR_UNSORTED, "reads are not sorted by position (bam_pileup.c:384-395)");
         if (fin.too_long) return fail(c, PB_ERR_UNSUPPORTED, "a read spans 65536 or more reference bases or has more than 255 aligned segments");
+        if (fin.total_bound > 8000) return fail(c, PB_ERR_UNSUPPORTED, "up to %d reads may be live at one position: above 8000 the reference's pileup drops reads (bam_pileup.c:260,375), which this library does not reproduce", fin.total_bound);
         if (getenv("POPBAM_B200_DEBUG"))
             fprintf(stderr, "[popbam_b200] asynchronous region: %llu cells left for k_hard_cells, overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
                     fin.n_cells, fin.arena_overflow, fin.qual_over, fin.qual_max_seen, fin.spec_fail);
@@ -740,7 +742,7 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     std::future<void> table_job;
     if (own_tables) {
         fk.resize(256); beta.resize(nb); lhet.resize(65536);
-        table_job = std::async(std::launch::async, [&]() { pb_build_errmod_tables(fk.data(), beta.data(), lhet.data()); });
+        table_job = std::async(std::launch::async, [&]() { pb_errmod_tables_cached(fk.data(), beta.data(), lhet.data(), nullptr); });
     }
     struct Joiner { std::future<void> &f; ~Joiner() { if (f.valid()) f.wait(); } } joiner{table_job};
     int ndev = 0;
@@ -976,6 +978,13 @@ int pb_region_end(pb_ctx *c, pb_region_result *out) {
     PB_TRY(pb_region_launch(c));
     return pb_region_wait(c, out);
 }
+
+void *pb_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pb_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 int pb_region_path(const pb_ctx *c) { return c ? (c->ran_fast ? 1 : 0) : PB_ERR_ARG; }
 int pb_region_reruns(const pb_ctx *c) { return c ? c->reruns : PB_ERR_ARG; }
