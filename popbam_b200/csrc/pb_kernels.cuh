@@ -51,6 +51,7 @@ struct PbCounters {               // device-side region counters (one cudaMemcpy
     int qual_high;                    // a quality byte >= 128 was seen by the kernel variant that assumes there is none
     unsigned int n_records;           // aligned-segment records of the region (all samples)
     int total_bound;                  // upper bound of the reads of ALL samples live at one position (bam_pileup.c:260,375: maxcnt)
+    int max_read_bytes;               // most bytes of qual[] one read takes (its padding included)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -68,14 +69,18 @@ __global__ void k_rebase(int64_t n, int64_t r0, const uint32_t *__restrict__ cig
 // Also counts the read's aligned segments (M/=/X ops): each becomes one record of the hot kernel.
 __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__restrict__ pos, const uint32_t *__restrict__ meta,
                                                    const uint32_t *__restrict__ cigstart, const uint32_t *__restrict__ ncig,
-                                                   const uint32_t *__restrict__ cigar, int n_samples, int min_mapQ,
-                                                   uint8_t *__restrict__ rkey, uint8_t *__restrict__ rnseg,
+                                                   const uint32_t *__restrict__ cigar, const uint64_t *__restrict__ base, uint64_t n_bytes,
+                                                   int n_samples, int min_mapQ, uint8_t *__restrict__ rkey, uint8_t *__restrict__ rnseg,
                                                    int bin_origin, int n_bins, int span_end, uint32_t *__restrict__ bins,
                                                    PbCounters *__restrict__ ctr) {
     unsigned long long used = 0, aligned = 0, mqmask = 0;
-    int span = 0, flags = 0;     // flags: 1 unsorted, 2 too long
+    int span = 0, flags = 0, rbytes = 0;     // flags: 1 unsorted, 2 too long
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t m = meta[r];
+        {
+            const uint64_t b0 = base[r], b1 = r + 1 < n ? base[r + 1] : n_bytes;
+            rbytes = max(rbytes, b1 >= b0 ? (int)min(b1 - b0, (uint64_t)0x7fffffff) : 0x7fffffff);
+        }
         const int p = pos[r];
         const uint32_t c0 = cigstart[r], nc = ncig[r];
         int x = p, al = 0, nseg = 0;
@@ -113,15 +118,17 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
         aligned += __shfl_xor_sync(0xffffffffu, aligned, o);
         mqmask |= __shfl_xor_sync(0xffffffffu, mqmask, o);
         span = max(span, __shfl_xor_sync(0xffffffffu, span, o));
+        rbytes = max(rbytes, __shfl_xor_sync(0xffffffffu, rbytes, o));
         flags |= __shfl_xor_sync(0xffffffffu, flags, o);
     }
     __shared__ unsigned long long s_used[8], s_al[8], s_mq[8];
-    __shared__ int s_span[8], s_flags[8];
+    __shared__ int s_span[8], s_flags[8], s_rb[8];
     const int wid = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { s_used[wid] = used; s_al[wid] = aligned; s_mq[wid] = mqmask; s_span[wid] = span; s_flags[wid] = flags; }
+    if ((threadIdx.x & 31) == 0) { s_used[wid] = used; s_al[wid] = aligned; s_mq[wid] = mqmask; s_span[wid] = span; s_flags[wid] = flags; s_rb[wid] = rbytes; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { used += s_used[i]; aligned += s_al[i]; mqmask |= s_mq[i]; span = max(span, s_span[i]); flags |= s_flags[i]; }
+        for (int i = 1; i < (int)(blockDim.x >> 5); ++i) { used += s_used[i]; aligned += s_al[i]; mqmask |= s_mq[i]; span = max(span, s_span[i]); flags |= s_flags[i]; rbytes = max(rbytes, s_rb[i]); }
+        if (rbytes) atomicMax(&ctr->max_read_bytes, rbytes);
         if (used) atomicAdd(&ctr->reads_used, used);
         if (aligned) atomicAdd(&ctr->aligned_bases, aligned);
         if (mqmask) atomicOr(&ctr->mapq_mask, mqmask);
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
 // max_depth the cap of call_base (popbam.cpp:242-248) can never bind, reads below min_mapQ contribute
 // nothing at all, and the hot kernel runs without depth bookkeeping.
 __global__ void __launch_bounds__(256) k_depth_bound(const uint32_t *__restrict__ bins, int n_samples, int n_bins, int max_depth,
-                                                     PbCounters *__restrict__ ctr) {
+                                                     const int32_t *__restrict__ pos, int64_t n_reads, PbCounters *__restrict__ ctr) {
     const int m = (ctr->max_span + (1 << PB_BIN_SHIFT) - 1) >> PB_BIN_SHIFT;
     const int64_t total = (int64_t)n_samples * n_bins;
     uint32_t best = 0;
@@ -148,17 +155,21 @@ __global__ void __launch_bounds__(256) k_depth_bound(const uint32_t *__restrict_
     }
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
     if ((threadIdx.x & 31) == 0 && best) atomicMax(&ctr->depth_bound, (int)min(best, 0x7fffffffu));
-    // the same bound over all samples together: bam_plp_push stops taking reads that start at the current position once
-    // more than 8000 are live (bam_pileup.c:260,375); the host refuses a region where that could happen
-    uint32_t tbest = 0;
-    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_bins; b += gridDim.x * blockDim.x) {
-        uint32_t sum = 0;
-        for (int s = 0; s < n_samples; ++s)
-            for (int d = 0; d <= m && d <= b; ++d) sum += bins[(int64_t)s * n_bins + b - d];
-        tbest = max(tbest, sum);
+    // bam_plp_push stops taking reads that start at the current position once more than 8000 nodes are live
+    // (bam_pileup.c:260,375; its count includes three bookkeeping nodes); the host refuses a region where that could
+    // happen.  Live when read r is pushed: at most the reads that start in (pos[r] - max_span, pos[r]].  One binary
+    // search per 256 consecutive reads bounds that for all of them.
+    const int ms = ctr->max_span;
+    int tbest = 0;
+    for (int64_t ch = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ch * 256 < n_reads; ch += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r0 = ch * 256, r1 = min(n_reads, r0 + 256);
+        const int thr = pos[r0] - ms;                      // live reads start after thr
+        int64_t lo = 0, hi = r0;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (pos[mid] > thr) hi = mid; else lo = mid + 1; }
+        tbest = max(tbest, (int)min((int64_t)0x7ffffff0, r1 - lo) + 3);
     }
     for (int o = 16; o > 0; o >>= 1) tbest = max(tbest, __shfl_xor_sync(0xffffffffu, tbest, o));
-    if ((threadIdx.x & 31) == 0 && tbest) atomicMax(&ctr->total_bound, (int)min(tbest, 0x7fffffffu));
+    if ((threadIdx.x & 31) == 0 && tbest) atomicMax(&ctr->total_bound, tbest);
 }
 __global__ void k_depth_decide(int max_depth, PbCounters *ctr) { ctr->nocap = ctr->depth_bound <= max_depth ? 1 : 0; }
 

@@ -14,6 +14,7 @@
 #include "../../include/popbam_b200.h"
 #include "pb_kernels.cuh"
 #include "pb_fast.cuh"
+#include "pb_pile.cuh"
 #include "pb_stats.cuh"
 #include "pb_ld.cuh"
 
@@ -42,7 +43,8 @@ struct pb_ctx {
     int64_t launches = 0;
     int n_sms = 148;
     // grids of the persistent (grid-stride) kernels: SM count x resident CTAs per SM, so every launch is one full wave
-    int g_encode = 148, g_qual_mask = 148, g_hard_cells = 148, g_read_prep = 148, g_strip_index = 148;
+    int g_encode = 148, g_qual_mask = 148, g_hard_cells = 148, g_read_prep = 148, g_hard_emit = 148;
+    size_t smem_per_sm = 0;
     size_t smem_optin = 0;
     // tables / contig
     DevBuf d_fk, d_beta, d_lhet, d_ref, d_rms_thr;
@@ -61,15 +63,16 @@ struct pb_ctx {
     // derived
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
-    DevBuf d_fastp, d_cov32, d_acc, d_sidx;     // bit-sliced path: PbFastParams, cov32, per-position accumulators, strip index
-    DevBuf d_cells, d_codes16, d_need_raw;      // cells left for k_hard_cells (directory + base codes), need_raw[64][256]
+    DevBuf d_fastp, d_acc, d_hard32;            // counting path: PbFastTables, per-position accumulators, hard masks + directory bases per (sample, strip)
+    DevBuf d_cells, d_cursor, d_codes16, d_need_raw;      // cells left for k_hard_cells (directory, fill cursors, base codes), need_raw[64][256]
     DevBuf d_refcode;                           // reference code bytes of the contig (k_ref_codes)
-    DevBuf d_carry;                             // k_pile_count: counts handed from a block to the next one, and their flags
+    DevBuf d_carry;                             // k_pile_reads: counts handed from a block to the next one, and their flags
     std::vector<DevBuf *> bufs;            // every device buffer of the context
     bool classic = false;                  // POPBAM_B200_PILEUP=classic: always k_pileup_call (A/B measurements)
-    int qual_ceiling = 41;                 // assumed largest base quality (pb_fast.cuh: checked on the device, raised on violation)
+    int qual_ceiling = 41;                 // largest quality of a stray base the one-stray-base rule covers (pb_fast.cuh; POPBAM_B200_QCEIL)
     bool qual_robust = false;              // quality bytes >= 128 occur: kernel variant whose packed compares are right for any byte
     int arena_scale = 1;                   // cell arena size factor (raised on overflow)
+    int pile_spc = 0, pile_warps = 0;      // POPBAM_B200_PILE=strips,warps: launch shape of k_pile_reads (measurements)
     bool need_raw_valid = false;
     bool ran_fast = false;                 // the last pipeline run took the bit-sliced path
     int force_classic = 0;                 // the bit-sliced path gave up on this region (arena overflow twice): k_pileup_call
@@ -77,7 +80,7 @@ struct pb_ctx {
     // what a context has learnt from its earlier regions: with it a region is enqueued without a host round trip
     bool spec_valid = false;
     int spec_span = 0;                     // largest reference span of a read seen so far
-    double spec_density = 0;               // segment records per position and sample of the last region
+    int spec_read_bytes = 0;               // most bytes of qual[] one read takes, seen so far
     bool async_run = false;                // the last run_pipeline left its checks and the segregating-site copy to fill_result
     bool no_async = false;                 // POPBAM_B200_SYNC=1: always take the host round trips (A/B measurements)
     int64_t seg_cap = 0;                   // device layout of the segregating-site arrays (async: sized by the span)
@@ -238,11 +241,6 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     PB_CUDA(c, cudaMemsetAsync(c->d_ctr.p, 0, sizeof(PbCounters), st));
     PB_TRY(dev_reserve(c, c->d_rkey, (size_t)std::max<int64_t>(N, 1)));
     PB_TRY(dev_reserve(c, c->d_rnseg, (size_t)std::max<int64_t>(N, 1)));
-    PB_TRY(dev_reserve(c, c->d_srec, sizeof(int4) * (size_t)std::max<int64_t>(c->n_cig, 1)));   // one record per M/=/X op at most
-    PB_TRY(dev_reserve(c, c->d_sstart, sizeof(uint32_t) * (PB_MAX_SAMPLES + 1)));
-    const int64_t n_chunks = std::max<int64_t>(1, (N + PB_PART_CHUNK - 1) / PB_PART_CHUNK);
-    const int64_t n_counts = (int64_t)n * n_chunks + 1;
-    PB_TRY(dev_reserve(c, c->d_counts, sizeof(uint32_t) * (size_t)n_counts));
     PbCounters *ctr = dp<PbCounters>(c->d_ctr);
     const int illumina = (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0;
     // read-start bins for the depth bound: 128 bp bins from 65536 bp before the span to its end
@@ -250,14 +248,13 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     const int n_bins = (int)((span + 65536) >> PB_BIN_SHIFT) + 2;
     PB_TRY(dev_reserve(c, c->d_bins, sizeof(uint32_t) * (size_t)n * n_bins));
     PB_CUDA(c, cudaMemsetAsync(c->d_bins.p, 0, sizeof(uint32_t) * (size_t)n * n_bins, st));
-    PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
     cudaStream_t s2 = c->stream2;
     PB_CUDA(c, cudaEventRecord(c->fk[0], st));
     PB_CUDA(c, cudaStreamWaitEvent(s2, c->fk[0], 0));
-    // -- per-read chain on the second stream: prep, depth bound, stable partition by sample
+    // -- per-read chain on the second stream: flag filter, reference end, depth bound
     if (N > 0) {
         k_read_prep<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->g_read_prep), 256, 0, s2>>>(N, dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint32_t>(c->d_cigstart),
-                                                 dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), n, P.min_mapQ,
+                                                 dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), dp<uint64_t>(c->d_base), (uint64_t)c->n_bytes, n, P.min_mapQ,
                                                  dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), bin_origin, n_bins, c->span_end,
                                                  dp<uint32_t>(c->d_bins), ctr);
         c->launches += 1;
@@ -265,37 +262,42 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     PB_CUDA(c, cudaEventRecord(c->fk[1], s2));                      // rkey, mapq mask, max_span
     if (c->dbg[0]) cudaEventRecord(c->dbg[0], s2);
     if (N > 0) {
-        k_depth_bound<<<c->n_sms * 4, 256, 0, s2>>>(dp<uint32_t>(c->d_bins), n, n_bins, P.max_depth, ctr);
+        k_depth_bound<<<c->n_sms * 4, 256, 0, s2>>>(dp<uint32_t>(c->d_bins), n, n_bins, P.max_depth, dp<int32_t>(c->d_pos), N, ctr);
         c->launches += 1;
     }
     k_depth_decide<<<1, 1, 0, s2>>>(P.max_depth, ctr);
-    const unsigned part_blocks = nblk(n_chunks * 32, 128);
-    k_part_count<<<part_blocks, 128, 0, s2>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), dp<uint32_t>(c->d_meta), P.min_mapQ, ctr, n, n_chunks,
-                                             dp<uint32_t>(c->d_counts));
-    c->launches += 2;
-    PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts, s2));
-    k_sample_starts<<<1, 128, 0, s2>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart), ctr);
-    k_part_scatter<<<part_blocks, 128, 0, s2>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts),
-                                               dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
-                                               dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
-                                               dp<int4>(c->d_srec));
-    c->launches += 2;
-    // The bit-sliced path (pb_fast.cuh) is tried when nobody wants the per-cell words and an empty cell is simply "not
-    // covered" (min_depth, min_snpQ > 0); whether it can be TAKEN also needs the depth bound from the device.  Its strip
-    // index and zeroed accumulators are prepared on the per-read stream.
+    c->launches += 1;
+    // The single-kernel path (k_pileup_call) takes the reads as aligned-segment records, stably partitioned by sample; the
+    // counting path (pb_pile.cuh) takes the batch as it is, so the partition only runs when that path is not taken.
+    auto partition = [&]() -> int {
+        PB_TRY(dev_reserve(c, c->d_srec, sizeof(int4) * (size_t)std::max<int64_t>(c->n_cig, 1)));   // one record per M/=/X op at most
+        PB_TRY(dev_reserve(c, c->d_sstart, sizeof(uint32_t) * (PB_MAX_SAMPLES + 1)));
+        const int64_t n_chunks = std::max<int64_t>(1, (N + PB_PART_CHUNK - 1) / PB_PART_CHUNK);
+        const int64_t n_counts = (int64_t)n * n_chunks + 1;
+        PB_TRY(dev_reserve(c, c->d_counts, sizeof(uint32_t) * (size_t)n_counts));
+        PB_CUDA(c, cudaMemsetAsync(c->d_counts.p, 0, sizeof(uint32_t) * (size_t)n_counts, st));
+        const unsigned part_blocks = nblk(n_chunks * 32, 128);
+        k_part_count<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), dp<uint32_t>(c->d_meta), P.min_mapQ, ctr, n, n_chunks,
+                                                 dp<uint32_t>(c->d_counts));
+        c->launches += 1;
+        PB_TRY(exclusive_scan_u32(c, dp<uint32_t>(c->d_counts), n_counts, st));
+        k_sample_starts<<<1, 128, 0, st>>>(dp<uint32_t>(c->d_counts), n, n_chunks, dp<uint32_t>(c->d_sstart), ctr);
+        k_part_scatter<<<part_blocks, 128, 0, st>>>(N, dp<uint8_t>(c->d_rkey), dp<uint8_t>(c->d_rnseg), n, n_chunks, dp<uint32_t>(c->d_counts),
+                                                   dp<int32_t>(c->d_pos), dp<uint32_t>(c->d_meta), dp<uint64_t>(c->d_base),
+                                                   dp<uint32_t>(c->d_cigstart), dp<uint32_t>(c->d_ncig), dp<uint32_t>(c->d_cigar), P.min_mapQ, ctr,
+                                                   dp<int4>(c->d_srec));
+        c->launches += 2;
+        PB_CUDA(c, cudaGetLastError());
+        return PB_OK;
+    };
+    // The counting path is tried when nobody wants the per-cell words and an empty cell is simply "not covered"
+    // (min_depth, min_snpQ > 0); whether it can be TAKEN also needs the depth bound from the device.
     const int qoff = illumina ? 31 : 0;
     const bool fast_try = !want_cb && P.min_depth > 0 && P.min_snpQ > 0 && !c->classic && !c->force_classic && N > 0 &&
                           P.min_baseQ + qoff <= 128 && span * n < (int64_t)0x7fffffff;
-    const int n_strips = (int)((span + 31) >> 5), fNI = n_strips + PB_SIDX_MMAX + 2;
+    const int n_strips = (int)((span + 31) >> 5);
     PB_TRY(dev_reserve(c, c->d_site_type, sizeof(uint64_t) * (size_t)span));
-    if (fast_try) {
-        PB_TRY(dev_reserve(c, c->d_sidx, sizeof(uint32_t) * (size_t)n * fNI));
-        PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
-        k_strip_index<<<c->g_strip_index, 256, 0, s2>>>(dp<int4>(c->d_srec), dp<uint32_t>(c->d_sstart), n, c->span_beg, ctr, fNI, dp<uint32_t>(c->d_sidx));
-        PB_CUDA(c, cudaMemsetAsync(c->d_acc.p, 0, (size_t)span * 12, s2));
-        PB_CUDA(c, cudaMemsetAsync(c->d_site_type.p, 0, sizeof(uint64_t) * (size_t)span, s2));
-        c->launches += 1;
-    }
+    if (fast_try) PB_TRY(dev_reserve(c, c->d_acc, (size_t)span * 12 + 16));
     PB_CUDA(c, cudaEventRecord(c->fk[2], s2));
     if (c->dbg[1]) cudaEventRecord(c->dbg[1], s2);
     if (c->dbg[2]) cudaEventRecord(c->dbg[2], st);
@@ -307,11 +309,6 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         PB_TRY(dev_reserve(c, c->d_need, 64 * 256));
         k_need_table<<<std::max(nl, 1), 256, 0, st>>>(ctr, dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need));
         c->launches += 1;
-        if (fast_try) {
-            PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastTables)));
-            k_fast_tables<<<1, 256, 0, st>>>(ctr, dp<uint8_t>(c->d_need), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), P.min_depth, dp<PbFastTables>(c->d_fastp));
-            c->launches += 1;
-        }
         PB_CUDA(c, cudaGetLastError());
         c->need_valid = true; c->need_nl = nl; memcpy(c->need_qval, qval, 64);
         return PB_OK;
@@ -332,28 +329,29 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         return PB_OK;
     };
     if (fast_try) {
+        // per-context tables of the counting path (pb_fast.cuh): level set {qlo, ..., 63}, need_raw, the per-depth rule tables
         const int qlo = std::max(4, std::min(63, std::min(P.min_baseQ, P.min_mapQ)));
-        const int qhi = std::max(qlo, std::min(63, c->qual_ceiling));
-        unsigned char qv[64] = {0};
-        for (int q = qlo; q <= qhi; ++q) qv[q - qlo] = (unsigned char)q;
-        k_set_levels<<<1, 64, 0, st>>>(ctr, qlo, qhi);
+        k_set_levels<<<1, 64, 0, st>>>(ctr, qlo, 63);
         c->launches += 1;
-        PB_TRY(need_tables(qv, qhi - qlo + 1));
         if (!c->need_raw_valid) {
             PB_TRY(dev_reserve(c, c->d_need_raw, 64 * 256));
+            PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastTables)));
             k_need_raw<<<64, 256, 0, st>>>(dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need_raw));
-            c->launches += 1;
+            k_fast_tables<<<1, 256, 0, st>>>(ctr, dp<uint8_t>(c->d_need_raw), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), P.min_depth,
+                                            c->qual_ceiling, dp<PbFastTables>(c->d_fastp));
+            c->launches += 2;
             c->need_raw_valid = true;
         }
     } else {
         PB_TRY(classic_levels());
     }
     PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));                // join
+    if (!fast_try) PB_TRY(partition());
     PB_CUDA(c, cudaGetLastError());
     PB_TRY(host_reserve(c, c->h_ctr, 3 * sizeof(PbCounters) + 64));
     PB_CUDA(c, cudaEventRecord(c->ev[1], st));
-    // Asynchronous mode: the launch parameters the counting pileup needs from the device (largest read span, record
-    // density, "the depth cap cannot bind") are taken from the context's earlier regions; k_pile_count verifies them on the
+    // Asynchronous mode: the launch parameters the counting pileup needs from the device (largest read span, most bytes
+    // of a read, "the depth cap cannot bind") are taken from the context's earlier regions; k_pile_reads verifies them on the
     // device, and fill_result looks at the verdict (and at the sorted / too-long flags) once the region is done.  No host
     // round trip in the middle of the pipeline, so one context keeps a GPU busy.
     const uint32_t sync_bits = PB_AN_SNP | PB_AN_LD_ZNS | PB_AN_LD_OMEGA;          // their buffers / grids are sized by the number of segregating sites
@@ -361,8 +359,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     c->async_run = async;
     if (async) {
         memset(&c->ctr_host, 0, sizeof c->ctr_host);
-        c->ctr_host.max_span = c->spec_span; c->ctr_host.nocap = 1;
-        c->ctr_host.n_records = (unsigned)std::min<double>(4.0e9, c->spec_density * (double)n * (double)span);
+        c->ctr_host.max_span = c->spec_span; c->ctr_host.nocap = 1; c->ctr_host.max_read_bytes = c->spec_read_bytes;
     } else {
         PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
         PB_CUDA(c, cudaStreamSynchronize(st));
@@ -376,12 +373,41 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     PB_TRY(dev_reserve(c, c->d_site_flag, (size_t)span));
     if (want_cb) PB_TRY(dev_reserve(c, c->d_cb, sizeof(uint64_t) * (size_t)span * n));
     const bool cap = c->ctr_host.nocap == 0;
-    const bool fast = fast_try && !cap && 2 * pb_cnt_halo(c->ctr_host.max_span) <= 32 * PB_CNT_SPC_MAX &&
-                      pb_cnt_smem(PB_CNT_SPC_MAX - pb_cnt_halo(c->ctr_host.max_span) / 32, c->ctr_host.max_span) <= c->smem_optin && pb_cnt_qslot(c->ctr_host.max_span) <= 16 + 16 * 32;
+    // launch shape of k_pile_reads: strips per CTA and warps per CTA that keep the most warps resident (the counters of all
+    // samples, the tiles of all warps and the registers decide), larger blocks first among equals
+    struct { int spc = 0, warps = 0, tile_q = 0, halo = 0; size_t smem = 0; } pc;
+    if (fast_try && !cap) {
+        const int rb = std::max(c->ctr_host.max_read_bytes, 16);
+        pc.halo = std::max(32, pb_pile_halo(c->ctr_host.max_span));
+        pc.tile_q = std::max(std::min((32 * rb + 32 + 31) & ~31, 8192 + 32), (rb + 16 + 31) & ~31);
+        int best = 0;
+        for (int spc = 64; spc >= 1; spc >>= 1) {
+            if (32 * spc < pc.halo) break;
+            for (int warps = 16; warps >= 4; warps >>= 1) {
+                const size_t smem = pb_pile_reads_smem(n, spc, pc.halo, pc.tile_q, warps);
+                if (smem > c->smem_optin) continue;
+                int per_sm = 0;
+                if (c->qual_robust) {
+                    cudaFuncSetAttribute(k_pile_reads<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<true>, warps * 32, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+                } else {
+                    cudaFuncSetAttribute(k_pile_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<false>, warps * 32, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+                }
+                if (per_sm * warps > best) { best = per_sm * warps; pc.spc = spc; pc.warps = warps; pc.smem = smem; }
+            }
+        }
+        if (c->pile_spc > 0 && c->pile_warps > 0) {                      // POPBAM_B200_PILE=spc,warps (measurements)
+            const size_t smem = pb_pile_reads_smem(n, c->pile_spc, pc.halo, pc.tile_q, c->pile_warps);
+            if (32 * c->pile_spc >= pc.halo && smem <= c->smem_optin) { pc.spc = c->pile_spc; pc.warps = c->pile_warps; pc.smem = smem; }
+        }
+    }
+    const bool fast = fast_try && !cap && pc.spc > 0;
     if (async && !fast) return run_pipeline(c, attempt, false);          // (cannot happen with the context's own numbers)
     if (fast_try && !fast) {
-        // the depth cap can bind (or a read is too long for the staged planes): the single-kernel path needs the levels present
+        // the depth cap can bind (or a read is too long for the counters / tiles): the single-kernel path needs the levels present
         PB_TRY(classic_levels());
+        PB_TRY(partition());
         PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
         PB_CUDA(c, cudaStreamSynchronize(st));
         c->ctr_host = *reinterpret_cast<PbCounters *>(c->h_ctr.p);
@@ -409,58 +435,60 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
                 c->ctr_host.depth_bound, c->ctr_host.max_span, c->qual_ceiling, (int)c->qual_robust);
     c->ran_fast = fast;
     if (fast) {
-        PB_TRY(dev_reserve(c, c->d_cov32, sizeof(uint32_t) * ((size_t)n * n_strips + 1)));
+        PB_TRY(dev_reserve(c, c->d_hard32, sizeof(uint32_t) * 2 * ((size_t)n * n_strips + 1)));
         // arena of the cells left for k_hard_cells: room for one cell in eight and one base in eight (times arena_scale);
-        // k_pile_count reports an overflow, the region is then run again with a larger arena
+        // k_pile_reads reports an overflow, the region is then run again with a larger arena
         const unsigned long long cell_cap = std::max<unsigned long long>(65536, (unsigned long long)span * n / 8 * c->arena_scale);
         const unsigned long long code_cap = std::min<unsigned long long>(0xfffffff0ULL, std::max<unsigned long long>(1 << 20, (unsigned long long)c->n_bytes / 8 * c->arena_scale));
         PB_TRY(dev_reserve(c, c->d_cells, sizeof(uint4) * cell_cap));
+        PB_TRY(dev_reserve(c, c->d_cursor, sizeof(uint32_t) * cell_cap));
         PB_TRY(dev_reserve(c, c->d_codes16, sizeof(uint16_t) * code_cap));
         PB_CUDA(c, cudaEventRecord(c->ev[2], st));
-        // strips per CTA: a CTA stages one record per thread and pass, so its positions should hold about that many records
-        const int ms = c->ctr_host.max_span;
-        const double density = std::max(1e-6, (double)c->ctr_host.n_records / ((double)n * (double)std::max<int64_t>(span, 1)));   // records starting per position and sample
-        const int halo = pb_cnt_halo(ms);
-        int spc = (int)(0.87 * PB_CNT_THREADS / density / 32.0);
-        spc = std::max(halo / 32, std::min(PB_CNT_SPC_MAX - halo / 32, spc));    // block >= halo (a read ends in the next block at the latest), block + halo <= the counter arrays
-        PbCountArgs fa;
-        fa.srec = pa.srec; fa.F = dp<uint32_t>(c->d_sidx); fa.NI = fNI;
+        PbPileReadsArgs fa;
+        fa.pos = dp<int32_t>(c->d_pos); fa.meta = dp<uint32_t>(c->d_meta); fa.cigstart = dp<uint32_t>(c->d_cigstart); fa.ncig = dp<uint32_t>(c->d_ncig);
+        fa.cigar = dp<uint32_t>(c->d_cigar); fa.base = dp<uint64_t>(c->d_base); fa.n_reads = N; fa.n_bytes = (uint64_t)c->n_bytes;
         fa.qual = dp<uint8_t>(c->d_qual); fa.seq4 = dp<uint8_t>(c->d_seq4);
-        fa.refcode = dp<uint8_t>(c->d_refcode); fa.span_beg = c->span_beg; fa.span_end = c->span_end;
-        fa.n_samples = n; fa.n_strips = n_strips; fa.spc = spc;
-        fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
-        fa.qual_ceiling = std::min(63, c->qual_ceiling);
-        fa.qslot = pb_cnt_qslot(ms); fa.sslot = pb_cnt_sslot(ms);
-        fa.lq = 0;
-        while ((16 << fa.lq) < std::max(fa.qslot, fa.sslot) - 16) ++fa.lq;      // lanes per record: covers the data chunks of either slot
+        fa.refcode = dp<uint32_t>(c->d_refcode); fa.span_beg = c->span_beg; fa.span_end = c->span_end;
+        fa.n_samples = n; fa.n_strips = n_strips; fa.spc = pc.spc; fa.halo = pc.halo; fa.asw = pb_pile_asw(pc.spc, pc.halo); fa.tile_q = pc.tile_q;
+        fa.min_mapQ = P.min_mapQ; fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
+        fa.qual_ceiling = c->qual_ceiling;
         fa.ctr = ctr; fa.tab = dp<PbFastTables>(c->d_fastp);
-        fa.cov32 = dp<uint32_t>(c->d_cov32);
-        fa.cells = dp<uint4>(c->d_cells); fa.codes = dp<uint16_t>(c->d_codes16); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
-        const unsigned n_blocks = (unsigned)((n_strips + spc - 1) / spc);
-        const size_t csm = pb_cnt_smem(spc, ms);
-        PB_TRY(dev_reserve(c, c->d_carry, sizeof(uint32_t) * ((size_t)n_blocks * n * (size_t)halo + (size_t)n_blocks * n)));
-        fa.carry = dp<uint32_t>(c->d_carry); fa.carry_flag = fa.carry + (size_t)n_blocks * n * (size_t)halo; fa.halo = halo;
-        PB_CUDA(c, cudaMemsetAsync(fa.carry_flag, 0, sizeof(uint32_t) * (size_t)n_blocks * n, st));
+        fa.acc_cov = dp<uint64_t>(c->d_acc); fa.acc_cnt4 = reinterpret_cast<uint32_t *>(fa.acc_cov + span); fa.site_type = dp<uint64_t>(c->d_site_type);
+        fa.hard32 = dp<uint32_t>(c->d_hard32); fa.hbase = fa.hard32 + ((size_t)n * n_strips + 1);
+        fa.cells = dp<uint4>(c->d_cells); fa.cursor = dp<uint32_t>(c->d_cursor); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
+        const unsigned n_blocks = (unsigned)((n_strips + pc.spc - 1) / pc.spc);
+        const size_t carry_words = (size_t)n_blocks * n * (size_t)pc.halo;
+        PB_TRY(dev_reserve(c, c->d_carry, sizeof(uint32_t) * (carry_words + n_blocks)));
+        fa.carry = dp<uint32_t>(c->d_carry); fa.carry_flag = fa.carry + carry_words;
+        PB_CUDA(c, cudaMemsetAsync(fa.carry_flag, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
+        if (getenv("POPBAM_B200_DEBUG"))
+            fprintf(stderr, "[popbam_b200] k_pile_reads: %u CTAs of %d warps, %d strips per CTA, halo %d, quality tile %d bytes, %zu bytes of shared memory\n",
+                    n_blocks, pc.warps, pc.spc, pc.halo, pc.tile_q, pc.smem);
         if (c->qual_robust) {
-            PB_CUDA(c, cudaFuncSetAttribute(k_pile_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-            k_pile_count<true><<<(unsigned)n * n_blocks, PB_CNT_THREADS, csm, st>>>(fa);
+            PB_CUDA(c, cudaFuncSetAttribute(k_pile_reads<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem));
+            k_pile_reads<true><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
         } else {
-            PB_CUDA(c, cudaFuncSetAttribute(k_pile_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
-            k_pile_count<false><<<(unsigned)n * n_blocks, PB_CNT_THREADS, csm, st>>>(fa);
+            PB_CUDA(c, cudaFuncSetAttribute(k_pile_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem));
+            k_pile_reads<false><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
         }
+        PbEmitArgs ea;
+        ea.pos = fa.pos; ea.meta = fa.meta; ea.cigstart = fa.cigstart; ea.ncig = fa.ncig; ea.cigar = fa.cigar; ea.base = fa.base; ea.n_reads = N;
+        ea.qual = fa.qual; ea.seq4 = fa.seq4; ea.span_beg = c->span_beg; ea.span_end = c->span_end; ea.n_samples = n; ea.n_strips = n_strips;
+        ea.min_mapQ = P.min_mapQ; ea.min_baseQ = P.min_baseQ; ea.illumina = illumina; ea.ctr = ctr;
+        ea.hard32 = fa.hard32; ea.hbase = fa.hbase; ea.cells = fa.cells; ea.cursor = fa.cursor; ea.codes = dp<uint16_t>(c->d_codes16);
+        k_hard_emit<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->g_hard_emit), 256, 0, st>>>(ea);
         PbHardArgs ha;
-        ha.cells = fa.cells; ha.codes = fa.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
+        ha.cells = fa.cells; ha.codes = ea.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
         ha.span_beg = pa.span_beg; ha.span_end = pa.span_end; ha.win_beg = pa.win_beg; ha.win_end = pa.win_end; ha.n_windows = NW;
         ha.n_samples = n; ha.n_strips = n_strips;
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
         ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need_raw = dp<uint8_t>(c->d_need_raw);
-        ha.cov32 = fa.cov32;
-        ha.acc_cov = dp<uint64_t>(c->d_acc); ha.acc_cnt4 = reinterpret_cast<uint32_t *>(ha.acc_cov + span);
+        ha.acc_cov = fa.acc_cov; ha.acc_cnt4 = fa.acc_cnt4;
         ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
         PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_hard_smem()));
         k_hard_cells<<<c->g_hard_cells, PB_HARD_THREADS, pb_hard_smem(), st>>>(ha);
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
-        c->launches += 3;
+        c->launches += 4;
     } else {
         PB_TRY(need_tables(c->ctr_host.qval, nl));
         pa.need = dp<uint8_t>(c->d_need);
@@ -516,8 +544,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         if (getenv("POPBAM_B200_DEBUG"))
             fprintf(stderr, "[popbam_b200] bit-sliced path: run again (arena overflow %d: %llu cells, %llu codes; quality %d above ceiling %d: %d; launch assumptions %d)\n",
                     h_final->arena_overflow, h_final->n_cells, h_final->n_codes, h_final->qual_max_seen, c->qual_ceiling, h_final->qual_over, h_final->spec_fail);
-        if (h_final->qual_over) c->qual_ceiling = std::min(63, std::max(c->qual_ceiling + 1, h_final->qual_max_seen));
-        if (h_final->qual_high) { c->qual_robust = true; c->qual_ceiling = 63; }
+        if (h_final->qual_high) c->qual_robust = true;
         if (h_final->arena_overflow) c->arena_scale *= 4;
         c->reruns += 1;
         if (attempt >= 2 || c->arena_scale > 64) c->force_classic = 1;
@@ -528,7 +555,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     if (!async && fast) {           // what this region teaches the context
         c->spec_valid = true;
         c->spec_span = std::max(c->spec_span, c->ctr_host.max_span);
-        c->spec_density = (double)c->ctr_host.n_records / ((double)n * (double)std::max<int64_t>(span, 1));
+        c->spec_read_bytes = std::max(c->spec_read_bytes, c->ctr_host.max_read_bytes);
     }
     // number of segregating sites: known now, or (asynchronous mode) bounded by the span -- the device arrays are laid out
     // for the bound, the kernels read the real offsets from device memory, and fill_result copies what there is
@@ -646,15 +673,14 @@ int fill_result(pb_ctx *c, pb_region_result *out) {
             fprintf(stderr, "[popbam_b200] asynchronous region: %llu cells left for k_hard_cells, overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
                     fin.n_cells, fin.arena_overflow, fin.qual_over, fin.qual_max_seen, fin.spec_fail);
         if (fin.arena_overflow || fin.qual_over || fin.spec_fail) {
-            if (fin.qual_over) c->qual_ceiling = std::min(63, std::max(c->qual_ceiling + 1, fin.qual_max_seen));
-            if (fin.qual_high) { c->qual_robust = true; c->qual_ceiling = 63; }
+            if (fin.qual_high) c->qual_robust = true;
             if (fin.arena_overflow) c->arena_scale *= 4;
             c->reruns += 1;
             PB_TRY(run_pipeline(c, 0, false));          // with the host round trips: learns the span / density / cap again
             PB_CUDA(c, cudaStreamSynchronize(c->stream));
         } else {
             c->spec_span = std::max(c->spec_span, fin.max_span);
-            c->spec_density = (double)fin.n_records / ((double)n * (double)std::max<int64_t>((int64_t)c->span_end - c->span_beg, 1));
+            c->spec_read_bytes = std::max(c->spec_read_bytes, fin.max_read_bytes);
             c->ctr_host = fin;
             // the segregating-site arrays: device layout for seg_cap entries, host layout for the S there are
             const int64_t S = *(reinterpret_cast<int64_t *>(c->h_ctr.p) + (sizeof(PbCounters) + 7) / 8);
@@ -759,9 +785,11 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     pb_ctx *c = new pb_ctx();
     c->prm = *p;
     c->n_sms = prop.multiProcessorCount;
-    c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->smem_optin = prop.sharedMemPerBlockOptin; c->smem_per_sm = prop.sharedMemPerMultiprocessor;
     { const char *e = getenv("POPBAM_B200_PILEUP"); c->classic = e && strcmp(e, "classic") == 0; }
     { const char *e = getenv("POPBAM_B200_SYNC"); c->no_async = e && *e == '1'; }
+    { const char *e = getenv("POPBAM_B200_PILE"); if (e) sscanf(e, "%d,%d", &c->pile_spc, &c->pile_warps); }
+    { const char *e = getenv("POPBAM_B200_QCEIL"); if (e && atoi(e) >= 4) c->qual_ceiling = std::min(63, atoi(e)); }
     {
         auto wave = [&](auto kern, int threads) {
             int per_sm = 0;
@@ -770,7 +798,7 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
         };
         c->g_encode = wave(k_encode, 256);
         c->g_qual_mask = wave(k_qual_mask, 256);
-        c->g_read_prep = wave(k_read_prep, 256); c->g_strip_index = wave(k_strip_index, 256);
+        c->g_read_prep = wave(k_read_prep, 256); c->g_hard_emit = wave(k_hard_emit, 256);
         {
             int per_sm = 0;
             cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_hard_smem());
@@ -830,8 +858,8 @@ int pb_set_contig(pb_ctx *c, int32_t tid, const char *ref_bases, int64_t len) {
     PB_TRY(dev_reserve(c, c->d_ref, (size_t)std::max<int64_t>(len, 1)));
     PB_CUDA(c, cudaMemcpyAsync(c->d_ref.p, ref_bases, (size_t)len, cudaMemcpyHostToDevice, c->stream));
     PB_CUDA(c, cudaStreamSynchronize(c->stream));
-    PB_TRY(dev_reserve(c, c->d_refcode, (size_t)len + PB_REFCODE_PAD));
-    k_ref_codes<<<c->n_sms * 4, 256, 0, c->stream>>>(dp<char>(c->d_ref), len, dp<uint8_t>(c->d_refcode));
+    PB_TRY(dev_reserve(c, c->d_refcode, ((size_t)len + PB_REFCODE_PAD) / 8 * 4 + 64));
+    k_ref_codes<<<c->n_sms * 4, 256, 0, c->stream>>>(dp<char>(c->d_ref), len, dp<uint32_t>(c->d_refcode));
     c->launches += 1;
     PB_CUDA(c, cudaGetLastError());
     PB_CUDA(c, cudaStreamSynchronize(c->stream));

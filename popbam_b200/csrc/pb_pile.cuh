@@ -1,0 +1,620 @@
+// pb_pile.cuh -- the counting pileup: reads in FILE order, all samples of a block of positions in one CTA.
+//
+// This is the north star's "CIGAR-expanding scatter of reads into a per-window [position x sample] integer count
+// tensor, using shared-memory staging and atomics".  What the counts are for and why ~99 % of the cells need nothing
+// else is explained at the top of pb_fast.cuh; this file holds the two kernels that touch the reads:
+//
+//   k_pile_reads   one CTA = `spc` strips of 32 positions x ALL samples.  Its reads are the ones that START in the block
+//                  (the reads are sorted, bam_pileup.c:384-395, so they are one contiguous run of the batch, found by two
+//                  binary searches in pos[]): no partition by sample, no segment records, no strip index -- the per-read
+//                  arrays of the C ABI are the kernel's input as they are.  A WARP takes 32 consecutive reads per step:
+//                  their quality bytes and packed bases lie back to back in qual[] / seq4[], so the tile is brought into
+//                  shared memory by two 1-D bulk copies (cp.async.bulk + mbarrier, issued by one lane) and every lane
+//                  then walks its own read: CIGAR -> aligned segments (resolve_cigar2, bam_pileup.c:90-221), four bases
+//                  per step with packed-byte arithmetic (below), counts added to the sample's byte counters with one
+//                  shared-memory reduction per counter and four positions.  The counters reach `halo` positions behind
+//                  the block; what lands there is handed to the next block's CTA through global memory.
+//                  Then one thread per position classifies the cells of all samples (easy / hard), writes the position's
+//                  coverage mask, and the hard cells get a directory entry and room for their base codes.
+//   k_hard_emit    one thread per read: the base codes (popbam.cpp:279-284) of the hard cells its segments cover, appended
+//                  to the cells' code lists (the order inside a cell does not matter: errmod_cal sorts, pop_utils.cpp:299).
+//
+// Packed-byte arithmetic of one position word (four positions, one byte each):
+//   PRMT aligns the quality bytes to the position grid; "byte + (128 - T)" puts a threshold test into bit 7; a PRMT with
+//   the four base nibbles as its selector is a 16-entry table lookup for four bases at once (valid A/C/G/T, base code);
+//   an XOR against the reference's code bytes finds stray bases.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "pb_kernels.cuh"
+#include "pb_fast.cuh"             // PB_H_QUALITY, PbFastTables
+
+struct PbPileReadsArgs {
+    // the read batch as pushed (file order)
+    const int32_t *pos;
+    const uint32_t *meta, *cigstart, *ncig, *cigar;
+    const uint64_t *base;                    // byte offset of a read's first base in qual[] (seq4[]: half of it)
+    int64_t n_reads;
+    uint64_t n_bytes;
+    const uint8_t *qual, *seq4;              // 16-byte aligned, at least 64 readable bytes behind the last base
+    const uint32_t *refcode;                 // reference code nibbles of the contig (k_ref_codes), padded behind its end
+    int span_beg, span_end;
+    int n_samples, n_strips;
+    int spc;                                 // strips of 32 positions per CTA
+    int halo;                                // positions behind the block the counters reach: max_span rounded up to 32, <= 32 * spc
+    int asw;                                 // words between the four counter arrays of a sample: >= (32 * spc + halo) / 4 + 1
+    int tile_q;                              // bytes of a warp's quality tile (multiple of 32); its packed-base tile: tile_q / 2 + 16
+    int min_mapQ, min_rmsQ, min_baseQ, illumina;
+    int qual_ceiling;                        // largest (adjusted) quality of a stray base the one-stray-base rule of the tables covers
+    PbCounters *ctr;
+    const PbFastTables *tab;
+    uint64_t *acc_cov;                       // [span] out: samples whose cell is easy and covered
+    uint32_t *acc_cnt4;                      // [span] out: zero (k_hard_cells adds the derived-base counts of its cells)
+    uint64_t *site_type;                     // [span] out: zero (k_hard_cells sets derived-allele bits)
+    uint32_t *hard32;                        // [n_samples][n_strips] out: cells left for k_hard_cells
+    uint32_t *hbase;                         // [n_samples][n_strips] out: directory index of a strip's first hard cell
+    uint4 *cells;                            // directory {pos, sample | k << 8, sum mapq^2 (k_hard_emit), first code}
+    uint32_t *cursor;                        // [cell_cap] codes written so far (k_hard_emit)
+    unsigned long long cell_cap, code_cap;
+    uint32_t *carry;                         // [blocks][n_samples][4][halo / 4] counts a CTA's reads add behind its block
+    uint32_t *carry_flag;                    // [blocks] set once they are published (zeroed per region)
+};
+
+static inline int pb_pile_halo(int max_span) { return (max_span + 31) & ~31; }
+static inline int pb_pile_asw(int spc, int halo) { return (32 * spc + halo) / 4 + 1; }
+// dynamic shared memory: counters, reference nibbles (two copies), tables, barriers, read lists, per-warp tiles (16 bytes of
+// padding around each)
+static inline size_t pb_pile_reads_smem(int n_samples, int spc, int halo, int tile_q, int warps) {
+    const size_t cnt = (size_t)n_samples * (4 * (size_t)pb_pile_asw(spc, halo) + 1) * 4;
+    const size_t rc = 2 * ((size_t)(32 * spc + halo) / 8 + 2) * 4 + 32;
+    const size_t lists = (size_t)warps * 32 * 4 * 2 + 16;
+    const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32);
+    const size_t scan = (size_t)n_samples * spc * 8;               // hard masks + code counts, in the tiles' place
+    return ((cnt + 15) & ~(size_t)15) + rc + 512 + 16 * (size_t)warps + lists + (tiles > scan ? tiles : scan) + 64;
+}
+
+__device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// prmt.b32 in its default mode: selector nibble n picks byte n & 7 of {a, b}; with bit 3 of the nibble set the SIGN of that
+// byte is replicated over the result byte (__byte_perm masks bit 3 away, hence the inline PTX)
+__device__ __forceinline__ uint32_t pb_prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// swap the two nibbles of every byte: seq4 keeps the first base of a byte in the HIGH nibble (bam.h:245-258); after the
+// swap base j of a little-endian word sits in bits 4j .. 4j+3, and any nibble shift keeps the order
+__device__ __forceinline__ uint32_t pb_nibble_order(uint32_t w) { return ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu); }
+
+// ---- mbarrier + 1-D bulk copy (TMA without a tensor map): global -> shared, completion counted in bytes on the barrier
+__device__ __forceinline__ void pb_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pb_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pb_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void pb_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "PB_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra PB_DONE_%=;\n"
+        "bra PB_WAIT_%=;\n"
+        "PB_DONE_%=:\n"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+
+// call_base's filter and code for one base (popbam.cpp:268-284): code = q << 5 | strand << 4 | nt4, q = clamp(min(baseQ', mapQ), 4, 63)
+__device__ __forceinline__ bool pb_base_code(const uint8_t *__restrict__ qual, const uint8_t *__restrict__ seq4, uint64_t off, int illumina, int min_baseQ,
+                                             int mq, uint32_t strand, uint32_t *code) {
+    int bq = (int)__ldg(qual + off);
+    const uint32_t sbyte = __ldg(seq4 + (off >> 1));
+    const uint32_t nib = (off & 1) ? (sbyte & 15u) : (sbyte >> 4);
+    const uint32_t nt = (uint32_t)((PB_NT16_NT4_LUT >> (nib * 4)) & 0xf);
+    if (illumina) bq = bq > 31 ? bq - 31 : 0;
+    if (nt > 3u || bq < min_baseQ) return false;
+    const int qq = max(4, min(63, min(bq, mq)));
+    *code = (uint32_t)qq << 5 | strand << 4 | nt;
+    return true;
+}
+
+// One position word (four positions, one byte each) of one read: quality bytes qv aligned to the positions, the four base
+// nibbles in the low 16 bits of sx, xn = those nibbles XOR the reference's (non-zero: a stray base), vm = 0x01 in the
+// bytes that belong to the segment.  Adds the passing bases (P) and the high-quality ones (H) to the counters at cp / cp +
+// ASW and returns the stray passing bases; the caller handles those (rare).
+template <bool ROBUST, bool MASKED>
+__device__ __forceinline__ uint32_t pb_count_word(uint32_t *cp, int ASW, uint32_t qm, uint32_t sx, uint32_t xn, uint32_t vm, uint32_t addP, uint32_t addH,
+                                                  uint32_t hmask, uint32_t *Hout) {
+    // 16-entry lookup for four bases: nibble 1 (A), 2 (C), 4 (G), 8 (T) -> bit 0 set (T: selector bit 3 replicates the sign
+    // of entry 0, 0x80, over the byte), everything else -> bit 0 clear
+    const uint32_t sq = pb_prmt(0x00050380u, 0x00000009u, sx);
+    uint32_t fa, fh;
+    if (ROBUST) {
+        const uint32_t lo7 = qm & 0x7f7f7f7fu;
+        fa = (lo7 + addP) | qm; fh = ((lo7 + addH) | qm) & hmask;
+    } else {
+        fa = qm + addP; fh = qm + addH;
+    }
+    const uint32_t P = (fa >> 7) & sq & vm;
+    const uint32_t H = (fh >> 7) & P;
+    // nibble != 0 -> bit 0 (entries 1..7: 0x81; entry 0: 0x80, and its sign makes nibble 8 0xff)
+    const uint32_t mm = pb_prmt(0x81818180u, 0x81818181u, xn) & P;
+    if (!MASKED || P) {
+        atomicAdd(cp, P);
+        atomicAdd(cp + ASW, H);
+    }
+    *Hout = H;
+    return mm;
+}
+// The stray bases of a word (rare): count them, note a high-quality one (flag bit 0), and take a cell whose stray base has
+// a quality above the ceiling of the one-stray-base rule off the easy path (flag bit 1).
+template <bool ROBUST>
+__device__ __forceinline__ void pb_count_stray(uint32_t *cp, int ASW, uint32_t mm, uint32_t H, uint32_t qm, uint32_t addC) {
+    atomicAdd(cp + 2 * ASW, mm);
+    const uint32_t oc = ((ROBUST ? (((qm & 0x7f7f7f7fu) + addC) | qm) : (qm + addC)) >> 7) & mm;
+    const uint32_t fl = (mm & H) | oc << 1;
+    if (fl) atomicOr(cp + 3 * ASW, fl);
+}
+
+#define PB_PILE_ROUND 4            // reads per thread and round of the read lists
+
+// ROBUST: quality bytes >= 128 were seen in this context (a BAM without qualities stores 0xff), so the packed threshold
+// tests use the form that is right for any byte value.
+template <bool ROBUST>
+__global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long s_range[2];
+    __shared__ unsigned long long s_resv[2];
+    __shared__ uint32_t s_wsum[2][16];
+    __shared__ int s_cur[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = (int)blockDim.x, NWARP = NT >> 5;
+    const int max_span = a.ctr->max_span;
+    if (!a.ctr->nocap || ((max_span + 31) & ~31) > a.halo) {          // launched on an assumption that does not hold: say so, do nothing
+        if (tid == 0) a.ctr->spec_fail = 1;
+        return;
+    }
+    const int n = a.n_samples;
+    const int PB = a.spc * 32, PH = PB + a.halo;
+    const int ASW = a.asw, RW = 4 * ASW + 1;                                // words: array stride, sample stride (odd: the samples' rows start in different banks)
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw);               // [n][K, H, M, F][ASW]: passing bases, those at or above the khi level, stray bases, flags (bit 0: a stray base at or above the khi level, bit 1: off the easy path)
+    const size_t cnt_bytes = (((size_t)n * RW * 4) + 15) & ~(size_t)15;
+    const int NRW = PH / 8 + 2;                                            // words of reference nibbles (eight positions each)
+    uint32_t *refA = reinterpret_cast<uint32_t *>(smem_raw + cnt_bytes);  // [NRW] position 8 i of the block in bits 0-3 of word i
+    uint32_t *refB = refA + NRW;                                          // [NRW] the same stream 16 bits (one position word) further on
+    uint8_t *tabS = smem_raw + ((cnt_bytes + (size_t)2 * NRW * 4 + 15) & ~(size_t)15);     // flags[256], hneed[256]
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tabS + 512);     // one per warp
+    const int LCAP = NT * PB_PILE_ROUND;
+    uint16_t *list = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(mbar) + 16 * (size_t)NWARP);     // [LCAP] reads of the round: one aligned segment from the front, several from the back
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(list) + (((size_t)LCAP * 2 + 15) & ~(size_t)15);
+    const int tile_s = a.tile_q / 2 + 16;
+    const size_t tile_bytes = (size_t)a.tile_q + 32 + (size_t)tile_s + 32;
+    const int t0s = (int)blockIdx.x * a.spc;                                    // first strip of the block
+    const int p0 = a.span_beg + t0s * 32, p1 = min(p0 + PB, a.span_end);
+    const int pend = p0 + PH;                                             // end of the counters
+    if (tid == 0) {
+        // the block's reads: pos in [p0, p0 + PB); the first block also takes the reads that start before the span
+        const int64_t N = a.n_reads;
+        int64_t lo = 0, hi = N;
+        if (blockIdx.x > 0) while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(a.pos + mid) >= p0) hi = mid; else lo = mid + 1; }
+        const int64_t rlo = blockIdx.x > 0 ? lo : 0;
+        lo = rlo; hi = N;
+        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(a.pos + mid) >= p0 + PB) hi = mid; else lo = mid + 1; }
+        s_range[0] = rlo; s_range[1] = lo;
+    }
+    for (int i = tid; i < n * RW; i += NT) cnt[i] = 0;
+    for (int i = tid; i < NRW; i += NT) {
+        // k_ref_codes packs by absolute position; the block starts at p0 (padded behind the contig)
+        const uint32_t *g = a.refcode + ((int64_t)p0 >> 3) + i;
+        const uint32_t w0 = __ldg(g), w1 = __ldg(g + 1), w2 = __ldg(g + 2);
+        const int sh = 4 * (p0 & 7);
+        const uint32_t c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh);
+        refA[i] = c0; refB[i] = c0 >> 16 | c1 << 16;
+    }
+    for (int i = tid; i < 128; i += NT) reinterpret_cast<uint32_t *>(tabS)[i] = __ldg(reinterpret_cast<const uint32_t *>(a.tab) + i);
+    if (lane == 0) pb_mbar_init(pb_smem_addr(mbar + 2 * wid), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    // raw quality byte thresholds (host: all <= 128): passing, khi level, above the ceiling of the one-stray-base rule
+    const int qoff = a.illumina ? 31 : 0;
+    const int tp = a.min_baseQ <= 0 ? 0 : a.min_baseQ + qoff;
+    const int th = min(128, PB_H_QUALITY + qoff);
+    const int tc = min(128, min(63, a.qual_ceiling) + 1 + qoff);
+    uint32_t addP = (uint32_t)(128 - tp) * 0x01010101u, addC = (uint32_t)(128 - tc) * 0x01010101u, addH1 = (uint32_t)(128 - th) * 0x01010101u;
+    asm volatile("" : "+r"(addP), "+r"(addC), "+r"(addH1));                // computed once (the compiler would recompute them inside the scatter loop)
+    const int64_t rlo = s_range[0], rhi = s_range[1];
+    unsigned char *tq = tiles + (size_t)wid * tile_bytes + 16;             // quality tile (16 bytes of padding in front: a segment's first word may start 3 bytes early)
+    unsigned char *ts = tq + a.tile_q + 16 + 16;                           // packed-base tile
+    const uint32_t bar = pb_smem_addr(mbar + 2 * wid);
+    uint32_t phase = 0;
+    for (int64_t rbase = rlo; rbase < rhi; rbase += LCAP) {
+        // ---- the reads of this round, by kind: dropped (flag filter of bam_plp_push, bam_pileup.c:371-374; no sample; below
+        // min_mapQ -- the raw-depth cap cannot bind, so such a read reaches no cell, popbam.cpp:242-266), one aligned segment
+        // (the ordinary read: one thread each, below), several (a warp each).  Lists in read order.
+        const int64_t rend = min(rhi, rbase + LCAP);
+        uint32_t kinds = 0;                                                  // 2 bits per step: 1 one segment, 2 several
+        uint32_t ns = 0, nc = 0;                                             // this warp's reads of either kind
+        for (int it = 0; it < PB_PILE_ROUND; ++it) {
+            const int64_t r = rbase + (int64_t)(wid * PB_PILE_ROUND + it) * 32 + lane;
+            uint32_t kind = 0;
+            if (r < rend) {
+                const uint32_t meta = __ldg(a.meta + r);
+                if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) {
+                    const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
+                    const uint64_t b0 = __ldg(a.base + r), b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes;
+                    uint64_t ql = 0;
+                    uint32_t nseg = 0;
+                    for (uint32_t ci = 0; ci < ncg; ++ci) {
+                        const uint32_t cg = __ldg(a.cigar + c0 + ci);
+                        const uint32_t op = cg & 15u, len = cg >> 4;
+                        const uint32_t aln = (0x181u >> op) & 1u;            // M = X consume reference and query
+                        if (aln | ((0x12u >> op) & 1u)) ql += len;           // ... I S query only
+                        nseg += aln & (len > 0u);
+                    }
+                    if (b1 < b0 || ql > b1 - b0) a.ctr->spec_fail = 1;       // CIGAR longer than the read's bases, or offsets out of order
+                    else kind = nseg == 0 ? 0u : nseg == 1 ? 1u : 2u;
+                }
+            }
+            kinds |= kind << (2 * it);
+            ns += (uint32_t)__popc(__ballot_sync(0xffffffffu, kind == 1u));
+            nc += (uint32_t)__popc(__ballot_sync(0xffffffffu, kind == 2u));
+        }
+        if (lane == 0) { s_wsum[0][wid] = ns; s_wsum[1][wid] = nc; }
+        if (tid == 0) { s_cur[0] = 0; s_cur[1] = 0; }
+        __syncthreads();
+        uint32_t off_s = 0, off_c = 0, tot_s = 0, tot_c = 0;
+        for (int w = 0; w < NWARP; ++w) {
+            if (w < wid) { off_s += s_wsum[0][w]; off_c += s_wsum[1][w]; }
+            tot_s += s_wsum[0][w]; tot_c += s_wsum[1][w];
+        }
+        for (int it = 0; it < PB_PILE_ROUND; ++it) {
+            const uint32_t kind = (kinds >> (2 * it)) & 3u;
+            const uint32_t ms = __ballot_sync(0xffffffffu, kind == 1u), mc = __ballot_sync(0xffffffffu, kind == 2u);
+            const uint32_t below = (1u << lane) - 1u;
+            const uint16_t idx = (uint16_t)((wid * PB_PILE_ROUND + it) * 32 + lane);
+            if (kind == 1u) list[off_s + (uint32_t)__popc(ms & below)] = idx;
+            if (kind == 2u) list[LCAP - 1 - (int)(off_c + (uint32_t)__popc(mc & below))] = idx;
+            off_s += (uint32_t)__popc(ms); off_c += (uint32_t)__popc(mc);
+        }
+        __syncthreads();
+        // ---- reads with one aligned segment: a warp takes 32 of them at a time (a shared cursor: the warps stay busy whatever
+        // the reads look like), brings the bytes from the first to the last of them into its tile, and every lane walks its own.
+        for (;;) {
+            int i0 = 0;
+            if (lane == 0) i0 = atomicAdd(&s_cur[0], 32);
+            i0 = __shfl_sync(0xffffffffu, i0, 0);
+            if (i0 >= (int)tot_s) break;
+            const int cnt_l = min(32, (int)tot_s - i0);
+            int64_t r = 0;
+            uint64_t b0 = 0, b1 = 0;
+            if (lane < cnt_l) {
+                r = rbase + list[i0 + lane];
+                b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes;
+            }
+            bool give_up = false;
+            for (int start = 0; start < cnt_l;) {
+                const uint64_t tq0 = __shfl_sync(0xffffffffu, b0, start) & ~(uint64_t)15;            // first byte of the quality tile
+                const bool fits = lane >= start && lane < cnt_l && b0 >= tq0 && b1 <= a.n_bytes && b1 - tq0 <= (uint64_t)a.tile_q;
+                const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> start;
+                const int nt = fm == 0xffffffffu ? 32 : __ffs((int)~fm) - 1;                         // reads of this tile (the offsets ascend)
+                if (nt == 0) {                                                                       // one read larger than a tile
+                    if (lane == 0) a.ctr->spec_fail = 1;
+                    give_up = true;
+                    break;
+                }
+                const uint64_t tend = __shfl_sync(0xffffffffu, b1, start + nt - 1);
+                const uint64_t ts0 = (tq0 >> 1) & ~(uint64_t)15;                                      // first byte of the packed-base tile
+                if (lane == 0) {
+                    const uint32_t nbq = (uint32_t)((tend - tq0 + 15) & ~(uint64_t)15), nbs = (uint32_t)((((tend + 1) >> 1) - ts0 + 15) & ~(uint64_t)15);
+                    pb_mbar_expect_tx(bar, nbq + nbs);
+                    if (nbq) pb_bulk_g2s(pb_smem_addr(tq), a.qual + tq0, nbq, bar);
+                    if (nbs) pb_bulk_g2s(pb_smem_addr(ts), a.seq4 + ts0, nbs, bar);
+                }
+                // the read's header and its aligned segment while the tile is on its way
+                const bool mine = lane >= start && lane < start + nt;
+                int sx0 = 0, slen = 0;
+                uint64_t so = b0;
+                uint32_t meta = 0;
+                if (mine) {
+                    sx0 = __ldg(a.pos + r); meta = __ldg(a.meta + r);
+                    const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
+                    for (uint32_t ci = 0; ci < ncg; ++ci) {
+                        const uint32_t cg = __ldg(a.cigar + c0 + ci);
+                        const uint32_t op = cg & 15u, len = cg >> 4;
+                        if (((0x181u >> op) & 1u) && len) { slen = (int)len; break; }
+                        if ((0x12u >> op) & 1u) so += len;                                          // I, S: query only
+                        else if ((0x0cu >> op) & 1u) sx0 += (int)len;                               // D, N: reference only
+                    }
+                }
+                const int mq = (int)((meta >> 8) & 0xffu);
+                pb_mbar_wait(bar, phase);
+                __syncwarp();                                                 // the lanes leave the wait loop one by one: walk the reads together
+                phase ^= 1u;
+                const int pa = max(sx0, p0), pb = min(sx0 + slen, pend);
+                if (mine && pb > pa) {
+                    uint32_t *row = cnt + (size_t)(meta & 0xffu) * RW;
+                    uint32_t addH = mq >= PB_H_QUALITY ? addH1 : 0u;          // mapQ below the khi level: no byte reaches bit 7
+                    uint32_t hmask = mq >= PB_H_QUALITY ? 0xffffffffu : 0u;
+                    asm volatile("" : "+r"(addH), "+r"(hmask));
+                    const int j0 = (pa - p0) >> 2, j1 = (pb - 1 - p0) >> 2;                          // position words of the block (four positions each)
+                    const int i0b = p0 + 4 * j0 - sx0;                                               // base index of word j0's first byte (>= -3)
+                    const int bq = (int)(so - tq0) + i0b;                                            // its byte in the quality tile (>= -3)
+                    const uint32_t *qw = reinterpret_cast<const uint32_t *>(tq) + (bq >> 2);
+                    const uint32_t selq = 0x3210u + 0x1111u * (uint32_t)(bq & 3);
+                    const int nb = (int)(so - 2 * ts0) + i0b;                                        // its nibble in the packed-base tile (>= -3)
+                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(ts) + (nb >> 3);
+                    const int sh = 4 * (nb & 7);
+                    // bytes of the first / last word that belong to the segment (and to the counters)
+                    const uint32_t mfirst = 0x01010101u << (8 * ((pa - p0) & 3));
+                    const uint32_t mlast = 0x01010101u >> (8 * (4 - (pb - p0 - 4 * j1)));
+                    uint32_t *cp = row + j0;
+                    const uint32_t *rp = ((j0 & 1) ? refB : refA) + (j0 >> 1);                       // reference nibbles of a pair of position words
+                    uint32_t over = 0;
+                    // pairs of position words share one 32-bit window of the nibble stream
+#define PB_CNT_PAIR(vmA, vmB, MASKED)                                                                                        \
+                    {                                                                                                        \
+                        const uint32_t wq1 = qw[1], wq2 = qw[2];                                                             \
+                        const uint32_t sn1 = pb_nibble_order(sw[1]);                                                         \
+                        const uint32_t sxw = __funnelshift_r(sn0, sn1, sh);                                                  \
+                        const uint32_t qa = __byte_perm(wq0, wq1, selq), qb = __byte_perm(wq1, wq2, selq);                   \
+                        const uint32_t xn = sxw ^ rp[0];                                                                     \
+                        sn0 = sn1; wq0 = wq2;                                                                                \
+                        if (!ROBUST) over |= MASKED ? ((qa & (vmA) << 7) | (qb & (vmB) << 7)) : (qa | qb);                   \
+                        uint32_t hA, hB;                                                                                     \
+                        const uint32_t mmA = pb_count_word<ROBUST, MASKED>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, &hA);             \
+                        const uint32_t mmB = pb_count_word<ROBUST, MASKED>(cp + 1, ASW, qb, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, &hB); \
+                        if (mmA | mmB) {                           /* stray bases: rare, one branch per pair */             \
+                            if (mmA) pb_count_stray<ROBUST>(cp, ASW, mmA, hA, qa, addC);                                     \
+                            if (mmB) pb_count_stray<ROBUST>(cp + 1, ASW, mmB, hB, qb, addC);                                 \
+                        }                                                                                                    \
+                        qw += 2; sw += 1; cp += 2; rp += 1;                                                                  \
+                    }
+                    const int NP = (j1 - j0 + 2) >> 1;                                               // pairs; the last one may hold one word only
+                    const bool odd = ((j1 - j0) & 1) == 0;
+                    uint32_t wq0 = qw[0], sn0 = pb_nibble_order(sw[0]);
+                    {
+                        // first pair (also the last one of a short segment)
+                        uint32_t vmA = mfirst, vmB = 0x01010101u;
+                        if (NP == 1) { if (odd) { vmA &= mlast; vmB = 0u; } else vmB = mlast; }
+                        PB_CNT_PAIR(vmA, vmB, true)
+                    }
+                    for (int p = 1; p < NP - 1; ++p) PB_CNT_PAIR(0x01010101u, 0x01010101u, false)
+                    if (NP > 1) {
+                        const uint32_t vmA = odd ? mlast : 0x01010101u, vmB = odd ? 0u : mlast;
+                        PB_CNT_PAIR(vmA, vmB, true)
+                    }
+#undef PB_CNT_PAIR
+                    if (mq < a.min_rmsQ) {
+                        // a read below min_rmsQ: every cell it covers leaves the easy path (its bases may or may not pass; k_hard_cells
+                        // computes the exact rms).  Rare, and outside the loop above.
+                        for (int j = j0; j <= j1; ++j) atomicOr(row + 3 * ASW + j, 0x02020202u);
+                    }
+                    if (!ROBUST && (over & 0x80808080u)) { a.ctr->qual_high = 1; a.ctr->qual_over = 1; }     // a quality byte >= 128: the host runs the region again with the robust variant
+                }
+                __syncwarp();                                                 // the warp's tile is free again
+                start += nt;
+            }
+            if (give_up) break;
+        }
+        // ---- reads with several aligned segments (deletions, insertions, reference skips: a few per cent): a WARP takes one read,
+        // all lanes walk its CIGAR, and the lanes share the position words of every segment, bases straight from global memory
+        for (;;) {
+            int ic = 0;
+            if (lane == 0) ic = atomicAdd(&s_cur[1], 1);
+            ic = __shfl_sync(0xffffffffu, ic, 0);
+            if (ic >= (int)tot_c) break;
+            const int64_t r = rbase + list[LCAP - 1 - ic];
+            const uint32_t meta = __ldg(a.meta + r);
+            const int mq = (int)((meta >> 8) & 0xffu);
+            uint32_t *row = cnt + (size_t)(meta & 0xffu) * RW;
+            const uint32_t addH = mq >= PB_H_QUALITY ? addH1 : 0u, hmask = mq >= PB_H_QUALITY ? 0xffffffffu : 0u;
+            const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
+            int x = __ldg(a.pos + r);
+            int64_t qo = (int64_t)__ldg(a.base + r);
+            uint32_t over = 0;
+            for (uint32_t ci = 0; ci < ncg; ++ci) {
+                const uint32_t cg = __ldg(a.cigar + c0 + ci);
+                const uint32_t op = cg & 15u;
+                const int len = (int)(cg >> 4);
+                if ((0x12u >> op) & 1u) { qo += len; continue; }                                    // I, S: query only
+                if ((0x0cu >> op) & 1u) { x += len; continue; }                                      // D, N: reference only
+                if (!((0x181u >> op) & 1u)) continue;                                                // H, P
+                const int sx0 = x;
+                const int64_t so = qo;
+                x += len; qo += len;
+                const int pa = max(sx0, p0), pb = min(sx0 + len, pend);
+                if (pb <= pa) continue;
+                const int j0 = (pa - p0) >> 2, j1 = (pb - 1 - p0) >> 2;
+                const uint32_t mfirst = 0x01010101u << (8 * ((pa - p0) & 3));
+                const uint32_t mlast = 0x01010101u >> (8 * (4 - (pb - p0 - 4 * j1)));
+                for (int w = j0 + lane; w <= j1; w += 32) {
+                    const int64_t A = so + (int64_t)(p0 + 4 * w - sx0);                              // byte / nibble index of the word's first base (>= -3)
+                    const int64_t Aq = A & ~(int64_t)3, As = (A >> 3) * 4;                           // the aligned words that hold it
+                    const uint32_t q0 = Aq >= 0 ? __ldg(reinterpret_cast<const uint32_t *>(a.qual + Aq)) : 0u;
+                    const uint32_t q1 = __ldg(reinterpret_cast<const uint32_t *>(a.qual + Aq + 4));
+                    const uint32_t s0 = As >= 0 ? __ldg(reinterpret_cast<const uint32_t *>(a.seq4 + As)) : 0u;
+                    const uint32_t s1 = __ldg(reinterpret_cast<const uint32_t *>(a.seq4 + As + 4));
+                    const uint32_t qv = __byte_perm(q0, q1, 0x3210u + 0x1111u * (uint32_t)(A & 3));
+                    const uint32_t sx = __funnelshift_r(pb_nibble_order(s0), pb_nibble_order(s1), 4 * (int)(A & 7));
+                    const uint32_t xn = sx ^ (refA[w >> 1] >> (16 * (w & 1)));
+                    uint32_t vm = 0x01010101u;
+                    if (w == j0) vm = mfirst;
+                    if (w == j1) vm &= mlast;
+                    if (!ROBUST) over |= qv & vm << 7;
+                    uint32_t hh;
+                    const uint32_t mm = pb_count_word<ROBUST, true>(row + w, ASW, qv, sx, xn, vm, addP, addH, hmask, &hh);
+                    if (mm) pb_count_stray<ROBUST>(row + w, ASW, mm, hh, qv, addC);
+                    if (mq < a.min_rmsQ) atomicOr(row + 3 * ASW + w, 0x02020202u);
+                }
+            }
+            if (!ROBUST && (over & 0x80808080u)) { a.ctr->qual_high = 1; a.ctr->qual_over = 1; }
+        }
+        __syncthreads();                                                      // the lists are free again
+    }
+    {
+        // publish what this CTA's reads added behind the block, take what the previous block's reads added to the front of this
+        // one.  The previous CTA has a lower block index, so it was scheduled no later than this one and does not wait for
+        // anything itself before it publishes: the wait below ends (decoupled look-back, as in a single-pass scan).
+        const int hw = a.halo / 4, per_s = 4 * hw;
+        uint32_t *mine = a.carry + (size_t)blockIdx.x * n * per_s;
+        for (int i = tid; i < n * per_s; i += NT) {
+            const int s = i / per_s, w = i % per_s;
+            mine[i] = cnt[(size_t)s * RW + (w / hw) * ASW + PB / 4 + (w % hw)];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            atomicExch(a.carry_flag + blockIdx.x, 1u);
+            if (blockIdx.x > 0) while (atomicAdd(a.carry_flag + (blockIdx.x - 1), 0u) == 0u) __nanosleep(20);
+            __threadfence();
+        }
+        __syncthreads();
+        if (blockIdx.x > 0) {
+            const uint32_t *prev = a.carry + (size_t)(blockIdx.x - 1) * n * per_s;
+            for (int i = tid; i < n * per_s; i += NT) {
+                const int s = i / per_s, w = i % per_s;
+                const uint32_t v = __ldcg(prev + i);
+                uint32_t *d = cnt + (size_t)s * RW + (w / hw) * ASW + (w % hw);
+                if (w / hw == 3) *d |= v; else *d += v;                       // counts add byte-wise (no cell exceeds 255); flags or
+            }
+            __syncthreads();
+        }
+    }
+    // ---- classify: one thread per position (a warp = one strip), all samples of the position one after the other
+    uint32_t *hardS = reinterpret_cast<uint32_t *>(tiles);                     // [n][spc] hard masks (the tiles are free now)
+    uint32_t *ksumS = hardS + (size_t)n * a.spc;                               // [n][spc] passing bases of a strip's hard cells
+    for (int q = tid; q < PB; q += NT) {
+        const bool inside = p0 + q < p1;
+        unsigned long long cov = 0;
+        for (int s = 0; s < n; ++s) {
+            const uint8_t *rb = reinterpret_cast<const uint8_t *>(cnt + (size_t)s * RW);
+            const int k = rb[q], kh = rb[4 * ASW + q], m = rb[8 * ASW + q], f = rb[12 * ASW + q];
+            const uint32_t fl = tabS[k], hn = tabS[256 + k];
+            const bool unan = (fl & 1u) || (hn && (uint32_t)kh >= hn);                       // the depth alone / the count of high-quality bases proves the shortcut
+            const bool stray = (fl & 2u) || (!(f & 1) && (fl & 4u));                         // one stray base that provably cannot change the call
+            const bool easy = k > 0 && !(f & 2) && ((m == 0 && unan) || (m == 1 && stray));
+            // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
+            // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is bit 3 of the table
+            if (inside && easy && (fl & 8u)) cov |= 1ULL << s;
+            const bool hard = inside && k > 0 && !easy;
+            const uint32_t hardb = __ballot_sync(0xffffffffu, hard);
+            const uint32_t ks = __reduce_add_sync(0xffffffffu, hard ? (uint32_t)k : 0u);
+            if (lane == 0) { hardS[s * a.spc + (q >> 5)] = hardb; ksumS[s * a.spc + (q >> 5)] = ks; }
+        }
+        if (inside) {
+            const int64_t o = (int64_t)(p0 + q) - a.span_beg;
+            a.acc_cov[o] = cov; a.acc_cnt4[o] = 0; a.site_type[o] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- the cells left over: a directory entry and room for the base codes of each, in (sample, strip, position) order
+    const int E = n * a.spc, per_t = (E + NT - 1) / NT;
+    const int e0 = min(E, tid * per_t), e1 = min(E, e0 + per_t);
+    uint32_t my_cells = 0, my_codes = 0;
+    for (int e = e0; e < e1; ++e) { my_cells += (uint32_t)__popc(hardS[e]); my_codes += ksumS[e]; }
+    uint32_t xc = my_cells, xk = my_codes;
+    for (int o2 = 1; o2 < 32; o2 <<= 1) {
+        const uint32_t yc = __shfl_up_sync(0xffffffffu, xc, o2), yk = __shfl_up_sync(0xffffffffu, xk, o2);
+        if (lane >= o2) { xc += yc; xk += yk; }
+    }
+    if (lane == 31) { s_wsum[0][wid] = xc; s_wsum[1][wid] = xk; }
+    __syncthreads();
+    uint32_t cell_at = xc - my_cells, code_at = xk - my_codes, tot_cells = 0, tot_codes = 0;
+    for (int w = 0; w < NWARP; ++w) {
+        if (w < wid) { cell_at += s_wsum[0][w]; code_at += s_wsum[1][w]; }
+        tot_cells += s_wsum[0][w]; tot_codes += s_wsum[1][w];
+    }
+    if (tid == 0) {
+        unsigned long long cb = 0, kb = 0;
+        if (tot_cells) {
+            cb = atomicAdd(&a.ctr->n_cells, (unsigned long long)tot_cells);
+            kb = atomicAdd(&a.ctr->n_codes, (unsigned long long)tot_codes);
+            if (cb + tot_cells > a.cell_cap || kb + tot_codes > a.code_cap) { a.ctr->arena_overflow = 1; cb = ~0ULL; }
+        }
+        s_resv[0] = cb; s_resv[1] = kb;
+    }
+    __syncthreads();
+    const bool lost = s_resv[0] == ~0ULL;                                       // no room: the host runs the region again with a larger arena
+    for (int e = e0; e < e1; ++e) {
+        const int s = e / a.spc, t = e % a.spc;
+        if (t0s + t >= a.n_strips) continue;
+        const uint32_t hm = lost ? 0u : hardS[e];
+        a.hard32[(size_t)s * a.n_strips + t0s + t] = hm;
+        a.hbase[(size_t)s * a.n_strips + t0s + t] = (uint32_t)(s_resv[0] + cell_at);
+        const uint8_t *rb = reinterpret_cast<const uint8_t *>(cnt + (size_t)s * RW);
+        for (uint32_t m = hm; m; m &= m - 1) {
+            const int q = 32 * t + (__ffs((int)m) - 1);
+            const uint32_t k = rb[q];
+            a.cells[s_resv[0] + cell_at] = make_uint4((uint32_t)(p0 + q), (uint32_t)s | k << 8, 0u, (uint32_t)(s_resv[1] + code_at));
+            a.cursor[s_resv[0] + cell_at] = 0u;
+            ++cell_at; code_at += k;
+        }
+    }
+}
+
+struct PbEmitArgs {
+    const int32_t *pos;
+    const uint32_t *meta, *cigstart, *ncig, *cigar;
+    const uint64_t *base;
+    int64_t n_reads;
+    const uint8_t *qual, *seq4;
+    int span_beg, span_end, n_samples, n_strips;
+    int min_mapQ, min_baseQ, illumina;
+    const PbCounters *ctr;
+    const uint32_t *hard32, *hbase;
+    uint4 *cells;
+    uint32_t *cursor;
+    uint16_t *codes;
+};
+
+// The base codes of the hard cells, one thread per read: exactly the bases k_pile_reads counted as passing (the same
+// filter, popbam.cpp:268-284), so a cell's k slots fill up exactly.
+__global__ void __launch_bounds__(256) k_hard_emit(const PbEmitArgs a) {
+    if (a.ctr->arena_overflow || a.ctr->spec_fail || a.ctr->n_cells == 0) return;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t meta = __ldg(a.meta + r);
+        const int mq = (int)((meta >> 8) & 0xffu);
+        const uint32_t smp = meta & 0xffu;
+        if (((meta >> 16) & 0x704u) || smp >= (uint32_t)a.n_samples || mq < a.min_mapQ) continue;
+        int x = __ldg(a.pos + r);
+        if (x >= a.span_end) continue;
+        const uint32_t c0 = __ldg(a.cigstart + r), nc = __ldg(a.ncig + r);
+        uint64_t qo = __ldg(a.base + r);
+        const uint32_t strand = (meta >> 20) & 1u;
+        const uint32_t *hrow = a.hard32 + (size_t)smp * a.n_strips, *brow = a.hbase + (size_t)smp * a.n_strips;
+        for (uint32_t ci = 0; ci < nc; ++ci) {
+            const uint32_t cg = __ldg(a.cigar + c0 + ci);
+            const int op = (int)(cg & 15u), len = (int)(cg >> 4);
+            if (op == 1 || op == 4) { qo += (uint64_t)len; continue; }
+            if (op == 2 || op == 3) { x += len; continue; }
+            if (op != 0 && op != 7 && op != 8) continue;
+            const int sx0 = x;
+            const uint64_t so = qo;
+            x += len; qo += (uint64_t)len;
+            const int pa = max(sx0, a.span_beg), pb = min(sx0 + len, a.span_end);
+            if (pb <= pa) continue;
+            for (int t = (pa - a.span_beg) >> 5; t <= (pb - 1 - a.span_beg) >> 5; ++t) {
+                const uint32_t hw = __ldg(hrow + t);
+                if (!hw) continue;
+                const int s0 = a.span_beg + 32 * t;                                            // the strip's first position
+                uint32_t m = hw;
+                if (pa > s0) m &= 0xffffffffu << (pa - s0);
+                if (pb < s0 + 32) m &= 0xffffffffu >> (s0 + 32 - pb);
+                for (; m; m &= m - 1) {
+                    const int bit = __ffs((int)m) - 1;
+                    uint32_t code;
+                    if (!pb_base_code(a.qual, a.seq4, so + (uint64_t)(s0 + bit - sx0), a.illumina, a.min_baseQ, mq, strand, &code)) continue;
+                    const uint32_t c = __ldg(brow + t) + (uint32_t)__popc(hw & ((1u << bit) - 1u));
+                    const uint4 cell = a.cells[c];
+                    const uint32_t slot = atomicAdd(a.cursor + c, 1u);
+                    if (slot < (cell.y >> 8)) a.codes[(size_t)cell.w + slot] = (uint16_t)code;
+                    atomicAdd(reinterpret_cast<uint32_t *>(a.cells + c) + 2, (uint32_t)(mq * mq));
+                }
+            }
+        }
+    }
+}
