@@ -7,6 +7,7 @@
 // "%.5f" and "%7s" produce the same bytes.  Host-only formatting of results the kernels computed.
 #include <cmath>
 #include <cstdarg>
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <cfloat>
@@ -64,104 +65,124 @@ const char kIupacLetters[17] = "AMRWNCSYNNGKNNNT";   // popbam.cpp iupac[]
 
 inline int popc(uint64_t x) { return __builtin_popcountll(x); }
 
-// Neighbour joining as the tree subcommand does it (calc_dist_matrix, join_tree, print_tree: pop_tree.cpp:496-515,
-// 254-429, 439-470), on flat arrays: taxon t (0 = the reference sequence) is end point t; interior node k has the three
-// end points T + 3k + {0, 1, 2}, of which 1 and 2 receive the two clusters it joins and 0 is joined later.  `mate[e]` is
-// the end point at the other end of e's branch, `len[e]` the branch length (stored at both ends).  The arithmetic keeps
-// the reference's order of operations: ties in the minimisation and the printed lengths depend on it.
-struct NjTree {
+// Neighbour joining for the tree subcommand (what pop_tree.cpp:208-470 computes: distances :496-515, joining :254-429,
+// Newick text :439-470), formulated on a live-cluster list:
+//   * D is kept symmetric; r[a] = sum of D(a, b) over the live b in ascending order (the reference accumulates its row
+//     sums pair by pair, which adds the same terms to every sum in the same order, and its "distance to everything
+//     else" sums of the chosen pair are these row sums again, zeros of merged clusters included);
+//   * the pair minimising Q(a, b) = (m - 2) D(a, b) - r[a] - r[b] is searched b-major, a < b, strict "<": the first
+//     minimum in that order wins, as in the reference (ties are common with integer difference counts);
+//   * the joined cluster keeps the smaller index, D(new, c) = (D(a, c) + D(b, c)) / 2, height[new] = D(a, b) / 2 and the
+//     branch lengths are (D(a,b) + (r[a] - D(a,b))/(m-2) - (r[b] - D(a,b))/(m-2)) / 2 - height[a] and D(a,b) - that - height[b],
+//     every operation in the reference's order because the printed %.5f digits depend on the rounding.
+// Tree: tips 0 .. T-1 (0 = the reference sequence), inner nodes T .. 2T-3 with three ports: port 1 and 2 take the two
+// clusters a node joins, port 0 is attached later; the final node joins the last three clusters on ports 0, 1, 2.
+// The text starts at the inner node the reference taxon hangs on, lists the subtrees behind its other two ports in port
+// order, then the reference taxon; any other node lists the two ports after the one it was entered through.
+struct NjNode {
+    int peer[3];          // neighbouring node per port
+    double len[3];        // branch length per port
+};
+struct NjForest {
     int T;
-    std::vector<int> mate;
-    std::vector<double> len;
-    const pb_print_opts *o;
-    void link(int a, int b) { mate[a] = b; mate[b] = a; }
-    bool tip(int e) const { return e < T; }
-    int next(int e) const { const int k = (e - T) / 3; return T + 3 * k + ((e - T) % 3 + 1) % 3; }
-    void print(Out &out, int e, int start) const {
-        if (tip(e)) out.s += e == 0 ? o->ref_name : o->sample_names[e - 1];
+    std::vector<NjNode> inner;                    // inner node k is node T + k
+    std::vector<int> up;                          // tip -> inner node it hangs on
+    std::vector<double> up_len;                   // tip -> its branch length
+    const pb_print_opts *names;
+    int port_of(int node, int neighbour) const {
+        const NjNode &v = inner[node - T];
+        return v.peer[0] == neighbour ? 0 : v.peer[1] == neighbour ? 1 : 2;
+    }
+    void branch(Out &out, double l) const {
+        if (l < 0) out.s += ":0.00000"; else out.f(":%.5f", l);
+    }
+    // the subtree behind `node`, entered from `from`, with the length of the branch it was entered through
+    void subtree(Out &out, int node, int from, double l) const {
+        if (node < T) out.s += node == 0 ? names->ref_name : names->sample_names[node - 1];
         else {
+            const NjNode &v = inner[node - T];
+            const int in = port_of(node, from);
             out.s += '(';
-            print(out, mate[next(e)], start);
+            subtree(out, v.peer[(in + 1) % 3], node, v.len[(in + 1) % 3]);
             out.s += ',';
-            print(out, mate[next(next(e))], start);
-            if (e == start) { out.s += ','; print(out, mate[e], start); }
+            subtree(out, v.peer[(in + 2) % 3], node, v.len[(in + 2) % 3]);
             out.s += ')';
         }
-        if (e == start) out.s += ";\n";
-        else if (len[e] < 0) out.s += ":0.00000";
-        else out.f(":%.5f", len[e]);
+        branch(out, l);
+    }
+    void newick(Out &out) const {
+        const int root = up[0];
+        const NjNode &v = inner[root - T];
+        const int in = port_of(root, 0);
+        out.s += '(';
+        subtree(out, v.peer[(in + 1) % 3], root, v.len[(in + 1) % 3]);
+        out.s += ',';
+        subtree(out, v.peer[(in + 2) % 3], root, v.len[(in + 2) % 3]);
+        out.s += ',';
+        subtree(out, 0, root, up_len[0]);
+        out.s += ");\n";
     }
 };
 
 void nj_newick(Out &out, const uint16_t *diff, int T, int num_sites, const pb_print_opts *o) {
-    std::vector<double> x((size_t)T * T, 0.0), av((size_t)T, 0.0), R((size_t)T);
-    auto X = [&](int a, int b) -> double & { return x[(size_t)a * T + b]; };
-    for (int i = 0; i < T - 1; ++i)
-        for (int j = i + 1; j < T; ++j) {
-            double d = (double)diff[i * T + j] / num_sites;                 // p-distance
+    std::vector<double> dist((size_t)T * T, 0.0), height((size_t)T, 0.0), rowsum((size_t)T, 0.0);
+    auto D = [&](int a, int b) -> double & { return dist[(size_t)a * T + b]; };
+    for (int a = 0; a < T; ++a)
+        for (int b = a + 1; b < T; ++b) {
+            double d = (double)diff[a * T + b] / num_sites;                 // p-distance
             if (o->jc) d = -0.75 * log(1.0 - (4.0 * d / 3.0));              // Jukes-Cantor
-            X(i, j) = d; X(j, i) = d;
+            D(a, b) = D(b, a) = d;
         }
-    NjTree t;
-    t.T = T; t.o = o;
-    t.mate.assign((size_t)T + 3 * (size_t)(T - 2), -1);
-    t.len.assign(t.mate.size(), 0.0);
-    std::vector<int> cl((size_t)T);          // live clusters: the end point that represents each, -1 when merged away
-    for (int i = 0; i < T; ++i) cl[i] = i;
-    for (int i = 0; i < T - 1; ++i)
-        for (int j = i + 1; j < T; ++j) { const double da = (X(i, j) + X(j, i)) / 2.0; X(i, j) = da; X(j, i) = da; }
-    double fotu2 = T - 2.0, total = 0.0;
-    int node = 0, mi = 0, mj = 0;
-    for (int cycle = 1; cycle <= T - 3; ++cycle, ++node) {
-        for (int j = 1; j < T; ++j)
-            for (int i = 0; i < j; ++i) X(j, i) = X(i, j);
-        double tmin = DBL_MAX;
-        for (int i = 0; i < T; ++i) R[i] = 0.0;
-        for (int j = 1; j < T; ++j) {
-            if (cl[j] < 0) continue;
-            for (int i = 0; i < j; ++i)
-                if (cl[i] >= 0) { R[i] += X(i, j); R[j] += X(i, j); }
+    NjForest f;
+    f.T = T; f.names = o;
+    f.inner.resize((size_t)(T - 2));
+    f.up.assign((size_t)T, -1); f.up_len.assign((size_t)T, 0.0);
+    std::vector<int> top((size_t)T);             // cluster index -> the node at its top (a tip, or the inner node that joined it last)
+    std::vector<int> live;                       // cluster indices still to be joined, ascending
+    for (int i = 0; i < T; ++i) { top[i] = i; live.push_back(i); }
+    // hang `child` (top node of a cluster) on port `port` of inner node `node`
+    auto attach = [&](int node, int port, int child, double l) {
+        NjNode &v = f.inner[node - T];
+        v.peer[port] = child; v.len[port] = l;
+        if (child < T) { f.up[child] = node; f.up_len[child] = l; }
+        else { NjNode &c = f.inner[child - T]; c.peer[0] = node; c.len[0] = l; }
+    };
+    int next_node = T;
+    while (live.size() > 3) {
+        const double m2 = (double)live.size() - 2.0;
+        for (int a : live) {
+            double r = 0.0;
+            for (int b : live) if (b != a) r += D(a, b);
+            rowsum[a] = r;
         }
-        for (int j = 1; j < T; ++j) {
-            if (cl[j] < 0) continue;
-            for (int i = 0; i < j; ++i) {
-                if (cl[i] >= 0) total = fotu2 * X(i, j) - R[i] - R[j];
-                if (total < tmin) { tmin = total; mi = i; mj = j; }          // the reference compares a stale total for dead i too
+        double best = DBL_MAX;
+        int ja = 0, jb = 0;
+        for (size_t ib = 1; ib < live.size(); ++ib)
+            for (size_t ia = 0; ia < ib; ++ia) {
+                const int a = live[ia], b = live[ib];
+                const double q = m2 * D(a, b) - rowsum[a] - rowsum[b];
+                if (q < best) { best = q; ja = a; jb = b; }
             }
-        }
-        double dio = 0.0, djo = 0.0;
-        for (int i = 0; i < T; ++i) { dio += X(i, mi); djo += X(i, mj); }
-        const double dmin = X(mi, mj);
-        dio = (dio - dmin) / fotu2;
-        djo = (djo - dmin) / fotu2;
-        double bi = (dmin + dio - djo) * 0.5, bj = dmin - bi;
-        bi -= av[mi]; bj -= av[mj];
-        const int e0 = T + 3 * node;
-        t.link(e0 + 1, cl[mi]); t.link(e0 + 2, cl[mj]);
-        t.len[cl[mi]] = bi; t.len[e0 + 1] = bi;
-        t.len[cl[mj]] = bj; t.len[e0 + 2] = bj;
-        cl[mi] = e0; cl[mj] = -1;
-        av[mi] = dmin * 0.5;
-        fotu2 -= 1.0;
-        for (int j = 0; j < T; ++j)
-            if (cl[j] >= 0) {
-                const double da = (X(mi, j) + X(mj, j)) * 0.5;
-                if (mi < j) X(mi, j) = da;
-                if (mi > j) X(j, mi) = da;
-            }
-        for (int j = 0; j < T; ++j) { X(mj, j) = 0.0; X(j, mj) = 0.0; }
+        const double dab = D(ja, jb);
+        const double ra = (rowsum[ja] - dab) / m2, rb = (rowsum[jb] - dab) / m2;
+        double la = (dab + ra - rb) * 0.5, lb = dab - la;
+        la -= height[ja]; lb -= height[jb];
+        const int node = next_node++;
+        attach(node, 1, top[ja], la);
+        attach(node, 2, top[jb], lb);
+        top[ja] = node;
+        height[ja] = dab * 0.5;
+        live.erase(std::find(live.begin(), live.end(), jb));
+        for (int c : live)
+            if (c != ja) D(ja, c) = D(c, ja) = (D(ja, c) + D(jb, c)) * 0.5;
     }
-    int el[3], k = 0;
-    for (int i = 0; i < T && k < 3; ++i) if (cl[i] >= 0) el[k++] = i;
-    double bi = (X(el[0], el[1]) + X(el[0], el[2]) - X(el[1], el[2])) * 0.5;
-    double bj = X(el[0], el[1]) - bi, bk = X(el[0], el[2]) - bi;
-    bi -= av[el[0]]; bj -= av[el[1]]; bk -= av[el[2]];
-    const int e0 = T + 3 * node;
-    t.link(e0, cl[el[0]]); t.link(e0 + 1, cl[el[1]]); t.link(e0 + 2, cl[el[2]]);
-    t.len[cl[el[0]]] = bi; t.len[e0] = bi;
-    t.len[cl[el[1]]] = bj; t.len[e0 + 1] = bj;
-    t.len[cl[el[2]]] = bk; t.len[e0 + 2] = bk;
-    t.print(out, t.mate[0], t.mate[0]);      // make_nj starts at the node the reference taxon hangs on
+    const int a = live[0], b = live[1], c = live[2];
+    double la = (D(a, b) + D(a, c) - D(b, c)) * 0.5;
+    double lb = D(a, b) - la, lc = D(a, c) - la;
+    la -= height[a]; lb -= height[b]; lc -= height[c];
+    const int node = next_node;
+    attach(node, 0, top[a], la); attach(node, 1, top[b], lb); attach(node, 2, top[c], lc);
+    f.newick(out);
 }
 
 }  // namespace

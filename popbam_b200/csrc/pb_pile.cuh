@@ -62,15 +62,14 @@ struct PbPileReadsArgs {
 
 static inline int pb_pile_halo(int max_span) { return (max_span + 31) & ~31; }
 static inline int pb_pile_asw(int spc, int halo) { return (32 * spc + halo) / 4 + 1; }
-// dynamic shared memory: counters, reference nibbles (two copies), tables, barriers, read lists, per-warp tiles (16 bytes of
+// dynamic shared memory: counters, reference nibbles (two copies), tables, barriers, per-warp tiles (16 bytes of
 // padding around each)
 static inline size_t pb_pile_reads_smem(int n_samples, int spc, int halo, int tile_q, int warps) {
     const size_t cnt = (size_t)n_samples * (4 * (size_t)pb_pile_asw(spc, halo) + 1) * 4;
     const size_t rc = 2 * ((size_t)(32 * spc + halo) / 8 + 2) * 4 + 32;
-    const size_t lists = (size_t)warps * 32 * 4 * 2 + 16;
     const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32);
     const size_t scan = (size_t)n_samples * spc * 8;               // hard masks + code counts, in the tiles' place
-    return ((cnt + 15) & ~(size_t)15) + rc + 512 + 16 * (size_t)warps + lists + (tiles > scan ? tiles : scan) + 64;
+    return ((cnt + 15) & ~(size_t)15) + rc + 512 + 16 * (size_t)warps + 16 * 256 + (tiles > scan ? tiles : scan) + 64;
 }
 
 __device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -161,7 +160,113 @@ __device__ __forceinline__ void pb_count_stray(uint32_t *cp, int ASW, uint32_t m
     if (fl) atomicOr(cp + 3 * ASW, fl);
 }
 
-#define PB_PILE_ROUND 4            // reads per thread and round of the read lists
+// What the scatter of one aligned segment needs besides the segment itself.
+struct PbScatter {
+    uint32_t *cnt;                 // counters [n][K, H, M, F][ASW]
+    const uint32_t *refA, *refB;   // reference nibbles of the block, and the same stream one position word further on
+    int ASW, RW;
+    int p0, pend;                  // the counters' positions
+    uint32_t addP, addC, addH1;    // packed thresholds: passing, ceiling of the one-stray-base rule, khi level
+    int min_rmsQ;
+    PbCounters *ctr;
+};
+template <bool GLOBAL> __device__ __forceinline__ uint32_t pb_ld32(const uint32_t *p) {
+    if (GLOBAL) return __ldg(p);
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pb_smem_addr(p)));
+    return v;
+}
+// One aligned segment of one read, by ONE thread: reference [sx0, sx0 + slen), its first base at byte qbase[qi] / nibble
+// 2 * sbase + qi... given as (word pointers + offsets) by the caller: `qb` / `sb` point to 4-byte aligned memory that holds
+// base i of the segment at byte qoff + i resp. nibble noff + i (both offsets may be negative by up to 3 for the masked bytes
+// in front of the segment; GLOBAL: the caller guarantees that memory is readable from 4 bytes before base 0, or qoff/noff >= 3).
+template <bool ROBUST, bool GLOBAL>
+__device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, int slen, uint32_t smp, int mq, const unsigned char *qb, long long qoff,
+                                                   const unsigned char *sb, long long noff) {
+    const int pa = max(sx0, c.p0), pb = min(sx0 + slen, c.pend);
+    if (pb <= pa) return;
+    const int ASW = c.ASW;
+    uint32_t *row = c.cnt + (size_t)smp * c.RW;
+    uint32_t addH = mq >= PB_H_QUALITY ? c.addH1 : 0u;                    // mapQ below the khi level: no byte reaches bit 7
+    uint32_t hmask = mq >= PB_H_QUALITY ? 0xffffffffu : 0u;
+    const uint32_t addP = c.addP, addC = c.addC;
+    asm volatile("" : "+r"(addH), "+r"(hmask));                           // keep them in registers (the compiler would recompute them per word)
+    const int j0 = (pa - c.p0) >> 2, j1 = (pb - 1 - c.p0) >> 2;           // position words of the block (four positions each)
+    const int i0b = c.p0 + 4 * j0 - sx0;                                  // base index of word j0's first byte (>= -3)
+    const long long bq = qoff + i0b;                                      // its byte (>= -3 relative to base 0)
+    const uint32_t *qw = reinterpret_cast<const uint32_t *>(qb + (bq & ~3LL));
+    const uint32_t selq = 0x3210u + 0x1111u * (uint32_t)(bq & 3);
+    const long long nb = noff + i0b;                                      // its nibble
+    const uint32_t *sw = reinterpret_cast<const uint32_t *>(sb + ((nb >> 3) << 2));
+    const int sh = 4 * (int)(nb & 7);
+    // bytes of the first / last word that belong to the segment (and to the counters)
+    const uint32_t mfirst = 0x01010101u << (8 * ((pa - c.p0) & 3));
+    const uint32_t mlast = 0x01010101u >> (8 * (4 - (pb - c.p0 - 4 * j1)));
+    uint32_t *cp = row + j0;
+    const uint32_t *rp = ((j0 & 1) ? c.refB : c.refA) + (j0 >> 1);        // reference nibbles of a pair of position words
+    uint32_t over = 0;
+    // pairs of position words share one 32-bit window of the nibble stream
+#define PB_CNT_PAIR(vmA, vmB, MASKED)                                                                                        \
+    {                                                                                                                        \
+        const uint32_t wq1 = pb_ld32<GLOBAL>(qw + 1), wq2 = pb_ld32<GLOBAL>(qw + 2);                                         \
+        const uint32_t sn1 = pb_nibble_order(pb_ld32<GLOBAL>(sw + 1));                                                       \
+        const uint32_t sxw = __funnelshift_r(sn0, sn1, sh);                                                                  \
+        const uint32_t qa = __byte_perm(wq0, wq1, selq), qb_ = __byte_perm(wq1, wq2, selq);                                  \
+        const uint32_t xn = sxw ^ rp[0];                                                                                     \
+        sn0 = sn1; wq0 = wq2;                                                                                                \
+        if (!ROBUST) over |= MASKED ? ((qa & (vmA) << 7) | (qb_ & (vmB) << 7)) : (qa | qb_);                                 \
+        uint32_t hA, hB;                                                                                                     \
+        const uint32_t mmA = pb_count_word<ROBUST, MASKED>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, &hA);             \
+        const uint32_t mmB = pb_count_word<ROBUST, MASKED>(cp + 1, ASW, qb_, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, &hB); \
+        if (mmA | mmB) {                                   /* stray bases: rare, one branch per pair */                     \
+            if (mmA) pb_count_stray<ROBUST>(cp, ASW, mmA, hA, qa, addC);                                                     \
+            if (mmB) pb_count_stray<ROBUST>(cp + 1, ASW, mmB, hB, qb_, addC);                                                \
+        }                                                                                                                    \
+        qw += 2; sw += 1; cp += 2; rp += 1;                                                                                  \
+    }
+    const int NP = (j1 - j0 + 2) >> 1;                                    // pairs; the last one may hold one word only
+    const bool odd = ((j1 - j0) & 1) == 0;
+    // GLOBAL: the word in front of base 0 may lie in front of the array
+    uint32_t wq0 = (GLOBAL && bq < 0) ? 0u : pb_ld32<GLOBAL>(qw);
+    uint32_t sn0 = (GLOBAL && nb < 0) ? 0u : pb_nibble_order(pb_ld32<GLOBAL>(sw));
+    {
+        // first pair (also the last one of a short segment)
+        uint32_t vmA = mfirst, vmB = 0x01010101u;
+        if (NP == 1) { if (odd) { vmA &= mlast; vmB = 0u; } else vmB = mlast; }
+        PB_CNT_PAIR(vmA, vmB, true)
+    }
+    for (int p = 1; p < NP - 1; ++p) PB_CNT_PAIR(0x01010101u, 0x01010101u, false)
+    if (NP > 1) {
+        const uint32_t vmA = odd ? mlast : 0x01010101u, vmB = odd ? 0u : mlast;
+        PB_CNT_PAIR(vmA, vmB, true)
+    }
+#undef PB_CNT_PAIR
+    if (mq < c.min_rmsQ) {
+        // a read below min_rmsQ: every cell it covers leaves the easy path (its bases may or may not pass; k_hard_cells
+        // computes the exact rms).  Rare, and outside the loop above.
+        for (int j = j0; j <= j1; ++j) atomicOr(row + 3 * ASW + j, 0x02020202u);
+    }
+    if (!ROBUST && (over & 0x80808080u)) { c.ctr->qual_high = 1; c.ctr->qual_over = 1; }     // a quality byte >= 128: the host runs the region again with the robust variant
+}
+
+// first index in [0, n) with pos[i] >= target (n if none), by a whole warp: 32 probes per step
+__device__ __forceinline__ long long pb_warp_lower_bound(const int32_t *__restrict__ pos, long long n, int target, int lane) {
+    long long lo = 0, hi = n;                                            // the answer is in [lo, hi]
+    while (hi - lo > 32) {
+        const long long stride = (hi - lo + 31) >> 5;
+        const long long idx = min(hi - 1, lo + (long long)(lane + 1) * stride - 1);
+        const uint32_t ge = __ballot_sync(0xffffffffu, __ldg(pos + idx) >= target);
+        if (!ge) { lo = min(hi, lo + 32 * stride); if (lo >= hi) return hi; continue; }
+        const int L = __ffs((int)ge) - 1;
+        hi = min(hi - 1, lo + (long long)(L + 1) * stride - 1);         // that probe is >= target
+        lo = lo + (long long)L * stride;
+    }
+    const long long idx = lo + lane;
+    const uint32_t ge = __ballot_sync(0xffffffffu, idx < hi && __ldg(pos + idx) >= target);
+    return ge ? lo + (__ffs((int)ge) - 1) : hi;
+}
+
+#define PB_PILE_QCAP 256           // extra segments (reads with deletions ...) a CTA queues for its last pass
 
 // ROBUST: quality bytes >= 128 were seen in this context (a BAM without qualities stores 0xff), so the packed threshold
 // tests use the form that is right for any byte value.
@@ -171,7 +276,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     __shared__ long long s_range[2];
     __shared__ unsigned long long s_resv[2];
     __shared__ uint32_t s_wsum[2][16];
-    __shared__ int s_cur[2];
+    __shared__ int s_next, s_qn;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = (int)blockDim.x, NWARP = NT >> 5;
     const int max_span = a.ctr->max_span;
     if (!a.ctr->nocap || ((max_span + 31) & ~31) > a.halo) {          // launched on an assumption that does not hold: say so, do nothing
@@ -188,23 +293,20 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     uint32_t *refB = refA + NRW;                                          // [NRW] the same stream 16 bits (one position word) further on
     uint8_t *tabS = smem_raw + ((cnt_bytes + (size_t)2 * NRW * 4 + 15) & ~(size_t)15);     // flags[256], hneed[256]
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tabS + 512);     // one per warp
-    const int LCAP = NT * PB_PILE_ROUND;
-    uint16_t *list = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(mbar) + 16 * (size_t)NWARP);     // [LCAP] reads of the round: one aligned segment from the front, several from the back
-    unsigned char *tiles = reinterpret_cast<unsigned char *>(list) + (((size_t)LCAP * 2 + 15) & ~(size_t)15);
+    int4 *queue = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(mbar) + 16 * (size_t)NWARP);       // [PB_PILE_QCAP] {sx0, offset lo, len | offset hi << 16 | sample << 24, mapq}
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(queue + PB_PILE_QCAP);
     const int tile_s = a.tile_q / 2 + 16;
     const size_t tile_bytes = (size_t)a.tile_q + 32 + (size_t)tile_s + 32;
     const int t0s = (int)blockIdx.x * a.spc;                                    // first strip of the block
     const int p0 = a.span_beg + t0s * 32, p1 = min(p0 + PB, a.span_end);
-    const int pend = p0 + PH;                                             // end of the counters
-    if (tid == 0) {
-        // the block's reads: pos in [p0, p0 + PB); the first block also takes the reads that start before the span
-        const int64_t N = a.n_reads;
-        int64_t lo = 0, hi = N;
-        if (blockIdx.x > 0) while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(a.pos + mid) >= p0) hi = mid; else lo = mid + 1; }
-        const int64_t rlo = blockIdx.x > 0 ? lo : 0;
-        lo = rlo; hi = N;
-        while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if (__ldg(a.pos + mid) >= p0 + PB) hi = mid; else lo = mid + 1; }
-        s_range[0] = rlo; s_range[1] = lo;
+    // the block's reads: pos in [p0, p0 + PB) -- one contiguous run of the sorted batch; the first block also takes the reads
+    // that start before the span.  Two warps look the ends up while the others clear the counters.
+    if (wid == 0) {
+        const long long rlo = blockIdx.x > 0 ? pb_warp_lower_bound(a.pos, a.n_reads, p0, lane) : 0;
+        if (lane == 0) { s_range[0] = rlo; s_next = 0; s_qn = 0; }
+    } else if (wid == 1) {
+        const long long rhi = pb_warp_lower_bound(a.pos, a.n_reads, p0 + PB, lane);
+        if (lane == 0) s_range[1] = rhi;
     }
     for (int i = tid; i < n * RW; i += NT) cnt[i] = 0;
     for (int i = tid; i < NRW; i += NT) {
@@ -219,251 +321,117 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     if (lane == 0) pb_mbar_init(pb_smem_addr(mbar + 2 * wid), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-    // raw quality byte thresholds (host: all <= 128): passing, khi level, above the ceiling of the one-stray-base rule
-    const int qoff = a.illumina ? 31 : 0;
-    const int tp = a.min_baseQ <= 0 ? 0 : a.min_baseQ + qoff;
-    const int th = min(128, PB_H_QUALITY + qoff);
-    const int tc = min(128, min(63, a.qual_ceiling) + 1 + qoff);
-    uint32_t addP = (uint32_t)(128 - tp) * 0x01010101u, addC = (uint32_t)(128 - tc) * 0x01010101u, addH1 = (uint32_t)(128 - th) * 0x01010101u;
-    asm volatile("" : "+r"(addP), "+r"(addC), "+r"(addH1));                // computed once (the compiler would recompute them inside the scatter loop)
-    const int64_t rlo = s_range[0], rhi = s_range[1];
+    PbScatter sc;
+    sc.cnt = cnt; sc.refA = refA; sc.refB = refB; sc.ASW = ASW; sc.RW = RW; sc.p0 = p0; sc.pend = p0 + PH; sc.min_rmsQ = a.min_rmsQ; sc.ctr = a.ctr;
+    {
+        // raw quality byte thresholds (host: all <= 128): passing, khi level, above the ceiling of the one-stray-base rule
+        const int qoff = a.illumina ? 31 : 0;
+        const int tp = a.min_baseQ <= 0 ? 0 : a.min_baseQ + qoff;
+        const int th = min(128, PB_H_QUALITY + qoff);
+        const int tc = min(128, min(63, a.qual_ceiling) + 1 + qoff);
+        uint32_t addP = (uint32_t)(128 - tp) * 0x01010101u, addC = (uint32_t)(128 - tc) * 0x01010101u, addH1 = (uint32_t)(128 - th) * 0x01010101u;
+        asm volatile("" : "+r"(addP), "+r"(addC), "+r"(addH1));            // computed once (the compiler would recompute them inside the scatter loop)
+        sc.addP = addP; sc.addC = addC; sc.addH1 = addH1;
+    }
+    const int64_t rlo = s_range[0];
+    const int n_blk = (int)(s_range[1] - rlo);                             // reads of the block
     unsigned char *tq = tiles + (size_t)wid * tile_bytes + 16;             // quality tile (16 bytes of padding in front: a segment's first word may start 3 bytes early)
     unsigned char *ts = tq + a.tile_q + 16 + 16;                           // packed-base tile
     const uint32_t bar = pb_smem_addr(mbar + 2 * wid);
     uint32_t phase = 0;
-    for (int64_t rbase = rlo; rbase < rhi; rbase += LCAP) {
-        // ---- the reads of this round, by kind: dropped (flag filter of bam_plp_push, bam_pileup.c:371-374; no sample; below
-        // min_mapQ -- the raw-depth cap cannot bind, so such a read reaches no cell, popbam.cpp:242-266), one aligned segment
-        // (the ordinary read: one thread each, below), several (a warp each).  Lists in read order.
-        const int64_t rend = min(rhi, rbase + LCAP);
-        uint32_t kinds = 0;                                                  // 2 bits per step: 1 one segment, 2 several
-        uint32_t ns = 0, nc = 0;                                             // this warp's reads of either kind
-        for (int it = 0; it < PB_PILE_ROUND; ++it) {
-            const int64_t r = rbase + (int64_t)(wid * PB_PILE_ROUND + it) * 32 + lane;
-            uint32_t kind = 0;
-            if (r < rend) {
+    // ---- scatter.  A warp takes the block's reads 32 at a time (a shared cursor: the warps stay busy whatever the reads look
+    // like), brings their bytes -- back to back in qual[] / seq4[] -- into its tile, and every lane walks the first aligned
+    // segment of its own read.  Further segments (a read with a deletion has two) are queued for the CTA's last pass.
+    for (;;) {
+        int ch = 0;
+        if (lane == 0) ch = atomicAdd(&s_next, 32);
+        ch = __shfl_sync(0xffffffffu, ch, 0);
+        if (ch >= n_blk) break;
+        const int cnt_l = min(32, n_blk - ch);
+        const int64_t r = rlo + ch + lane;
+        uint64_t b0 = 0, b1 = 0;
+        if (lane < cnt_l) { b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes; }
+        bool give_up = false;
+        for (int start = 0; start < cnt_l;) {
+            const uint64_t tq0 = __shfl_sync(0xffffffffu, b0, start) & ~(uint64_t)15;                // first byte of the quality tile
+            const bool fits = lane >= start && lane < cnt_l && b0 >= tq0 && b1 >= b0 && b1 <= a.n_bytes && b1 - tq0 <= (uint64_t)a.tile_q;
+            const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> start;
+            const int nt = fm == 0xffffffffu ? 32 : __ffs((int)~fm) - 1;                             // reads of this tile (the offsets ascend)
+            if (nt == 0) {                                                                           // one read larger than a tile, or offsets out of order
+                if (lane == 0) a.ctr->spec_fail = 1;
+                give_up = true;
+                break;
+            }
+            const uint64_t tend = __shfl_sync(0xffffffffu, b1, start + nt - 1);
+            const uint64_t ts0 = (tq0 >> 1) & ~(uint64_t)15;                                          // first byte of the packed-base tile
+            if (lane == 0) {
+                const uint32_t nbq = (uint32_t)((tend - tq0 + 15) & ~(uint64_t)15), nbs = (uint32_t)((((tend + 1) >> 1) - ts0 + 15) & ~(uint64_t)15);
+                pb_mbar_expect_tx(bar, nbq + nbs);
+                if (nbq) pb_bulk_g2s(pb_smem_addr(tq), a.qual + tq0, nbq, bar);
+                if (nbs) pb_bulk_g2s(pb_smem_addr(ts), a.seq4 + ts0, nbs, bar);
+            }
+            // the read's header and aligned segments while the tile is on its way.  Dropped: flag filter of bam_plp_push
+            // (bam_pileup.c:371-374), no sample, below min_mapQ (the raw-depth cap cannot bind, so such a read reaches no cell:
+            // popbam.cpp:242-266)
+            int sx0 = 0, slen = 0, mq = 0;
+            uint64_t so = 0;
+            uint32_t smp = 0;
+            if (lane >= start && lane < start + nt) {
                 const uint32_t meta = __ldg(a.meta + r);
-                if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) {
+                mq = (int)((meta >> 8) & 0xffu); smp = meta & 0xffu;
+                if (!((meta >> 16) & 0x704u) && smp < (uint32_t)n && mq >= a.min_mapQ) {
+                    int x = __ldg(a.pos + r);
                     const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
-                    const uint64_t b0 = __ldg(a.base + r), b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes;
-                    uint64_t ql = 0;
-                    uint32_t nseg = 0;
+                    uint64_t qo = b0;
                     for (uint32_t ci = 0; ci < ncg; ++ci) {
                         const uint32_t cg = __ldg(a.cigar + c0 + ci);
                         const uint32_t op = cg & 15u, len = cg >> 4;
-                        const uint32_t aln = (0x181u >> op) & 1u;            // M = X consume reference and query
-                        if (aln | ((0x12u >> op) & 1u)) ql += len;           // ... I S query only
-                        nseg += aln & (len > 0u);
+                        if ((0x181u >> op) & 1u) {                                                   // M = X: reference and query
+                            if (qo + len > b1 || len > 0xffffu) { a.ctr->spec_fail = 1; break; }     // CIGAR longer than the read's bases (or a segment the queue entry cannot hold)
+                            if (len) {
+                                if (!slen) { sx0 = x; so = qo; slen = (int)len; }
+                                else if (x < p0 + PH && x + (int)len > p0) {
+                                    const int qi = atomicAdd(&s_qn, 1);
+                                    if (qi < PB_PILE_QCAP) queue[qi] = make_int4(x, (int)(uint32_t)qo, (int)(len | (uint32_t)(qo >> 32) << 16 | smp << 24), mq);
+                                    else a.ctr->spec_fail = 1;                                       // (more such segments than the queue holds: the host takes the other path)
+                                }
+                            }
+                            x += (int)len; qo += len;
+                        } else if ((0x12u >> op) & 1u) qo += len;                                    // I, S: query only
+                        else if ((0x0cu >> op) & 1u) x += (int)len;                                  // D, N: reference only
                     }
-                    if (b1 < b0 || ql > b1 - b0) a.ctr->spec_fail = 1;       // CIGAR longer than the read's bases, or offsets out of order
-                    else kind = nseg == 0 ? 0u : nseg == 1 ? 1u : 2u;
                 }
             }
-            kinds |= kind << (2 * it);
-            ns += (uint32_t)__popc(__ballot_sync(0xffffffffu, kind == 1u));
-            nc += (uint32_t)__popc(__ballot_sync(0xffffffffu, kind == 2u));
+            pb_mbar_wait(bar, phase);
+            __syncwarp();                                                     // the lanes leave the wait loop one by one: walk the segments together
+            phase ^= 1u;
+            if (slen) pb_scatter_segment<ROBUST, false>(sc, sx0, slen, smp, mq, tq, (long long)(so - tq0), ts, (long long)(so - 2 * ts0));
+            __syncwarp();                                                     // the warp's tile is free again
+            start += nt;
         }
-        if (lane == 0) { s_wsum[0][wid] = ns; s_wsum[1][wid] = nc; }
-        if (tid == 0) { s_cur[0] = 0; s_cur[1] = 0; }
-        __syncthreads();
-        uint32_t off_s = 0, off_c = 0, tot_s = 0, tot_c = 0;
-        for (int w = 0; w < NWARP; ++w) {
-            if (w < wid) { off_s += s_wsum[0][w]; off_c += s_wsum[1][w]; }
-            tot_s += s_wsum[0][w]; tot_c += s_wsum[1][w];
-        }
-        for (int it = 0; it < PB_PILE_ROUND; ++it) {
-            const uint32_t kind = (kinds >> (2 * it)) & 3u;
-            const uint32_t ms = __ballot_sync(0xffffffffu, kind == 1u), mc = __ballot_sync(0xffffffffu, kind == 2u);
-            const uint32_t below = (1u << lane) - 1u;
-            const uint16_t idx = (uint16_t)((wid * PB_PILE_ROUND + it) * 32 + lane);
-            if (kind == 1u) list[off_s + (uint32_t)__popc(ms & below)] = idx;
-            if (kind == 2u) list[LCAP - 1 - (int)(off_c + (uint32_t)__popc(mc & below))] = idx;
-            off_s += (uint32_t)__popc(ms); off_c += (uint32_t)__popc(mc);
-        }
-        __syncthreads();
-        // ---- reads with one aligned segment: a warp takes 32 of them at a time (a shared cursor: the warps stay busy whatever
-        // the reads look like), brings the bytes from the first to the last of them into its tile, and every lane walks its own.
-        for (;;) {
-            int i0 = 0;
-            if (lane == 0) i0 = atomicAdd(&s_cur[0], 32);
-            i0 = __shfl_sync(0xffffffffu, i0, 0);
-            if (i0 >= (int)tot_s) break;
-            const int cnt_l = min(32, (int)tot_s - i0);
-            int64_t r = 0;
-            uint64_t b0 = 0, b1 = 0;
-            if (lane < cnt_l) {
-                r = rbase + list[i0 + lane];
-                b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes;
-            }
-            bool give_up = false;
-            for (int start = 0; start < cnt_l;) {
-                const uint64_t tq0 = __shfl_sync(0xffffffffu, b0, start) & ~(uint64_t)15;            // first byte of the quality tile
-                const bool fits = lane >= start && lane < cnt_l && b0 >= tq0 && b1 <= a.n_bytes && b1 - tq0 <= (uint64_t)a.tile_q;
-                const uint32_t fm = __ballot_sync(0xffffffffu, fits) >> start;
-                const int nt = fm == 0xffffffffu ? 32 : __ffs((int)~fm) - 1;                         // reads of this tile (the offsets ascend)
-                if (nt == 0) {                                                                       // one read larger than a tile
-                    if (lane == 0) a.ctr->spec_fail = 1;
-                    give_up = true;
-                    break;
-                }
-                const uint64_t tend = __shfl_sync(0xffffffffu, b1, start + nt - 1);
-                const uint64_t ts0 = (tq0 >> 1) & ~(uint64_t)15;                                      // first byte of the packed-base tile
-                if (lane == 0) {
-                    const uint32_t nbq = (uint32_t)((tend - tq0 + 15) & ~(uint64_t)15), nbs = (uint32_t)((((tend + 1) >> 1) - ts0 + 15) & ~(uint64_t)15);
-                    pb_mbar_expect_tx(bar, nbq + nbs);
-                    if (nbq) pb_bulk_g2s(pb_smem_addr(tq), a.qual + tq0, nbq, bar);
-                    if (nbs) pb_bulk_g2s(pb_smem_addr(ts), a.seq4 + ts0, nbs, bar);
-                }
-                // the read's header and its aligned segment while the tile is on its way
-                const bool mine = lane >= start && lane < start + nt;
-                int sx0 = 0, slen = 0;
-                uint64_t so = b0;
-                uint32_t meta = 0;
-                if (mine) {
-                    sx0 = __ldg(a.pos + r); meta = __ldg(a.meta + r);
-                    const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
-                    for (uint32_t ci = 0; ci < ncg; ++ci) {
-                        const uint32_t cg = __ldg(a.cigar + c0 + ci);
-                        const uint32_t op = cg & 15u, len = cg >> 4;
-                        if (((0x181u >> op) & 1u) && len) { slen = (int)len; break; }
-                        if ((0x12u >> op) & 1u) so += len;                                          // I, S: query only
-                        else if ((0x0cu >> op) & 1u) sx0 += (int)len;                               // D, N: reference only
-                    }
-                }
-                const int mq = (int)((meta >> 8) & 0xffu);
-                pb_mbar_wait(bar, phase);
-                __syncwarp();                                                 // the lanes leave the wait loop one by one: walk the reads together
-                phase ^= 1u;
-                const int pa = max(sx0, p0), pb = min(sx0 + slen, pend);
-                if (mine && pb > pa) {
-                    uint32_t *row = cnt + (size_t)(meta & 0xffu) * RW;
-                    uint32_t addH = mq >= PB_H_QUALITY ? addH1 : 0u;          // mapQ below the khi level: no byte reaches bit 7
-                    uint32_t hmask = mq >= PB_H_QUALITY ? 0xffffffffu : 0u;
-                    asm volatile("" : "+r"(addH), "+r"(hmask));
-                    const int j0 = (pa - p0) >> 2, j1 = (pb - 1 - p0) >> 2;                          // position words of the block (four positions each)
-                    const int i0b = p0 + 4 * j0 - sx0;                                               // base index of word j0's first byte (>= -3)
-                    const int bq = (int)(so - tq0) + i0b;                                            // its byte in the quality tile (>= -3)
-                    const uint32_t *qw = reinterpret_cast<const uint32_t *>(tq) + (bq >> 2);
-                    const uint32_t selq = 0x3210u + 0x1111u * (uint32_t)(bq & 3);
-                    const int nb = (int)(so - 2 * ts0) + i0b;                                        // its nibble in the packed-base tile (>= -3)
-                    const uint32_t *sw = reinterpret_cast<const uint32_t *>(ts) + (nb >> 3);
-                    const int sh = 4 * (nb & 7);
-                    // bytes of the first / last word that belong to the segment (and to the counters)
-                    const uint32_t mfirst = 0x01010101u << (8 * ((pa - p0) & 3));
-                    const uint32_t mlast = 0x01010101u >> (8 * (4 - (pb - p0 - 4 * j1)));
-                    uint32_t *cp = row + j0;
-                    const uint32_t *rp = ((j0 & 1) ? refB : refA) + (j0 >> 1);                       // reference nibbles of a pair of position words
-                    uint32_t over = 0;
-                    // pairs of position words share one 32-bit window of the nibble stream
-#define PB_CNT_PAIR(vmA, vmB, MASKED)                                                                                        \
-                    {                                                                                                        \
-                        const uint32_t wq1 = qw[1], wq2 = qw[2];                                                             \
-                        const uint32_t sn1 = pb_nibble_order(sw[1]);                                                         \
-                        const uint32_t sxw = __funnelshift_r(sn0, sn1, sh);                                                  \
-                        const uint32_t qa = __byte_perm(wq0, wq1, selq), qb = __byte_perm(wq1, wq2, selq);                   \
-                        const uint32_t xn = sxw ^ rp[0];                                                                     \
-                        sn0 = sn1; wq0 = wq2;                                                                                \
-                        if (!ROBUST) over |= MASKED ? ((qa & (vmA) << 7) | (qb & (vmB) << 7)) : (qa | qb);                   \
-                        uint32_t hA, hB;                                                                                     \
-                        const uint32_t mmA = pb_count_word<ROBUST, MASKED>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, &hA);             \
-                        const uint32_t mmB = pb_count_word<ROBUST, MASKED>(cp + 1, ASW, qb, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, &hB); \
-                        if (mmA | mmB) {                           /* stray bases: rare, one branch per pair */             \
-                            if (mmA) pb_count_stray<ROBUST>(cp, ASW, mmA, hA, qa, addC);                                     \
-                            if (mmB) pb_count_stray<ROBUST>(cp + 1, ASW, mmB, hB, qb, addC);                                 \
-                        }                                                                                                    \
-                        qw += 2; sw += 1; cp += 2; rp += 1;                                                                  \
-                    }
-                    const int NP = (j1 - j0 + 2) >> 1;                                               // pairs; the last one may hold one word only
-                    const bool odd = ((j1 - j0) & 1) == 0;
-                    uint32_t wq0 = qw[0], sn0 = pb_nibble_order(sw[0]);
-                    {
-                        // first pair (also the last one of a short segment)
-                        uint32_t vmA = mfirst, vmB = 0x01010101u;
-                        if (NP == 1) { if (odd) { vmA &= mlast; vmB = 0u; } else vmB = mlast; }
-                        PB_CNT_PAIR(vmA, vmB, true)
-                    }
-                    for (int p = 1; p < NP - 1; ++p) PB_CNT_PAIR(0x01010101u, 0x01010101u, false)
-                    if (NP > 1) {
-                        const uint32_t vmA = odd ? mlast : 0x01010101u, vmB = odd ? 0u : mlast;
-                        PB_CNT_PAIR(vmA, vmB, true)
-                    }
-#undef PB_CNT_PAIR
-                    if (mq < a.min_rmsQ) {
-                        // a read below min_rmsQ: every cell it covers leaves the easy path (its bases may or may not pass; k_hard_cells
-                        // computes the exact rms).  Rare, and outside the loop above.
-                        for (int j = j0; j <= j1; ++j) atomicOr(row + 3 * ASW + j, 0x02020202u);
-                    }
-                    if (!ROBUST && (over & 0x80808080u)) { a.ctr->qual_high = 1; a.ctr->qual_over = 1; }     // a quality byte >= 128: the host runs the region again with the robust variant
-                }
-                __syncwarp();                                                 // the warp's tile is free again
-                start += nt;
-            }
-            if (give_up) break;
-        }
-        // ---- reads with several aligned segments (deletions, insertions, reference skips: a few per cent): a WARP takes one read,
-        // all lanes walk its CIGAR, and the lanes share the position words of every segment, bases straight from global memory
-        for (;;) {
-            int ic = 0;
-            if (lane == 0) ic = atomicAdd(&s_cur[1], 1);
-            ic = __shfl_sync(0xffffffffu, ic, 0);
-            if (ic >= (int)tot_c) break;
-            const int64_t r = rbase + list[LCAP - 1 - ic];
-            const uint32_t meta = __ldg(a.meta + r);
-            const int mq = (int)((meta >> 8) & 0xffu);
-            uint32_t *row = cnt + (size_t)(meta & 0xffu) * RW;
-            const uint32_t addH = mq >= PB_H_QUALITY ? addH1 : 0u, hmask = mq >= PB_H_QUALITY ? 0xffffffffu : 0u;
-            const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
-            int x = __ldg(a.pos + r);
-            int64_t qo = (int64_t)__ldg(a.base + r);
-            uint32_t over = 0;
-            for (uint32_t ci = 0; ci < ncg; ++ci) {
-                const uint32_t cg = __ldg(a.cigar + c0 + ci);
-                const uint32_t op = cg & 15u;
-                const int len = (int)(cg >> 4);
-                if ((0x12u >> op) & 1u) { qo += len; continue; }                                    // I, S: query only
-                if ((0x0cu >> op) & 1u) { x += len; continue; }                                      // D, N: reference only
-                if (!((0x181u >> op) & 1u)) continue;                                                // H, P
-                const int sx0 = x;
-                const int64_t so = qo;
-                x += len; qo += len;
-                const int pa = max(sx0, p0), pb = min(sx0 + len, pend);
-                if (pb <= pa) continue;
-                const int j0 = (pa - p0) >> 2, j1 = (pb - 1 - p0) >> 2;
-                const uint32_t mfirst = 0x01010101u << (8 * ((pa - p0) & 3));
-                const uint32_t mlast = 0x01010101u >> (8 * (4 - (pb - p0 - 4 * j1)));
-                for (int w = j0 + lane; w <= j1; w += 32) {
-                    const int64_t A = so + (int64_t)(p0 + 4 * w - sx0);                              // byte / nibble index of the word's first base (>= -3)
-                    const int64_t Aq = A & ~(int64_t)3, As = (A >> 3) * 4;                           // the aligned words that hold it
-                    const uint32_t q0 = Aq >= 0 ? __ldg(reinterpret_cast<const uint32_t *>(a.qual + Aq)) : 0u;
-                    const uint32_t q1 = __ldg(reinterpret_cast<const uint32_t *>(a.qual + Aq + 4));
-                    const uint32_t s0 = As >= 0 ? __ldg(reinterpret_cast<const uint32_t *>(a.seq4 + As)) : 0u;
-                    const uint32_t s1 = __ldg(reinterpret_cast<const uint32_t *>(a.seq4 + As + 4));
-                    const uint32_t qv = __byte_perm(q0, q1, 0x3210u + 0x1111u * (uint32_t)(A & 3));
-                    const uint32_t sx = __funnelshift_r(pb_nibble_order(s0), pb_nibble_order(s1), 4 * (int)(A & 7));
-                    const uint32_t xn = sx ^ (refA[w >> 1] >> (16 * (w & 1)));
-                    uint32_t vm = 0x01010101u;
-                    if (w == j0) vm = mfirst;
-                    if (w == j1) vm &= mlast;
-                    if (!ROBUST) over |= qv & vm << 7;
-                    uint32_t hh;
-                    const uint32_t mm = pb_count_word<ROBUST, true>(row + w, ASW, qv, sx, xn, vm, addP, addH, hmask, &hh);
-                    if (mm) pb_count_stray<ROBUST>(row + w, ASW, mm, hh, qv, addC);
-                    if (mq < a.min_rmsQ) atomicOr(row + 3 * ASW + w, 0x02020202u);
-                }
-            }
-            if (!ROBUST && (over & 0x80808080u)) { a.ctr->qual_high = 1; a.ctr->qual_over = 1; }
-        }
-        __syncthreads();                                                      // the lists are free again
+        if (give_up) break;
     }
+    __syncthreads();
+    // ---- the queued segments, one per thread, bases straight from global memory (a few per cent of the reads)
     {
-        // publish what this CTA's reads added behind the block, take what the previous block's reads added to the front of this
-        // one.  The previous CTA has a lower block index, so it was scheduled no later than this one and does not wait for
+        const int nq = min(s_qn, PB_PILE_QCAP);
+        for (int i = tid; i < nq; i += NT) {
+            const int4 e = queue[i];
+            const uint32_t z = (uint32_t)e.z;
+            const long long so = (long long)(((uint64_t)((z >> 16) & 0xffu) << 32) | (uint32_t)e.y);
+            pb_scatter_segment<ROBUST, true>(sc, e.x, (int)(z & 0xffffu), z >> 24, e.w, a.qual, so, a.seq4, so);
+        }
+    }
+    __syncthreads();                                                          // this CTA's reads are counted
+    {
+        // publish what they added behind the block, take what the previous block's reads added to the front of this one.
+        // The previous CTA has a lower block index, so it was scheduled no later than this one and does not wait for
         // anything itself before it publishes: the wait below ends (decoupled look-back, as in a single-pass scan).
-        const int hw = a.halo / 4, per_s = 4 * hw;
-        uint32_t *mine = a.carry + (size_t)blockIdx.x * n * per_s;
-        for (int i = tid; i < n * per_s; i += NT) {
-            const int s = i / per_s, w = i % per_s;
-            mine[i] = cnt[(size_t)s * RW + (w / hw) * ASW + PB / 4 + (w % hw)];
+        const int hw = a.halo / 4;
+        uint32_t *mine = a.carry + (size_t)blockIdx.x * n * 4 * hw;
+        for (int sa = wid; sa < 4 * n; sa += NWARP) {                         // (sample, array): one warp each
+            const uint32_t *src = cnt + (size_t)(sa >> 2) * RW + (sa & 3) * ASW + PB / 4;
+            for (int w = lane; w < hw; w += 32) mine[sa * hw + w] = src[w];
         }
         __threadfence();
         __syncthreads();
@@ -474,41 +442,52 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         }
         __syncthreads();
         if (blockIdx.x > 0) {
-            const uint32_t *prev = a.carry + (size_t)(blockIdx.x - 1) * n * per_s;
-            for (int i = tid; i < n * per_s; i += NT) {
-                const int s = i / per_s, w = i % per_s;
-                const uint32_t v = __ldcg(prev + i);
-                uint32_t *d = cnt + (size_t)s * RW + (w / hw) * ASW + (w % hw);
-                if (w / hw == 3) *d |= v; else *d += v;                       // counts add byte-wise (no cell exceeds 255); flags or
+            const uint32_t *prev = a.carry + (size_t)(blockIdx.x - 1) * n * 4 * hw;
+            for (int sa = wid; sa < 4 * n; sa += NWARP) {
+                uint32_t *dst = cnt + (size_t)(sa >> 2) * RW + (sa & 3) * ASW;
+                const bool flags = (sa & 3) == 3;
+                for (int w = lane; w < hw; w += 32) {
+                    const uint32_t v = __ldcg(prev + sa * hw + w);
+                    if (flags) dst[w] |= v; else dst[w] += v;                 // counts add byte-wise (no cell exceeds 255); flags or
+                }
             }
             __syncthreads();
         }
     }
-    // ---- classify: one thread per position (a warp = one strip), all samples of the position one after the other
+    // ---- classify: one thread per position word (four positions; eight threads = one strip), all samples one after the other
     uint32_t *hardS = reinterpret_cast<uint32_t *>(tiles);                     // [n][spc] hard masks (the tiles are free now)
     uint32_t *ksumS = hardS + (size_t)n * a.spc;                               // [n][spc] passing bases of a strip's hard cells
-    for (int q = tid; q < PB; q += NT) {
-        const bool inside = p0 + q < p1;
-        unsigned long long cov = 0;
+    for (int w = tid; w < ((PB / 4 + 31) & ~31); w += NT) {                     // (whole warps: the strip's threads exchange their bits)
+        const uint32_t inside = w >= PB / 4 ? 0u : p0 + 4 * w + 3 < p1 ? 0xfu : p0 + 4 * w >= p1 ? 0u : (0xfu >> (p0 + 4 * w + 4 - p1));     // the word's positions inside the span
+        unsigned long long cov[4] = {0, 0, 0, 0};
         for (int s = 0; s < n; ++s) {
-            const uint8_t *rb = reinterpret_cast<const uint8_t *>(cnt + (size_t)s * RW);
-            const int k = rb[q], kh = rb[4 * ASW + q], m = rb[8 * ASW + q], f = rb[12 * ASW + q];
-            const uint32_t fl = tabS[k], hn = tabS[256 + k];
-            const bool unan = (fl & 1u) || (hn && (uint32_t)kh >= hn);                       // the depth alone / the count of high-quality bases proves the shortcut
-            const bool stray = (fl & 2u) || (!(f & 1) && (fl & 4u));                         // one stray base that provably cannot change the call
-            const bool easy = k > 0 && !(f & 2) && ((m == 0 && unan) || (m == 1 && stray));
-            // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
-            // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is bit 3 of the table
-            if (inside && easy && (fl & 8u)) cov |= 1ULL << s;
-            const bool hard = inside && k > 0 && !easy;
-            const uint32_t hardb = __ballot_sync(0xffffffffu, hard);
-            const uint32_t ks = __reduce_add_sync(0xffffffffu, hard ? (uint32_t)k : 0u);
-            if (lane == 0) { hardS[s * a.spc + (q >> 5)] = hardb; ksumS[s * a.spc + (q >> 5)] = ks; }
+            const uint32_t *rw = cnt + (size_t)s * RW + min(w, PB / 4 - 1);
+            const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
+            uint32_t hard4 = 0, ks = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t k = (K4 >> (8 * j)) & 0xffu, kh = (H4 >> (8 * j)) & 0xffu, m = (M4 >> (8 * j)) & 0xffu, f = (F4 >> (8 * j)) & 0xffu;
+                const uint32_t fl = tabS[k], hn = tabS[256 + k];
+                const bool unan = (fl & 1u) || (hn && kh >= hn);                             // the depth alone / the count of high-quality bases proves the shortcut
+                const bool stray = (fl & 2u) || (!(f & 1u) && (fl & 4u));                    // one stray base that provably cannot change the call
+                const bool easy = k > 0 && !(f & 2u) && ((m == 0 && unan) || (m == 1 && stray));
+                const bool in = (inside >> j) & 1u;
+                // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
+                // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is bit 3 of the table
+                if (in && easy && (fl & 8u)) cov[j] |= 1ULL << s;
+                if (in && k > 0 && !easy) { hard4 |= 1u << j; ks += k; }
+            }
+            // the strip's mask and code count: the eight threads of a strip
+            uint32_t hm = hard4 << (4 * (lane & 7));
+            for (int o2 = 1; o2 < 8; o2 <<= 1) { hm |= __shfl_xor_sync(0xffffffffu, hm, o2); ks += __shfl_xor_sync(0xffffffffu, ks, o2); }
+            if ((lane & 7) == 0 && w < PB / 4) { hardS[s * a.spc + (w >> 3)] = hm; ksumS[s * a.spc + (w >> 3)] = ks; }
         }
-        if (inside) {
-            const int64_t o = (int64_t)(p0 + q) - a.span_beg;
-            a.acc_cov[o] = cov; a.acc_cnt4[o] = 0; a.site_type[o] = 0;
-        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if ((inside >> j) & 1u) {
+                const int64_t o = (int64_t)(p0 + 4 * w + j) - a.span_beg;
+                a.acc_cov[o] = cov[j]; a.acc_cnt4[o] = 0; a.site_type[o] = 0;
+            }
     }
     __syncthreads();
     // ---- the cells left over: a directory entry and room for the base codes of each, in (sample, strip, position) order
@@ -539,20 +518,22 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     }
     __syncthreads();
     const bool lost = s_resv[0] == ~0ULL;                                       // no room: the host runs the region again with a larger arena
+    int es = e0 / a.spc, et = e0 - es * a.spc;                                  // entry = (sample, strip of the block)
     for (int e = e0; e < e1; ++e) {
-        const int s = e / a.spc, t = e % a.spc;
-        if (t0s + t >= a.n_strips) continue;
-        const uint32_t hm = lost ? 0u : hardS[e];
-        a.hard32[(size_t)s * a.n_strips + t0s + t] = hm;
-        a.hbase[(size_t)s * a.n_strips + t0s + t] = (uint32_t)(s_resv[0] + cell_at);
-        const uint8_t *rb = reinterpret_cast<const uint8_t *>(cnt + (size_t)s * RW);
-        for (uint32_t m = hm; m; m &= m - 1) {
-            const int q = 32 * t + (__ffs((int)m) - 1);
-            const uint32_t k = rb[q];
-            a.cells[s_resv[0] + cell_at] = make_uint4((uint32_t)(p0 + q), (uint32_t)s | k << 8, 0u, (uint32_t)(s_resv[1] + code_at));
-            a.cursor[s_resv[0] + cell_at] = 0u;
-            ++cell_at; code_at += k;
+        if (t0s + et < a.n_strips) {
+            const uint32_t hm = lost ? 0u : hardS[e];
+            a.hard32[(size_t)es * a.n_strips + t0s + et] = hm;
+            a.hbase[(size_t)es * a.n_strips + t0s + et] = (uint32_t)(s_resv[0] + cell_at);
+            const uint8_t *rb = reinterpret_cast<const uint8_t *>(cnt + (size_t)es * RW);
+            for (uint32_t m = hm; m; m &= m - 1) {
+                const int q = 32 * et + (__ffs((int)m) - 1);
+                const uint32_t k = rb[q];
+                a.cells[s_resv[0] + cell_at] = make_uint4((uint32_t)(p0 + q), (uint32_t)es | k << 8, 0u, (uint32_t)(s_resv[1] + code_at));
+                a.cursor[s_resv[0] + cell_at] = 0u;
+                ++cell_at; code_at += k;
+            }
         }
+        if (++et == a.spc) { et = 0; ++es; }
     }
 }
 
