@@ -15,9 +15,9 @@
 //     easy = k > 0 and no lowq and ( m == 0 and (depth k alone suffices  or  khi >= hneed[k])
 //                                 or m == 1 and (one stray base is harmless at depth k, or a low-quality one is) )
 //
-// The kernels that touch the reads are in pb_pile.cuh: k_pile_reads (the scatter of the reads into byte counters in shared
-// memory, all samples of a block of positions in one CTA, reads in file order, and the classification of the cells) and
-// k_hard_emit (the base codes of the ~1 % of cells that are not easy).  Here: the per-context tables of the rule
+// The kernel that touches the reads is in pb_pile.cuh: k_pile_reads (the scatter of the reads into byte counters in shared
+// memory, all samples of a block of positions in one CTA, reads in file order; the classification of the cells; the base
+// codes of the cells that are not settled by counts).  Here: the per-context tables of the rule
 // (k_set_levels / k_need_raw / k_fast_tables), the reference code bytes (k_ref_codes), k_hard_cells (the hard cells,
 // one per thread, with the exact machinery of pb_cell.cuh / pb_walk.cuh) and k_fast_sites (sites from the two).
 // History: round 1 built bit-planes in a separate streaming kernel and walked them per (record, 32 positions) with
@@ -65,10 +65,16 @@ __global__ void __launch_bounds__(256) k_need_raw(const double *__restrict__ fk,
 //             bit 2  the same for a stray base below the khi level
 //             bit 3  k >= min_depth (qfilter; k <= max_depth holds because the cap cannot bind)
 //   hneed[k]  khi >= hneed[k] bases at or above the khi level prove the shortcut (0: never)
-struct PbFastTables { uint8_t flags[256]; uint8_t hneed[256]; };
+//   altok[k]  bit b: k unanimous bases b that differ from the reference base are a derived allele -- segbase keeps the
+//             homozygote because the shortcut's snpQ (a function of k and b alone, pb_unanimous_result) reaches min_snpQ
+//             (pop_utils.cpp:139-150; below min_snpQ segbase reverts the call with arithmetic on the packed word, SURVEY Q8:
+//             those cells go to k_hard_cells)
+//   klo, khi  a run of depths with flags bits 0 and 3 set: four cells of a position word whose counts all lie in it, without
+//             stray bases or flags, are settled by two packed compares
+struct PbFastTables { uint8_t flags[256]; uint8_t hneed[256]; uint8_t altok[256]; uint8_t klo, khi, pad[14]; };
 __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restrict__ ctr, const uint8_t *__restrict__ need_raw,
                                                      const double *__restrict__ fk, const double *__restrict__ beta,
-                                                     const double *__restrict__ lhet, int min_depth, int ceiling, PbFastTables *__restrict__ tab) {
+                                                     const double *__restrict__ lhet, int min_depth, int min_snpQ, int ceiling, PbFastTables *__restrict__ tab) {
     const int nl = ctr->n_levels, k = threadIdx.x, qlo = ctr->qval[0];
     const int top = max(0, min(nl, ceiling - qlo + 1)), hi = max(0, min(top, PB_H_QUALITY - qlo));      // stray-base levels [0, top), low-quality ones [0, hi)
     uint32_t f = 0;
@@ -79,6 +85,27 @@ __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restric
     if (k >= min_depth) f |= 8u;
     tab->flags[k] = (uint8_t)f;
     tab->hneed[k] = k >= 1 ? need_raw[PB_H_QUALITY * 256 + k] : 0;
+    uint32_t ok = 0;
+    if (k >= 1)
+        for (int b = 0; b < 4; ++b) {
+            const uint64_t cb = pb_unanimous_result(lhet, k, b, 0);
+            if ((cb >> 48) == 0 && (int)((cb >> 32) & 0xffff) >= min_snpQ && pb_unanimous_het(lhet, k, b) > 0.0f) ok |= 1u << b;      // (no carry out of the 16-bit snpQ field)
+        }
+    tab->altok[k] = (uint8_t)ok;
+    __shared__ uint8_t fs[256];
+    fs[k] = (uint8_t)f;
+    __syncthreads();
+    if (k == 0) {
+        int best_lo = 1, best_hi = 0;
+        for (int i = 1; i < 128;) {                        // (packed compares: counts below 128)
+            if ((fs[i] & 9) != 9) { ++i; continue; }
+            int j = i;
+            while (j + 1 < 128 && (fs[j + 1] & 9) == 9) ++j;
+            if (j - i > best_hi - best_lo) { best_lo = i; best_hi = j; }
+            i = j + 1;
+        }
+        tab->klo = (uint8_t)best_lo; tab->khi = (uint8_t)best_hi;
+    }
 }
 
 // Reference codes of a contig, one NIBBLE per position in the code of seq4 (bam.h:245-258: A 1, C 2, G 4, T 8), eight
@@ -100,7 +127,7 @@ __global__ void __launch_bounds__(256) k_ref_codes(const char *__restrict__ ref,
 }
 
 struct PbHardArgs {
-    const uint4 *cells;                      // directory written by k_pile_reads, codes and sums of mapq^2 by k_hard_emit
+    const uint4 *cells;                      // directory and base codes written by k_pile_reads
     const uint16_t *codes;
     const char *ref;
     int64_t ref_len;

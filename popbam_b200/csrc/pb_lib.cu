@@ -43,7 +43,7 @@ struct pb_ctx {
     int64_t launches = 0;
     int n_sms = 148;
     // grids of the persistent (grid-stride) kernels: SM count x resident CTAs per SM, so every launch is one full wave
-    int g_encode = 148, g_qual_mask = 148, g_hard_cells = 148, g_read_prep = 148, g_hard_emit = 148;
+    int g_encode = 148, g_qual_mask = 148, g_hard_cells = 148, g_read_prep = 148;
     size_t smem_per_sm = 0;
     size_t smem_optin = 0;
     // tables / contig
@@ -63,8 +63,8 @@ struct pb_ctx {
     // derived
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
-    DevBuf d_fastp, d_acc, d_hard32;            // counting path: PbFastTables, per-position accumulators, hard masks + directory bases per (sample, strip)
-    DevBuf d_cells, d_cursor, d_codes16, d_need_raw;      // cells left for k_hard_cells (directory, fill cursors, base codes), need_raw[64][256]
+    DevBuf d_fastp, d_acc;                      // counting path: PbFastTables, per-position accumulators
+    DevBuf d_cells, d_codes16, d_need_raw;      // cells left for k_hard_cells (directory, base codes), need_raw[64][256]
     DevBuf d_refcode;                           // reference code bytes of the contig (k_ref_codes)
     DevBuf d_carry;                             // k_pile_reads: counts handed from a block to the next one, and their flags
     std::vector<DevBuf *> bufs;            // every device buffer of the context
@@ -338,7 +338,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
             PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastTables)));
             k_need_raw<<<64, 256, 0, st>>>(dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need_raw));
             k_fast_tables<<<1, 256, 0, st>>>(ctr, dp<uint8_t>(c->d_need_raw), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), P.min_depth,
-                                            c->qual_ceiling, dp<PbFastTables>(c->d_fastp));
+                                            P.min_snpQ, c->qual_ceiling, dp<PbFastTables>(c->d_fastp));
             c->launches += 2;
             c->need_raw_valid = true;
         }
@@ -435,13 +435,11 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
                 c->ctr_host.depth_bound, c->ctr_host.max_span, c->qual_ceiling, (int)c->qual_robust);
     c->ran_fast = fast;
     if (fast) {
-        PB_TRY(dev_reserve(c, c->d_hard32, sizeof(uint32_t) * 2 * ((size_t)n * n_strips + 1)));
         // arena of the cells left for k_hard_cells: room for one cell in eight and one base in eight (times arena_scale);
         // k_pile_reads reports an overflow, the region is then run again with a larger arena
         const unsigned long long cell_cap = std::max<unsigned long long>(65536, (unsigned long long)span * n / 8 * c->arena_scale);
         const unsigned long long code_cap = std::min<unsigned long long>(0xfffffff0ULL, std::max<unsigned long long>(1 << 20, (unsigned long long)c->n_bytes / 8 * c->arena_scale));
         PB_TRY(dev_reserve(c, c->d_cells, sizeof(uint4) * cell_cap));
-        PB_TRY(dev_reserve(c, c->d_cursor, sizeof(uint32_t) * cell_cap));
         PB_TRY(dev_reserve(c, c->d_codes16, sizeof(uint16_t) * code_cap));
         PB_CUDA(c, cudaEventRecord(c->ev[2], st));
         PbPileReadsArgs fa;
@@ -454,8 +452,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         fa.qual_ceiling = c->qual_ceiling;
         fa.ctr = ctr; fa.tab = dp<PbFastTables>(c->d_fastp);
         fa.acc_cov = dp<uint64_t>(c->d_acc); fa.acc_cnt4 = reinterpret_cast<uint32_t *>(fa.acc_cov + span); fa.site_type = dp<uint64_t>(c->d_site_type);
-        fa.hard32 = dp<uint32_t>(c->d_hard32); fa.hbase = fa.hard32 + ((size_t)n * n_strips + 1);
-        fa.cells = dp<uint4>(c->d_cells); fa.cursor = dp<uint32_t>(c->d_cursor); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
+        fa.cells = dp<uint4>(c->d_cells); fa.codes = dp<uint16_t>(c->d_codes16); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
         const unsigned n_blocks = (unsigned)((n_strips + pc.spc - 1) / pc.spc);
         const size_t carry_words = (size_t)n_blocks * n * (size_t)pc.halo;
         PB_TRY(dev_reserve(c, c->d_carry, sizeof(uint32_t) * (carry_words + n_blocks)));
@@ -471,14 +468,13 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
             PB_CUDA(c, cudaFuncSetAttribute(k_pile_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem));
             k_pile_reads<false><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
         }
-        PbEmitArgs ea;
-        ea.pos = fa.pos; ea.meta = fa.meta; ea.cigstart = fa.cigstart; ea.ncig = fa.ncig; ea.cigar = fa.cigar; ea.base = fa.base; ea.n_reads = N;
-        ea.qual = fa.qual; ea.seq4 = fa.seq4; ea.span_beg = c->span_beg; ea.span_end = c->span_end; ea.n_samples = n; ea.n_strips = n_strips;
-        ea.min_mapQ = P.min_mapQ; ea.min_baseQ = P.min_baseQ; ea.illumina = illumina; ea.ctr = ctr;
-        ea.hard32 = fa.hard32; ea.hbase = fa.hbase; ea.cells = fa.cells; ea.cursor = fa.cursor; ea.codes = dp<uint16_t>(c->d_codes16);
-        k_hard_emit<<<(unsigned)std::min<int64_t>(nblk(N, 256), (int64_t)c->g_hard_emit), 256, 0, st>>>(ea);
+        PbCellCodesArgs ca;
+        ca.pos = fa.pos; ca.meta = fa.meta; ca.cigstart = fa.cigstart; ca.ncig = fa.ncig; ca.cigar = fa.cigar; ca.base = fa.base; ca.n_reads = N;
+        ca.qual = fa.qual; ca.seq4 = fa.seq4; ca.min_mapQ = P.min_mapQ; ca.min_baseQ = P.min_baseQ; ca.illumina = illumina; ca.ctr = ctr;
+        ca.cells = fa.cells; ca.codes = fa.codes;
+        k_cell_codes<<<c->n_sms * 8, 256, 0, st>>>(ca);
         PbHardArgs ha;
-        ha.cells = fa.cells; ha.codes = ea.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
+        ha.cells = fa.cells; ha.codes = fa.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
         ha.span_beg = pa.span_beg; ha.span_end = pa.span_end; ha.win_beg = pa.win_beg; ha.win_end = pa.win_end; ha.n_windows = NW;
         ha.n_samples = n; ha.n_strips = n_strips;
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
@@ -798,7 +794,7 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
         };
         c->g_encode = wave(k_encode, 256);
         c->g_qual_mask = wave(k_qual_mask, 256);
-        c->g_read_prep = wave(k_read_prep, 256); c->g_hard_emit = wave(k_hard_emit, 256);
+        c->g_read_prep = wave(k_read_prep, 256);
         {
             int per_sm = 0;
             cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_hard_smem());

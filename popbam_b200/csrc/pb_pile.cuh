@@ -2,7 +2,7 @@
 //
 // This is the north star's "CIGAR-expanding scatter of reads into a per-window [position x sample] integer count
 // tensor, using shared-memory staging and atomics".  What the counts are for and why ~99 % of the cells need nothing
-// else is explained at the top of pb_fast.cuh; this file holds the two kernels that touch the reads:
+// else is explained at the top of pb_fast.cuh; this file holds the kernel that touches the reads:
 //
 //   k_pile_reads   one CTA = `spc` strips of 32 positions x ALL samples.  Its reads are the ones that START in the block
 //                  (the reads are sorted, bam_pileup.c:384-395, so they are one contiguous run of the batch, found by two
@@ -16,8 +16,6 @@
 //                  the block; what lands there is handed to the next block's CTA through global memory.
 //                  Then one thread per position classifies the cells of all samples (easy / hard), writes the position's
 //                  coverage mask, and the hard cells get a directory entry and room for their base codes.
-//   k_hard_emit    one thread per read: the base codes (popbam.cpp:279-284) of the hard cells its segments cover, appended
-//                  to the cells' code lists (the order inside a cell does not matter: errmod_cal sorts, pop_utils.cpp:299).
 //
 // Packed-byte arithmetic of one position word (four positions, one byte each):
 //   PRMT aligns the quality bytes to the position grid; "byte + (128 - T)" puts a threshold test into bit 7; a PRMT with
@@ -48,15 +46,13 @@ struct PbPileReadsArgs {
     int qual_ceiling;                        // largest (adjusted) quality of a stray base the one-stray-base rule of the tables covers
     PbCounters *ctr;
     const PbFastTables *tab;
-    uint64_t *acc_cov;                       // [span] out: samples whose cell is easy and covered
-    uint32_t *acc_cnt4;                      // [span] out: zero (k_hard_cells adds the derived-base counts of its cells)
-    uint64_t *site_type;                     // [span] out: zero (k_hard_cells sets derived-allele bits)
-    uint32_t *hard32;                        // [n_samples][n_strips] out: cells left for k_hard_cells
-    uint32_t *hbase;                         // [n_samples][n_strips] out: directory index of a strip's first hard cell
-    uint4 *cells;                            // directory {pos, sample | k << 8, sum mapq^2 (k_hard_emit), first code}
-    uint32_t *cursor;                        // [cell_cap] codes written so far (k_hard_emit)
+    uint64_t *acc_cov;                       // [span] out: samples whose cell is settled here and covered (k_hard_cells adds its cells)
+    uint32_t *acc_cnt4;                      // [span] out: derived-base counts of the cells settled here (k_hard_cells adds its cells')
+    uint64_t *site_type;                     // [span] out: derived-allele bits of the cells settled here (k_hard_cells adds its cells')
+    uint4 *cells;                            // out: directory of the cells left for k_hard_cells {pos, sample | k << 8, sum mapq^2, first code}
+    uint16_t *codes;                         // out: their base codes  q << 5 | strand << 4 | base  (popbam.cpp:279-284)
     unsigned long long cell_cap, code_cap;
-    uint32_t *carry;                         // [blocks][n_samples][4][halo / 4] counts a CTA's reads add behind its block
+    uint32_t *carry;                         // [blocks][n_samples][4][halo / 4] what a CTA's reads add behind its block
     uint32_t *carry_flag;                    // [blocks] set once they are published (zeroed per region)
 };
 
@@ -66,10 +62,11 @@ static inline int pb_pile_asw(int spc, int halo) { return (32 * spc + halo) / 4 
 // padding around each)
 static inline size_t pb_pile_reads_smem(int n_samples, int spc, int halo, int tile_q, int warps) {
     const size_t cnt = (size_t)n_samples * (4 * (size_t)pb_pile_asw(spc, halo) + 1) * 4;
-    const size_t rc = 2 * ((size_t)(32 * spc + halo) / 8 + 2) * 4 + 32;
+    const size_t rc = (2 * ((size_t)(32 * spc + halo) / 8 + 2) + (size_t)(32 * spc + halo) / 32 + 2) * 4 + 32;
     const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32);
-    const size_t scan = (size_t)n_samples * spc * 8;               // hard masks + code counts, in the tiles' place
-    return ((cnt + 15) & ~(size_t)15) + rc + 512 + 16 * (size_t)warps + 16 * 256 + (tiles > scan ? tiles : scan) + 64;
+    // ... and, in the tiles' place once the reads are counted: per-position masks, the classification queue, the hard-cell list
+    const size_t scan = (size_t)20 * 32 * spc + ((((size_t)n_samples * 8 * spc) + 1) & ~(size_t)1) * 2 + 8 * 1024;
+    return ((cnt + 15) & ~(size_t)15) + rc + 800 + 16 * (size_t)warps + 16 * 256 + (tiles > scan ? tiles : scan) + 64;
 }
 
 __device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -150,14 +147,19 @@ __device__ __forceinline__ uint32_t pb_count_word(uint32_t *cp, int ASW, uint32_
     *Hout = H;
     return mm;
 }
-// The stray bases of a word (rare): count them, note a high-quality one (flag bit 0), and take a cell whose stray base has
-// a quality above the ceiling of the one-stray-base rule off the easy path (flag bit 1).
+// The stray bases of a word (rare): count them and OR into the cells' flag bytes
+//   bits 0-3  the stray letters seen (one-hot in seq4's code, bam.h:245-258): a cell whose bases are all the same stray
+//             letter is a homozygous variant, settled by the classification
+//   bit 4     a stray base at or above the khi level
+//   bit 5     off the easy path: a stray base with a quality above the ceiling of the one-stray-base rule (or, set by the
+//             caller, a read below min_rmsQ)
 template <bool ROBUST>
-__device__ __forceinline__ void pb_count_stray(uint32_t *cp, int ASW, uint32_t mm, uint32_t H, uint32_t qm, uint32_t addC) {
+__device__ __forceinline__ void pb_count_stray(uint32_t *cp, int ASW, uint32_t mm, uint32_t H, uint32_t qm, uint32_t sx, uint32_t addC) {
     atomicAdd(cp + 2 * ASW, mm);
     const uint32_t oc = ((ROBUST ? (((qm & 0x7f7f7f7fu) + addC) | qm) : (qm + addC)) >> 7) & mm;
-    const uint32_t fl = (mm & H) | oc << 1;
-    if (fl) atomicOr(cp + 3 * ASW, fl);
+    // the four nibbles of sx, one per byte
+    const uint32_t letters = (sx & 0xfu) | (sx & 0xf0u) << 4 | (sx & 0xf00u) << 8 | (sx & 0xf000u) << 12;
+    atomicOr(cp + 3 * ASW, (letters & mm * 15u) | (mm & H) << 4 | oc << 5);
 }
 
 // What the scatter of one aligned segment needs besides the segment itself.
@@ -219,8 +221,8 @@ __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, 
         const uint32_t mmA = pb_count_word<ROBUST, MASKED>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, &hA);             \
         const uint32_t mmB = pb_count_word<ROBUST, MASKED>(cp + 1, ASW, qb_, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, &hB); \
         if (mmA | mmB) {                                   /* stray bases: rare, one branch per pair */                     \
-            if (mmA) pb_count_stray<ROBUST>(cp, ASW, mmA, hA, qa, addC);                                                     \
-            if (mmB) pb_count_stray<ROBUST>(cp + 1, ASW, mmB, hB, qb_, addC);                                                \
+            if (mmA) pb_count_stray<ROBUST>(cp, ASW, mmA, hA, qa, sxw, addC);                                                \
+            if (mmB) pb_count_stray<ROBUST>(cp + 1, ASW, mmB, hB, qb_, sxw >> 16, addC);                                     \
         }                                                                                                                    \
         qw += 2; sw += 1; cp += 2; rp += 1;                                                                                  \
     }
@@ -244,7 +246,7 @@ __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, 
     if (mq < c.min_rmsQ) {
         // a read below min_rmsQ: every cell it covers leaves the easy path (its bases may or may not pass; k_hard_cells
         // computes the exact rms).  Rare, and outside the loop above.
-        for (int j = j0; j <= j1; ++j) atomicOr(row + 3 * ASW + j, 0x02020202u);
+        for (int j = j0; j <= j1; ++j) atomicOr(row + 3 * ASW + j, 0x20202020u);
     }
     if (!ROBUST && (over & 0x80808080u)) { c.ctr->qual_high = 1; c.ctr->qual_over = 1; }     // a quality byte >= 128: the host runs the region again with the robust variant
 }
@@ -276,7 +278,8 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     __shared__ long long s_range[2];
     __shared__ unsigned long long s_resv[2];
     __shared__ uint32_t s_wsum[2][16];
-    __shared__ int s_next, s_qn;
+    __shared__ int s_next, s_qn, s_nh, s_nc;
+    __shared__ long long s_rback;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = (int)blockDim.x, NWARP = NT >> 5;
     const int max_span = a.ctr->max_span;
     if (!a.ctr->nocap || ((max_span + 31) & ~31) > a.halo) {          // launched on an assumption that does not hold: say so, do nothing
@@ -286,13 +289,15 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     const int n = a.n_samples;
     const int PB = a.spc * 32, PH = PB + a.halo;
     const int ASW = a.asw, RW = 4 * ASW + 1;                                // words: array stride, sample stride (odd: the samples' rows start in different banks)
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw);               // [n][K, H, M, F][ASW]: passing bases, those at or above the khi level, stray bases, flags (bit 0: a stray base at or above the khi level, bit 1: off the easy path)
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw);               // [n][K, H, M, F][ASW]: passing bases, those at or above the khi level, stray bases, flags (pb_count_stray)
     const size_t cnt_bytes = (((size_t)n * RW * 4) + 15) & ~(size_t)15;
     const int NRW = PH / 8 + 2;                                            // words of reference nibbles (eight positions each)
     uint32_t *refA = reinterpret_cast<uint32_t *>(smem_raw + cnt_bytes);  // [NRW] position 8 i of the block in bits 0-3 of word i
     uint32_t *refB = refA + NRW;                                          // [NRW] the same stream 16 bits (one position word) further on
-    uint8_t *tabS = smem_raw + ((cnt_bytes + (size_t)2 * NRW * 4 + 15) & ~(size_t)15);     // flags[256], hneed[256]
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tabS + 512);     // one per warp
+    int *sfirst = reinterpret_cast<int *>(refB + NRW);                    // [PH / 32 + 2] first read (relative to the block's first) that starts in a strip or behind it
+    const int NSF = PH / 32 + 2;
+    uint8_t *tabS = smem_raw + ((cnt_bytes + ((size_t)2 * NRW + NSF) * 4 + 15) & ~(size_t)15);     // PbFastTables
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tabS + 800);     // one per warp
     int4 *queue = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(mbar) + 16 * (size_t)NWARP);       // [PB_PILE_QCAP] {sx0, offset lo, len | offset hi << 16 | sample << 24, mapq}
     unsigned char *tiles = reinterpret_cast<unsigned char *>(queue + PB_PILE_QCAP);
     const int tile_s = a.tile_q / 2 + 16;
@@ -303,12 +308,17 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     // that start before the span.  Two warps look the ends up while the others clear the counters.
     if (wid == 0) {
         const long long rlo = blockIdx.x > 0 ? pb_warp_lower_bound(a.pos, a.n_reads, p0, lane) : 0;
-        if (lane == 0) { s_range[0] = rlo; s_next = 0; s_qn = 0; }
+        if (lane == 0) { s_range[0] = rlo; s_next = 0; s_qn = 0; s_nh = 0; s_nc = 0; }
     } else if (wid == 1) {
         const long long rhi = pb_warp_lower_bound(a.pos, a.n_reads, p0 + PB, lane);
         if (lane == 0) s_range[1] = rhi;
+    } else if (wid == 2) {
+        // first read that can cover a position of the block (for the hard cells' base codes)
+        const long long rb = blockIdx.x > 0 ? pb_warp_lower_bound(a.pos, a.n_reads, p0 - max_span + 1, lane) : 0;
+        if (lane == 0) s_rback = rb;
     }
-    for (int i = tid; i < n * RW; i += NT) cnt[i] = 0;
+    for (int i = tid; i < (int)(cnt_bytes / 16); i += NT) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NSF; i += NT) sfirst[i] = 0x7fffffff;
     for (int i = tid; i < NRW; i += NT) {
         // k_ref_codes packs by absolute position; the block starts at p0 (padded behind the contig)
         const uint32_t *g = a.refcode + ((int64_t)p0 >> 3) + i;
@@ -317,7 +327,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         const uint32_t c0 = __funnelshift_r(w0, w1, sh), c1 = __funnelshift_r(w1, w2, sh);
         refA[i] = c0; refB[i] = c0 >> 16 | c1 << 16;
     }
-    for (int i = tid; i < 128; i += NT) reinterpret_cast<uint32_t *>(tabS)[i] = __ldg(reinterpret_cast<const uint32_t *>(a.tab) + i);
+    for (int i = tid; i < (int)(sizeof(PbFastTables) / 4); i += NT) reinterpret_cast<uint32_t *>(tabS)[i] = __ldg(reinterpret_cast<const uint32_t *>(a.tab) + i);
     if (lane == 0) pb_mbar_init(pb_smem_addr(mbar + 2 * wid), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -350,7 +360,10 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         const int cnt_l = min(32, n_blk - ch);
         const int64_t r = rlo + ch + lane;
         uint64_t b0 = 0, b1 = 0;
-        if (lane < cnt_l) { b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes; }
+        if (lane < cnt_l) {
+            b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes;
+            atomicMin(&sfirst[max(0, __ldg(a.pos + r) - p0) >> 5], ch + lane);
+        }
         bool give_up = false;
         for (int start = 0; start < cnt_l;) {
             const uint64_t tq0 = __shfl_sync(0xffffffffu, b0, start) & ~(uint64_t)15;                // first byte of the quality tile
@@ -427,8 +440,8 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         // publish what they added behind the block, take what the previous block's reads added to the front of this one.
         // The previous CTA has a lower block index, so it was scheduled no later than this one and does not wait for
         // anything itself before it publishes: the wait below ends (decoupled look-back, as in a single-pass scan).
-        const int hw = a.halo / 4;
-        uint32_t *mine = a.carry + (size_t)blockIdx.x * n * 4 * hw;
+        const int hw = a.halo / 4, per_blk = n * 4 * hw;
+        uint32_t *mine = a.carry + (size_t)blockIdx.x * per_blk;
         for (int sa = wid; sa < 4 * n; sa += NWARP) {                         // (sample, array): one warp each
             const uint32_t *src = cnt + (size_t)(sa >> 2) * RW + (sa & 3) * ASW + PB / 4;
             for (int w = lane; w < hw; w += 32) mine[sa * hw + w] = src[w];
@@ -442,7 +455,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         }
         __syncthreads();
         if (blockIdx.x > 0) {
-            const uint32_t *prev = a.carry + (size_t)(blockIdx.x - 1) * n * 4 * hw;
+            const uint32_t *prev = a.carry + (size_t)(blockIdx.x - 1) * per_blk;
             for (int sa = wid; sa < 4 * n; sa += NWARP) {
                 uint32_t *dst = cnt + (size_t)(sa >> 2) * RW + (sa & 3) * ASW;
                 const bool flags = (sa & 3) == 3;
@@ -454,148 +467,210 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
             __syncthreads();
         }
     }
-    // ---- classify: one thread per position word (four positions; eight threads = one strip), all samples one after the other
-    uint32_t *hardS = reinterpret_cast<uint32_t *>(tiles);                     // [n][spc] hard masks (the tiles are free now)
-    uint32_t *ksumS = hardS + (size_t)n * a.spc;                               // [n][spc] passing bases of a strip's hard cells
-    for (int w = tid; w < ((PB / 4 + 31) & ~31); w += NT) {                     // (whole warps: the strip's threads exchange their bits)
-        const uint32_t inside = w >= PB / 4 ? 0u : p0 + 4 * w + 3 < p1 ? 0xfu : p0 + 4 * w >= p1 ? 0u : (0xfu >> (p0 + 4 * w + 4 - p1));     // the word's positions inside the span
-        unsigned long long cov[4] = {0, 0, 0, 0};
-        for (int s = 0; s < n; ++s) {
-            const uint32_t *rw = cnt + (size_t)s * RW + min(w, PB / 4 - 1);
-            const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
-            uint32_t hard4 = 0, ks = 0;
+    // ---- classify.  Pass 1, one thread per position word (four positions), all samples one after the other: four covered
+    // homozygous-reference cells at once by two packed compares; the (word, sample) pairs that fail the test are queued.
+    // Pass 2, one thread per queued pair: the cells one by one.  Pass 3: the positions' masks go to global memory.
+    // In the tiles' place (they are free now):
+    uint32_t *covS = reinterpret_cast<uint32_t *>(tiles);                      // [PB][2] samples whose cell is settled and covered
+    uint32_t *derS = covS + 2 * PB;                                            // [PB][2] ... and holds a derived allele
+    uint32_t *dcntS = derS + 2 * PB;                                           // [PB] derived-base counts (one byte per base)
+    uint16_t *cq = reinterpret_cast<uint16_t *>(dcntS + PB);                   // [n * PB / 4] queued pairs: word | sample << 9
+    uint32_t *hlist = reinterpret_cast<uint32_t *>(cq + (((size_t)n * (PB / 4) + 1) & ~(size_t)1));     // [hcap] cells left for k_hard_cells: k | position of the block << 8 | sample << 20
+    const size_t region = max((size_t)NWARP * tile_bytes, (size_t)20 * PB + (((size_t)n * (PB / 4) + 1) & ~(size_t)1) * 2 + 8 * 1024);     // (pb_pile_reads_smem)
+    const int hcap = (int)((region - (size_t)20 * PB - (((size_t)n * (PB / 4) + 1) & ~(size_t)1) * 2) / 8);
+    uint32_t *hoff = hlist + hcap;                                             // [hcap] first code of the cell, relative to the CTA's reservation
+    const PbFastTables *T = reinterpret_cast<const PbFastTables *>(tabS);
+    if (tid == 0) {
+        // strips without a read of their own: the next strip's first read
+        int nxt = n_blk;
+        for (int i = NSF - 1; i >= 0; --i) { nxt = min(nxt, sfirst[i]); sfirst[i] = nxt; }
+    }
+    {
+        const uint32_t addLo = (uint32_t)(128 - T->klo) * 0x01010101u, addHi = (uint32_t)(127 - T->khi) * 0x01010101u;
+        for (int w = tid; w < PB / 4; w += NT) {
+            const bool whole = p0 + 4 * w + 3 < p1;                            // the word's positions all inside the span
+            unsigned long long cov = 0;
+            for (int s = 0; s < n; ++s) {
+                const uint32_t *rw = cnt + (size_t)s * RW + w;
+                const uint32_t K4 = rw[0], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
+                if (whole && !(M4 | F4) && (((K4 + addLo) & ~(K4 + addHi) & ~K4 & 0x80808080u) == 0x80808080u)) cov |= 1ULL << s;
+                else if (K4) cq[atomicAdd(&s_nc, 1)] = (uint16_t)(w | s << 9);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const uint32_t k = (K4 >> (8 * j)) & 0xffu, kh = (H4 >> (8 * j)) & 0xffu, m = (M4 >> (8 * j)) & 0xffu, f = (F4 >> (8 * j)) & 0xffu;
-                const uint32_t fl = tabS[k], hn = tabS[256 + k];
-                const bool unan = (fl & 1u) || (hn && kh >= hn);                             // the depth alone / the count of high-quality bases proves the shortcut
-                const bool stray = (fl & 2u) || (!(f & 1u) && (fl & 4u));                    // one stray base that provably cannot change the call
-                const bool easy = k > 0 && !(f & 2u) && ((m == 0 && unan) || (m == 1 && stray));
-                const bool in = (inside >> j) & 1u;
-                // qfilter for easy cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ;
-                // depth <= max_depth holds because the cap cannot bind; depth >= min_depth is bit 3 of the table
-                if (in && easy && (fl & 8u)) cov[j] |= 1ULL << s;
-                if (in && k > 0 && !easy) { hard4 |= 1u << j; ks += k; }
+                covS[2 * (4 * w + j)] = (uint32_t)cov; covS[2 * (4 * w + j) + 1] = (uint32_t)(cov >> 32);
+                derS[2 * (4 * w + j)] = 0; derS[2 * (4 * w + j) + 1] = 0; dcntS[4 * w + j] = 0;
             }
-            // the strip's mask and code count: the eight threads of a strip
-            uint32_t hm = hard4 << (4 * (lane & 7));
-            for (int o2 = 1; o2 < 8; o2 <<= 1) { hm |= __shfl_xor_sync(0xffffffffu, hm, o2); ks += __shfl_xor_sync(0xffffffffu, ks, o2); }
-            if ((lane & 7) == 0 && w < PB / 4) { hardS[s * a.spc + (w >> 3)] = hm; ksumS[s * a.spc + (w >> 3)] = ks; }
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < s_nc; i += NT) {
+        const int w = cq[i] & 511, s = cq[i] >> 9, pw = p0 + 4 * w;
+        const uint32_t *rw = cnt + (size_t)s * RW + w;
+        const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
+        const uint32_t ref16 = (refA[w >> 1] >> (16 * (w & 1))) & 0xffffu;
+        const uint32_t sbit = 1u << (s & 31);
+        const int hs = s >> 5;
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if ((inside >> j) & 1u) {
-                const int64_t o = (int64_t)(p0 + 4 * w + j) - a.span_beg;
-                a.acc_cov[o] = cov[j]; a.acc_cnt4[o] = 0; a.site_type[o] = 0;
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t k = (K4 >> (8 * j)) & 0xffu, kh = (H4 >> (8 * j)) & 0xffu, m = (M4 >> (8 * j)) & 0xffu, f = (F4 >> (8 * j)) & 0xffu;
+            if (k == 0 || pw + j >= p1) continue;                                        // an empty cell is not covered
+            const uint32_t fl = T->flags[k], hn = T->hneed[k];
+            const bool unan = (fl & 1u) || (hn && kh >= hn);                             // the depth alone / the count of high-quality bases proves the shortcut
+            const bool stray = (fl & 2u) || (!(f & 0x10u) && (fl & 4u));                 // one stray base that provably cannot change the call
+            // qfilter for settled cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ (flag
+            // bit 5 clear); depth <= max_depth because the cap cannot bind; depth >= min_depth is bit 3 of the table
+            const int q = 4 * w + j;
+            bool settled = false;
+            if (!(f & 0x20u)) {
+                if ((m == 0 && unan) || (m == 1 && stray)) {                             // homozygous reference
+                    settled = true;
+                    if (fl & 8u) atomicOr(&covS[2 * q + hs], sbit);
+                } else if (m == k && unan && ((ref16 >> (4 * j)) & 0xfu)) {              // every base a stray one, the reference base a proper one
+                    const uint32_t al = f & 0xfu;
+                    if (__popc(al) == 1) {                                               // ... and all the same letter: homozygous variant
+                        const int b = __ffs((int)al) - 1;
+                        if ((T->altok[k] >> b) & 1u) {                                   // segbase keeps it (pop_utils.cpp:139-150): derived allele
+                            settled = true;
+                            atomicAdd(&dcntS[q], 1u << (8 * b));
+                            if (fl & 8u) { atomicOr(&covS[2 * q + hs], sbit); atomicOr(&derS[2 * q + hs], sbit); }
+                        }
+                    }
+                }
             }
-    }
-    __syncthreads();
-    // ---- the cells left over: a directory entry and room for the base codes of each, in (sample, strip, position) order
-    const int E = n * a.spc, per_t = (E + NT - 1) / NT;
-    const int e0 = min(E, tid * per_t), e1 = min(E, e0 + per_t);
-    uint32_t my_cells = 0, my_codes = 0;
-    for (int e = e0; e < e1; ++e) { my_cells += (uint32_t)__popc(hardS[e]); my_codes += ksumS[e]; }
-    uint32_t xc = my_cells, xk = my_codes;
-    for (int o2 = 1; o2 < 32; o2 <<= 1) {
-        const uint32_t yc = __shfl_up_sync(0xffffffffu, xc, o2), yk = __shfl_up_sync(0xffffffffu, xk, o2);
-        if (lane >= o2) { xc += yc; xk += yk; }
-    }
-    if (lane == 31) { s_wsum[0][wid] = xc; s_wsum[1][wid] = xk; }
-    __syncthreads();
-    uint32_t cell_at = xc - my_cells, code_at = xk - my_codes, tot_cells = 0, tot_codes = 0;
-    for (int w = 0; w < NWARP; ++w) {
-        if (w < wid) { cell_at += s_wsum[0][w]; code_at += s_wsum[1][w]; }
-        tot_cells += s_wsum[0][w]; tot_codes += s_wsum[1][w];
-    }
-    if (tid == 0) {
-        unsigned long long cb = 0, kb = 0;
-        if (tot_cells) {
-            cb = atomicAdd(&a.ctr->n_cells, (unsigned long long)tot_cells);
-            kb = atomicAdd(&a.ctr->n_codes, (unsigned long long)tot_codes);
-            if (cb + tot_cells > a.cell_cap || kb + tot_codes > a.code_cap) { a.ctr->arena_overflow = 1; cb = ~0ULL; }
-        }
-        s_resv[0] = cb; s_resv[1] = kb;
-    }
-    __syncthreads();
-    const bool lost = s_resv[0] == ~0ULL;                                       // no room: the host runs the region again with a larger arena
-    int es = e0 / a.spc, et = e0 - es * a.spc;                                  // entry = (sample, strip of the block)
-    for (int e = e0; e < e1; ++e) {
-        if (t0s + et < a.n_strips) {
-            const uint32_t hm = lost ? 0u : hardS[e];
-            a.hard32[(size_t)es * a.n_strips + t0s + et] = hm;
-            a.hbase[(size_t)es * a.n_strips + t0s + et] = (uint32_t)(s_resv[0] + cell_at);
-            const uint8_t *rb = reinterpret_cast<const uint8_t *>(cnt + (size_t)es * RW);
-            for (uint32_t m = hm; m; m &= m - 1) {
-                const int q = 32 * et + (__ffs((int)m) - 1);
-                const uint32_t k = rb[q];
-                a.cells[s_resv[0] + cell_at] = make_uint4((uint32_t)(p0 + q), (uint32_t)es | k << 8, 0u, (uint32_t)(s_resv[1] + code_at));
-                a.cursor[s_resv[0] + cell_at] = 0u;
-                ++cell_at; code_at += k;
+            if (!settled) {
+                const int hi = atomicAdd(&s_nh, 1);
+                if (hi < hcap) hlist[hi] = k | (uint32_t)q << 8 | (uint32_t)s << 20;
             }
         }
-        if (++et == a.spc) { et = 0; ++es; }
+    }
+    __syncthreads();
+    for (int q = tid; q < PB; q += NT)
+        if (p0 + q < p1) {
+            const int64_t o = (int64_t)(p0 + q) - a.span_beg;
+            a.acc_cov[o] = (unsigned long long)covS[2 * q + 1] << 32 | covS[2 * q];
+            a.acc_cnt4[o] = dcntS[q];
+            a.site_type[o] = (unsigned long long)derS[2 * q + 1] << 32 | derS[2 * q];
+        }
+    // ---- the cells left over: a directory entry each {position, sample | k << 8, first read that can cover it, first code};
+    // k_cell_codes collects their base codes
+    const int nh = s_nh;
+    if (nh == 0) return;
+    if (nh > hcap) { if (tid == 0) a.ctr->arena_overflow = 1; return; }          // (more than the list holds: the host gives up on this path for the region)
+    if (wid == 0) {
+        uint32_t run = 0;
+        for (int i0 = 0; i0 < nh; i0 += 32) {
+            const int i = i0 + lane;
+            const uint32_t k = i < nh ? (hlist[i] & 0xffu) : 0u;
+            uint32_t x = k;
+            for (int o2 = 1; o2 < 32; o2 <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o2); if (lane >= o2) x += y; }
+            if (i < nh) hoff[i] = run + x - k;
+            run += __shfl_sync(0xffffffffu, x, 31);
+        }
+        if (lane == 0) {
+            unsigned long long cb = atomicAdd(&a.ctr->n_cells, (unsigned long long)nh);
+            const unsigned long long kb = atomicAdd(&a.ctr->n_codes, (unsigned long long)run);
+            if (cb + nh > a.cell_cap || kb + run > a.code_cap) { a.ctr->arena_overflow = 1; cb = ~0ULL; }
+            s_resv[0] = cb; s_resv[1] = kb;
+        }
+    }
+    __syncthreads();
+    if (s_resv[0] == ~0ULL) return;                                             // no room: the host runs the region again with a larger arena
+    const long long rback = s_rback;
+    for (int i = tid; i < nh; i += NT) {
+        const uint32_t e = hlist[i];
+        const int q = (int)((e >> 8) & 0xfffu), ws = p0 + q - max_span + 1;     // the covering reads start at ws or behind
+        const long long clo = ws < p0 ? rback : rlo + sfirst[(ws - p0) >> 5];
+        a.cells[s_resv[0] + i] = make_uint4((uint32_t)(p0 + q), (e >> 20) | (e & 0xffu) << 8, (uint32_t)clo, (uint32_t)(s_resv[1] + hoff[i]));
     }
 }
 
-struct PbEmitArgs {
+struct PbCellCodesArgs {
     const int32_t *pos;
     const uint32_t *meta, *cigstart, *ncig, *cigar;
     const uint64_t *base;
     int64_t n_reads;
     const uint8_t *qual, *seq4;
-    int span_beg, span_end, n_samples, n_strips;
     int min_mapQ, min_baseQ, illumina;
     const PbCounters *ctr;
-    const uint32_t *hard32, *hbase;
-    uint4 *cells;
-    uint32_t *cursor;
+    uint4 *cells;                            // in: {position, sample | k << 8, first read to look at, first code}; out: .y = sample | codes found << 8, .z = sum of mapq^2
     uint16_t *codes;
 };
 
-// The base codes of the hard cells, one thread per read: exactly the bases k_pile_reads counted as passing (the same
-// filter, popbam.cpp:268-284), so a cell's k slots fill up exactly.
-__global__ void __launch_bounds__(256) k_hard_emit(const PbEmitArgs a) {
-    if (a.ctr->arena_overflow || a.ctr->spec_fail || a.ctr->n_cells == 0) return;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_reads; r += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t meta = __ldg(a.meta + r);
-        const int mq = (int)((meta >> 8) & 0xffu);
-        const uint32_t smp = meta & 0xffu;
-        if (((meta >> 16) & 0x704u) || smp >= (uint32_t)a.n_samples || mq < a.min_mapQ) continue;
-        int x = __ldg(a.pos + r);
-        if (x >= a.span_end) continue;
-        const uint32_t c0 = __ldg(a.cigstart + r), nc = __ldg(a.ncig + r);
-        uint64_t qo = __ldg(a.base + r);
-        const uint32_t strand = (meta >> 20) & 1u;
-        const uint32_t *hrow = a.hard32 + (size_t)smp * a.n_strips, *brow = a.hbase + (size_t)smp * a.n_strips;
-        for (uint32_t ci = 0; ci < nc; ++ci) {
-            const uint32_t cg = __ldg(a.cigar + c0 + ci);
-            const int op = (int)(cg & 15u), len = (int)(cg >> 4);
-            if (op == 1 || op == 4) { qo += (uint64_t)len; continue; }
-            if (op == 2 || op == 3) { x += len; continue; }
-            if (op != 0 && op != 7 && op != 8) continue;
-            const int sx0 = x;
-            const uint64_t so = qo;
-            x += len; qo += (uint64_t)len;
-            const int pa = max(sx0, a.span_beg), pb = min(sx0 + len, a.span_end);
-            if (pb <= pa) continue;
-            for (int t = (pa - a.span_beg) >> 5; t <= (pb - 1 - a.span_beg) >> 5; ++t) {
-                const uint32_t hw = __ldg(hrow + t);
-                if (!hw) continue;
-                const int s0 = a.span_beg + 32 * t;                                            // the strip's first position
-                uint32_t m = hw;
-                if (pa > s0) m &= 0xffffffffu << (pa - s0);
-                if (pb < s0 + 32) m &= 0xffffffffu >> (s0 + 32 - pb);
-                for (; m; m &= m - 1) {
-                    const int bit = __ffs((int)m) - 1;
-                    uint32_t code;
-                    if (!pb_base_code(a.qual, a.seq4, so + (uint64_t)(s0 + bit - sx0), a.illumina, a.min_baseQ, mq, strand, &code)) continue;
-                    const uint32_t c = __ldg(brow + t) + (uint32_t)__popc(hw & ((1u << bit) - 1u));
-                    const uint4 cell = a.cells[c];
-                    const uint32_t slot = atomicAdd(a.cursor + c, 1u);
-                    if (slot < (cell.y >> 8)) a.codes[(size_t)cell.w + slot] = (uint16_t)code;
-                    atomicAdd(reinterpret_cast<uint32_t *>(a.cells + c) + 2, (uint32_t)(mq * mq));
+// The base codes of the cells left for k_hard_cells, exactly as call_base forms them (popbam.cpp:268-284), one WARP per
+// cell: the reads that can cover the cell's position are a run of the sorted batch that starts at the read the directory
+// names; the lanes look at 32 of them at a time (sample, flag filter, mapping quality), the ones that qualify are
+// gathered in shared memory and handled 32 at a time (CIGAR walk to the position, filter, code).
+__global__ void __launch_bounds__(256) k_cell_codes(const PbCellCodesArgs a) {
+    __shared__ uint32_t s_list[8][64];
+    if (a.ctr->arena_overflow || a.ctr->spec_fail) return;
+    const unsigned long long total = a.ctr->n_cells;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int max_span = a.ctr->max_span;
+    uint32_t *list = s_list[wid];
+    for (unsigned long long c = (unsigned long long)blockIdx.x * 8 + wid; c < total; c += (unsigned long long)gridDim.x * 8) {
+        const uint4 cell = a.cells[c];
+        const int pos = (int)cell.x, smp = (int)(cell.y & 0xffu);
+        const uint32_t k = cell.y >> 8;
+        uint16_t *out = a.codes + cell.w;
+        uint32_t kk = 0, n_acc = 0;
+        int rmsq = 0;
+        // the first `cnt` gathered reads: code of the base at the cell's position, if the read has one there and it passes
+        auto take = [&](uint32_t cnt) {
+            bool ok = false;
+            uint32_t code = 0;
+            int mq = 0;
+            if ((uint32_t)lane < cnt) {
+                const int64_t r = (int64_t)list[lane];
+                const uint32_t meta = __ldg(a.meta + r);
+                mq = (int)((meta >> 8) & 0xffu);
+                int x = __ldg(a.pos + r);
+                const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
+                uint64_t qo = __ldg(a.base + r);
+                for (uint32_t ci = 0; ci < ncg && x <= pos; ++ci) {
+                    const uint32_t cg = __ldg(a.cigar + c0 + ci);
+                    const uint32_t op = cg & 15u;
+                    const int len = (int)(cg >> 4);
+                    if ((0x181u >> op) & 1u) {
+                        if (pos < x + len) { ok = pb_base_code(a.qual, a.seq4, qo + (uint64_t)(pos - x), a.illumina, a.min_baseQ, mq, (meta >> 20) & 1u, &code); break; }
+                        x += len; qo += (uint64_t)len;
+                    } else if ((0x12u >> op) & 1u) qo += (uint64_t)len;
+                    else if ((0x0cu >> op) & 1u) x += len;
                 }
             }
+            const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const uint32_t at = kk + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                if (at < k) out[at] = (uint16_t)code;
+                rmsq += mq * mq;
+            }
+            kk += (uint32_t)__popc(bal);
+        };
+        for (int64_t jb = (int64_t)cell.z;; jb += 32) {
+            const int64_t r = jb + lane;
+            const int x = r < a.n_reads ? __ldg(a.pos + r) : 0x7fffffff;
+            bool acc = false;
+            if (x <= pos && x + max_span > pos) {
+                const uint32_t meta = __ldg(a.meta + r);
+                acc = (int)(meta & 0xffu) == smp && !((meta >> 16) & 0x704u) && (int)((meta >> 8) & 0xffu) >= a.min_mapQ;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+            if (acc) list[n_acc + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint32_t)r;
+            n_acc += (uint32_t)__popc(bal);
+            __syncwarp();
+            if (n_acc >= 32) {
+                take(32);
+                const uint32_t rest = n_acc - 32, moved = (uint32_t)lane < rest ? list[32 + lane] : 0u;
+                __syncwarp();
+                if ((uint32_t)lane < rest) list[lane] = moved;
+                n_acc = rest;
+                __syncwarp();
+            }
+            if (__ballot_sync(0xffffffffu, x > pos)) break;                     // sorted: no later read starts at or before the position
         }
+        if (n_acc) take(n_acc);
+        rmsq = __reduce_add_sync(0xffffffffu, rmsq);
+        if (lane == 0) { a.cells[c].y = (uint32_t)smp | min(kk, k) << 8; a.cells[c].z = (uint32_t)rmsq; }
+        __syncwarp();
     }
 }

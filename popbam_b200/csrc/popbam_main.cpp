@@ -140,7 +140,12 @@ Options parse(int argc, char **argv) {
 
 struct Shard {
     int w0, w1;                 // windows [w0, w1)
-    pbio::Batch batch;
+    // the shard's reads as one or more batches in file order: PIECES of one bam_fetch (pbio::fetch_piece), decoded by
+    // different threads when there are fewer shards than threads (no -w: one window is the whole region) and so that no
+    // batch outgrows its 32-bit offsets
+    std::vector<pbio::Batch> pieces;
+    std::vector<std::pair<int32_t, int32_t>> cuts;     // [lo, hi) of every piece
+    int pieces_left = 0;
     std::string text;
     std::string error;
     int state = 0;              // 0 pending, 1 decoded, 2 done
@@ -164,26 +169,46 @@ struct Run {
     std::shared_future<void> tables_ready;
     std::mutex mu;
     std::condition_variable cv;
+    bool pinned = true;
     std::atomic<int> next_decode{0};
+    std::vector<std::pair<int, int>> items;      // decode work: (shard, piece), shard-major
     int max_ahead = 4;
     int printed = 0;
+    // batches are page-locked (pb_host_alloc) and expensive to allocate: used ones go back to a pool
+    std::vector<pbio::Batch> pool;
+    pbio::Batch take_batch() {
+        std::lock_guard<std::mutex> lk(mu);
+        if (pool.empty()) return pbio::Batch();
+        pbio::Batch b = std::move(pool.back());
+        pool.pop_back();
+        return b;
+    }
+    void give_batch(pbio::Batch &&b) {
+        b.clear();
+        std::lock_guard<std::mutex> lk(mu);
+        pool.push_back(std::move(b));
+    }
 };
 
 void decode_worker(Run *R) {
     for (;;) {
-        const int s = R->next_decode.fetch_add(1);
-        if (s >= (int)R->shards.size()) return;
+        const int it = R->next_decode.fetch_add(1);
+        if (it >= (int)R->items.size()) return;
+        const int s = R->items[it].first, pc = R->items[it].second;
         {   // do not run too far ahead of the printer (bounds host memory)
             std::unique_lock<std::mutex> lk(R->mu);
             R->cv.wait(lk, [&] { return s < R->printed + R->max_ahead; });
         }
         Shard &sh = R->shards[s];
+        pbio::Batch b = R->take_batch();
+        std::string err;
         try {
-            pbio::fetch_region(R->bam, R->idx, R->st, R->tid, R->wb[sh.w0], R->we[sh.w1 - 1], sh.batch);
-        } catch (const pbio::Error &e) { sh.error = e.msg; }
+            pbio::fetch_piece(R->bam, R->idx, R->st, R->tid, R->wb[sh.w0], R->we[sh.w1 - 1], sh.cuts[pc].first, sh.cuts[pc].second, b);
+        } catch (const pbio::Error &e) { err = e.msg; }
         std::lock_guard<std::mutex> lk(R->mu);
-        sh.state = 1;
-        R->cv.notify_all();
+        sh.pieces[pc] = std::move(b);
+        if (!err.empty() && sh.error.empty()) sh.error = err;
+        if (--sh.pieces_left == 0) { sh.state = 1; R->cv.notify_all(); }
     }
 }
 
@@ -216,16 +241,19 @@ void gpu_worker(Run *R, int g, int G, int device) {
             R->cv.wait(lk, [&] { return sh.state >= 1; });
         }
         if (err.empty() && sh.error.empty()) {
-            pbio::Batch &b = sh.batch;
-            pb_read_batch rb;
-            rb.n_reads = b.n_reads(); rb.n_cigar = (int64_t)b.cigar.size(); rb.n_bases = (int64_t)b.qual.size();
-            static const uint32_t zero = 0;
-            rb.pos = b.pos.data(); rb.meta = b.meta.data(); rb.cig_off = b.cig_off.data();
-            rb.cigar = b.cigar.empty() ? &zero : b.cigar.data();
-            rb.base_off = b.base_off.data(); rb.seq4 = b.seq4.data(); rb.qual = b.qual.data();
             pb_region_result res;
             int rc = pb_region_begin(ctx, R->analysis, sh.w1 - sh.w0, &R->wb[sh.w0], &R->we[sh.w0]);
-            if (rc == PB_OK && rb.n_reads > 0) rc = pb_push_batch(ctx, &rb);
+            for (pbio::Batch &b : sh.pieces) {
+                // the copies are asynchronous (the batches are page-locked and stay alive until the region is done)
+                if (rc != PB_OK || b.n_reads() == 0) continue;
+                pb_read_batch rb;
+                rb.n_reads = b.n_reads(); rb.n_cigar = (int64_t)b.cigar.size(); rb.n_bases = (int64_t)b.qual.size();
+                static const uint32_t zero = 0;
+                rb.pos = b.pos.data(); rb.meta = b.meta.data(); rb.cig_off = b.cig_off.data();
+                rb.cigar = b.cigar.empty() ? &zero : b.cigar.data();
+                rb.base_off = b.base_off.data(); rb.seq4 = b.seq4.data(); rb.qual = b.qual.data();
+                rc = R->pinned ? pb_push_batch_async(ctx, &rb) : pb_push_batch(ctx, &rb);
+            }
             if (rc == PB_OK) rc = pb_region_end(ctx, &res);
             if (rc != PB_OK) sh.error = pb_last_error(ctx);
             else
@@ -236,7 +264,8 @@ void gpu_worker(Run *R, int g, int G, int device) {
                     sh.text.append(line.data(), (size_t)k);
                 }
         } else if (sh.error.empty()) sh.error = err;
-        sh.batch = pbio::Batch();       // release the host memory
+        for (pbio::Batch &b : sh.pieces) R->give_batch(std::move(b));       // (pb_region_end has waited for the copies)
+        sh.pieces.clear();
         std::lock_guard<std::mutex> lk(R->mu);
         sh.state = 2;
         R->cv.notify_all();
@@ -317,7 +346,8 @@ int main(int argc, char **argv) {
         { std::ifstream t(o.reffile); if (!t) fatal("Specified reference file: " + o.reffile + " does not exist"); }
         // the error-model tables take ~0.25 s of host arithmetic: build them while the files are opened and CUDA comes up
         R.fk.resize(256); R.beta.resize((size_t)64 * 256 * 256); R.lhet.resize(65536);
-        R.tables_ready = std::async(std::launch::async, [&R]() { pb_build_errmod_tables(R.fk.data(), R.beta.data(), R.lhet.data()); }).share();
+        // (cached on disk after the first run on a machine: pb_errmod_tables_cached)
+        R.tables_ready = std::async(std::launch::async, [&R]() { pb_errmod_tables_cached(R.fk.data(), R.beta.data(), R.lhet.data(), nullptr); }).share();
         R.bam.open(bamfile);
         R.hdr = pbio::read_header(R.bam);
         std::string text = R.hdr.text;
@@ -334,7 +364,17 @@ int main(int argc, char **argv) {
             while (e < R.hdr.text.size() && R.hdr.text[e] && R.hdr.text[e] != '\t' && R.hdr.text[e] != '\n') ++e;
             R.ref_name = R.hdr.text.substr(at + 3, e - (at + 3));
         }
-        R.idx.load(bamfile + ".bai", R.hdr.names.size());
+        {
+            // <bam>.bai, else <bam without its extension>.bai (bam_index_load_local, bam_index.c:552-560)
+            std::string bai = bamfile + ".bai";
+            std::ifstream t(bai);
+            const size_t dot = bamfile.rfind('.');
+            if (!t && dot != std::string::npos && bamfile.compare(dot, std::string::npos, ".bam") == 0) {
+                std::ifstream t2(bamfile.substr(0, dot) + ".bai");
+                if (t2) bai = bamfile.substr(0, dot) + ".bai";
+            }
+            R.idx.load(bai, R.hdr.names.size());
+        }
         if (!pbio::parse_region(R.hdr, region, &R.tid, &R.beg, &R.end)) fatal("Bad genome coordinates: " + region);
         R.ref = pbio::fetch_contig(o.reffile, R.hdr.names[R.tid]);
     } catch (const pbio::Error &e) { fatal(e.msg); }
@@ -381,6 +421,26 @@ int main(int argc, char **argv) {
     }
     const int G = std::max(1, o.gpus);
     const int D = o.threads > 0 ? o.threads : std::max(2u, std::min(32u, std::thread::hardware_concurrency()));
+    // decode work items: every shard in pieces of at most 1 Mb, more of them when there are fewer shards than threads
+    {
+        const int want = (int)std::min<size_t>(16, ((size_t)D + R.shards.size() - 1) / R.shards.size());
+        for (size_t si = 0; si < R.shards.size(); ++si) {
+            Shard &sh = R.shards[si];
+            const int64_t lo = R.wb[sh.w0], hi = R.we[sh.w1 - 1];
+            const int np = (int)std::max<int64_t>(want, (hi - lo + 999999) / 1000000);
+            for (int i = 0; i < np; ++i) {
+                const int32_t a = (int32_t)(lo + (hi - lo) * i / np), b = (int32_t)(lo + (hi - lo) * (i + 1) / np);
+                if (b > a || i == 0) { sh.cuts.push_back({a, b}); R.items.push_back({(int)si, (int)sh.cuts.size() - 1}); }
+            }
+            sh.pieces.resize(sh.cuts.size());
+            sh.pieces_left = (int)sh.cuts.size();
+        }
+    }
+    {
+        const char *e = getenv("POPBAM_B200_PAGEABLE");
+        R.pinned = !(e && *e == '1');
+        if (R.pinned) pbio::set_batch_allocator(pb_host_alloc, pb_host_free);
+    }
     // two contexts (host threads) per GPU: one shard's host->device copy runs beside another shard's kernels
     const int W = 2 * G;
     // every decode thread can have a shard in hand and one waiting (a decoded 50 kb shard of the bench workload is 34 MB)
