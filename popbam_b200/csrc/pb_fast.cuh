@@ -69,9 +69,9 @@ __global__ void __launch_bounds__(256) k_need_raw(const double *__restrict__ fk,
 //             homozygote because the shortcut's snpQ (a function of k and b alone, pb_unanimous_result) reaches min_snpQ
 //             (pop_utils.cpp:139-150; below min_snpQ segbase reverts the call with arithmetic on the packed word, SURVEY Q8:
 //             those cells go to k_hard_cells)
-//   klo, khi  a run of depths with flags bits 0 and 3 set: four cells of a position word whose counts all lie in it, without
-//             stray bases or flags, are settled by two packed compares
-struct PbFastTables { uint8_t flags[256]; uint8_t hneed[256]; uint8_t altok[256]; uint8_t klo, khi, pad[14]; };
+//   rlo, rhi, rh   three runs of depths [rlo, rhi] (all below 128) in which a cell without stray bases or flags is settled by
+//             packed compares: bit 3 holds throughout, and bit 0 in run 0 (rh[0] = 0), khi >= rh[i] >= hneed[k] in the others
+struct PbFastTables { uint8_t flags[256]; uint8_t hneed[256]; uint8_t altok[256]; uint8_t rlo[3], rhi[3], rh[3], pad[7]; };
 __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restrict__ ctr, const uint8_t *__restrict__ need_raw,
                                                      const double *__restrict__ fk, const double *__restrict__ beta,
                                                      const double *__restrict__ lhet, int min_depth, int min_snpQ, int ceiling, PbFastTables *__restrict__ tab) {
@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restric
     __shared__ uint8_t fs[256];
     fs[k] = (uint8_t)f;
     __syncthreads();
+    __shared__ uint8_t hs[256];
+    hs[k] = tab->hneed[k];
+    __syncthreads();
     if (k == 0) {
         int best_lo = 1, best_hi = 0;
         for (int i = 1; i < 128;) {                        // (packed compares: counts below 128)
@@ -104,7 +107,16 @@ __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restric
             if (j - i > best_hi - best_lo) { best_lo = i; best_hi = j; }
             i = j + 1;
         }
-        tab->klo = (uint8_t)best_lo; tab->khi = (uint8_t)best_hi;
+        tab->rlo[0] = (uint8_t)best_lo; tab->rhi[0] = (uint8_t)best_hi; tab->rh[0] = 0;
+        // the depths behind that run, as long as the count of high-quality bases they ask for stays small
+        int at = best_hi >= best_lo ? best_hi + 1 : 1;
+        const int lim[2] = {8, 16};
+        for (int r = 0; r < 2; ++r) {
+            int lo = at, hi = at - 1, hmax = 0;
+            while (hi + 1 < 128 && (fs[hi + 1] & 8) && hs[hi + 1] > 0 && hs[hi + 1] <= lim[r]) { ++hi; hmax = max(hmax, (int)hs[hi]); }
+            tab->rlo[r + 1] = (uint8_t)lo; tab->rhi[r + 1] = (uint8_t)hi; tab->rh[r + 1] = (uint8_t)max(hmax, 1);
+            at = hi + 1;
+        }
     }
 }
 

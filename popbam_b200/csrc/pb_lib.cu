@@ -36,8 +36,12 @@ enum RegionState { ST_IDLE = 0, ST_OPEN = 1, ST_LAUNCHED = 2, ST_DONE = 3 };
 
 }  // namespace
 
+// launch shape of k_pile_reads and what it was chosen for
+struct PileShape { int spc = 0, warps = 0, tile_q = 0, halo = 0, qcap = 0, dens16 = 0, tail = 0; bool robust = false; size_t smem = 0; };
+
 struct pb_ctx {
     pb_params prm;
+    PileShape pile_shape;
     cudaStream_t stream = nullptr;
     std::string err;
     int64_t launches = 0;
@@ -64,7 +68,7 @@ struct pb_ctx {
     DevBuf d_rkey, d_rnseg, d_codes, d_bins, d_need, d_qtab, d_counts, d_blocktot, d_srec, d_sstart, d_ctr;
     DevBuf d_site_type, d_site_flag, d_cb;
     DevBuf d_fastp, d_acc;                      // counting path: PbFastTables, per-position accumulators
-    DevBuf d_cells, d_codes16, d_need_raw;      // cells left for k_hard_cells (directory, base codes), need_raw[64][256]
+    DevBuf d_cells, d_codes16, d_need_raw, d_blk;      // cells left for k_hard_cells (directory, base codes), need_raw[64][256], per-block records of the directory
     DevBuf d_refcode;                           // reference code bytes of the contig (k_ref_codes)
     DevBuf d_carry;                             // k_pile_reads: counts handed from a block to the next one, and their flags
     std::vector<DevBuf *> bufs;            // every device buffer of the context
@@ -239,7 +243,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     // ---- per-read preparation, quality levels, partition by sample
     PB_TRY(dev_reserve(c, c->d_ctr, sizeof(PbCounters)));
     PB_CUDA(c, cudaMemsetAsync(c->d_ctr.p, 0, sizeof(PbCounters), st));
-    PB_TRY(dev_reserve(c, c->d_rkey, (size_t)std::max<int64_t>(N, 1)));
+    PB_TRY(dev_reserve(c, c->d_rkey, (size_t)std::max<int64_t>(N, 1) + 8));
     PB_TRY(dev_reserve(c, c->d_rnseg, (size_t)std::max<int64_t>(N, 1)));
     PbCounters *ctr = dp<PbCounters>(c->d_ctr);
     const int illumina = (P.flags & PB_FLAG_ILLUMINA) ? 1 : 0;
@@ -375,31 +379,40 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     const bool cap = c->ctr_host.nocap == 0;
     // launch shape of k_pile_reads: strips per CTA and warps per CTA that keep the most warps resident (the counters of all
     // samples, the tiles of all warps and the registers decide), larger blocks first among equals
-    struct { int spc = 0, warps = 0, tile_q = 0, halo = 0; size_t smem = 0; } pc;
+    PileShape pc;
     if (fast_try && !cap) {
         const int rb = std::max(c->ctr_host.max_read_bytes, 16);
         pc.halo = std::max(32, pb_pile_halo(c->ctr_host.max_span));
         pc.tile_q = std::max(std::min((32 * rb + 32 + 31) & ~31, 8192 + 32), (rb + 16 + 31) & ~31);
-        int best = 0;
-        for (int spc = 64; spc >= 1; spc >>= 1) {
-            if (32 * spc < pc.halo) break;
-            for (int warps = 16; warps >= 4; warps >>= 1) {
-                const size_t smem = pb_pile_reads_smem(n, spc, pc.halo, pc.tile_q, warps);
-                if (smem > c->smem_optin) continue;
-                int per_sm = 0;
-                if (c->qual_robust) {
-                    cudaFuncSetAttribute(k_pile_reads<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<true>, warps * 32, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
-                } else {
-                    cudaFuncSetAttribute(k_pile_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<false>, warps * 32, smem) != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+        // reads per position of the span; a fifth of a block's reads may have a second aligned segment to queue
+        pc.dens16 = (int)std::min<double>(1e6, 16.0 * (double)N / (double)std::max<int64_t>(span, 1)) + 1;
+        if (c->pile_shape.spc > 0 && c->pile_shape.halo == pc.halo && c->pile_shape.tile_q == pc.tile_q && c->pile_shape.dens16 >= pc.dens16 &&
+            c->pile_shape.dens16 <= 2 * pc.dens16 && c->pile_shape.robust == c->qual_robust)
+            pc = c->pile_shape;                                            // the same question as for the region before
+        else {
+            int best = 0;
+            for (int spc = 64; spc >= 1; spc >>= 1) {
+                if (32 * spc < pc.halo) break;
+                const int qcap = std::max(128, std::min(4096, ((int)(0.2 * 32.0 * spc * pc.dens16 / 16.0) + 63) & ~63));
+                for (int warps = 16; warps >= 4; warps >>= 1) {
+                    const int lreads = 0;
+                    const size_t smem = pb_pile_reads_smem(n, spc, pc.halo, pc.tile_q, warps, qcap, lreads);
+                    if (smem > c->smem_optin) continue;
+                    int per_sm = 0;
+                    const cudaError_t e = c->qual_robust ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<true>, warps * 32, smem)
+                                                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<false>, warps * 32, smem);
+                    if (e != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
+                    if (per_sm * warps > best) { best = per_sm * warps; pc.spc = spc; pc.warps = warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, spc, pc.tile_q, warps, lreads); }
                 }
-                if (per_sm * warps > best) { best = per_sm * warps; pc.spc = spc; pc.warps = warps; pc.smem = smem; }
             }
-        }
-        if (c->pile_spc > 0 && c->pile_warps > 0) {                      // POPBAM_B200_PILE=spc,warps (measurements)
-            const size_t smem = pb_pile_reads_smem(n, c->pile_spc, pc.halo, pc.tile_q, c->pile_warps);
-            if (32 * c->pile_spc >= pc.halo && smem <= c->smem_optin) { pc.spc = c->pile_spc; pc.warps = c->pile_warps; pc.smem = smem; }
+            if (c->pile_spc > 0 && c->pile_warps > 0) {                      // POPBAM_B200_PILE=spc,warps (measurements)
+                const int qcap = std::max(128, std::min(4096, ((int)(0.2 * 32.0 * c->pile_spc * pc.dens16 / 16.0) + 63) & ~63));
+                const int lreads = 0;
+                const size_t smem = pb_pile_reads_smem(n, c->pile_spc, pc.halo, pc.tile_q, c->pile_warps, qcap, lreads);
+                if (32 * c->pile_spc >= pc.halo && smem <= c->smem_optin) { pc.spc = c->pile_spc; pc.warps = c->pile_warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, c->pile_spc, pc.tile_q, c->pile_warps, lreads); }
+            }
+            pc.robust = c->qual_robust;
+            c->pile_shape = pc;
         }
     }
     const bool fast = fast_try && !cap && pc.spc > 0;
@@ -447,13 +460,14 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         fa.cigar = dp<uint32_t>(c->d_cigar); fa.base = dp<uint64_t>(c->d_base); fa.n_reads = N; fa.n_bytes = (uint64_t)c->n_bytes;
         fa.qual = dp<uint8_t>(c->d_qual); fa.seq4 = dp<uint8_t>(c->d_seq4);
         fa.refcode = dp<uint32_t>(c->d_refcode); fa.span_beg = c->span_beg; fa.span_end = c->span_end;
-        fa.n_samples = n; fa.n_strips = n_strips; fa.spc = pc.spc; fa.halo = pc.halo; fa.asw = pb_pile_asw(pc.spc, pc.halo); fa.tile_q = pc.tile_q;
+        fa.n_samples = n; fa.n_strips = n_strips; fa.spc = pc.spc; fa.halo = pc.halo; fa.asw = pb_pile_asw(pc.spc, pc.halo); fa.tile_q = pc.tile_q; fa.qcap = pc.qcap; fa.tail_bytes = pc.tail;
         fa.min_mapQ = P.min_mapQ; fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
         fa.qual_ceiling = c->qual_ceiling;
         fa.ctr = ctr; fa.tab = dp<PbFastTables>(c->d_fastp);
         fa.acc_cov = dp<uint64_t>(c->d_acc); fa.acc_cnt4 = reinterpret_cast<uint32_t *>(fa.acc_cov + span); fa.site_type = dp<uint64_t>(c->d_site_type);
-        fa.cells = dp<uint4>(c->d_cells); fa.codes = dp<uint16_t>(c->d_codes16); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
         const unsigned n_blocks = (unsigned)((n_strips + pc.spc - 1) / pc.spc);
+        PB_TRY(dev_reserve(c, c->d_blk, sizeof(uint4) * (size_t)n_blocks));
+        fa.blk = dp<uint4>(c->d_blk); fa.cells = dp<uint4>(c->d_cells); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
         const size_t carry_words = (size_t)n_blocks * n * (size_t)pc.halo;
         PB_TRY(dev_reserve(c, c->d_carry, sizeof(uint32_t) * (carry_words + n_blocks)));
         fa.carry = dp<uint32_t>(c->d_carry); fa.carry_flag = fa.carry + carry_words;
@@ -461,20 +475,18 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         if (getenv("POPBAM_B200_DEBUG"))
             fprintf(stderr, "[popbam_b200] k_pile_reads: %u CTAs of %d warps, %d strips per CTA, halo %d, quality tile %d bytes, %zu bytes of shared memory\n",
                     n_blocks, pc.warps, pc.spc, pc.halo, pc.tile_q, pc.smem);
-        if (c->qual_robust) {
-            PB_CUDA(c, cudaFuncSetAttribute(k_pile_reads<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem));
-            k_pile_reads<true><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
-        } else {
-            PB_CUDA(c, cudaFuncSetAttribute(k_pile_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc.smem));
-            k_pile_reads<false><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
-        }
+        if (c->qual_robust) k_pile_reads<true><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
+        else k_pile_reads<false><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
         PbCellCodesArgs ca;
-        ca.pos = fa.pos; ca.meta = fa.meta; ca.cigstart = fa.cigstart; ca.ncig = fa.ncig; ca.cigar = fa.cigar; ca.base = fa.base; ca.n_reads = N;
-        ca.qual = fa.qual; ca.seq4 = fa.seq4; ca.min_mapQ = P.min_mapQ; ca.min_baseQ = P.min_baseQ; ca.illumina = illumina; ca.ctr = ctr;
-        ca.cells = fa.cells; ca.codes = fa.codes;
-        k_cell_codes<<<c->n_sms * 8, 256, 0, st>>>(ca);
+        ca.pos = fa.pos; ca.meta = fa.meta; ca.cigstart = fa.cigstart; ca.ncig = fa.ncig; ca.cigar = fa.cigar; ca.base = fa.base;
+        ca.qual = fa.qual; ca.seq4 = fa.seq4; ca.span_beg = c->span_beg; ca.n_samples = n; ca.spc = pc.spc;
+        ca.min_mapQ = P.min_mapQ; ca.min_baseQ = P.min_baseQ; ca.illumina = illumina; ca.ctr = ctr;
+        ca.blk = fa.blk; ca.cells = fa.cells; ca.codes = dp<uint16_t>(c->d_codes16);
+        // room for the reads that can cover a block, three times the region's average (then: the other path)
+        ca.lcap = std::min(std::min(65535, (int)((c->smem_optin - pb_cell_codes_smem(n, 0)) / 4) - 64), (int)(3.0 * (32.0 * pc.spc + pc.halo) * pc.dens16 / 16.0) + 256);
+        k_cell_codes<<<n_blocks, 256, pb_cell_codes_smem(n, ca.lcap), st>>>(ca);
         PbHardArgs ha;
-        ha.cells = fa.cells; ha.codes = fa.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
+        ha.cells = fa.cells; ha.codes = ca.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;
         ha.span_beg = pa.span_beg; ha.span_end = pa.span_end; ha.win_beg = pa.win_beg; ha.win_end = pa.win_end; ha.n_windows = NW;
         ha.n_samples = n; ha.n_strips = n_strips;
         ha.min_depth = pa.min_depth; ha.max_depth = pa.max_depth; ha.min_rmsQ = pa.min_rmsQ; ha.min_snpQ = pa.min_snpQ;
@@ -801,6 +813,14 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_hard_cells, PB_HARD_THREADS, pb_hard_smem()) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
             c->g_hard_cells = c->n_sms * per_sm;
         }
+    }
+    // (once per process would do: the attribute belongs to the function, not to the context)
+    c->smem_optin -= std::min<size_t>(c->smem_optin, 2048);              // (room for the kernels' static shared memory)
+    if (cudaFuncSetAttribute(k_pile_reads<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_pile_reads<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess ||
+        cudaFuncSetAttribute(k_cell_codes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_optin) != cudaSuccess) {
+        cudaGetLastError();
+        return bail(PB_ERR_CUDA, "cudaFuncSetAttribute(shared memory) failed", c);
     }
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
     if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);

@@ -42,6 +42,8 @@ struct PbPileReadsArgs {
     int halo;                                // positions behind the block the counters reach: max_span rounded up to 32, <= 32 * spc
     int asw;                                 // words between the four counter arrays of a sample: >= (32 * spc + halo) / 4 + 1
     int tile_q;                              // bytes of a warp's quality tile (multiple of 32); its packed-base tile: tile_q / 2 + 16
+    int tail_bytes;                          // shared memory from the tiles' start to the end (pb_pile_tail_bytes)
+    int qcap;                                // further aligned segments (reads with deletions ...) a CTA can queue for its last pass
     int min_mapQ, min_rmsQ, min_baseQ, illumina;
     int qual_ceiling;                        // largest (adjusted) quality of a stray base the one-stray-base rule of the tables covers
     PbCounters *ctr;
@@ -49,24 +51,35 @@ struct PbPileReadsArgs {
     uint64_t *acc_cov;                       // [span] out: samples whose cell is settled here and covered (k_hard_cells adds its cells)
     uint32_t *acc_cnt4;                      // [span] out: derived-base counts of the cells settled here (k_hard_cells adds its cells')
     uint64_t *site_type;                     // [span] out: derived-allele bits of the cells settled here (k_hard_cells adds its cells')
-    uint4 *cells;                            // out: directory of the cells left for k_hard_cells {pos, sample | k << 8, sum mapq^2, first code}
-    uint16_t *codes;                         // out: their base codes  q << 5 | strand << 4 | base  (popbam.cpp:279-284)
+    uint4 *blk;                              // out: per block {first directory entry, entries, first read that can cover the block, end of the block's reads}
+    uint4 *cells;                            // out: directory of the cells left for k_hard_cells {pos, sample | k << 8, -, first code}
     unsigned long long cell_cap, code_cap;
     uint32_t *carry;                         // [blocks][n_samples][4][halo / 4] what a CTA's reads add behind its block
     uint32_t *carry_flag;                    // [blocks] set once they are published (zeroed per region)
 };
 
 static inline int pb_pile_halo(int max_span) { return (max_span + 31) & ~31; }
+// in the tiles' place once the reads are counted: per-position masks, the classification queue, the hard-cell list (and its
+// code offsets), per-sample read lists for the hard cells' base codes (room for `reads` entries), per-warp scratch
+__host__ __device__ static inline int pb_pile_hcap(int n_samples, int spc) { return n_samples * 32 * spc; }      // (every cell may end up in the list)
+__host__ __device__ static inline size_t pb_pile_tail_smem(int n_samples, int spc, int warps, int reads = 0) {
+    return (size_t)20 * 32 * spc + ((((size_t)n_samples * 8 * spc) + 1) & ~(size_t)1) * 2 + (4 + (size_t)1 / 8) * (size_t)pb_pile_hcap(n_samples, spc) + (size_t)pb_pile_hcap(n_samples, spc) / 8 + 8 + (2 * (size_t)n_samples + 1) * 4 +
+           256 * (size_t)warps + 4 * (size_t)reads + 64;
+}
 static inline int pb_pile_asw(int spc, int halo) { return (32 * spc + halo) / 4 + 1; }
 // dynamic shared memory: counters, reference nibbles (two copies), tables, barriers, per-warp tiles (16 bytes of
 // padding around each)
-static inline size_t pb_pile_reads_smem(int n_samples, int spc, int halo, int tile_q, int warps) {
+static inline size_t pb_pile_reads_smem(int n_samples, int spc, int halo, int tile_q, int warps, int qcap, int list_reads) {
     const size_t cnt = (size_t)n_samples * (4 * (size_t)pb_pile_asw(spc, halo) + 1) * 4;
-    const size_t rc = (2 * ((size_t)(32 * spc + halo) / 8 + 2) + (size_t)(32 * spc + halo) / 32 + 2) * 4 + 32;
+    const size_t rc = 2 * ((size_t)(32 * spc + halo) / 8 + 2) * 4 + 32;
     const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32);
-    // ... and, in the tiles' place once the reads are counted: per-position masks, the classification queue, the hard-cell list
-    const size_t scan = (size_t)20 * 32 * spc + ((((size_t)n_samples * 8 * spc) + 1) & ~(size_t)1) * 2 + 8 * 1024;
-    return ((cnt + 15) & ~(size_t)15) + rc + 800 + 16 * (size_t)warps + 16 * 256 + (tiles > scan ? tiles : scan) + 64;
+    const size_t scan = pb_pile_tail_smem(n_samples, spc, warps, list_reads);
+    return ((cnt + 15) & ~(size_t)15) + rc + 800 + 16 * (size_t)warps + 16 * (size_t)qcap + (tiles > scan ? tiles : scan) + 64;
+}
+
+static inline size_t pb_pile_tail_bytes(int n_samples, int spc, int tile_q, int warps, int list_reads) {
+    const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32), scan = pb_pile_tail_smem(n_samples, spc, warps, list_reads);
+    return tiles > scan ? tiles : scan;
 }
 
 __device__ __forceinline__ uint32_t pb_smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -268,7 +281,6 @@ __device__ __forceinline__ long long pb_warp_lower_bound(const int32_t *__restri
     return ge ? lo + (__ffs((int)ge) - 1) : hi;
 }
 
-#define PB_PILE_QCAP 256           // extra segments (reads with deletions ...) a CTA queues for its last pass
 
 // ROBUST: quality bytes >= 128 were seen in this context (a BAM without qualities stores 0xff), so the packed threshold
 // tests use the form that is right for any byte value.
@@ -294,12 +306,10 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     const int NRW = PH / 8 + 2;                                            // words of reference nibbles (eight positions each)
     uint32_t *refA = reinterpret_cast<uint32_t *>(smem_raw + cnt_bytes);  // [NRW] position 8 i of the block in bits 0-3 of word i
     uint32_t *refB = refA + NRW;                                          // [NRW] the same stream 16 bits (one position word) further on
-    int *sfirst = reinterpret_cast<int *>(refB + NRW);                    // [PH / 32 + 2] first read (relative to the block's first) that starts in a strip or behind it
-    const int NSF = PH / 32 + 2;
-    uint8_t *tabS = smem_raw + ((cnt_bytes + ((size_t)2 * NRW + NSF) * 4 + 15) & ~(size_t)15);     // PbFastTables
+    uint8_t *tabS = smem_raw + ((cnt_bytes + (size_t)2 * NRW * 4 + 15) & ~(size_t)15);     // PbFastTables
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tabS + 800);     // one per warp
-    int4 *queue = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(mbar) + 16 * (size_t)NWARP);       // [PB_PILE_QCAP] {sx0, offset lo, len | offset hi << 16 | sample << 24, mapq}
-    unsigned char *tiles = reinterpret_cast<unsigned char *>(queue + PB_PILE_QCAP);
+    int4 *queue = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(mbar) + 16 * (size_t)NWARP);       // [qcap] {sx0, offset lo, len | offset hi << 16 | sample << 24, mapq}
+    unsigned char *tiles = reinterpret_cast<unsigned char *>(queue + a.qcap);
     const int tile_s = a.tile_q / 2 + 16;
     const size_t tile_bytes = (size_t)a.tile_q + 32 + (size_t)tile_s + 32;
     const int t0s = (int)blockIdx.x * a.spc;                                    // first strip of the block
@@ -307,18 +317,18 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     // the block's reads: pos in [p0, p0 + PB) -- one contiguous run of the sorted batch; the first block also takes the reads
     // that start before the span.  Two warps look the ends up while the others clear the counters.
     if (wid == 0) {
-        const long long rlo = blockIdx.x > 0 ? pb_warp_lower_bound(a.pos, a.n_reads, p0, lane) : 0;
+        // (the first block also takes the reads that start before the span and can reach it)
+        const long long rlo = pb_warp_lower_bound(a.pos, a.n_reads, blockIdx.x > 0 ? p0 : p0 - max_span + 1, lane);
         if (lane == 0) { s_range[0] = rlo; s_next = 0; s_qn = 0; s_nh = 0; s_nc = 0; }
     } else if (wid == 1) {
         const long long rhi = pb_warp_lower_bound(a.pos, a.n_reads, p0 + PB, lane);
         if (lane == 0) s_range[1] = rhi;
     } else if (wid == 2) {
         // first read that can cover a position of the block (for the hard cells' base codes)
-        const long long rb = blockIdx.x > 0 ? pb_warp_lower_bound(a.pos, a.n_reads, p0 - max_span + 1, lane) : 0;
+        const long long rb = pb_warp_lower_bound(a.pos, a.n_reads, p0 - max_span + 1, lane);
         if (lane == 0) s_rback = rb;
     }
     for (int i = tid; i < (int)(cnt_bytes / 16); i += NT) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < NSF; i += NT) sfirst[i] = 0x7fffffff;
     for (int i = tid; i < NRW; i += NT) {
         // k_ref_codes packs by absolute position; the block starts at p0 (padded behind the contig)
         const uint32_t *g = a.refcode + ((int64_t)p0 >> 3) + i;
@@ -360,10 +370,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         const int cnt_l = min(32, n_blk - ch);
         const int64_t r = rlo + ch + lane;
         uint64_t b0 = 0, b1 = 0;
-        if (lane < cnt_l) {
-            b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes;
-            atomicMin(&sfirst[max(0, __ldg(a.pos + r) - p0) >> 5], ch + lane);
-        }
+        if (lane < cnt_l) { b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes; }
         bool give_up = false;
         for (int start = 0; start < cnt_l;) {
             const uint64_t tq0 = __shfl_sync(0xffffffffu, b0, start) & ~(uint64_t)15;                // first byte of the quality tile
@@ -405,8 +412,8 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
                                 if (!slen) { sx0 = x; so = qo; slen = (int)len; }
                                 else if (x < p0 + PH && x + (int)len > p0) {
                                     const int qi = atomicAdd(&s_qn, 1);
-                                    if (qi < PB_PILE_QCAP) queue[qi] = make_int4(x, (int)(uint32_t)qo, (int)(len | (uint32_t)(qo >> 32) << 16 | smp << 24), mq);
-                                    else a.ctr->spec_fail = 1;                                       // (more such segments than the queue holds: the host takes the other path)
+                                    if (qi < a.qcap) queue[qi] = make_int4(x, (int)(uint32_t)qo, (int)(len | (uint32_t)(qo >> 32) << 16 | smp << 24), mq);
+                                    else a.ctr->spec_fail = 1;                                       // (more such segments than the queue holds -- it is sized for a fifth of the block's reads: the host takes the other path)
                                 }
                             }
                             x += (int)len; qo += len;
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     __syncthreads();
     // ---- the queued segments, one per thread, bases straight from global memory (a few per cent of the reads)
     {
-        const int nq = min(s_qn, PB_PILE_QCAP);
+        const int nq = min(s_qn, a.qcap);
         for (int i = tid; i < nq; i += NT) {
             const int4 e = queue[i];
             const uint32_t z = (uint32_t)e.z;
@@ -476,24 +483,26 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     uint32_t *dcntS = derS + 2 * PB;                                           // [PB] derived-base counts (one byte per base)
     uint16_t *cq = reinterpret_cast<uint16_t *>(dcntS + PB);                   // [n * PB / 4] queued pairs: word | sample << 9
     uint32_t *hlist = reinterpret_cast<uint32_t *>(cq + (((size_t)n * (PB / 4) + 1) & ~(size_t)1));     // [hcap] cells left for k_hard_cells: k | position of the block << 8 | sample << 20
-    const size_t region = max((size_t)NWARP * tile_bytes, (size_t)20 * PB + (((size_t)n * (PB / 4) + 1) & ~(size_t)1) * 2 + 8 * 1024);     // (pb_pile_reads_smem)
-    const int hcap = (int)((region - (size_t)20 * PB - (((size_t)n * (PB / 4) + 1) & ~(size_t)1) * 2) / 8);
-    uint32_t *hoff = hlist + hcap;                                             // [hcap] first code of the cell, relative to the CTA's reservation
+    const int hcap = pb_pile_hcap(n, a.spc);
+    uint32_t *hoff = hlist + hcap;                                             // [hcap / 32 + 1] first code of every 32nd cell, relative to the CTA's reservation
+
     const PbFastTables *T = reinterpret_cast<const PbFastTables *>(tabS);
-    if (tid == 0) {
-        // strips without a read of their own: the next strip's first read
-        int nxt = n_blk;
-        for (int i = NSF - 1; i >= 0; --i) { nxt = min(nxt, sfirst[i]); sfirst[i] = nxt; }
-    }
     {
-        const uint32_t addLo = (uint32_t)(128 - T->klo) * 0x01010101u, addHi = (uint32_t)(127 - T->khi) * 0x01010101u;
+        // bit 7 of (x + (128 - t)) says x >= t for bytes below 128: three depth runs, the count of high-quality bases in two of them
+        uint32_t aLo[3], aHi[3], aH[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            aLo[r] = (uint32_t)(128 - T->rlo[r]) * 0x01010101u; aHi[r] = (uint32_t)(127 - T->rhi[r]) * 0x01010101u;
+            aH[r] = (uint32_t)(128 - T->rh[r]) * 0x01010101u;
+        }
         for (int w = tid; w < PB / 4; w += NT) {
             const bool whole = p0 + 4 * w + 3 < p1;                            // the word's positions all inside the span
             unsigned long long cov = 0;
             for (int s = 0; s < n; ++s) {
                 const uint32_t *rw = cnt + (size_t)s * RW + w;
-                const uint32_t K4 = rw[0], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
-                if (whole && !(M4 | F4) && (((K4 + addLo) & ~(K4 + addHi) & ~K4 & 0x80808080u) == 0x80808080u)) cov |= 1ULL << s;
+                const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
+                const uint32_t ok = ((K4 + aLo[0]) & ~(K4 + aHi[0])) | ((K4 + aLo[1]) & ~(K4 + aHi[1]) & (H4 + aH[1])) | ((K4 + aLo[2]) & ~(K4 + aHi[2]) & (H4 + aH[2]));
+                if (whole && !(M4 | F4) && ((ok & ~K4 & 0x80808080u) == 0x80808080u)) cov |= 1ULL << s;
                 else if (K4) cq[atomicAdd(&s_nc, 1)] = (uint16_t)(w | s << 9);
             }
 #pragma unroll
@@ -552,36 +561,36 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
             a.acc_cnt4[o] = dcntS[q];
             a.site_type[o] = (unsigned long long)derS[2 * q + 1] << 32 | derS[2 * q];
         }
-    // ---- the cells left over: a directory entry each {position, sample | k << 8, first read that can cover it, first code};
-    // k_cell_codes collects their base codes
+    // ---- the cells left over: a directory entry each {position, sample | k << 8, -, first code} and a record of the block's
+    // run of the directory; k_cell_codes collects their base codes
     const int nh = s_nh;
+    if (tid == 0) a.blk[blockIdx.x] = make_uint4(0u, 0u, 0u, 0u);
     if (nh == 0) return;
-    if (nh > hcap) { if (tid == 0) a.ctr->arena_overflow = 1; return; }          // (more than the list holds: the host gives up on this path for the region)
     if (wid == 0) {
         uint32_t run = 0;
         for (int i0 = 0; i0 < nh; i0 += 32) {
             const int i = i0 + lane;
-            const uint32_t k = i < nh ? (hlist[i] & 0xffu) : 0u;
-            uint32_t x = k;
+            uint32_t x = i < nh ? (hlist[i] & 0xffu) : 0u;
             for (int o2 = 1; o2 < 32; o2 <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o2); if (lane >= o2) x += y; }
-            if (i < nh) hoff[i] = run + x - k;
+            if (lane == 0) hoff[i0 >> 5] = run;
             run += __shfl_sync(0xffffffffu, x, 31);
         }
         if (lane == 0) {
             unsigned long long cb = atomicAdd(&a.ctr->n_cells, (unsigned long long)nh);
             const unsigned long long kb = atomicAdd(&a.ctr->n_codes, (unsigned long long)run);
             if (cb + nh > a.cell_cap || kb + run > a.code_cap) { a.ctr->arena_overflow = 1; cb = ~0ULL; }
+            else a.blk[blockIdx.x] = make_uint4((uint32_t)cb, (uint32_t)nh, (uint32_t)s_rback, (uint32_t)s_range[1]);
             s_resv[0] = cb; s_resv[1] = kb;
         }
     }
     __syncthreads();
     if (s_resv[0] == ~0ULL) return;                                             // no room: the host runs the region again with a larger arena
-    const long long rback = s_rback;
-    for (int i = tid; i < nh; i += NT) {
-        const uint32_t e = hlist[i];
-        const int q = (int)((e >> 8) & 0xfffu), ws = p0 + q - max_span + 1;     // the covering reads start at ws or behind
-        const long long clo = ws < p0 ? rback : rlo + sfirst[(ws - p0) >> 5];
-        a.cells[s_resv[0] + i] = make_uint4((uint32_t)(p0 + q), (e >> 20) | (e & 0xffu) << 8, (uint32_t)clo, (uint32_t)(s_resv[1] + hoff[i]));
+    for (int g = wid; 32 * g < nh; g += NWARP) {
+        const int i = 32 * g + lane;
+        const uint32_t e = i < nh ? hlist[i] : 0u, k = e & 0xffu;
+        uint32_t x = k;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o2); if (lane >= o2) x += y; }
+        if (i < nh) a.cells[s_resv[0] + i] = make_uint4((uint32_t)(p0 + (int)((e >> 8) & 0xfffu)), (e >> 20) | k << 8, 0u, (uint32_t)(s_resv[1] + hoff[g] + x - k));
     }
 }
 
@@ -589,29 +598,72 @@ struct PbCellCodesArgs {
     const int32_t *pos;
     const uint32_t *meta, *cigstart, *ncig, *cigar;
     const uint64_t *base;
-    int64_t n_reads;
     const uint8_t *qual, *seq4;
+    int span_beg, n_samples, spc;
     int min_mapQ, min_baseQ, illumina;
-    const PbCounters *ctr;
-    uint4 *cells;                            // in: {position, sample | k << 8, first read to look at, first code}; out: .y = sample | codes found << 8, .z = sum of mapq^2
+    int lcap;                                // reads the shared-memory lists hold
+    PbCounters *ctr;
+    const uint4 *blk;                        // per block of k_pile_reads: {first directory entry, entries, first read that can cover the block, end of the block's reads}
+    uint4 *cells;                            // in: {position, sample | k << 8, -, first code}; out: .y = sample | codes found << 8, .z = sum of mapq^2
     uint16_t *codes;
 };
+static inline size_t pb_cell_codes_smem(int n_samples, int lcap) { return (2 * (size_t)n_samples + 2) * 4 + 8 * 64 * 4 + 4 * (size_t)lcap + 16; }
 
-// The base codes of the cells left for k_hard_cells, exactly as call_base forms them (popbam.cpp:268-284), one WARP per
-// cell: the reads that can cover the cell's position are a run of the sorted batch that starts at the read the directory
-// names; the lanes look at 32 of them at a time (sample, flag filter, mapping quality), the ones that qualify are
-// gathered in shared memory and handled 32 at a time (CIGAR walk to the position, filter, code).
+// The base codes of the cells left for k_hard_cells, exactly as call_base forms them (popbam.cpp:268-284).  One CTA per
+// block of k_pile_reads: the reads that can cover a position of the block -- a run of the sorted batch, fresh in L2 --
+// are listed per sample in shared memory with their start positions; a WARP takes a cell, scans its sample's list,
+// gathers the reads that start in (position - max_span, position] and handles them 32 at a time (CIGAR walk to the
+// position, base filter, code).
 __global__ void __launch_bounds__(256) k_cell_codes(const PbCellCodesArgs a) {
-    __shared__ uint32_t s_list[8][64];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.ctr->arena_overflow || a.ctr->spec_fail) return;
-    const unsigned long long total = a.ctr->n_cells;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint4 rec = a.blk[blockIdx.x];
+    const int nh = (int)rec.y;
+    if (nh == 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, n = a.n_samples;
     const int max_span = a.ctr->max_span;
-    uint32_t *list = s_list[wid];
-    for (unsigned long long c = (unsigned long long)blockIdx.x * 8 + wid; c < total; c += (unsigned long long)gridDim.x * 8) {
+    const int p0 = a.span_beg + (int)blockIdx.x * a.spc * 32;
+    const long long rback = (long long)rec.z, rend = (long long)rec.w;
+    int *cntS = reinterpret_cast<int *>(smem_raw);                             // [n + 1] reads per sample; then: their lists' starts
+    int *curS = cntS + n + 1;                                                  // [n] fill cursors of the lists
+    uint32_t *wlist = reinterpret_cast<uint32_t *>(curS + n + 1);              // [8][64] a warp's gathered reads
+    uint32_t *rlist = wlist + 64 * 8;                                          // [lcap] the lists: read (relative to rback) | (start - p0) << 16
+    __shared__ int s_bad;
+    for (int i = tid; i <= n; i += 256) cntS[i] = 0;
+    if (tid == 0) s_bad = (rend - rback > 0xffff) ? 1 : 0;
+    __syncthreads();
+    for (long long r = rback + tid; r < rend; r += 256) {
+        const uint32_t meta = __ldg(a.meta + r);
+        if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) atomicAdd(&cntS[meta & 0xffu], 1);
+    }
+    __syncthreads();
+    if (wid == 0) {
+        // starts of the samples' lists (n <= 64: two per lane)
+        const int c0 = lane < n ? cntS[lane] : 0, c1 = lane + 32 < n ? cntS[lane + 32] : 0;
+        int x0 = c0, x1 = c1;
+        for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y0 = __shfl_up_sync(0xffffffffu, x0, o2), y1 = __shfl_up_sync(0xffffffffu, x1, o2); if (lane >= o2) { x0 += y0; x1 += y1; } }
+        const int t0 = __shfl_sync(0xffffffffu, x0, 31), t1 = __shfl_sync(0xffffffffu, x1, 31);
+        __syncwarp();
+        if (lane < n) { cntS[lane] = x0 - c0; curS[lane] = x0 - c0; }
+        if (lane + 32 < n) { cntS[lane + 32] = t0 + x1 - c1; curS[lane + 32] = t0 + x1 - c1; }
+        if (lane == 0) { cntS[n] = t0 + t1; if (t0 + t1 > a.lcap) s_bad = 1; }
+    }
+    __syncthreads();
+    if (s_bad) { if (tid == 0) a.ctr->arena_overflow = 1; return; }            // (more reads than the lists hold: the host gives up on this path for the region)
+    for (long long r = rback + tid; r < rend; r += 256) {
+        const uint32_t meta = __ldg(a.meta + r);
+        if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) {
+            const int rel = max(-32768, __ldg(a.pos + r) - p0);                 // (a read that starts further back than that covers nothing here)
+            rlist[atomicAdd(&curS[meta & 0xffu], 1)] = (uint32_t)(r - rback) | (uint32_t)(uint16_t)(int16_t)rel << 16;
+        }
+    }
+    __syncthreads();
+    uint32_t *gl = wlist + 64 * wid;
+    for (int i = wid; i < nh; i += 8) {
+        const unsigned long long c = (unsigned long long)rec.x + i;
         const uint4 cell = a.cells[c];
-        const int pos = (int)cell.x, smp = (int)(cell.y & 0xffu);
-        const uint32_t k = cell.y >> 8;
+        const int pos = (int)cell.x, q = pos - p0, smp = (int)(cell.y & 0xffu);
+        const uint32_t k = (cell.y >> 8) & 0xffu;
         uint16_t *out = a.codes + cell.w;
         uint32_t kk = 0, n_acc = 0;
         int rmsq = 0;
@@ -621,7 +673,7 @@ __global__ void __launch_bounds__(256) k_cell_codes(const PbCellCodesArgs a) {
             uint32_t code = 0;
             int mq = 0;
             if ((uint32_t)lane < cnt) {
-                const int64_t r = (int64_t)list[lane];
+                const long long r = rback + (long long)(gl[lane] & 0xffffu);
                 const uint32_t meta = __ldg(a.meta + r);
                 mq = (int)((meta >> 8) & 0xffu);
                 int x = __ldg(a.pos + r);
@@ -646,27 +698,27 @@ __global__ void __launch_bounds__(256) k_cell_codes(const PbCellCodesArgs a) {
             }
             kk += (uint32_t)__popc(bal);
         };
-        for (int64_t jb = (int64_t)cell.z;; jb += 32) {
-            const int64_t r = jb + lane;
-            const int x = r < a.n_reads ? __ldg(a.pos + r) : 0x7fffffff;
+        for (int jb = cntS[smp]; jb < cntS[smp + 1]; jb += 32) {
+            const int j = jb + lane;
+            uint32_t ent = 0;
             bool acc = false;
-            if (x <= pos && x + max_span > pos) {
-                const uint32_t meta = __ldg(a.meta + r);
-                acc = (int)(meta & 0xffu) == smp && !((meta >> 16) & 0x704u) && (int)((meta >> 8) & 0xffu) >= a.min_mapQ;
+            if (j < cntS[smp + 1]) {
+                ent = rlist[j];
+                const int rel = (int)(int16_t)(uint16_t)(ent >> 16);
+                acc = rel <= q && rel + max_span > q;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-            if (acc) list[n_acc + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (uint32_t)r;
+            if (acc) gl[n_acc + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = ent;
             n_acc += (uint32_t)__popc(bal);
             __syncwarp();
             if (n_acc >= 32) {
                 take(32);
-                const uint32_t rest = n_acc - 32, moved = (uint32_t)lane < rest ? list[32 + lane] : 0u;
+                const uint32_t rest = n_acc - 32, moved = (uint32_t)lane < rest ? gl[32 + lane] : 0u;
                 __syncwarp();
-                if ((uint32_t)lane < rest) list[lane] = moved;
+                if ((uint32_t)lane < rest) gl[lane] = moved;
                 n_acc = rest;
                 __syncwarp();
             }
-            if (__ballot_sync(0xffffffffu, x > pos)) break;                     // sorted: no later read starts at or before the position
         }
         if (n_acc) take(n_acc);
         rmsq = __reduce_add_sync(0xffffffffu, rmsq);
