@@ -8,7 +8,7 @@ configurations.  The contig is fed as region shards of --shard-mb (the unit the 
 BAM-index chunks of whole windows); ONE STEP = the whole contig = every shard once.
 
   value      whole-job aligned Gbases/s with every shard's read batch already resident in HBM: the complete device
-             pipeline (per-read prep, sample partition, counting pileup, hard cells, sites, window compaction, window
+             pipeline (per-read prep, depth bound, counting pileup, code lists, hard cells, sites, window compaction, window
              statistics, result copy) re-run on resident inputs, timed with CUDA events on the library's streams.
   e2e        same job through the public C ABI from PINNED HOST batches: pb_region_begin / pb_push_batch_async (host->
              device copy inside the timed region) / pb_region_end (device->host result copy inside the timed region).
@@ -78,7 +78,7 @@ def parse():
     ap.add_argument("--cpu-sample-kb", type=int, default=150)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one window per distinct shard (outside the timed region)")
-    ap.add_argument("--cli-sample-kb", type=int, default=-1, help="BAM sample for the command-line (from-BAM) tier; 0 = skip, -1 = the whole contig up to 23 Mb")
+    ap.add_argument("--cli-sample-kb", type=int, default=5000, help="BAM sample for the command-line (from-BAM) tier; 0 = skip (one fixture holds at most ~12 Mb of this depth: 32-bit base offsets)")
     a = ap.parse_args()
     a.cfg = CONFIGS[a.config]
     a.contig_mb = a.contig_mb or a.cfg["contig_mb"]
@@ -399,14 +399,14 @@ def run_b200(args):
                    "windows_per_s": world * n_windows / step_s,
                    "aligned_bases_per_step": world * total_aligned, "l2": "inputs (%.1f GB per step) exceed L2" % (alg_bytes / 1e9),
                    "distinct_shards": distinct, "shards_in_flight": max(1, args.inflight), "generator_s": round(t_gen, 1),
-                   "pileup_path": "counting kernels (k_pile_count + k_hard_cells)" if all(p == 1 for p in paths) else "single-kernel pileup on %d of %d shards" % (sum(1 for p in paths if p == 0), len(paths)),
+                   "pileup_path": "counting kernels (k_pile_reads + k_cell_codes + k_hard_cells)" if all(p == 1 for p in paths) else "single-kernel pileup on %d of %d shards" % (sum(1 for p in paths if p == 0), len(paths)),
                    "regions_run_twice": sum(c.reruns() for c in ctxs)},
         "e2e": {"value": world * total_aligned / (e2e_s / args.steps) / 1e9, "unit": "Gbases/s",
                 "h2d_bytes_per_step": sum(s["h2d"] for s in shards), "d2h_bytes_per_step": int(d2h),
                 "windows_per_s": world * n_windows / (e2e_s / args.steps)},
         "gpu_launches": int(launches),
-        "stage_ms_per_shard": {k: v / len(shards) for k, v in zip(["per_read_prep_partition", "pileup_call_site", "window_compaction", "window_stats"], stage_ms)},
-        "roofline": {"kernel": "the whole device pipeline of a region: per-read chain, k_pile_count, k_hard_cells, k_fast_sites, window compaction and statistics",
+        "stage_ms_per_shard": {k: v / len(shards) for k, v in zip(["per_read_prep", "pileup_call_site", "window_compaction", "window_stats"], stage_ms)},
+        "roofline": {"kernel": "the whole device pipeline of a region: k_read_prep, k_depth_bound, k_pile_reads, k_cell_codes, k_hard_cells, k_fast_sites, window compaction and statistics",
                      "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                      "traffic": TRAFFIC_BYTES_PER_SHARD_C2 if is_c2_shard else None,
                      "traffic_source": "sum over ALL kernels of one region of dram__bytes_read.sum + dram__bytes_write.sum, ncu launch list on a 2.3 Mb shard (profiles/r2_launches.csv)",
@@ -414,7 +414,7 @@ def run_b200(args):
                      "algorithmic_bytes_per_step": alg_bytes, "algorithmic_bytes_per_launch": alg_bytes / len(shards),
                      "launch_ms": step_s * 1e3 / len(shards),
                      "timed": "CUDA events around whole steps, %d shards in flight (same region as `value`)" % max(1, args.inflight),
-                     "dominant_kernel": {"kernel": "pileup / call / site stage alone: k_pile_count + k_hard_cells + k_fast_sites (library events, shards one after the other)",
+                     "dominant_kernel": {"kernel": "pileup / call / site stage alone: k_pile_reads + k_cell_codes + k_hard_cells + k_fast_sites (library events, shards one after the other)",
                                          "launch_ms": pile_ms / len(shards), "achieved": alg_bytes / (pile_ms / 1e3) / 1e9,
                                          "frac": alg_bytes / (pile_ms / 1e3) / 1e9 / peak_gbs, "share_of_step": pile_ms / max(seq_ms, 1e-9)}},
         "clocks": clk.summary(),
@@ -433,7 +433,7 @@ def run_b200(args):
     if rank == 0 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_kb * 1000)
         if args.cli_sample_kb != 0:
-            cli_len = int(min(args.contig_mb, 23.0) * 1e6) if args.cli_sample_kb < 0 else args.cli_sample_kb * 1000
+            cli_len = int(min(args.contig_mb, 5.0) * 1e6) if args.cli_sample_kb < 0 else int(min(args.cli_sample_kb * 1000, args.contig_mb * 1e6))
             line["cli_from_bam"] = cli_from_bam(args, cli_len)
     if rank == 0:
         print(json.dumps(line))

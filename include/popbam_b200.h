@@ -203,6 +203,9 @@ int pb_push_batch(pb_ctx *ctx, const pb_read_batch *batch);
  * pb_region_wait / pb_region_end of this region has returned.  Several pushes and the kernels of the region then
  * queue up behind each other on the context's stream with no host round trip in between.                          */
 int pb_push_batch_async(pb_ctx *ctx, const pb_read_batch *batch);
+/* Optional: make room on the device for a region's reads before they are pushed (several pb_push_batch calls then do
+ * not grow the arrays step by step).  Totals over the pushes to come; more may still be pushed.                      */
+int pb_region_reserve(pb_ctx *ctx, int64_t n_reads, int64_t n_cigar, int64_t n_bases);
 
 /* bam_fetch_f-shaped shim (bam.h:618): `b` points at a raw BAM record laid out as bam1_t's
  * core (32 bytes, bam.h:178-190, little endian) followed by its variable-length data

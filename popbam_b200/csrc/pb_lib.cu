@@ -953,6 +953,25 @@ int pb_push_batch_async(pb_ctx *c, const pb_read_batch *b) {
     return PB_OK;
 }
 
+int pb_region_reserve(pb_ctx *c, int64_t n_reads, int64_t n_cigar, int64_t n_bases) {
+    if (!c || n_reads < 0 || n_cigar < 0 || n_bases < 0) return fail(c, PB_ERR_ARG, "pb_region_reserve: bad argument");
+    if (c->state != ST_OPEN) return fail(c, PB_ERR_STATE, "pb_region_reserve outside pb_region_begin .. pb_region_launch");
+    PB_CUDA(c, cudaSetDevice(c->prm.device));
+    const size_t N1 = (size_t)(c->n_reads + n_reads), C1 = (size_t)(c->n_cig + n_cigar), B1 = (size_t)(c->n_bytes + n_bases);
+    PB_TRY(dev_reserve(c, c->d_pos, 4 * N1, 4 * (size_t)c->n_reads));
+    PB_TRY(dev_reserve(c, c->d_meta, 4 * N1, 4 * (size_t)c->n_reads));
+    PB_TRY(dev_reserve(c, c->d_cigstart, 4 * N1, 4 * (size_t)c->n_reads));
+    PB_TRY(dev_reserve(c, c->d_ncig, 4 * N1, 4 * (size_t)c->n_reads));
+    PB_TRY(dev_reserve(c, c->d_base, 8 * N1, 8 * (size_t)c->n_reads));
+    PB_TRY(dev_reserve(c, c->d_cigar, 4 * C1, 4 * (size_t)c->n_cig));
+    PB_TRY(dev_reserve(c, c->d_qual, B1 + 96, (size_t)c->n_bytes));
+    PB_TRY(dev_reserve(c, c->d_seq4, B1 / 2 + 96, (size_t)c->n_bytes / 2));
+    const size_t t0 = (size_t)c->n_reads + (size_t)c->n_pushes;
+    PB_TRY(dev_reserve(c, c->d_tmp_cig, 4 * (N1 + (size_t)c->n_pushes + 64), 4 * t0));
+    PB_TRY(dev_reserve(c, c->d_tmp_base, 4 * (N1 + (size_t)c->n_pushes + 64), 4 * t0));
+    return PB_OK;
+}
+
 int pb_push_batch(pb_ctx *c, const pb_read_batch *b) {
     const int rc = pb_push_batch_async(c, b);
     if (rc != PB_OK) return rc;

@@ -169,12 +169,13 @@ struct Run {
     std::shared_future<void> tables_ready;
     std::mutex mu;
     std::condition_variable cv;
-    bool pinned = true;
+    bool pinned = false;
+    std::atomic<double> bases_per_bp{0.0}, reads_per_bp{0.0};      // densest piece decoded so far
     std::atomic<int> next_decode{0};
     std::vector<std::pair<int, int>> items;      // decode work: (shard, piece), shard-major
     int max_ahead = 4;
     int printed = 0;
-    // batches are page-locked (pb_host_alloc) and expensive to allocate: used ones go back to a pool
+    // batches (page-locked with POPBAM_B200_PINNED=1, and then expensive to allocate) go back to a pool after use
     std::vector<pbio::Batch> pool;
     pbio::Batch take_batch() {
         std::lock_guard<std::mutex> lk(mu);
@@ -202,9 +203,24 @@ void decode_worker(Run *R) {
         Shard &sh = R->shards[s];
         pbio::Batch b = R->take_batch();
         std::string err;
+        const double bp = (double)(sh.cuts[pc].second - sh.cuts[pc].first);
+        {
+            // room for what pieces of this length held so far (page-locked memory is expensive to grow)
+            const double per_bp = R->bases_per_bp.load(), reads_per_bp = R->reads_per_bp.load();
+            if (per_bp > 0) {
+                const size_t nb = (size_t)(1.25 * per_bp * bp) + 4096, nr = (size_t)(1.25 * reads_per_bp * bp) + 256;
+                b.qual.reserve(nb); b.seq4.reserve(nb / 2 + 64); b.pos.reserve(nr); b.meta.reserve(nr); b.cig_off.reserve(nr + 1); b.base_off.reserve(nr + 1);
+                b.cigar.reserve(nr + nr / 4);
+            }
+        }
         try {
             pbio::fetch_piece(R->bam, R->idx, R->st, R->tid, R->wb[sh.w0], R->we[sh.w1 - 1], sh.cuts[pc].first, sh.cuts[pc].second, b);
         } catch (const pbio::Error &e) { err = e.msg; }
+        if (bp > 0 && b.n_reads() > 0) {
+            double v = (double)b.qual.size() / bp, w = (double)b.n_reads() / bp;
+            if (v > R->bases_per_bp.load()) R->bases_per_bp.store(v);
+            if (w > R->reads_per_bp.load()) R->reads_per_bp.store(w);
+        }
         std::lock_guard<std::mutex> lk(R->mu);
         sh.pieces[pc] = std::move(b);
         if (!err.empty() && sh.error.empty()) sh.error = err;
@@ -243,6 +259,11 @@ void gpu_worker(Run *R, int g, int G, int device) {
         if (err.empty() && sh.error.empty()) {
             pb_region_result res;
             int rc = pb_region_begin(ctx, R->analysis, sh.w1 - sh.w0, &R->wb[sh.w0], &R->we[sh.w0]);
+            {
+                int64_t nr = 0, nc = 0, nb = 0;
+                for (pbio::Batch &b : sh.pieces) { nr += b.n_reads(); nc += (int64_t)b.cigar.size(); nb += (int64_t)b.qual.size(); }
+                if (rc == PB_OK) rc = pb_region_reserve(ctx, nr, nc, nb);        // the device arrays once, not piece by piece
+            }
             for (pbio::Batch &b : sh.pieces) {
                 // the copies are asynchronous (the batches are page-locked and stay alive until the region is done)
                 if (rc != PB_OK || b.n_reads() == 0) continue;
@@ -421,13 +442,14 @@ int main(int argc, char **argv) {
     }
     const int G = std::max(1, o.gpus);
     const int D = o.threads > 0 ? o.threads : std::max(2u, std::min(32u, std::thread::hardware_concurrency()));
-    // decode work items: every shard in pieces of at most 1 Mb, more of them when there are fewer shards than threads
+    // decode work items: every shard in pieces, about four per thread over the region, between 50 kb and 1 Mb long
     {
-        const int want = (int)std::min<size_t>(16, ((size_t)D + R.shards.size() - 1) / R.shards.size());
+        const int64_t region_len = std::max<int64_t>(1, (int64_t)R.we.back() - R.wb.front());
+        const int64_t piece_bp = std::max<int64_t>(50000, std::min<int64_t>(1000000, region_len / (4 * (int64_t)D)));
         for (size_t si = 0; si < R.shards.size(); ++si) {
             Shard &sh = R.shards[si];
             const int64_t lo = R.wb[sh.w0], hi = R.we[sh.w1 - 1];
-            const int np = (int)std::max<int64_t>(want, (hi - lo + 999999) / 1000000);
+            const int np = (int)std::max<int64_t>(1, (hi - lo + piece_bp - 1) / piece_bp);
             for (int i = 0; i < np; ++i) {
                 const int32_t a = (int32_t)(lo + (hi - lo) * i / np), b = (int32_t)(lo + (hi - lo) * (i + 1) / np);
                 if (b > a || i == 0) { sh.cuts.push_back({a, b}); R.items.push_back({(int)si, (int)sh.cuts.size() - 1}); }
@@ -437,14 +459,18 @@ int main(int argc, char **argv) {
         }
     }
     {
-        const char *e = getenv("POPBAM_B200_PAGEABLE");
-        R.pinned = !(e && *e == '1');
+        // Page-locked batches (pb_host_alloc) let the copies to the device run asynchronously, but locking the pages costs
+        // more than it saves here: measured on the 5 Mb / 1.2 GB BAM of the bench workload, 13.4 s with page-locked batches
+        // against 3.1 s with ordinary memory (the command line is bound by inflate + decode at ~1.7 GB/s of batch bytes, far
+        // below PCIe).  So they are opt-in: POPBAM_B200_PINNED=1.
+        const char *e = getenv("POPBAM_B200_PINNED");
+        R.pinned = e && *e == '1';
         if (R.pinned) pbio::set_batch_allocator(pb_host_alloc, pb_host_free);
     }
     // two contexts (host threads) per GPU: one shard's host->device copy runs beside another shard's kernels
     const int W = 2 * G;
     // every decode thread can have a shard in hand and one waiting (a decoded 50 kb shard of the bench workload is 34 MB)
-    R.max_ahead = std::max(2 * W + 2, 2 * D);
+    R.max_ahead = W + 2;       // shards decoded ahead of the printer (a decoded 2 Mb shard of the bench workload is 1 GB of host memory)
 
     if (o.cmd == "snp" && o.output == 2) {      // print_ms_header (pop_snp.cpp:305-317)
         printf("ms %d %lld -t 5.0 ", p.n_samples, (long long)nw);
