@@ -37,7 +37,7 @@ enum RegionState { ST_IDLE = 0, ST_OPEN = 1, ST_LAUNCHED = 2, ST_DONE = 3 };
 }  // namespace
 
 // launch shape of k_pile_reads and what it was chosen for
-struct PileShape { int spc = 0, warps = 0, tile_q = 0, halo = 0, qcap = 0, dens16 = 0, tail = 0; bool robust = false; size_t smem = 0; };
+struct PileShape { int spc = 0, warps = 0, tile_q = 0, span32 = 0, qcap = 0, dens16 = 0, tail = 0; bool robust = false; size_t smem = 0; };
 
 struct pb_ctx {
     pb_params prm;
@@ -70,7 +70,6 @@ struct pb_ctx {
     DevBuf d_fastp, d_acc;                      // counting path: PbFastTables, per-position accumulators
     DevBuf d_cells, d_codes16, d_need_raw, d_blk;      // cells left for k_hard_cells (directory, base codes), need_raw[64][256], per-block records of the directory
     DevBuf d_refcode;                           // reference code bytes of the contig (k_ref_codes)
-    DevBuf d_carry;                             // k_pile_reads: counts handed from a block to the next one, and their flags
     std::vector<DevBuf *> bufs;            // every device buffer of the context
     bool classic = false;                  // POPBAM_B200_PILEUP=classic: always k_pileup_call (A/B measurements)
     int qual_ceiling = 41;                 // largest quality of a stray base the one-stray-base rule covers (pb_fast.cuh; POPBAM_B200_QCEIL)
@@ -382,21 +381,20 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     PileShape pc;
     if (fast_try && !cap) {
         const int rb = std::max(c->ctr_host.max_read_bytes, 16);
-        pc.halo = std::max(32, pb_pile_halo(c->ctr_host.max_span));
+        pc.span32 = (std::max(c->ctr_host.max_span, 1) + 31) & ~31;         // reads of the block before reach that far into a block
         pc.tile_q = std::max(std::min((32 * rb + 32 + 31) & ~31, 8192 + 32), (rb + 16 + 31) & ~31);
         // reads per position of the span; a fifth of a block's reads may have a second aligned segment to queue
         pc.dens16 = (int)std::min<double>(1e6, 16.0 * (double)N / (double)std::max<int64_t>(span, 1)) + 1;
-        if (c->pile_shape.spc > 0 && c->pile_shape.halo == pc.halo && c->pile_shape.tile_q == pc.tile_q && c->pile_shape.dens16 >= pc.dens16 &&
+        if (c->pile_shape.spc > 0 && c->pile_shape.span32 == pc.span32 && c->pile_shape.tile_q == pc.tile_q && c->pile_shape.dens16 >= pc.dens16 &&
             c->pile_shape.dens16 <= 2 * pc.dens16 && c->pile_shape.robust == c->qual_robust)
             pc = c->pile_shape;                                            // the same question as for the region before
         else {
             int best = 0;
             for (int spc = 64; spc >= 1; spc >>= 1) {
-                if (32 * spc < pc.halo) break;
-                const int qcap = std::max(128, std::min(4096, ((int)(0.2 * 32.0 * spc * pc.dens16 / 16.0) + 63) & ~63));
+                const int qcap = std::max(128, std::min(4096, ((int)(0.2 * (32.0 * spc + pc.span32) * pc.dens16 / 16.0) + 63) & ~63));
                 for (int warps = 16; warps >= 4; warps >>= 1) {
                     const int lreads = 0;
-                    const size_t smem = pb_pile_reads_smem(n, spc, pc.halo, pc.tile_q, warps, qcap, lreads);
+                    const size_t smem = pb_pile_reads_smem(n, spc, pc.tile_q, warps, qcap, lreads);
                     if (smem > c->smem_optin) continue;
                     int per_sm = 0;
                     const cudaError_t e = c->qual_robust ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<true>, warps * 32, smem)
@@ -406,10 +404,10 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
                 }
             }
             if (c->pile_spc > 0 && c->pile_warps > 0) {                      // POPBAM_B200_PILE=spc,warps (measurements)
-                const int qcap = std::max(128, std::min(4096, ((int)(0.2 * 32.0 * c->pile_spc * pc.dens16 / 16.0) + 63) & ~63));
+                const int qcap = std::max(128, std::min(4096, ((int)(0.2 * (32.0 * c->pile_spc + pc.span32) * pc.dens16 / 16.0) + 63) & ~63));
                 const int lreads = 0;
-                const size_t smem = pb_pile_reads_smem(n, c->pile_spc, pc.halo, pc.tile_q, c->pile_warps, qcap, lreads);
-                if (32 * c->pile_spc >= pc.halo && smem <= c->smem_optin) { pc.spc = c->pile_spc; pc.warps = c->pile_warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, c->pile_spc, pc.tile_q, c->pile_warps, lreads); }
+                const size_t smem = pb_pile_reads_smem(n, c->pile_spc, pc.tile_q, c->pile_warps, qcap, lreads);
+                if (smem <= c->smem_optin) { pc.spc = c->pile_spc; pc.warps = c->pile_warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, c->pile_spc, pc.tile_q, c->pile_warps, lreads); }
             }
             pc.robust = c->qual_robust;
             c->pile_shape = pc;
@@ -460,7 +458,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         fa.cigar = dp<uint32_t>(c->d_cigar); fa.base = dp<uint64_t>(c->d_base); fa.n_reads = N; fa.n_bytes = (uint64_t)c->n_bytes;
         fa.qual = dp<uint8_t>(c->d_qual); fa.seq4 = dp<uint8_t>(c->d_seq4);
         fa.refcode = dp<uint32_t>(c->d_refcode); fa.span_beg = c->span_beg; fa.span_end = c->span_end;
-        fa.n_samples = n; fa.n_strips = n_strips; fa.spc = pc.spc; fa.halo = pc.halo; fa.asw = pb_pile_asw(pc.spc, pc.halo); fa.tile_q = pc.tile_q; fa.qcap = pc.qcap; fa.tail_bytes = pc.tail;
+        fa.n_samples = n; fa.n_strips = n_strips; fa.spc = pc.spc; fa.asw = pb_pile_asw(pc.spc); fa.tile_q = pc.tile_q; fa.qcap = pc.qcap; fa.tail_bytes = pc.tail;
         fa.min_mapQ = P.min_mapQ; fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
         fa.qual_ceiling = c->qual_ceiling;
         fa.ctr = ctr; fa.tab = dp<PbFastTables>(c->d_fastp);
@@ -468,13 +466,9 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         const unsigned n_blocks = (unsigned)((n_strips + pc.spc - 1) / pc.spc);
         PB_TRY(dev_reserve(c, c->d_blk, sizeof(uint4) * (size_t)n_blocks));
         fa.blk = dp<uint4>(c->d_blk); fa.cells = dp<uint4>(c->d_cells); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
-        const size_t carry_words = (size_t)n_blocks * n * (size_t)pc.halo;
-        PB_TRY(dev_reserve(c, c->d_carry, sizeof(uint32_t) * (carry_words + n_blocks)));
-        fa.carry = dp<uint32_t>(c->d_carry); fa.carry_flag = fa.carry + carry_words;
-        PB_CUDA(c, cudaMemsetAsync(fa.carry_flag, 0, sizeof(uint32_t) * (size_t)n_blocks, st));
         if (getenv("POPBAM_B200_DEBUG"))
-            fprintf(stderr, "[popbam_b200] k_pile_reads: %u CTAs of %d warps, %d strips per CTA, halo %d, quality tile %d bytes, %zu bytes of shared memory\n",
-                    n_blocks, pc.warps, pc.spc, pc.halo, pc.tile_q, pc.smem);
+            fprintf(stderr, "[popbam_b200] k_pile_reads: %u CTAs of %d warps, %d strips per CTA, quality tile %d bytes, %zu bytes of shared memory\n",
+                    n_blocks, pc.warps, pc.spc, pc.tile_q, pc.smem);
         if (c->qual_robust) k_pile_reads<true><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
         else k_pile_reads<false><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
         PbCellCodesArgs ca;
@@ -483,7 +477,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         ca.min_mapQ = P.min_mapQ; ca.min_baseQ = P.min_baseQ; ca.illumina = illumina; ca.ctr = ctr;
         ca.blk = fa.blk; ca.cells = fa.cells; ca.codes = dp<uint16_t>(c->d_codes16);
         // room for the reads that can cover a block, three times the region's average (then: the other path)
-        ca.lcap = std::min(std::min(65535, (int)((c->smem_optin - pb_cell_codes_smem(n, 0)) / 4) - 64), (int)(3.0 * (32.0 * pc.spc + pc.halo) * pc.dens16 / 16.0) + 256);
+        ca.lcap = std::min(std::min(65535, (int)((c->smem_optin - pb_cell_codes_smem(n, 0)) / 4) - 64), (int)(3.0 * (32.0 * pc.spc + pc.span32) * pc.dens16 / 16.0) + 256);
         k_cell_codes<<<n_blocks, 256, pb_cell_codes_smem(n, ca.lcap), st>>>(ca);
         PbHardArgs ha;
         ha.cells = fa.cells; ha.codes = ca.codes; ha.ref = pa.ref; ha.ref_len = pa.ref_len;

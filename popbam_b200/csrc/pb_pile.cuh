@@ -12,8 +12,8 @@
 //                  shared memory by two 1-D bulk copies (cp.async.bulk + mbarrier, issued by one lane) and every lane
 //                  then walks its own read: CIGAR -> aligned segments (resolve_cigar2, bam_pileup.c:90-221), four bases
 //                  per step with packed-byte arithmetic (below), counts added to the sample's byte counters with one
-//                  shared-memory reduction per counter and four positions.  The counters reach `halo` positions behind
-//                  the block; what lands there is handed to the next block's CTA through global memory.
+//                  shared-memory reduction per counter and four positions.  A read that starts in an earlier block and
+//                  reaches into this one is walked by this CTA as well (clipped to the block): no CTA waits for another.
 //                  Then one thread per position classifies the cells of all samples (easy / hard), writes the position's
 //                  coverage mask, and the hard cells get a directory entry and room for their base codes.
 //
@@ -39,8 +39,7 @@ struct PbPileReadsArgs {
     int span_beg, span_end;
     int n_samples, n_strips;
     int spc;                                 // strips of 32 positions per CTA
-    int halo;                                // positions behind the block the counters reach: max_span rounded up to 32, <= 32 * spc
-    int asw;                                 // words between the four counter arrays of a sample: >= (32 * spc + halo) / 4 + 1
+    int asw;                                 // words between the four counter arrays of a sample: 8 * spc + 1
     int tile_q;                              // bytes of a warp's quality tile (multiple of 32); its packed-base tile: tile_q / 2 + 16
     int tail_bytes;                          // shared memory from the tiles' start to the end (pb_pile_tail_bytes)
     int qcap;                                // further aligned segments (reads with deletions ...) a CTA can queue for its last pass
@@ -54,11 +53,8 @@ struct PbPileReadsArgs {
     uint4 *blk;                              // out: per block {first directory entry, entries, first read that can cover the block, end of the block's reads}
     uint4 *cells;                            // out: directory of the cells left for k_hard_cells {pos, sample | k << 8, -, first code}
     unsigned long long cell_cap, code_cap;
-    uint32_t *carry;                         // [blocks][n_samples][4][halo / 4] what a CTA's reads add behind its block
-    uint32_t *carry_flag;                    // [blocks] set once they are published (zeroed per region)
 };
 
-static inline int pb_pile_halo(int max_span) { return (max_span + 31) & ~31; }
 // in the tiles' place once the reads are counted: per-position masks, the classification queue, the hard-cell list (and its
 // code offsets), per-sample read lists for the hard cells' base codes (room for `reads` entries), per-warp scratch
 __host__ __device__ static inline int pb_pile_hcap(int n_samples, int spc) { return n_samples * 32 * spc; }      // (every cell may end up in the list)
@@ -66,12 +62,12 @@ __host__ __device__ static inline size_t pb_pile_tail_smem(int n_samples, int sp
     return (size_t)20 * 32 * spc + ((((size_t)n_samples * 8 * spc) + 1) & ~(size_t)1) * 2 + (4 + (size_t)1 / 8) * (size_t)pb_pile_hcap(n_samples, spc) + (size_t)pb_pile_hcap(n_samples, spc) / 8 + 8 + (2 * (size_t)n_samples + 1) * 4 +
            256 * (size_t)warps + 4 * (size_t)reads + 64;
 }
-static inline int pb_pile_asw(int spc, int halo) { return (32 * spc + halo) / 4 + 1; }
+static inline int pb_pile_asw(int spc) { return 8 * spc + 1; }
 // dynamic shared memory: counters, reference nibbles (two copies), tables, barriers, per-warp tiles (16 bytes of
 // padding around each)
-static inline size_t pb_pile_reads_smem(int n_samples, int spc, int halo, int tile_q, int warps, int qcap, int list_reads) {
-    const size_t cnt = (size_t)n_samples * (4 * (size_t)pb_pile_asw(spc, halo) + 1) * 4;
-    const size_t rc = 2 * ((size_t)(32 * spc + halo) / 8 + 2) * 4 + 32;
+static inline size_t pb_pile_reads_smem(int n_samples, int spc, int tile_q, int warps, int qcap, int list_reads) {
+    const size_t cnt = (size_t)n_samples * (4 * (size_t)pb_pile_asw(spc) + 1) * 4;
+    const size_t rc = 2 * ((size_t)(32 * spc) / 8 + 2) * 4 + 32;
     const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32);
     const size_t scan = pb_pile_tail_smem(n_samples, spc, warps, list_reads);
     return ((cnt + 15) & ~(size_t)15) + rc + 800 + 16 * (size_t)warps + 16 * (size_t)qcap + (tiles > scan ? tiles : scan) + 64;
@@ -294,16 +290,16 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     __shared__ long long s_rback;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = (int)blockDim.x, NWARP = NT >> 5;
     const int max_span = a.ctr->max_span;
-    if (!a.ctr->nocap || ((max_span + 31) & ~31) > a.halo) {          // launched on an assumption that does not hold: say so, do nothing
+    if (!a.ctr->nocap) {                                              // launched on an assumption that does not hold: say so, do nothing
         if (tid == 0) a.ctr->spec_fail = 1;
         return;
     }
     const int n = a.n_samples;
-    const int PB = a.spc * 32, PH = PB + a.halo;
+    const int PB = a.spc * 32;
     const int ASW = a.asw, RW = 4 * ASW + 1;                                // words: array stride, sample stride (odd: the samples' rows start in different banks)
     uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw);               // [n][K, H, M, F][ASW]: passing bases, those at or above the khi level, stray bases, flags (pb_count_stray)
     const size_t cnt_bytes = (((size_t)n * RW * 4) + 15) & ~(size_t)15;
-    const int NRW = PH / 8 + 2;                                            // words of reference nibbles (eight positions each)
+    const int NRW = PB / 8 + 2;                                            // words of reference nibbles (eight positions each)
     uint32_t *refA = reinterpret_cast<uint32_t *>(smem_raw + cnt_bytes);  // [NRW] position 8 i of the block in bits 0-3 of word i
     uint32_t *refB = refA + NRW;                                          // [NRW] the same stream 16 bits (one position word) further on
     uint8_t *tabS = smem_raw + ((cnt_bytes + (size_t)2 * NRW * 4 + 15) & ~(size_t)15);     // PbFastTables
@@ -314,19 +310,14 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     const size_t tile_bytes = (size_t)a.tile_q + 32 + (size_t)tile_s + 32;
     const int t0s = (int)blockIdx.x * a.spc;                                    // first strip of the block
     const int p0 = a.span_beg + t0s * 32, p1 = min(p0 + PB, a.span_end);
-    // the block's reads: pos in [p0, p0 + PB) -- one contiguous run of the sorted batch; the first block also takes the reads
-    // that start before the span.  Two warps look the ends up while the others clear the counters.
+    // the block's reads: every read that can reach a position of the block, i.e. starts in (p0 - max_span, p0 + PB) -- one
+    // contiguous run of the sorted batch.  Two warps look the ends up while the others clear the counters.
     if (wid == 0) {
-        // (the first block also takes the reads that start before the span and can reach it)
-        const long long rlo = pb_warp_lower_bound(a.pos, a.n_reads, blockIdx.x > 0 ? p0 : p0 - max_span + 1, lane);
-        if (lane == 0) { s_range[0] = rlo; s_next = 0; s_qn = 0; s_nh = 0; s_nc = 0; }
+        const long long rlo = pb_warp_lower_bound(a.pos, a.n_reads, p0 - max_span + 1, lane);
+        if (lane == 0) { s_range[0] = rlo; s_rback = rlo; s_next = 0; s_qn = 0; s_nh = 0; s_nc = 0; }
     } else if (wid == 1) {
         const long long rhi = pb_warp_lower_bound(a.pos, a.n_reads, p0 + PB, lane);
         if (lane == 0) s_range[1] = rhi;
-    } else if (wid == 2) {
-        // first read that can cover a position of the block (for the hard cells' base codes)
-        const long long rb = pb_warp_lower_bound(a.pos, a.n_reads, p0 - max_span + 1, lane);
-        if (lane == 0) s_rback = rb;
     }
     for (int i = tid; i < (int)(cnt_bytes / 16); i += NT) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NRW; i += NT) {
@@ -342,7 +333,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     PbScatter sc;
-    sc.cnt = cnt; sc.refA = refA; sc.refB = refB; sc.ASW = ASW; sc.RW = RW; sc.p0 = p0; sc.pend = p0 + PH; sc.min_rmsQ = a.min_rmsQ; sc.ctr = a.ctr;
+    sc.cnt = cnt; sc.refA = refA; sc.refB = refB; sc.ASW = ASW; sc.RW = RW; sc.p0 = p0; sc.pend = p0 + PB; sc.min_rmsQ = a.min_rmsQ; sc.ctr = a.ctr;
     {
         // raw quality byte thresholds (host: all <= 128): passing, khi level, above the ceiling of the one-stray-base rule
         const int qoff = a.illumina ? 31 : 0;
@@ -410,7 +401,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
                             if (qo + len > b1 || len > 0xffffu) { a.ctr->spec_fail = 1; break; }     // CIGAR longer than the read's bases (or a segment the queue entry cannot hold)
                             if (len) {
                                 if (!slen) { sx0 = x; so = qo; slen = (int)len; }
-                                else if (x < p0 + PH && x + (int)len > p0) {
+                                else if (x < p0 + PB && x + (int)len > p0) {
                                     const int qi = atomicAdd(&s_qn, 1);
                                     if (qi < a.qcap) queue[qi] = make_int4(x, (int)(uint32_t)qo, (int)(len | (uint32_t)(qo >> 32) << 16 | smp << 24), mq);
                                     else a.ctr->spec_fail = 1;                                       // (more such segments than the queue holds -- it is sized for a fifth of the block's reads: the host takes the other path)
@@ -443,37 +434,6 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         }
     }
     __syncthreads();                                                          // this CTA's reads are counted
-    {
-        // publish what they added behind the block, take what the previous block's reads added to the front of this one.
-        // The previous CTA has a lower block index, so it was scheduled no later than this one and does not wait for
-        // anything itself before it publishes: the wait below ends (decoupled look-back, as in a single-pass scan).
-        const int hw = a.halo / 4, per_blk = n * 4 * hw;
-        uint32_t *mine = a.carry + (size_t)blockIdx.x * per_blk;
-        for (int sa = wid; sa < 4 * n; sa += NWARP) {                         // (sample, array): one warp each
-            const uint32_t *src = cnt + (size_t)(sa >> 2) * RW + (sa & 3) * ASW + PB / 4;
-            for (int w = lane; w < hw; w += 32) mine[sa * hw + w] = src[w];
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            atomicExch(a.carry_flag + blockIdx.x, 1u);
-            if (blockIdx.x > 0) while (atomicAdd(a.carry_flag + (blockIdx.x - 1), 0u) == 0u) __nanosleep(20);
-            __threadfence();
-        }
-        __syncthreads();
-        if (blockIdx.x > 0) {
-            const uint32_t *prev = a.carry + (size_t)(blockIdx.x - 1) * per_blk;
-            for (int sa = wid; sa < 4 * n; sa += NWARP) {
-                uint32_t *dst = cnt + (size_t)(sa >> 2) * RW + (sa & 3) * ASW;
-                const bool flags = (sa & 3) == 3;
-                for (int w = lane; w < hw; w += 32) {
-                    const uint32_t v = __ldcg(prev + sa * hw + w);
-                    if (flags) dst[w] |= v; else dst[w] += v;                 // counts add byte-wise (no cell exceeds 255); flags or
-                }
-            }
-            __syncthreads();
-        }
-    }
     // ---- classify.  Pass 1, one thread per position word (four positions), all samples one after the other: four covered
     // homozygous-reference cells at once by two packed compares; the (word, sample) pairs that fail the test are queued.
     // Pass 2, one thread per queued pair: the cells one by one.  Pass 3: the positions' masks go to global memory.

@@ -166,9 +166,10 @@ def test_asynchronous_regions_equal_the_oracle_and_the_synchronous_run():
 
 
 def test_asynchronous_region_whose_assumptions_fail_is_run_again():
-    """Region 2 has longer reads than the context has seen (staging slots too small) and base qualities far above the
-    assumed ceiling; region 3 is deep enough for the raw-depth cap to bind.  The device reports each, the host runs the
-    region again (with the round trips), and the results still equal the oracle."""
+    """Region 2 has longer reads than the context has seen (a warp's tile then holds fewer of them: no failure) and base
+    qualities far above the ceiling of the one-stray-base rule (such cells go to k_hard_cells: no failure either);
+    region 3 is deep enough for the raw-depth cap to bind.  The device reports that, the host runs the region again
+    (with the round trips), and the results still equal the oracle."""
     a = pbtest.Fixture(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=20.0, snp_density=0.04, seed=91)
     b = pbtest.Fixture(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=20.0, read_len=150, snp_density=0.2, het_frac=0.4, edge_mode=1, seed=92)
     c = pbtest.Fixture(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=90.0, snp_density=0.04, seed=93)
@@ -187,7 +188,7 @@ def test_asynchronous_region_whose_assumptions_fail_is_run_again():
         assert_same(pbtest.result_arrays(ctx.res), pbtest.result_arrays(orc.res), NOSYNC)
         orc.close()
     assert paths == [1, 1, 0, 1], paths          # region 3 ends up in the single-kernel pileup (cap binds)
-    assert ctx.reruns() >= 2
+    assert ctx.reruns() >= 1
     # unsorted reads in asynchronous mode are still reported (bam_pileup.c:384-395)
     import ctypes as C
     from test_gpu_parity import _slice_batch
