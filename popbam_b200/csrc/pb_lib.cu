@@ -106,6 +106,9 @@ struct pb_ctx {
     // second stream: the per-read chain (prep, depth bound, sample partition, strip index) runs beside the per-base
     // chain (quality mask, encode, bit-planes); fk[] = fork / join events (no timing)
     cudaStream_t stream2 = nullptr;
+    // k_pile_reads runs on a stream of LOWER priority: the short, latency-bound kernels of other contexts' regions (their
+    // per-read chain, hard cells, sites, windows) are scheduled ahead of its remaining CTAs and run beside it
+    cudaStream_t stream_lo = nullptr;
     cudaEvent_t fk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t dbg[4] = {nullptr, nullptr, nullptr, nullptr};   // POPBAM_B200_DEBUG: timeline of the two prep chains
     float ms_prep = 0, ms_pileup = 0, ms_sites = 0, ms_stats = 0;
@@ -469,8 +472,12 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         if (getenv("POPBAM_B200_DEBUG"))
             fprintf(stderr, "[popbam_b200] k_pile_reads: %u CTAs of %d warps, %d strips per CTA, quality tile %d bytes, %zu bytes of shared memory\n",
                     n_blocks, pc.warps, pc.spc, pc.tile_q, pc.smem);
-        if (c->qual_robust) k_pile_reads<true><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
-        else k_pile_reads<false><<<n_blocks, pc.warps * 32, pc.smem, st>>>(fa);
+        PB_CUDA(c, cudaEventRecord(c->fk[3], st));
+        PB_CUDA(c, cudaStreamWaitEvent(c->stream_lo, c->fk[3], 0));
+        if (c->qual_robust) k_pile_reads<true><<<n_blocks, pc.warps * 32, pc.smem, c->stream_lo>>>(fa);
+        else k_pile_reads<false><<<n_blocks, pc.warps * 32, pc.smem, c->stream_lo>>>(fa);
+        PB_CUDA(c, cudaEventRecord(c->fk[4], c->stream_lo));
+        PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[4], 0));
         PbCellCodesArgs ca;
         ca.pos = fa.pos; ca.meta = fa.meta; ca.cigstart = fa.cigstart; ca.ncig = fa.ncig; ca.cigar = fa.cigar; ca.base = fa.base;
         ca.qual = fa.qual; ca.seq4 = fa.seq4; ca.span_beg = c->span_beg; ca.n_samples = n; ca.spc = pc.spc;
@@ -816,8 +823,13 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
         cudaGetLastError();
         return bail(PB_ERR_CUDA, "cudaFuncSetAttribute(shared memory) failed", c);
     }
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
-    if (cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
+    {
+        int least = 0, greatest = 0;
+        if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) { cudaGetLastError(); least = greatest = 0; }
+        if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
+        if (cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, greatest) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
+        if (cudaStreamCreateWithPriority(&c->stream_lo, cudaStreamNonBlocking, least) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaStreamCreate failed", c);
+    }
     for (auto &ev : c->ev)
         if (cudaEventCreate(&ev) != cudaSuccess) return bail(PB_ERR_CUDA, "cudaEventCreate failed", c);
     for (auto &ev : c->fk)
@@ -850,6 +862,7 @@ void pb_destroy(pb_ctx *c) {
     cudaSetDevice(c->prm.device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
+    if (c->stream_lo) cudaStreamSynchronize(c->stream_lo);
     for (DevBuf *b : c->bufs) if (b->p) { cudaFree(b->p); b->p = nullptr; b->cap = 0; }
     HostBuf *hb[] = {&c->h_ctr, &c->h_small, &c->h_seg, &c->h_span};
     for (HostBuf *b : hb) if (b->p) cudaFreeHost(b->p);
@@ -857,6 +870,7 @@ void pb_destroy(pb_ctx *c) {
     for (auto &ev : c->fk) if (ev) cudaEventDestroy(ev);
     for (auto &ev : c->dbg) if (ev) cudaEventDestroy(ev);
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream_lo) cudaStreamDestroy(c->stream_lo);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
