@@ -85,6 +85,7 @@ struct pb_ctx {
     int spec_span = 0;                     // largest reference span of a read seen so far
     int spec_read_bytes = 0;               // most bytes of qual[] one read takes, seen so far
     bool async_run = false;                // the last run_pipeline left its checks and the segregating-site copy to fill_result
+    int async_span = 0;                    // ... and assumed this largest read span
     bool no_async = false;                 // POPBAM_B200_SYNC=1: always take the host round trips (A/B measurements)
     int64_t seg_cap = 0;                   // device layout of the segregating-site arrays (async: sized by the span)
     DevBuf d_seg_type;     // arena of the segregating-site arrays (seg_layout)
@@ -351,21 +352,23 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     } else {
         PB_TRY(classic_levels());
     }
-    PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));                // join
+    // Asynchronous mode: the launch parameters the counting pileup needs from the device (largest read span, most bytes
+    // of a read, "the depth cap cannot bind") are taken from the context's earlier regions; the per-read chain then runs
+    // BESIDE k_pile_reads instead of in front of it, and fill_result compares what it found with what was assumed (and looks
+    // at the sorted / too-long flags) once the region is done.  No host round trip in the middle of the pipeline, so one
+    // context keeps a GPU busy.
+    const uint32_t sync_bits = PB_AN_SNP | PB_AN_LD_ZNS | PB_AN_LD_OMEGA;          // their buffers / grids are sized by the number of segregating sites
+    const bool async = allow_async && !c->no_async && fast_try && c->spec_valid && attempt == 0 && !(c->analyses & sync_bits) && !(P.flags & PB_FLAG_EMIT_CB);
+    c->async_run = async;
+    if (!async) PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));    // join
     if (!fast_try) PB_TRY(partition());
     PB_CUDA(c, cudaGetLastError());
     PB_TRY(host_reserve(c, c->h_ctr, 3 * sizeof(PbCounters) + 64));
     PB_CUDA(c, cudaEventRecord(c->ev[1], st));
-    // Asynchronous mode: the launch parameters the counting pileup needs from the device (largest read span, most bytes
-    // of a read, "the depth cap cannot bind") are taken from the context's earlier regions; k_pile_reads verifies them on the
-    // device, and fill_result looks at the verdict (and at the sorted / too-long flags) once the region is done.  No host
-    // round trip in the middle of the pipeline, so one context keeps a GPU busy.
-    const uint32_t sync_bits = PB_AN_SNP | PB_AN_LD_ZNS | PB_AN_LD_OMEGA;          // their buffers / grids are sized by the number of segregating sites
-    const bool async = allow_async && !c->no_async && fast_try && c->spec_valid && attempt == 0 && !(c->analyses & sync_bits) && !(P.flags & PB_FLAG_EMIT_CB);
-    c->async_run = async;
     if (async) {
         memset(&c->ctr_host, 0, sizeof c->ctr_host);
         c->ctr_host.max_span = c->spec_span; c->ctr_host.nocap = 1; c->ctr_host.max_read_bytes = c->spec_read_bytes;
+        c->async_span = c->spec_span;
     } else {
         PB_CUDA(c, cudaMemcpyAsync(c->h_ctr.p, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
         PB_CUDA(c, cudaStreamSynchronize(st));
@@ -462,6 +465,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         fa.qual = dp<uint8_t>(c->d_qual); fa.seq4 = dp<uint8_t>(c->d_seq4);
         fa.refcode = dp<uint32_t>(c->d_refcode); fa.span_beg = c->span_beg; fa.span_end = c->span_end;
         fa.n_samples = n; fa.n_strips = n_strips; fa.spc = pc.spc; fa.asw = pb_pile_asw(pc.spc); fa.tile_q = pc.tile_q; fa.qcap = pc.qcap; fa.tail_bytes = pc.tail;
+        fa.max_span = async ? c->async_span : 0;
         fa.min_mapQ = P.min_mapQ; fa.min_rmsQ = P.min_rmsQ; fa.min_baseQ = P.min_baseQ; fa.illumina = illumina;
         fa.qual_ceiling = c->qual_ceiling;
         fa.ctr = ctr; fa.tab = dp<PbFastTables>(c->d_fastp);
@@ -480,7 +484,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[4], 0));
         PbCellCodesArgs ca;
         ca.pos = fa.pos; ca.meta = fa.meta; ca.cigstart = fa.cigstart; ca.ncig = fa.ncig; ca.cigar = fa.cigar; ca.base = fa.base;
-        ca.qual = fa.qual; ca.seq4 = fa.seq4; ca.span_beg = c->span_beg; ca.n_samples = n; ca.spc = pc.spc;
+        ca.qual = fa.qual; ca.seq4 = fa.seq4; ca.span_beg = c->span_beg; ca.n_samples = n; ca.spc = pc.spc; ca.max_span = fa.max_span;
         ca.min_mapQ = P.min_mapQ; ca.min_baseQ = P.min_baseQ; ca.illumina = illumina; ca.ctr = ctr;
         ca.blk = fa.blk; ca.cells = fa.cells; ca.codes = dp<uint16_t>(c->d_codes16);
         // room for the reads that can cover a block, three times the region's average (then: the other path)
@@ -494,7 +498,6 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         ha.het_mode = pa.het_mode; ha.fk = pa.fk; ha.beta = pa.beta; ha.lhet = pa.lhet; ha.ctr = ctr; ha.need_raw = dp<uint8_t>(c->d_need_raw);
         ha.acc_cov = fa.acc_cov; ha.acc_cnt4 = fa.acc_cnt4;
         ha.site_type = pa.site_type; ha.site_flag = pa.site_flag;
-        PB_CUDA(c, cudaFuncSetAttribute(k_hard_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pb_hard_smem()));
         k_hard_cells<<<c->g_hard_cells, PB_HARD_THREADS, pb_hard_smem(), st>>>(ha);
         k_fast_sites<<<nblk(span, 256), 256, 0, st>>>(ha);
         c->launches += 4;
@@ -540,6 +543,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     const SmallLayout hl0 = small_layout(c->h_small.p, NW, P.n_pops, n, (c->analyses & PB_AN_TREE) != 0);
     PB_CUDA(c, cudaMemcpyAsync(hl0.segsites, dl.segsites, sizeof(int32_t) * (size_t)NW, cudaMemcpyDeviceToHost, st));
     PbCounters *h_final = reinterpret_cast<PbCounters *>(reinterpret_cast<unsigned char *>(c->h_ctr.p) + 2 * sizeof(PbCounters));
+    if (async) PB_CUDA(c, cudaStreamWaitEvent(st, c->fk[2], 0));     // the per-read chain that ran beside the pileup
     PB_CUDA(c, cudaMemcpyAsync(h_final, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
     if (!async) PB_CUDA(c, cudaStreamSynchronize(st));
     if (!async && fast && getenv("POPBAM_B200_DEBUG"))
@@ -681,7 +685,7 @@ int fill_result(pb_ctx *c, pb_region_result *out) {
         if (getenv("POPBAM_B200_DEBUG"))
             fprintf(stderr, "[popbam_b200] asynchronous region: %llu cells left for k_hard_cells, overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
                     fin.n_cells, fin.arena_overflow, fin.qual_over, fin.qual_max_seen, fin.spec_fail);
-        if (fin.arena_overflow || fin.qual_over || fin.spec_fail) {
+        if (fin.arena_overflow || fin.qual_over || fin.spec_fail || fin.max_span > c->async_span || !fin.nocap) {
             if (fin.qual_high) c->qual_robust = true;
             if (fin.arena_overflow) c->arena_scale *= 4;
             c->reruns += 1;

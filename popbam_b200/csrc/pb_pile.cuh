@@ -42,6 +42,8 @@ struct PbPileReadsArgs {
     int asw;                                 // words between the four counter arrays of a sample: 8 * spc + 1
     int tile_q;                              // bytes of a warp's quality tile (multiple of 32); its packed-base tile: tile_q / 2 + 16
     int tail_bytes;                          // shared memory from the tiles' start to the end (pb_pile_tail_bytes)
+    int max_span;                            // > 0: the largest read span ASSUMED (the per-read chain runs beside this kernel; the host compares afterwards, and
+                                             // likewise "the depth cap cannot bind"); 0: read both from the counters
     int qcap;                                // further aligned segments (reads with deletions ...) a CTA can queue for its last pass
     int min_mapQ, min_rmsQ, min_baseQ, illumina;
     int qual_ceiling;                        // largest (adjusted) quality of a stray base the one-stray-base rule of the tables covers
@@ -289,8 +291,8 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     __shared__ int s_next, s_qn, s_nh, s_nc;
     __shared__ long long s_rback;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = (int)blockDim.x, NWARP = NT >> 5;
-    const int max_span = a.ctr->max_span;
-    if (!a.ctr->nocap) {                                              // launched on an assumption that does not hold: say so, do nothing
+    const int max_span = a.max_span > 0 ? a.max_span : a.ctr->max_span;
+    if (a.max_span <= 0 && !a.ctr->nocap) {                           // launched on an assumption that does not hold: say so, do nothing
         if (tid == 0) a.ctr->spec_fail = 1;
         return;
     }
@@ -562,6 +564,7 @@ struct PbCellCodesArgs {
     int span_beg, n_samples, spc;
     int min_mapQ, min_baseQ, illumina;
     int lcap;                                // reads the shared-memory lists hold
+    int max_span;                            // as in PbPileReadsArgs
     PbCounters *ctr;
     const uint4 *blk;                        // per block of k_pile_reads: {first directory entry, entries, first read that can cover the block, end of the block's reads}
     uint4 *cells;                            // in: {position, sample | k << 8, -, first code}; out: .y = sample | codes found << 8, .z = sum of mapq^2
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(256) k_cell_codes(const PbCellCodesArgs a) {
     const int nh = (int)rec.y;
     if (nh == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, n = a.n_samples;
-    const int max_span = a.ctr->max_span;
+    const int max_span = a.max_span > 0 ? a.max_span : a.ctr->max_span;
     const int p0 = a.span_beg + (int)blockIdx.x * a.spc * 32;
     const long long rback = (long long)rec.z, rend = (long long)rec.w;
     int *cntS = reinterpret_cast<int *>(smem_raw);                             // [n + 1] reads per sample; then: their lists' starts
