@@ -313,7 +313,15 @@ int main(int argc, char **argv) {
             int tid, beg, end;
             if (!pbio::parse_region(hdr, argv[3], &tid, &beg, &end)) fatal(std::string("Bad genome coordinates: ") + argv[3]);
             pbio::Batch b;
-            pbio::fetch_region(bam, idx, st, tid, beg, end, b);
+            // popbam _fetch <in.bam> <region> <out.bin> [pieces]: with a piece count the region is fetched as that many
+            // pieces (pbio::fetch_piece), appended to one batch in order -- it must equal the single fetch
+            const int pieces = argc > 5 ? atoi(argv[5]) : 0;
+            if (pieces <= 0) pbio::fetch_region(bam, idx, st, tid, beg, end, b);
+            else
+                for (int i = 0; i < pieces; ++i) {
+                    const int32_t lo = (int32_t)(beg + (int64_t)(end - beg) * i / pieces), hi = (int32_t)(beg + (int64_t)(end - beg) * (i + 1) / pieces);
+                    if (hi > lo || i == 0) pbio::fetch_piece(bam, idx, st, tid, beg, end, lo, hi, b);
+                }
             FILE *f = fopen(argv[4], "wb");
             if (!f) return 2;
             const int64_t hdrv[6] = {b.n_reads(), (int64_t)b.cigar.size(), (int64_t)b.qual.size(), tid, beg, end};

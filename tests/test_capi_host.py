@@ -54,6 +54,30 @@ def test_errmod_tables_equal_reference(L):
     assert hashlib.sha256(fk.tobytes() + beta.tobytes() + lhet.tobytes()).hexdigest() == kat["sha256"]
 
 
+def test_errmod_tables_cache_on_disk(L, tmp_path):
+    """the tables through the cache -- computed and written the first time, read back the second time,
+    rebuilt when the file does not verify; always the reference's tables (sha256 of errmod_init's, kat_tables.json)."""
+    dp = C.POINTER(C.c_double)
+    kat = json.load(open(pbtest.GOLDEN / "kat_tables.json"))
+    d = str(tmp_path / "cache").encode()
+
+    def run():
+        fk = np.zeros(256); beta = np.zeros(64 * 65536); lhet = np.zeros(65536)
+        hit = C.c_int(-1)
+        assert L.pb_errmod_tables_cached_ex(fk.ctypes.data_as(dp), beta.ctypes.data_as(dp), lhet.ctypes.data_as(dp), d, C.byref(hit)) == 0
+        assert hashlib.sha256(fk.tobytes() + beta.tobytes() + lhet.tobytes()).hexdigest() == kat["sha256"]
+        return hit.value
+    assert run() == 0
+    files = list((tmp_path / "cache").glob("errmod-v1-*.bin"))
+    assert len(files) == 1 and files[0].stat().st_size == 24 + 8 * (256 + 64 * 65536 + 65536)
+    assert run() == 1
+    raw = bytearray(files[0].read_bytes())
+    raw[5000] ^= 0x40                                      # a flipped bit: the checksum does not verify, the tables are rebuilt
+    files[0].write_bytes(bytes(raw))
+    assert run() == 0
+    assert run() == 1
+
+
 def test_no_cpu_fallback(L):
     """Without a CUDA device pb_create must fail with PB_ERR_CUDA; with one, bad parameters are rejected."""
     import torch

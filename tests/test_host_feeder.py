@@ -71,6 +71,22 @@ def test_fetch_region_equals_generator_batch(tmp_path, fxname, region, beg, end)
         assert np.array_equal(got["seq4"][g0 // 2:g0 // 2 + (R + 1) // 2], seq[bo[i] // 2:bo[i] // 2 + (R + 1) // 2])
 
 
+@pytest.mark.parametrize("fxname,region,pieces", [("edge", "chr1", 7), ("edge", "chr1:5001-9000", 3), ("rg2", "chr1:12,001-20,500", 16),
+                                                   ("c1", "chr1:30000-30400", 5)])
+def test_fetch_in_pieces_equals_one_fetch(tmp_path, fxname, region, pieces):
+    """The command line decodes a region as several pieces on different threads (pbio::fetch_piece); appended in order
+    they must be the batch of the single bam_fetch (bam_index.c:943-957), byte for byte."""
+    popbam_b200.build()
+    fx = pbtest.fixture(fxname)
+    bam, fa = fx.write_files(tmp_path / fxname)
+    one, many = tmp_path / "one.bin", tmp_path / "many.bin"
+    for out, extra in ((one, []), (many, [str(pieces)])):
+        r = subprocess.run([str(EXE), "_fetch", bam, region, str(out)] + extra, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+    assert one.read_bytes() == many.read_bytes()
+    assert len(_load(one)["pos"]) > 0
+
+
 def test_cli_errors_without_gpu(tmp_path):
     popbam_b200.build()
     r = subprocess.run([str(EXE), "nucdiv", "-f", "nope.fa", str(tmp_path / "missing.bam"), "chr1"], stderr=subprocess.PIPE, text=True)
