@@ -395,7 +395,9 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
             c->pile_shape.dens16 <= 2 * pc.dens16 && c->pile_shape.robust == c->qual_robust)
             pc = c->pile_shape;                                            // the same question as for the region before
         else {
-            int best = 0;
+            // score: resident warps x the share of a block's reads that start in it (a read that reaches in from the block before
+            // is walked twice)
+            double best = 0;
             for (int spc = 64; spc >= 1; spc >>= 1) {
                 const int qcap = std::max(128, std::min(4096, ((int)(0.2 * (32.0 * spc + pc.span32) * pc.dens16 / 16.0) + 63) & ~63));
                 for (int warps = 16; warps >= 4; warps >>= 1) {
@@ -406,7 +408,8 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
                     const cudaError_t e = c->qual_robust ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<true>, warps * 32, smem)
                                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<false>, warps * 32, smem);
                     if (e != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
-                    if (per_sm * warps > best) { best = per_sm * warps; pc.spc = spc; pc.warps = warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, spc, pc.tile_q, warps, lreads); }
+                    const double score = (double)per_sm * warps * (32.0 * spc) / (32.0 * spc + c->ctr_host.max_span);
+                    if (score > best) { best = score; pc.spc = spc; pc.warps = warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, spc, pc.tile_q, warps, lreads); }
                 }
             }
             if (c->pile_spc > 0 && c->pile_warps > 0) {                      // POPBAM_B200_PILE=spc,warps (measurements)
