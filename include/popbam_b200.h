@@ -224,9 +224,9 @@ int pb_region_wait(pb_ctx *ctx, pb_region_result *out);
 /* Re-run the kernels on the reads already resident on the device (bench: kernel-only
  * timing with inputs in HBM).  Valid after pb_region_launch and before the next begin.    */
 int pb_region_relaunch(pb_ctx *ctx);
-/* Which formulation of the pileup stage the last region took: 1 = the bit-sliced kernels (the default), 0 = the
+/* Which formulation of the pileup stage the last region took: 1 = the counting pileup (k_pile_reads, the default), 0 = the
  * single-kernel pileup (per-cell words requested, min_depth / min_snpQ of 0, or the raw-depth cap can bind).
- * pb_region_reruns: how many regions of this context were run a second time because an assumption the bit-sliced
+ * pb_region_reruns: how many regions of this context were run a second time because an assumption the counting
  * kernels verify on the device (largest base quality, size of the hard-cell arena) did not hold.                */
 int pb_region_path(const pb_ctx *ctx);
 int pb_region_reruns(const pb_ctx *ctx);

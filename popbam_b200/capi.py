@@ -202,7 +202,7 @@ class Context:
         return self.L.pb_kernel_launches(self.h)
 
     def path(self):
-        """1: the last region took the bit-sliced pileup kernels, 0: the single-kernel pileup."""
+        """1: the last region took the counting pileup (k_pile_reads), 0: the single-kernel pileup."""
         return self.L.pb_region_path(self.h)
 
     def reruns(self):

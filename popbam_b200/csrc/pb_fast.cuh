@@ -172,7 +172,7 @@ struct PbLocalLevels {
     __device__ __forceinline__ int operator[](int L) const { return q[L]; }
 };
 
-// The cells the bit-sliced pass could not settle, one per THREAD, straight from the directory (consecutive threads
+// The cells the counts could not settle, one per THREAD, straight from the directory (consecutive threads
 // take consecutive cells: neighbouring positions of one sample, contiguous code runs).  A cell's codes are exactly
 // what call_base hands to errmod_cal, in no particular order -- errmod_cal sorts them, and the histogram walk of
 // pb_walk.cuh only needs the multiset.  The levels are ranked per cell (64-bit mask of the quality values present,

@@ -41,7 +41,7 @@ struct PbCounters {               // device-side region counters (one cudaMemcpy
     int nocap;                        // depth_bound <= max_depth: the raw-depth cap can never bind
     unsigned char qrank[64];          // quality value -> level
     unsigned char qval[64];           // level -> quality value (ascending)
-    // bit-sliced path (pb_fast.cuh): the cells it hands to k_hard_cells, and the assumptions it verified
+    // counting path (pb_pile.cuh): the cells it hands to k_hard_cells, and the assumptions it verified
     unsigned long long n_cells;       // directory entries written
     unsigned long long n_codes;       // base-code slots reserved in the arena
     int arena_overflow;               // the directory or the code arena was too small: results incomplete

@@ -77,9 +77,9 @@ struct pb_ctx {
     int arena_scale = 1;                   // cell arena size factor (raised on overflow)
     int pile_spc = 0, pile_warps = 0;      // POPBAM_B200_PILE=strips,warps: launch shape of k_pile_reads (measurements)
     bool need_raw_valid = false;
-    bool ran_fast = false;                 // the last pipeline run took the bit-sliced path
-    int force_classic = 0;                 // the bit-sliced path gave up on this region (arena overflow twice): k_pileup_call
-    int reruns = 0;                        // regions run again because an assumption of the bit-sliced path did not hold
+    bool ran_fast = false;                 // the last pipeline run took the counting path
+    int force_classic = 0;                 // the counting path gave up on this region (arena overflow twice): k_pileup_call
+    int reruns = 0;                        // regions run again because an assumption of the counting path did not hold
     // what a context has learnt from its earlier regions: with it a region is enqueued without a host round trip
     bool spec_valid = false;
     int spec_span = 0;                     // largest reference span of a read seen so far
@@ -515,7 +515,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         void (*kern)(const PbPileArgs) = big ? (cap ? k_pileup_call<256, true> : k_pileup_call<256, false>)
                                              : (cap ? k_pileup_call<128, true> : k_pileup_call<128, false>);
         PB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // base codes for k_pileup_call (the bit-sliced path reads qual[] / seq4[] directly)
+        // base codes for k_pileup_call (the counting path reads qual[] / seq4[] directly)
         PB_TRY(dev_reserve(c, c->d_codes, (size_t)std::max<int64_t>(c->n_bytes, 1)));
         pa.codes = dp<uint8_t>(c->d_codes);
         if (N > 0)
@@ -550,15 +550,15 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
     PB_CUDA(c, cudaMemcpyAsync(h_final, c->d_ctr.p, sizeof(PbCounters), cudaMemcpyDeviceToHost, st));
     if (!async) PB_CUDA(c, cudaStreamSynchronize(st));
     if (!async && fast && getenv("POPBAM_B200_DEBUG"))
-        fprintf(stderr, "[popbam_b200] bit-sliced path: %llu of %lld cells left for k_hard_cells (%.2f %%), %llu code slots; overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
+        fprintf(stderr, "[popbam_b200] counting path: %llu of %lld cells left for k_hard_cells (%.2f %%), %llu code slots; overflow %d, quality over ceiling %d (max %d), launch assumptions failed %d\n",
                 h_final->n_cells, (long long)(span * n), 100.0 * (double)h_final->n_cells / (double)(span * n), h_final->n_codes,
                 h_final->arena_overflow, h_final->qual_over, h_final->qual_max_seen, h_final->spec_fail);
     if (!async && fast && (h_final->arena_overflow || h_final->qual_over || h_final->spec_fail)) {
-        // an assumption of the bit-sliced path did not hold for this region: nothing of its result is used.  Raise the
+        // an assumption of the counting path did not hold for this region: nothing of its result is used.  Raise the
         // quality ceiling / the arena size (both stay raised for the context) and run the region again; give up on the
-        // bit-sliced path for this region after three attempts.
+        // counting path for this region after three attempts.
         if (getenv("POPBAM_B200_DEBUG"))
-            fprintf(stderr, "[popbam_b200] bit-sliced path: run again (arena overflow %d: %llu cells, %llu codes; quality %d above ceiling %d: %d; launch assumptions %d)\n",
+            fprintf(stderr, "[popbam_b200] counting path: run again (arena overflow %d: %llu cells, %llu codes; quality %d above ceiling %d: %d; launch assumptions %d)\n",
                     h_final->arena_overflow, h_final->n_cells, h_final->n_codes, h_final->qual_max_seen, c->qual_ceiling, h_final->qual_over, h_final->spec_fail);
         if (h_final->qual_high) c->qual_robust = true;
         if (h_final->arena_overflow) c->arena_scale *= 4;
@@ -942,7 +942,7 @@ int pb_push_batch_async(pb_ctx *c, const pb_read_batch *b) {
     PB_TRY(dev_reserve(c, c->d_ncig, 4 * (size_t)N1, 4 * (size_t)N0));
     PB_TRY(dev_reserve(c, c->d_base, 8 * (size_t)N1, 8 * (size_t)N0));
     PB_TRY(dev_reserve(c, c->d_cigar, 4 * (size_t)(c->n_cig + b->n_cigar), 4 * (size_t)c->n_cig));
-    // 64 zeroed bytes behind the last base: k_pile_fast converts whole 32-byte groups of qual[] (16 of seq4[])
+    // 64 zeroed bytes behind the last base: the bulk copies of k_pile_reads round a tile's end up to 16 bytes, its scatter reads a few words past a segment
     PB_TRY(dev_reserve(c, c->d_qual, (size_t)(c->n_bytes + b->n_bases) + 96, (size_t)c->n_bytes));
     PB_TRY(dev_reserve(c, c->d_seq4, (size_t)(c->n_bytes + b->n_bases) / 2 + 96, (size_t)c->n_bytes / 2));
     // batch-relative offsets of every push of the region, one after the other (no push waits for the one before it)

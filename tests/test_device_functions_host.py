@@ -85,7 +85,7 @@ def test_unanimous_shortcut_equals_oracle(hd):
 
 
 def test_one_stray_base_rule_equals_oracle(hd):
-    """pb_one_stray_entry (the bit-sliced pass settles cells with k-1 reference bases and one other base when it says
+    """pb_one_stray_entry (the counting pass settles cells with k-1 reference bases and one other base when it says
     so): wherever it answers 1, the reference-pinned oracle must call the cell homozygous for the majority base, for
     every quality / strand arrangement tried.  Two rounds per level set: the stray base's level from all levels, and only
     from those below quality 30 (what the kernel knows about a stray base outside the H plane)."""

@@ -1,5 +1,5 @@
-"""GPU parity of the bit-sliced pileup path (popbam_b200/csrc/pb_fast.cuh) on shapes chosen to hit its branches:
-the same region is run through the bit-sliced path, through k_pileup_call (POPBAM_B200_PILEUP=classic) and through
+"""GPU parity of the counting pileup path (popbam_b200/csrc/pb_pile.cuh, pb_fast.cuh) on shapes chosen to hit its branches:
+the same region is run through the counting path, through k_pileup_call (POPBAM_B200_PILEUP=classic) and through
 the CPU oracle, and all three must agree bit for bit on the integer results (1e-9 on the fp64 statistics)."""
 import os
 
@@ -28,24 +28,24 @@ def _ctx(fx, p, an, wb, we, classic):
 
 
 @pytest.mark.parametrize("name,kw,pkw", [
-    # several staging passes per CTA in k_pile_fast (more than 512 records per 64 strips), depths beyond the
-    # 6-plane counters' easy range: most cells go through the H-plane test or k_hard_cells
+    # several tiles per warp in k_pile_reads, depths beyond the run that a count alone settles: most cells go through the
+    # test of the high-quality count or to k_hard_cells
     ("deep", dict(contig_len=9000, n_ingroup=3, has_outgroup=1, depth=60.0, snp_density=0.02, het_frac=0.3, seed=41), {}),
     # variants everywhere, N / = / X / D cigar operations, lower-case and N reference bytes
     ("dense_edge", dict(contig_len=9000, n_ingroup=7, has_outgroup=1, depth=25.0, snp_density=0.3, het_frac=0.5, edge_mode=1, seed=42), {}),
-    # 36 bp reads: many records per strip, one staged plane element pair per record
+    # 36 bp reads: short segments (the masked first / last pair of the scatter loop is most of the loop)
     ("short", dict(contig_len=9000, n_ingroup=4, has_outgroup=1, depth=18.0, read_len=36, snp_density=0.03, seed=43), {}),
-    # 250 bp reads: nine plane elements per record, fewer records per staging pass
+    # 250 bp reads: a warp's tile holds fewer reads than lanes
     ("long", dict(contig_len=12000, n_ingroup=4, has_outgroup=1, depth=30.0, read_len=250, snp_density=0.03, seed=44), {}),
-    # reads with mapQ below min_rmsQ contribute: their cells must leave the bit-sliced path (the rms test is per cell)
+    # reads with mapQ below min_rmsQ contribute: their cells must leave the easy path (the rms test is per cell)
     ("lowq", dict(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=24.0, snp_density=0.03, seed=45), dict(min_rmsQ=38)),
-    # min_depth above the mean passing depth, min_baseQ high: coverage decided by the bit-sliced depth compare
+    # min_depth above the mean passing depth, min_baseQ high: coverage decided by the packed depth compare
     ("min_depth", dict(contig_len=9000, n_ingroup=2, has_outgroup=1, depth=30.0, snp_density=0.03, seed=46),
      dict(min_depth=10, min_baseQ=25)),
     # 64 samples: both halves of the 64-bit site masks, sparse coverage (empty cells, strips without records)
     ("n64_sparse", dict(contig_len=6000, n_ingroup=63, has_outgroup=1, depth=14.0, snp_density=0.05, het_frac=0.2, seed=47),
      dict(min_depth=2)),
-    # Illumina-1.3 qualities (-i): the packed quality thresholds of k_planes are offset by 31
+    # Illumina-1.3 qualities (-i): the packed quality thresholds of k_pile_reads are offset by 31
     ("illumina", dict(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=24.0, snp_density=0.03, seed=49),
      dict(flags=pbtest.FLAG["ILLUMINA"], min_baseQ=4)),
     # odd read length (padding nibble / byte after every read), two read groups per sample
@@ -67,7 +67,7 @@ def test_bit_sliced_path_equals_classic_kernel_and_oracle(name, kw, pkw):
         an |= pbtest.AN[a]
     fast = _ctx(fx, p, an, wb, we, classic=False)
     classic = _ctx(fx, p, an, wb, we, classic=True)
-    assert fast.path() == 1 and classic.path() == 0, "bit-sliced path was not taken"
+    assert fast.path() == 1 and classic.path() == 0, "counting path was not taken"
     orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
     got, ref, want = pbtest.result_arrays(fast.res), pbtest.result_arrays(classic.res), pbtest.result_arrays(orc.res)
     assert int(want["segsites"].sum()) > 0
@@ -95,7 +95,7 @@ def test_bit_sliced_path_region_shapes(name, pkw, windows):
         an |= pbtest.AN[a]
     fast = _ctx(fx, p, an, wb, we, classic=False)
     classic = _ctx(fx, p, an, wb, we, classic=True)
-    assert fast.path() == 1 and classic.path() == 0, "bit-sliced path was not taken"
+    assert fast.path() == 1 and classic.path() == 0, "counting path was not taken"
     orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
     got, ref, want = pbtest.result_arrays(fast.res), pbtest.result_arrays(classic.res), pbtest.result_arrays(orc.res)
     assert_same(got, ref, AN_NAMES)
