@@ -69,12 +69,28 @@ __global__ void __launch_bounds__(256) k_need_raw(const double *__restrict__ fk,
 //             homozygote because the shortcut's snpQ (a function of k and b alone, pb_unanimous_result) reaches min_snpQ
 //             (pop_utils.cpp:139-150; below min_snpQ segbase reverts the call with arithmetic on the packed word, SURVEY Q8:
 //             those cells go to k_hard_cells)
-//   rlo, rhi, rh   three runs of depths [rlo, rhi] (all below 128) in which a cell without stray bases or flags is settled by
-//             packed compares: bit 3 holds throughout, and bit 0 in run 0 (rh[0] = 0), khi >= rh[i] >= hneed[k] in the others
-struct PbFastTables { uint8_t flags[256]; uint8_t hneed[256]; uint8_t altok[256]; uint8_t rlo[3], rhi[3], rh[3], pad[7]; };
+//             bit 6  qfilter's rms >= min_rmsQ holds for k bases of reads whose mapping quality is in the top class (below)
+//   rlo, rhi, rh   three runs of depths [rlo, rhi] (all below 128) in which a cell without stray bases, flags or mapping-quality
+//             deficits is settled by packed compares: bits 3 and 6 hold throughout, and bit 0 in run 0 (rh[0] = 0),
+//             khi >= rh[i] >= hneed[k] in the others
+//   dq[mapq], m0sq, qstep, rthr[k]   qfilter (pop_utils.cpp:102-120) wants rms = (u64)(sqrtf(sum mapq^2 / k) + 0.499) >= min_rmsQ,
+//             i.e. sum mapq^2 >= rthr[k] (k_rms_table: every step of that expression is monotone).  A read's mapq^2 is
+//             bounded below by m0sq + qstep * (3 - dq[mapq]) -- four classes between min_mapQ^2 and (min_rmsQ + 4)^2 -- and
+//             the cells count the DEFICITS dq of their passing bases (reads of the top class, mapq >= min_rmsQ + 4, add
+//             nothing: in ordinary data that is nearly every read), so sum mapq^2 >= k * m0sq + qstep * (3 k - D).  A few
+//             reads between min_mapQ and min_rmsQ no longer cost their cells the easy path; sound for k <= 84 (D is a
+//             byte); deeper cells go to k_hard_cells.
+struct PbFastTables {
+    uint8_t flags[256]; uint8_t hneed[256]; uint8_t altok[256]; uint8_t dq[256];
+    uint8_t rlo[3], rhi[3], rh[3], pad[7];
+    int32_t m0sq, qstep, pad2[2];
+    int32_t rthr[256];
+};
+#define PB_RMS_KMAX 84            // 3 * 84 + the carries a neighbouring byte's overflow can add stays below 256
 __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restrict__ ctr, const uint8_t *__restrict__ need_raw,
                                                      const double *__restrict__ fk, const double *__restrict__ beta,
-                                                     const double *__restrict__ lhet, int min_depth, int min_snpQ, int ceiling, PbFastTables *__restrict__ tab) {
+                                                     const double *__restrict__ lhet, int min_depth, int min_snpQ, int ceiling, int min_mapQ, int min_rmsQ,
+                                                     const int32_t *__restrict__ rms_thr, PbFastTables *__restrict__ tab) {
     const int nl = ctr->n_levels, k = threadIdx.x, qlo = ctr->qval[0];
     const int top = max(0, min(nl, ceiling - qlo + 1)), hi = max(0, min(top, PB_H_QUALITY - qlo));      // stray-base levels [0, top), low-quality ones [0, hi)
     uint32_t f = 0;
@@ -83,6 +99,17 @@ __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restric
     if (top > 0 && pb_one_stray_entry(nl, ctr->qval, k, fk, beta, lhet, 0, top)) f |= 2u;
     if (hi > 0 && pb_one_stray_entry(nl, ctr->qval, k, fk, beta, lhet, 0, hi)) f |= 4u;
     if (k >= min_depth) f |= 8u;
+    // mapping-quality classes: lower bounds of mapq^2 in four steps from min_mapQ^2 to mtop^2, mtop = min_rmsQ + 4
+    const int m0 = max(0, min(250, min_mapQ)), m0sq = m0 * m0, mtop = max(m0 + 3, min(255, min_rmsQ + 4)), qstep = (mtop * mtop - m0sq) / 3;
+    {
+        const int mq = k;                                  // (this thread's table entry: mapping quality k)
+        const int q = mq >= m0 ? min(3, (mq * mq - m0sq) / qstep) : 0;
+        tab->dq[mq] = (uint8_t)(3 - q);
+    }
+    const int thr = rms_thr[k];
+    tab->rthr[k] = thr;
+    if (k >= 1 && k <= PB_RMS_KMAX && (long long)k * m0sq + (long long)qstep * 3 * k >= (long long)thr) f |= 0x40u;
+    if (k == 0) { tab->m0sq = m0sq; tab->qstep = qstep; }
     tab->flags[k] = (uint8_t)f;
     tab->hneed[k] = k >= 1 ? need_raw[PB_H_QUALITY * 256 + k] : 0;
     uint32_t ok = 0;
@@ -101,9 +128,9 @@ __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restric
     if (k == 0) {
         int best_lo = 1, best_hi = 0;
         for (int i = 1; i < 128;) {                        // (packed compares: counts below 128)
-            if ((fs[i] & 9) != 9) { ++i; continue; }
+            if ((fs[i] & 0x49) != 0x49) { ++i; continue; }
             int j = i;
-            while (j + 1 < 128 && (fs[j + 1] & 9) == 9) ++j;
+            while (j + 1 < 128 && (fs[j + 1] & 0x49) == 0x49) ++j;
             if (j - i > best_hi - best_lo) { best_lo = i; best_hi = j; }
             i = j + 1;
         }
@@ -113,7 +140,7 @@ __global__ void __launch_bounds__(256) k_fast_tables(const PbCounters *__restric
         const int lim[2] = {8, 16};
         for (int r = 0; r < 2; ++r) {
             int lo = at, hi = at - 1, hmax = 0;
-            while (hi + 1 < 128 && (fs[hi + 1] & 8) && hs[hi + 1] > 0 && hs[hi + 1] <= lim[r]) { ++hi; hmax = max(hmax, (int)hs[hi]); }
+            while (hi + 1 < 128 && (fs[hi + 1] & 0x48) == 0x48 && hs[hi + 1] > 0 && hs[hi + 1] <= lim[r]) { ++hi; hmax = max(hmax, (int)hs[hi]); }
             tab->rlo[r + 1] = (uint8_t)lo; tab->rhi[r + 1] = (uint8_t)hi; tab->rh[r + 1] = (uint8_t)max(hmax, 1);
             at = hi + 1;
         }

@@ -345,7 +345,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
             PB_TRY(dev_reserve(c, c->d_fastp, sizeof(PbFastTables)));
             k_need_raw<<<64, 256, 0, st>>>(dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), dp<uint8_t>(c->d_need_raw));
             k_fast_tables<<<1, 256, 0, st>>>(ctr, dp<uint8_t>(c->d_need_raw), dp<double>(c->d_fk), dp<double>(c->d_beta), dp<double>(c->d_lhet), P.min_depth,
-                                            P.min_snpQ, c->qual_ceiling, dp<PbFastTables>(c->d_fastp));
+                                            P.min_snpQ, c->qual_ceiling, P.min_mapQ, P.min_rmsQ, dp<int32_t>(c->d_rms_thr), dp<PbFastTables>(c->d_fastp));
             c->launches += 2;
             c->need_raw_valid = true;
         }
@@ -398,7 +398,8 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
             // score: resident warps x the share of a block's reads that start in it (a read that reaches in from the block before
             // is walked twice)
             double best = 0;
-            for (int spc = 64; spc >= 1; spc >>= 1) {
+            static const int kSpc[] = {64, 48, 32, 24, 16, 14, 12, 8, 6, 4, 3, 2, 1};
+            for (int spc : kSpc) {
                 const int qcap = std::max(128, std::min(4096, ((int)(0.2 * (32.0 * spc + pc.span32) * pc.dens16 / 16.0) + 63) & ~63));
                 for (int warps = 16; warps >= 4; warps >>= 1) {
                     const int lreads = 0;

@@ -68,11 +68,11 @@ static inline int pb_pile_asw(int spc) { return 8 * spc + 1; }
 // dynamic shared memory: counters, reference nibbles (two copies), tables, barriers, per-warp tiles (16 bytes of
 // padding around each)
 static inline size_t pb_pile_reads_smem(int n_samples, int spc, int tile_q, int warps, int qcap, int list_reads) {
-    const size_t cnt = (size_t)n_samples * (4 * (size_t)pb_pile_asw(spc) + 1) * 4;
+    const size_t cnt = (size_t)n_samples * (5 * (size_t)pb_pile_asw(spc) + 1) * 4;
     const size_t rc = 2 * ((size_t)(32 * spc) / 8 + 2) * 4 + 32;
     const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32);
     const size_t scan = pb_pile_tail_smem(n_samples, spc, warps, list_reads);
-    return ((cnt + 15) & ~(size_t)15) + rc + 800 + 16 * (size_t)warps + 16 * (size_t)qcap + (tiles > scan ? tiles : scan) + 64;
+    return ((cnt + 15) & ~(size_t)15) + rc + ((sizeof(PbFastTables) + 15) & ~(size_t)15) + 16 * (size_t)warps + 16 * (size_t)qcap + (tiles > scan ? tiles : scan) + 64;
 }
 
 static inline size_t pb_pile_tail_bytes(int n_samples, int spc, int tile_q, int warps, int list_reads) {
@@ -136,7 +136,7 @@ __device__ __forceinline__ bool pb_base_code(const uint8_t *__restrict__ qual, c
 // ASW and returns the stray passing bases; the caller handles those (rare).
 template <bool ROBUST, bool MASKED>
 __device__ __forceinline__ uint32_t pb_count_word(uint32_t *cp, int ASW, uint32_t qm, uint32_t sx, uint32_t xn, uint32_t vm, uint32_t addP, uint32_t addH,
-                                                  uint32_t hmask, uint32_t *Hout) {
+                                                  uint32_t hmask, uint32_t dq, uint32_t *Hout) {
     // 16-entry lookup for four bases: nibble 1 (A), 2 (C), 4 (G), 8 (T) -> bit 0 set (T: selector bit 3 replicates the sign
     // of entry 0, 0x80, over the byte), everything else -> bit 0 clear
     const uint32_t sq = pb_prmt(0x00050380u, 0x00000009u, sx);
@@ -154,6 +154,7 @@ __device__ __forceinline__ uint32_t pb_count_word(uint32_t *cp, int ASW, uint32_
     if (!MASKED || P) {
         atomicAdd(cp, P);
         atomicAdd(cp + ASW, H);
+        if (dq) atomicAdd(cp + 4 * ASW, P * dq);          // a read below the top mapping-quality class (PbFastTables::dq)
     }
     *Hout = H;
     return mm;
@@ -175,12 +176,12 @@ __device__ __forceinline__ void pb_count_stray(uint32_t *cp, int ASW, uint32_t m
 
 // What the scatter of one aligned segment needs besides the segment itself.
 struct PbScatter {
-    uint32_t *cnt;                 // counters [n][K, H, M, F][ASW]
+    uint32_t *cnt;                 // counters [n][K, H, M, F, D][ASW]
     const uint32_t *refA, *refB;   // reference nibbles of the block, and the same stream one position word further on
     int ASW, RW;
     int p0, pend;                  // the counters' positions
     uint32_t addP, addC, addH1;    // packed thresholds: passing, ceiling of the one-stray-base rule, khi level
-    int min_rmsQ;
+    const uint8_t *dqtab;          // mapping quality -> deficit (PbFastTables::dq)
     PbCounters *ctr;
 };
 template <bool GLOBAL> __device__ __forceinline__ uint32_t pb_ld32(const uint32_t *p) {
@@ -203,7 +204,8 @@ __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, 
     uint32_t addH = mq >= PB_H_QUALITY ? c.addH1 : 0u;                    // mapQ below the khi level: no byte reaches bit 7
     uint32_t hmask = mq >= PB_H_QUALITY ? 0xffffffffu : 0u;
     const uint32_t addP = c.addP, addC = c.addC;
-    asm volatile("" : "+r"(addH), "+r"(hmask));                           // keep them in registers (the compiler would recompute them per word)
+    uint32_t dq = c.dqtab[min(mq, 255)];
+    asm volatile("" : "+r"(addH), "+r"(hmask), "+r"(dq));                 // keep them in registers (the compiler would recompute them per word)
     const int j0 = (pa - c.p0) >> 2, j1 = (pb - 1 - c.p0) >> 2;           // position words of the block (four positions each)
     const int i0b = c.p0 + 4 * j0 - sx0;                                  // base index of word j0's first byte (>= -3)
     const long long bq = qoff + i0b;                                      // its byte (>= -3 relative to base 0)
@@ -229,8 +231,8 @@ __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, 
         sn0 = sn1; wq0 = wq2;                                                                                                \
         if (!ROBUST) over |= MASKED ? ((qa & (vmA) << 7) | (qb_ & (vmB) << 7)) : (qa | qb_);                                 \
         uint32_t hA, hB;                                                                                                     \
-        const uint32_t mmA = pb_count_word<ROBUST, MASKED>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, &hA);             \
-        const uint32_t mmB = pb_count_word<ROBUST, MASKED>(cp + 1, ASW, qb_, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, &hB); \
+        const uint32_t mmA = pb_count_word<ROBUST, MASKED>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, dq, &hA);             \
+        const uint32_t mmB = pb_count_word<ROBUST, MASKED>(cp + 1, ASW, qb_, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, dq, &hB); \
         if (mmA | mmB) {                                   /* stray bases: rare, one branch per pair */                     \
             if (mmA) pb_count_stray<ROBUST>(cp, ASW, mmA, hA, qa, sxw, addC);                                                \
             if (mmB) pb_count_stray<ROBUST>(cp + 1, ASW, mmB, hB, qb_, sxw >> 16, addC);                                     \
@@ -254,11 +256,6 @@ __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, 
         PB_CNT_PAIR(vmA, vmB, true)
     }
 #undef PB_CNT_PAIR
-    if (mq < c.min_rmsQ) {
-        // a read below min_rmsQ: every cell it covers leaves the easy path (its bases may or may not pass; k_hard_cells
-        // computes the exact rms).  Rare, and outside the loop above.
-        for (int j = j0; j <= j1; ++j) atomicOr(row + 3 * ASW + j, 0x20202020u);
-    }
     if (!ROBUST && (over & 0x80808080u)) { c.ctr->qual_high = 1; c.ctr->qual_over = 1; }     // a quality byte >= 128: the host runs the region again with the robust variant
 }
 
@@ -298,14 +295,14 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     }
     const int n = a.n_samples;
     const int PB = a.spc * 32;
-    const int ASW = a.asw, RW = 4 * ASW + 1;                                // words: array stride, sample stride (odd: the samples' rows start in different banks)
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw);               // [n][K, H, M, F][ASW]: passing bases, those at or above the khi level, stray bases, flags (pb_count_stray)
+    const int ASW = a.asw, RW = 5 * ASW + 1;                                // words: array stride, sample stride (the samples' rows start in different banks)
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(smem_raw);               // [n][K, H, M, F, D][ASW]: passing bases, those at or above the khi level, stray bases, flags (pb_count_stray), mapping-quality deficits (PbFastTables)
     const size_t cnt_bytes = (((size_t)n * RW * 4) + 15) & ~(size_t)15;
     const int NRW = PB / 8 + 2;                                            // words of reference nibbles (eight positions each)
     uint32_t *refA = reinterpret_cast<uint32_t *>(smem_raw + cnt_bytes);  // [NRW] position 8 i of the block in bits 0-3 of word i
     uint32_t *refB = refA + NRW;                                          // [NRW] the same stream 16 bits (one position word) further on
     uint8_t *tabS = smem_raw + ((cnt_bytes + (size_t)2 * NRW * 4 + 15) & ~(size_t)15);     // PbFastTables
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tabS + 800);     // one per warp
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(tabS + ((sizeof(PbFastTables) + 15) & ~(size_t)15));     // one per warp
     int4 *queue = reinterpret_cast<int4 *>(reinterpret_cast<unsigned char *>(mbar) + 16 * (size_t)NWARP);       // [qcap] {sx0, offset lo, len | offset hi << 16 | sample << 24, mapq}
     unsigned char *tiles = reinterpret_cast<unsigned char *>(queue + a.qcap);
     const int tile_s = a.tile_q / 2 + 16;
@@ -335,7 +332,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
     PbScatter sc;
-    sc.cnt = cnt; sc.refA = refA; sc.refB = refB; sc.ASW = ASW; sc.RW = RW; sc.p0 = p0; sc.pend = p0 + PB; sc.min_rmsQ = a.min_rmsQ; sc.ctr = a.ctr;
+    sc.cnt = cnt; sc.refA = refA; sc.refB = refB; sc.ASW = ASW; sc.RW = RW; sc.p0 = p0; sc.pend = p0 + PB; sc.dqtab = reinterpret_cast<const PbFastTables *>(tabS)->dq; sc.ctr = a.ctr;
     {
         // raw quality byte thresholds (host: all <= 128): passing, khi level, above the ceiling of the one-stray-base rule
         const int qoff = a.illumina ? 31 : 0;
@@ -462,7 +459,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
             unsigned long long cov = 0;
             for (int s = 0; s < n; ++s) {
                 const uint32_t *rw = cnt + (size_t)s * RW + w;
-                const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
+                const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW] | rw[4 * ASW];      // (flags or deficits: not for the packed test)
                 const uint32_t ok = ((K4 + aLo[0]) & ~(K4 + aHi[0])) | ((K4 + aLo[1]) & ~(K4 + aHi[1]) & (H4 + aH[1])) | ((K4 + aLo[2]) & ~(K4 + aHi[2]) & (H4 + aH[2]));
                 if (whole && !(M4 | F4) && ((ok & ~K4 & 0x80808080u) == 0x80808080u)) cov |= 1ULL << s;
                 else if (K4) cq[atomicAdd(&s_nc, 1)] = (uint16_t)(w | s << 9);
@@ -478,7 +475,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     for (int i = tid; i < s_nc; i += NT) {
         const int w = cq[i] & 511, s = cq[i] >> 9, pw = p0 + 4 * w;
         const uint32_t *rw = cnt + (size_t)s * RW + w;
-        const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW];
+        const uint32_t K4 = rw[0], H4 = rw[ASW], M4 = rw[2 * ASW], F4 = rw[3 * ASW], D4 = rw[4 * ASW];
         const uint32_t ref16 = (refA[w >> 1] >> (16 * (w & 1))) & 0xffffu;
         const uint32_t sbit = 1u << (s & 31);
         const int hs = s >> 5;
@@ -489,11 +486,14 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
             const uint32_t fl = T->flags[k], hn = T->hneed[k];
             const bool unan = (fl & 1u) || (hn && kh >= hn);                             // the depth alone / the count of high-quality bases proves the shortcut
             const bool stray = (fl & 2u) || (!(f & 0x10u) && (fl & 4u));                 // one stray base that provably cannot change the call
-            // qfilter for settled cells: rms >= min_rmsQ holds because every contributing read has mapQ >= min_rmsQ (flag
-            // bit 5 clear); depth <= max_depth because the cap cannot bind; depth >= min_depth is bit 3 of the table
+            // qfilter for settled cells: rms >= min_rmsQ is proven from the mapping-quality deficits (PbFastTables); depth <=
+            // max_depth because the cap cannot bind; depth >= min_depth is bit 3 of the table
             const int q = 4 * w + j;
+            const uint32_t d = (D4 >> (8 * j)) & 0xffu;
+            const bool rms_ok = d == 0 ? (fl & 0x40u) != 0
+                                       : (k <= PB_RMS_KMAX && (int)k * T->m0sq + T->qstep * (3 * (int)k - (int)d) >= T->rthr[k]);
             bool settled = false;
-            if (!(f & 0x20u)) {
+            if (!(f & 0x20u) && rms_ok) {
                 if ((m == 0 && unan) || (m == 1 && stray)) {                             // homozygous reference
                     settled = true;
                     if (fl & 8u) atomicOr(&covS[2 * q + hs], sbit);
