@@ -134,7 +134,7 @@ __device__ __forceinline__ bool pb_base_code(const uint8_t *__restrict__ qual, c
 // nibbles in the low 16 bits of sx, xn = those nibbles XOR the reference's (non-zero: a stray base), vm = 0x01 in the
 // bytes that belong to the segment.  Adds the passing bases (P) and the high-quality ones (H) to the counters at cp / cp +
 // ASW and returns the stray passing bases; the caller handles those (rare).
-template <bool ROBUST, bool MASKED>
+template <bool ROBUST, bool MASKED, bool DQ>
 __device__ __forceinline__ uint32_t pb_count_word(uint32_t *cp, int ASW, uint32_t qm, uint32_t sx, uint32_t xn, uint32_t vm, uint32_t addP, uint32_t addH,
                                                   uint32_t hmask, uint32_t dq, uint32_t *Hout) {
     // 16-entry lookup for four bases: nibble 1 (A), 2 (C), 4 (G), 8 (T) -> bit 0 set (T: selector bit 3 replicates the sign
@@ -154,7 +154,7 @@ __device__ __forceinline__ uint32_t pb_count_word(uint32_t *cp, int ASW, uint32_
     if (!MASKED || P) {
         atomicAdd(cp, P);
         atomicAdd(cp + ASW, H);
-        if (dq) atomicAdd(cp + 4 * ASW, P * dq);          // a read below the top mapping-quality class (PbFastTables::dq)
+        if (DQ && dq) atomicAdd(cp + 4 * ASW, P * dq);    // a read below the top mapping-quality class (PbFastTables::dq)
     }
     *Hout = H;
     return mm;
@@ -194,7 +194,9 @@ template <bool GLOBAL> __device__ __forceinline__ uint32_t pb_ld32(const uint32_
 // 2 * sbase + qi... given as (word pointers + offsets) by the caller: `qb` / `sb` point to 4-byte aligned memory that holds
 // base i of the segment at byte qoff + i resp. nibble noff + i (both offsets may be negative by up to 3 for the masked bytes
 // in front of the segment; GLOBAL: the caller guarantees that memory is readable from 4 bytes before base 0, or qoff/noff >= 3).
-template <bool ROBUST, bool GLOBAL>
+// DQ: some read of the warp is below the top mapping-quality class (the deficit counter is then updated, one more reduction
+// per word for those reads; the common case -- no such read among the warp's 32 -- runs without it).
+template <bool ROBUST, bool GLOBAL, bool DQ>
 __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, int slen, uint32_t smp, int mq, const unsigned char *qb, long long qoff,
                                                    const unsigned char *sb, long long noff) {
     const int pa = max(sx0, c.p0), pb = min(sx0 + slen, c.pend);
@@ -204,7 +206,7 @@ __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, 
     uint32_t addH = mq >= PB_H_QUALITY ? c.addH1 : 0u;                    // mapQ below the khi level: no byte reaches bit 7
     uint32_t hmask = mq >= PB_H_QUALITY ? 0xffffffffu : 0u;
     const uint32_t addP = c.addP, addC = c.addC;
-    uint32_t dq = c.dqtab[min(mq, 255)];
+    uint32_t dq = DQ ? c.dqtab[min(mq, 255)] : 0u;
     asm volatile("" : "+r"(addH), "+r"(hmask), "+r"(dq));                 // keep them in registers (the compiler would recompute them per word)
     const int j0 = (pa - c.p0) >> 2, j1 = (pb - 1 - c.p0) >> 2;           // position words of the block (four positions each)
     const int i0b = c.p0 + 4 * j0 - sx0;                                  // base index of word j0's first byte (>= -3)
@@ -231,8 +233,8 @@ __device__ __forceinline__ void pb_scatter_segment(const PbScatter &c, int sx0, 
         sn0 = sn1; wq0 = wq2;                                                                                                \
         if (!ROBUST) over |= MASKED ? ((qa & (vmA) << 7) | (qb_ & (vmB) << 7)) : (qa | qb_);                                 \
         uint32_t hA, hB;                                                                                                     \
-        const uint32_t mmA = pb_count_word<ROBUST, MASKED>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, dq, &hA);             \
-        const uint32_t mmB = pb_count_word<ROBUST, MASKED>(cp + 1, ASW, qb_, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, dq, &hB); \
+        const uint32_t mmA = pb_count_word<ROBUST, MASKED, DQ>(cp, ASW, qa, sxw, xn, (vmA), addP, addH, hmask, dq, &hA);             \
+        const uint32_t mmB = pb_count_word<ROBUST, MASKED, DQ>(cp + 1, ASW, qb_, sxw >> 16, xn >> 16, (vmB), addP, addH, hmask, dq, &hB); \
         if (mmA | mmB) {                                   /* stray bases: rare, one branch per pair */                     \
             if (mmA) pb_count_stray<ROBUST>(cp, ASW, mmA, hA, qa, sxw, addC);                                                \
             if (mmB) pb_count_stray<ROBUST>(cp + 1, ASW, mmB, hB, qb_, sxw >> 16, addC);                                     \
@@ -415,7 +417,9 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
             pb_mbar_wait(bar, phase);
             __syncwarp();                                                     // the lanes leave the wait loop one by one: walk the segments together
             phase ^= 1u;
-            if (slen) pb_scatter_segment<ROBUST, false>(sc, sx0, slen, smp, mq, tq, (long long)(so - tq0), ts, (long long)(so - 2 * ts0));
+            if (__any_sync(0xffffffffu, slen && sc.dqtab[min(mq, 255)])) {
+                if (slen) pb_scatter_segment<ROBUST, false, true>(sc, sx0, slen, smp, mq, tq, (long long)(so - tq0), ts, (long long)(so - 2 * ts0));
+            } else if (slen) pb_scatter_segment<ROBUST, false, false>(sc, sx0, slen, smp, mq, tq, (long long)(so - tq0), ts, (long long)(so - 2 * ts0));
             __syncwarp();                                                     // the warp's tile is free again
             start += nt;
         }
@@ -429,7 +433,7 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
             const int4 e = queue[i];
             const uint32_t z = (uint32_t)e.z;
             const long long so = (long long)(((uint64_t)((z >> 16) & 0xffu) << 32) | (uint32_t)e.y);
-            pb_scatter_segment<ROBUST, true>(sc, e.x, (int)(z & 0xffffu), z >> 24, e.w, a.qual, so, a.seq4, so);
+            pb_scatter_segment<ROBUST, true, true>(sc, e.x, (int)(z & 0xffffu), z >> 24, e.w, a.qual, so, a.seq4, so);
         }
     }
     __syncthreads();                                                          // this CTA's reads are counted
