@@ -42,7 +42,7 @@ import numpy as np  # noqa: E402
 
 # DRAM bytes (read + written) of ALL kernels of one region on a 2.3 Mb shard of configs[1], summed over the committed ncu
 # launch list profiles/r2_launches.csv (dram__bytes_read.sum + dram__bytes_write.sum per kernel, one pipeline run)
-TRAFFIC_BYTES_PER_SHARD_C2 = 2.30e9
+TRAFFIC_BYTES_PER_SHARD_C2 = 2.29e9
 READ_LEN = 100
 
 # BASELINE.json configs[0..4] as c1..c5 (SURVEY.md §8(d) data model).  One STEP = the whole contig = every shard once.
