@@ -85,9 +85,16 @@ __global__ void __launch_bounds__(256) k_read_prep(int64_t n, const int32_t *__r
         const uint32_t c0 = cigstart[r], nc = ncig[r];
         int x = p, al = 0, nseg = 0;
         bool longseg = false;
-        // branch-free per operation (most reads have one, a few have five: the warp runs the longest list):
-        // M = X consume reference and query (bits 0, 7, 8 of the class masks), D N consume reference (bits 2, 3)
-        for (uint32_t i = 0; i < nc; ++i) {
+        // branch-free per operation: M = X consume reference and query (bits 0, 7, 8 of the class masks), D N consume
+        // reference (bits 2, 3).  Most reads have one operation, a few have five: the first is taken by all lanes together,
+        // the loop behind it runs for the warp's longest list
+        {
+            const uint32_t c = nc ? __ldg(cigar + c0) : 0u;
+            const int op = c & 15, len = (int)(c >> 4);
+            const int aln = (0x181 >> op) & 1, ref = (0x18d >> op) & 1;
+            x += len & -ref; al = len & -aln; nseg = aln & (len > 0); longseg = (aln & (len > 65535)) != 0;
+        }
+        for (uint32_t i = 1; i < nc; ++i) {
             const uint32_t c = __ldg(cigar + c0 + i);
             const int op = c & 15, len = (int)(c >> 4);
             const int aln = (0x181 >> op) & 1, ref = (0x18d >> op) & 1;

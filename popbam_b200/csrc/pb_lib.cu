@@ -76,6 +76,8 @@ struct pb_ctx {
     bool qual_robust = false;              // quality bytes >= 128 occur: kernel variant whose packed compares are right for any byte
     int arena_scale = 1;                   // cell arena size factor (raised on overflow)
     int pile_spc = 0, pile_warps = 0;      // POPBAM_B200_PILE=strips,warps: launch shape of k_pile_reads (measurements)
+    bool fuse_codes = true;                // POPBAM_B200_CODES=separate: all base codes of the hard cells by k_cell_codes (measurements);
+    int codes_skip = 0;                    // =mixed: every other block's (tests: both ways in one region)
     bool need_raw_valid = false;
     bool ran_fast = false;                 // the last pipeline run took the counting path
     int force_classic = 0;                 // the counting path gave up on this region (arena overflow twice): k_pileup_call
@@ -477,6 +479,7 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
         const unsigned n_blocks = (unsigned)((n_strips + pc.spc - 1) / pc.spc);
         PB_TRY(dev_reserve(c, c->d_blk, sizeof(uint4) * (size_t)n_blocks));
         fa.blk = dp<uint4>(c->d_blk); fa.cells = dp<uint4>(c->d_cells); fa.cell_cap = cell_cap; fa.code_cap = code_cap;
+        fa.codes = c->fuse_codes ? dp<uint16_t>(c->d_codes16) : nullptr; fa.codes_skip = c->codes_skip;
         if (getenv("POPBAM_B200_DEBUG"))
             fprintf(stderr, "[popbam_b200] k_pile_reads: %u CTAs of %d warps, %d strips per CTA, quality tile %d bytes, %zu bytes of shared memory\n",
                     n_blocks, pc.warps, pc.spc, pc.tile_q, pc.smem);
@@ -806,6 +809,7 @@ pb_ctx *pb_create(const pb_params *p, const pb_errmod_tables *tables, int *statu
     { const char *e = getenv("POPBAM_B200_PILEUP"); c->classic = e && strcmp(e, "classic") == 0; }
     { const char *e = getenv("POPBAM_B200_SYNC"); c->no_async = e && *e == '1'; }
     { const char *e = getenv("POPBAM_B200_PILE"); if (e) sscanf(e, "%d,%d", &c->pile_spc, &c->pile_warps); }
+    { const char *e = getenv("POPBAM_B200_CODES"); if (e && !strcmp(e, "separate")) c->fuse_codes = false; if (e && !strcmp(e, "mixed")) c->codes_skip = 1; }
     { const char *e = getenv("POPBAM_B200_QCEIL"); if (e && atoi(e) >= 4) c->qual_ceiling = std::min(63, atoi(e)); }
     {
         auto wave = [&](auto kern, int threads) {

@@ -52,9 +52,11 @@ struct PbPileReadsArgs {
     uint64_t *acc_cov;                       // [span] out: samples whose cell is settled here and covered (k_hard_cells adds its cells)
     uint32_t *acc_cnt4;                      // [span] out: derived-base counts of the cells settled here (k_hard_cells adds its cells')
     uint64_t *site_type;                     // [span] out: derived-allele bits of the cells settled here (k_hard_cells adds its cells')
-    uint4 *blk;                              // out: per block {first directory entry, entries, first read that can cover the block, end of the block's reads}
+    uint4 *blk;                              // out: per block {first directory entry, entries (bit 31: codes done), first read that can cover the block, end of the block's reads}
     uint4 *cells;                            // out: directory of the cells left for k_hard_cells {pos, sample | k << 8, -, first code}
     unsigned long long cell_cap, code_cap;
+    uint16_t *codes;                         // the code arena: the block's CTA fills in its cells' codes itself (pb_block_codes); null: all left to k_cell_codes
+    int codes_skip;                          // (tests) blocks with (index & codes_skip) != 0 leave their codes to k_cell_codes all the same
 };
 
 // in the tiles' place once the reads are counted: per-position masks, the classification queue, the hard-cell list (and its
@@ -281,6 +283,142 @@ __device__ __forceinline__ long long pb_warp_lower_bound(const int32_t *__restri
 
 // ROBUST: quality bytes >= 128 were seen in this context (a BAM without qualities stores 0xff), so the packed threshold
 // tests use the form that is right for any byte value.
+// shared memory of pb_block_codes: list starts and cursors, a flag, every warp's gathered reads, the lists
+__host__ __device__ static inline size_t pb_block_codes_smem(int n_samples, int warps, int lcap) { return (2 * (size_t)n_samples + 4) * 4 + (size_t)warps * 64 * 4 + 4 * (size_t)lcap; }
+
+// The base codes of the cells a block of k_pile_reads leaves for k_hard_cells, exactly as call_base forms them
+// (popbam.cpp:268-284).  The reads that can cover a position of the block -- a run of the sorted batch, fresh in L2 -- are
+// listed per sample in shared memory with their start positions; a WARP takes a cell, scans its sample's list, gathers
+// the reads that start in (position - max_span, position] and handles them 32 at a time (CIGAR walk to the position,
+// base filter, code).  All threads of the CTA call it; false: more reads than the lists hold (nothing written).  FIXED: the
+// lists have equal room (no counting pass over the reads first).
+struct PbBlockCodes {
+    const int32_t *pos;
+    const uint32_t *meta, *cigstart, *ncig, *cigar;
+    const uint64_t *base;
+    const uint8_t *qual, *seq4;
+    int n_samples, min_mapQ, min_baseQ, illumina, lcap, max_span;
+    uint4 *cells;
+    uint16_t *codes;
+};
+template <bool FIXED>
+__device__ __forceinline__ bool pb_block_codes(const PbBlockCodes &a, unsigned long long first_cell, int nh, long long rback, long long rend, int p0, unsigned char *smem) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, NT = (int)blockDim.x, NWARP = NT >> 5, n = a.n_samples;
+    const int max_span = a.max_span;
+    int *cntS = reinterpret_cast<int *>(smem);                                 // [n + 1] reads per sample; then: their lists' starts
+    int *curS = cntS + n + 1;                                                  // [n + 1] fill cursors of the lists
+    int *badS = curS + n + 1;                                                  // [2]
+    uint32_t *wlist = reinterpret_cast<uint32_t *>(badS + 2);                  // [warps][64] a warp's gathered reads
+    uint32_t *rlist = wlist + 64 * NWARP;                                      // [lcap] the lists: read (relative to rback) | (start - p0) << 16
+    const int cap_s = a.lcap / max(n, 1);                                      // FIXED: every sample's list has this room
+    if (FIXED) {
+        for (int i = tid; i <= n; i += NT) { cntS[i] = i * cap_s; curS[i] = i * cap_s; }
+        if (tid == 0) badS[0] = (rend - rback > 0xffff) ? 1 : 0;
+    } else {
+        for (int i = tid; i <= n; i += NT) cntS[i] = 0;
+        if (tid == 0) badS[0] = (rend - rback > 0xffff) ? 1 : 0;
+        __syncthreads();
+        for (long long r = rback + tid; r < rend; r += NT) {
+            const uint32_t meta = __ldg(a.meta + r);
+            if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) atomicAdd(&cntS[meta & 0xffu], 1);
+        }
+        __syncthreads();
+        if (wid == 0) {
+            // starts of the samples' lists (n <= 64: two per lane)
+            const int c0 = lane < n ? cntS[lane] : 0, c1 = lane + 32 < n ? cntS[lane + 32] : 0;
+            int x0 = c0, x1 = c1;
+            for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y0 = __shfl_up_sync(0xffffffffu, x0, o2), y1 = __shfl_up_sync(0xffffffffu, x1, o2); if (lane >= o2) { x0 += y0; x1 += y1; } }
+            const int t0 = __shfl_sync(0xffffffffu, x0, 31), t1 = __shfl_sync(0xffffffffu, x1, 31);
+            __syncwarp();
+            if (lane < n) { cntS[lane] = x0 - c0; curS[lane] = x0 - c0; }
+            if (lane + 32 < n) { cntS[lane + 32] = t0 + x1 - c1; curS[lane + 32] = t0 + x1 - c1; }
+            if (lane == 0) { cntS[n] = t0 + t1; if (t0 + t1 > a.lcap) badS[0] = 1; }
+        }
+    }
+    __syncthreads();
+    if (badS[0]) return false;
+    for (long long r = rback + tid; r < rend; r += NT) {
+        const uint32_t meta = __ldg(a.meta + r);
+        if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) {
+            const int rel = max(-32768, __ldg(a.pos + r) - p0);                 // (a read that starts further back than that covers nothing here)
+            const int at = atomicAdd(&curS[meta & 0xffu], 1);
+            if (!FIXED || at < cntS[meta & 0xffu] + cap_s) rlist[at] = (uint32_t)(r - rback) | (uint32_t)(uint16_t)(int16_t)rel << 16;
+            else badS[0] = 1;                                                  // (a sample with more reads than its share of the room)
+        }
+    }
+    __syncthreads();
+    if (FIXED && badS[0]) return false;
+    uint32_t *gl = wlist + 64 * wid;
+    for (int i = wid; i < nh; i += NWARP) {
+        const unsigned long long c = first_cell + i;
+        const uint4 cell = a.cells[c];
+        const int pos = (int)cell.x, q = pos - p0, smp = (int)(cell.y & 0xffu);
+        const uint32_t k = (cell.y >> 8) & 0xffu;
+        uint16_t *out = a.codes + cell.w;
+        uint32_t kk = 0, n_acc = 0;
+        int rmsq = 0;
+        // the first `cnt` gathered reads: code of the base at the cell's position, if the read has one there and it passes
+        auto take = [&](uint32_t cnt) {
+            bool ok = false;
+            uint32_t code = 0;
+            int mq = 0;
+            if ((uint32_t)lane < cnt) {
+                const long long r = rback + (long long)(gl[lane] & 0xffffu);
+                const uint32_t meta = __ldg(a.meta + r);
+                mq = (int)((meta >> 8) & 0xffu);
+                int x = __ldg(a.pos + r);
+                const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
+                uint64_t qo = __ldg(a.base + r);
+                for (uint32_t ci = 0; ci < ncg && x <= pos; ++ci) {
+                    const uint32_t cg = __ldg(a.cigar + c0 + ci);
+                    const uint32_t op = cg & 15u;
+                    const int len = (int)(cg >> 4);
+                    if ((0x181u >> op) & 1u) {
+                        if (pos < x + len) { ok = pb_base_code(a.qual, a.seq4, qo + (uint64_t)(pos - x), a.illumina, a.min_baseQ, mq, (meta >> 20) & 1u, &code); break; }
+                        x += len; qo += (uint64_t)len;
+                    } else if ((0x12u >> op) & 1u) qo += (uint64_t)len;
+                    else if ((0x0cu >> op) & 1u) x += len;
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const uint32_t at = kk + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+                if (at < k) out[at] = (uint16_t)code;
+                rmsq += mq * mq;
+            }
+            kk += (uint32_t)__popc(bal);
+        };
+        const int jend = FIXED ? min(curS[smp], cntS[smp] + cap_s) : cntS[smp + 1];
+        for (int jb = cntS[smp]; jb < jend; jb += 32) {
+            const int j = jb + lane;
+            uint32_t ent = 0;
+            bool acc = false;
+            if (j < jend) {
+                ent = rlist[j];
+                const int rel = (int)(int16_t)(uint16_t)(ent >> 16);
+                acc = rel <= q && rel + max_span > q;
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
+            if (acc) gl[n_acc + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = ent;
+            n_acc += (uint32_t)__popc(bal);
+            __syncwarp();
+            if (n_acc >= 32) {
+                take(32);
+                const uint32_t rest = n_acc - 32, moved = (uint32_t)lane < rest ? gl[32 + lane] : 0u;
+                __syncwarp();
+                if ((uint32_t)lane < rest) gl[lane] = moved;
+                n_acc = rest;
+                __syncwarp();
+            }
+        }
+        if (n_acc) take(n_acc);
+        rmsq = __reduce_add_sync(0xffffffffu, rmsq);
+        if (lane == 0) { a.cells[c].y = (uint32_t)smp | min(kk, k) << 8; a.cells[c].z = (uint32_t)rmsq; }
+        __syncwarp();
+    }
+    return true;
+}
+
 template <bool ROBUST>
 __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -558,6 +696,19 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         for (int o2 = 1; o2 < 32; o2 <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o2); if (lane >= o2) x += y; }
         if (i < nh) a.cells[s_resv[0] + i] = make_uint4((uint32_t)(p0 + (int)((e >> 8) & 0xfffu)), (e >> 20) | k << 8, 0u, (uint32_t)(s_resv[1] + hoff[g] + x - k));
     }
+    // ---- their base codes, while the block's reads are fresh in L2: the lists of pb_block_codes take the counters' place
+    if (a.codes && !((int)blockIdx.x & a.codes_skip)) {
+        const long long lroom = ((long long)cnt_bytes - (long long)pb_block_codes_smem(n, NWARP, 0)) / 4;
+        if (lroom >= (long long)n_blk) {                                       // (else: k_cell_codes)
+            __syncthreads();                                                   // the directory entries are written, the counters read
+            PbBlockCodes b;
+            b.pos = a.pos; b.meta = a.meta; b.cigstart = a.cigstart; b.ncig = a.ncig; b.cigar = a.cigar; b.base = a.base; b.qual = a.qual; b.seq4 = a.seq4;
+            b.n_samples = n; b.min_mapQ = a.min_mapQ; b.min_baseQ = a.min_baseQ; b.illumina = a.illumina; b.lcap = (int)min(lroom, (long long)0x7fffffff);
+            b.max_span = max_span; b.cells = a.cells; b.codes = a.codes;
+            if (pb_block_codes<true>(b, s_resv[0], nh, (long long)rlo, (long long)rlo + n_blk, p0, smem_raw) && tid == 0)
+                a.blk[blockIdx.x].y = (uint32_t)nh | 0x80000000u;              // done: nothing left for k_cell_codes here
+        }
+    }
 }
 
 struct PbCellCodesArgs {
@@ -570,126 +721,24 @@ struct PbCellCodesArgs {
     int lcap;                                // reads the shared-memory lists hold
     int max_span;                            // as in PbPileReadsArgs
     PbCounters *ctr;
-    const uint4 *blk;                        // per block of k_pile_reads: {first directory entry, entries, first read that can cover the block, end of the block's reads}
+    const uint4 *blk;                        // per block of k_pile_reads: {first directory entry, entries (bit 31: codes already there), first read that can cover the block, end of the block's reads}
     uint4 *cells;                            // in: {position, sample | k << 8, -, first code}; out: .y = sample | codes found << 8, .z = sum of mapq^2
     uint16_t *codes;
 };
-static inline size_t pb_cell_codes_smem(int n_samples, int lcap) { return (2 * (size_t)n_samples + 2) * 4 + 8 * 64 * 4 + 4 * (size_t)lcap + 16; }
+static inline size_t pb_cell_codes_smem(int n_samples, int lcap) { return pb_block_codes_smem(n_samples, 8, lcap) + 16; }
 
-// The base codes of the cells left for k_hard_cells, exactly as call_base forms them (popbam.cpp:268-284).  One CTA per
-// block of k_pile_reads: the reads that can cover a position of the block -- a run of the sorted batch, fresh in L2 --
-// are listed per sample in shared memory with their start positions; a WARP takes a cell, scans its sample's list,
-// gathers the reads that start in (position - max_span, position] and handles them 32 at a time (CIGAR walk to the
-// position, base filter, code).
+// pb_block_codes for the blocks whose k_pile_reads CTA did not do it itself (its lists were too small), one CTA per block
 __global__ void __launch_bounds__(256) k_cell_codes(const PbCellCodesArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.ctr->arena_overflow || a.ctr->spec_fail) return;
     const uint4 rec = a.blk[blockIdx.x];
-    const int nh = (int)rec.y;
-    if (nh == 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, n = a.n_samples;
-    const int max_span = a.max_span > 0 ? a.max_span : a.ctr->max_span;
+    if (rec.y == 0 || (rec.y >> 31)) return;
+    PbBlockCodes b;
+    b.pos = a.pos; b.meta = a.meta; b.cigstart = a.cigstart; b.ncig = a.ncig; b.cigar = a.cigar; b.base = a.base; b.qual = a.qual; b.seq4 = a.seq4;
+    b.n_samples = a.n_samples; b.min_mapQ = a.min_mapQ; b.min_baseQ = a.min_baseQ; b.illumina = a.illumina; b.lcap = a.lcap;
+    b.max_span = a.max_span > 0 ? a.max_span : a.ctr->max_span;
+    b.cells = a.cells; b.codes = a.codes;
     const int p0 = a.span_beg + (int)blockIdx.x * a.spc * 32;
-    const long long rback = (long long)rec.z, rend = (long long)rec.w;
-    int *cntS = reinterpret_cast<int *>(smem_raw);                             // [n + 1] reads per sample; then: their lists' starts
-    int *curS = cntS + n + 1;                                                  // [n] fill cursors of the lists
-    uint32_t *wlist = reinterpret_cast<uint32_t *>(curS + n + 1);              // [8][64] a warp's gathered reads
-    uint32_t *rlist = wlist + 64 * 8;                                          // [lcap] the lists: read (relative to rback) | (start - p0) << 16
-    __shared__ int s_bad;
-    for (int i = tid; i <= n; i += 256) cntS[i] = 0;
-    if (tid == 0) s_bad = (rend - rback > 0xffff) ? 1 : 0;
-    __syncthreads();
-    for (long long r = rback + tid; r < rend; r += 256) {
-        const uint32_t meta = __ldg(a.meta + r);
-        if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) atomicAdd(&cntS[meta & 0xffu], 1);
-    }
-    __syncthreads();
-    if (wid == 0) {
-        // starts of the samples' lists (n <= 64: two per lane)
-        const int c0 = lane < n ? cntS[lane] : 0, c1 = lane + 32 < n ? cntS[lane + 32] : 0;
-        int x0 = c0, x1 = c1;
-        for (int o2 = 1; o2 < 32; o2 <<= 1) { const int y0 = __shfl_up_sync(0xffffffffu, x0, o2), y1 = __shfl_up_sync(0xffffffffu, x1, o2); if (lane >= o2) { x0 += y0; x1 += y1; } }
-        const int t0 = __shfl_sync(0xffffffffu, x0, 31), t1 = __shfl_sync(0xffffffffu, x1, 31);
-        __syncwarp();
-        if (lane < n) { cntS[lane] = x0 - c0; curS[lane] = x0 - c0; }
-        if (lane + 32 < n) { cntS[lane + 32] = t0 + x1 - c1; curS[lane + 32] = t0 + x1 - c1; }
-        if (lane == 0) { cntS[n] = t0 + t1; if (t0 + t1 > a.lcap) s_bad = 1; }
-    }
-    __syncthreads();
-    if (s_bad) { if (tid == 0) a.ctr->arena_overflow = 1; return; }            // (more reads than the lists hold: the host gives up on this path for the region)
-    for (long long r = rback + tid; r < rend; r += 256) {
-        const uint32_t meta = __ldg(a.meta + r);
-        if (!((meta >> 16) & 0x704u) && (meta & 0xffu) < (uint32_t)n && (int)((meta >> 8) & 0xffu) >= a.min_mapQ) {
-            const int rel = max(-32768, __ldg(a.pos + r) - p0);                 // (a read that starts further back than that covers nothing here)
-            rlist[atomicAdd(&curS[meta & 0xffu], 1)] = (uint32_t)(r - rback) | (uint32_t)(uint16_t)(int16_t)rel << 16;
-        }
-    }
-    __syncthreads();
-    uint32_t *gl = wlist + 64 * wid;
-    for (int i = wid; i < nh; i += 8) {
-        const unsigned long long c = (unsigned long long)rec.x + i;
-        const uint4 cell = a.cells[c];
-        const int pos = (int)cell.x, q = pos - p0, smp = (int)(cell.y & 0xffu);
-        const uint32_t k = (cell.y >> 8) & 0xffu;
-        uint16_t *out = a.codes + cell.w;
-        uint32_t kk = 0, n_acc = 0;
-        int rmsq = 0;
-        // the first `cnt` gathered reads: code of the base at the cell's position, if the read has one there and it passes
-        auto take = [&](uint32_t cnt) {
-            bool ok = false;
-            uint32_t code = 0;
-            int mq = 0;
-            if ((uint32_t)lane < cnt) {
-                const long long r = rback + (long long)(gl[lane] & 0xffffu);
-                const uint32_t meta = __ldg(a.meta + r);
-                mq = (int)((meta >> 8) & 0xffu);
-                int x = __ldg(a.pos + r);
-                const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
-                uint64_t qo = __ldg(a.base + r);
-                for (uint32_t ci = 0; ci < ncg && x <= pos; ++ci) {
-                    const uint32_t cg = __ldg(a.cigar + c0 + ci);
-                    const uint32_t op = cg & 15u;
-                    const int len = (int)(cg >> 4);
-                    if ((0x181u >> op) & 1u) {
-                        if (pos < x + len) { ok = pb_base_code(a.qual, a.seq4, qo + (uint64_t)(pos - x), a.illumina, a.min_baseQ, mq, (meta >> 20) & 1u, &code); break; }
-                        x += len; qo += (uint64_t)len;
-                    } else if ((0x12u >> op) & 1u) qo += (uint64_t)len;
-                    else if ((0x0cu >> op) & 1u) x += len;
-                }
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-            if (ok) {
-                const uint32_t at = kk + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                if (at < k) out[at] = (uint16_t)code;
-                rmsq += mq * mq;
-            }
-            kk += (uint32_t)__popc(bal);
-        };
-        for (int jb = cntS[smp]; jb < cntS[smp + 1]; jb += 32) {
-            const int j = jb + lane;
-            uint32_t ent = 0;
-            bool acc = false;
-            if (j < cntS[smp + 1]) {
-                ent = rlist[j];
-                const int rel = (int)(int16_t)(uint16_t)(ent >> 16);
-                acc = rel <= q && rel + max_span > q;
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, acc);
-            if (acc) gl[n_acc + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = ent;
-            n_acc += (uint32_t)__popc(bal);
-            __syncwarp();
-            if (n_acc >= 32) {
-                take(32);
-                const uint32_t rest = n_acc - 32, moved = (uint32_t)lane < rest ? gl[32 + lane] : 0u;
-                __syncwarp();
-                if ((uint32_t)lane < rest) gl[lane] = moved;
-                n_acc = rest;
-                __syncwarp();
-            }
-        }
-        if (n_acc) take(n_acc);
-        rmsq = __reduce_add_sync(0xffffffffu, rmsq);
-        if (lane == 0) { a.cells[c].y = (uint32_t)smp | min(kk, k) << 8; a.cells[c].z = (uint32_t)rmsq; }
-        __syncwarp();
-    }
+    if (!pb_block_codes<false>(b, (unsigned long long)rec.x, (int)rec.y, (long long)rec.z, (long long)rec.w, p0, smem_raw) && threadIdx.x == 0)
+        a.ctr->arena_overflow = 1;                                             // (more reads than the lists hold: the host gives up on this path for the region)
 }

@@ -15,16 +15,28 @@ pytestmark = pytest.mark.gpu
 AN_NAMES = ["NUCDIV", "SFS", "LD_ZNS", "HAPLO_K", "DIVERGE_POP"]
 
 
-def _ctx(fx, p, an, wb, we, classic):
-    old = os.environ.pop("POPBAM_B200_PILEUP", None)
-    if classic:
-        os.environ["POPBAM_B200_PILEUP"] = "classic"
+def _an(names=AN_NAMES):
+    an = 0
+    for a in names:
+        an |= pbtest.AN[a]
+    return an
+
+
+def _ctx(fx, p, an, wb, we, classic, codes=None):
+    """One region through a fresh context; the switches are read in pb_create.  codes: POPBAM_B200_CODES (who collects
+    the hard cells' base codes: the block's own k_pile_reads CTA, k_cell_codes, or every other block each)."""
+    want = {"POPBAM_B200_PILEUP": "classic" if classic else None, "POPBAM_B200_CODES": codes}
+    old = {k: os.environ.pop(k, None) for k in want}
+    for k, v in want.items():
+        if v is not None:
+            os.environ[k] = v
     try:
-        return run_gpu(fx, p, an, wb, we)          # the switch is read in pb_create
+        return run_gpu(fx, p, an, wb, we)
     finally:
-        os.environ.pop("POPBAM_B200_PILEUP", None)
-        if old is not None:
-            os.environ["POPBAM_B200_PILEUP"] = old
+        for k in want:
+            os.environ.pop(k, None)
+            if old[k] is not None:
+                os.environ[k] = old[k]
 
 
 @pytest.mark.parametrize("name,kw,pkw", [
@@ -56,7 +68,7 @@ def _ctx(fx, p, an, wb, we, classic):
     ("het", dict(contig_len=9000, n_ingroup=6, has_outgroup=1, depth=28.0, snp_density=0.05, het_frac=0.6, seed=48),
      dict(flags=pbtest.FLAG["HETEROZYGOTE"])),
 ])
-def test_bit_sliced_path_equals_classic_kernel_and_oracle(name, kw, pkw):
+def test_counting_path_equals_classic_kernel_and_oracle(name, kw, pkw):
     fx = pbtest.Fixture(**kw)
     pkw = dict(pkw)
     flags = pkw.pop("flags", 0)
@@ -77,16 +89,16 @@ def test_bit_sliced_path_equals_classic_kernel_and_oracle(name, kw, pkw):
 
 
 @pytest.mark.parametrize("name,pkw,windows", [
-    # no read passes min_mapQ: every list is empty, the planes hold no passing base
+    # no read passes min_mapQ: no read is counted, every cell is empty
     ("no_usable_reads", dict(min_mapQ=255), [(0, 3000), (3000, 6000)]),
-    # windows with gaps between them, starting at an odd offset: strips straddle window edges and gap positions
+    # windows with gaps between them, starting at an odd offset: position blocks straddle window edges and gap positions
     ("gaps_unaligned", {}, [(1237, 2001), (2500, 4999), (6001, 8000)]),
     # a region shorter than one strip
     ("tiny", {}, [(4111, 4130)]),
     # one-position windows
     ("single_positions", {}, [(100, 101), (5000, 5001), (8999, 9000)]),
 ])
-def test_bit_sliced_path_region_shapes(name, pkw, windows):
+def test_counting_path_region_shapes(name, pkw, windows):
     fx = pbtest.Fixture(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=22.0, snp_density=0.05, het_frac=0.3, seed=61)
     p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=fx.n_samples - 1, **pkw)
     wb = np.array([w[0] for w in windows], dtype=np.int32); we = np.array([w[1] for w in windows], dtype=np.int32)
@@ -103,9 +115,34 @@ def test_bit_sliced_path_region_shapes(name, pkw, windows):
     orc.close(); fast.close(); classic.close(); fx.close()
 
 
-def test_depth_cap_binds_after_the_planes_were_built():
-    """The plane pass runs before the host knows the depth bound; when the cap turns out to bind, the region falls back to
-    k_pileup_call (base codes built then, quality levels taken from the plane pass) and must still equal the oracle."""
+@pytest.mark.parametrize("name,kw", [
+    ("dense_edge", dict(contig_len=9000, n_ingroup=7, has_outgroup=1, depth=25.0, snp_density=0.3, het_frac=0.5, edge_mode=1, seed=42)),
+    ("n64_sparse", dict(contig_len=6000, n_ingroup=63, has_outgroup=1, depth=14.0, snp_density=0.05, het_frac=0.2, seed=47)),
+    # two samples, deep: long per-sample read lists in a block
+    ("deep_few", dict(contig_len=9000, n_ingroup=1, has_outgroup=1, depth=60.0, snp_density=0.1, het_frac=0.5, seed=52)),
+])
+def test_hard_cell_codes_collected_in_the_block_or_by_k_cell_codes(name, kw):
+    """The base codes of the cells left for k_hard_cells are collected by the block's own k_pile_reads CTA (reads fresh in
+    L2) or, when its lists lack the room, by k_cell_codes: all in the block, all by k_cell_codes, and every other block each
+    must give the same results, equal to the oracle's."""
+    fx = pbtest.Fixture(**kw)
+    p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=fx.n_samples - 1, min_depth=2)
+    wb, we = pbtest.window_grid(0, fx.contig_len, 3000)
+    an = _an()
+    orc = pbtest.OracleRun(p, fx.batch(), fx.ref(), an, wb, we)
+    want = pbtest.result_arrays(orc.res)
+    assert int(want["segsites"].sum()) > 0
+    for codes in (None, "separate", "mixed"):
+        ctx = _ctx(fx, p, an, wb, we, classic=False, codes=codes)
+        assert ctx.path() == 1, "counting path was not taken"
+        assert_same(pbtest.result_arrays(ctx.res), want, AN_NAMES)
+        ctx.close()
+    orc.close(); fx.close()
+
+
+def test_depth_cap_binds_and_the_region_takes_the_single_kernel_pileup():
+    """The counting path needs "the raw-depth cap can never bind" (k_depth_bound); when it can, the region goes through
+    k_pileup_call (sample partition, base codes and quality levels built then) and must still equal the oracle."""
     fx = pbtest.Fixture(contig_len=9000, n_ingroup=5, has_outgroup=1, depth=26.0, snp_density=0.04, het_frac=0.3, seed=71)
     p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=fx.n_samples - 1, max_depth=14)
     wb, we = pbtest.window_grid(0, fx.contig_len, 3000)
@@ -118,13 +155,6 @@ def test_depth_cap_binds_after_the_planes_were_built():
     assert int(want["segsites"].sum()) > 0
     assert_same(got, want, AN_NAMES)
     orc.close(); ctx.close(); fx.close()
-
-
-def _an(names=AN_NAMES):
-    an = 0
-    for a in names:
-        an |= pbtest.AN[a]
-    return an
 
 
 NOSYNC = ["NUCDIV", "SFS", "HAPLO_K", "DIVERGE_POP"]     # analyses whose buffers do not depend on the number of segregating sites
