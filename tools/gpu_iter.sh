@@ -3,7 +3,7 @@
 # usage (under gpurun): bash tools/gpu_iter.sh <outdir-name> [shapes...]
 out=gpurun_out/$1; shift
 mkdir -p $out
-timeout 600 python -m pytest tests/test_gpu_fastpath.py -x -q -m gpu 2>&1 | tail -15
+[ -n "$NO_TESTS" ] || timeout 600 python -m pytest tests/test_gpu_fastpath.py -x -q -m gpu 2>&1 | tail -15
 B="python bench.py --steps 1 --warmup 1 --contig-mb 2.3 --inflight 1 --no-cpu-baseline --cli-sample-kb 0"
 for cfg in "$@"; do
   [ "$cfg" = auto ] && { $B 2>/dev/null | python -c "import sys,json; j=json.loads(sys.stdin.read()); print('auto', j['ms_per_step'], j['stage_ms_per_shard'])"; continue; }
