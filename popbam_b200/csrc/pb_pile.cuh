@@ -500,7 +500,13 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
         const int cnt_l = min(32, n_blk - ch);
         const int64_t r = rlo + ch + lane;
         uint64_t b0 = 0, b1 = 0;
-        if (lane < cnt_l) { b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes; }
+        uint32_t meta_r = 0x7040000u, c0_r = 0, ncg_r = 0;                     // (no read: dropped by the flag filter)
+        int x_r = 0;
+        if (lane < cnt_l) {
+            // the whole header at once (the loads do not wait for one another; a dropped read's are wasted)
+            b0 = __ldg(a.base + r); b1 = r + 1 < a.n_reads ? __ldg(a.base + r + 1) : a.n_bytes;
+            meta_r = __ldg(a.meta + r); x_r = __ldg(a.pos + r); c0_r = __ldg(a.cigstart + r); ncg_r = __ldg(a.ncig + r);
+        }
         bool give_up = false;
         for (int start = 0; start < cnt_l;) {
             const uint64_t tq0 = __shfl_sync(0xffffffffu, b0, start) & ~(uint64_t)15;                // first byte of the quality tile
@@ -527,11 +533,11 @@ __global__ void __launch_bounds__(512) k_pile_reads(const PbPileReadsArgs a) {
             uint64_t so = 0;
             uint32_t smp = 0;
             if (lane >= start && lane < start + nt) {
-                const uint32_t meta = __ldg(a.meta + r);
+                const uint32_t meta = meta_r;
                 mq = (int)((meta >> 8) & 0xffu); smp = meta & 0xffu;
                 if (!((meta >> 16) & 0x704u) && smp < (uint32_t)n && mq >= a.min_mapQ) {
-                    int x = __ldg(a.pos + r);
-                    const uint32_t c0 = __ldg(a.cigstart + r), ncg = __ldg(a.ncig + r);
+                    int x = x_r;
+                    const uint32_t c0 = c0_r, ncg = ncg_r;
                     uint64_t qo = b0;
                     for (uint32_t ci = 0; ci < ncg; ++ci) {
                         const uint32_t cg = __ldg(a.cigar + c0 + ci);
