@@ -170,6 +170,7 @@ struct Run {
     std::mutex mu;
     std::condition_variable cv;
     bool pinned = false;
+    bool feed_only = false;     // `popbam _feed ...` (test hook, no GPU): the workers print what they were fed instead of results
     std::atomic<double> bases_per_bp{0.0}, reads_per_bp{0.0};      // densest piece decoded so far
     std::atomic<int> next_decode{0};
     std::vector<std::pair<int, int>> items;      // decode work: (shard, piece), shard-major
@@ -233,6 +234,35 @@ void gpu_worker(Run *R, int g, int G, int device) {
     pb_params prm = R->prm;
     prm.device = device;
     int st = 0;
+    if (R->feed_only) {
+        // what a shard's pieces hold, in a form that does not depend on where the pieces were cut or who decoded them
+        for (int s = g; s < (int)R->shards.size(); s += G) {
+            Shard &sh = R->shards[s];
+            {
+                std::unique_lock<std::mutex> lk(R->mu);
+                R->cv.wait(lk, [&] { return sh.state >= 1; });
+            }
+            uint64_t hp = 1469598103934665603ULL, hm = hp, hc = hp, sq = 0, ss = 0;
+            int64_t nr = 0, nc = 0;
+            auto fnv = [](uint64_t h, const void *v, size_t n) { const unsigned char *b = (const unsigned char *)v; for (size_t i = 0; i < n; ++i) h = (h ^ b[i]) * 1099511628211ULL; return h; };
+            for (pbio::Batch &b : sh.pieces) {
+                nr += b.n_reads(); nc += (int64_t)b.cigar.size();
+                hp = fnv(hp, b.pos.data(), 4 * b.pos.size()); hm = fnv(hm, b.meta.data(), 4 * b.meta.size()); hc = fnv(hc, b.cigar.data(), 4 * b.cigar.size());
+                for (size_t i = 0; i < b.qual.size(); ++i) sq += b.qual.data()[i];
+                for (size_t i = 0; i < b.seq4.size(); ++i) ss += b.seq4.data()[i];
+            }
+            char line[256];
+            snprintf(line, sizeof line, "%d\t%d\t%lld\t%lld\t%016llx\t%016llx\t%016llx\t%llu\t%llu\n", sh.w0, sh.w1, (long long)nr, (long long)nc,
+                     (unsigned long long)hp, (unsigned long long)hm, (unsigned long long)hc, (unsigned long long)sq, (unsigned long long)ss);
+            if (sh.error.empty()) sh.text = line;
+            for (pbio::Batch &b : sh.pieces) R->give_batch(std::move(b));
+            sh.pieces.clear();
+            std::lock_guard<std::mutex> lk(R->mu);
+            sh.state = 2;
+            R->cv.notify_all();
+        }
+        return;
+    }
     R->tables_ready.wait();
     pb_errmod_tables tb;
     tb.fk = R->fk.data(); tb.beta = R->beta.data(); tb.lhet = R->lhet.data();
@@ -364,6 +394,14 @@ int main(int argc, char **argv) {
         return 0;
     }
     Run R;
+    if (!strcmp(argv[1], "_feed")) {
+        // test hook (no GPU needed): popbam _feed <options and arguments of nucdiv> runs the whole host side -- shards, pieces,
+        // decode threads, batch pool, workers in shard order -- and prints one line per shard of what the workers were
+        // handed (windows, reads, CIGAR operations, hashes of pos / meta / cigar, byte sums of qual / seq4)
+        static char nucdiv[] = "nucdiv";
+        argv[1] = nucdiv;
+        R.feed_only = true;
+    }
     R.opt = parse(argc, argv);
     Options &o = R.opt;
     if (o.positional.size() < 2) { usage(o.cmd.c_str()); fatal("Need to specify BAM file name"); }
@@ -376,7 +414,7 @@ int main(int argc, char **argv) {
         // the error-model tables take ~0.25 s of host arithmetic: build them while the files are opened and CUDA comes up
         R.fk.resize(256); R.beta.resize((size_t)64 * 256 * 256); R.lhet.resize(65536);
         // (cached on disk after the first run on a machine: pb_errmod_tables_cached)
-        R.tables_ready = std::async(std::launch::async, [&R]() { pb_errmod_tables_cached(R.fk.data(), R.beta.data(), R.lhet.data(), nullptr); }).share();
+        if (!R.feed_only) R.tables_ready = std::async(std::launch::async, [&R]() { pb_errmod_tables_cached(R.fk.data(), R.beta.data(), R.lhet.data(), nullptr); }).share();
         R.bam.open(bamfile);
         R.hdr = pbio::read_header(R.bam);
         std::string text = R.hdr.text;
@@ -473,6 +511,7 @@ int main(int argc, char **argv) {
         // below PCIe).  So they are opt-in: POPBAM_B200_PINNED=1.
         const char *e = getenv("POPBAM_B200_PINNED");
         R.pinned = e && *e == '1';
+        if (R.feed_only) R.pinned = false;
         if (R.pinned) pbio::set_batch_allocator(pb_host_alloc, pb_host_free);
     }
     // two contexts (host threads) per GPU: one shard's host->device copy runs beside another shard's kernels

@@ -87,6 +87,43 @@ def test_fetch_in_pieces_equals_one_fetch(tmp_path, fxname, region, pieces):
     assert len(_load(one)["pos"]) > 0
 
 
+def _fnv(a):
+    h = 1469598103934665603
+    for b in np.ascontiguousarray(a).view(np.uint8).tolist():
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+@pytest.mark.parametrize("fxname,region,opts", [("edge", "chr1", ["-w", "1", "--shard-mb", "0.003"]), ("rg2", "chr1", ["-w", "2", "--shard-mb", "0.004"]),
+                                                 ("c1", "chr1", [])])
+def test_feeder_threads_hand_over_every_shard_whole_and_in_order(tmp_path, fxname, region, opts):
+    """`popbam _feed` runs the command line's host side (shards, pieces, decode threads, batch pool, workers) without a
+    GPU and prints what each shard's worker was handed.  It must not depend on the number of decode threads or workers,
+    and every shard must hold exactly the reads a single bam_fetch of its windows delivers (bam_index.c:943-957)."""
+    popbam_b200.build()
+    fx = pbtest.fixture(fxname)
+    bam, fa = fx.write_files(tmp_path / fxname)
+    outs = []
+    for extra in (["--threads", "1"], ["--threads", "7", "--gpus", "3"], ["--threads", "16", "--gpus", "2"]):
+        r = subprocess.run([str(EXE), "_feed", "-f", fa] + opts + extra + [bam, region], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout)
+    assert outs[0] == outs[1] == outs[2]
+    rows = [ln.split("\t") for ln in outs[0].splitlines()]
+    assert len(rows) >= 1 and [int(x[0]) for x in rows] == sorted(int(x[0]) for x in rows)
+    win = int(opts[1]) * 1000 if opts else None
+    wb, we = pbtest.window_grid(0, fx.contig_len, win) if win else (np.array([0]), np.array([fx.contig_len]))
+    for x in rows[:3] + rows[-2:]:
+        w0, w1 = int(x[0]), int(x[1])
+        out = tmp_path / "shard.bin"
+        rr = subprocess.run([str(EXE), "_fetch", bam, "chr1:%d-%d" % (int(wb[w0]) + 1, int(we[w1 - 1])), str(out)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+        assert rr.returncode == 0, rr.stderr
+        got = _load(out)
+        assert int(x[2]) == len(got["pos"]) and int(x[3]) == len(got["cigar"])
+        assert x[4] == _fnv(got["pos"]) and x[5] == _fnv(got["meta"]) and x[6] == _fnv(got["cigar"])
+        assert int(x[7]) == int(got["qual"].astype(np.uint64).sum()) and int(x[8]) == int(got["seq4"].astype(np.uint64).sum())
+
+
 def test_cli_errors_without_gpu(tmp_path):
     popbam_b200.build()
     r = subprocess.run([str(EXE), "nucdiv", "-f", "nope.fa", str(tmp_path / "missing.bam"), "chr1"], stderr=subprocess.PIPE, text=True)
