@@ -404,22 +404,20 @@ int run_pipeline(pb_ctx *c, int attempt = 0, bool allow_async = true) {
             for (int spc : kSpc) {
                 const int qcap = std::max(128, std::min(4096, ((int)(0.2 * (32.0 * spc + pc.span32) * pc.dens16 / 16.0) + 63) & ~63));
                 for (int warps = 16; warps >= 4; warps >>= 1) {
-                    const int lreads = 0;
-                    const size_t smem = pb_pile_reads_smem(n, spc, pc.tile_q, warps, qcap, lreads);
+                    const size_t smem = pb_pile_reads_smem(n, spc, pc.tile_q, warps, qcap);
                     if (smem > c->smem_optin) continue;
                     int per_sm = 0;
                     const cudaError_t e = c->qual_robust ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<true>, warps * 32, smem)
                                                          : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pile_reads<false>, warps * 32, smem);
                     if (e != cudaSuccess) { cudaGetLastError(); per_sm = 0; }
                     const double score = (double)per_sm * warps * (32.0 * spc) / (32.0 * spc + c->ctr_host.max_span);
-                    if (score > best) { best = score; pc.spc = spc; pc.warps = warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, spc, pc.tile_q, warps, lreads); }
+                    if (score > best) { best = score; pc.spc = spc; pc.warps = warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, spc, pc.tile_q, warps); }
                 }
             }
             if (c->pile_spc > 0 && c->pile_warps > 0) {                      // POPBAM_B200_PILE=spc,warps (measurements)
                 const int qcap = std::max(128, std::min(4096, ((int)(0.2 * (32.0 * c->pile_spc + pc.span32) * pc.dens16 / 16.0) + 63) & ~63));
-                const int lreads = 0;
-                const size_t smem = pb_pile_reads_smem(n, c->pile_spc, pc.tile_q, c->pile_warps, qcap, lreads);
-                if (smem <= c->smem_optin) { pc.spc = c->pile_spc; pc.warps = c->pile_warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, c->pile_spc, pc.tile_q, c->pile_warps, lreads); }
+                const size_t smem = pb_pile_reads_smem(n, c->pile_spc, pc.tile_q, c->pile_warps, qcap);
+                if (smem <= c->smem_optin) { pc.spc = c->pile_spc; pc.warps = c->pile_warps; pc.smem = smem; pc.qcap = qcap; pc.tail = (int)pb_pile_tail_bytes(n, c->pile_spc, pc.tile_q, c->pile_warps); }
             }
             pc.robust = c->qual_robust;
             c->pile_shape = pc;

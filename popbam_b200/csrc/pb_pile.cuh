@@ -60,25 +60,25 @@ struct PbPileReadsArgs {
 };
 
 // in the tiles' place once the reads are counted: per-position masks, the classification queue, the hard-cell list (and its
-// code offsets), per-sample read lists for the hard cells' base codes (room for `reads` entries), per-warp scratch
+// code offsets), some slack (the read lists of pb_block_codes take the counters' place, not this one)
 __host__ __device__ static inline int pb_pile_hcap(int n_samples, int spc) { return n_samples * 32 * spc; }      // (every cell may end up in the list)
-__host__ __device__ static inline size_t pb_pile_tail_smem(int n_samples, int spc, int warps, int reads = 0) {
+__host__ __device__ static inline size_t pb_pile_tail_smem(int n_samples, int spc, int warps) {
     return (size_t)20 * 32 * spc + ((((size_t)n_samples * 8 * spc) + 1) & ~(size_t)1) * 2 + (4 + (size_t)1 / 8) * (size_t)pb_pile_hcap(n_samples, spc) + (size_t)pb_pile_hcap(n_samples, spc) / 8 + 8 + (2 * (size_t)n_samples + 1) * 4 +
-           256 * (size_t)warps + 4 * (size_t)reads + 64;
+           256 * (size_t)warps + 64;
 }
 static inline int pb_pile_asw(int spc) { return 8 * spc + 1; }
 // dynamic shared memory: counters, reference nibbles (two copies), tables, barriers, per-warp tiles (16 bytes of
 // padding around each)
-static inline size_t pb_pile_reads_smem(int n_samples, int spc, int tile_q, int warps, int qcap, int list_reads) {
+static inline size_t pb_pile_reads_smem(int n_samples, int spc, int tile_q, int warps, int qcap) {
     const size_t cnt = (size_t)n_samples * (5 * (size_t)pb_pile_asw(spc) + 1) * 4;
     const size_t rc = 2 * ((size_t)(32 * spc) / 8 + 2) * 4 + 32;
     const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32);
-    const size_t scan = pb_pile_tail_smem(n_samples, spc, warps, list_reads);
+    const size_t scan = pb_pile_tail_smem(n_samples, spc, warps);
     return ((cnt + 15) & ~(size_t)15) + rc + ((sizeof(PbFastTables) + 15) & ~(size_t)15) + 16 * (size_t)warps + 16 * (size_t)qcap + (tiles > scan ? tiles : scan) + 64;
 }
 
-static inline size_t pb_pile_tail_bytes(int n_samples, int spc, int tile_q, int warps, int list_reads) {
-    const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32), scan = pb_pile_tail_smem(n_samples, spc, warps, list_reads);
+static inline size_t pb_pile_tail_bytes(int n_samples, int spc, int tile_q, int warps) {
+    const size_t tiles = (size_t)warps * ((size_t)tile_q + 32 + (size_t)tile_q / 2 + 16 + 32), scan = pb_pile_tail_smem(n_samples, spc, warps);
     return tiles > scan ? tiles : scan;
 }
 
