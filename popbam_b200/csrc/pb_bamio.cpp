@@ -272,7 +272,15 @@ FreeFn g_free = nullptr;
 }  // namespace
 void set_batch_allocator(AllocFn alloc, FreeFn release) { g_alloc = alloc; g_free = release; }
 void *batch_alloc(size_t bytes) {
-    void *p = g_alloc ? g_alloc(bytes) : malloc(bytes);
+    void *p = nullptr;
+    if (g_alloc) p = g_alloc(bytes);
+    else if (bytes >= (size_t)4 << 20) {
+        // a decoded piece is tens to hundreds of megabytes written once: with 4 KB pages a quarter of the decode time is
+        // page faults, so ask for huge pages (transparent_hugepage=madvise is the usual setting)
+        const size_t huge = (size_t)2 << 20;
+        if (posix_memalign(&p, huge, (bytes + huge - 1) & ~(huge - 1)) != 0) p = nullptr;
+        else madvise(p, (bytes + huge - 1) & ~(huge - 1), MADV_HUGEPAGE);
+    } else p = malloc(bytes);
     if (!p) fail("out of host memory for read batches");
     return p;
 }

@@ -7,6 +7,8 @@
 //   * one 11-bit primary table for literal/length codes (with sub-tables for the rare longer codes) and an
 //     8-bit primary table for distance codes; every entry carries the symbol, its base value and the
 //     number of extra bits, so a symbol is one lookup,
+//   * two literals per lookup where both codes fit the primary index (read data is literal-heavy: few quality values,
+//     short codes), so the serial chain shift -> index -> load -> shift is walked once for two bytes,
 //   * matches copied eight bytes at a time when they do not overlap closely.
 // Output is byte-identical to zlib's (tests/test_host_feeder.py compares every block of the fixtures
 // and randomised streams at all compression levels).
@@ -24,12 +26,12 @@ constexpr int kMaxCodeLen = 15;
 
 // Table entry (32 bits):
 //   bits  0..7   code length to consume (for a sub-table pointer: the primary bits)
-//   bits  8..12  number of extra bits (length / distance symbols)
+//   bits  8..12  number of extra bits (length / distance symbols); literals: bit 8 = TWO literals (second one in bits 24..31)
 //   bit   13     literal
 //   bit   14     end of block
 //   bit   15     sub-table pointer (value = offset of the sub-table, extra-bits field = its index width)
 //   bits 16..31  literal byte / base length / base distance / sub-table offset
-constexpr uint32_t kLiteral = 1u << 13, kEob = 1u << 14, kSub = 1u << 15;
+constexpr uint32_t kLiteral = 1u << 13, kEob = 1u << 14, kSub = 1u << 15, kDouble = 1u << 8;
 
 const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -107,12 +109,27 @@ struct Tables {
 };
 
 bool build_litlen(const uint8_t *lens, int n, Tables &t) {
-    return build_table(lens, n, kLitLenBits, t.litlen, (int)(sizeof t.litlen / 4), [](int sym) -> uint32_t {
+    if (!build_table(lens, n, kLitLenBits, t.litlen, (int)(sizeof t.litlen / 4), [](int sym) -> uint32_t {
         if (sym < 256) return kLiteral | ((uint32_t)sym << 16);
         if (sym == 256) return kEob;
         if (sym > 285) return kEob | kLiteral;        // invalid symbol: flagged, rejected when met
         return ((uint32_t)kLenBase[sym - 257] << 16) | ((uint32_t)kLenExtra[sym - 257] << 8);
-    });
+    })) return false;
+    // Two literals in one entry: where a literal's code leaves enough of the primary index for the whole code of another
+    // literal, that one is determined by the index bits alone (prefix code) and the entry takes both.
+    uint32_t one[1 << kLitLenBits];
+    memcpy(one, t.litlen, sizeof one);
+    for (uint32_t i = 0; i < (1u << kLitLenBits); ++i) {
+        const uint32_t e1 = one[i];
+        if ((e1 & (kLiteral | kEob | kSub)) != kLiteral) continue;
+        const uint32_t l1 = e1 & 0xff;
+        const uint32_t e2 = one[i >> l1];
+        if ((e2 & (kLiteral | kEob | kSub)) != kLiteral) continue;
+        const uint32_t l2 = e2 & 0xff;
+        if (l1 + l2 > (uint32_t)kLitLenBits) continue;
+        t.litlen[i] = kLiteral | kDouble | (l1 + l2) | (e1 & 0x00ff0000u) | ((e2 & 0x00ff0000u) << 8);
+    }
+    return true;
 }
 bool build_dist(const uint8_t *lens, int n, Tables &t) {
     return build_table(lens, n, kDistBits, t.dist, (int)(sizeof t.dist / 4), [](int sym) -> uint32_t {
@@ -238,14 +255,27 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
             br.drop((int)(e & 0xff));
             if (e & kLiteral) {
                 if (e & kEob) return false;           // invalid symbol 286/287
-                if (op >= oend) return false;
-                *op++ = (uint8_t)(e >> 16);
-                // up to two more literals from the bits already in the buffer
-                e = LL[br.peek(kLitLenBits)];
-                if ((e & (kLiteral | kEob | kSub)) == kLiteral && op < oend) {
-                    br.drop((int)(e & 0xff)); *op++ = (uint8_t)(e >> 16);
+                if ((size_t)(oend - op) >= 8) {
+                    // one or two literals per entry (the second byte of a single one is overwritten by what follows);
+                    // up to two more entries from the bits already in the buffer (3 x 11 + 15 <= 56)
+                    uint16_t v = (uint16_t)(e >> 16);
+                    memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
                     e = LL[br.peek(kLitLenBits)];
-                    if ((e & (kLiteral | kEob | kSub)) == kLiteral && op < oend) { br.drop((int)(e & 0xff)); *op++ = (uint8_t)(e >> 16); }
+                    if ((e & (kLiteral | kEob | kSub)) == kLiteral) {
+                        br.drop((int)(e & 0xff));
+                        v = (uint16_t)(e >> 16); memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
+                        e = LL[br.peek(kLitLenBits)];
+                        if ((e & (kLiteral | kEob | kSub)) == kLiteral) {
+                            br.drop((int)(e & 0xff));
+                            v = (uint16_t)(e >> 16); memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
+                        }
+                    }
+                } else {
+                    // the last bytes of the block, one at a time
+                    const uint32_t cnt = 1 + ((e >> 8) & 1u);
+                    if ((size_t)(oend - op) < cnt) return false;
+                    *op++ = (uint8_t)(e >> 16);
+                    if (cnt == 2) *op++ = (uint8_t)(e >> 24);
                 }
                 br.refill();
                 e = LL[br.peek(kLitLenBits)];
