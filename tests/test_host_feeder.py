@@ -164,7 +164,7 @@ def test_own_inflate_equals_zlib(tmp_path):
     popbam_b200.build()
     rng = np.random.default_rng(7)
     payloads = []
-    for n in (0, 1, 2, 7, 100, 4095, 20000, 60000):
+    for n in (0, 1, 2, 3, 7, 8, 9, 10, 11, 15, 16, 17, 100, 4095, 20000, 60000):     # (small ones: the decoder's careful last bytes)
         payloads.append(rng.integers(0, 256, n, dtype=np.uint8).tobytes())                  # incompressible
         payloads.append(rng.integers(0, 4, n, dtype=np.uint8).tobytes())                    # low entropy
         payloads.append((b"ACGTTGCA" * (n // 8 + 1))[:n])                                   # periodic: overlapping copies
@@ -193,11 +193,11 @@ def test_own_inflate_equals_zlib(tmp_path):
     assert r.returncode == 0, r.stderr
     assert out.read_bytes() == want
     # corrupt streams are rejected, not mis-decoded silently
-    bad = bytearray(_bgzf_block(payloads[3 * 5 + 1] + payloads[5 * 5], 6, zlib.Z_DEFAULT_STRATEGY))
+    bad = bytearray(_bgzf_block(payloads[4 * 5 + 1] + payloads[13 * 5], 6, zlib.Z_DEFAULT_STRATEGY))
     bad[40] ^= 0x55
     (tmp_path / "bad.bgzf").write_bytes(bytes(bad))
     r = subprocess.run([str(EXE), "_inflate", str(tmp_path / "bad.bgzf"), str(out)], stderr=subprocess.PIPE, text=True)
-    assert r.returncode != 0 or out.read_bytes() != payloads[3 * 5 + 1] + payloads[5 * 5]
+    assert r.returncode != 0 or out.read_bytes() != payloads[4 * 5 + 1] + payloads[13 * 5]
     # the generator's BAM (level 1) and a level-6 rewrite
     fx = pbtest.fixture("edge")
     for level in (1, 6):
