@@ -233,3 +233,27 @@ def test_asynchronous_region_whose_assumptions_fail_is_run_again():
     ctx.close()
     for fx in (a, b, c):
         fx.close()
+
+
+def test_more_than_8000_live_reads_are_refused():
+    """bam_plp_push drops a read once 8000 are live at its start position (bam_pileup.c:260,375); the library does not
+    reproduce that and must say so instead of diverging silently: k_depth_bound bounds the live reads from the sorted
+    start positions, the region ends with PB_ERR_UNSUPPORTED."""
+    import ctypes as C
+    fx = pbtest.Fixture(contig_len=2000, n_ingroup=1, has_outgroup=1, depth=4500.0, snp_density=0.01, seed=77)
+    p = fx.params(flags=pbtest.FLAG["OUTGROUP"], outidx=fx.n_samples - 1)
+    wb, we = pbtest.window_grid(0, fx.contig_len, 1000)
+    for sync in (True, False):
+        if sync:
+            os.environ["POPBAM_B200_SYNC"] = "1"
+        try:
+            ctx = popbam_b200.Context(p)
+        finally:
+            os.environ.pop("POPBAM_B200_SYNC", None)
+        ctx.set_contig(0, fx.ref())
+        ctx.region_begin(_an(NOSYNC), wb, we)
+        ctx.push_batch(fx.batch())
+        assert ctx.L.pb_region_end(ctx.h, C.byref(ctx.res)) == -6
+        assert b"8000" in ctx.L.pb_last_error(ctx.h)
+        ctx.close()
+    fx.close()
