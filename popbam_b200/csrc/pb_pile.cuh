@@ -15,7 +15,9 @@
 //                  shared-memory reduction per counter and four positions.  A read that starts in an earlier block and
 //                  reaches into this one is walked by this CTA as well (clipped to the block): no CTA waits for another.
 //                  Then one thread per position classifies the cells of all samples (easy / hard), writes the position's
-//                  coverage mask, and the hard cells get a directory entry and room for their base codes.
+//                  coverage mask, and the hard cells get a directory entry and room for their base codes, which the CTA
+//                  collects itself while its reads are in L2 (pb_block_codes; k_cell_codes is the same function as a
+//                  kernel of its own, for the blocks whose CTA lacked the shared memory for the read lists).
 //
 // Packed-byte arithmetic of one position word (four positions, one byte each):
 //   PRMT aligns the quality bytes to the position grid; "byte + (128 - T)" puts a threshold test into bit 7; a PRMT with
