@@ -32,6 +32,9 @@ constexpr int kMaxCodeLen = 15;
 //   bit   15     sub-table pointer (value = offset of the sub-table, extra-bits field = its index width)
 //   bits 16..31  literal byte / base length / base distance / sub-table offset
 constexpr uint32_t kLiteral = 1u << 13, kEob = 1u << 14, kSub = 1u << 15, kDouble = 1u << 8;
+// an index no code leads to: "end of block" and "literal" at once (and one bit long), which every path of the decoder rejects
+// where it tests for the end of the block anyway -- no test of its own per symbol
+constexpr uint32_t kInvalid = kEob | kLiteral | 1u;
 
 const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -54,7 +57,7 @@ bool build_table(const uint8_t *lens, int n_syms, int primary_bits, uint32_t *ta
     int used = 0;
     for (int l = 1; l <= kMaxCodeLen; ++l) used += count[l];
     const int primary_size = 1 << primary_bits;
-    for (int i = 0; i < primary_size; ++i) table[i] = 0;
+    for (int i = 0; i < primary_size; ++i) table[i] = kInvalid;
     if (used == 0) return true;                       // no codes: only legal for an unused distance tree
     // canonical first codes
     uint32_t next_code[kMaxCodeLen + 2];
@@ -91,7 +94,7 @@ bool build_table(const uint8_t *lens, int n_syms, int primary_bits, uint32_t *ta
                 if (sub_next + (1 << sub_bits) > table_cap) return false;
                 p = kSub | ((uint32_t)sub_bits << 8) | (uint32_t)primary_bits | ((uint32_t)sub_next << 16);
                 table[prefix] = p;
-                for (int i = 0; i < (1 << sub_bits); ++i) table[sub_next + i] = 0;
+                for (int i = 0; i < (1 << sub_bits); ++i) table[sub_next + i] = kInvalid;
                 sub_next += 1 << sub_bits;
             }
             const int sub_bits = (int)((p >> 8) & 31);
@@ -226,7 +229,7 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
                 br.refill();
                 const uint32_t e = cltab[br.peek(7)];
                 const int l = (int)(e & 0xff);
-                if (!l) return false;
+                if (e & kEob) return false;           // (no code leads here)
                 br.drop(l);
                 const int sym = (int)(e >> 16);
                 if (sym < 16) lens[i++] = (uint8_t)sym;
@@ -251,8 +254,7 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
         uint32_t e = LL[br.peek(kLitLenBits)];        // the entry of the next symbol is always looked up one step ahead,
         for (;;) {                                    // so its load overlaps the copy of the match before it
             if (e & kSub) { br.drop(kLitLenBits); e = LL[(e >> 16) + br.peek((int)((e >> 8) & 31))]; }
-            if (!(e & 0xff)) return false;
-            br.drop((int)(e & 0xff));
+            br.drop((int)(e & 0xff));                 // (an index without a code: kInvalid, rejected below as a literal that is also the end of the block)
             if (e & kLiteral) {
                 if (e & kEob) return false;           // invalid symbol 286/287
                 if ((size_t)(oend - op) >= 8) {
@@ -285,7 +287,7 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
             uint32_t len = (e >> 16) + br.take((int)((e >> 8) & 31));
             uint32_t d = DD[br.peek(kDistBits)];
             if (d & kSub) { br.drop(kDistBits); d = DD[(d >> 16) + br.peek((int)((d >> 8) & 31))]; }
-            if (!(d & 0xff) || (d & kEob)) return false;
+            if (d & kEob) return false;               // invalid distance symbol, or an index without a code
             br.drop((int)(d & 0xff));
             // no refill needed here: the buffer held >= 56 bits when this symbol started (refilled before the look-ahead)
             // and a length (15 + 5) plus a distance (15 + 13) take at most 48
@@ -294,8 +296,13 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
             br.refill();
             e = LL[br.peek(kLitLenBits)];
             const uint8_t *src = op - dist;
-            if (dist >= 8 && (size_t)(oend - op) >= len + 8) {
-                // most matches of read data are short: one unconditional 8-byte move, more only when needed
+            if (dist >= 16 && (size_t)(oend - op) >= len + 16) {
+                // sixteen bytes at a time (the moves may run up to 15 bytes past the match: overwritten by what follows)
+                struct W16 { uint64_t a, b; } w;
+                memcpy(&w, src, 16); memcpy(op, &w, 16);
+                for (uint32_t k = 16; k < len; k += 16) { memcpy(&w, src + k, 16); memcpy(op + k, &w, 16); }
+                op += len;
+            } else if (dist >= 8 && (size_t)(oend - op) >= len + 8) {
                 uint64_t w;
                 memcpy(&w, src, 8); memcpy(op, &w, 8);
                 for (uint32_t k = 8; k < len; k += 8) { memcpy(&w, src + k, 8); memcpy(op + k, &w, 8); }
