@@ -9,7 +9,8 @@
 //     number of extra bits, so a symbol is one lookup,
 //   * two literals per lookup where both codes fit the primary index (read data is literal-heavy: few quality values,
 //     short codes), so the serial chain shift -> index -> load -> shift is walked once for two bytes,
-//   * matches copied eight bytes at a time when they do not overlap closely.
+//   * a code's extra bits consumed together with the code (the entry holds the sum; the value is cut out of the bits as
+//     they were before the shift), matches copied sixteen bytes at a time when they do not overlap closely.
 // Output is byte-identical to zlib's (tests/test_host_feeder.py compares every block of the fixtures
 // and randomised streams at all compression levels).
 #include "pb_inflate.h"
@@ -25,7 +26,7 @@ constexpr int kDistBits = 8;
 constexpr int kMaxCodeLen = 15;
 
 // Table entry (32 bits):
-//   bits  0..7   code length to consume (for a sub-table pointer: the primary bits)
+//   bits  0..7   bits to consume: the code's length PLUS its extra bits (for a sub-table pointer: the primary bits)
 //   bits  8..12  number of extra bits (length / distance symbols); literals: bit 8 = TWO literals (second one in bits 24..31)
 //   bit   13     literal
 //   bit   14     end of block
@@ -79,8 +80,9 @@ bool build_table(const uint8_t *lens, int n_syms, int primary_bits, uint32_t *ta
         const uint32_t c = next_code[l]++;
         const uint32_t rev = reverse_bits(c, l);
         const uint32_t e = sym_entry(sym);
+        const uint32_t xb = (e & kLiteral) ? 0u : (e >> 8) & 31u;     // extra bits: consumed together with the code
         if (l <= primary_bits) {
-            for (uint32_t i = rev; i < (uint32_t)primary_size; i += 1u << l) table[i] = e | (uint32_t)l;
+            for (uint32_t i = rev; i < (uint32_t)primary_size; i += 1u << l) table[i] = e | ((uint32_t)l + xb);
         } else {
             const uint32_t prefix = rev & (uint32_t)(primary_size - 1);
             uint32_t p = table[prefix];
@@ -100,7 +102,7 @@ bool build_table(const uint8_t *lens, int n_syms, int primary_bits, uint32_t *ta
             const int sub_bits = (int)((p >> 8) & 31);
             const uint32_t off = p >> 16;
             const uint32_t hi = rev >> primary_bits;             // the code's bits beyond the primary index
-            for (uint32_t i = hi; i < (1u << sub_bits); i += 1u << (l - primary_bits)) table[off + i] = e | (uint32_t)(l - primary_bits);
+            for (uint32_t i = hi; i < (1u << sub_bits); i += 1u << (l - primary_bits)) table[off + i] = e | ((uint32_t)(l - primary_bits) + xb);
         }
     }
     return true;
@@ -152,9 +154,8 @@ struct BitReader {
             uint64_t w;
             memcpy(&w, p, 8);
             buf |= w << n;
-            const int take = (63 - n) >> 3;
-            p += take;
-            n += take << 3;
+            p += (63 - n) >> 3;                       // whole bytes that fit; n becomes 56 + (n & 7)
+            n |= 56;
         } else {
             while (n <= 56) {
                 if (p < end) buf |= (uint64_t)*p++ << n;
@@ -254,6 +255,7 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
         uint32_t e = LL[br.peek(kLitLenBits)];        // the entry of the next symbol is always looked up one step ahead,
         for (;;) {                                    // so its load overlaps the copy of the match before it
             if (e & kSub) { br.drop(kLitLenBits); e = LL[(e >> 16) + br.peek((int)((e >> 8) & 31))]; }
+            const uint64_t saved = br.buf;            // (the extra bits of a length are taken from here: one shift consumes both)
             br.drop((int)(e & 0xff));                 // (an index without a code: kInvalid, rejected below as a literal that is also the end of the block)
             if (e & kLiteral) {
                 if (e & kEob) return false;           // invalid symbol 286/287
@@ -284,14 +286,17 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
                 continue;
             }
             if (e & kEob) break;
-            uint32_t len = (e >> 16) + br.take((int)((e >> 8) & 31));
+            const uint32_t xl = (e >> 8) & 31u;
+            const uint32_t len = (e >> 16) + ((uint32_t)(saved >> ((e & 0xff) - xl)) & ((1u << xl) - 1u));
             uint32_t d = DD[br.peek(kDistBits)];
             if (d & kSub) { br.drop(kDistBits); d = DD[(d >> 16) + br.peek((int)((d >> 8) & 31))]; }
             if (d & kEob) return false;               // invalid distance symbol, or an index without a code
-            br.drop((int)(d & 0xff));
             // no refill needed here: the buffer held >= 56 bits when this symbol started (refilled before the look-ahead)
             // and a length (15 + 5) plus a distance (15 + 13) take at most 48
-            const uint32_t dist = (d >> 16) + br.take((int)((d >> 8) & 31));
+            const uint64_t saved_d = br.buf;
+            br.drop((int)(d & 0xff));
+            const uint32_t xd = (d >> 8) & 31u;
+            const uint32_t dist = (d >> 16) + ((uint32_t)(saved_d >> ((d & 0xff) - xd)) & ((1u << xd) - 1u));
             if (dist > (size_t)(op - out) || len > (size_t)(oend - op)) return false;
             br.refill();
             e = LL[br.peek(kLitLenBits)];
