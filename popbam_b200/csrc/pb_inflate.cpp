@@ -254,43 +254,48 @@ bool inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len)
         br.refill();                                  // >= 56 bits: enough for a length (15+5) and a distance (15+13) symbol
         uint32_t e = LL[br.peek(kLitLenBits)];        // the entry of the next symbol is always looked up one step ahead,
         for (;;) {                                    // so its load overlaps the copy of the match before it
-            if (e & kSub) { br.drop(kLitLenBits); e = LL[(e >> 16) + br.peek((int)((e >> 8) & 31))]; }
-            const uint64_t saved = br.buf;            // (the extra bits of a length are taken from here: one shift consumes both)
-            br.drop((int)(e & 0xff));                 // (an index without a code: kInvalid, rejected below as a literal that is also the end of the block)
-            if (e & kLiteral) {
-                if (e & kEob) return false;           // invalid symbol 286/287
-                if ((size_t)(oend - op) >= 8) {
-                    // one or two literals per entry (the second byte of a single one is overwritten by what follows);
-                    // up to two more entries from the bits already in the buffer (3 x 11 + 15 <= 56)
-                    uint16_t v = (uint16_t)(e >> 16);
-                    memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
-                    e = LL[br.peek(kLitLenBits)];
-                    if ((e & (kLiteral | kEob | kSub)) == kLiteral) {
-                        br.drop((int)(e & 0xff));
-                        v = (uint16_t)(e >> 16); memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
+            if (e & (kSub | kLiteral | kEob)) {       // (not a length: one test on the way to a match, the common symbol of read data)
+                if (e & kSub) { br.drop(kLitLenBits); e = LL[(e >> 16) + br.peek((int)((e >> 8) & 31))]; }
+                if (e & kLiteral) {
+                    br.drop((int)(e & 0xff));             // (an index without a code: kInvalid, rejected here as a literal that is also the end of the block)
+                    if (e & kEob) return false;           // invalid symbol 286/287
+                    if ((size_t)(oend - op) >= 8) {
+                        // one or two literals per entry (the second byte of a single one is overwritten by what follows);
+                        // up to two more entries from the bits already in the buffer (3 x 11 + 15 <= 56)
+                        uint16_t v = (uint16_t)(e >> 16);
+                        memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
                         e = LL[br.peek(kLitLenBits)];
                         if ((e & (kLiteral | kEob | kSub)) == kLiteral) {
                             br.drop((int)(e & 0xff));
                             v = (uint16_t)(e >> 16); memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
+                            e = LL[br.peek(kLitLenBits)];
+                            if ((e & (kLiteral | kEob | kSub)) == kLiteral) {
+                                br.drop((int)(e & 0xff));
+                                v = (uint16_t)(e >> 16); memcpy(op, &v, 2); op += 1 + ((e >> 8) & 1u);
+                            }
                         }
+                    } else {
+                        // the last bytes of the block, one at a time
+                        const uint32_t cnt = 1 + ((e >> 8) & 1u);
+                        if ((size_t)(oend - op) < cnt) return false;
+                        *op++ = (uint8_t)(e >> 16);
+                        if (cnt == 2) *op++ = (uint8_t)(e >> 24);
                     }
-                } else {
-                    // the last bytes of the block, one at a time
-                    const uint32_t cnt = 1 + ((e >> 8) & 1u);
-                    if ((size_t)(oend - op) < cnt) return false;
-                    *op++ = (uint8_t)(e >> 16);
-                    if (cnt == 2) *op++ = (uint8_t)(e >> 24);
+                    br.refill();
+                    e = LL[br.peek(kLitLenBits)];
+                    continue;
                 }
-                br.refill();
-                e = LL[br.peek(kLitLenBits)];
-                continue;
+                if (e & kEob) { br.drop((int)(e & 0xff)); break; }
             }
-            if (e & kEob) break;
+            const uint64_t saved = br.buf;            // (the extra bits of a length are taken from here: one shift consumes both)
+            br.drop((int)(e & 0xff));
             const uint32_t xl = (e >> 8) & 31u;
             const uint32_t len = (e >> 16) + ((uint32_t)(saved >> ((e & 0xff) - xl)) & ((1u << xl) - 1u));
             uint32_t d = DD[br.peek(kDistBits)];
-            if (d & kSub) { br.drop(kDistBits); d = DD[(d >> 16) + br.peek((int)((d >> 8) & 31))]; }
-            if (d & kEob) return false;               // invalid distance symbol, or an index without a code
+            if (d & (kSub | kEob)) {
+                if (d & kSub) { br.drop(kDistBits); d = DD[(d >> 16) + br.peek((int)((d >> 8) & 31))]; }
+                if (d & kEob) return false;           // invalid distance symbol, or an index without a code
+            }
             // no refill needed here: the buffer held >= 56 bits when this symbol started (refilled before the look-ahead)
             // and a length (15 + 5) plus a distance (15 + 13) take at most 48
             const uint64_t saved_d = br.buf;
